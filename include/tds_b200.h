@@ -1,0 +1,123 @@
+/* C-ABI of libtds_b200.so: the B200-native batched rigid-body env-step.
+ *
+ * Plain pointers and sizes only (no torch / C++ types).  Each entry point cites the reference
+ * interface it replaces (paths relative to erwincoumans/tiny-differentiable-simulator @ 8381b8c).
+ * INTEGRATION.md shows the reference-side bindings (dlopen of the v1 symbols, a
+ * CustomForwardDynamicsStepper subclass, a pybind shim).
+ *
+ * Device-side state is SoA fp32: array[dim][n_stride], environment index fastest
+ * (n_stride = n_envs rounded up to 32), so a warp of 32 environments reads 128 contiguous bytes
+ * per coordinate.
+ */
+#ifndef TDS_B200_H
+#define TDS_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tds_b200_sim tds_b200_sim;
+
+/* pipeline selector of tds_b200_step_* */
+#define TDS_B200_MODE_FD 0        /* tds::forward_dynamics only, src/dynamics/forward_dynamics.hpp:11 (qdd out) */
+#define TDS_B200_MODE_NOCONTACT 1 /* FD -> integrate_euler, examples/environments/cartpole_environment2.h:86-93 */
+#define TDS_B200_MODE_FULL 2      /* FD -> integrate_euler_qdd -> World::step -> integrate_euler,
+                                     examples/environments/locomotion_contact_simulation.h:261-269 */
+
+/* arithmetic selector */
+#define TDS_B200_PREC_MIXED 0 /* ABA fp32, kinematics + contact solve fp64 (default) */
+#define TDS_B200_PREC_F64 1
+#define TDS_B200_PREC_F32 2
+
+const char* tds_b200_last_error(void);
+
+/* ---- model compiler (setup time) -------------------------------------------------------------
+ * Replaces UrdfCache::construct -> UrdfParser::load_urdf + UrdfToMultiBody::convert_to_multi_body
+ * (src/urdf/urdf_cache.hpp:74-84, src/urdf/urdf_parser.hpp:707-925, src/urdf/urdf_to_multi_body.hpp:41).
+ * urdf / plane_urdf: file path or URDF text (text if the first non-blank char is '<'); plane_urdf may
+ * be NULL/"" for a world without ground plane.  Writes the flat model (include/tds_b200_model.h);
+ * returns its length in doubles (call with out=NULL to size), <0 on error. */
+int tds_b200_urdf_to_model(const char* urdf, const char* plane_urdf, int floating, double* out, int cap);
+
+/* ---- simulator lifecycle ----------------------------------------------------------------------
+ * One sim = n_envs independent copies of World{plane, MultiBody} (src/world.hpp:41, multi_body.hpp:13)
+ * resident on CUDA device `device`.  Returns NULL on error (see tds_b200_last_error). */
+tds_b200_sim* tds_b200_create(const double* model, int n_model_doubles, int n_envs, int device);
+void tds_b200_destroy(tds_b200_sim* sim);
+
+/* World / solver parameters: World::{default_friction,default_restitution} (src/world.hpp:68-69),
+ * gravity (world.hpp:50), MultiBodyConstraintSolver::{erp_,cfm_,pgs_iterations_,keep_all_points_}
+ * (src/mb_constraint_solver.hpp:59-70).  Defaults equal the reference's. */
+int tds_b200_set_params(tds_b200_sim* sim, double dt, const double gravity[3], double friction, double restitution,
+                        double erp, double cfm, int pgs_iterations, int keep_all_points);
+
+/* PD / environment parameters of LocomotionContactSimulation
+ * (examples/environments/locomotion_contact_simulation.h:28-48,168-258): action k drives the k-th
+ * non-fixed link at or after `start_link` (base_dof_) towards initial_poses[k] + clamp(action, +-limit).
+ * reward_kind: 0 none, 1 Laikago fixed-base emulation, 2 floating
+ * (examples/environments/laikago_environment2.h:130-171). */
+int tds_b200_set_env(tds_b200_sim* sim, int n_act, const double* initial_poses, int start_link, double kp,
+                     double kd, double max_force, double action_limit, int reward_kind);
+
+int tds_b200_set_precision(tds_b200_sim* sim, int precision);
+
+/* dims[0..7] = n_envs, n_stride, n_q (MultiBody::dof), n_qd (dof_qd), n_tau (dof_actuated), n_links,
+ *              n_contact_points, n_act */
+int tds_b200_get_dims(const tds_b200_sim* sim, int dims[8]);
+
+/* ---- device-resident fast path -------------------------------------------------------------------
+ * One launch = one step of all environments.  Pointers are DEVICE pointers to SoA fp32 arrays
+ * [dim][n_stride]; q_in/qd_in may alias q_out/qd_out.  `tau_or_action`: [n_tau][n_stride] joint torques
+ * (MultiBody::tau_, multi_body.hpp:86) when use_pd == 0, else [n_act][n_stride] policy actions.
+ * Optional outputs may be NULL: qdd_out [n_qd][ns] (MODE_FD), reward/done [n_stride],
+ * contact_dist [n_contact_points][ns] (ContactPoint::distance of every candidate point in the
+ * reference's enumeration order, src/world.hpp:212-281), link_xf [n_links*12][ns].
+ * stream: a cudaStream_t (NULL = default stream).  Asynchronous.  Returns a cudaError_t value. */
+int tds_b200_step_device(tds_b200_sim* sim, int mode, int use_pd, const float* q_in, const float* qd_in,
+                         const float* tau_or_action, float* q_out, float* qd_out, float* qdd_out, float* reward,
+                         float* done, float* contact_dist, float* link_xf, void* stream);
+
+/* ---- host-buffer path (what VectorizedEnvironment-style callers use) --------------------------------
+ * Replaces the per-call loop of SerialForwardStepper / OpenMPForwardStepper::step
+ * (examples/ars/ars_vectorized_environment.h:88-137) with MultiBody-style host arrays:
+ * q [n_envs][n_q], qd [n_envs][n_qd], tau_or_action [n_envs][n_tau | n_act], AoS fp64 host memory.
+ * Copies in, steps once, copies out (synchronous).  Outputs may be NULL. */
+int tds_b200_step_host(tds_b200_sim* sim, int mode, int use_pd, const double* q, const double* qd,
+                       const double* tau_or_action, double* q_out, double* qd_out, double* qdd_out,
+                       double* contact_dist);
+
+/* Environment-level step on the sim's own resident state: VectorizedEnvironment::step
+ * (examples/ars/ars_vectorized_environment.h:214-291) minus the policy: actions [n_envs][n_act] fp32
+ * host (pinned for speed) -> obs [n_envs][n_q+n_qd], rewards [n_envs], dones [n_envs] fp32 host.
+ * State stays on the device between calls.  Synchronous. */
+int tds_b200_env_set_state_host(tds_b200_sim* sim, const double* q, const double* qd);
+int tds_b200_env_get_state_host(tds_b200_sim* sim, double* q, double* qd);
+int tds_b200_env_step_host(tds_b200_sim* sim, const float* actions, float* obs, float* rewards, float* dones);
+/* Same, device-resident: actions/reward/done are device SoA arrays; advances the resident state. */
+int tds_b200_env_step_device(tds_b200_sim* sim, const float* actions, float* reward, float* done, void* stream);
+/* Device pointers of the resident state (SoA fp32 [n_q][ns], [n_qd][ns]). */
+float* tds_b200_env_q(tds_b200_sim* sim);
+float* tds_b200_env_qd(tds_b200_sim* sim);
+
+/* ---- C-ABI v1 drop-in ---------------------------------------------------------------------------------
+ * Exactly the symbols the reference's CudaSourceGen emits and ars_train_policy_cuda / cuda_codegen dlsym
+ * (src/utils/cuda_codegen.hpp:156-266; loaded at examples/ars/ars_train_policy_cuda.cpp:183-230):
+ *   input  = num_total_threads blocks of input_dim  (51 = q18|qd18|action12|kp,kd,max_force) fp64, AoS, host
+ *   output = num_total_threads blocks of output_dim (411 = q18|qd18|17x(pos3,quat4)|up.z|zeros) fp64, AoS, host
+ * Synchronous: H2D, one step, D2H.  num_blocks / num_threads_per_block are accepted and ignored (the
+ * launch geometry is chosen for sm_100a). */
+typedef struct {
+  int output_dim;
+  int input_dim;
+  int global_dim;
+} CudaFunctionMetaData; /* src/utils/cuda_codegen.hpp:27-31 */
+
+void cuda_model_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block,
+                                     double* output, const double* input);
+CudaFunctionMetaData cuda_model_laikago_forward_zero_meta(void);
+void cuda_model_laikago_forward_zero_allocate(int num_total_threads);
+void cuda_model_laikago_forward_zero_deallocate(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDS_B200_H */

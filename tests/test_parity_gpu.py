@@ -1,0 +1,159 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libtds_b200.so), against
+  (1) the committed golden vectors generated from the unmodified reference (tests/golden/*.npz),
+  (2) the plain-C fp64 oracle (oracle/tds_oracle.c) on fresh seeded inputs,
+  (3) the compiled reference itself (oracle/_ref) when the prebuilt library travelled with the repo.
+Tolerance (north_star): |gpu - ref| <= 1e-5 * max(1, |ref|) on q', qd' (and qdd for the
+forward-dynamics-only config), single step from identical fp32-representable inputs; candidate contact
+lists (count, order, penetration mask) must match exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import tds_b200
+import tds_b200.workloads as wl
+from tds_b200.model import fixture_path, load_model
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid"]
+
+
+def rel_err(a, ref):
+    return float(np.max(np.abs(a - ref) / np.maximum(1.0, np.abs(ref)))) if ref.size else 0.0
+
+
+def params_from_golden(g):
+    kw = {}
+    for k in g.files:
+        if k.startswith("param_"):
+            v = g[k]
+            kw[k[6:]] = tuple(v.tolist()) if v.ndim else (bool(v) if k == "param_keep_all_points" else float(v))
+    return kw
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("precision", [tds_b200.PREC_MIXED, tds_b200.PREC_F64])
+def test_golden_vectors(name, precision, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = load_model(fixture_path(name))
+    n = g["q_in"].shape[0]
+    sim = tds_b200.BatchSim(model, n, precision=precision, **params_from_golden(g))
+    mode = int(g["mode"])
+    tau = g["tau"] if "tau" in g.files else None
+    if tau is not None and tau.shape[1] != sim.n_tau:
+        tau = tau[:, -sim.n_tau:]
+    out = sim.step_host(mode, g["q_in"], g["qd_in"], tau, want_contacts=(mode == 2))
+    if mode == 0:
+        assert rel_err(out["qdd"], g["qdd"]) <= (TOL if precision == tds_b200.PREC_F64 else 5e-5)
+        return
+    assert rel_err(out["q"], g["q_out"]) <= TOL
+    assert rel_err(out["qd"], g["qd_out"]) <= TOL
+    if mode == 2 and sim.n_contact_points:
+        ref_d = np.stack(list(g["contact_dist"]))
+        assert out["contact_dist"].shape == ref_d.shape          # same number of candidate points
+        assert np.array_equal(out["contact_dist"] < 0, ref_d < 0)  # same penetrating set
+        assert np.max(np.abs(out["contact_dist"] - ref_d)) < 1e-6
+
+
+def test_laikago_env_step_vs_reference_env(golden_dir):
+    """Env-level: PD + step through the vectorized-env host API vs the reference's
+    LocomotionContactSimulation::step_forward_original (golden: env_output_templated)."""
+    g = np.load(os.path.join(golden_dir, "laikago.npz"))
+    n = g["q_in"].shape[0]
+    sim = tds_b200.laikago_sim(n)
+    sim.env_set_state(g["q_in"], g["qd_in"])
+    obs = np.zeros((n, 36), dtype=np.float32)
+    rew = np.zeros(n, dtype=np.float32)
+    done = np.zeros(n, dtype=np.float32)
+    sim.env_step_host(g["action"].astype(np.float32), obs, rew, done)
+    ref = g["env_output_templated"]
+    assert rel_err(obs.astype(np.float64), ref[:, :36]) <= TOL
+    assert np.array_equal(done, g["env_done"].astype(np.float32))
+    assert np.max(np.abs(rew - g["env_reward"])) <= 1e-5
+
+
+def test_v1_abi_dropin(golden_dir):
+    """cuda_model_laikago_forward_zero{,_meta,_allocate,_deallocate}: 51 doubles in, 411 out."""
+    g = np.load(os.path.join(golden_dir, "laikago.npz"))
+    m = tds_b200.CudaModelV1("cuda_model_laikago")
+    assert (m.input_dim, m.output_dim, m.global_dim) == (51, 411, 0)
+    x = g["env_input"]
+    m.allocate(x.shape[0])
+    sentinel = 123.0
+    out = np.full((x.shape[0], 411), sentinel)
+    m.forward_zero(x, out)
+    m.deallocate()
+    ref = g["env_output_templated"]
+    assert rel_err(out[:, :36], ref[:, :36]) <= TOL
+    # visual transforms: positions to fp32 accuracy, quaternions up to fp32 accuracy (same sign convention)
+    vis, rvis = out[:, 36:155].reshape(-1, 17, 7), ref[:, 36:155].reshape(-1, 17, 7)
+    assert np.max(np.abs(vis[..., :3] - rvis[..., :3])) < 5e-6
+    assert np.max(np.abs(vis[..., 3:] - rvis[..., 3:])) < 5e-6
+    assert np.array_equal(out[:, 155], ref[:, 155])
+    assert np.all(out[:, 156:] == sentinel)   # never written, like the reference's kernel
+
+
+@pytest.mark.parametrize("name,gen,n", [("laikago", wl.laikago_perturbed, 512), ("sphere2", wl.sphere2, 1024),
+                                        ("pendulum5", wl.pendulum5, 512), ("cartpole", wl.cartpole, 64)])
+def test_fresh_inputs_vs_c_oracle(name, gen, n):
+    model = load_model(fixture_path(name))
+    w = gen(n, seed=777)
+    sim = tds_b200.BatchSim(model, n, **w["params"])
+    P = port.make_params(**w["params"])
+    if name == "laikago":
+        sim.set_env(tds_b200.envs.LAIKAGO_INITIAL_POSES, start_link=6, kp=100.0, kd=2.0, max_force=50.0)
+        out = sim.step_host(2, w["q"], w["qd"], w["action"], use_pd=True)
+        x = np.zeros((n, 51))
+        x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = w["q"], w["qd"], w["action"], [100.0, 2.0, 50.0]
+        ref = port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
+        assert rel_err(out["q"], ref[:, :18]) <= TOL
+        assert rel_err(out["qd"], ref[:, 18:36]) <= TOL
+        return
+    mode = w["mode"]
+    out = sim.step_host(mode, w["q"], w["qd"], w["tau"])
+    refs = [port.step(model, P, mode, w["q"][i], w["qd"][i], None if w["tau"] is None else w["tau"][i]) for i in range(n)]
+    if mode == 0:
+        sim.set_precision(tds_b200.PREC_F64)
+        out = sim.step_host(mode, w["q"], w["qd"], w["tau"])
+        assert rel_err(out["qdd"], np.array([r["qdd"] for r in refs])) <= TOL
+    else:
+        assert rel_err(out["q"], np.array([r["q"] for r in refs])) <= TOL
+        assert rel_err(out["qd"], np.array([r["qd"] for r in refs])) <= TOL
+
+
+def test_full_size_properties():
+    """BASELINE sizes (4096 Laikago envs): properties that do not need the oracle at scale -
+    determinism, environment independence (permutation equivariance) and agreement of the
+    device-resident path with the host-buffer path."""
+    import torch
+    n = 4096
+    w = wl.laikago(n)
+    sim = tds_b200.laikago_sim(n)
+    a = sim.step_host(2, w["q"], w["qd"], w["action"], use_pd=True)
+    b = sim.step_host(2, w["q"], w["qd"], w["action"], use_pd=True)
+    assert np.array_equal(a["q"], b["q"]) and np.array_equal(a["qd"], b["qd"])   # bitwise deterministic
+    perm = np.random.default_rng(0).permutation(n)
+    c = sim.step_host(2, w["q"][perm], w["qd"][perm], w["action"][perm], use_pd=True)
+    assert np.array_equal(c["q"], a["q"][perm]) and np.array_equal(c["qd"], a["qd"][perm])
+    assert np.all(np.isfinite(a["q"])) and np.all(np.isfinite(a["qd"]))
+    # subset agrees with the oracle
+    model = sim.model
+    P = port.make_params(friction=1.0, keep_all_points=True)
+    idx = np.arange(0, n, 256)
+    x = np.zeros((idx.size, 51))
+    x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = w["q"][idx], w["qd"][idx], w["action"][idx], [100.0, 2.0, 50.0]
+    ref = port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
+    assert rel_err(a["q"][idx], ref[:, :18]) <= TOL and rel_err(a["qd"][idx], ref[:, 18:36]) <= TOL
+    # device-resident path: SoA torch tensors
+    q = sim.alloc(18); qd = sim.alloc(18); act = sim.alloc(12)
+    q[:, :n] = torch.tensor(w["q"].T, dtype=torch.float32)
+    qd[:, :n] = torch.tensor(w["qd"].T, dtype=torch.float32)
+    act[:, :n] = torch.tensor(w["action"].T, dtype=torch.float32)
+    sim.step_device(2, q, qd, act, use_pd=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(q[:, :n].T.cpu().numpy().astype(np.float64), a["q"])
+    assert np.array_equal(qd[:, :n].T.cpu().numpy().astype(np.float64), a["qd"])

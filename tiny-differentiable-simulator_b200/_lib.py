@@ -1,0 +1,86 @@
+"""ctypes loader of libtds_b200.so (in-tree build, see build.py).  Fails loudly when missing."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libtds_b200.so")
+
+
+class CudaFunctionMetaData(ctypes.Structure):
+    _fields_ = [("output_dim", ctypes.c_int), ("input_dim", ctypes.c_int), ("global_dim", ctypes.c_int)]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LibraryMissing(
+            f"{path} not found: build it with `python tiny-differentiable-simulator_b200/build.py` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    L = ctypes.CDLL(path)
+    dp = ctypes.POINTER(ctypes.c_double)
+    fp = ctypes.c_void_p  # device or host float pointers are passed as raw addresses
+    vp = ctypes.c_void_p
+    ci = ctypes.c_int
+    cd = ctypes.c_double
+    L.tds_b200_last_error.restype = ctypes.c_char_p
+    L.tds_b200_urdf_to_model.restype = ci
+    L.tds_b200_urdf_to_model.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, dp, ci]
+    L.tds_b200_create.restype = vp
+    L.tds_b200_create.argtypes = [dp, ci, ci, ci]
+    L.tds_b200_destroy.argtypes = [vp]
+    L.tds_b200_set_params.restype = ci
+    L.tds_b200_set_params.argtypes = [vp, cd, dp, cd, cd, cd, cd, ci, ci]
+    L.tds_b200_set_env.restype = ci
+    L.tds_b200_set_env.argtypes = [vp, ci, dp, ci, cd, cd, cd, cd, ci]
+    L.tds_b200_set_precision.restype = ci
+    L.tds_b200_set_precision.argtypes = [vp, ci]
+    L.tds_b200_get_dims.restype = ci
+    L.tds_b200_get_dims.argtypes = [vp, ctypes.POINTER(ci)]
+    L.tds_b200_step_device.restype = ci
+    L.tds_b200_step_device.argtypes = [vp, ci, ci] + [fp] * 10 + [vp]
+    L.tds_b200_step_host.restype = ci
+    L.tds_b200_step_host.argtypes = [vp, ci, ci, dp, dp, dp, dp, dp, dp, dp]
+    L.tds_b200_env_set_state_host.restype = ci
+    L.tds_b200_env_set_state_host.argtypes = [vp, dp, dp]
+    L.tds_b200_env_get_state_host.restype = ci
+    L.tds_b200_env_get_state_host.argtypes = [vp, dp, dp]
+    L.tds_b200_env_step_host.restype = ci
+    L.tds_b200_env_step_host.argtypes = [vp, fp, fp, fp, fp]
+    L.tds_b200_env_step_device.restype = ci
+    L.tds_b200_env_step_device.argtypes = [vp, fp, fp, fp, vp]
+    L.tds_b200_env_q.restype = vp
+    L.tds_b200_env_q.argtypes = [vp]
+    L.tds_b200_env_qd.restype = vp
+    L.tds_b200_env_qd.argtypes = [vp]
+    L.cuda_model_laikago_forward_zero.argtypes = [ci, ci, ci, dp, dp]
+    L.cuda_model_laikago_forward_zero_meta.restype = CudaFunctionMetaData
+    L.cuda_model_laikago_forward_zero_allocate.argtypes = [ci]
+    _LIB = L
+    return L
+
+
+def last_error():
+    return lib().tds_b200_last_error().decode()
+
+
+# every symbol include/tds_b200.h declares (checked by the CPU test-suite)
+DECLARED_SYMBOLS = [
+    "tds_b200_last_error", "tds_b200_urdf_to_model", "tds_b200_create", "tds_b200_destroy",
+    "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_precision", "tds_b200_get_dims",
+    "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
+    "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
+    "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",
+    "cuda_model_laikago_forward_zero_meta", "cuda_model_laikago_forward_zero_allocate",
+    "cuda_model_laikago_forward_zero_deallocate",
+]

@@ -1,0 +1,505 @@
+// C-ABI of libtds_b200.so (include/tds_b200.h): simulator lifecycle, device fast path, host-buffer
+// paths and the reference's "C-ABI v1" drop-in symbols for the Laikago model.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "tds_b200.h"
+#include "tds_b200_model.h"
+#include "tds_model.h"
+#include "tds_types.h"
+
+extern "C" int tds_launch_step(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
+                               int mode, int use_pd, int precision, char* gscratch, int use_smem,
+                               int warps_per_block, cudaStream_t stream);
+
+namespace {
+
+std::string g_err;  // mirror of the last error (the public accessor lives in urdf_model.cpp)
+extern "C" void tds_b200_set_error(const char* msg);
+void set_err(const std::string& s) { g_err = s; tds_b200_set_error(s.c_str()); }
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      set_err(std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+// ---- layout conversion kernels (host AoS fp64/fp32 <-> device SoA fp32) --------------------------
+template <typename TI>
+__global__ void aos_to_soa_kernel(const TI* __restrict__ in, int in_stride, int in_off, float* __restrict__ out,
+                                  int dim, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  for (int k = 0; k < dim; ++k) out[(size_t)k * ns + e] = (float)in[(size_t)e * in_stride + in_off + k];
+}
+template <typename TO>
+__global__ void soa_to_aos_kernel(const float* __restrict__ in, TO* __restrict__ out, int out_stride, int out_off,
+                                  int dim, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  for (int k = 0; k < dim; ++k) out[(size_t)e * out_stride + out_off + k] = (TO)in[(size_t)k * ns + e];
+}
+
+// TinyMatrix3x3::getRotation, src/math/tiny/tiny_matrix3x3.h:434-466 (used for the visual outputs)
+__device__ void matrix_to_quat_dev(const float* m, float* q) {
+  float trace = m[0] + m[4] + m[8];
+  float temp[4];
+  if (trace < 0.f) {
+    int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    float tmp = ((m[i * 3 + i] - m[j * 3 + j]) - m[k * 3 + k]) + 1.f;
+    float s = sqrtf(tmp);
+    temp[i] = s * 0.5f;
+    s = 0.5f / s;
+    temp[3] = (m[j * 3 + k] - m[k * 3 + j]) * s;
+    temp[j] = (m[i * 3 + j] + m[j * 3 + i]) * s;
+    temp[k] = (m[i * 3 + k] + m[k * 3 + i]) * s;
+  } else {
+    float s = sqrtf(trace + 1.f);
+    temp[3] = s * 0.5f;
+    s = 0.5f / s;
+    temp[0] = (m[5] - m[7]) * s;
+    temp[1] = (m[6] - m[2]) * s;
+    temp[2] = (m[1] - m[3]) * s;
+  }
+  q[0] = temp[0]; q[1] = temp[1]; q[2] = temp[2]; q[3] = -temp[3];
+}
+
+// Output packing of LocomotionContactSimulation::step_forward_original,
+// examples/environments/locomotion_contact_simulation.h:273-303: q | qd | visuals (pos3, quat4) | up.z
+__global__ void pack_v1_output_kernel(const __grid_constant__ DevVisuals V, const float* __restrict__ q,
+                                      const float* __restrict__ qd, const float* __restrict__ link_xf,
+                                      double* __restrict__ out, int out_dim, int n, int ns, int floating) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double* o = out + (size_t)e * out_dim;
+  int j = 0;
+  for (int k = 0; k < V.n_q; ++k) o[j++] = (double)q[(size_t)k * ns + e];
+  for (int k = 0; k < V.n_qd; ++k) o[j++] = (double)qd[(size_t)k * ns + e];
+  for (int v = 0; v < V.n_vis; ++v) {
+    const float* x = link_xf + (size_t)V.v_link[v] * 12 * ns + e;
+    float R[9], t[3], Rv[9], q4[4];
+    for (int k = 0; k < 9; ++k) R[k] = x[(size_t)k * ns];
+    for (int k = 0; k < 3; ++k) t[k] = x[(size_t)(9 + k) * ns];
+    for (int r = 0; r < 3; ++r) {
+      o[j++] = (double)(t[r] + R[r * 3] * V.v_t[v][0] + R[r * 3 + 1] * V.v_t[v][1] + R[r * 3 + 2] * V.v_t[v][2]);
+      for (int c = 0; c < 3; ++c)
+        Rv[r * 3 + c] = R[r * 3] * V.v_R[v][c] + R[r * 3 + 1] * V.v_R[v][3 + c] + R[r * 3 + 2] * V.v_R[v][6 + c];
+    }
+    matrix_to_quat_dev(Rv, q4);
+    o[j++] = q4[0]; o[j++] = q4[1]; o[j++] = q4[2]; o[j++] = q4[3];
+  }
+  double upz = 1.0;  // base_X_world.rotation(2,2): identity for fixed base (:131), else from the new base quat
+  if (floating) {
+    const double x = q[e], y = q[(size_t)ns + e], z = q[(size_t)2 * ns + e], w = q[(size_t)3 * ns + e];
+    upz = 1.0 - 2.0 * (x * x + y * y) / (x * x + y * y + z * z + w * w);
+  }
+  o[j++] = upz;
+}
+
+}  // namespace
+
+struct tds_b200_sim {
+  int device = 0;
+  int n = 0, ns = 0;
+  DevModel dm[3];         // one layout per precision mode
+  bool smem_ok[3] = {false, false, false};
+  int warps_per_block[3] = {1, 1, 1};
+  DevVisuals vis;
+  SimParams P;
+  EnvParams E;
+  int precision = TDS_B200_PREC_MIXED;
+  int n_tau = 0, n_points = 0;
+  // resident state + staging
+  float *q = nullptr, *qd = nullptr, *act = nullptr, *qdd = nullptr, *reward = nullptr, *done = nullptr;
+  float *cdist = nullptr, *link_xf = nullptr;
+  char* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* stage_dev = nullptr;   // device staging for AoS host buffers
+  size_t stage_dev_bytes = 0;
+  void* stage_host = nullptr;  // pinned host staging
+  size_t stage_host_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int max_smem_optin = 0;
+};
+
+static int ensure_stage(tds_b200_sim* s, size_t dev_bytes, size_t host_bytes) {
+  if (dev_bytes > s->stage_dev_bytes) {
+    if (s->stage_dev) cudaFree(s->stage_dev);
+    s->stage_dev = nullptr; s->stage_dev_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s->stage_dev, dev_bytes));
+    s->stage_dev_bytes = dev_bytes;
+  }
+  if (host_bytes > s->stage_host_bytes) {
+    if (s->stage_host) cudaFreeHost(s->stage_host);
+    s->stage_host = nullptr; s->stage_host_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&s->stage_host, host_bytes));
+    s->stage_host_bytes = host_bytes;
+  }
+  return 0;
+}
+
+static int ensure_scratch(tds_b200_sim* s, int prec) {
+  size_t need = (size_t)s->dm[prec].w_total * 4 * s->ns;
+  if (need > s->scratch_bytes) {
+    if (s->scratch) cudaFree(s->scratch);
+    s->scratch = nullptr; s->scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&s->scratch, need));
+    s->scratch_bytes = need;
+  }
+  return 0;
+}
+
+extern "C" {
+
+tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int device) {
+  if (!model || n_envs <= 0) { set_err("bad arguments"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device available: libtds_b200 has no CPU fallback");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+  tds_b200_sim* s = new tds_b200_sim;
+  s->device = device;
+  s->n = n_envs;
+  s->ns = (n_envs + 31) & ~31;
+  DevModel base;
+  int rc = tds_build_dev_model(model, n_model, &base);
+  if (rc) {
+    set_err("unsupported model (rc=" + std::to_string(rc) + "): magic/size mismatch, too many links/geoms, or spherical joints");
+    delete s;
+    return nullptr;
+  }
+  cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const int sizes[3][2] = {{4, 8}, {8, 8}, {4, 4}};
+  for (int p = 0; p < 3; ++p) {
+    s->dm[p] = base;
+    tds_build_layout(&s->dm[p], sizes[p][0], sizes[p][1], -1);
+    size_t per_warp = (size_t)s->dm[p].w_total * 32 * 4;
+    s->smem_ok[p] = per_warp <= (size_t)s->max_smem_optin;
+    // several warps per block only help when many blocks would otherwise be needed per SM
+    s->warps_per_block[p] = 1;
+  }
+  s->n_tau = base.n_qd - (base.floating ? 6 : 0);
+  s->n_points = base.max_contacts;
+  // visuals for the v1 output packing
+  memset(&s->vis, 0, sizeof(s->vis));
+  {
+    const double* vis = model + TDSM_HEADER + TDSM_BASE + (size_t)base.n_links * TDSM_LINK + (size_t)base.n_geoms * TDSM_GEOM;
+    int nv = base.n_vis < TDS_MAX_VIS ? base.n_vis : TDS_MAX_VIS;
+    s->vis.n_vis = nv; s->vis.n_links = base.n_links; s->vis.n_q = base.n_q; s->vis.n_qd = base.n_qd;
+    for (int v = 0; v < nv; ++v) {
+      const double* r = vis + (size_t)v * TDSM_VIS;
+      s->vis.v_link[v] = (int)r[TDSM_V_LINK];
+      for (int k = 0; k < 9; ++k) s->vis.v_R[v][k] = (float)r[TDSM_V_R + k];
+      for (int k = 0; k < 3; ++k) s->vis.v_t[v][k] = (float)r[TDSM_V_T + k];
+    }
+  }
+  // defaults = the reference's (world.hpp:65-72, mb_constraint_solver.hpp:59-70)
+  s->P.dt = 1e-3;
+  s->P.gravity[0] = 0; s->P.gravity[1] = 0; s->P.gravity[2] = -9.81;
+  s->P.friction = 0.5; s->P.restitution = 0.0; s->P.erp = 0.2; s->P.cfm = 1e-5;
+  s->P.pgs_iterations = 1; s->P.keep_all_points = 0;
+  memset(&s->E, 0, sizeof(s->E));
+  const size_t ns = s->ns;
+  auto alloc = [&](float** p, size_t rows) { return cudaMalloc((void**)p, sizeof(float) * rows * ns) == cudaSuccess && cudaMemset(*p, 0, sizeof(float) * rows * ns) == cudaSuccess; };
+  bool ok = alloc(&s->q, base.n_q > 0 ? base.n_q : 1) && alloc(&s->qd, base.n_qd > 0 ? base.n_qd : 1) &&
+            alloc(&s->act, (base.n_qd > TDS_MAX_ACT ? base.n_qd : TDS_MAX_ACT)) && alloc(&s->qdd, base.n_qd > 0 ? base.n_qd : 1) &&
+            alloc(&s->reward, 1) && alloc(&s->done, 1) && alloc(&s->cdist, s->n_points > 0 ? s->n_points : 1) &&
+            alloc(&s->link_xf, (size_t)(base.n_links > 0 ? base.n_links : 1) * 12);
+  if (!ok || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_err("device allocation failed");
+    tds_b200_destroy(s);
+    return nullptr;
+  }
+  return s;
+}
+
+void tds_b200_destroy(tds_b200_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->q); cudaFree(s->qd); cudaFree(s->act); cudaFree(s->qdd); cudaFree(s->reward); cudaFree(s->done);
+  cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev);
+  if (s->stage_host) cudaFreeHost(s->stage_host);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int tds_b200_set_params(tds_b200_sim* s, double dt, const double gravity[3], double friction, double restitution,
+                        double erp, double cfm, int pgs_iterations, int keep_all_points) {
+  if (!s) return -1;
+  s->P.dt = dt;
+  for (int k = 0; k < 3; ++k) s->P.gravity[k] = gravity[k];
+  s->P.friction = friction; s->P.restitution = restitution; s->P.erp = erp; s->P.cfm = cfm;
+  s->P.pgs_iterations = pgs_iterations; s->P.keep_all_points = keep_all_points;
+  return 0;
+}
+
+int tds_b200_set_env(tds_b200_sim* s, int n_act, const double* initial_poses, int start_link, double kp, double kd,
+                     double max_force, double action_limit, int reward_kind) {
+  if (!s || n_act < 0 || n_act > TDS_MAX_ACT) { set_err("bad n_act"); return -1; }
+  const DevModel& M = s->dm[0];
+  EnvParams E;
+  memset(&E, 0, sizeof(E));
+  E.n_act = n_act; E.start_link = start_link;
+  E.kp = (float)kp; E.kd = (float)kd; E.max_force = (float)max_force; E.action_limit = (float)action_limit;
+  E.reward_kind = reward_kind;
+  int k = 0;
+  const int first = M.floating ? 0 : start_link;  // locomotion_contact_simulation.h:181
+  for (int i = first; i < M.n_links && k < n_act; ++i) {
+    if (M.flags[i] & TDS_LF_FIXED) continue;
+    E.act_link[k] = i;
+    E.initial_poses[k] = (float)initial_poses[k];
+    ++k;
+  }
+  if (k != n_act) { set_err("model has fewer actuated links than n_act"); return -2; }
+  s->E = E;
+  return 0;
+}
+
+int tds_b200_set_precision(tds_b200_sim* s, int precision) {
+  if (!s || precision < 0 || precision > 2) return -1;
+  s->precision = precision;
+  return 0;
+}
+
+int tds_b200_get_dims(const tds_b200_sim* s, int dims[8]) {
+  if (!s) return -1;
+  const DevModel& M = s->dm[0];
+  dims[0] = s->n; dims[1] = s->ns; dims[2] = M.n_q; dims[3] = M.n_qd; dims[4] = s->n_tau; dims[5] = M.n_links;
+  dims[6] = s->n_points; dims[7] = s->E.n_act;
+  return 0;
+}
+
+int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_in, const float* qd_in,
+                         const float* tau_or_action, float* q_out, float* qd_out, float* qdd_out, float* reward,
+                         float* done, float* contact_dist, float* link_xf, void* stream) {
+  if (!s) return -1;
+  const int p = s->precision;
+  StepIO io;
+  io.q_in = q_in; io.qd_in = qd_in; io.tau_in = tau_or_action;
+  io.q_out = q_out; io.qd_out = qd_out; io.qdd_out = qdd_out;
+  io.reward = reward; io.done = done; io.contact_dist = contact_dist; io.link_xf = link_xf;
+  io.n = s->n; io.n_stride = s->ns;
+  if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
+  const int use_smem = s->smem_ok[p] ? 1 : 0;
+  if (!use_smem) { int rc = ensure_scratch(s, p); if (rc) return rc; }
+  int rc = tds_launch_step(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
+                           s->warps_per_block[p], (cudaStream_t)stream);
+  if (rc) set_err(std::string("step launch: ") + cudaGetErrorString((cudaError_t)rc));
+  return rc;
+}
+
+int tds_b200_step_host(tds_b200_sim* s, int mode, int use_pd, const double* q, const double* qd,
+                       const double* tau_or_action, double* q_out, double* qd_out, double* qdd_out,
+                       double* contact_dist) {
+  if (!s || !q || !qd) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const DevModel& M = s->dm[0];
+  const int n = s->n, ns = s->ns;
+  const int n_in = use_pd ? s->E.n_act : s->n_tau;
+  const size_t maxdim = (size_t)(M.n_q > M.n_qd ? M.n_q : M.n_qd) + s->n_points + 1;
+  int rc = ensure_stage(s, sizeof(double) * n * maxdim, 0);
+  if (rc) return rc;
+  double* st = (double*)s->stage_dev;
+  const int T = 128, B = (n + T - 1) / T;
+  cudaStream_t sm = s->stream;
+  auto up = [&](const double* src, int dim, float* dst) -> int {
+    if (dim == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(st, src, sizeof(double) * n * dim, cudaMemcpyHostToDevice, sm));
+    aos_to_soa_kernel<double><<<B, T, 0, sm>>>(st, dim, 0, dst, dim, n, ns);
+    return 0;
+  };
+  if ((rc = up(q, M.n_q, s->q))) return rc;
+  if ((rc = up(qd, M.n_qd, s->qd))) return rc;
+  if (tau_or_action) { if ((rc = up(tau_or_action, n_in, s->act))) return rc; }
+  else CUDA_TRY(cudaMemsetAsync(s->act, 0, sizeof(float) * ns * (n_in > 0 ? n_in : 1), sm));
+  rc = tds_b200_step_device(s, mode, use_pd, s->q, s->qd, s->act, s->q, s->qd, s->qdd, nullptr, nullptr,
+                            contact_dist ? s->cdist : nullptr, nullptr, sm);
+  if (rc) return rc;
+  auto down = [&](const float* src, int dim, double* dst) -> int {
+    if (dim == 0 || !dst) return 0;
+    soa_to_aos_kernel<double><<<B, T, 0, sm>>>(src, st, dim, 0, dim, n, ns);
+    CUDA_TRY(cudaMemcpyAsync(dst, st, sizeof(double) * n * dim, cudaMemcpyDeviceToHost, sm));
+    CUDA_TRY(cudaStreamSynchronize(sm));
+    return 0;
+  };
+  if ((rc = down(s->q, M.n_q, q_out))) return rc;
+  if ((rc = down(s->qd, M.n_qd, qd_out))) return rc;
+  if (mode == TDS_B200_MODE_FD && (rc = down(s->qdd, M.n_qd, qdd_out))) return rc;
+  if ((rc = down(s->cdist, s->n_points, contact_dist))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(sm));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_env_set_state_host(tds_b200_sim* s, const double* q, const double* qd) {
+  if (!s) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const DevModel& M = s->dm[0];
+  const int n = s->n, ns = s->ns;
+  int rc = ensure_stage(s, sizeof(double) * n * (size_t)(M.n_q + M.n_qd), 0);
+  if (rc) return rc;
+  double* st = (double*)s->stage_dev;
+  const int T = 128, B = (n + T - 1) / T;
+  CUDA_TRY(cudaMemcpyAsync(st, q, sizeof(double) * n * M.n_q, cudaMemcpyHostToDevice, s->stream));
+  aos_to_soa_kernel<double><<<B, T, 0, s->stream>>>(st, M.n_q, 0, s->q, M.n_q, n, ns);
+  double* st2 = st + (size_t)n * M.n_q;
+  CUDA_TRY(cudaMemcpyAsync(st2, qd, sizeof(double) * n * M.n_qd, cudaMemcpyHostToDevice, s->stream));
+  aos_to_soa_kernel<double><<<B, T, 0, s->stream>>>(st2, M.n_qd, 0, s->qd, M.n_qd, n, ns);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int tds_b200_env_get_state_host(tds_b200_sim* s, double* q, double* qd) {
+  if (!s) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const DevModel& M = s->dm[0];
+  const int n = s->n, ns = s->ns;
+  int rc = ensure_stage(s, sizeof(double) * n * (size_t)(M.n_q + M.n_qd), 0);
+  if (rc) return rc;
+  double* st = (double*)s->stage_dev;
+  const int T = 128, B = (n + T - 1) / T;
+  soa_to_aos_kernel<double><<<B, T, 0, s->stream>>>(s->q, st, M.n_q, 0, M.n_q, n, ns);
+  soa_to_aos_kernel<double><<<B, T, 0, s->stream>>>(s->qd, st + (size_t)n * M.n_q, M.n_qd, 0, M.n_qd, n, ns);
+  if (q) CUDA_TRY(cudaMemcpyAsync(q, st, sizeof(double) * n * M.n_q, cudaMemcpyDeviceToHost, s->stream));
+  if (qd) CUDA_TRY(cudaMemcpyAsync(qd, st + (size_t)n * M.n_q, sizeof(double) * n * M.n_qd, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int tds_b200_env_step_device(tds_b200_sim* s, const float* actions, float* reward, float* done, void* stream) {
+  if (!s) return -1;
+  return tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, actions, s->q, s->qd, nullptr, reward, done,
+                              nullptr, nullptr, stream);
+}
+
+float* tds_b200_env_q(tds_b200_sim* s) { return s ? s->q : nullptr; }
+float* tds_b200_env_qd(tds_b200_sim* s) { return s ? s->qd : nullptr; }
+
+int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, float* rewards, float* dones) {
+  if (!s || !actions) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const DevModel& M = s->dm[0];
+  const int n = s->n, ns = s->ns, na = s->E.n_act, nobs = M.n_q + M.n_qd;
+  // device staging: actions AoS in | obs AoS out | reward | done
+  const size_t in_b = sizeof(float) * (size_t)n * na, obs_b = sizeof(float) * (size_t)n * nobs;
+  int rc = ensure_stage(s, in_b + obs_b, 0);
+  if (rc) return rc;
+  float* d_in = (float*)s->stage_dev;
+  float* d_obs = (float*)((char*)s->stage_dev + in_b);
+  cudaStream_t sm = s->stream;
+  const int T = 128, B = (n + T - 1) / T;
+  CUDA_TRY(cudaMemcpyAsync(d_in, actions, in_b, cudaMemcpyHostToDevice, sm));
+  aos_to_soa_kernel<float><<<B, T, 0, sm>>>(d_in, na, 0, s->act, na, n, ns);
+  rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, s->reward, s->done,
+                            nullptr, nullptr, sm);
+  if (rc) return rc;
+  if (obs) {
+    soa_to_aos_kernel<float><<<B, T, 0, sm>>>(s->q, d_obs, nobs, 0, M.n_q, n, ns);
+    soa_to_aos_kernel<float><<<B, T, 0, sm>>>(s->qd, d_obs, nobs, M.n_q, M.n_qd, n, ns);
+    CUDA_TRY(cudaMemcpyAsync(obs, d_obs, obs_b, cudaMemcpyDeviceToHost, sm));
+  }
+  if (rewards) CUDA_TRY(cudaMemcpyAsync(rewards, s->reward, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
+  if (dones) CUDA_TRY(cudaMemcpyAsync(dones, s->done, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
+  CUDA_TRY(cudaStreamSynchronize(sm));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- C-ABI v1 drop-in for "cuda_model_laikago" (src/utils/cuda_codegen.hpp:156-266) -------------------
+static const double k_laikago_model[] = {
+#include "generated/laikago_model.inc"
+};
+static const int k_laikago_in = 51, k_laikago_out = 411, k_laikago_written = 156;
+static tds_b200_sim* g_v1 = nullptr;
+static double* g_v1_dev_in = nullptr;
+static double* g_v1_dev_out = nullptr;
+static int g_v1_n = 0;
+static std::mutex g_v1_mu;
+
+static void v1_fail(const char* what) {
+  // the reference prints and exits on allocation failure (cuda_codegen.hpp:201-208)
+  fprintf(stderr, "cuda_model_laikago (tds_b200): %s: %s\n", what, g_err.c_str());
+  exit(1);
+}
+
+CudaFunctionMetaData cuda_model_laikago_forward_zero_meta(void) {
+  CudaFunctionMetaData d;
+  d.output_dim = k_laikago_out;
+  d.input_dim = k_laikago_in;
+  d.global_dim = 0;
+  return d;
+}
+
+void cuda_model_laikago_forward_zero_allocate(int num_total_threads) {
+  std::lock_guard<std::mutex> lk(g_v1_mu);
+  if (g_v1) { tds_b200_destroy(g_v1); g_v1 = nullptr; cudaFree(g_v1_dev_in); cudaFree(g_v1_dev_out); }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  g_v1 = tds_b200_create(k_laikago_model, (int)(sizeof(k_laikago_model) / sizeof(double)), num_total_threads, dev);
+  if (!g_v1) v1_fail("allocate");
+  // LaikagoContactSimulation parameters: laikago_environment2.h:36-61, locomotion_contact_simulation.h:131-135
+  const double g[3] = {0, 0, -9.81};
+  tds_b200_set_params(g_v1, 1e-3, g, 1.0, 0.0, 0.2, 1e-5, 1, 1);
+  const double init[12] = {0.2, 0, -0.7, 0.2, 0, -0.7, 0.2, 0, -0.7, 0.2, 0, -0.7};
+  tds_b200_set_env(g_v1, 12, init, 6, 100.0, 2.0, 50.0, 0.4, 1);
+  g_v1_n = num_total_threads;
+  if (cudaMalloc((void**)&g_v1_dev_in, sizeof(double) * (size_t)num_total_threads * k_laikago_in) != cudaSuccess ||
+      cudaMalloc((void**)&g_v1_dev_out, sizeof(double) * (size_t)num_total_threads * k_laikago_written) != cudaSuccess) {
+    set_err("cudaMalloc failed");
+    v1_fail("allocate");
+  }
+}
+
+void cuda_model_laikago_forward_zero_deallocate(void) {
+  std::lock_guard<std::mutex> lk(g_v1_mu);
+  if (g_v1) tds_b200_destroy(g_v1);
+  g_v1 = nullptr;
+  cudaFree(g_v1_dev_in); cudaFree(g_v1_dev_out);
+  g_v1_dev_in = g_v1_dev_out = nullptr;
+  g_v1_n = 0;
+}
+
+void cuda_model_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output,
+                                     const double* input) {
+  (void)num_blocks; (void)num_threads_per_block;
+  std::lock_guard<std::mutex> lk(g_v1_mu);
+  if (!g_v1 || num_total_threads > g_v1_n) { set_err("forward_zero called before allocate (or with more threads)"); v1_fail("forward_zero"); }
+  tds_b200_sim* s = g_v1;
+  const int n = num_total_threads, ns = s->ns;
+  cudaStream_t sm = s->stream;
+  const int T = 128, B = (n + T - 1) / T;
+  const int saved_n = s->n;
+  s->n = n;
+  cudaMemcpyAsync(g_v1_dev_in, input, sizeof(double) * (size_t)n * k_laikago_in, cudaMemcpyHostToDevice, sm);
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(g_v1_dev_in, k_laikago_in, 0, s->q, 18, n, ns);
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(g_v1_dev_in, k_laikago_in, 18, s->qd, 18, n, ns);
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(g_v1_dev_in, k_laikago_in, 36, s->act, 12, n, ns);
+  // kp, kd, max_force travel in the input vector (locomotion_contact_simulation.h:164-166); the v1 ABI is
+  // called with one value for the whole batch (ars_vectorized_environment.h:223-236): read env 0's.
+  s->E.kp = (float)input[48]; s->E.kd = (float)input[49]; s->E.max_force = (float)input[50];
+  int rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, nullptr, nullptr,
+                                nullptr, s->link_xf, sm);
+  if (rc) v1_fail("step");
+  pack_v1_output_kernel<<<B, T, 0, sm>>>(s->vis, s->q, s->qd, s->link_xf, g_v1_dev_out, k_laikago_written, n, ns,
+                                         s->dm[0].floating);
+  // entries >= 156 are never written by the reference either (they keep the caller's values)
+  cudaMemcpy2DAsync(output, sizeof(double) * k_laikago_out, g_v1_dev_out, sizeof(double) * k_laikago_written,
+                    sizeof(double) * k_laikago_written, n, cudaMemcpyDeviceToHost, sm);
+  cudaError_t e = cudaStreamSynchronize(sm);
+  s->n = saved_n;
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); v1_fail("forward_zero"); }
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Host-side "model compiler" back end: flat model (include/tds_b200_model.h) -> DevModel
+// (constant-bank kernel parameter) + per-environment scratch layout.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "tds_b200_model.h"
+#include "tds_types.h"
+
+#ifndef __CUDACC__
+#define TDS_HOST_INLINE static inline
+#else
+#define TDS_HOST_INLINE static inline __host__
+#endif
+
+// MultiBodyConstraintSolver::plane_space, src/mb_constraint_solver.hpp:506-520 (evaluated once on the
+// host: the contact normal of every plane contact is the constant -plane_normal).
+TDS_HOST_INLINE void tds_plane_space(const double* n, double* p, double* q) {
+  double n_sqr = n[2] * n[2];
+  int mz = n_sqr > 0.5;
+  double a = n[1] * n[1] + (mz ? n_sqr : n[0] * n[0]);
+  double k = sqrt(a);
+  p[0] = mz ? 0.0 : -n[1] * k;
+  p[1] = mz ? -n[2] * k : n[0] * k;
+  p[2] = mz ? n[1] * k : n[1] * k;
+  q[0] = mz ? a * k : -n[2] * p[1];
+  q[1] = mz ? -n[0] * p[2] : n[2] * p[0];
+  q[2] = mz ? n[0] * p[1] : a * k;
+}
+
+// rigid-body inertia (mass, com, inertia about com) -> (m, h = m com, I about the link origin),
+// i.e. the blocks of ArticulatedBodyInertia(rbi), src/math/inertia.hpp:114-119.
+TDS_HOST_INLINE void tds_rbi_pack(const double* rec /* mass, com[3], inertia[9] */, float* out) {
+  double m = rec[0];
+  const double* c = rec + 1;
+  const double* I = rec + 4;
+  // H = cross(com); I_o = inertia + H H^T m ; H H^T = (c.c) 1 - c c^T
+  double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+  out[0] = (float)m;
+  out[1] = (float)(m * c[0]); out[2] = (float)(m * c[1]); out[3] = (float)(m * c[2]);
+  out[4] = (float)(I[0] + m * (cc - c[0] * c[0]));
+  out[5] = (float)(0.5 * (I[1] + I[3]) - m * c[0] * c[1]);
+  out[6] = (float)(0.5 * (I[2] + I[6]) - m * c[0] * c[2]);
+  out[7] = (float)(I[4] + m * (cc - c[1] * c[1]));
+  out[8] = (float)(0.5 * (I[5] + I[7]) - m * c[1] * c[2]);
+  out[9] = (float)(I[8] + m * (cc - c[2] * c[2]));
+}
+
+// Returns 0 on success, <0 on unsupported / oversized models.
+TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel* D) {
+  if (n_doubles < TDSM_HEADER || (int)m[TDSM_H_MAGIC] != TDSM_MAGIC) return -1;
+  memset(D, 0, sizeof(*D));
+  D->n_links = (int)m[TDSM_H_NLINKS];
+  D->floating = (int)m[TDSM_H_FLOATING];
+  D->n_q = (int)m[TDSM_H_NQ];
+  D->n_qd = (int)m[TDSM_H_NQD];
+  D->n_geoms = (int)m[TDSM_H_NGEOMS];
+  D->n_vis = (int)m[TDSM_H_NVIS];
+  D->has_plane = (int)m[TDSM_H_HASPLANE];
+  if (D->n_links > TDS_MAX_LINKS || D->n_geoms > TDS_MAX_GEOMS) return -2;
+  const double* base = m + TDSM_HEADER;
+  const double* links = base + TDSM_BASE;
+  const double* geoms = links + (size_t)D->n_links * TDSM_LINK;
+  if (n_doubles < TDSM_HEADER + TDSM_BASE + D->n_links * TDSM_LINK + D->n_geoms * TDSM_GEOM) return -1;
+  tds_rbi_pack(base, D->base_rbi);
+  for (int k = 0; k < 9; ++k) D->base_inertia_com[k] = (float)base[4 + k];
+  int n_acc = 0;
+  for (int i = 0; i < D->n_links; ++i) D->acc_slot[i] = -1;
+  D->base_acc = -1;
+  for (int i = 0; i < D->n_links; ++i) {
+    const double* l = links + (size_t)i * TDSM_LINK;
+    int jt = (int)l[TDSM_L_JTYPE];
+    if (jt == TDSJ_SPHERICAL || jt < TDSJ_FIXED || jt > TDSJ_SPHERICAL) return -3;  // spherical joints: not supported
+    D->parent[i] = (int)l[TDSM_L_PARENT];
+    if (D->parent[i] >= i) return -4;
+    D->jtype[i] = jt;
+    D->q_idx[i] = (int)l[TDSM_L_QIDX];
+    D->qd_idx[i] = (int)l[TDSM_L_QDIDX];
+    int fl = 0;
+    if (jt == TDSJ_FIXED) fl |= TDS_LF_FIXED;
+    else if (jt <= TDSJ_PRISMATIC_AXIS) fl |= TDS_LF_PRISMATIC;
+    else fl |= TDS_LF_REVOLUTE;
+    if (D->parent[i] == i - 1) fl |= TDS_LF_PARENT_ADJ;
+    D->flags[i] = fl;
+    for (int k = 0; k < 3; ++k) D->axis[i][k] = l[TDSM_L_AXIS + k];
+    for (int k = 0; k < 9; ++k) D->XT[i][k] = l[TDSM_L_XT_R + k];
+    for (int k = 0; k < 3; ++k) D->XT[i][9 + k] = l[TDSM_L_XT_T + k];
+    tds_rbi_pack(l + TDSM_L_MASS, D->rbi[i]);
+    D->stiffness[i] = (float)l[TDSM_L_STIFFNESS];
+    D->damping[i] = (float)l[TDSM_L_DAMPING];
+  }
+  for (int i = 0; i < D->n_links; ++i) {
+    int p = D->parent[i];
+    if (D->flags[i] & TDS_LF_PARENT_ADJ) {
+      if (p >= 0) D->flags[p] |= TDS_LF_CHILD_ADJ;
+    } else if (p >= 0) {
+      if (D->acc_slot[p] < 0) D->acc_slot[p] = n_acc++;
+    } else if (D->floating) {
+      if (D->base_acc < 0) D->base_acc = n_acc++;
+    }
+  }
+  D->n_acc = n_acc;
+  int n_points = 0;
+  for (int g = 0; g < D->n_geoms; ++g) {
+    const double* gg = geoms + (size_t)g * TDSM_GEOM;
+    D->g_link[g] = (int)gg[TDSM_G_LINK];
+    D->g_type[g] = (int)gg[TDSM_G_TYPE];
+    D->g_radius[g] = gg[TDSM_G_P];
+    for (int k = 0; k < 3; ++k) D->g_t[g][k] = gg[TDSM_G_T + k];
+    double hl = 0.5 * gg[TDSM_G_P + 1];
+    for (int k = 0; k < 3; ++k) D->g_half[g][k] = gg[TDSM_G_R + k * 3 + 2] * hl;  // R_local * (0,0,L/2)
+    if (D->g_type[g] == TDSG_SPHERE) n_points += 1;
+    if (D->g_type[g] == TDSG_CAPSULE) n_points += 2;
+  }
+  D->max_contacts = D->has_plane ? n_points : 0;
+  for (int k = 0; k < 3; ++k) D->plane_n[k] = m[TDSM_H_PLANE_N + k];
+  D->plane_c = m[TDSM_H_PLANE_C];
+  double nb[3] = {-D->plane_n[0], -D->plane_n[1], -D->plane_n[2]};
+  tds_plane_space(nb, D->fr1, D->fr2);
+  return 0;
+}
+
+// Number of candidate contact points (static per model: every sphere / capsule end emits one,
+// src/contact_point.hpp:112-124,149-158).
+TDS_HOST_INLINE int tds_num_contact_points(const DevModel* D) { return D->max_contacts; }
+
+// Per-environment scratch layout in 4-byte words.  size_ra / size_rc = sizeof of the ABA / contact
+// scalar.  The Y rows of the contact solve alias the per-link ABA region (dead after pass 3).
+TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int max_contacts) {
+  const int ra = size_ra / 4, rc = size_rc / 4;
+  const int n = D->n_qd;
+  if (max_contacts >= 0 && max_contacts < D->max_contacts) D->max_contacts = max_contacts;
+  int w = 0;
+  auto even = [](int x) { return (x + 1) & ~1; };
+  D->w_q = w; w += D->n_q;
+  D->w_qd = w; w += n;
+  D->w_tau = w; w += n;
+  w = even(w);
+  D->w_acc = w; w += D->n_acc * 37 * ra;
+  w = even(w);
+  D->w_xw = w; w += (D->n_links + 1) * 12 * rc;
+  D->w_M = w; w += (n * (n + 1) / 2) * rc;
+  D->w_w = w; w += n * rc;
+  D->w_con = w; w += D->max_contacts * 11 * rc;
+  w = even(w);
+  D->link_words = 26 * ra;
+  const int link_region = D->n_links * D->link_words;
+  const int y_region = 3 * D->max_contacts * n * rc;
+  D->w_link = w;
+  D->w_Y = w;
+  w += link_region > y_region ? link_region : y_region;
+  w = even(w);
+  D->w_total = w;
+}

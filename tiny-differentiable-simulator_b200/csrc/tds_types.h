@@ -1,0 +1,88 @@
+// Host/device shared POD types of the batched simulator.
+#pragma once
+#include <stdint.h>
+
+#define TDS_MAX_LINKS 40
+#define TDS_MAX_GEOMS 24
+#define TDS_MAX_VIS 24
+#define TDS_MAX_ACT 32
+
+// link flags
+#define TDS_LF_PARENT_ADJ 1   // parent == i-1  -> deltas are carried in registers
+#define TDS_LF_CHILD_ADJ 2    // link i+1 exists and its parent is i
+#define TDS_LF_REVOLUTE 4
+#define TDS_LF_PRISMATIC 8
+#define TDS_LF_FIXED 16
+
+// Device model: constant for all environments, passed as a __grid_constant__ kernel parameter
+// (lives in the constant bank; every lane reads the same entry -> broadcast).
+// Flattened from the reference's MultiBody/Link (src/multi_body.hpp:13, src/link.hpp:24).
+struct DevModel {
+  int n_links, floating, n_q, n_qd;
+  int n_geoms, n_acc, has_plane, max_contacts;
+  int base_acc;      // accumulator slot of the floating base (-1 if fixed base)
+  int n_vis, pad1, pad2;
+  // scratch arena layout, in 4-byte words per environment (see tds_step.cu)
+  int w_q, w_qd, w_tau, w_link, w_acc, w_xw, w_M, w_w, w_con, w_Y, w_total;
+  int link_words;    // words per link in the per-link region
+  int parent[TDS_MAX_LINKS];
+  int jtype[TDS_MAX_LINKS];
+  int q_idx[TDS_MAX_LINKS];
+  int qd_idx[TDS_MAX_LINKS];
+  int flags[TDS_MAX_LINKS];
+  int acc_slot[TDS_MAX_LINKS];   // accumulator slot receiving non-adjacent children (-1: none)
+  double XT[TDS_MAX_LINKS][12];  // X_T: R row-major [9], t [3]
+  double axis[TDS_MAX_LINKS][3];
+  float rbi[TDS_MAX_LINKS][10];  // mass, h = m*com [3], I about link origin (xx,xy,xz,yy,yz,zz)
+  float stiffness[TDS_MAX_LINKS];
+  float damping[TDS_MAX_LINKS];
+  float base_rbi[10];
+  float base_inertia_com[9];     // base_rbi.inertia (about com), for the gyroscopic term
+  // collision geoms of the robot in the reference's enumeration order
+  int g_link[TDS_MAX_GEOMS];
+  int g_type[TDS_MAX_GEOMS];
+  double g_t[TDS_MAX_GEOMS][3];     // local translation
+  double g_half[TDS_MAX_GEOMS][3];  // capsule: local half-axis R_local * (0,0,L/2)
+  double g_radius[TDS_MAX_GEOMS];
+  // static ground plane (multibody 0)
+  double plane_n[3];
+  double plane_c;
+  double fr1[3], fr2[3];  // plane_space(-n), src/mb_constraint_solver.hpp:506-520
+};
+
+struct DevVisuals {   // only used by the drop-in (v1 ABI) output packing
+  int n_vis, n_links, n_q, n_qd;
+  int v_link[TDS_MAX_VIS];
+  float v_R[TDS_MAX_VIS][9];
+  float v_t[TDS_MAX_VIS][3];
+};
+
+// World / solver / env parameters (src/world.hpp:65-69, src/mb_constraint_solver.hpp:59-70,
+// examples/environments/locomotion_contact_simulation.h:168-258).
+struct SimParams {
+  double dt;
+  double gravity[3];
+  double friction, restitution, erp, cfm;
+  int pgs_iterations;
+  int keep_all_points;
+};
+
+struct EnvParams {
+  int n_act;           // action_dim
+  int start_link;      // base_dof_ for fixed-base emulation (first PD-controlled link)
+  float kp, kd, max_force, action_limit;
+  float initial_poses[TDS_MAX_ACT];
+  int act_link[TDS_MAX_ACT];   // link index driven by action k
+  // reward/done (examples/environments/laikago_environment2.h:130-171)
+  int reward_kind;     // 0 none, 1 laikago (fixed-base emulation), 2 laikago floating
+};
+
+// Pointers to SoA state in HBM: array [dim][n_stride] (environment index fastest).
+struct StepIO {
+  const float* q_in; const float* qd_in; const float* tau_in;  // tau_in: [n_tau][n] or action [n_act][n]
+  float* q_out; float* qd_out; float* qdd_out;
+  float* reward; float* done;           // may be null
+  float* contact_dist;                  // [n_contact_points][n] or null
+  float* link_xf;                       // [n_links*12][n] world transforms of the step's FK, or null
+  int n; int n_stride;
+};

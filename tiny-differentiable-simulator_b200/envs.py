@@ -1,0 +1,129 @@
+"""Environment-level mirrors of the reference's vectorized Laikago environment and of the dlopen'd
+"C-ABI v1" model library.
+
+VectorizedLaikagoEnv follows pytinydiffsim.VectorizedLaikagoEnv
+(python/pytinydiffsim_includes.h:153-227, bound at python/pytinydiffsim.inl:1155-1175) which wraps
+VectorizedEnvironment<Algebra, LaikagoContactSimulation>::{reset,step}
+(examples/ars/ars_vectorized_environment.h:163-291).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .model import fixture_path, load_model
+from .sim import BatchSim, MODE_FULL
+
+LAIKAGO_INITIAL_POSES = np.array([0.2, 0.0, -0.7] * 4)   # laikago_environment2.h:50-61
+LAIKAGO_KP, LAIKAGO_KD, LAIKAGO_MAX_FORCE = 100.0, 2.0, 50.0  # laikago_environment2.h:43-45
+LAIKAGO_START_Z = 0.48
+
+
+def laikago_sim(n_envs, device=0, model=None, **kw):
+    """BatchSim configured like LaikagoContactSimulation (fixed-base emulation, friction 1,
+    keep_all_points, dt 1e-3; locomotion_contact_simulation.h:131-135, laikago_environment2.h:36-47)."""
+    if model is None:
+        model = load_model(fixture_path("laikago"))
+    sim = BatchSim(model, n_envs, device=device, dt=1e-3, friction=1.0, keep_all_points=True, **kw)
+    sim.set_env(LAIKAGO_INITIAL_POSES, start_link=6, kp=LAIKAGO_KP, kd=LAIKAGO_KD, max_force=LAIKAGO_MAX_FORCE,
+                action_limit=0.4, reward_kind=1)
+    return sim
+
+
+class VectorizedLaikagoEnvOutput:
+    def __init__(self, obs, rewards, dones, visual_world_transforms=None):
+        self.obs = obs
+        self.rewards = rewards
+        self.dones = dones
+        self.visual_world_transforms = visual_world_transforms
+
+
+class VectorizedLaikagoEnv:
+    def __init__(self, num_envs, auto_reset_when_done=True, device=0, seed=12345, model=None):
+        self.num_envs = num_envs
+        self.auto_reset = auto_reset_when_done
+        self.sim = laikago_sim(num_envs, device=device, model=model)
+        self.rng = np.random.default_rng(seed)
+        self._obs = np.zeros((num_envs, self.obs_dim()), dtype=np.float32)
+        self._rew = np.zeros(num_envs, dtype=np.float32)
+        self._done = np.zeros(num_envs, dtype=np.float32)
+
+    def action_dim(self):
+        return 12
+
+    def obs_dim(self):
+        return self.sim.n_q + self.sim.n_qd
+
+    def urdf_filename(self):
+        return "laikago/laikago_toes_zup_xyz_xyzrot.urdf"
+
+    def _initial_state(self, n):
+        # LaikagoContactSimulation::reset, laikago_environment2.h:63-116 (fixed-base branch)
+        q = np.zeros((n, self.sim.n_q))
+        q[:, 2] = LAIKAGO_START_Z
+        q[:, 6:18] = LAIKAGO_INITIAL_POSES + 0.05 * (self.rng.random((n, 12)) - 0.5) * 2.0
+        return q, np.zeros((n, self.sim.n_qd))
+
+    def _settle(self, steps=10):
+        zero = np.zeros((self.num_envs, 12), dtype=np.float32)
+        for _ in range(steps):
+            self.sim.env_step_host(zero, self._obs, self._rew, self._done)
+
+    def reset(self):
+        q, qd = self._initial_state(self.num_envs)
+        self.sim.env_set_state(q, qd)
+        self._settle()
+        return self._obs.copy()
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        assert a.shape == (self.num_envs, 12)
+        self.sim.env_step_host(a, self._obs, self._rew, self._done)
+        obs = self._obs.copy()
+        rewards, dones = self._rew.copy(), self._done.copy()
+        if self.auto_reset and dones.any():  # ars_vectorized_environment.h:262-283
+            idx = np.nonzero(dones)[0]
+            q, qd = self.sim.env_get_state()
+            q0, qd0 = self._initial_state(idx.size)
+            q[idx], qd[idx] = q0, qd0
+            self.sim.env_set_state(q, qd)
+            obs[idx, :self.sim.n_q] = q0
+            obs[idx, self.sim.n_q:] = qd0
+        obs[:, 0] = 0.0  # ars_vectorized_environment.h:285-287
+        obs[:, 1] = 0.0
+        return VectorizedLaikagoEnvOutput(obs, rewards, dones)
+
+
+class CudaModelV1:
+    """What tds::CudaModel / ars_train_policy_cuda's loader do with the dlopen'd library
+    (examples/ars/ars_train_policy_cuda.cpp:183-308): meta, allocate, forward_zero, deallocate."""
+
+    def __init__(self, model_name="cuda_model_laikago"):
+        self._L = _lib.lib()
+        self._name = model_name
+        self._fz = getattr(self._L, model_name + "_forward_zero")
+        self._meta = getattr(self._L, model_name + "_forward_zero_meta")
+        self._alloc = getattr(self._L, model_name + "_forward_zero_allocate")
+        self._dealloc = getattr(self._L, model_name + "_forward_zero_deallocate")
+        m = self._meta()
+        self.input_dim, self.output_dim, self.global_dim = m.input_dim, m.output_dim, m.global_dim
+        self._n = 0
+
+    def allocate(self, num_total_threads):
+        self._alloc(int(num_total_threads))
+        self._n = num_total_threads
+
+    def deallocate(self):
+        self._dealloc()
+        self._n = 0
+
+    def forward_zero(self, inputs, outputs=None, num_threads_per_block=64):
+        x = np.ascontiguousarray(inputs, dtype=np.float64)
+        n = x.shape[0]
+        assert x.shape[1] == self.input_dim and n <= self._n
+        if outputs is None:
+            outputs = np.zeros((n, self.output_dim))
+        dp = ctypes.POINTER(ctypes.c_double)
+        blocks = (n + num_threads_per_block - 1) // num_threads_per_block
+        self._fz(n, blocks, num_threads_per_block, outputs.ctypes.data_as(dp), x.ctypes.data_as(dp))
+        return outputs

@@ -1,0 +1,142 @@
+"""BatchSim: N independent copies of World{plane, MultiBody} resident on one GPU.
+
+Python-side mirror of the fine-grained pytinydiffsim surface for the hot path
+(forward_dynamics / integrate_euler_qdd / TinyWorld.step / integrate_euler,
+python/pytinydiffsim.inl:659-663,857-876), batched: one call = one step of all environments.
+torch is used for device memory and streams only.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .model import model_dims
+
+MODE_FD, MODE_NOCONTACT, MODE_FULL = 0, 1, 2
+PREC_MIXED, PREC_F64, PREC_F32 = 0, 1, 2
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchSim:
+    def __init__(self, model, n_envs, device=0, dt=1e-3, gravity=(0.0, 0.0, -9.81), friction=0.5,
+                 restitution=0.0, erp=0.2, cfm=1e-5, pgs_iterations=1, keep_all_points=False,
+                 precision=PREC_MIXED):
+        self._L = _lib.lib()
+        self.model = np.ascontiguousarray(model, dtype=np.float64)
+        self.info = model_dims(self.model)
+        self._h = self._L.tds_b200_create(_dp(self.model), self.model.size, int(n_envs), int(device))
+        if not self._h:
+            raise RuntimeError("tds_b200_create failed: " + _lib.last_error())
+        dims = (ctypes.c_int * 8)()
+        self._L.tds_b200_get_dims(self._h, dims)
+        (self.n_envs, self.n_stride, self.n_q, self.n_qd, self.n_tau, self.n_links,
+         self.n_contact_points, self.n_act) = list(dims)
+        self.device = device
+        self.set_params(dt, gravity, friction, restitution, erp, cfm, pgs_iterations, keep_all_points)
+        self.set_precision(precision)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tds_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what} failed (rc={rc}): {_lib.last_error()}")
+
+    def set_params(self, dt=1e-3, gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, erp=0.2, cfm=1e-5,
+                   pgs_iterations=1, keep_all_points=False):
+        g = np.asarray(gravity, dtype=np.float64)
+        self.dt = dt
+        self._check(self._L.tds_b200_set_params(self._h, dt, _dp(g), friction, restitution, erp, cfm,
+                                                pgs_iterations, int(keep_all_points)), "set_params")
+
+    def set_env(self, initial_poses, start_link=0, kp=0.0, kd=0.0, max_force=0.0, action_limit=0.4,
+                reward_kind=0):
+        ip = np.ascontiguousarray(initial_poses, dtype=np.float64)
+        self._check(self._L.tds_b200_set_env(self._h, ip.size, _dp(ip), start_link, kp, kd, max_force,
+                                             action_limit, reward_kind), "set_env")
+        self.n_act = ip.size
+
+    def set_precision(self, precision):
+        self._check(self._L.tds_b200_set_precision(self._h, precision), "set_precision")
+        self.precision = precision
+
+    # ---- device-resident fast path (torch CUDA tensors, SoA [dim, n_stride] float32) ----
+    def alloc(self, dim):
+        import torch
+        return torch.zeros((max(dim, 1), self.n_stride), dtype=torch.float32, device=f"cuda:{self.device}")
+
+    def step_device(self, mode, q, qd, tau_or_action=None, q_out=None, qd_out=None, qdd_out=None, reward=None,
+                    done=None, contact_dist=None, link_xf=None, use_pd=False, stream=None):
+        import torch
+        q_out = q if q_out is None else q_out
+        qd_out = qd if qd_out is None else qd_out
+        st = ctypes.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        rc = self._L.tds_b200_step_device(self._h, mode, int(use_pd), _ptr(q), _ptr(qd), _ptr(tau_or_action),
+                                          _ptr(q_out), _ptr(qd_out), _ptr(qdd_out), _ptr(reward), _ptr(done),
+                                          _ptr(contact_dist), _ptr(link_xf), st)
+        self._check(rc, "step_device")
+
+    # ---- host-buffer path: numpy [n_envs, dim] float64 in / out ----
+    def step_host(self, mode, q, qd, tau_or_action=None, use_pd=False, want_contacts=False):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qd = np.ascontiguousarray(qd, dtype=np.float64)
+        n = self.n_envs
+        assert q.shape == (n, self.n_q) and qd.shape == (n, self.n_qd)
+        t = None
+        if tau_or_action is not None:
+            t = np.ascontiguousarray(tau_or_action, dtype=np.float64)
+            assert t.shape == (n, self.n_act if use_pd else self.n_tau), t.shape
+        out = dict(q=np.zeros_like(q), qd=np.zeros_like(qd))
+        qdd = np.zeros_like(qd) if mode == MODE_FD else None
+        cd = np.zeros((n, max(self.n_contact_points, 1))) if want_contacts else None
+        rc = self._L.tds_b200_step_host(self._h, mode, int(use_pd), _dp(q), _dp(qd), _dp(t), _dp(out["q"]),
+                                        _dp(out["qd"]), _dp(qdd), _dp(cd))
+        self._check(rc, "step_host")
+        if qdd is not None:
+            out["qdd"] = qdd
+        if cd is not None:
+            out["contact_dist"] = cd[:, :self.n_contact_points]
+        return out
+
+    # ---- resident environment state ----
+    def env_set_state(self, q, qd):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qd = np.ascontiguousarray(qd, dtype=np.float64)
+        assert q.shape == (self.n_envs, self.n_q) and qd.shape == (self.n_envs, self.n_qd)
+        self._check(self._L.tds_b200_env_set_state_host(self._h, _dp(q), _dp(qd)), "env_set_state")
+
+    def env_get_state(self):
+        q = np.zeros((self.n_envs, self.n_q))
+        qd = np.zeros((self.n_envs, self.n_qd))
+        self._check(self._L.tds_b200_env_get_state_host(self._h, _dp(q), _dp(qd)), "env_get_state")
+        return q, qd
+
+    def env_step_host(self, actions, obs, rewards, dones):
+        """actions/obs/rewards/dones: float32 host arrays (numpy or pinned torch tensors)."""
+        def hp(a):
+            if a is None:
+                return None
+            return ctypes.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+        self._check(self._L.tds_b200_env_step_host(self._h, hp(actions), hp(obs), hp(rewards), hp(dones)),
+                    "env_step_host")
+
+    def env_step_device(self, actions, reward=None, done=None, stream=None):
+        import torch
+        st = ctypes.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        self._check(self._L.tds_b200_env_step_device(self._h, _ptr(actions), _ptr(reward), _ptr(done), st),
+                    "env_step_device")

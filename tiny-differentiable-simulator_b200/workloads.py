@@ -1,0 +1,81 @@
+"""Synthetic, deterministic inputs for the BASELINE.json configs.
+seed 12345 = ARSConfig::env_seed (examples/ars/ars_config.h:10).  Values are rounded to fp32 so the
+fp64 oracle and the fp32-state GPU path see identical inputs."""
+import numpy as np
+
+SEED = 12345
+
+
+def _f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def cartpole(n, seed=SEED):
+    """C1: cartpole.urdf, q,qd ~ U(-0.05,0.05), tau0 ~ U(-10,10), dt=1/60, g=-10 (cartpole_environment2.h)."""
+    r = np.random.default_rng(seed)
+    q = r.uniform(-0.05, 0.05, (n, 2))
+    qd = r.uniform(-0.05, 0.05, (n, 2))
+    tau = np.zeros((n, 2))
+    tau[:, 0] = r.uniform(-10, 10, n)
+    return dict(q=_f32(q), qd=_f32(qd), tau=_f32(tau), params=dict(dt=1.0 / 60.0, gravity=(0.0, 0.0, -10.0)), mode=1)
+
+
+def pendulum5(n, seed=SEED):
+    """C2: pendulum5.urdf, forward_dynamics only."""
+    r = np.random.default_rng(seed)
+    return dict(q=_f32(r.uniform(-np.pi, np.pi, (n, 5))), qd=_f32(r.uniform(-2, 2, (n, 5))),
+                tau=_f32(r.uniform(-1, 1, (n, 5))), params=dict(), mode=0)
+
+
+def sphere2(n, seed=SEED):
+    """C3: sphere2.urdf (floating) on plane_implicit: ~50% penetrating, friction 0.5, keep_all_points false."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 7))
+    q[:, 3] = 1.0
+    q[:, 4:6] = r.uniform(-1, 1, (n, 2))
+    q[:, 6] = r.uniform(0.45, 0.55, n)
+    qd = r.uniform(-1, 1, (n, 6))
+    return dict(q=_f32(q), qd=_f32(qd), tau=None, params=dict(friction=0.5, keep_all_points=False), mode=2)
+
+
+def laikago(n, seed=SEED):
+    """C4: Laikago on plane; LaikagoContactSimulation::reset state + noise, actions ~ U(-0.4, 0.4)."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 18))
+    q[:, 2] = 0.48
+    q[:, 6:18] = np.array([0.2, 0.0, -0.7] * 4) + 0.05 * (r.random((n, 12)) - 0.5) * 2.0
+    qd = np.zeros((n, 18))
+    act = r.uniform(-0.4, 0.4, (n, 12))
+    return dict(q=_f32(q), qd=_f32(qd), action=_f32(act), params=dict(friction=1.0, keep_all_points=True), mode=2)
+
+
+def laikago_perturbed(n, seed=SEED):
+    """Laikago states spread over the reachable set (for parity tests): base height such that 0-4 toes
+    penetrate, non-zero base orientation and velocities."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 18))
+    q[:, 0:2] = r.uniform(-0.2, 0.2, (n, 2))
+    q[:, 2] = r.uniform(0.36, 0.50, n)
+    q[:, 3:6] = r.uniform(-0.25, 0.25, (n, 3))
+    q[:, 6:18] = np.array([0.2, 0.0, -0.7] * 4) + r.uniform(-0.15, 0.15, (n, 12))
+    qd = r.uniform(-1.0, 1.0, (n, 18))
+    act = r.uniform(-0.5, 0.5, (n, 12))
+    return dict(q=_f32(q), qd=_f32(qd), action=_f32(act), params=dict(friction=1.0, keep_all_points=True), mode=2)
+
+
+def humanoid(n, seed=SEED, z_range=(0.9, 1.45)):
+    """C5: humanoid.urdf floating base; identity-ish base orientation, joints U(+-0.05)."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 28))
+    quat = np.zeros((n, 4)); quat[:, 3] = 1.0
+    quat[:, :3] = r.uniform(-0.1, 0.1, (n, 3))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    q[:, :4] = quat
+    q[:, 4:6] = r.uniform(-0.5, 0.5, (n, 2))
+    q[:, 6] = r.uniform(z_range[0], z_range[1], n)
+    q[:, 7:] = r.uniform(-0.05, 0.05, (n, 21))
+    qd = r.uniform(-0.5, 0.5, (n, 27))
+    tau = r.uniform(-1, 1, (n, 21))
+    # re-normalise after fp32 rounding so the reference's unit-quaternion assert holds
+    q = _f32(q)
+    return dict(q=q, qd=_f32(qd), tau=_f32(tau), params=dict(friction=1.0, keep_all_points=False), mode=2)
