@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/sec of the batched Laikago-on-plane step (BASELINE.json configs[3]:
+"laikago on plane, 4096 envs, full step + PD actuators") on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU path on the host cores
+
+One "step" = one env-step of every environment (PD -> ABA -> integrate -> collide -> LCP/PGS ->
+integrate).  Environments are sharded across ranks (4096 per GPU: weak scaling), there is no
+data-path collective.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+ALGO_BYTES_PER_ENV_STEP = 344       # q18+qd18+action12 read, q18+qd18+reward+done written (fp32)
+FLOPS_PER_ENV_STEP = 27e3           # op count of the reference's CppAD tape
+METRIC = "env-steps/sec (N parallel sims)"
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json, burst copy bandwidth)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_rate(seconds=12.0, envs=ENVS_PER_GPU, impl=0, threads=None, seed=12345):
+    """env-steps/s of the reference's own CPU implementation (oracle/_ref, compiled in place from
+    /root/reference by oracle/build_ref.sh): LocomotionContactSimulation::step_forward_original
+    (impl 0, one instance per thread) or its codegen kernel (impl 1), on `threads` host threads."""
+    from oracle import ref
+    import tds_b200.workloads as wl
+    threads = threads or (os.cpu_count() or 1)
+    L = ref.LaikagoRef(threads)
+    w = wl.laikago(envs, seed=seed)
+    x = np.zeros((envs, 51))
+    x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = w["q"], w["qd"], w["action"], [100.0, 2.0, 50.0]
+    out = np.zeros((envs, L.output_dim))
+    L.step(x, impl, out)  # warm-up
+    n_batches, t0 = 0, time.perf_counter()
+    while True:
+        L.step(x, impl, out)
+        x[:, :36] = out[:, :36]
+        n_batches += 1
+        el = time.perf_counter() - t0
+        if el >= seconds and n_batches >= 2:
+            break
+    return envs * n_batches / el, threads, f"{n_batches} batches of {envs} env-steps in {el:.1f} s"
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU path for the same metric/config, rank 0 only."""
+    if rank != 0:
+        return
+    envs = ENVS_PER_GPU
+    from oracle import ref
+    import tds_b200.workloads as wl
+    threads = os.cpu_count() or 1
+    L = ref.LaikagoRef(threads)
+    w = wl.laikago(envs)
+    x = np.zeros((envs, 51))
+    x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = w["q"], w["qd"], w["action"], [100.0, 2.0, 50.0]
+    out = np.zeros((envs, L.output_dim))
+    # keep the whole run within a few minutes: a step of this arm = one batch of `sample` env-steps
+    sample = envs
+    for _ in range(max(1, min(args.warmup, 3))):
+        L.step(x[:sample], 0, out[:sample])
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 40))
+    for _ in range(steps):
+        L.step(x[:sample], 0, out[:sample])
+        x[:sample, :36] = out[:sample, :36]
+    el = time.perf_counter() - t0
+    val = sample * steps / el
+    line = {"metric": METRIC, "value": val, "unit": "env-steps/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "laikago on plane, 4096 envs, full step + PD actuators (BASELINE.json configs[3])",
+                       "envs_per_step": sample, "path": "LocomotionContactSimulation::step_forward_original (templated CPU path), "
+                       "one instance per OpenMP thread"},
+            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "reference",
+                             "sample": f"{steps} steps x {sample} envs"},
+            "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--precision", type=int, default=0, help="0 mixed (fp32 ABA + fp64 contact), 1 fp64, 2 fp32")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-reward", action="store_true",
+                    help="all-gather {reward, done} per step (only needed by a single centralized policy)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import tds_b200
+    import tds_b200.workloads as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    n = args.envs
+    K, W = args.steps, max(args.warmup, 3)
+
+    sim = tds_b200.laikago_sim(n, device=local_rank, precision=args.precision)
+    w = wl.laikago(n, seed=wl.SEED + rank)
+    sim.env_set_state(w["q"], w["qd"])
+    ns = sim.n_stride
+    # a ring of distinct resident action tensors (synthetic policy output), SoA [12][ns]
+    ring = 16
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    actions = [(torch.rand((12, ns), generator=g) * 0.8 - 0.4).to(dev) for _ in range(ring)]
+    reward = torch.zeros(ns, device=dev)
+    done = torch.zeros(ns, device=dev)
+    gathered = torch.zeros((world, 2, ns), device=dev) if (args.gather_reward and world > 1) else None
+    flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    zero = torch.zeros((12, ns), device=dev)
+    for _ in range(10):  # settle like LaikagoContactSimulation::reset (laikago_environment2.h:96-104)
+        sim.env_step_device(zero, reward, done)
+
+    def one_step(i, ev0=None, ev1=None):
+        if flush_buf is not None:
+            flush_buf.fill_(i & 0xFF)       # evict L2 (126 MB) between timed steps; not timed
+        if ev0 is not None:
+            ev0.record(stream)
+        sim.env_step_device(actions[i % ring], reward, done)
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered.view(-1), torch.stack([reward, done]).view(-1))
+        if ev1 is not None:
+            ev1.record(stream)
+
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        one_step(i, *evs[i])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))       # device time of the K timed steps
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    q_chk, _ = sim.env_get_state()
+    if not np.all(np.isfinite(q_chk)):
+        raise SystemExit("bench.py: non-finite state after the timed region")
+
+    # ---- end-to-end through the public host API: pinned host actions in, obs/reward/done out, every step
+    act_h = torch.rand((n, 12)).mul_(0.8).sub_(0.4).pin_memory()
+    obs_h = torch.zeros((n, 36)).pin_memory()
+    rew_h = torch.zeros(n).pin_memory()
+    done_h = torch.zeros(n).pin_memory()
+    Ke = min(K, 200)
+    for _ in range(5):
+        sim.env_step_host(act_h, obs_h, rew_h, done_h)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        sim.env_step_host(act_h, obs_h, rew_h, done_h)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = n * world * Ke / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = n * world * K / (total_ms * 1e-3)
+    peaks, peak_src = _measured_peaks()
+    kernel_s = (total_ms * 1e-3) / K
+    achieved = ALGO_BYTES_PER_ENV_STEP * n / kernel_s / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_step_kernel_ncu.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": ["f32 (ABA) + f64 (kinematics, contact solve)", "f64", "f32"][args.precision], "data": "synthetic",
+        "config": {"workload": "laikago on plane, 4096 envs/GPU, full step + PD actuators (BASELINE.json configs[3])",
+                   "envs_per_gpu": n, "global_envs": n * world, "dt": 1e-3, "parallelism": f"env-sharded x{world}, no data-path collective"
+                   + (" + all-gather(reward,done)" if gathered is not None else ""),
+                   "state": "SoA fp32 resident in HBM", "timing": "sum of per-step CUDA-event intervals, max over ranks",
+                   "l2": ("flushed: 256 MiB write between timed steps" if flush_buf is not None else "not flushed (state 0.6 MB stays L2-resident)"),
+                   "wall_s_timed_region": t_wall},
+        "gpu_launches": K, "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4,
+                                    "d2h_bytes_per_step": n * 36 * 4 + n * 4 + n * 4, "steps": Ke, "gpu_launches_per_step": 4,
+                                    "api": "tds_b200_env_step_host (actions host->device, obs/reward/done device->host, pinned)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "tds_step_kernel<float,double,smem>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "note": "path is issue/latency bound (~27 kFLOP and 344 B per env-step); fp32-equivalent GFLOP/s reported beside it",
+                     "gflops": FLOPS_PER_ENV_STEP * n / kernel_s / 1e9},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, cores, sample = cpu_reference_rate(seconds=12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "reference", "sample": sample,
+                                    "path": "step_forward_original (templated World::step path), one instance per thread"}
+            v2, _, sample2 = cpu_reference_rate(seconds=4.0, impl=1)
+            line["cpu_baseline_codegen"] = {"value": v2, "unit": "env-steps/s", "cores": cores, "kind": "reference",
+                                            "sample": sample2, "path": "omp_model_laikago_forward_zero_kernel (reference's codegen CPU path)"}
+        except Exception as ex:  # the oracle library did not travel: report it, do not fake it
+            line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,14 +52,15 @@ def main():
                    meta=dict(source=os.path.relpath(urdf, D), plane=bool(plane), floating=floating,
                              exported_by="reference UrdfCache::construct via oracle/_ref"))
         w = gen(N)
-        if name == "humanoid":  # half the batch low enough to penetrate
-            w2 = wl.humanoid(N, seed=wl.SEED + 1, z_range=(0.0, 0.6))
-            for k in ("q", "qd", "tau"):
-                w[k][N // 2:] = w2[k][N // 2:]
-            # unit quaternions (reference asserts |q|^2 > 0.999, kinematics.hpp:37-39)
-            w["q"][:, :4] /= np.linalg.norm(w["q"][:, :4], axis=1, keepdims=True)
-            w["q"] = w["q"].astype(np.float32).astype(np.float64)
         sim.set_params(**w["params"])
+        if name == "humanoid":
+            # second half of the batch: lower the base until the lowest contact point penetrates by 0..3 cm
+            # (the base z that does this is found with the reference's own contact distances)
+            rng = np.random.default_rng(99)
+            for i in range(N // 2, N):
+                o = sim.step(2, w["q"][i], w["qd"][i], w["tau"][i], contact_cap=64)
+                w["q"][i, 6] -= o["contact_data"][:, 9].min() + rng.uniform(0.0, 0.03)
+            w["q"] = w["q"].astype(np.float32).astype(np.float64)
         mode = w["mode"]
         tau = w.get("tau")
         if name == "laikago":

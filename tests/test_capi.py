@@ -1,0 +1,55 @@
+"""C-ABI library: loads on a CPU box, exports every symbol include/tds_b200.h declares, and refuses
+to create a simulator without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import tds_b200
+from tds_b200 import _lib
+from tds_b200.model import fixture_path, load_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_in_header():
+    text = open(os.path.join(ROOT, "include", "tds_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:tds_b200|cuda_model_laikago)_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    L = tds_b200.lib()
+    names = declared_in_header()
+    assert len(names) >= 18
+    for nm in names:
+        assert hasattr(L, nm), f"{nm} declared in include/tds_b200.h but not exported"
+    assert sorted(_lib.DECLARED_SYMBOLS) == names
+
+
+def test_v1_meta_matches_reference_dims():
+    m = tds_b200.lib().cuda_model_laikago_forward_zero_meta()
+    assert (m.input_dim, m.output_dim, m.global_dim) == (51, 411, 0)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError) as e:
+        tds_b200.BatchSim(load_model(fixture_path("laikago")), 8)
+    assert "no CUDA device" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing in the product package may import, include or load it."""
+    pkg = os.path.dirname(tds_b200.lib_path())
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                continue
+            txt = open(os.path.join(dp, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+            assert not re.search(r"#include\s*[\"<][^\n]*oracle", txt), f
+            assert "libtds_oracle" not in txt and "libtds_ref" not in txt and "tdso_" not in txt and "tdsref_" not in txt, f

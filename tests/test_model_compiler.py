@@ -1,0 +1,90 @@
+"""Host-side model compiler (csrc/urdf_model.cpp): URDF -> flat model.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import tds_b200
+from tds_b200.model import compile_urdf, fixture_path, load_model, model_dims
+from conftest import REFERENCE_ROOT, have_reference_tree
+
+TINY_URDF = """<?xml version="1.0"?>
+<!-- two-link arm with a fixed tool and a capsule -->
+<robot name="arm">
+  <link name="base"><inertial><mass value="0"/><inertia ixx="0" iyy="0" izz="0" ixy="0" ixz="0" iyz="0"/></inertial></link>
+  <link name="upper"><inertial><origin xyz="0 0 0.25" rpy="0 0 0"/><mass value="2"/><inertia ixx="0.1" iyy="0.2" izz="0.3"/></inertial>
+    <collision><origin xyz="0 0 0.25"/><geometry><capsule radius="0.05" length="0.5"/></geometry></collision></link>
+  <link name="tool"><inertial><mass value="0.1"/><inertia ixx="1e-3" iyy="1e-3" izz="1e-3"/></inertial>
+    <collision><geometry><sphere radius='0.02'/></geometry></collision>
+    <visual><origin xyz="0 0 0.1" rpy="0 0 1.57"/><geometry><mesh filename="x.obj"/></geometry></visual></link>
+  <link name="lower"><inertial><origin xyz="0 0 0.2"/><mass value="1"/><inertia ixx="0.05" iyy="0.05" izz="0.01"/></inertial></link>
+  <joint name="j2" type="continuous"><parent link="upper"/><child link="lower"/><origin xyz="0 0 0.5"/><axis xyz="0 -1 0"/></joint>
+  <joint name="j1" type="revolute"><parent link="base"/><child link="upper"/><origin xyz="0 0 0.1" rpy="0 0 0.3"/><axis xyz="1 0 0"/></joint>
+  <joint name="jt" type="fixed"><parent link="lower"/><child link="tool"/><origin xyz="0 0 0.4"/></joint>
+</robot>"""
+PLANE = '<robot name="p"><link name="l"><collision><geometry><plane normal="0 0 2"/></geometry></collision></link></robot>'
+
+
+def test_tiny_urdf_structure():
+    m = compile_urdf(TINY_URDF, PLANE, floating=False)
+    d = model_dims(m)
+    assert d == dict(n_links=3, floating=0, n_q=2, n_qd=2, n_geoms=2, n_vis=1, has_plane=1)
+    assert np.allclose(m[8:11], [0, 0, 1])                       # plane normal normalised, constant 0
+    links = m[16 + 13:].reshape(-1)[:3 * 34].reshape(3, 34)
+    # pre-order DFS, children in joint document order: upper(0) <- lower(1) <- tool(2)
+    assert links[:, 0].tolist() == [-1, 0, 1]
+    assert links[:, 1].tolist() == [4, 7, -1]                    # REVOLUTE_X, REVOLUTE_AXIS (axis -y != +1), FIXED
+    assert links[:, 2].tolist() == [0, 1, -2] and links[:, 3].tolist() == [0, 1, -2]
+    assert links[1, 4:7].tolist() == [0, -1, 0]
+    assert np.allclose(links[0, 7:16].reshape(3, 3), [[np.cos(.3), -np.sin(.3), 0], [np.sin(.3), np.cos(.3), 0], [0, 0, 1]])
+    geoms = m[16 + 13 + 3 * 34:][:2 * 18].reshape(2, 18)
+    assert geoms[:, 0].tolist() == [0, 2] and geoms[:, 1].tolist() == [2, 0]     # capsule on link 0, sphere on link 2
+
+
+def test_floating_indices_and_default_axis():
+    u = TINY_URDF.replace('<axis xyz="1 0 0"/>', "")
+    m = compile_urdf(u, None, floating=True)
+    d = model_dims(m)
+    assert (d["n_q"], d["n_qd"], d["has_plane"]) == (9, 8, 0)
+    links = m[16 + 13:][:3 * 34].reshape(3, 34)
+    assert links[0, 1] == 6 and links[0, 2] == 7 and links[0, 3] == 6           # default axis (0,0,1) -> REVOLUTE_Z; q starts at 7
+
+
+@pytest.mark.parametrize("bad,msg", [
+    ("<robot name='x'><link name='a'/><link name='b'/></robot>", "multiple parent links"),
+    ("<robot name='x'><link name='a'></robot>", "XML error"),
+    (TINY_URDF.replace('type="continuous"', 'type="planar"'), "unsupported type"),
+    (TINY_URDF.replace('type="continuous"', 'type="spherical"'), "spherical"),
+    ("<robot><link name='a'/></robot>", "name"),
+])
+def test_errors(bad, msg):
+    with pytest.raises(ValueError) as e:
+        compile_urdf(bad)
+    assert msg in str(e.value)
+
+
+@pytest.mark.skipif(not have_reference_tree(), reason="reference URDF data only exists in the build container")
+@pytest.mark.parametrize("name,urdf,plane,floating", [
+    ("cartpole", "cartpole.urdf", None, False), ("pendulum5", "pendulum5.urdf", None, False),
+    ("sphere2", "sphere2.urdf", "plane_implicit.urdf", True),
+    ("laikago", "laikago/laikago_toes_zup_xyz_xyzrot.urdf", "plane_implicit.urdf", False),
+    ("humanoid", "humanoid.urdf", "plane_implicit.urdf", True)])
+def test_matches_reference_loader(name, urdf, plane, floating):
+    """Our compiler on the reference's URDFs == the flat export of the reference's own loader
+    (fixtures were exported from UrdfCache::construct by tests/golden/make_golden.py)."""
+    D = os.path.join(REFERENCE_ROOT, "data")
+    mine = compile_urdf(os.path.join(D, urdf), os.path.join(D, plane) if plane else None, floating)
+    ref = load_model(fixture_path(name))
+    assert mine.shape == ref.shape
+    assert np.abs(mine - ref).max() < 1e-15
+
+
+def test_generated_laikago_table_is_the_fixture():
+    """The model table embedded in the C-ABI v1 drop-in equals the reference-exported Laikago model."""
+    inc = os.path.join(os.path.dirname(tds_b200.lib_path()), "csrc", "generated", "laikago_model.inc")
+    vals = []
+    for line in open(inc):
+        if line.startswith("//"):
+            continue
+        vals += [float(x) for x in line.strip().rstrip(",").split(",") if x.strip()]
+    assert np.array_equal(np.array(vals), load_model(fixture_path("laikago")))

@@ -1,0 +1,89 @@
+"""CPU tests of the test oracles themselves (no GPU):
+  * the plain-C fp64 restatement (oracle/tds_oracle.c) against the committed golden vectors that were
+    generated from the UNMODIFIED reference compiled in place (tests/golden/make_golden.py);
+  * live against oracle/_ref/libtds_ref.so when that library is present (container; it also travels
+    to the GPU box as a prebuilt file).
+This is what pins the oracle ("parity pinned")."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from tds_b200.model import fixture_path, load_model
+import tds_b200.workloads as wl
+
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid"]
+
+
+def params_of(g):
+    kw = {}
+    for k in g.files:
+        if k.startswith("param_"):
+            v = g[k]
+            kw[k[6:]] = tuple(v.tolist()) if v.ndim else (bool(v) if k == "param_keep_all_points" else float(v))
+    return kw
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_c_oracle_matches_reference_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+    model = load_model(fixture_path(name))
+    P = port.make_params(**params_of(g))
+    mode = int(g["mode"])
+    n = g["q_in"].shape[0]
+    tau = g["tau"] if "tau" in g.files else None
+    worst = 0.0
+    for i in range(n):
+        o = port.step(model, P, mode, g["q_in"][i], g["qd_in"][i], None if tau is None else tau[i])
+        worst = max(worst, np.abs(o["qdd"] - g["qdd"][i]).max() / max(1.0, np.abs(g["qdd"][i]).max()))
+        if mode > 0:
+            worst = max(worst, np.abs(o["q"] - g["q_out"][i]).max(), np.abs(o["qd"] - g["qd_out"][i]).max()
+                        / max(1.0, np.abs(g["qd_out"][i]).max()))
+        if mode == 2:
+            assert o["n_contacts"] == int(g["n_contacts"][i])
+            if o["n_contacts"]:
+                assert np.array_equal(o["contact_idx"][:, 1], g["contact_link_b"][i])   # bit-exact index list
+                assert np.abs(o["contact_data"][:, 9] - g["contact_dist"][i]).max() < 1e-12
+    assert worst < 1e-9, worst
+
+
+def test_c_oracle_laikago_env_step_matches_reference_env(golden_dir):
+    g = np.load(os.path.join(golden_dir, "laikago.npz"))
+    model = load_model(fixture_path("laikago"))
+    P = port.make_params(friction=1.0, keep_all_points=True)
+    out = port.locomotion_step(model, P, np.array([0.2, 0.0, -0.7] * 4), 6, g["env_input"], 411)
+    assert np.abs(out - g["env_output_templated"]).max() < 1e-10        # all 411 outputs incl. visual quats
+    # the reference's second CPU implementation (its CppAD-generated kernel) agrees on q/qd
+    assert np.abs(out[:, :36] - g["env_output_codegen"][:, :36]).max() < 1e-10
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libtds_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("name", CONFIGS)
+def test_c_oracle_matches_live_reference(name):
+    model = load_model(fixture_path(name))
+    rs = ref.RefSim.from_model(model)            # reference MultiBody rebuilt from the flat model
+    gen = dict(cartpole=wl.cartpole, pendulum5=wl.pendulum5, sphere2=wl.sphere2, laikago=wl.laikago_perturbed,
+               humanoid=wl.humanoid)[name]
+    w = gen(24, seed=31337)
+    if name == "humanoid":
+        w["q"][:, 6] = np.random.default_rng(5).uniform(0.05, 0.4, 24)   # deep, violent contacts too
+    rs.set_params(**w["params"])
+    P = port.make_params(**w["params"])
+    tau = w.get("tau")
+    if name == "laikago":
+        tau = np.zeros((24, 18))
+        tau[:, 6:] = np.clip(100 * (np.array([0.2, 0, -0.7] * 4) + np.clip(w["action"], -.4, .4) - w["q"][:, 6:]) - 2 * w["qd"][:, 6:], -50, 50)
+    for i in range(24):
+        t = None if tau is None else tau[i]
+        a = rs.step(w["mode"], w["q"][i], w["qd"][i], t, contact_cap=64)
+        b = port.step(model, P, w["mode"], w["q"][i], w["qd"][i], t)
+        scale = max(1.0, np.abs(a["qd"]).max(), np.abs(a["qdd"]).max())
+        assert np.abs(a["q"] - b["q"]).max() < 1e-9
+        assert np.abs(a["qd"] - b["qd"]).max() / scale < 1e-9
+        assert np.abs(a["qdd"] - b["qdd"]).max() / scale < 1e-9
+        assert a["n_contacts"] == b["n_contacts"]
+        if a["n_contacts"]:
+            assert np.array_equal(a["contact_idx"], b["contact_idx"])
+    Ma, Mb = rs.mass_matrix(w["q"][0]), port.mass_matrix(model, w["q"][0])
+    assert np.abs(Ma - Mb).max() < 1e-10

@@ -30,20 +30,20 @@ TDS_HOST_INLINE void tds_plane_space(const double* n, double* p, double* q) {
 
 // rigid-body inertia (mass, com, inertia about com) -> (m, h = m com, I about the link origin),
 // i.e. the blocks of ArticulatedBodyInertia(rbi), src/math/inertia.hpp:114-119.
-TDS_HOST_INLINE void tds_rbi_pack(const double* rec /* mass, com[3], inertia[9] */, float* out) {
+TDS_HOST_INLINE void tds_rbi_pack(const double* rec /* mass, com[3], inertia[9] */, double* out) {
   double m = rec[0];
   const double* c = rec + 1;
   const double* I = rec + 4;
   // H = cross(com); I_o = inertia + H H^T m ; H H^T = (c.c) 1 - c c^T
   double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
-  out[0] = (float)m;
-  out[1] = (float)(m * c[0]); out[2] = (float)(m * c[1]); out[3] = (float)(m * c[2]);
-  out[4] = (float)(I[0] + m * (cc - c[0] * c[0]));
-  out[5] = (float)(0.5 * (I[1] + I[3]) - m * c[0] * c[1]);
-  out[6] = (float)(0.5 * (I[2] + I[6]) - m * c[0] * c[2]);
-  out[7] = (float)(I[4] + m * (cc - c[1] * c[1]));
-  out[8] = (float)(0.5 * (I[5] + I[7]) - m * c[1] * c[2]);
-  out[9] = (float)(I[8] + m * (cc - c[2] * c[2]));
+  out[0] = m;
+  out[1] = (m * c[0]); out[2] = (m * c[1]); out[3] = (m * c[2]);
+  out[4] = (I[0] + m * (cc - c[0] * c[0]));
+  out[5] = (0.5 * (I[1] + I[3]) - m * c[0] * c[1]);
+  out[6] = (0.5 * (I[2] + I[6]) - m * c[0] * c[2]);
+  out[7] = (I[4] + m * (cc - c[1] * c[1]));
+  out[8] = (0.5 * (I[5] + I[7]) - m * c[1] * c[2]);
+  out[9] = (I[8] + m * (cc - c[2] * c[2]));
 }
 
 // Returns 0 on success, <0 on unsupported / oversized models.
@@ -136,7 +136,9 @@ TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int
   D->w_qd = w; w += n;
   D->w_tau = w; w += n;
   w = even(w);
-  D->w_acc = w; w += D->n_acc * 37 * ra;
+  D->acc_ic_word = even(27 * ra);
+  D->acc_words = even(D->acc_ic_word + 10 * rc);
+  D->w_acc = w; w += D->n_acc * D->acc_words;
   w = even(w);
   D->w_xw = w; w += (D->n_links + 1) * 12 * rc;
   D->w_M = w; w += (n * (n + 1) / 2) * rc;

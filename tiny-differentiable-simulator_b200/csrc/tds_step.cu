@@ -71,8 +71,9 @@ template <typename T> TDS_D Sv<T> ld_sv(const Arena& A, int w, int k) { Sv<T> s;
 
 // per-link region (element offsets, in units of RA)
 enum { LK_XP = 0, LK_VC = 12, LK_U = 18, LK_INVD = 24, LK_u = 25, LK_SIZE = 26 };
-// accumulator slot (units of RA): abi 21, pA 6, Ic 10
-enum { AC_ABI = 0, AC_PA = 21, AC_IC = 27, AC_SIZE = 37 };
+// accumulator slot: abi 21 + pA 6 (units of RA), then Ic 10 (units of RC) at word offset M.acc_ic_word;
+// the slot stride in words is M.acc_words (both computed on the host, tds_build_layout).
+enum { AC_ABI = 0, AC_PA = 21, AC_NRA = 27, AC_NIC = 10 };
 // contact record (units of RC): pb 3, dist, link, b[3], x[3]
 enum { CN_PB = 0, CN_DIST = 3, CN_LINK = 4, CN_B = 5, CN_X = 8, CN_SIZE = 11 };
 
@@ -86,22 +87,26 @@ template <typename T> TDS_D void acc_add_abi(const Arena& A, int w, const Abi<T>
   A.at<T>(w, AC_PA + 3) += p.bot.x; A.at<T>(w, AC_PA + 4) += p.bot.y; A.at<T>(w, AC_PA + 5) += p.bot.z;
 }
 template <typename T> TDS_D void acc_add_rbi(const Arena& A, int w, const Rbi<T>& r) {
-  A.at<T>(w, AC_IC + 0) += r.m; A.at<T>(w, AC_IC + 1) += r.h.x; A.at<T>(w, AC_IC + 2) += r.h.y; A.at<T>(w, AC_IC + 3) += r.h.z;
-  A.at<T>(w, AC_IC + 4) += r.I.xx; A.at<T>(w, AC_IC + 5) += r.I.xy; A.at<T>(w, AC_IC + 6) += r.I.xz;
-  A.at<T>(w, AC_IC + 7) += r.I.yy; A.at<T>(w, AC_IC + 8) += r.I.yz; A.at<T>(w, AC_IC + 9) += r.I.zz;
+  A.at<T>(w, 0) += r.m; A.at<T>(w, 1) += r.h.x; A.at<T>(w, 2) += r.h.y; A.at<T>(w, 3) += r.h.z;
+  A.at<T>(w, 4) += r.I.xx; A.at<T>(w, 5) += r.I.xy; A.at<T>(w, 6) += r.I.xz;
+  A.at<T>(w, 7) += r.I.yy; A.at<T>(w, 8) += r.I.yz; A.at<T>(w, 9) += r.I.zz;
 }
-template <typename T> TDS_D void acc_load(const Arena& A, int w, Abi<T>& a, Sv<T>& p, Rbi<T>& r) {
+template <typename T> TDS_D Rbi<T> acc_load_rbi(const Arena& A, int w) {
+  Rbi<T> r;
+  r.m = A.at<T>(w, 0); r.h = ld_v3<T>(A, w, 1);
+  r.I.xx = A.at<T>(w, 4); r.I.xy = A.at<T>(w, 5); r.I.xz = A.at<T>(w, 6);
+  r.I.yy = A.at<T>(w, 7); r.I.yz = A.at<T>(w, 8); r.I.zz = A.at<T>(w, 9);
+  return r;
+}
+template <typename T> TDS_D void acc_load(const Arena& A, int w, Abi<T>& a, Sv<T>& p) {
   a.I.xx = A.at<T>(w, 0); a.I.xy = A.at<T>(w, 1); a.I.xz = A.at<T>(w, 2); a.I.yy = A.at<T>(w, 3); a.I.yz = A.at<T>(w, 4); a.I.zz = A.at<T>(w, 5);
   a.H.xx = A.at<T>(w, 6); a.H.xy = A.at<T>(w, 7); a.H.xz = A.at<T>(w, 8); a.H.yx = A.at<T>(w, 9); a.H.yy = A.at<T>(w, 10); a.H.yz = A.at<T>(w, 11);
   a.H.zx = A.at<T>(w, 12); a.H.zy = A.at<T>(w, 13); a.H.zz = A.at<T>(w, 14);
   a.M.xx = A.at<T>(w, 15); a.M.xy = A.at<T>(w, 16); a.M.xz = A.at<T>(w, 17); a.M.yy = A.at<T>(w, 18); a.M.yz = A.at<T>(w, 19); a.M.zz = A.at<T>(w, 20);
   p = ld_sv<T>(A, w, AC_PA);
-  r.m = A.at<T>(w, AC_IC + 0); r.h = ld_v3<T>(A, w, AC_IC + 1);
-  r.I.xx = A.at<T>(w, AC_IC + 4); r.I.xy = A.at<T>(w, AC_IC + 5); r.I.xz = A.at<T>(w, AC_IC + 6);
-  r.I.yy = A.at<T>(w, AC_IC + 7); r.I.yz = A.at<T>(w, AC_IC + 8); r.I.zz = A.at<T>(w, AC_IC + 9);
 }
 
-template <typename T> TDS_D Rbi<T> model_rbi(const float* r) {
+template <typename T> TDS_D Rbi<T> model_rbi(const double* r) {
   Rbi<T> o;
   o.m = T(r[0]); o.h = v3<T>(T(r[1]), T(r[2]), T(r[3]));
   o.I.xx = T(r[4]); o.I.xy = T(r[5]); o.I.xz = T(r[6]); o.I.yy = T(r[7]); o.I.yz = T(r[8]); o.I.zz = T(r[9]);
@@ -206,8 +211,10 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     const int off = M.floating ? 6 : 0;
     for (int k = off; k < n; ++k) A.at<float>(M.w_tau, k) = io.tau_in[(size_t)(k - off) * ns + e];
   }
-  for (int s = 0; s < M.n_acc; ++s)
-    for (int k = 0; k < AC_SIZE; ++k) A.at<RA>(M.w_acc + s * AC_SIZE * (int)(sizeof(RA) / 4), k) = RA(0);
+  for (int s = 0; s < M.n_acc; ++s) {
+    for (int k = 0; k < AC_NRA; ++k) A.at<RA>(M.w_acc + s * M.acc_words, k) = RA(0);
+    for (int k = 0; k < AC_NIC; ++k) A.at<RC>(M.w_acc + s * M.acc_words + M.acc_ic_word, k) = RC(0);
+  }
 
   // ---- pass 1: kinematics root -> leaf (kinematics.hpp:18-148) -----------------------------------
   Xf<RC> Xw_prev;
@@ -301,21 +308,25 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   // ---- pass 2: leaf -> root.  ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ---
   Abi<RA> cA;
   Sv<RA> cP;
-  Rbi<RA> cC;
+  Rbi<RC> cC;   // composite rigid-body inertia (CRBA) is carried in RC: see the precision note above
+  if (any_contact)
+    for (int k = 0; k < n * (n + 1) / 2; ++k) A.at<RC>(M.w_M, k) = RC(0);
   for (int i = n_links - 1; i >= 0; --i) {
     const int p = M.parent[i];
     const int fl = M.flags[i];
     const int wl = M.w_link + i * LW;
     const Xf<RA> Xp = ld_xf<RA>(A, wl);
     const Sv<RA> v = ld_sv<RA>(A, wl, LK_VC);
-    Rbi<RA> Ic = model_rbi<RA>(M.rbi[i]);
-    Abi<RA> Ai = abi_from_rbi(Ic);
-    Sv<RA> pA = cross_mf(v, rbi_mul(Ic, v));        // kinematics.hpp:132
+    const Rbi<RA> rb = model_rbi<RA>(M.rbi[i]);
+    Rbi<RC> Ic = model_rbi<RC>(M.rbi[i]);
+    Abi<RA> Ai = abi_from_rbi(rb);
+    Sv<RA> pA = cross_mf(v, rbi_mul(rb, v));        // kinematics.hpp:132
     if (fl & TDS_LF_CHILD_ADJ) { abi_add(Ai, cA); pA = pA + cP; rbi_add(Ic, cC); }
     if (M.acc_slot[i] >= 0) {
-      Abi<RA> sa; Sv<RA> sp; Rbi<RA> sc;
-      acc_load<RA>(A, M.w_acc + M.acc_slot[i] * AC_SIZE * (int)(sizeof(RA) / 4), sa, sp, sc);
-      abi_add(Ai, sa); pA = pA + sp; rbi_add(Ic, sc);
+      Abi<RA> sa; Sv<RA> sp;
+      const int ws = M.w_acc + M.acc_slot[i] * M.acc_words;
+      acc_load<RA>(A, ws, sa, sp);
+      abi_add(Ai, sa); pA = pA + sp; rbi_add(Ic, acc_load_rbi<RC>(A, ws + M.acc_ic_word));
     }
     Sv<RA> pa = pA;
     Abi<RA> Ia = Ai;
@@ -357,34 +368,37 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       pa.bot = pA.bot + Iac.bot + U.bot * uD;
       // CRBA column of this joint, mass_matrix.hpp:86-111 (only needed when some lane has contacts)
       if (any_contact) {
-        Sv<RA> F = rbi_mul(Ic, S);
-        A.at<RC>(M.w_M, tri(qdi, qdi)) = RC(dot(S, F));
+        const Sv<RC> Sc = link_S<RC>(M, i);
+        Sv<RC> F = rbi_mul(Ic, Sc);
+        A.at<RC>(M.w_M, tri(qdi, qdi)) = dot(Sc, F);
         int j = i;
-        Xf<RA> Xj = Xp;
+        Xf<RC> Xj; Xj.R = cvt<RC>(Xp.R); Xj.t = cvt<RC>(Xp.t);
         while (true) {
           F = xf_apply_force(Xj, F);
           j = M.parent[j];
           if (j < 0) break;
-          if (!(M.flags[j] & TDS_LF_FIXED)) A.at<RC>(M.w_M, tri(qdi, M.qd_idx[j])) = RC(dot(F, link_S<RA>(M, j)));
-          Xj = ld_xf<RA>(A, M.w_link + j * LW);
+          if (!(M.flags[j] & TDS_LF_FIXED)) A.at<RC>(M.w_M, tri(qdi, M.qd_idx[j])) = dot(F, link_S<RC>(M, j));
+          const Xf<RA> Xa = ld_xf<RA>(A, M.w_link + j * LW);
+          Xj.R = cvt<RC>(Xa.R); Xj.t = cvt<RC>(Xa.t);
         }
         if (M.floating) {
-          A.at<RC>(M.w_M, tri(qdi, 0)) = RC(F.top.x); A.at<RC>(M.w_M, tri(qdi, 1)) = RC(F.top.y); A.at<RC>(M.w_M, tri(qdi, 2)) = RC(F.top.z);
-          A.at<RC>(M.w_M, tri(qdi, 3)) = RC(F.bot.x); A.at<RC>(M.w_M, tri(qdi, 4)) = RC(F.bot.y); A.at<RC>(M.w_M, tri(qdi, 5)) = RC(F.bot.z);
+          A.at<RC>(M.w_M, tri(qdi, 0)) = F.top.x; A.at<RC>(M.w_M, tri(qdi, 1)) = F.top.y; A.at<RC>(M.w_M, tri(qdi, 2)) = F.top.z;
+          A.at<RC>(M.w_M, tri(qdi, 3)) = F.bot.x; A.at<RC>(M.w_M, tri(qdi, 4)) = F.bot.y; A.at<RC>(M.w_M, tri(qdi, 5)) = F.bot.z;
         }
       }
     }
     // propagate to the parent: register carry along chains, accumulator at branch points
     const Abi<RA> dA = xt_abi_x(Xp, Ia);               // :187-189
     const Sv<RA> dP = xf_apply_force(Xp, pa);          // :181
-    const Rbi<RA> dC = xt_rbi_x(Xp, Ic);               // mass_matrix.hpp:45-46
+    Rbi<RC> dC = Ic;
+    if (any_contact) { Xf<RC> Xc; Xc.R = cvt<RC>(Xp.R); Xc.t = cvt<RC>(Xp.t); dC = xt_rbi_x(Xc, Ic); }  // mass_matrix.hpp:45-46
     if (fl & TDS_LF_PARENT_ADJ) { cA = dA; cP = dP; cC = dC; }
     else {
       const int slot = (p >= 0) ? M.acc_slot[p] : M.base_acc;
       if (slot >= 0) {
-        const int w = M.w_acc + slot * AC_SIZE * (int)(sizeof(RA) / 4);
+        const int w = M.w_acc + slot * M.acc_words;
         acc_add_abi<RA>(A, w, dA, dP);
-        acc_add_rbi<RA>(A, w, dC);
+        acc_add_rbi<RC>(A, w + M.acc_ic_word, dC);
       }
     }
   }
@@ -393,8 +407,8 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   Sv<RA> a_prev;
   Sv<RC> base_acc;
   if (M.floating) {
-    Rbi<RA> Ib = model_rbi<RA>(M.base_rbi);
-    Abi<RA> Ab = abi_from_rbi(Ib);
+    Rbi<RC> Ib = model_rbi<RC>(M.base_rbi);
+    Abi<RA> Ab = abi_from_rbi(model_rbi<RA>(M.base_rbi));
     // gyroscopic bias, kinematics.hpp:54-61
     M3<RA> Rb = cvt<RA>(baseR);
     M3<RA> Ic0;
@@ -405,14 +419,15 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     Sv<RA> pb; pb.top = cross(v_base.top, mul(Iw, v_base.top)); pb.bot = v3<RA>(RA(0), RA(0), RA(0));
     if (n_links > 0 && M.parent[0] < 0) { abi_add(Ab, cA); pb = pb + cP; rbi_add(Ib, cC); }
     if (M.base_acc >= 0) {
-      Abi<RA> sa; Sv<RA> sp; Rbi<RA> sc;
-      acc_load<RA>(A, M.w_acc + M.base_acc * AC_SIZE * (int)(sizeof(RA) / 4), sa, sp, sc);
-      abi_add(Ab, sa); pb = pb + sp; rbi_add(Ib, sc);
+      Abi<RA> sa; Sv<RA> sp;
+      const int ws = M.w_acc + M.base_acc * M.acc_words;
+      acc_load<RA>(A, ws, sa, sp);
+      abi_add(Ab, sa); pb = pb + sp; rbi_add(Ib, acc_load_rbi<RC>(A, ws + M.acc_ic_word));
     }
     if (any_contact) {  // mass_matrix.hpp:114-120: base block = composite inertia
       const RC z = RC(0);
-      A.at<RC>(M.w_M, tri(0, 0)) = RC(Ib.I.xx); A.at<RC>(M.w_M, tri(1, 0)) = RC(Ib.I.xy); A.at<RC>(M.w_M, tri(1, 1)) = RC(Ib.I.yy);
-      A.at<RC>(M.w_M, tri(2, 0)) = RC(Ib.I.xz); A.at<RC>(M.w_M, tri(2, 1)) = RC(Ib.I.yz); A.at<RC>(M.w_M, tri(2, 2)) = RC(Ib.I.zz);
+      A.at<RC>(M.w_M, tri(0, 0)) = Ib.I.xx; A.at<RC>(M.w_M, tri(1, 0)) = Ib.I.xy; A.at<RC>(M.w_M, tri(1, 1)) = Ib.I.yy;
+      A.at<RC>(M.w_M, tri(2, 0)) = Ib.I.xz; A.at<RC>(M.w_M, tri(2, 1)) = Ib.I.yz; A.at<RC>(M.w_M, tri(2, 2)) = Ib.I.zz;
       // rows 3..5: [H^T | M], H = h x
       A.at<RC>(M.w_M, tri(3, 0)) = z;            A.at<RC>(M.w_M, tri(3, 1)) = RC(Ib.h.z);  A.at<RC>(M.w_M, tri(3, 2)) = RC(-Ib.h.y);
       A.at<RC>(M.w_M, tri(4, 0)) = RC(-Ib.h.z);  A.at<RC>(M.w_M, tri(4, 1)) = z;           A.at<RC>(M.w_M, tri(4, 2)) = RC(Ib.h.x);

@@ -25,6 +25,7 @@ struct DevModel {
   // scratch arena layout, in 4-byte words per environment (see tds_step.cu)
   int w_q, w_qd, w_tau, w_link, w_acc, w_xw, w_M, w_w, w_con, w_Y, w_total;
   int link_words;    // words per link in the per-link region
+  int acc_words, acc_ic_word;  // accumulator slot stride / offset of its Ic part (words)
   int parent[TDS_MAX_LINKS];
   int jtype[TDS_MAX_LINKS];
   int q_idx[TDS_MAX_LINKS];
@@ -33,10 +34,10 @@ struct DevModel {
   int acc_slot[TDS_MAX_LINKS];   // accumulator slot receiving non-adjacent children (-1: none)
   double XT[TDS_MAX_LINKS][12];  // X_T: R row-major [9], t [3]
   double axis[TDS_MAX_LINKS][3];
-  float rbi[TDS_MAX_LINKS][10];  // mass, h = m*com [3], I about link origin (xx,xy,xz,yy,yz,zz)
+  double rbi[TDS_MAX_LINKS][10]; // mass, h = m*com [3], I about link origin (xx,xy,xz,yy,yz,zz)
   float stiffness[TDS_MAX_LINKS];
   float damping[TDS_MAX_LINKS];
-  float base_rbi[10];
+  double base_rbi[10];
   float base_inertia_com[9];     // base_rbi.inertia (about com), for the gyroscopic term
   // collision geoms of the robot in the reference's enumeration order
   int g_link[TDS_MAX_GEOMS];

@@ -386,6 +386,12 @@ extern "C" int tds_b200_urdf_to_model(const char* urdf, const char* plane_urdf, 
   for (int i = 0; i < n_links; ++i) add_shapes(i, *ordered[i]);
   const int n_geoms = (int)(geoms.size() / TDSM_GEOM), n_vis = (int)(vis.size() / TDSM_VIS);
   const int total = TDSM_HEADER + TDSM_BASE + n_links * TDSM_LINK + n_geoms * TDSM_GEOM + n_vis * TDSM_VIS;
+  for (int i = 0; i < n_links; ++i) {  // validate before sizing so that errors surface on the first call
+    const UJoint& j = *ojoints[i];
+    if (j.type == TDSJ_SPHERICAL) { g_error = "spherical joints are not supported (joint " + j.name + ")"; return -7; }
+    if ((j.type == TDSJ_REVOLUTE_AXIS || j.type == TDSJ_PRISMATIC_AXIS) &&
+        j.axis.v[0] == 0.0 && j.axis.v[1] == 0.0 && j.axis.v[2] == 0.0) { g_error = "zero joint axis on " + j.name; return -6; }
+  }
   if (!out || cap < total) return total;
   memset(out, 0, sizeof(double) * total);
   double* b = out + TDSM_HEADER;
