@@ -17,6 +17,22 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libtds_ref.so")
 _lib = None
 
 
+class _quiet_stdout:
+    """The reference prints "Loading URDF ..." on stdout from C++; keep it out of JSON-producing callers."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        os.close(self._null)
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -84,7 +100,8 @@ class RefSim:
 
     @classmethod
     def from_urdf(cls, urdf, plane_urdf=None, floating=False, prec=64):
-        h = lib().tdsref_create_from_urdf((plane_urdf or "").encode(), urdf.encode(), int(floating), prec)
+        with _quiet_stdout():
+            h = lib().tdsref_create_from_urdf((plane_urdf or "").encode(), urdf.encode(), int(floating), prec)
         return cls(h)
 
     @classmethod
@@ -161,7 +178,8 @@ class LaikagoRef:
 
     def __init__(self, num_threads=1):
         L = lib()
-        self._h = L.tdsref_laikago_create(num_threads)
+        with _quiet_stdout():
+            self._h = L.tdsref_laikago_create(num_threads)
         self.input_dim = L.tdsref_laikago_input_dim(self._h)
         self.output_dim = L.tdsref_laikago_output_dim(self._h)
         self.num_threads = L.tdsref_laikago_num_threads(self._h)

@@ -1,0 +1,25 @@
+"""Per-phase cycle breakdown of the step kernel (clock64 stamps, lane 0 of every warp)."""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import tds_b200, tds_b200.workloads as wl
+n = 4096
+sim = tds_b200.laikago_sim(n)
+w = wl.laikago(n)
+sim.env_set_state(w["q"], w["qd"])
+act = sim.alloc(12)
+for _ in range(200):
+    sim.env_step_device(act)
+L = tds_b200.lib()
+L.tds_b200_debug_phase_clocks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+nw = L.tds_b200_debug_phase_clocks(sim._h, 1, None, 0)
+for _ in range(3):
+    sim.env_step_device(act)
+buf = np.zeros((nw, 16), dtype=np.int64)
+L.tds_b200_debug_phase_clocks(sim._h, 1, buf.ctypes.data, nw)
+names = ["load+PD", "pass1 FK", "contacts", "pass2 ABA+CRBA", "base", "pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate", "writeback"]
+d = np.diff(buf[:, :13], axis=1).astype(np.float64)
+tot = (buf[:, 12] - buf[:, 0]).astype(np.float64)
+print("cycles per warp: total median %.0f (min %.0f max %.0f)" % (np.median(tot), tot.min(), tot.max()))
+for k, nm in enumerate(names):
+    print(f"  {nm:16s} {np.median(d[:, k]):9.0f} cycles  {100 * np.median(d[:, k]) / np.median(tot):5.1f}%")

@@ -130,6 +130,7 @@ struct tds_b200_sim {
   size_t stage_host_bytes = 0;
   cudaStream_t stream = nullptr;
   int max_smem_optin = 0;
+  long long* phase_clk = nullptr;  // profiling only (tds_b200_debug_phase_clocks)
 };
 
 static int ensure_stage(tds_b200_sim* s, size_t dev_bytes, size_t host_bytes) {
@@ -229,7 +230,7 @@ void tds_b200_destroy(tds_b200_sim* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->q); cudaFree(s->qd); cudaFree(s->act); cudaFree(s->qdd); cudaFree(s->reward); cudaFree(s->done);
-  cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev);
+  cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk);
   if (s->stage_host) cudaFreeHost(s->stage_host);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -290,6 +291,7 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.q_in = q_in; io.qd_in = qd_in; io.tau_in = tau_or_action;
   io.q_out = q_out; io.qd_out = qd_out; io.qdd_out = qdd_out;
   io.reward = reward; io.done = done; io.contact_dist = contact_dist; io.link_xf = link_xf;
+  io.phase_clk = s->phase_clk;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   const int use_smem = s->smem_ok[p] ? 1 : 0;
@@ -382,6 +384,23 @@ int tds_b200_env_step_device(tds_b200_sim* s, const float* actions, float* rewar
   if (!s) return -1;
   return tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, actions, s->q, s->qd, nullptr, reward, done,
                               nullptr, nullptr, stream);
+}
+
+// Profiling aid (not part of the drop-in surface): enable per-warp clock64() stamps at the phase
+// boundaries of the step kernel; out (host) receives [n_warps][16] stamps of the last step.
+int tds_b200_debug_phase_clocks(tds_b200_sim* s, int enable, long long* out_host, int cap_warps) {
+  if (!s) return -1;
+  const int nw = s->ns / 32;
+  if (enable && !s->phase_clk) {
+    CUDA_TRY(cudaMalloc((void**)&s->phase_clk, sizeof(long long) * 16 * nw));
+    CUDA_TRY(cudaMemset(s->phase_clk, 0, sizeof(long long) * 16 * nw));
+  }
+  if (out_host && s->phase_clk) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out_host, s->phase_clk, sizeof(long long) * 16 * (nw < cap_warps ? nw : cap_warps), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && s->phase_clk) { cudaFree(s->phase_clk); s->phase_clk = nullptr; }
+  return nw;
 }
 
 float* tds_b200_env_q(tds_b200_sim* s) { return s ? s->q : nullptr; }

@@ -186,6 +186,9 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   }
   const int ns = io.n_stride;
   const int n_links = M.n_links;
+  int phase_id = 0;
+#define TDS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[(size_t)(env >> 5) * 16 + (phase_id++)] = clock64(); } while (0)
+  TDS_PHASE();
   const int n = M.n_qd;
   const RA dtA = RA(P.dt);
 
@@ -216,6 +219,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     for (int k = 0; k < AC_NIC; ++k) A.at<RC>(M.w_acc + s * M.acc_words + M.acc_ic_word, k) = RC(0);
   }
 
+  TDS_PHASE();  // 1: state loaded, PD done
   // ---- pass 1: kinematics root -> leaf (kinematics.hpp:18-148) -----------------------------------
   Xf<RC> Xw_prev;
   Sv<RA> v_prev;
@@ -270,6 +274,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     v_prev = v;
   }
 
+  TDS_PHASE();  // 2: pass 1 done
   // ---- contact detection (world.hpp:206-282, contact_point.hpp:97-161) ----------------------------
   // Every sphere / capsule end emits one candidate point in the reference; only penetrating points
   // produce non-zero LCP rows, so only those are recorded for the solve.
@@ -304,6 +309,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     }
   }
   const bool any_contact = __any_sync(0xffffffffu, n_active > 0);
+  TDS_PHASE();  // 3: contacts detected
 
   // ---- pass 2: leaf -> root.  ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ---
   Abi<RA> cA;
@@ -403,6 +409,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     }
   }
 
+  TDS_PHASE();  // 4: pass 2 (ABA + CRBA) done
   // ---- base acceleration (forward_dynamics.hpp:218-243) -----------------------------------------
   Sv<RA> a_prev;
   Sv<RC> base_acc;
@@ -473,6 +480,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   a_prev.bot = cvt<RA>(base_acc.bot);
   const Sv<RA> a_base = a_prev;
 
+  TDS_PHASE();  // 5: base done
   // ---- pass 3: root -> leaf accelerations (forward_dynamics.hpp:245-302) + integrate_euler_qdd ----
   for (int i = 0; i < n_links; ++i) {
     const int p = M.parent[i];
@@ -508,6 +516,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       else A.at<float>(M.w_qd, k) = (float)(RC(A.at<float>(M.w_qd, k)) + qb[k] * RC(P.dt));
     }
   }
+  TDS_PHASE();  // 6: pass 3 done
   if (mode == MODE_FD) return;
 
   // ---- contact solve ------------------------------------------------------------------------------
@@ -527,6 +536,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
         A.at<RC>(M.w_M, tri(i, j)) = s * inv;
       }
     }
+    TDS_PHASE();  // 7: Cholesky done
     const int max_active = __reduce_max_sync(0xffffffffu, n_active);
     const V3<RC> nb = v3<RC>(RC(-M.plane_n[0]), RC(-M.plane_n[1]), RC(-M.plane_n[2]));  // world_normal_on_b
     const V3<RC> f1 = v3<RC>(RC(M.fr1[0]), RC(M.fr1[1]), RC(M.fr1[2]));
@@ -584,6 +594,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
         }
       }
     }
+    TDS_PHASE();  // 8: Jacobians + Y done
     // matrix-free projected Gauss-Seidel on w = Y p; row order normals | friction-1 | friction-2
     // (solve_pgs, mb_constraint_solver.hpp:101-142; bounds :417-436)
     for (int k = 0; k < n; ++k) A.at<RC>(M.w_w, k) = RC(0);
@@ -614,6 +625,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
         }
       }
     }
+    TDS_PHASE();  // 9: PGS done
     // qd_b -= M^-1 Jc^T p = L^-T w   (mb_constraint_solver.hpp:476-497)
     for (int i = n - 1; i >= 0; --i) {
       RC s = A.at<RC>(M.w_w, i);
@@ -624,6 +636,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     }
   }
 
+  TDS_PHASE();  // 10: impulses applied
   // ---- integrate_euler with qdd = 0 (integrator.hpp:10-133) ---------------------------------------
   RC up_z = RC(1);
   if (M.floating) {
@@ -648,6 +661,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     A.at<float>(M.w_q, qi) = (float)(RC(A.at<float>(M.w_q, qi)) + RC(A.at<float>(M.w_qd, M.qd_idx[i])) * RC(P.dt));
   }
 
+  TDS_PHASE();  // 11: integrated
   // ---- write back -----------------------------------------------------------------------------------
   if (live) {
     for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = A.at<float>(M.w_q, k);
@@ -684,7 +698,11 @@ extern "C" int tds_launch_step(const DevModel* M, const SimParams* P, const EnvP
 #define TDS_LAUNCH(RA, RC, SM)                                                                          \
   do {                                                                                                  \
     auto k = tds_step_kernel<RA, RC, SM>;                                                               \
-    if (smem > 48 * 1024) err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    static size_t smem_set = 0; /* opt-in once per instantiation, not per launch */                     \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                          \
+      err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      if (err == cudaSuccess) smem_set = smem;                                                          \
+    }                                                                                                   \
     if (err == cudaSuccess) {                                                                           \
       k<<<blocks, threads, smem, stream>>>(*M, *P, *E, *io, mode, use_pd, gscratch);                    \
       err = cudaGetLastError();                                                                         \

@@ -85,5 +85,6 @@ struct StepIO {
   float* reward; float* done;           // may be null
   float* contact_dist;                  // [n_contact_points][n] or null
   float* link_xf;                       // [n_links*12][n] world transforms of the step's FK, or null
+  long long* phase_clk;                 // [n_warps][16] clock64() stamps at phase boundaries (profiling), or null
   int n; int n_stride;
 };
