@@ -170,7 +170,7 @@ def main():
     n = args.envs
     K, W = args.steps, max(args.warmup, 3)
 
-    sim = tds_b200.laikago_sim(n, device=local_rank, precision=args.precision)
+    sim = tds_b200.laikago_sim(n, device=local_rank, precision=args.precision, auto_reset=True)
     w = wl.laikago(n, seed=wl.SEED + rank)
     sim.env_set_state(w["q"], w["qd"])
     ns = sim.n_stride

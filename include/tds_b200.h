@@ -58,6 +58,12 @@ int tds_b200_set_params(tds_b200_sim* sim, double dt, const double gravity[3], d
 int tds_b200_set_env(tds_b200_sim* sim, int n_act, const double* initial_poses, int start_link, double kp,
                      double kd, double max_force, double action_limit, int reward_kind);
 
+/* VectorizedEnvironment's auto_reset_when_done (examples/ars/ars_vectorized_environment.h:262-283) on the
+ * device: an environment that reports done is put back to reset_q[n_q] with zero velocity at the end of
+ * that step (the reward/done outputs of the step are kept).  The host-side reset() of the Python mirror adds
+ * the reference's joint noise and settle steps (laikago_environment2.h:63-116). */
+int tds_b200_set_auto_reset(tds_b200_sim* sim, int enable, const double* reset_q);
+
 int tds_b200_set_precision(tds_b200_sim* sim, int precision);
 
 /* dims[0..7] = n_envs, n_stride, n_q (MultiBody::dof), n_qd (dof_qd), n_tau (dof_actuated), n_links,

@@ -160,3 +160,20 @@ def test_full_size_properties():
     torch.cuda.synchronize()
     assert np.array_equal(q[:, :n].T.cpu().numpy().astype(np.float64), a["q"])
     assert np.array_equal(qd[:, :n].T.cpu().numpy().astype(np.float64), a["qd"])
+
+
+def test_device_auto_reset():
+    """An environment that reports done is put back to the reset pose (auto_reset_when_done)."""
+    n = 64
+    sim = tds_b200.laikago_sim(n, auto_reset=True)
+    w = wl.laikago(n)
+    q = w["q"].copy()
+    q[::2, 2] = 0.1            # below the z < 0.2 termination height -> done
+    sim.env_set_state(q, w["qd"])
+    obs = np.zeros((n, 36), dtype=np.float32); rew = np.zeros(n, dtype=np.float32); done = np.zeros(n, dtype=np.float32)
+    sim.env_step_host(np.zeros((n, 12), dtype=np.float32), obs, rew, done)
+    assert np.array_equal(done[::2], np.ones(n // 2, dtype=np.float32)) and not done[1::2].any()
+    assert np.all(rew[::2] == 0)
+    rp = tds_b200.envs.laikago_reset_pose().astype(np.float32)
+    assert np.array_equal(obs[::2, :18], np.tile(rp, (n // 2, 1))) and not obs[::2, 18:].any()
+    assert np.abs(obs[1::2, 2] - 0.48).max() < 1e-3

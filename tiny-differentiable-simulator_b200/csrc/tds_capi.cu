@@ -182,10 +182,10 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     return nullptr;
   }
   cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const int sizes[3][2] = {{4, 8}, {8, 8}, {4, 4}};
+  const int sizes[3][3] = {{4, 8, 4}, {8, 8, 8}, {4, 4, 4}};  // sizeof(RA, RC, RS) per precision mode
   for (int p = 0; p < 3; ++p) {
     s->dm[p] = base;
-    tds_build_layout(&s->dm[p], sizes[p][0], sizes[p][1], -1);
+    tds_build_layout(&s->dm[p], sizes[p][0], sizes[p][1], sizes[p][2], -1);
     size_t per_warp = (size_t)s->dm[p].w_total * 32 * 4;
     s->smem_ok[p] = per_warp <= (size_t)s->max_smem_optin;
     // several warps per block only help when many blocks would otherwise be needed per SM
@@ -264,7 +264,19 @@ int tds_b200_set_env(tds_b200_sim* s, int n_act, const double* initial_poses, in
     ++k;
   }
   if (k != n_act) { set_err("model has fewer actuated links than n_act"); return -2; }
+  E.auto_reset = s->E.auto_reset;
+  memcpy(E.reset_q, s->E.reset_q, sizeof(E.reset_q));
   s->E = E;
+  return 0;
+}
+
+int tds_b200_set_auto_reset(tds_b200_sim* s, int enable, const double* reset_q) {
+  if (!s) return -1;
+  const DevModel& M = s->dm[0];
+  if (enable && !reset_q) { set_err("auto-reset needs a reset pose"); return -1; }
+  s->E.auto_reset = enable ? 1 : 0;
+  if (reset_q)
+    for (int k = 0; k < M.n_q; ++k) s->E.reset_q[k] = (float)reset_q[k];
   return 0;
 }
 

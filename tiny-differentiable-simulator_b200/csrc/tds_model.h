@@ -126,8 +126,8 @@ TDS_HOST_INLINE int tds_num_contact_points(const DevModel* D) { return D->max_co
 
 // Per-environment scratch layout in 4-byte words.  size_ra / size_rc = sizeof of the ABA / contact
 // scalar.  The Y rows of the contact solve alias the per-link ABA region (dead after pass 3).
-TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int max_contacts) {
-  const int ra = size_ra / 4, rc = size_rc / 4;
+TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int size_rs, int max_contacts) {
+  const int ra = size_ra / 4, rc = size_rc / 4, rs = size_rs / 4;
   const int n = D->n_qd;
   if (max_contacts >= 0 && max_contacts < D->max_contacts) D->max_contacts = max_contacts;
   int w = 0;
@@ -137,17 +137,23 @@ TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int
   D->w_tau = w; w += n;
   w = even(w);
   D->acc_ic_word = even(27 * ra);
-  D->acc_words = even(D->acc_ic_word + 10 * rc);
+  D->acc_words = even(D->acc_ic_word + 10 * rs);
   D->w_acc = w; w += D->n_acc * D->acc_words;
   w = even(w);
   D->w_xw = w; w += (D->n_links + 1) * 12 * rc;
-  D->w_M = w; w += (n * (n + 1) / 2) * rc;
-  D->w_w = w; w += n * rc;
-  D->w_con = w; w += D->max_contacts * 11 * rc;
+  D->w_con = w; w += D->max_contacts * 5 * rc;
+  w = even(w);
+  D->w_M = w; w += (n * (n + 1) / 2) * rs;
+  w = even(w);
+  D->w_invd = w; w += n * rs;
+  w = even(w);
+  D->w_w = w; w += n * rs;
+  w = even(w);
+  D->w_conS = w; w += D->max_contacts * 6 * rs;
   w = even(w);
   D->link_words = 26 * ra;
   const int link_region = D->n_links * D->link_words;
-  const int y_region = 3 * D->max_contacts * n * rc;
+  const int y_region = 3 * D->max_contacts * n * rs;
   D->w_link = w;
   D->w_Y = w;
   w += link_region > y_region ? link_region : y_region;

@@ -22,8 +22,10 @@
 //     w = Y p (A = Y^T Y + cfm is never formed), dqd = L^-T w;
 //   * non-penetrating contact rows (masked to zero by the reference, :285-291) are skipped - their
 //     impulse is exactly 0 in the reference's sweep as well;
-//   * mixed precision: ABA in RA (fp32), kinematics + contact solve in RC (fp64) because
-//     erp/dt = 200 amplifies fp32 position round-off beyond the 1e-5 parity budget.
+//   * three scalar types: RA for the ABA, RC for kinematics / contact geometry, RS for CRBA + the
+//     contact solve.  Default "mixed" = (fp32, fp64, fp32): erp/dt = 200 amplifies fp32 *position*
+//     round-off beyond the 1e-5 parity budget, so world transforms, contact distances and the LCP
+//     right-hand side are fp64; M is well conditioned (scaled cond ~10 for Laikago), fp32 suffices there.
 #include <cuda_runtime.h>
 #include <stdio.h>
 
@@ -74,8 +76,8 @@ enum { LK_XP = 0, LK_VC = 12, LK_U = 18, LK_INVD = 24, LK_u = 25, LK_SIZE = 26 }
 // accumulator slot: abi 21 + pA 6 (units of RA), then Ic 10 (units of RC) at word offset M.acc_ic_word;
 // the slot stride in words is M.acc_words (both computed on the host, tds_build_layout).
 enum { AC_ABI = 0, AC_PA = 21, AC_NRA = 27, AC_NIC = 10 };
-// contact record (units of RC): pb 3, dist, link, b[3], x[3]
-enum { CN_PB = 0, CN_DIST = 3, CN_LINK = 4, CN_B = 5, CN_X = 8, CN_SIZE = 11 };
+// contact record, RC part: pb 3, dist, link (the RS part b[3], x[3] lives at M.w_conS)
+enum { CN_PB = 0, CN_DIST = 3, CN_LINK = 4, CN_SIZE = 5 };
 
 template <typename T> TDS_D void acc_add_abi(const Arena& A, int w, const Abi<T>& a, const Sv<T>& p) {
   T* dummy = nullptr; (void)dummy;
@@ -163,7 +165,23 @@ TDS_D int tri(int r, int c) { return r * (r + 1) / 2 + c; }  // lower triangle, 
 
 enum StepMode { MODE_FD = 0, MODE_NOCONTACT = 1, MODE_FULL = 2 };
 
-template <typename RA, typename RC, bool SMEM>
+// ---- strided small-vector helpers for the contact solve (element k of a vector lives at p[k*s]) ----
+// Dot products use four independent accumulators so that consecutive shared-memory loads and FMAs
+// overlap (a single dependent chain costs one LDS + FMA latency per element on a lone warp).
+template <typename T> TDS_D T sdot(const T* a, const T* b, int s, int len) {
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+  int k = 0;
+  for (; k + 3 < len; k += 4) {
+    s0 += a[k * s] * b[k * s];
+    s1 += a[(k + 1) * s] * b[(k + 1) * s];
+    s2 += a[(k + 2) * s] * b[(k + 2) * s];
+    s3 += a[(k + 3) * s] * b[(k + 3) * s];
+  }
+  for (; k < len; ++k) s0 += a[k * s] * b[k * s];
+  return (s0 + s1) + (s2 + s3);
+}
+
+template <typename RA, typename RC, typename RS, bool SMEM>
 __global__ void __launch_bounds__(128, 1)
 tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimParams P,
                 const __grid_constant__ EnvParams E, const StepIO io, const int mode, const int use_pd,
@@ -184,6 +202,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     A.stride = io.n_stride;
     A.col = e;
   }
+  const int ST = A.stride;
   const int ns = io.n_stride;
   const int n_links = M.n_links;
   int phase_id = 0;
@@ -191,11 +210,15 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   TDS_PHASE();
   const int n = M.n_qd;
   const RA dtA = RA(P.dt);
+  constexpr int RAW = (int)(sizeof(RA) / 4), RCW = (int)(sizeof(RC) / 4), RSW = (int)(sizeof(RS) / 4);
+  float* const qv = &A.at<float>(M.w_q, 0);     // q, qd, tau live as fp32 (the HBM state type)
+  float* const qdv = &A.at<float>(M.w_qd, 0);
+  float* const tauv = &A.at<float>(M.w_tau, 0);
 
   // ---- load state ------------------------------------------------------------------------------
-  for (int k = 0; k < M.n_q; ++k) A.at<float>(M.w_q, k) = io.q_in[(size_t)k * ns + e];
-  for (int k = 0; k < n; ++k) A.at<float>(M.w_qd, k) = io.qd_in[(size_t)k * ns + e];
-  for (int k = 0; k < n; ++k) A.at<float>(M.w_tau, k) = 0.f;
+  for (int k = 0; k < M.n_q; ++k) qv[k * ST] = io.q_in[(size_t)k * ns + e];
+  for (int k = 0; k < n; ++k) qdv[k * ST] = io.qd_in[(size_t)k * ns + e];
+  for (int k = 0; k < n; ++k) tauv[k * ST] = 0.f;
   if (use_pd) {
     // PD torques, locomotion_contact_simulation.h:168-258
     for (int k = 0; k < E.n_act; ++k) {
@@ -204,32 +227,32 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       a = fminf(a, E.action_limit);
       a = fmaxf(a, -E.action_limit);
       const float q_des = E.initial_poses[k] + a;
-      const float qa = A.at<float>(M.w_q, M.q_idx[li]);
-      const float qda = A.at<float>(M.w_qd, M.qd_idx[li]);
+      const float qa = qv[M.q_idx[li] * ST];
+      const float qda = qdv[M.qd_idx[li] * ST];
       float f = E.kp * (q_des - qa) + E.kd * (0.f - qda);
       f = fminf(fmaxf(f, -E.max_force), E.max_force);
-      A.at<float>(M.w_tau, M.qd_idx[li]) = f;
+      tauv[M.qd_idx[li] * ST] = f;
     }
   } else if (io.tau_in) {
     const int off = M.floating ? 6 : 0;
-    for (int k = off; k < n; ++k) A.at<float>(M.w_tau, k) = io.tau_in[(size_t)(k - off) * ns + e];
+    for (int k = off; k < n; ++k) tauv[k * ST] = io.tau_in[(size_t)(k - off) * ns + e];
   }
   for (int s = 0; s < M.n_acc; ++s) {
     for (int k = 0; k < AC_NRA; ++k) A.at<RA>(M.w_acc + s * M.acc_words, k) = RA(0);
-    for (int k = 0; k < AC_NIC; ++k) A.at<RC>(M.w_acc + s * M.acc_words + M.acc_ic_word, k) = RC(0);
+    for (int k = 0; k < AC_NIC; ++k) A.at<RS>(M.w_acc + s * M.acc_words + M.acc_ic_word, k) = RS(0);
   }
-
   TDS_PHASE();  // 1: state loaded, PD done
-  // ---- pass 1: kinematics root -> leaf (kinematics.hpp:18-148) -----------------------------------
+
+  // ---- pass 1: kinematics root -> leaf (kinematics.hpp:18-148), positions in RC ---------------------
   Xf<RC> Xw_prev;
   Sv<RA> v_prev;
   M3<RC> baseR = m3_identity<RC>();
   if (M.floating) {
-    baseR = quat_to_matrix<RC>(RC(A.at<float>(M.w_q, 0)), RC(A.at<float>(M.w_q, 1)), RC(A.at<float>(M.w_q, 2)), RC(A.at<float>(M.w_q, 3)));
+    baseR = quat_to_matrix<RC>(RC(qv[0]), RC(qv[ST]), RC(qv[2 * ST]), RC(qv[3 * ST]));
     Xw_prev.R = baseR;
-    Xw_prev.t = v3<RC>(RC(A.at<float>(M.w_q, 4)), RC(A.at<float>(M.w_q, 5)), RC(A.at<float>(M.w_q, 6)));
-    v_prev.top = v3<RA>(RA(A.at<float>(M.w_qd, 0)), RA(A.at<float>(M.w_qd, 1)), RA(A.at<float>(M.w_qd, 2)));
-    v_prev.bot = v3<RA>(RA(A.at<float>(M.w_qd, 3)), RA(A.at<float>(M.w_qd, 4)), RA(A.at<float>(M.w_qd, 5)));
+    Xw_prev.t = v3<RC>(RC(qv[4 * ST]), RC(qv[5 * ST]), RC(qv[6 * ST]));
+    v_prev.top = v3<RA>(RA(qdv[0]), RA(qdv[ST]), RA(qdv[2 * ST]));
+    v_prev.bot = v3<RA>(RA(qdv[3 * ST]), RA(qdv[4 * ST]), RA(qdv[5 * ST]));
   } else {
     Xw_prev.R = baseR;
     Xw_prev.t = v3<RC>(RC(0), RC(0), RC(0));
@@ -239,7 +262,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   const Xf<RC> Xw_base = Xw_prev;
   const Sv<RA> v_base = v_prev;
   st_xf<RC>(A, M.w_xw, Xw_base);
-  const int XWW = 12 * (int)(sizeof(RC) / 4);
+  constexpr int XWW = 12 * RCW;
   const int LW = M.link_words;
   for (int i = 0; i < n_links; ++i) {
     const int p = M.parent[i];
@@ -249,18 +272,18 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     if (fl & TDS_LF_PARENT_ADJ) { Xw_p = Xw_prev; v_p = v_prev; }
     else if (p >= 0) { Xw_p = ld_xf<RC>(A, M.w_xw + (p + 1) * XWW); v_p = ld_sv<RA>(A, M.w_link + p * LW, LK_VC); }
     else { Xw_p = Xw_base; v_p = v_base; }
-    RC qv = (fl & TDS_LF_FIXED) ? RC(0) : RC(A.at<float>(M.w_q, M.q_idx[i]));
-    Xf<RC> Xp = jcalc<RC>(M, i, qv);
+    RC qi = (fl & TDS_LF_FIXED) ? RC(0) : RC(qv[M.q_idx[i] * ST]);
+    Xf<RC> Xp = jcalc<RC>(M, i, qi);
     Xf<RC> Xw = xf_mul(Xw_p, Xp);
     st_xf<RC>(A, M.w_xw + (i + 1) * XWW, Xw);
     Xf<RA> XpA; XpA.R = cvt<RA>(Xp.R); XpA.t = cvt<RA>(Xp.t);
     st_xf<RA>(A, M.w_link + i * LW, XpA);
     Sv<RA> v = xf_apply_motion(XpA, v_p);
     if (!(fl & TDS_LF_FIXED)) {
-      RA qdv = RA(A.at<float>(M.w_qd, M.qd_idx[i]));
+      RA qdi = RA(qdv[M.qd_idx[i] * ST]);
       Sv<RA> S = link_S<RA>(M, i);
-      v.top = v.top + S.top * qdv;
-      v.bot = v.bot + S.bot * qdv;
+      v.top = v.top + S.top * qdi;
+      v.bot = v.bot + S.bot * qdi;
     }
     st_sv<RA>(A, M.w_link + i * LW, LK_VC, v);
     if (io.link_xf && live) {
@@ -273,8 +296,8 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     Xw_prev = Xw;
     v_prev = v;
   }
-
   TDS_PHASE();  // 2: pass 1 done
+
   // ---- contact detection (world.hpp:206-282, contact_point.hpp:97-161) ----------------------------
   // Every sphere / capsule end emits one candidate point in the reference; only penetrating points
   // produce non-zero LCP rows, so only those are recorded for the solve.
@@ -299,7 +322,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
         if (io.contact_dist && live) io.contact_dist[(size_t)pt * ns + e] = (float)dist;
         ++pt;
         if (dist < RC(0) && n_active < M.max_contacts) {
-          const int w = M.w_con + n_active * CN_SIZE * (int)(sizeof(RC) / 4);
+          const int w = M.w_con + n_active * CN_SIZE * RCW;
           st_v3<RC>(A, w, CN_PB, pos - pn * rad);      // world_point_on_b
           A.at<RC>(w, CN_DIST) = dist;
           A.at<RC>(w, CN_LINK) = RC(L);
@@ -312,11 +335,12 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   TDS_PHASE();  // 3: contacts detected
 
   // ---- pass 2: leaf -> root.  ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ---
+  RS* const Mm = &A.at<RS>(M.w_M, 0);          // lower triangle of M, later of its Cholesky factor
   Abi<RA> cA;
   Sv<RA> cP;
-  Rbi<RC> cC;   // composite rigid-body inertia (CRBA) is carried in RC: see the precision note above
+  Rbi<RS> cC;   // composite rigid-body inertia of the CRBA
   if (any_contact)
-    for (int k = 0; k < n * (n + 1) / 2; ++k) A.at<RC>(M.w_M, k) = RC(0);
+    for (int k = 0; k < n * (n + 1) / 2; ++k) Mm[k * ST] = RS(0);
   for (int i = n_links - 1; i >= 0; --i) {
     const int p = M.parent[i];
     const int fl = M.flags[i];
@@ -324,7 +348,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     const Xf<RA> Xp = ld_xf<RA>(A, wl);
     const Sv<RA> v = ld_sv<RA>(A, wl, LK_VC);
     const Rbi<RA> rb = model_rbi<RA>(M.rbi[i]);
-    Rbi<RC> Ic = model_rbi<RC>(M.rbi[i]);
+    Rbi<RS> Ic = model_rbi<RS>(M.rbi[i]);
     Abi<RA> Ai = abi_from_rbi(rb);
     Sv<RA> pA = cross_mf(v, rbi_mul(rb, v));        // kinematics.hpp:132
     if (fl & TDS_LF_CHILD_ADJ) { abi_add(Ai, cA); pA = pA + cP; rbi_add(Ic, cC); }
@@ -332,7 +356,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       Abi<RA> sa; Sv<RA> sp;
       const int ws = M.w_acc + M.acc_slot[i] * M.acc_words;
       acc_load<RA>(A, ws, sa, sp);
-      abi_add(Ai, sa); pA = pA + sp; rbi_add(Ic, acc_load_rbi<RC>(A, ws + M.acc_ic_word));
+      abi_add(Ai, sa); pA = pA + sp; rbi_add(Ic, acc_load_rbi<RS>(A, ws + M.acc_ic_word));
     }
     Sv<RA> pa = pA;
     Abi<RA> Ia = Ai;
@@ -345,15 +369,15 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     } else {
       const Sv<RA> S = link_S<RA>(M, i);
       const int qdi = M.qd_idx[i];
-      const RA qdv = RA(A.at<float>(M.w_qd, qdi));
-      Sv<RA> vJ; vJ.top = S.top * qdv; vJ.bot = S.bot * qdv;
+      const RA qdj = RA(qdv[qdi * ST]);
+      Sv<RA> vJ; vJ.top = S.top * qdj; vJ.bot = S.bot * qdj;
       const Sv<RA> c = cross_mm(v, vJ);               // kinematics.hpp:96-97
       const Sv<RA> U = abi_mul(Ai, S);                // forward_dynamics.hpp:111
       const RA D = dot(S, U);
       const RA invD = RA(1) / D;
-      RA tau = RA(A.at<float>(M.w_tau, qdi));
-      tau -= RA(M.stiffness[i]) * RA(A.at<float>(M.w_q, M.q_idx[i]));
-      tau -= RA(M.damping[i]) * qdv;
+      RA tau = RA(tauv[qdi * ST]);
+      tau -= RA(M.stiffness[i]) * RA(qv[M.q_idx[i] * ST]);
+      tau -= RA(M.damping[i]) * qdj;
       const RA u = tau - dot(S, pA);                  // :129
       st_sv<RA>(A, wl, LK_VC, c);
       st_sv<RA>(A, wl, LK_U, U);
@@ -374,47 +398,48 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       pa.bot = pA.bot + Iac.bot + U.bot * uD;
       // CRBA column of this joint, mass_matrix.hpp:86-111 (only needed when some lane has contacts)
       if (any_contact) {
-        const Sv<RC> Sc = link_S<RC>(M, i);
-        Sv<RC> F = rbi_mul(Ic, Sc);
-        A.at<RC>(M.w_M, tri(qdi, qdi)) = dot(Sc, F);
+        const Sv<RS> Sc = link_S<RS>(M, i);
+        Sv<RS> F = rbi_mul(Ic, Sc);
+        RS* const row = Mm + tri(qdi, 0) * ST;
+        row[qdi * ST] = dot(Sc, F);
         int j = i;
-        Xf<RC> Xj; Xj.R = cvt<RC>(Xp.R); Xj.t = cvt<RC>(Xp.t);
+        Xf<RS> Xj; Xj.R = cvt<RS>(Xp.R); Xj.t = cvt<RS>(Xp.t);
         while (true) {
           F = xf_apply_force(Xj, F);
           j = M.parent[j];
           if (j < 0) break;
-          if (!(M.flags[j] & TDS_LF_FIXED)) A.at<RC>(M.w_M, tri(qdi, M.qd_idx[j])) = dot(F, link_S<RC>(M, j));
+          if (!(M.flags[j] & TDS_LF_FIXED)) row[M.qd_idx[j] * ST] = dot(F, link_S<RS>(M, j));
           const Xf<RA> Xa = ld_xf<RA>(A, M.w_link + j * LW);
-          Xj.R = cvt<RC>(Xa.R); Xj.t = cvt<RC>(Xa.t);
+          Xj.R = cvt<RS>(Xa.R); Xj.t = cvt<RS>(Xa.t);
         }
         if (M.floating) {
-          A.at<RC>(M.w_M, tri(qdi, 0)) = F.top.x; A.at<RC>(M.w_M, tri(qdi, 1)) = F.top.y; A.at<RC>(M.w_M, tri(qdi, 2)) = F.top.z;
-          A.at<RC>(M.w_M, tri(qdi, 3)) = F.bot.x; A.at<RC>(M.w_M, tri(qdi, 4)) = F.bot.y; A.at<RC>(M.w_M, tri(qdi, 5)) = F.bot.z;
+          row[0] = F.top.x; row[ST] = F.top.y; row[2 * ST] = F.top.z;
+          row[3 * ST] = F.bot.x; row[4 * ST] = F.bot.y; row[5 * ST] = F.bot.z;
         }
       }
     }
     // propagate to the parent: register carry along chains, accumulator at branch points
     const Abi<RA> dA = xt_abi_x(Xp, Ia);               // :187-189
     const Sv<RA> dP = xf_apply_force(Xp, pa);          // :181
-    Rbi<RC> dC = Ic;
-    if (any_contact) { Xf<RC> Xc; Xc.R = cvt<RC>(Xp.R); Xc.t = cvt<RC>(Xp.t); dC = xt_rbi_x(Xc, Ic); }  // mass_matrix.hpp:45-46
+    Rbi<RS> dC = Ic;
+    if (any_contact) { Xf<RS> Xc; Xc.R = cvt<RS>(Xp.R); Xc.t = cvt<RS>(Xp.t); dC = xt_rbi_x(Xc, Ic); }  // mass_matrix.hpp:45-46
     if (fl & TDS_LF_PARENT_ADJ) { cA = dA; cP = dP; cC = dC; }
     else {
       const int slot = (p >= 0) ? M.acc_slot[p] : M.base_acc;
       if (slot >= 0) {
         const int w = M.w_acc + slot * M.acc_words;
         acc_add_abi<RA>(A, w, dA, dP);
-        acc_add_rbi<RC>(A, w + M.acc_ic_word, dC);
+        acc_add_rbi<RS>(A, w + M.acc_ic_word, dC);
       }
     }
   }
-
   TDS_PHASE();  // 4: pass 2 (ABA + CRBA) done
+
   // ---- base acceleration (forward_dynamics.hpp:218-243) -----------------------------------------
   Sv<RA> a_prev;
   Sv<RC> base_acc;
   if (M.floating) {
-    Rbi<RC> Ib = model_rbi<RC>(M.base_rbi);
+    Rbi<RS> Ib = model_rbi<RS>(M.base_rbi);
     Abi<RA> Ab = abi_from_rbi(model_rbi<RA>(M.base_rbi));
     // gyroscopic bias, kinematics.hpp:54-61
     M3<RA> Rb = cvt<RA>(baseR);
@@ -429,18 +454,17 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       Abi<RA> sa; Sv<RA> sp;
       const int ws = M.w_acc + M.base_acc * M.acc_words;
       acc_load<RA>(A, ws, sa, sp);
-      abi_add(Ab, sa); pb = pb + sp; rbi_add(Ib, acc_load_rbi<RC>(A, ws + M.acc_ic_word));
+      abi_add(Ab, sa); pb = pb + sp; rbi_add(Ib, acc_load_rbi<RS>(A, ws + M.acc_ic_word));
     }
-    if (any_contact) {  // mass_matrix.hpp:114-120: base block = composite inertia
-      const RC z = RC(0);
-      A.at<RC>(M.w_M, tri(0, 0)) = Ib.I.xx; A.at<RC>(M.w_M, tri(1, 0)) = Ib.I.xy; A.at<RC>(M.w_M, tri(1, 1)) = Ib.I.yy;
-      A.at<RC>(M.w_M, tri(2, 0)) = Ib.I.xz; A.at<RC>(M.w_M, tri(2, 1)) = Ib.I.yz; A.at<RC>(M.w_M, tri(2, 2)) = Ib.I.zz;
-      // rows 3..5: [H^T | M], H = h x
-      A.at<RC>(M.w_M, tri(3, 0)) = z;            A.at<RC>(M.w_M, tri(3, 1)) = RC(Ib.h.z);  A.at<RC>(M.w_M, tri(3, 2)) = RC(-Ib.h.y);
-      A.at<RC>(M.w_M, tri(4, 0)) = RC(-Ib.h.z);  A.at<RC>(M.w_M, tri(4, 1)) = z;           A.at<RC>(M.w_M, tri(4, 2)) = RC(Ib.h.x);
-      A.at<RC>(M.w_M, tri(5, 0)) = RC(Ib.h.y);   A.at<RC>(M.w_M, tri(5, 1)) = RC(-Ib.h.x); A.at<RC>(M.w_M, tri(5, 2)) = z;
-      A.at<RC>(M.w_M, tri(3, 3)) = RC(Ib.m); A.at<RC>(M.w_M, tri(4, 3)) = z; A.at<RC>(M.w_M, tri(4, 4)) = RC(Ib.m);
-      A.at<RC>(M.w_M, tri(5, 3)) = z; A.at<RC>(M.w_M, tri(5, 4)) = z; A.at<RC>(M.w_M, tri(5, 5)) = RC(Ib.m);
+    if (any_contact) {  // mass_matrix.hpp:114-120: base block = composite inertia [I  hx; hx^T  m1]
+      const RS z = RS(0);
+      Mm[tri(0, 0) * ST] = Ib.I.xx; Mm[tri(1, 0) * ST] = Ib.I.xy; Mm[tri(1, 1) * ST] = Ib.I.yy;
+      Mm[tri(2, 0) * ST] = Ib.I.xz; Mm[tri(2, 1) * ST] = Ib.I.yz; Mm[tri(2, 2) * ST] = Ib.I.zz;
+      Mm[tri(3, 0) * ST] = z;        Mm[tri(3, 1) * ST] = Ib.h.z;  Mm[tri(3, 2) * ST] = -Ib.h.y;
+      Mm[tri(4, 0) * ST] = -Ib.h.z;  Mm[tri(4, 1) * ST] = z;       Mm[tri(4, 2) * ST] = Ib.h.x;
+      Mm[tri(5, 0) * ST] = Ib.h.y;   Mm[tri(5, 1) * ST] = -Ib.h.x; Mm[tri(5, 2) * ST] = z;
+      Mm[tri(3, 3) * ST] = Ib.m; Mm[tri(4, 3) * ST] = z; Mm[tri(4, 4) * ST] = Ib.m;
+      Mm[tri(5, 3) * ST] = z; Mm[tri(5, 4) * ST] = z; Mm[tri(5, 5) * ST] = Ib.m;
     }
     // -base_abi.inv_mul(bias) with the reference's block inverse (C = -H), inertia.hpp:302-328
     {
@@ -479,8 +503,8 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
   a_prev.top = cvt<RA>(base_acc.top);
   a_prev.bot = cvt<RA>(base_acc.bot);
   const Sv<RA> a_base = a_prev;
-
   TDS_PHASE();  // 5: base done
+
   // ---- pass 3: root -> leaf accelerations (forward_dynamics.hpp:245-302) + integrate_euler_qdd ----
   for (int i = 0; i < n_links; ++i) {
     const int p = M.parent[i];
@@ -502,7 +526,7 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       a.bot = a.bot + S.bot * qdd;
       const int qdi = M.qd_idx[i];
       if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)qdi * ns + e] = (float)qdd; }
-      else A.at<float>(M.w_qd, qdi) = (float)(RA(A.at<float>(M.w_qd, qdi)) + qdd * dtA);
+      else qdv[qdi * ST] = (float)(RA(qdv[qdi * ST]) + qdd * dtA);
     }
     st_sv<RA>(A, wl, LK_VC, a);
     a_prev = a;
@@ -513,28 +537,29 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
-      else A.at<float>(M.w_qd, k) = (float)(RC(A.at<float>(M.w_qd, k)) + qb[k] * RC(P.dt));
+      else qdv[k * ST] = (float)(RC(qdv[k * ST]) + qb[k] * RC(P.dt));
     }
   }
   TDS_PHASE();  // 6: pass 3 done
   if (mode == MODE_FD) return;
 
-  // ---- contact solve ------------------------------------------------------------------------------
+  // ---- contact solve (RS arithmetic; only the right-hand side b needs the RC positions) ------------
   if (mode == MODE_FULL && any_contact) {
-    const int RCW = (int)(sizeof(RC) / 4);
-    // Cholesky M = L L^T in place (lower triangle).  The reference inverts M
-    // (tiny_matrix_x.h:240-344); only products with M^-1 are needed.
-    for (int j = 0; j < n; ++j) {
-      RC d = A.at<RC>(M.w_M, tri(j, j));
-      for (int k = 0; k < j; ++k) { const RC l = A.at<RC>(M.w_M, tri(j, k)); d -= l * l; }
-      const RC ljj = sqrt_t(d);
-      const RC inv = RC(1) / ljj;
-      A.at<RC>(M.w_M, tri(j, j)) = ljj;
-      for (int i = j + 1; i < n; ++i) {
-        RC s = A.at<RC>(M.w_M, tri(i, j));
-        for (int k = 0; k < j; ++k) s -= A.at<RC>(M.w_M, tri(i, k)) * A.at<RC>(M.w_M, tri(j, k));
-        A.at<RC>(M.w_M, tri(i, j)) = s * inv;
+    RS* const invd = &A.at<RS>(M.w_invd, 0);
+    RS* const wv = &A.at<RS>(M.w_w, 0);
+    // Cholesky M = L L^T in place, row by row (L[i][j] needs rows i and j only; both are contiguous in the
+    // row-major lower triangle).  The reference inverts M (tiny_matrix_x.h:240-344); only products with
+    // M^-1 are needed here.
+    for (int i = 0; i < n; ++i) {
+      RS* const ri = Mm + tri(i, 0) * ST;
+      for (int j = 0; j < i; ++j) {
+        const RS* rj = Mm + tri(j, 0) * ST;
+        ri[j * ST] = (ri[j * ST] - sdot(ri, rj, ST, j)) * invd[j * ST];
       }
+      const RS d = ri[i * ST] - sdot(ri, ri, ST, i);
+      const RS l = sqrt_t(d);
+      ri[i * ST] = l;
+      invd[i * ST] = RS(1) / l;
     }
     TDS_PHASE();  // 7: Cholesky done
     const int max_active = __reduce_max_sync(0xffffffffu, n_active);
@@ -544,11 +569,13 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     for (int c = 0; c < max_active; ++c) {
       if (c < n_active) {
         const int wc = M.w_con + c * CN_SIZE * RCW;
-        const int wy = M.w_Y + c * 3 * n * RCW;
+        RS* const y0 = &A.at<RS>(M.w_Y, 0) + (c * 3) * n * ST;
+        RS* const y1 = y0 + n * ST;
+        RS* const y2 = y1 + n * ST;
         const V3<RC> pb = ld_v3<RC>(A, wc, CN_PB);
         const RC dist = A.at<RC>(wc, CN_DIST);
         const int L = (int)A.at<RC>(wc, CN_LINK);
-        for (int k = 0; k < 3 * n; ++k) A.at<RC>(wy, k) = RC(0);
+        for (int k = 0; k < 3 * n; ++k) y0[k * ST] = RS(0);
         V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));   // vel_b = J qd
         if (M.floating) {  // jacobian.hpp:39-58
           const V3<RC> r = pb - Xw_base.t;
@@ -558,69 +585,84 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
           const V3<RC> cols[6] = {c0, c1, c2, e0, e1, e2};
 #pragma unroll
           for (int k = 0; k < 6; ++k) {
-            A.at<RC>(wy, k) = dot(nb, cols[k]);
-            A.at<RC>(wy, n + k) = dot(f1, cols[k]);
-            A.at<RC>(wy, 2 * n + k) = dot(f2, cols[k]);
-            vel = vel + cols[k] * RC(A.at<float>(M.w_qd, k));
+            y0[k * ST] = RS(dot(nb, cols[k]));
+            y1[k * ST] = RS(dot(f1, cols[k]));
+            y2[k * ST] = RS(dot(f2, cols[k]));
+            vel = vel + cols[k] * RC(qdv[k * ST]);
           }
         }
         for (int j = L; j >= 0; j = M.parent[j]) {  // jacobian.hpp:63-80
           if (M.flags[j] & TDS_LF_FIXED) continue;
           const Xf<RC> Xw = ld_xf<RC>(A, M.w_xw + (j + 1) * XWW);
           const Sv<RC> S = link_S<RC>(M, j);
-          const V3<RC> wv = mul(Xw.R, S.top);
-          const V3<RC> col = mul(Xw.R, S.bot) + cross(wv, pb - Xw.t);
+          const V3<RC> wv3 = mul(Xw.R, S.top);
+          const V3<RC> col = mul(Xw.R, S.bot) + cross(wv3, pb - Xw.t);
           const int qj = M.qd_idx[j];
-          A.at<RC>(wy, qj) = dot(nb, col);
-          A.at<RC>(wy, n + qj) = dot(f1, col);
-          A.at<RC>(wy, 2 * n + qj) = dot(f2, col);
-          vel = vel + col * RC(A.at<float>(M.w_qd, qj));
+          y0[qj * ST] = RS(dot(nb, col));
+          y1[qj * ST] = RS(dot(f1, col));
+          y2[qj * ST] = RS(dot(f2, col));
+          vel = vel + col * RC(qdv[qj * ST]);
         }
         // rel_vel = vel_a - vel_b = -vel ; mb_constraint_solver.hpp:299-345
         const RC nrv = -dot(nb, vel);
-        A.at<RC>(wc, CN_B + 0) = -(RC(1) + RC(P.restitution)) * nrv - RC(P.erp) * dist / RC(P.dt);
-        A.at<RC>(wc, CN_B + 1) = dot(f1, vel);
-        A.at<RC>(wc, CN_B + 2) = dot(f2, vel);
-        A.at<RC>(wc, CN_X + 0) = RC(0); A.at<RC>(wc, CN_X + 1) = RC(0); A.at<RC>(wc, CN_X + 2) = RC(0);
-        // Y rows = L^-1 * Jc rows (forward substitution, three right-hand sides share the loads of L)
+        RS* const cs = &A.at<RS>(M.w_conS + c * 6 * RSW, 0);   // b[3], x[3]
+        cs[0] = RS(-(RC(1) + RC(P.restitution)) * nrv - RC(P.erp) * dist / RC(P.dt));
+        cs[ST] = RS(dot(f1, vel));
+        cs[2 * ST] = RS(dot(f2, vel));
+        cs[3 * ST] = RS(0); cs[4 * ST] = RS(0); cs[5 * ST] = RS(0);
+        // Y rows = L^-1 * Jc rows: forward substitution, the three right-hand sides share the loads of L
         for (int i = 0; i < n; ++i) {
-          RC s0 = A.at<RC>(wy, i), s1 = A.at<RC>(wy, n + i), s2 = A.at<RC>(wy, 2 * n + i);
-          for (int k = 0; k < i; ++k) {
-            const RC l = A.at<RC>(M.w_M, tri(i, k));
-            s0 -= l * A.at<RC>(wy, k); s1 -= l * A.at<RC>(wy, n + k); s2 -= l * A.at<RC>(wy, 2 * n + k);
+          const RS* ri = Mm + tri(i, 0) * ST;
+          RS a0 = RS(0), a1 = RS(0), a2 = RS(0), b0 = RS(0), b1 = RS(0), b2 = RS(0);
+          int k = 0;
+          for (; k + 1 < i; k += 2) {
+            const RS l0 = ri[k * ST], l1 = ri[(k + 1) * ST];
+            a0 += l0 * y0[k * ST]; a1 += l0 * y1[k * ST]; a2 += l0 * y2[k * ST];
+            b0 += l1 * y0[(k + 1) * ST]; b1 += l1 * y1[(k + 1) * ST]; b2 += l1 * y2[(k + 1) * ST];
           }
-          const RC inv = RC(1) / A.at<RC>(M.w_M, tri(i, i));
-          A.at<RC>(wy, i) = s0 * inv; A.at<RC>(wy, n + i) = s1 * inv; A.at<RC>(wy, 2 * n + i) = s2 * inv;
+          if (k < i) { const RS l0 = ri[k * ST]; a0 += l0 * y0[k * ST]; a1 += l0 * y1[k * ST]; a2 += l0 * y2[k * ST]; }
+          const RS inv = invd[i * ST];
+          y0[i * ST] = (y0[i * ST] - (a0 + b0)) * inv;
+          y1[i * ST] = (y1[i * ST] - (a1 + b1)) * inv;
+          y2[i * ST] = (y2[i * ST] - (a2 + b2)) * inv;
         }
       }
     }
     TDS_PHASE();  // 8: Jacobians + Y done
     // matrix-free projected Gauss-Seidel on w = Y p; row order normals | friction-1 | friction-2
     // (solve_pgs, mb_constraint_solver.hpp:101-142; bounds :417-436)
-    for (int k = 0; k < n; ++k) A.at<RC>(M.w_w, k) = RC(0);
+    for (int k = 0; k < n; ++k) wv[k * ST] = RS(0);
+    const RS cfm = RS(P.cfm), mu = RS(P.friction);
     for (int it = 0; it < P.pgs_iterations; ++it) {
       for (int blk = 0; blk < 3; ++blk) {
         for (int c = 0; c < max_active; ++c) {
           if (c < n_active) {
-            const int wc = M.w_con + c * CN_SIZE * RCW;
-            const int wy = M.w_Y + (c * 3 + blk) * n * RCW;
-            RC yy = RC(0), yw = RC(0);
-            for (int k = 0; k < n; ++k) { const RC y = A.at<RC>(wy, k); yy += y * y; yw += y * A.at<RC>(M.w_w, k); }
-            const RC x_old = A.at<RC>(wc, CN_X + blk);
-            RC x = (A.at<RC>(wc, CN_B + blk) - yw + yy * x_old) / (yy + RC(P.cfm));
+            RS* const cs = &A.at<RS>(M.w_conS + c * 6 * RSW, 0);
+            const RS* y = &A.at<RS>(M.w_Y, 0) + (c * 3 + blk) * n * ST;
+            RS yy0 = RS(0), yy1 = RS(0), yw0 = RS(0), yw1 = RS(0);
+            int k = 0;
+            for (; k + 1 < n; k += 2) {
+              const RS ya = y[k * ST], yb = y[(k + 1) * ST];
+              yy0 += ya * ya; yw0 += ya * wv[k * ST];
+              yy1 += yb * yb; yw1 += yb * wv[(k + 1) * ST];
+            }
+            if (k < n) { const RS ya = y[k * ST]; yy0 += ya * ya; yw0 += ya * wv[k * ST]; }
+            const RS yy = yy0 + yy1, yw = yw0 + yw1;
+            const RS x_old = cs[(3 + blk) * ST];
+            RS x = (cs[blk * ST] - yw + yy * x_old) / (yy + cfm);
             if (blk == 0) {
-              x = x < RC(0) ? RC(0) : x;
-              x = x > RC(100000) ? RC(100000) : x;
+              x = x < RS(0) ? RS(0) : x;
+              x = x > RS(100000) ? RS(100000) : x;
             } else {
-              RC s = A.at<RC>(wc, CN_X + 0);
-              s = s < RC(0) ? RC(0) : s;
-              const RC lim = RC(P.friction) * s;
+              RS s = cs[3 * ST];
+              s = s < RS(0) ? RS(0) : s;
+              const RS lim = mu * s;
               x = x < -lim ? -lim : x;
               x = x > lim ? lim : x;
             }
-            A.at<RC>(wc, CN_X + blk) = x;
-            const RC dx = x - x_old;
-            for (int k = 0; k < n; ++k) A.at<RC>(M.w_w, k) += dx * A.at<RC>(wy, k);
+            cs[(3 + blk) * ST] = x;
+            const RS dx = x - x_old;
+            for (int k2 = 0; k2 < n; ++k2) wv[k2 * ST] += dx * y[k2 * ST];
           }
         }
       }
@@ -628,21 +670,26 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     TDS_PHASE();  // 9: PGS done
     // qd_b -= M^-1 Jc^T p = L^-T w   (mb_constraint_solver.hpp:476-497)
     for (int i = n - 1; i >= 0; --i) {
-      RC s = A.at<RC>(M.w_w, i);
-      for (int k = i + 1; k < n; ++k) s -= A.at<RC>(M.w_M, tri(k, i)) * A.at<RC>(M.w_w, k);
-      s = s / A.at<RC>(M.w_M, tri(i, i));
-      A.at<RC>(M.w_w, i) = s;
-      if (n_active > 0) A.at<float>(M.w_qd, i) = (float)(RC(A.at<float>(M.w_qd, i)) - s);
+      RS s0 = wv[i * ST], s1 = RS(0);
+      int k = i + 1;
+      for (; k + 1 < n; k += 2) {
+        s0 -= Mm[(tri(k, 0) + i) * ST] * wv[k * ST];
+        s1 -= Mm[(tri(k + 1, 0) + i) * ST] * wv[(k + 1) * ST];
+      }
+      if (k < n) s0 -= Mm[(tri(k, 0) + i) * ST] * wv[k * ST];
+      const RS z = (s0 + s1) * invd[i * ST];
+      wv[i * ST] = z;
+      if (n_active > 0) qdv[i * ST] = (float)(RS(qdv[i * ST]) - z);
     }
   }
-
   TDS_PHASE();  // 10: impulses applied
+
   // ---- integrate_euler with qdd = 0 (integrator.hpp:10-133) ---------------------------------------
   RC up_z = RC(1);
   if (M.floating) {
     const RC h = RC(0.5) * RC(P.dt);
-    RC qx = RC(A.at<float>(M.w_q, 0)), qy = RC(A.at<float>(M.w_q, 1)), qz = RC(A.at<float>(M.w_q, 2)), qw = RC(A.at<float>(M.w_q, 3));
-    const RC w0 = RC(A.at<float>(M.w_qd, 0)), w1 = RC(A.at<float>(M.w_qd, 1)), w2 = RC(A.at<float>(M.w_qd, 2));
+    RC qx = RC(qv[0]), qy = RC(qv[ST]), qz = RC(qv[2 * ST]), qw = RC(qv[3 * ST]);
+    const RC w0 = RC(qdv[0]), w1 = RC(qdv[ST]), w2 = RC(qdv[2 * ST]);
     const RC dw = (-qx * w0 - qy * w1 - qz * w2) * h;
     const RC dx = (qw * w0 + qz * w1 - qy * w2) * h;
     const RC dy = (qw * w1 + qx * w2 - qz * w0) * h;
@@ -650,36 +697,42 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     qx += dx; qy += dy; qz += dz; qw += dw;
     const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
     qx /= len; qy /= len; qz /= len; qw /= len;
-    A.at<float>(M.w_q, 0) = (float)qx; A.at<float>(M.w_q, 1) = (float)qy; A.at<float>(M.w_q, 2) = (float)qz; A.at<float>(M.w_q, 3) = (float)qw;
+    qv[0] = (float)qx; qv[ST] = (float)qy; qv[2 * ST] = (float)qz; qv[3 * ST] = (float)qw;
     for (int k = 0; k < 3; ++k)
-      A.at<float>(M.w_q, 4 + k) = (float)(RC(A.at<float>(M.w_q, 4 + k)) + RC(A.at<float>(M.w_qd, 3 + k)) * RC(P.dt));
+      qv[(4 + k) * ST] = (float)(RC(qv[(4 + k) * ST]) + RC(qdv[(3 + k) * ST]) * RC(P.dt));
     up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
   }
   for (int i = 0; i < n_links; ++i) {
     if (M.flags[i] & TDS_LF_FIXED) continue;
     const int qi = M.q_idx[i];
-    A.at<float>(M.w_q, qi) = (float)(RC(A.at<float>(M.w_q, qi)) + RC(A.at<float>(M.w_qd, M.qd_idx[i])) * RC(P.dt));
+    qv[qi * ST] = (float)(RC(qv[qi * ST]) + RC(qdv[M.qd_idx[i] * ST]) * RC(P.dt));
   }
-
   TDS_PHASE();  // 11: integrated
-  // ---- write back -----------------------------------------------------------------------------------
+
+  // ---- reward / done / auto-reset, write back --------------------------------------------------------
   if (live) {
-    for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = A.at<float>(M.w_q, k);
-    for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = A.at<float>(M.w_qd, k);
-    if (io.reward && E.reward_kind == 1) {
-      // laikago_environment2.h:130-171, fixed-base emulation: x = q0, z = q2, rpy = q3..5
-      const float x = A.at<float>(M.w_q, 0), z = A.at<float>(M.w_q, 2);
-      const float roll = A.at<float>(M.w_q, 3), pitch = A.at<float>(M.w_q, 4);
+    bool done = false;
+    if (E.reward_kind == 1) {
+      // laikago_environment2.h:130-171, fixed-base emulation: x = q0, z = q2, rpy = q3..5;
       // up.z of quat_to_matrix(quat_from_euler_rpy(rpy)) = cos(roll) cos(pitch)
-      const float upz = cosf(roll) * cosf(pitch);
-      const bool done = (upz < 0.6f) || (z < 0.2f);
-      io.reward[e] = done ? 0.f : x;
-      if (io.done) io.done[e] = done ? 1.f : 0.f;
-    } else if (io.reward && E.reward_kind == 2) {
-      const float x = A.at<float>(M.w_q, 4), z = A.at<float>(M.w_q, 6);
-      const bool done = ((float)up_z < 0.6f) || (z < 0.2f);
-      io.reward[e] = done ? 0.f : x;
-      if (io.done) io.done[e] = done ? 1.f : 0.f;
+      const float x = qv[0], z = qv[2 * ST];
+      const float upz = cosf(qv[3 * ST]) * cosf(qv[4 * ST]);
+      done = (upz < 0.6f) || (z < 0.2f);
+      if (io.reward) io.reward[e] = done ? 0.f : x;
+    } else if (E.reward_kind == 2) {
+      const float x = qv[4 * ST], z = qv[6 * ST];
+      done = ((float)up_z < 0.6f) || (z < 0.2f);
+      if (io.reward) io.reward[e] = done ? 0.f : x;
+    }
+    if (io.done && E.reward_kind) io.done[e] = done ? 1.f : 0.f;
+    if (done && E.auto_reset) {
+      // VectorizedEnvironment auto_reset_when_done (ars_vectorized_environment.h:262-283): back to the
+      // reset pose (deterministic; the host-side reset() adds the reference's joint noise and settle steps)
+      for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = E.reset_q[k];
+      for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = 0.f;
+    } else {
+      for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = qv[k * ST];
+      for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = qdv[k * ST];
     }
   }
 }
@@ -695,9 +748,9 @@ extern "C" int tds_launch_step(const DevModel* M, const SimParams* P, const EnvP
   const int blocks = (io->n + threads - 1) / threads;
   const size_t smem = use_smem ? (size_t)warps_per_block * M->w_total * 32 * 4 : 0;
   cudaError_t err = cudaSuccess;
-#define TDS_LAUNCH(RA, RC, SM)                                                                          \
+#define TDS_LAUNCH(RA, RC, RS, SM)                                                                      \
   do {                                                                                                  \
-    auto k = tds_step_kernel<RA, RC, SM>;                                                               \
+    auto k = tds_step_kernel<RA, RC, RS, SM>;                                                           \
     static size_t smem_set = 0; /* opt-in once per instantiation, not per launch */                     \
     if (smem > 48 * 1024 && smem > smem_set) {                                                          \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
@@ -708,12 +761,12 @@ extern "C" int tds_launch_step(const DevModel* M, const SimParams* P, const EnvP
       err = cudaGetLastError();                                                                         \
     }                                                                                                   \
   } while (0)
-  if (precision == 0) {        // mixed: fp32 ABA, fp64 kinematics + contact
-    if (use_smem) TDS_LAUNCH(float, double, true); else TDS_LAUNCH(float, double, false);
+  if (precision == 0) {        // mixed: fp32 ABA + fp32 contact solve, fp64 kinematics / contact geometry
+    if (use_smem) TDS_LAUNCH(float, double, float, true); else TDS_LAUNCH(float, double, float, false);
   } else if (precision == 1) { // all fp64
-    if (use_smem) TDS_LAUNCH(double, double, true); else TDS_LAUNCH(double, double, false);
+    if (use_smem) TDS_LAUNCH(double, double, double, true); else TDS_LAUNCH(double, double, double, false);
   } else {                     // all fp32
-    if (use_smem) TDS_LAUNCH(float, float, true); else TDS_LAUNCH(float, float, false);
+    if (use_smem) TDS_LAUNCH(float, float, float, true); else TDS_LAUNCH(float, float, float, false);
   }
 #undef TDS_LAUNCH
   return (int)err;

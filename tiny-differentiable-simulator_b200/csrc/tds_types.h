@@ -23,7 +23,7 @@ struct DevModel {
   int base_acc;      // accumulator slot of the floating base (-1 if fixed base)
   int n_vis, pad1, pad2;
   // scratch arena layout, in 4-byte words per environment (see tds_step.cu)
-  int w_q, w_qd, w_tau, w_link, w_acc, w_xw, w_M, w_w, w_con, w_Y, w_total;
+  int w_q, w_qd, w_tau, w_link, w_acc, w_xw, w_M, w_invd, w_w, w_con, w_conS, w_Y, w_total;
   int link_words;    // words per link in the per-link region
   int acc_words, acc_ic_word;  // accumulator slot stride / offset of its Ic part (words)
   int parent[TDS_MAX_LINKS];
@@ -76,6 +76,8 @@ struct EnvParams {
   int act_link[TDS_MAX_ACT];   // link index driven by action k
   // reward/done (examples/environments/laikago_environment2.h:130-171)
   int reward_kind;     // 0 none, 1 laikago (fixed-base emulation), 2 laikago floating
+  int auto_reset;      // reset an environment to reset_q when it reports done
+  float reset_q[TDS_MAX_LINKS + 8];
 };
 
 // Pointers to SoA state in HBM: array [dim][n_stride] (environment index fastest).

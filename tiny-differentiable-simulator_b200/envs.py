@@ -19,7 +19,14 @@ LAIKAGO_KP, LAIKAGO_KD, LAIKAGO_MAX_FORCE = 100.0, 2.0, 50.0  # laikago_environm
 LAIKAGO_START_Z = 0.48
 
 
-def laikago_sim(n_envs, device=0, model=None, **kw):
+def laikago_reset_pose():
+    q = np.zeros(18)
+    q[2] = LAIKAGO_START_Z
+    q[6:18] = LAIKAGO_INITIAL_POSES
+    return q
+
+
+def laikago_sim(n_envs, device=0, model=None, auto_reset=False, **kw):
     """BatchSim configured like LaikagoContactSimulation (fixed-base emulation, friction 1,
     keep_all_points, dt 1e-3; locomotion_contact_simulation.h:131-135, laikago_environment2.h:36-47)."""
     if model is None:
@@ -27,6 +34,8 @@ def laikago_sim(n_envs, device=0, model=None, **kw):
     sim = BatchSim(model, n_envs, device=device, dt=1e-3, friction=1.0, keep_all_points=True, **kw)
     sim.set_env(LAIKAGO_INITIAL_POSES, start_link=6, kp=LAIKAGO_KP, kd=LAIKAGO_KD, max_force=LAIKAGO_MAX_FORCE,
                 action_limit=0.4, reward_kind=1)
+    if auto_reset:
+        sim.set_auto_reset(True, laikago_reset_pose())
     return sim
 
 

@@ -71,6 +71,12 @@ class BatchSim:
                                              action_limit, reward_kind), "set_env")
         self.n_act = ip.size
 
+    def set_auto_reset(self, enable, reset_q=None):
+        rq = None if reset_q is None else np.ascontiguousarray(reset_q, dtype=np.float64)
+        if rq is not None:
+            assert rq.size == self.n_q
+        self._check(self._L.tds_b200_set_auto_reset(self._h, int(enable), _dp(rq)), "set_auto_reset")
+
     def set_precision(self, precision):
         self._check(self._L.tds_b200_set_precision(self._h, precision), "set_precision")
         self.precision = precision
