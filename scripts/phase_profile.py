@@ -17,9 +17,12 @@ for _ in range(3):
     sim.env_step_device(act)
 buf = np.zeros((nw, 16), dtype=np.int64)
 L.tds_b200_debug_phase_clocks(sim._h, 1, buf.ctypes.data, nw)
-names = ["load+PD", "pass1 FK", "contacts", "pass2 ABA+CRBA", "base", "pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate", "writeback"]
-d = np.diff(buf[:, :13], axis=1).astype(np.float64)
-tot = (buf[:, 12] - buf[:, 0]).astype(np.float64)
+names = ["load+PD", "pass1 FK+contacts", "pass2 ABA+CRBA", "base+pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate+write"]
+if os.environ.get("TDS_B200_KERNEL") == "link":
+    names = ["load+PD", "pass1 FK", "contacts", "pass2 ABA+CRBA", "base", "pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate", "writeback"]
+K = len(names)
+d = np.diff(buf[:, :K + 1], axis=1).astype(np.float64)
+tot = (buf[:, K] - buf[:, 0]).astype(np.float64)
 print("cycles per warp: total median %.0f (min %.0f max %.0f)" % (np.median(tot), tot.min(), tot.max()))
 for k, nm in enumerate(names):
     print(f"  {nm:16s} {np.median(d[:, k]):9.0f} cycles  {100 * np.median(d[:, k]) / np.median(tot):5.1f}%")

@@ -14,6 +14,9 @@
 #include "tds_model.h"
 #include "tds_types.h"
 
+extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
+                                int mode, int use_pd, int precision, char* gscratch, int use_smem,
+                                int warps_per_block, cudaStream_t stream);
 extern "C" int tds_launch_step(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                int warps_per_block, cudaStream_t stream);
@@ -113,6 +116,8 @@ struct tds_b200_sim {
   int n = 0, ns = 0;
   DevModel dm[3];         // one layout per precision mode
   bool smem_ok[3] = {false, false, false};
+  bool smem_ok_w[3] = {false, false, false};
+  int kernel = 1;          // 1: world-frame kernel (tds_stepw.cu), 0: link-frame kernel (tds_step.cu)
   int warps_per_block[3] = {1, 1, 1};
   DevVisuals vis;
   SimParams P;
@@ -150,7 +155,8 @@ static int ensure_stage(tds_b200_sim* s, size_t dev_bytes, size_t host_bytes) {
 }
 
 static int ensure_scratch(tds_b200_sim* s, int prec) {
-  size_t need = (size_t)s->dm[prec].w_total * 4 * s->ns;
+  const int words = s->dm[prec].w_total > s->dm[prec].x_total ? s->dm[prec].w_total : s->dm[prec].x_total;
+  size_t need = (size_t)words * 4 * s->ns;
   if (need > s->scratch_bytes) {
     if (s->scratch) cudaFree(s->scratch);
     s->scratch = nullptr; s->scratch_bytes = 0;
@@ -186,11 +192,14 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
   for (int p = 0; p < 3; ++p) {
     s->dm[p] = base;
     tds_build_layout(&s->dm[p], sizes[p][0], sizes[p][1], sizes[p][2], -1);
+    tds_build_layout_w(&s->dm[p], sizes[p][0], sizes[p][1], sizes[p][2], -1);
     size_t per_warp = (size_t)s->dm[p].w_total * 32 * 4;
     s->smem_ok[p] = per_warp <= (size_t)s->max_smem_optin;
+    s->smem_ok_w[p] = (size_t)s->dm[p].x_total * 32 * 4 <= (size_t)s->max_smem_optin;
     // several warps per block only help when many blocks would otherwise be needed per SM
     s->warps_per_block[p] = 1;
   }
+  if (const char* kv = getenv("TDS_B200_KERNEL")) s->kernel = (strcmp(kv, "link") == 0) ? 0 : 1;
   s->n_tau = base.n_qd - (base.floating ? 6 : 0);
   s->n_points = base.max_contacts;
   // visuals for the v1 output packing
@@ -306,10 +315,12 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.phase_clk = s->phase_clk;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
-  const int use_smem = s->smem_ok[p] ? 1 : 0;
+  const int use_smem = (s->kernel ? s->smem_ok_w[p] : s->smem_ok[p]) ? 1 : 0;
   if (!use_smem) { int rc = ensure_scratch(s, p); if (rc) return rc; }
-  int rc = tds_launch_step(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
-                           s->warps_per_block[p], (cudaStream_t)stream);
+  int rc = s->kernel ? tds_launch_stepw(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
+                                        s->warps_per_block[p], (cudaStream_t)stream)
+                     : tds_launch_step(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
+                                       s->warps_per_block[p], (cudaStream_t)stream);
   if (rc) set_err(std::string("step launch: ") + cudaGetErrorString((cudaError_t)rc));
   return rc;
 }

@@ -46,6 +46,15 @@ TDS_HOST_INLINE void tds_rbi_pack(const double* rec /* mass, com[3], inertia[9] 
   out[9] = (I[8] + m * (cc - c[2] * c[2]));
 }
 
+// (mass, com, inertia about com) kept as given, symmetric part of the inertia.
+TDS_HOST_INLINE void tds_rbic_pack(const double* rec, double* out) {
+  out[0] = rec[0];
+  out[1] = rec[1]; out[2] = rec[2]; out[3] = rec[3];
+  const double* I = rec + 4;
+  out[4] = I[0]; out[5] = 0.5 * (I[1] + I[3]); out[6] = 0.5 * (I[2] + I[6]);
+  out[7] = I[4]; out[8] = 0.5 * (I[5] + I[7]); out[9] = I[8];
+}
+
 // Returns 0 on success, <0 on unsupported / oversized models.
 TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel* D) {
   if (n_doubles < TDSM_HEADER || (int)m[TDSM_H_MAGIC] != TDSM_MAGIC) return -1;
@@ -63,6 +72,7 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
   const double* geoms = links + (size_t)D->n_links * TDSM_LINK;
   if (n_doubles < TDSM_HEADER + TDSM_BASE + D->n_links * TDSM_LINK + D->n_geoms * TDSM_GEOM) return -1;
   tds_rbi_pack(base, D->base_rbi);
+  tds_rbic_pack(base, D->base_rbic);
   for (int k = 0; k < 9; ++k) D->base_inertia_com[k] = (float)base[4 + k];
   int n_acc = 0;
   for (int i = 0; i < D->n_links; ++i) D->acc_slot[i] = -1;
@@ -86,6 +96,13 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     for (int k = 0; k < 9; ++k) D->XT[i][k] = l[TDSM_L_XT_R + k];
     for (int k = 0; k < 3; ++k) D->XT[i][9 + k] = l[TDSM_L_XT_T + k];
     tds_rbi_pack(l + TDSM_L_MASS, D->rbi[i]);
+    tds_rbic_pack(l + TDSM_L_MASS, D->rbic[i]);
+    {
+      const double* r = l + TDSM_L_XT_R;
+      if (r[0] == 1.0 && r[4] == 1.0 && r[8] == 1.0 && r[1] == 0.0 && r[2] == 0.0 && r[3] == 0.0 && r[5] == 0.0 &&
+          r[6] == 0.0 && r[7] == 0.0)
+        D->flags[i] |= TDS_LF_XT_IDENT;
+    }
     D->stiffness[i] = (float)l[TDSM_L_STIFFNESS];
     D->damping[i] = (float)l[TDSM_L_DAMPING];
   }
@@ -100,6 +117,21 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     }
   }
   D->n_acc = n_acc;
+  // world transforms that must outlive the register carry: parents of non-adjacent children
+  D->n_xw = 0;
+  for (int i = 0; i < D->n_links; ++i) D->xw_slot[i] = -1;
+  for (int i = 0; i < D->n_links; ++i) {
+    int p = D->parent[i];
+    if (!(D->flags[i] & TDS_LF_PARENT_ADJ) && p >= 0 && D->xw_slot[p] < 0) D->xw_slot[p] = D->n_xw++;
+  }
+  // common-frame origin: floating base -> base position; else the position of the first link that is not
+  // reached through prismatic / fixed joints only (the root chain prefix)
+  D->n_prefix = -1;
+  if (!D->floating) {
+    int k = 0;
+    while (k < D->n_links && D->parent[k] == k - 1 && (D->flags[k] & (TDS_LF_PRISMATIC | TDS_LF_FIXED))) ++k;
+    D->n_prefix = k;   // links 0..k-1 are translation-only; origin = world position of link k (or of link k-1's frame end)
+  }
   int n_points = 0;
   for (int g = 0; g < D->n_geoms; ++g) {
     const double* gg = geoms + (size_t)g * TDSM_GEOM;
@@ -113,6 +145,15 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     if (D->g_type[g] == TDSG_CAPSULE) n_points += 2;
   }
   D->max_contacts = D->has_plane ? n_points : 0;
+  {  // geoms are enumerated base first, then link 0, 1, ...: ranges per link
+    int g = 0;
+    for (int li = -1; li < D->n_links; ++li) {
+      D->geom_begin[li + 1] = g;
+      while (g < D->n_geoms && D->g_link[g] == li) ++g;
+    }
+    D->geom_begin[D->n_links + 1] = g;
+    if (g != D->n_geoms) return -5;  // geoms not grouped by link
+  }
   for (int k = 0; k < 3; ++k) D->plane_n[k] = m[TDSM_H_PLANE_N + k];
   D->plane_c = m[TDSM_H_PLANE_C];
   double nb[3] = {-D->plane_n[0], -D->plane_n[1], -D->plane_n[2]};
@@ -159,4 +200,47 @@ TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int
   w += link_region > y_region ? link_region : y_region;
   w = even(w);
   D->w_total = w;
+}
+
+// Scratch layout of the world-frame kernel (tds_stepw.cu).
+TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, int size_rs, int max_contacts) {
+  const int ra = size_ra / 4, rc = size_rc / 4, rs = size_rs / 4;
+  const int n = D->n_qd;
+  if (max_contacts >= 0 && max_contacts < D->max_contacts) D->max_contacts = max_contacts;
+  D->nb = (n + 2) / 3;
+  const int n3 = 3 * D->nb;
+  int w = 0;
+  auto even = [](int x) { return (x + 1) & ~1; };
+  D->x_q = w; w += D->n_q;
+  D->x_qd = w; w += n;
+  D->x_tau = w; w += n;
+  w = even(w);
+  D->x_S = w; w += D->n_links * 6 * rc;                     // motion subspace in the common frame
+  w = even(w);
+  D->x_xw = w; w += (D->n_xw + 1) * 12 * rc;                // slot 0: base
+  w = even(w);
+  D->x_acc_ic_word = even(27 * ra);
+  D->x_acc_words = even(D->x_acc_ic_word + 10 * rc);
+  D->x_acc = w; w += D->n_acc * D->x_acc_words;
+  w = even(w);
+  D->x_con = w; w += D->max_contacts * 5 * rc;
+  w = even(w);
+  D->x_M = w; w += (D->nb * (D->nb + 1) / 2) * 9 * rs;
+  w = even(w);
+  D->x_dinv = w; w += D->nb * 6 * rs;
+  w = even(w);
+  D->x_w = w; w += n3 * rs;
+  w = even(w);
+  D->x_conS = w; w += D->max_contacts * 6 * rs;
+  w = even(w);
+  // per-link: rigid inertia about the origin (10 RC), later reused for U (6 RA), invD, u ; v / c / a (6 RA)
+  const int first = 10 * rc > 8 * ra ? 10 * rc : 8 * ra;
+  D->x_link_words = even(first + 6 * ra);
+  const int link_region = D->n_links * D->x_link_words;
+  const int y_region = D->max_contacts * n3 * 3 * rs;
+  D->x_link = w;
+  D->x_Y = w;
+  w += link_region > y_region ? link_region : y_region;
+  w = even(w);
+  D->x_total = w;
 }

@@ -1,0 +1,831 @@
+// World-frame batched env-step kernel for sm_100a (successor of tds_step.cu's link-frame kernel).
+//
+// Same reference path as tds_step.cu (PD -> kinematics -> ABA -> integrate_euler_qdd -> contacts -> CRBA ->
+// LCP/PGS -> integrate_euler; citations at each stage), restructured once more around the instruction count,
+// because with 4096 environments one warp owns an SM and every instruction is paid at single-warp latency:
+//
+//   * ALL spatial quantities of an environment live in ONE common frame: world axes, origin O that moves
+//     with the robot (base position, or the end of the translation-only root chain).  Then
+//       - velocities / accelerations propagate by addition (v_i = v_parent + S_i qd_i),
+//       - articulated and composite inertias accumulate by addition: the per-link congruence transform
+//         X^T Ia X of the reference (forward_dynamics.hpp:187-189, mass_matrix.hpp:45-46; ~250 FMA per link
+//         even in block form) disappears; the price is moving each link's rigid-body inertia into the common
+//         frame once (~70 FMA, shared by ABA and CRBA),
+//       - M_ij = S_j . (Ic_i S_i) and contact Jacobian columns = S_j.bot + S_j.top x x_c need no chain walks
+//         with transforms.
+//     Equivalent to the reference in exact arithmetic (spatial algebra is frame invariant); the floating-base
+//     quirks that ARE frame dependent (block inverse with C = -H, gyroscopic term, un-rotated gravity) are
+//     evaluated in the base frame exactly as the reference does.
+//   * Only S (6 numbers), v/c/a, U, 1/D, u per link are kept; world transforms are carried in registers and
+//     stored only for branch points.
+//   * The contact solve works on 3x3 register blocks (dofs padded to a multiple of 3): blocked Cholesky,
+//     blocked forward substitution of 3 right-hand sides per contact, matrix-free PGS on w = Y p, blocked
+//     back substitution.  A block op is 18 shared loads for 27 FMA with compile-time indexing.
+//   * Scalar types: RA (ABA) fp32, RC (kinematics, contact geometry, inertias in the common frame, CRBA
+//     products, Jacobians, LCP right-hand side) fp64, RS (factorisation, substitutions, PGS) fp32 in the
+//     default mixed mode.
+#include <cuda_runtime.h>
+
+#include "tds_math.cuh"
+#include "tds_types.h"
+#include "tds_b200_model.h"
+
+namespace tdsw {
+using namespace tds;
+
+struct Arena {
+  char* blk;
+  int stride;
+  int col;
+  template <typename T> TDS_D T* ptr(int word) const {
+    if (sizeof(T) == 4) return ((T*)blk) + (size_t)word * stride + col;
+    return ((T*)blk) + (size_t)(word >> 1) * stride + col;
+  }
+};
+
+template <typename T> TDS_D void st3(T* p, int s, const V3<T>& v) { p[0] = v.x; p[s] = v.y; p[2 * s] = v.z; }
+template <typename T> TDS_D V3<T> ld3(const T* p, int s) { return v3<T>(p[0], p[s], p[2 * s]); }
+template <typename T> TDS_D void st6(T* p, int s, const Sv<T>& v) { st3(p, s, v.top); st3(p + 3 * s, s, v.bot); }
+template <typename T> TDS_D Sv<T> ld6(const T* p, int s) { Sv<T> r; r.top = ld3(p, s); r.bot = ld3(p + 3 * s, s); return r; }
+template <typename T> TDS_D void st9(T* p, int s, const M3<T>& m) {
+  p[0] = m.xx; p[s] = m.xy; p[2 * s] = m.xz; p[3 * s] = m.yx; p[4 * s] = m.yy; p[5 * s] = m.yz; p[6 * s] = m.zx; p[7 * s] = m.zy; p[8 * s] = m.zz;
+}
+template <typename T> TDS_D M3<T> ld9(const T* p, int s) {
+  M3<T> m;
+  m.xx = p[0]; m.xy = p[s]; m.xz = p[2 * s]; m.yx = p[3 * s]; m.yy = p[4 * s]; m.yz = p[5 * s]; m.zx = p[6 * s]; m.zy = p[7 * s]; m.zz = p[8 * s];
+  return m;
+}
+template <typename T> TDS_D void st_rbi(T* p, int s, const Rbi<T>& r) {
+  p[0] = r.m; p[s] = r.h.x; p[2 * s] = r.h.y; p[3 * s] = r.h.z;
+  p[4 * s] = r.I.xx; p[5 * s] = r.I.xy; p[6 * s] = r.I.xz; p[7 * s] = r.I.yy; p[8 * s] = r.I.yz; p[9 * s] = r.I.zz;
+}
+template <typename T> TDS_D Rbi<T> ld_rbi(const T* p, int s) {
+  Rbi<T> r;
+  r.m = p[0]; r.h = v3<T>(p[s], p[2 * s], p[3 * s]);
+  r.I.xx = p[4 * s]; r.I.xy = p[5 * s]; r.I.xz = p[6 * s]; r.I.yy = p[7 * s]; r.I.yz = p[8 * s]; r.I.zz = p[9 * s];
+  return r;
+}
+template <typename TO, typename TI> TDS_D Rbi<TO> cvt_rbi(const Rbi<TI>& a) {
+  Rbi<TO> r;
+  r.m = TO(a.m); r.h = cvt<TO>(a.h);
+  r.I.xx = TO(a.I.xx); r.I.xy = TO(a.I.xy); r.I.xz = TO(a.I.xz); r.I.yy = TO(a.I.yy); r.I.yz = TO(a.I.yz); r.I.zz = TO(a.I.zz);
+  return r;
+}
+template <typename TO, typename TI> TDS_D Sv<TO> cvt_sv(const Sv<TI>& a) { Sv<TO> r; r.top = cvt<TO>(a.top); r.bot = cvt<TO>(a.bot); return r; }
+template <typename T> TDS_D M3<T> transpose(const M3<T>& a) {
+  M3<T> r; r.xx = a.xx; r.xy = a.yx; r.xz = a.zx; r.yx = a.xy; r.yy = a.yy; r.yz = a.zy; r.zx = a.xz; r.zy = a.yz; r.zz = a.zz;
+  return r;
+}
+template <typename T> TDS_D V3<T> col_x(const M3<T>& a) { return v3<T>(a.xx, a.yx, a.zx); }
+template <typename T> TDS_D V3<T> col_y(const M3<T>& a) { return v3<T>(a.xy, a.yy, a.zy); }
+template <typename T> TDS_D V3<T> col_z(const M3<T>& a) { return v3<T>(a.xz, a.yz, a.zz); }
+template <typename T> TDS_D void set_cols(M3<T>& a, V3<T> x, V3<T> y, V3<T> z) {
+  a.xx = x.x; a.yx = x.y; a.zx = x.z; a.xy = y.x; a.yy = y.y; a.zy = y.z; a.xz = z.x; a.yz = z.y; a.zz = z.z;
+}
+template <typename T> TDS_D V3<T> axpy(V3<T> a, T s, V3<T> b) { return v3<T>(a.x * s + b.x, a.y * s + b.y, a.z * s + b.z); }
+
+// accumulator slot: Ia 21 + pA 6 (RA), composite Ic 10 (RC) at word offset x_acc_ic_word
+template <typename T> TDS_D void acc_add27(T* p, int s, const Abi<T>& a, const Sv<T>& f) {
+  p[0] += a.I.xx; p[s] += a.I.xy; p[2 * s] += a.I.xz; p[3 * s] += a.I.yy; p[4 * s] += a.I.yz; p[5 * s] += a.I.zz;
+  p[6 * s] += a.H.xx; p[7 * s] += a.H.xy; p[8 * s] += a.H.xz; p[9 * s] += a.H.yx; p[10 * s] += a.H.yy; p[11 * s] += a.H.yz;
+  p[12 * s] += a.H.zx; p[13 * s] += a.H.zy; p[14 * s] += a.H.zz;
+  p[15 * s] += a.M.xx; p[16 * s] += a.M.xy; p[17 * s] += a.M.xz; p[18 * s] += a.M.yy; p[19 * s] += a.M.yz; p[20 * s] += a.M.zz;
+  p[21 * s] += f.top.x; p[22 * s] += f.top.y; p[23 * s] += f.top.z; p[24 * s] += f.bot.x; p[25 * s] += f.bot.y; p[26 * s] += f.bot.z;
+}
+template <typename T> TDS_D void acc_ld27(const T* p, int s, Abi<T>& a, Sv<T>& f) {
+  a.I.xx = p[0]; a.I.xy = p[s]; a.I.xz = p[2 * s]; a.I.yy = p[3 * s]; a.I.yz = p[4 * s]; a.I.zz = p[5 * s];
+  a.H.xx = p[6 * s]; a.H.xy = p[7 * s]; a.H.xz = p[8 * s]; a.H.yx = p[9 * s]; a.H.yy = p[10 * s]; a.H.yz = p[11 * s];
+  a.H.zx = p[12 * s]; a.H.zy = p[13 * s]; a.H.zz = p[14 * s];
+  a.M.xx = p[15 * s]; a.M.xy = p[16 * s]; a.M.xz = p[17 * s]; a.M.yy = p[18 * s]; a.M.yz = p[19 * s]; a.M.zz = p[20 * s];
+  f.top = v3<T>(p[21 * s], p[22 * s], p[23 * s]); f.bot = v3<T>(p[24 * s], p[25 * s], p[26 * s]);
+}
+template <typename T> TDS_D void rbi_acc(T* p, int s, const Rbi<T>& r) {
+  p[0] += r.m; p[s] += r.h.x; p[2 * s] += r.h.y; p[3 * s] += r.h.z;
+  p[4 * s] += r.I.xx; p[5 * s] += r.I.xy; p[6 * s] += r.I.xz; p[7 * s] += r.I.yy; p[8 * s] += r.I.yz; p[9 * s] += r.I.zz;
+}
+
+// ---- 3x3 register blocks on strided shared memory ------------------------------------------------
+template <typename T> struct B9 { T a[9]; };
+template <typename T> TDS_D B9<T> ldb(const T* p, int s) {
+  B9<T> b;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) b.a[k] = p[k * s];
+  return b;
+}
+template <typename T> TDS_D void stb(T* p, int s, const B9<T>& b) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) p[k * s] = b.a[k];
+}
+// C -= A * B^T
+template <typename T> TDS_D void gemm_nt_sub(B9<T>& C, const B9<T>& A, const B9<T>& B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      C.a[r * 3 + c] -= A.a[r * 3] * B.a[c * 3] + A.a[r * 3 + 1] * B.a[c * 3 + 1] + A.a[r * 3 + 2] * B.a[c * 3 + 2];
+}
+// C -= A * B
+template <typename T> TDS_D void gemm_nn_sub(B9<T>& C, const B9<T>& A, const B9<T>& B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      C.a[r * 3 + c] -= A.a[r * 3] * B.a[c] + A.a[r * 3 + 1] * B.a[3 + c] + A.a[r * 3 + 2] * B.a[6 + c];
+}
+// inverse of the lower Cholesky factor of a diagonal block: i00, i10, i11, i20, i21, i22
+template <typename T> struct L6 { T i00, i10, i11, i20, i21, i22; };
+template <typename T> TDS_D L6<T> chol3_inv(const B9<T>& A) {
+  const T l00 = sqrt_t(A.a[0]);
+  const T i00 = T(1) / l00;
+  const T l10 = A.a[3] * i00, l20 = A.a[6] * i00;
+  const T l11 = sqrt_t(A.a[4] - l10 * l10);
+  const T i11 = T(1) / l11;
+  const T l21 = (A.a[7] - l20 * l10) * i11;
+  const T l22 = sqrt_t(A.a[8] - l20 * l20 - l21 * l21);
+  const T i22 = T(1) / l22;
+  L6<T> r;
+  r.i00 = i00; r.i11 = i11; r.i22 = i22;
+  r.i10 = -l10 * i00 * i11;
+  r.i21 = -l21 * i11 * i22;
+  r.i20 = -(l20 * i00 + l21 * r.i10) * i22;
+  return r;
+}
+template <typename T> TDS_D L6<T> ldl6(const T* p, int s) { L6<T> r; r.i00 = p[0]; r.i10 = p[s]; r.i11 = p[2 * s]; r.i20 = p[3 * s]; r.i21 = p[4 * s]; r.i22 = p[5 * s]; return r; }
+template <typename T> TDS_D void stl6(T* p, int s, const L6<T>& r) { p[0] = r.i00; p[s] = r.i10; p[2 * s] = r.i11; p[3 * s] = r.i20; p[4 * s] = r.i21; p[5 * s] = r.i22; }
+// X = A * Li^T   (off-diagonal block of L = A * L_jj^-T)
+template <typename T> TDS_D B9<T> mul_linvT(const B9<T>& A, const L6<T>& li) {
+  B9<T> X;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    X.a[r * 3] = A.a[r * 3] * li.i00;
+    X.a[r * 3 + 1] = A.a[r * 3] * li.i10 + A.a[r * 3 + 1] * li.i11;
+    X.a[r * 3 + 2] = A.a[r * 3] * li.i20 + A.a[r * 3 + 1] * li.i21 + A.a[r * 3 + 2] * li.i22;
+  }
+  return X;
+}
+// Y = Li * A   (3 right-hand-side columns)
+template <typename T> TDS_D B9<T> linv_mul(const L6<T>& li, const B9<T>& A) {
+  B9<T> Y;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    Y.a[c] = li.i00 * A.a[c];
+    Y.a[3 + c] = li.i10 * A.a[c] + li.i11 * A.a[3 + c];
+    Y.a[6 + c] = li.i20 * A.a[c] + li.i21 * A.a[3 + c] + li.i22 * A.a[6 + c];
+  }
+  return Y;
+}
+
+TDS_D int btri(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * 9; }
+
+template <typename T> TDS_D Rbi<T> model_rbi_of(const double* r) {
+  Rbi<T> o;
+  o.m = T(r[0]); o.h = v3<T>(T(r[1]), T(r[2]), T(r[3]));
+  o.I.xx = T(r[4]); o.I.xy = T(r[5]); o.I.xz = T(r[6]); o.I.yy = T(r[7]); o.I.yz = T(r[8]); o.I.zz = T(r[9]);
+  return o;
+}
+
+template <typename T> TDS_D Sv<T> link_axis(const DevModel& M, int i, V3<T>& ax) {
+  ax = v3<T>(T(M.axis[i][0]), T(M.axis[i][1]), T(M.axis[i][2]));
+  Sv<T> z; z.top = v3<T>(T(0), T(0), T(0)); z.bot = z.top;
+  return z;
+}
+
+enum StepMode { MODE_FD = 0, MODE_NOCONTACT = 1, MODE_FULL = 2 };
+// per-link region, element offsets: [rigid inertia (10 RC) | later U (6 RA), invD, u] then v / c / a (6 RA)
+
+template <typename RA, typename RC, typename RS, bool SMEM>
+__global__ void __launch_bounds__(128, 1)
+tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimParams P,
+                 const __grid_constant__ EnvParams E, const StepIO io, const int mode, const int use_pd,
+                 char* __restrict__ gscratch) {
+  extern __shared__ __align__(16) char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_blk = threadIdx.x >> 5;
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = env < io.n;
+  const int e = live ? env : io.n - 1;
+  Arena A;
+  if (SMEM) { A.blk = smem_raw + (size_t)warp_in_blk * M.x_total * 32 * 4; A.stride = 32; A.col = lane; }
+  else { A.blk = gscratch; A.stride = io.n_stride; A.col = e; }
+  const int ST = A.stride;
+  const int ns = io.n_stride;
+  const int n_links = M.n_links;
+  const int n = M.n_qd;
+  const int nb = M.nb;
+  const int n3 = 3 * nb;
+  int phase_id = 0;
+#define TDSW_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[(size_t)(env >> 5) * 16 + (phase_id++)] = clock64(); } while (0)
+  TDSW_PHASE();
+  constexpr int RAW = (int)(sizeof(RA) / 4), RCW = (int)(sizeof(RC) / 4);
+  float* const qv = A.ptr<float>(M.x_q);
+  float* const qdv = A.ptr<float>(M.x_qd);
+  float* const tauv = A.ptr<float>(M.x_tau);
+  RC* const Sw = A.ptr<RC>(M.x_S);                 // S of link i at Sw + i*6*ST
+  const int LWD = M.x_link_words;
+  const int VOFF = LWD - 6 * RAW;                  // word offset of v/c/a inside a link record
+  RS* const Mb = A.ptr<RS>(M.x_M);
+  RS* const dinv = A.ptr<RS>(M.x_dinv);
+  RS* const wv = A.ptr<RS>(M.x_w);
+
+  // ---- load state, PD torques (locomotion_contact_simulation.h:168-258) ---------------------------
+  for (int k = 0; k < M.n_q; ++k) qv[k * ST] = io.q_in[(size_t)k * ns + e];
+  for (int k = 0; k < n; ++k) qdv[k * ST] = io.qd_in[(size_t)k * ns + e];
+  for (int k = 0; k < n; ++k) tauv[k * ST] = 0.f;
+  if (use_pd) {
+    for (int k = 0; k < E.n_act; ++k) {
+      const int li = E.act_link[k];
+      float a = io.tau_in[(size_t)k * ns + e];
+      a = fmaxf(fminf(a, E.action_limit), -E.action_limit);
+      const float q_des = E.initial_poses[k] + a;
+      float f = E.kp * (q_des - qv[M.q_idx[li] * ST]) + E.kd * (0.f - qdv[M.qd_idx[li] * ST]);
+      f = fminf(fmaxf(f, -E.max_force), E.max_force);
+      tauv[M.qd_idx[li] * ST] = f;
+    }
+  } else if (io.tau_in) {
+    const int off = M.floating ? 6 : 0;
+    for (int k = off; k < n; ++k) tauv[k * ST] = io.tau_in[(size_t)(k - off) * ns + e];
+  }
+  for (int s = 0; s < M.n_acc; ++s) {
+    RA* pa = A.ptr<RA>(M.x_acc + s * M.x_acc_words);
+    for (int k = 0; k < 27; ++k) pa[k * ST] = RA(0);
+    RC* pc = A.ptr<RC>(M.x_acc + s * M.x_acc_words + M.x_acc_ic_word);
+    for (int k = 0; k < 10; ++k) pc[k * ST] = RC(0);
+  }
+  const bool want_contacts = (mode == MODE_FULL) && M.has_plane;
+  TDSW_PHASE();  // 1
+
+  // ---- common-frame origin O (world coordinates) -----------------------------------------------------
+  M3<RC> Rb = m3_identity<RC>();
+  V3<RC> O = v3<RC>(RC(0), RC(0), RC(0));
+  if (M.floating) {
+    Rb = quat_to_matrix<RC>(RC(qv[0]), RC(qv[ST]), RC(qv[2 * ST]), RC(qv[3 * ST]));
+    O = v3<RC>(RC(qv[4 * ST]), RC(qv[5 * ST]), RC(qv[6 * ST]));
+  } else {
+    // end of the translation-only root chain: constant rotations, no trigonometry
+    M3<RC> Rc = m3_identity<RC>();
+    const int kp = M.n_prefix < n_links ? M.n_prefix + 1 : n_links;
+    for (int i = 0; i < kp; ++i) {
+      const double* xt = M.XT[i];
+      O = O + mul(Rc, v3<RC>(RC(xt[9]), RC(xt[10]), RC(xt[11])));
+      if (i == M.n_prefix) break;
+      if (!(M.flags[i] & TDS_LF_XT_IDENT)) {
+        M3<RC> r; r.xx = RC(xt[0]); r.xy = RC(xt[1]); r.xz = RC(xt[2]); r.yx = RC(xt[3]); r.yy = RC(xt[4]); r.yz = RC(xt[5]); r.zx = RC(xt[6]); r.zy = RC(xt[7]); r.zz = RC(xt[8]);
+        Rc = mul(Rc, r);
+      }
+      if (M.flags[i] & TDS_LF_PRISMATIC) {
+        const RC qi = RC(qv[M.q_idx[i] * ST]);
+        O = O + mul(Rc, v3<RC>(RC(M.axis[i][0]) * qi, RC(M.axis[i][1]) * qi, RC(M.axis[i][2]) * qi));
+      }
+    }
+  }
+
+  // ---- pass 1: root -> leaf.  kinematics.hpp:18-148 in the common frame + contact detection ------------
+  const V3<RC> pn = v3<RC>(RC(M.plane_n[0]), RC(M.plane_n[1]), RC(M.plane_n[2]));
+  const RC plane_off = dot(O, pn) - RC(M.plane_c);   // n.(O + x) - c = n.x + plane_off
+  int n_active = 0, pt_index = 0;
+  auto emit_geoms = [&](int li, const M3<RC>& R, const V3<RC>& pr) {
+    for (int g = M.geom_begin[li + 1]; g < M.geom_begin[li + 2]; ++g) {
+      const int ty = M.g_type[g];
+      if (ty != TDSG_SPHERE && ty != TDSG_CAPSULE) continue;
+      const V3<RC> c = pr + mul(R, v3<RC>(RC(M.g_t[g][0]), RC(M.g_t[g][1]), RC(M.g_t[g][2])));
+      const RC rad = RC(M.g_radius[g]);
+      const int npts = (ty == TDSG_CAPSULE) ? 2 : 1;
+      V3<RC> half = v3<RC>(RC(0), RC(0), RC(0));
+      if (ty == TDSG_CAPSULE) half = mul(R, v3<RC>(RC(M.g_half[g][0]), RC(M.g_half[g][1]), RC(M.g_half[g][2])));
+      for (int k = 0; k < npts; ++k) {
+        const V3<RC> pos = (ty == TDSG_CAPSULE) ? (k == 0 ? c + half : c - half) : c;
+        const RC dist = dot(pos, pn) + plane_off - rad;       // contact_point.hpp:112-116
+        if (io.contact_dist && live) io.contact_dist[(size_t)pt_index * ns + e] = (float)dist;
+        ++pt_index;
+        if (dist < RC(0) && n_active < M.max_contacts) {
+          RC* pc = A.ptr<RC>(M.x_con + n_active * 5 * RCW);
+          st3<RC>(pc, ST, pos - pn * rad);                     // world_point_on_b, relative to O
+          pc[3 * ST] = dist;
+          pc[4 * ST] = RC(li);
+          ++n_active;
+        }
+      }
+    }
+  };
+  M3<RC> R_prev = Rb;
+  V3<RC> p_prev = M.floating ? v3<RC>(RC(0), RC(0), RC(0)) : v3<RC>(-O.x, -O.y, -O.z);
+  Sv<RA> v_prev;
+  if (M.floating) {  // base-frame spatial velocity qd[0:6] (kinematics.hpp:45-47) expressed in the common frame
+    const M3<RA> RbA = cvt<RA>(Rb);
+    v_prev.top = mul(RbA, v3<RA>(RA(qdv[0]), RA(qdv[ST]), RA(qdv[2 * ST])));
+    v_prev.bot = mul(RbA, v3<RA>(RA(qdv[3 * ST]), RA(qdv[4 * ST]), RA(qdv[5 * ST])));
+  } else {
+    v_prev.top = v3<RA>(RA(0), RA(0), RA(0)); v_prev.bot = v_prev.top;
+  }
+  const M3<RC> R_base = R_prev;
+  const V3<RC> p_base = p_prev;
+  const Sv<RA> v_base = v_prev;
+  { RC* px = A.ptr<RC>(M.x_xw); st9<RC>(px, ST, R_base); st3<RC>(px + 9 * ST, ST, p_base); }
+  if (want_contacts) emit_geoms(-1, R_base, p_base);
+  for (int i = 0; i < n_links; ++i) {
+    const int p = M.parent[i];
+    const int fl = M.flags[i];
+    M3<RC> Rp; V3<RC> pp; Sv<RA> vp;
+    if (fl & TDS_LF_PARENT_ADJ) { Rp = R_prev; pp = p_prev; vp = v_prev; }
+    else if (p >= 0) {
+      const RC* px = A.ptr<RC>(M.x_xw + (M.xw_slot[p] + 1) * 12 * RCW);
+      Rp = ld9<RC>(px, ST); pp = ld3<RC>(px + 9 * ST, ST);
+      vp = ld6<RA>(A.ptr<RA>(M.x_link + p * LWD + VOFF), ST);
+    } else { Rp = R_base; pp = p_base; vp = v_base; }
+    const double* xt = M.XT[i];
+    V3<RC> pi = pp + mul(Rp, v3<RC>(RC(xt[9]), RC(xt[10]), RC(xt[11])));
+    M3<RC> Ri = Rp;
+    if (!(fl & TDS_LF_XT_IDENT)) {
+      M3<RC> r; r.xx = RC(xt[0]); r.xy = RC(xt[1]); r.xz = RC(xt[2]); r.yx = RC(xt[3]); r.yy = RC(xt[4]); r.yz = RC(xt[5]); r.zx = RC(xt[6]); r.zy = RC(xt[7]); r.zz = RC(xt[8]);
+      Ri = mul(Rp, r);
+    }
+    Sv<RC> S; S.top = v3<RC>(RC(0), RC(0), RC(0)); S.bot = S.top;
+    if (!(fl & TDS_LF_FIXED)) {   // Link::jcalc, link.hpp:229-336
+      const RC qi = RC(qv[M.q_idx[i] * ST]);
+      const int jt = M.jtype[i];
+      const V3<RC> ax = v3<RC>(RC(M.axis[i][0]), RC(M.axis[i][1]), RC(M.axis[i][2]));
+      if (fl & TDS_LF_PRISMATIC) {
+        const V3<RC> d = mul(Ri, ax);
+        pi = axpy(d, qi, pi);
+        S.bot = d;
+      } else {
+        const V3<RC> w = mul(Ri, ax);          // the joint axis is invariant under X_J
+        if (jt == TDSJ_REVOLUTE_AXIS) {        // TinyQuaternion::setRotation(axis, angle), tiny_quaternion.h:178-183
+          const RC dl = sqrt_t(dot(ax, ax));
+          RC s, c;
+          sincos_t(qi * RC(0.5), &s, &c);
+          s = s / dl;
+          Ri = mul(Ri, quat_to_matrix<RC>(ax.x * s, ax.y * s, ax.z * s, c));
+        } else {
+          RC s, c;
+          sincos_t(qi, &s, &c);
+          const V3<RC> cx = col_x(Ri), cy = col_y(Ri), cz = col_z(Ri);
+          if (jt == TDSJ_REVOLUTE_X) set_cols(Ri, cx, axpy(cz, s, cy * c), axpy(cy, -s, cz * c));          // y' = c y + s z, z' = -s y + c z
+          else if (jt == TDSJ_REVOLUTE_Y) set_cols(Ri, axpy(cz, -s, cx * c), cy, axpy(cx, s, cz * c));     // x' = c x - s z, z' = s x + c z
+          else set_cols(Ri, axpy(cy, s, cx * c), axpy(cx, -s, cy * c), cz);                                 // x' = c x + s y, y' = -s x + c y
+        }
+        S.top = w;
+        S.bot = cross(pi, w);
+      }
+    }
+    st6<RC>(Sw + i * 6 * ST, ST, S);
+    if (M.xw_slot[i] >= 0) { RC* px = A.ptr<RC>(M.x_xw + (M.xw_slot[i] + 1) * 12 * RCW); st9<RC>(px, ST, Ri); st3<RC>(px + 9 * ST, ST, pi); }
+    // rigid-body inertia about O in world axes: com c = p_i + R_i com_l, I = R Icom R^T + m (|c|^2 1 - c c^T)
+    {
+      const double* rb = M.rbic[i];
+      Rbi<RC> r;
+      r.m = RC(rb[0]);
+      const V3<RC> c = pi + mul(Ri, v3<RC>(RC(rb[1]), RC(rb[2]), RC(rb[3])));
+      r.h = c * r.m;
+      S3<RC> Ic; Ic.xx = RC(rb[4]); Ic.xy = RC(rb[5]); Ic.xz = RC(rb[6]); Ic.yy = RC(rb[7]); Ic.yz = RC(rb[8]); Ic.zz = RC(rb[9]);
+      r.I = rot_sym(Ri, Ic);
+      const RC cc = dot(c, c);
+      r.I.xx += r.m * (cc - c.x * c.x); r.I.yy += r.m * (cc - c.y * c.y); r.I.zz += r.m * (cc - c.z * c.z);
+      r.I.xy -= r.m * c.x * c.y; r.I.xz -= r.m * c.x * c.z; r.I.yz -= r.m * c.y * c.z;
+      st_rbi<RC>(A.ptr<RC>(M.x_link + i * LWD), ST, r);
+    }
+    Sv<RA> v = vp;
+    if (!(fl & TDS_LF_FIXED)) {
+      const RA qdi = RA(qdv[M.qd_idx[i] * ST]);
+      const Sv<RA> Sf = cvt_sv<RA>(S);
+      v.top = axpy(Sf.top, qdi, v.top);
+      v.bot = axpy(Sf.bot, qdi, v.bot);
+    }
+    st6<RA>(A.ptr<RA>(M.x_link + i * LWD + VOFF), ST, v);
+    if (want_contacts) emit_geoms(i, Ri, pi);
+    if (io.link_xf && live) {
+      float* o = io.link_xf + (size_t)i * 12 * ns + e;
+      o[0] = (float)Ri.xx; o[(size_t)1 * ns] = (float)Ri.xy; o[(size_t)2 * ns] = (float)Ri.xz;
+      o[(size_t)3 * ns] = (float)Ri.yx; o[(size_t)4 * ns] = (float)Ri.yy; o[(size_t)5 * ns] = (float)Ri.yz;
+      o[(size_t)6 * ns] = (float)Ri.zx; o[(size_t)7 * ns] = (float)Ri.zy; o[(size_t)8 * ns] = (float)Ri.zz;
+      o[(size_t)9 * ns] = (float)(pi.x + O.x); o[(size_t)10 * ns] = (float)(pi.y + O.y); o[(size_t)11 * ns] = (float)(pi.z + O.z);
+    }
+    R_prev = Ri; p_prev = pi; v_prev = v;
+  }
+  const bool any_contact = __any_sync(0xffffffffu, n_active > 0);
+  TDSW_PHASE();  // 2
+
+  // ---- pass 2: leaf -> root.  ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ----------
+  if (any_contact) {
+    const int nblk = nb * (nb + 1) / 2 * 9;
+    for (int k = 0; k < nblk; ++k) Mb[k * ST] = RS(0);
+    for (int k = n; k < n3; ++k) Mb[(btri(k / 3, k / 3) + (k % 3) * 4) * ST] = RS(1);   // padding dofs: identity
+  }
+  Abi<RA> cA; Sv<RA> cP; Rbi<RC> cC;
+  for (int i = n_links - 1; i >= 0; --i) {
+    const int p = M.parent[i];
+    const int fl = M.flags[i];
+    RC* const rec = A.ptr<RC>(M.x_link + i * LWD);
+    RA* const vrec = A.ptr<RA>(M.x_link + i * LWD + VOFF);
+    Rbi<RC> Ic = ld_rbi<RC>(rec, ST);
+    const Rbi<RA> rb = cvt_rbi<RA>(Ic);
+    const Sv<RA> v = ld6<RA>(vrec, ST);
+    Abi<RA> Ia = abi_from_rbi(rb);
+    Sv<RA> pA = cross_mf(v, rbi_mul(rb, v));                 // kinematics.hpp:132
+    if (fl & TDS_LF_CHILD_ADJ) { abi_add(Ia, cA); pA = pA + cP; rbi_add(Ic, cC); }
+    if (M.acc_slot[i] >= 0) {
+      Abi<RA> sa; Sv<RA> sp;
+      acc_ld27<RA>(A.ptr<RA>(M.x_acc + M.acc_slot[i] * M.x_acc_words), ST, sa, sp);
+      abi_add(Ia, sa); pA = pA + sp;
+      rbi_add(Ic, ld_rbi<RC>(A.ptr<RC>(M.x_acc + M.acc_slot[i] * M.x_acc_words + M.x_acc_ic_word), ST));
+    }
+    Sv<RA> pa = pA;
+    // U (6), invD, u overwrite the rigid-inertia record.  The RA and RC views interleave lanes differently, so
+    // every lane must have finished reading its RC record before any lane writes the RA view.
+    __syncwarp();
+    RA* const urec = A.ptr<RA>(M.x_link + i * LWD);
+    if (fl & TDS_LF_FIXED) {
+      Sv<RA> z; z.top = v3<RA>(RA(0), RA(0), RA(0)); z.bot = z.top;
+      st6<RA>(vrec, ST, z);
+      st6<RA>(urec, ST, z);
+      urec[6 * ST] = RA(0); urec[7 * ST] = RA(0);
+    } else {
+      const Sv<RC> Sd = ld6<RC>(Sw + i * 6 * ST, ST);
+      const Sv<RA> S = cvt_sv<RA>(Sd);
+      const int qdi = M.qd_idx[i];
+      const RA qdj = RA(qdv[qdi * ST]);
+      Sv<RA> vJ; vJ.top = S.top * qdj; vJ.bot = S.bot * qdj;
+      const Sv<RA> c = cross_mm(v, vJ);                      // kinematics.hpp:96-97
+      const Sv<RA> U = abi_mul(Ia, S);                       // forward_dynamics.hpp:111
+      const RA D = dot(S, U);
+      const RA invD = RA(1) / D;
+      RA tau = RA(tauv[qdi * ST]);
+      tau -= RA(M.stiffness[i]) * RA(qv[M.q_idx[i] * ST]);
+      tau -= RA(M.damping[i]) * qdj;
+      const RA u = tau - dot(S, pA);                         // :129
+      st6<RA>(vrec, ST, c);
+      st6<RA>(urec, ST, U);
+      urec[6 * ST] = invD; urec[7 * ST] = u;
+      const V3<RA> ut = U.top * invD, ub = U.bot * invD;     // Ia -= U (U/D)^T, :160-168
+      Ia.I.xx -= U.top.x * ut.x; Ia.I.xy -= U.top.x * ut.y; Ia.I.xz -= U.top.x * ut.z;
+      Ia.I.yy -= U.top.y * ut.y; Ia.I.yz -= U.top.y * ut.z; Ia.I.zz -= U.top.z * ut.z;
+      Ia.H.xx -= U.top.x * ub.x; Ia.H.xy -= U.top.x * ub.y; Ia.H.xz -= U.top.x * ub.z;
+      Ia.H.yx -= U.top.y * ub.x; Ia.H.yy -= U.top.y * ub.y; Ia.H.yz -= U.top.y * ub.z;
+      Ia.H.zx -= U.top.z * ub.x; Ia.H.zy -= U.top.z * ub.y; Ia.H.zz -= U.top.z * ub.z;
+      Ia.M.xx -= U.bot.x * ub.x; Ia.M.xy -= U.bot.x * ub.y; Ia.M.xz -= U.bot.x * ub.z;
+      Ia.M.yy -= U.bot.y * ub.y; Ia.M.yz -= U.bot.y * ub.z; Ia.M.zz -= U.bot.z * ub.z;
+      const Sv<RA> Iac = abi_mul(Ia, c);                     // :171
+      const RA uD = u * invD;
+      pa.top = pA.top + Iac.top + U.top * uD;                // :173
+      pa.bot = pA.bot + Iac.bot + U.bot * uD;
+      if (any_contact) {   // CRBA column, mass_matrix.hpp:86-111: M_ij = S_j . (Ic_i S_i), no transforms needed
+        const Sv<RC> F = rbi_mul(Ic, Sd);
+        const int bi = qdi / 3, ri = qdi - 3 * bi;
+        Mb[(btri(bi, bi) + ri * 4) * ST] = RS(dot(Sd, F));
+        for (int j = M.parent[i]; j >= 0; j = M.parent[j]) {
+          if (M.flags[j] & TDS_LF_FIXED) continue;
+          const int qj = M.qd_idx[j];
+          const int bj = qj / 3, cj = qj - 3 * bj;
+          Mb[(btri(bi, bj) + ri * 3 + cj) * ST] = RS(dot(ld6<RC>(Sw + j * 6 * ST, ST), F));
+        }
+        if (M.floating) {  // base columns: F in the base frame (:107-111); O is the base origin
+          const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
+          RS* row0 = Mb + (btri(bi, 0) + ri * 3) * ST;
+          RS* row1 = Mb + (btri(bi, 1) + ri * 3) * ST;
+          row0[0] = RS(ft.x); row0[ST] = RS(ft.y); row0[2 * ST] = RS(ft.z);
+          row1[0] = RS(fb.x); row1[ST] = RS(fb.y); row1[2 * ST] = RS(fb.z);
+        }
+      }
+    }
+    // hand (Ia, pa, Ic) to the parent: plain sums in the common frame
+    if (fl & TDS_LF_PARENT_ADJ) { cA = Ia; cP = pa; cC = Ic; }
+    else {
+      const int slot = (p >= 0) ? M.acc_slot[p] : M.base_acc;
+      if (slot >= 0) {
+        acc_add27<RA>(A.ptr<RA>(M.x_acc + slot * M.x_acc_words), ST, Ia, pa);
+        rbi_acc<RC>(A.ptr<RC>(M.x_acc + slot * M.x_acc_words + M.x_acc_ic_word), ST, Ic);
+      }
+    }
+  }
+  TDSW_PHASE();  // 3
+
+  // ---- base acceleration (forward_dynamics.hpp:218-243) ----------------------------------------------------
+  Sv<RA> a_prev;
+  Sv<RC> base_acc_b;   // base-frame value of the reference (floating) - needed for qdd[0:6]
+  base_acc_b.top = v3<RC>(RC(0), RC(0), RC(0)); base_acc_b.bot = base_acc_b.top;
+  if (M.floating) {
+    // children sums in the common frame -> base frame (pure rotation: O is the base origin)
+    Abi<RA> Ach; Sv<RA> pch; Rbi<RC> Icch;
+    Ach.I = {RA(0), RA(0), RA(0), RA(0), RA(0), RA(0)}; Ach.M = Ach.I;
+    Ach.H.xx = Ach.H.xy = Ach.H.xz = Ach.H.yx = Ach.H.yy = Ach.H.yz = Ach.H.zx = Ach.H.zy = Ach.H.zz = RA(0);
+    pch.top = v3<RA>(RA(0), RA(0), RA(0)); pch.bot = pch.top;
+    Icch.m = RC(0); Icch.h = v3<RC>(RC(0), RC(0), RC(0)); Icch.I = {RC(0), RC(0), RC(0), RC(0), RC(0), RC(0)};
+    if (n_links > 0 && M.parent[0] < 0) { abi_add(Ach, cA); pch = pch + cP; rbi_add(Icch, cC); }
+    if (M.base_acc >= 0) {
+      Abi<RA> sa; Sv<RA> sp;
+      acc_ld27<RA>(A.ptr<RA>(M.x_acc + M.base_acc * M.x_acc_words), ST, sa, sp);
+      abi_add(Ach, sa); pch = pch + sp;
+      rbi_add(Icch, ld_rbi<RC>(A.ptr<RC>(M.x_acc + M.base_acc * M.x_acc_words + M.x_acc_ic_word), ST));
+    }
+    const M3<RA> Rt = cvt<RA>(transpose(Rb));
+    Abi<RA> Ab;
+    {
+      Rbi<RA> rbb = model_rbi_of<RA>(M.base_rbi);
+      Ab = abi_from_rbi(rbb);
+      Abi<RA> Arot;
+      Arot.I = rot_sym(Rt, Ach.I); Arot.M = rot_sym(Rt, Ach.M); Arot.H = rot_gen(Rt, Ach.H);
+      abi_add(Ab, Arot);
+    }
+    Sv<RA> pb;
+    {
+      // gyroscopic bias, kinematics.hpp:54-61 (reference mixes frames here; reproduced as written)
+      const M3<RA> RbA = cvt<RA>(Rb);
+      M3<RA> Ic0;
+      Ic0.xx = RA(M.base_inertia_com[0]); Ic0.xy = RA(M.base_inertia_com[1]); Ic0.xz = RA(M.base_inertia_com[2]);
+      Ic0.yx = RA(M.base_inertia_com[3]); Ic0.yy = RA(M.base_inertia_com[4]); Ic0.yz = RA(M.base_inertia_com[5]);
+      Ic0.zx = RA(M.base_inertia_com[6]); Ic0.zy = RA(M.base_inertia_com[7]); Ic0.zz = RA(M.base_inertia_com[8]);
+      const M3<RA> Iw = rot_gen(RbA, Ic0);
+      const V3<RA> wb = v3<RA>(RA(qdv[0]), RA(qdv[ST]), RA(qdv[2 * ST]));
+      pb.top = cross(wb, mul(Iw, wb)) + mul(Rt, pch.top);
+      pb.bot = mul(Rt, pch.bot);
+    }
+    if (any_contact) {  // mass_matrix.hpp:114-120: base block = composite inertia in the base frame
+      Rbi<RC> Ib = model_rbi_of<RC>(M.base_rbi);
+      const M3<RC> RtC = transpose(Rb);
+      Rbi<RC> rot; rot.m = Icch.m; rot.h = mul(RtC, Icch.h); rot.I = rot_sym(RtC, Icch.I);
+      rbi_add(Ib, rot);
+      const RS z = RS(0);
+      RS* b00 = Mb + btri(0, 0) * ST; RS* b10 = Mb + btri(1, 0) * ST; RS* b11 = Mb + btri(1, 1) * ST;
+      b00[0] = RS(Ib.I.xx); b00[3 * ST] = RS(Ib.I.xy); b00[4 * ST] = RS(Ib.I.yy); b00[6 * ST] = RS(Ib.I.xz); b00[7 * ST] = RS(Ib.I.yz); b00[8 * ST] = RS(Ib.I.zz);
+      // rows 3..5, cols 0..2: H^T with H = h x
+      b10[0] = z;               b10[ST] = RS(Ib.h.z);      b10[2 * ST] = RS(-Ib.h.y);
+      b10[3 * ST] = RS(-Ib.h.z); b10[4 * ST] = z;           b10[5 * ST] = RS(Ib.h.x);
+      b10[6 * ST] = RS(Ib.h.y);  b10[7 * ST] = RS(-Ib.h.x); b10[8 * ST] = z;
+      b11[0] = RS(Ib.m); b11[3 * ST] = z; b11[4 * ST] = RS(Ib.m); b11[6 * ST] = z; b11[7 * ST] = z; b11[8 * ST] = RS(Ib.m);
+    }
+    // -base_abi.inv_mul(bias) with the reference's block inverse (C = -H), inertia.hpp:302-328
+    {
+      M3<RC> I3, H3, M3m;
+      I3.xx = Ab.I.xx; I3.xy = Ab.I.xy; I3.xz = Ab.I.xz; I3.yx = Ab.I.xy; I3.yy = Ab.I.yy; I3.yz = Ab.I.yz; I3.zx = Ab.I.xz; I3.zy = Ab.I.yz; I3.zz = Ab.I.zz;
+      H3 = cvt<RC>(Ab.H);
+      M3m.xx = Ab.M.xx; M3m.xy = Ab.M.xy; M3m.xz = Ab.M.xz; M3m.yx = Ab.M.xy; M3m.yy = Ab.M.yy; M3m.yz = Ab.M.yz; M3m.zx = Ab.M.xz; M3m.zy = Ab.M.yz; M3m.zz = Ab.M.zz;
+      auto inv3 = [](const M3<RC>& m) {
+        M3<RC> o;
+        RC c0 = m.yy * m.zz - m.yz * m.zy, c1 = m.yz * m.zx - m.yx * m.zz, c2 = m.yx * m.zy - m.yy * m.zx;
+        RC s = RC(1) / (m.xx * c0 + m.xy * c1 + m.xz * c2);
+        o.xx = c0 * s; o.xy = (m.xz * m.zy - m.xy * m.zz) * s; o.xz = (m.xy * m.yz - m.xz * m.yy) * s;
+        o.yx = c1 * s; o.yy = (m.xx * m.zz - m.xz * m.zx) * s; o.yz = (m.xz * m.yx - m.xx * m.yz) * s;
+        o.zx = c2 * s; o.zy = (m.xy * m.zx - m.xx * m.zy) * s; o.zz = (m.xx * m.yy - m.xy * m.yx) * s;
+        return o;
+      };
+      auto neg = [](M3<RC> m) { m.xx = -m.xx; m.xy = -m.xy; m.xz = -m.xz; m.yx = -m.yx; m.yy = -m.yy; m.yz = -m.yz; m.zx = -m.zx; m.zy = -m.zy; m.zz = -m.zz; return m; };
+      auto sub = [](M3<RC> a, const M3<RC>& b) { a.xx -= b.xx; a.xy -= b.xy; a.xz -= b.xz; a.yx -= b.yx; a.yy -= b.yy; a.yz -= b.yz; a.zx -= b.zx; a.zy -= b.zy; a.zz -= b.zz; return a; };
+      auto add = [](M3<RC> a, const M3<RC>& b) { a.xx += b.xx; a.xy += b.xy; a.xz += b.xz; a.yx += b.yx; a.yy += b.yy; a.yz += b.yz; a.zx += b.zx; a.zy += b.zy; a.zz += b.zz; return a; };
+      M3<RC> Ainv = inv3(I3);
+      M3<RC> C = neg(H3);
+      M3<RC> D = inv3(sub(M3m, mul(mul(C, Ainv), H3)));
+      M3<RC> AinvBD = mul(mul(Ainv, H3), D);
+      M3<RC> Ii = add(Ainv, mul(mul(AinvBD, C), Ainv));
+      M3<RC> Hi = neg(AinvBD);
+      V3<RC> ft = cvt<RC>(pb.top), fb = cvt<RC>(pb.bot);
+      V3<RC> at = mul(Ii, ft) + mul(Hi, fb);
+      V3<RC> ab = mul(D, fb) + mulT(Hi, ft);
+      base_acc_b.top = v3<RC>(-at.x, -at.y, -at.z);
+      base_acc_b.bot = v3<RC>(-ab.x, -ab.y, -ab.z);
+    }
+    a_prev.top = cvt<RA>(mul(Rb, base_acc_b.top));
+    a_prev.bot = cvt<RA>(mul(Rb, base_acc_b.bot));
+  } else {
+    a_prev.top = v3<RA>(RA(0), RA(0), RA(0));
+    a_prev.bot = v3<RA>(RA(-P.gravity[0]), RA(-P.gravity[1]), RA(-P.gravity[2]));
+  }
+  const Sv<RA> a_base = a_prev;
+  const RA dtA = RA(P.dt);
+
+  // ---- pass 3: root -> leaf (forward_dynamics.hpp:245-302) + integrate_euler_qdd (integrator.hpp:141-195) ----
+  for (int i = 0; i < n_links; ++i) {
+    const int p = M.parent[i];
+    const int fl = M.flags[i];
+    RA* const vrec = A.ptr<RA>(M.x_link + i * LWD + VOFF);
+    Sv<RA> a;
+    if (fl & TDS_LF_PARENT_ADJ) a = a_prev;
+    else if (p >= 0) a = ld6<RA>(A.ptr<RA>(M.x_link + p * LWD + VOFF), ST);
+    else a = a_base;
+    if (!(fl & TDS_LF_FIXED)) {
+      const RA* urec = A.ptr<RA>(M.x_link + i * LWD);
+      const Sv<RA> c = ld6<RA>(vrec, ST);
+      const Sv<RA> U = ld6<RA>(urec, ST);
+      a = a + c;
+      const RA qdd = urec[6 * ST] * (urec[7 * ST] - dot(U, a));
+      const Sv<RA> S = cvt_sv<RA>(ld6<RC>(Sw + i * 6 * ST, ST));
+      a.top = axpy(S.top, qdd, a.top);
+      a.bot = axpy(S.bot, qdd, a.bot);
+      const int qdi = M.qd_idx[i];
+      if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)qdi * ns + e] = (float)qdd; }
+      else qdv[qdi * ST] = (float)(RA(qdv[qdi * ST]) + qdd * dtA);
+    }
+    st6<RA>(vrec, ST, a);
+    a_prev = a;
+  }
+  if (M.floating) {  // forward_dynamics.hpp:317-322 (gravity added un-rotated), integrator.hpp:153-163
+    const RC qb[6] = {base_acc_b.top.x, base_acc_b.top.y, base_acc_b.top.z, base_acc_b.bot.x + RC(P.gravity[0]),
+                      base_acc_b.bot.y + RC(P.gravity[1]), base_acc_b.bot.z + RC(P.gravity[2])};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
+      else qdv[k * ST] = (float)(RC(qdv[k * ST]) + qb[k] * RC(P.dt));
+    }
+  }
+  TDSW_PHASE();  // 4
+  if (mode == MODE_FD) return;
+
+  // ---- contact solve -------------------------------------------------------------------------------------------
+  __syncwarp();   // the Y rows below reuse the per-link records with another lane interleave
+  if (mode == MODE_FULL && any_contact) {
+    // blocked Cholesky M = L L^T (3x3 blocks, lower): off-diagonal blocks of L overwrite M, diagonal blocks are
+    // kept as their inverses.  (The reference inverts M, tiny_matrix_x.h:240-344; only M^-1 products are needed.)
+    for (int bi = 0; bi < nb; ++bi) {
+      for (int bj = 0; bj <= bi; ++bj) {
+        B9<RS> Ab = ldb<RS>(Mb + btri(bi, bj) * ST, ST);
+        for (int bk = 0; bk < bj; ++bk)
+          gemm_nt_sub(Ab, ldb<RS>(Mb + btri(bi, bk) * ST, ST), ldb<RS>(Mb + btri(bj, bk) * ST, ST));
+        if (bj < bi) stb<RS>(Mb + btri(bi, bj) * ST, ST, mul_linvT(Ab, ldl6<RS>(dinv + bj * 6 * ST, ST)));
+        else stl6<RS>(dinv + bi * 6 * ST, ST, chol3_inv(Ab));
+      }
+    }
+    TDSW_PHASE();  // 5
+    const int max_active = __reduce_max_sync(0xffffffffu, n_active);
+    const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b
+    const V3<RC> f1 = v3<RC>(RC(M.fr1[0]), RC(M.fr1[1]), RC(M.fr1[2]));
+    const V3<RC> f2 = v3<RC>(RC(M.fr2[0]), RC(M.fr2[1]), RC(M.fr2[2]));
+    for (int c = 0; c < max_active; ++c) {
+      if (c < n_active) {
+        const RC* pc = A.ptr<RC>(M.x_con + c * 5 * RCW);
+        RS* const Y = A.ptr<RS>(M.x_Y) + c * n3 * 3 * ST;       // [dof k][rhs] : element (3k + rhs)
+        const V3<RC> xc = ld3<RC>(pc, ST);
+        const RC dist = pc[3 * ST];
+        const int L = (int)pc[4 * ST];
+        for (int k = 0; k < 3 * n3; ++k) Y[k * ST] = RS(0);
+        V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));                  // vel_b = J qd
+        if (M.floating) {  // jacobian.hpp:39-58 with r = x_c (O is the base origin)
+          const V3<RC> cols[6] = {v3<RC>(RC(0), -xc.z, xc.y), v3<RC>(xc.z, RC(0), -xc.x), v3<RC>(-xc.y, xc.x, RC(0)),
+                                  v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            Y[(3 * k) * ST] = RS(dot(nbv, cols[k])); Y[(3 * k + 1) * ST] = RS(dot(f1, cols[k])); Y[(3 * k + 2) * ST] = RS(dot(f2, cols[k]));
+            vel = vel + cols[k] * RC(qdv[k * ST]);
+          }
+        }
+        for (int j = L; j >= 0; j = M.parent[j]) {  // jacobian.hpp:63-80: column = S_j evaluated at the contact point
+          if (M.flags[j] & TDS_LF_FIXED) continue;
+          const Sv<RC> S = ld6<RC>(Sw + j * 6 * ST, ST);
+          const V3<RC> col = S.bot + cross(S.top, xc);
+          const int qj = M.qd_idx[j];
+          Y[(3 * qj) * ST] = RS(dot(nbv, col)); Y[(3 * qj + 1) * ST] = RS(dot(f1, col)); Y[(3 * qj + 2) * ST] = RS(dot(f2, col));
+          vel = vel + col * RC(qdv[qj * ST]);
+        }
+        // rel_vel = vel_a - vel_b = -vel ; mb_constraint_solver.hpp:299-345
+        RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;   // b[3], x[3]
+        cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
+        cs[ST] = RS(dot(f1, vel));
+        cs[2 * ST] = RS(dot(f2, vel));
+        cs[3 * ST] = RS(0); cs[4 * ST] = RS(0); cs[5 * ST] = RS(0);
+        // Y <- L^-1 Y (blocked forward substitution, 3 right-hand sides)
+        for (int bi = 0; bi < nb; ++bi) {
+          B9<RS> a = ldb<RS>(Y + bi * 9 * ST, ST);
+          for (int bk = 0; bk < bi; ++bk) gemm_nn_sub(a, ldb<RS>(Mb + btri(bi, bk) * ST, ST), ldb<RS>(Y + bk * 9 * ST, ST));
+          stb<RS>(Y + bi * 9 * ST, ST, linv_mul(ldl6<RS>(dinv + bi * 6 * ST, ST), a));
+        }
+      }
+    }
+    TDSW_PHASE();  // 6
+    // matrix-free projected Gauss-Seidel on w = Y p; row order normals | friction-1 | friction-2
+    // (solve_pgs, mb_constraint_solver.hpp:101-142; bounds :417-436)
+    for (int k = 0; k < n3; ++k) wv[k * ST] = RS(0);
+    const RS cfm = RS(P.cfm), mu = RS(P.friction);
+    for (int it = 0; it < P.pgs_iterations; ++it) {
+      for (int blk = 0; blk < 3; ++blk) {
+        for (int c = 0; c < max_active; ++c) {
+          if (c < n_active) {
+            RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;
+            const RS* y = A.ptr<RS>(M.x_Y) + (c * n3 * 3 + blk) * ST;     // element k at y[3k * ST]
+            RS yy0 = RS(0), yy1 = RS(0), yy2 = RS(0), yw0 = RS(0), yw1 = RS(0), yw2 = RS(0);
+            for (int b = 0; b < nb; ++b) {
+              const RS y0 = y[(9 * b) * ST], y1 = y[(9 * b + 3) * ST], y2 = y[(9 * b + 6) * ST];
+              yy0 += y0 * y0; yy1 += y1 * y1; yy2 += y2 * y2;
+              yw0 += y0 * wv[(3 * b) * ST]; yw1 += y1 * wv[(3 * b + 1) * ST]; yw2 += y2 * wv[(3 * b + 2) * ST];
+            }
+            const RS yy = (yy0 + yy1) + yy2, yw = (yw0 + yw1) + yw2;
+            const RS x_old = cs[(3 + blk) * ST];
+            RS x = (cs[blk * ST] - yw + yy * x_old) / (yy + cfm);
+            if (blk == 0) {
+              x = x < RS(0) ? RS(0) : x;
+              x = x > RS(100000) ? RS(100000) : x;
+            } else {
+              RS s = cs[3 * ST];
+              s = s < RS(0) ? RS(0) : s;
+              const RS lim = mu * s;
+              x = x < -lim ? -lim : x;
+              x = x > lim ? lim : x;
+            }
+            cs[(3 + blk) * ST] = x;
+            const RS dx = x - x_old;
+            for (int b = 0; b < nb; ++b) {
+              wv[(3 * b) * ST] += dx * y[(9 * b) * ST];
+              wv[(3 * b + 1) * ST] += dx * y[(9 * b + 3) * ST];
+              wv[(3 * b + 2) * ST] += dx * y[(9 * b + 6) * ST];
+            }
+          }
+        }
+      }
+    }
+    TDSW_PHASE();  // 7
+    // qd_b -= M^-1 Jc^T p = L^-T w   (mb_constraint_solver.hpp:476-497), blocked back substitution
+    for (int bi = nb - 1; bi >= 0; --bi) {
+      RS a0 = wv[(3 * bi) * ST], a1 = wv[(3 * bi + 1) * ST], a2 = wv[(3 * bi + 2) * ST];
+      for (int bk = bi + 1; bk < nb; ++bk) {
+        const B9<RS> Lb = ldb<RS>(Mb + btri(bk, bi) * ST, ST);
+        const RS z0 = wv[(3 * bk) * ST], z1 = wv[(3 * bk + 1) * ST], z2 = wv[(3 * bk + 2) * ST];
+        a0 -= Lb.a[0] * z0 + Lb.a[3] * z1 + Lb.a[6] * z2;
+        a1 -= Lb.a[1] * z0 + Lb.a[4] * z1 + Lb.a[7] * z2;
+        a2 -= Lb.a[2] * z0 + Lb.a[5] * z1 + Lb.a[8] * z2;
+      }
+      const L6<RS> li = ldl6<RS>(dinv + bi * 6 * ST, ST);
+      const RS z0 = li.i00 * a0 + li.i10 * a1 + li.i20 * a2;
+      const RS z1 = li.i11 * a1 + li.i21 * a2;
+      const RS z2 = li.i22 * a2;
+      wv[(3 * bi) * ST] = z0; wv[(3 * bi + 1) * ST] = z1; wv[(3 * bi + 2) * ST] = z2;
+    }
+    if (n_active > 0)
+      for (int k = 0; k < n; ++k) qdv[k * ST] = (float)(RS(qdv[k * ST]) - wv[k * ST]);
+  }
+  TDSW_PHASE();  // 8
+
+  // ---- integrate_euler with qdd = 0 (integrator.hpp:10-133) -----------------------------------------------------
+  RC up_z = RC(1);
+  if (M.floating) {
+    const RC h = RC(0.5) * RC(P.dt);
+    RC qx = RC(qv[0]), qy = RC(qv[ST]), qz = RC(qv[2 * ST]), qw = RC(qv[3 * ST]);
+    const RC w0 = RC(qdv[0]), w1 = RC(qdv[ST]), w2 = RC(qdv[2 * ST]);
+    const RC dw = (-qx * w0 - qy * w1 - qz * w2) * h;
+    const RC dx = (qw * w0 + qz * w1 - qy * w2) * h;
+    const RC dy = (qw * w1 + qx * w2 - qz * w0) * h;
+    const RC dz = (qw * w2 + qy * w0 - qx * w1) * h;
+    qx += dx; qy += dy; qz += dz; qw += dw;
+    const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx /= len; qy /= len; qz /= len; qw /= len;
+    qv[0] = (float)qx; qv[ST] = (float)qy; qv[2 * ST] = (float)qz; qv[3 * ST] = (float)qw;
+    for (int k = 0; k < 3; ++k)
+      qv[(4 + k) * ST] = (float)(RC(qv[(4 + k) * ST]) + RC(qdv[(3 + k) * ST]) * RC(P.dt));
+    up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
+  }
+  for (int i = 0; i < n_links; ++i) {
+    if (M.flags[i] & TDS_LF_FIXED) continue;
+    const int qi = M.q_idx[i];
+    qv[qi * ST] = (float)(RC(qv[qi * ST]) + RC(qdv[M.qd_idx[i] * ST]) * RC(P.dt));
+  }
+
+  // ---- reward / done / auto-reset, write back ------------------------------------------------------------------------
+  if (live) {
+    bool done = false;
+    if (E.reward_kind == 1) {   // laikago_environment2.h:130-171 (fixed-base emulation)
+      const float x = qv[0], z = qv[2 * ST];
+      const float upz = cosf(qv[3 * ST]) * cosf(qv[4 * ST]);
+      done = (upz < 0.6f) || (z < 0.2f);
+      if (io.reward) io.reward[e] = done ? 0.f : x;
+    } else if (E.reward_kind == 2) {
+      const float x = qv[4 * ST], z = qv[6 * ST];
+      done = ((float)up_z < 0.6f) || (z < 0.2f);
+      if (io.reward) io.reward[e] = done ? 0.f : x;
+    }
+    if (io.done && E.reward_kind) io.done[e] = done ? 1.f : 0.f;
+    if (done && E.auto_reset) {   // ars_vectorized_environment.h:262-283
+      for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = E.reset_q[k];
+      for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = 0.f;
+    } else {
+      for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = qv[k * ST];
+      for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = qdv[k * ST];
+    }
+  }
+  TDSW_PHASE();  // 9
+}
+
+}  // namespace tdsw
+
+extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
+                                int mode, int use_pd, int precision, char* gscratch, int use_smem,
+                                int warps_per_block, cudaStream_t stream) {
+  using namespace tdsw;
+  const int threads = 32 * warps_per_block;
+  const int blocks = (io->n + threads - 1) / threads;
+  const size_t smem = use_smem ? (size_t)warps_per_block * M->x_total * 32 * 4 : 0;
+  cudaError_t err = cudaSuccess;
+#define TDSW_LAUNCH(RA, RC, RS, SM)                                                                     \
+  do {                                                                                                  \
+    auto k = tds_stepw_kernel<RA, RC, RS, SM>;                                                          \
+    static size_t smem_set = 0;                                                                         \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                          \
+      err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      if (err == cudaSuccess) smem_set = smem;                                                          \
+    }                                                                                                   \
+    if (err == cudaSuccess) {                                                                           \
+      k<<<blocks, threads, smem, stream>>>(*M, *P, *E, *io, mode, use_pd, gscratch);                    \
+      err = cudaGetLastError();                                                                         \
+    }                                                                                                   \
+  } while (0)
+  if (precision == 0) { if (use_smem) TDSW_LAUNCH(float, double, float, true); else TDSW_LAUNCH(float, double, float, false); }
+  else if (precision == 1) { if (use_smem) TDSW_LAUNCH(double, double, double, true); else TDSW_LAUNCH(double, double, double, false); }
+  else { if (use_smem) TDSW_LAUNCH(float, float, float, true); else TDSW_LAUNCH(float, float, float, false); }
+#undef TDSW_LAUNCH
+  return (int)err;
+}

@@ -13,6 +13,7 @@
 #define TDS_LF_REVOLUTE 4
 #define TDS_LF_PRISMATIC 8
 #define TDS_LF_FIXED 16
+#define TDS_LF_XT_IDENT 32     // X_T rotation is the identity
 
 // Device model: constant for all environments, passed as a __grid_constant__ kernel parameter
 // (lives in the constant bank; every lane reads the same entry -> broadcast).
@@ -26,6 +27,17 @@ struct DevModel {
   int w_q, w_qd, w_tau, w_link, w_acc, w_xw, w_M, w_invd, w_w, w_con, w_conS, w_Y, w_total;
   int link_words;    // words per link in the per-link region
   int acc_words, acc_ic_word;  // accumulator slot stride / offset of its Ic part (words)
+  // ---- layout of the world-frame kernel (tds_stepw.cu), 4-byte words ----
+  int x_q, x_qd, x_tau, x_S, x_link, x_xw, x_acc, x_M, x_dinv, x_w, x_con, x_conS, x_Y, x_total;
+  int x_link_words, x_acc_words, x_acc_ic_word;
+  int nb;            // number of 3x3 dof blocks (n_qd padded to a multiple of 3)
+  int n_prefix;      // leading chain links with prismatic / fixed joints only: the common-frame origin is the
+                     // world position of link n_prefix (computable without trigonometry); -1: floating base
+  int n_xw;          // links whose world transform must be kept for non-adjacent children
+  int xw_slot[TDS_MAX_LINKS];
+  int geom_begin[TDS_MAX_LINKS + 2];   // geoms of link i (-1 = base) are [geom_begin[i+1], geom_begin[i+2])
+  double rbic[TDS_MAX_LINKS][10];      // mass, com (link frame) [3], inertia about the com (xx,xy,xz,yy,yz,zz)
+  double base_rbic[10];
   int parent[TDS_MAX_LINKS];
   int jtype[TDS_MAX_LINKS];
   int q_idx[TDS_MAX_LINKS];
