@@ -198,9 +198,9 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
     A.stride = 32;
     A.col = lane;
   } else {
-    A.blk = gscratch;
-    A.stride = io.n_stride;
-    A.col = e;
+    A.blk = gscratch + (size_t)(env >> 5) * M.w_total * 32 * 4;   // per-warp block, same addressing as shared memory
+    A.stride = 32;
+    A.col = lane;
   }
   const int ST = A.stride;
   const int ns = io.n_stride;

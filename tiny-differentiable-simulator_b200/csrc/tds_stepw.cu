@@ -206,7 +206,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   const int e = live ? env : io.n - 1;
   Arena A;
   if (SMEM) { A.blk = smem_raw + (size_t)warp_in_blk * M.x_total * 32 * 4; A.stride = 32; A.col = lane; }
-  else { A.blk = gscratch; A.stride = io.n_stride; A.col = e; }
+  else { A.blk = gscratch + (size_t)(env >> 5) * M.x_total * 32 * 4; A.stride = 32; A.col = lane; }  // per-warp block, same addressing as shared memory
   const int ST = A.stride;
   const int ns = io.n_stride;
   const int n_links = M.n_links;
@@ -377,8 +377,11 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       r.m = RC(rb[0]);
       const V3<RC> c = pi + mul(Ri, v3<RC>(RC(rb[1]), RC(rb[2]), RC(rb[3])));
       r.h = c * r.m;
-      S3<RC> Ic; Ic.xx = RC(rb[4]); Ic.xy = RC(rb[5]); Ic.xz = RC(rb[6]); Ic.yy = RC(rb[7]); Ic.yz = RC(rb[8]); Ic.zz = RC(rb[9]);
-      r.I = rot_sym(Ri, Ic);
+      // R Icom R^T enters every product additively (no cancellation) -> RA precision is enough; the parallel-axis
+      // terms m(|c|^2 1 - c c^T) and h = m c cancel against each other in M_ij and stay in RC.
+      S3<RA> Icf; Icf.xx = RA(rb[4]); Icf.xy = RA(rb[5]); Icf.xz = RA(rb[6]); Icf.yy = RA(rb[7]); Icf.yz = RA(rb[8]); Icf.zz = RA(rb[9]);
+      const S3<RA> Irot = rot_sym(cvt<RA>(Ri), Icf);
+      r.I.xx = RC(Irot.xx); r.I.xy = RC(Irot.xy); r.I.xz = RC(Irot.xz); r.I.yy = RC(Irot.yy); r.I.yz = RC(Irot.yz); r.I.zz = RC(Irot.zz);
       const RC cc = dot(c, c);
       r.I.xx += r.m * (cc - c.x * c.x); r.I.yy += r.m * (cc - c.y * c.y); r.I.zz += r.m * (cc - c.z * c.z);
       r.I.xy -= r.m * c.x * c.y; r.I.xz -= r.m * c.x * c.z; r.I.yz -= r.m * c.y * c.z;
