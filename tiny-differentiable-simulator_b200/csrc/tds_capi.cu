@@ -13,7 +13,11 @@
 #include "tds_b200_model.h"
 #include "tds_model.h"
 #include "tds_types.h"
+#include "tds_team.h"
 
+extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, const DevModel* M, const SimParams* P,
+                                const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
+                                char* gscratch, int use_smem, cudaStream_t stream);
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream);
@@ -117,7 +121,13 @@ struct tds_b200_sim {
   DevModel dm[3];         // one layout per precision mode
   bool smem_ok[3] = {false, false, false};
   bool smem_ok_w[3] = {false, false, false};
-  int kernel = 1;          // 1: world-frame kernel (tds_stepw.cu), 0: link-frame kernel (tds_step.cu)
+  int kernel = 2;          // 2: team kernel (tds_stept.cu), 1: one-lane world-frame kernel (tds_stepw.cu), 0: link-frame kernel
+  int kernel_req = 2;
+  bool team_ok = false;
+  bool smem_ok_t[3] = {false, false, false};
+  TeamModel tm[3];
+  std::vector<TeamLink> team_table;
+  TeamLink* team_dev = nullptr;
   int warps_per_block[3] = {1, 1, 1};
   DevVisuals vis;
   SimParams P;
@@ -166,6 +176,25 @@ static int ensure_scratch(tds_b200_sim* s, int prec) {
   return 0;
 }
 
+// (Re)build the team decomposition: depends on the model and on the action -> link map of the environment.
+static int rebuild_team(tds_b200_sim* s) {
+  s->team_ok = false;
+  TeamModel base;
+  int rc = tds_build_team(&s->dm[0], &s->E, &base, &s->team_table);
+  if (rc != 0) return 0;   // chains etc.: the one-lane kernel is used
+  const int sizes[3][3] = {{4, 8, 4}, {8, 8, 8}, {4, 4, 4}};
+  for (int p = 0; p < 3; ++p) {
+    s->tm[p] = base;
+    tds_build_team_layout(&s->tm[p], sizes[p][0], sizes[p][1], sizes[p][2]);
+    const size_t warp_bytes = ((size_t)s->tm[p].t_total * (32 / TDS_TEAM_T) + (size_t)s->tm[p].l_total * 32) * 4;
+    s->smem_ok_t[p] = warp_bytes <= (size_t)s->max_smem_optin;
+  }
+  if (!s->team_dev) CUDA_TRY(cudaMalloc((void**)&s->team_dev, sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK));
+  CUDA_TRY(cudaMemcpy(s->team_dev, s->team_table.data(), sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK, cudaMemcpyHostToDevice));
+  s->team_ok = true;
+  return 0;
+}
+
 extern "C" {
 
 tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int device) {
@@ -199,7 +228,8 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     // several warps per block only help when many blocks would otherwise be needed per SM
     s->warps_per_block[p] = 1;
   }
-  if (const char* kv = getenv("TDS_B200_KERNEL")) s->kernel = (strcmp(kv, "link") == 0) ? 0 : 1;
+  if (const char* kv = getenv("TDS_B200_KERNEL")) s->kernel_req = (strcmp(kv, "link") == 0) ? 0 : (strcmp(kv, "world") == 0 ? 1 : 2);
+  s->kernel = s->kernel_req;
   s->n_tau = base.n_qd - (base.floating ? 6 : 0);
   s->n_points = base.max_contacts;
   // visuals for the v1 output packing
@@ -227,7 +257,7 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
             alloc(&s->act, (base.n_qd > TDS_MAX_ACT ? base.n_qd : TDS_MAX_ACT)) && alloc(&s->qdd, base.n_qd > 0 ? base.n_qd : 1) &&
             alloc(&s->reward, 1) && alloc(&s->done, 1) && alloc(&s->cdist, s->n_points > 0 ? s->n_points : 1) &&
             alloc(&s->link_xf, (size_t)(base.n_links > 0 ? base.n_links : 1) * 12);
-  if (!ok || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (!ok || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || rebuild_team(s) != 0) {
     set_err("device allocation failed");
     tds_b200_destroy(s);
     return nullptr;
@@ -239,7 +269,7 @@ void tds_b200_destroy(tds_b200_sim* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->q); cudaFree(s->qd); cudaFree(s->act); cudaFree(s->qdd); cudaFree(s->reward); cudaFree(s->done);
-  cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk);
+  cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk); cudaFree(s->team_dev);
   if (s->stage_host) cudaFreeHost(s->stage_host);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -276,7 +306,7 @@ int tds_b200_set_env(tds_b200_sim* s, int n_act, const double* initial_poses, in
   E.auto_reset = s->E.auto_reset;
   memcpy(E.reset_q, s->E.reset_q, sizeof(E.reset_q));
   s->E = E;
-  return 0;
+  return rebuild_team(s);
 }
 
 int tds_b200_set_auto_reset(tds_b200_sim* s, int enable, const double* reset_q) {
@@ -315,9 +345,27 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.phase_clk = s->phase_clk;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
-  const int use_smem = (s->kernel ? s->smem_ok_w[p] : s->smem_ok[p]) ? 1 : 0;
+  const int kern = (s->kernel_req == 2 && !s->team_ok) ? 1 : s->kernel_req;
+  if (kern == 2) {
+    const int use_smem_t = s->smem_ok_t[p] ? 1 : 0;
+    if (!use_smem_t) {
+      const size_t warp_bytes = ((size_t)s->tm[p].t_total * (32 / TDS_TEAM_T) + (size_t)s->tm[p].l_total * 32) * 4;
+      const size_t need = warp_bytes * ((s->n + (32 / TDS_TEAM_T) - 1) / (32 / TDS_TEAM_T));
+      if (need > s->scratch_bytes) {
+        if (s->scratch) cudaFree(s->scratch);
+        s->scratch = nullptr; s->scratch_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&s->scratch, need));
+        s->scratch_bytes = need;
+      }
+    }
+    int rct = tds_launch_stept(&s->tm[p], s->team_dev, &s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem_t,
+                               (cudaStream_t)stream);
+    if (rct) set_err(std::string("team step launch: ") + cudaGetErrorString((cudaError_t)rct));
+    return rct;
+  }
+  const int use_smem = (kern ? s->smem_ok_w[p] : s->smem_ok[p]) ? 1 : 0;
   if (!use_smem) { int rc = ensure_scratch(s, p); if (rc) return rc; }
-  int rc = s->kernel ? tds_launch_stepw(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
+  int rc = kern ? tds_launch_stepw(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
                                         s->warps_per_block[p], (cudaStream_t)stream)
                      : tds_launch_step(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
                                        s->warps_per_block[p], (cudaStream_t)stream);
@@ -413,7 +461,7 @@ int tds_b200_env_step_device(tds_b200_sim* s, const float* actions, float* rewar
 // boundaries of the step kernel; out (host) receives [n_warps][16] stamps of the last step.
 int tds_b200_debug_phase_clocks(tds_b200_sim* s, int enable, long long* out_host, int cap_warps) {
   if (!s) return -1;
-  const int nw = s->ns / 32;
+  const int nw = s->ns / (32 / TDS_TEAM_T);   // team kernel: 8 environments per warp
   if (enable && !s->phase_clk) {
     CUDA_TRY(cudaMalloc((void**)&s->phase_clk, sizeof(long long) * 16 * nw));
     CUDA_TRY(cudaMemset(s->phase_clk, 0, sizeof(long long) * 16 * nw));
