@@ -73,6 +73,22 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
 #define TDST_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[(size_t)gwarp * 16 + (phase_id++)] = clock64(); } while (0)
   TDST_PHASE();
 
+  // warm L1 with the per-role link tables (read many times below through the non-coherent path) and issue the
+  // loads of this team's coordinates early; a lone warp otherwise pays one L2 round trip per first touch
+  {
+    const char* tbl = (const char*)tl;
+    const int lines = (TDS_TEAM_T * TDS_TEAM_MAXK * (int)sizeof(TeamLink) + 127) / 128;
+    for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(tbl + (size_t)l * 128));
+    const int nqp = M.n_q > M.n_qd ? M.n_q : M.n_qd;
+    for (int k = role; k < nqp; k += TT) {
+      if (k < M.n_q) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.q_in + (size_t)k * ns + e));
+      if (k < M.n_qd) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.qd_in + (size_t)k * ns + e));
+    }
+    if (io.tau_in) {
+      const int nt = use_pd ? E.n_act : (M.n_qd - (M.floating ? 6 : 0));
+      for (int k = role; k < nt; k += TT) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.tau_in + (size_t)k * ns + e));
+    }
+  }
   float* const tq = tp(TM.t_q, 0.f);
   float* const tqd = tp(TM.t_qd, 0.f);
   float* const ttau = tp(TM.t_tau, 0.f);
@@ -883,6 +899,8 @@ extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, con
     static size_t smem_set = 0;                                                                         \
     if (smem > 48 * 1024 && smem > smem_set) {                                                          \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      /* several one-warp CTAs must be co-resident per SM: ask for the largest shared-memory carveout */ \
+      if (err == cudaSuccess) err = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
       if (err == cudaSuccess) smem_set = smem;                                                          \
     }                                                                                                   \
     if (err == cudaSuccess) {                                                                           \
