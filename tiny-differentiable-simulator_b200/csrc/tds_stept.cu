@@ -41,12 +41,12 @@ template <typename T> TDS_D T team_sum(T v, unsigned mask) {
   return v;
 }
 
-template <typename RA, typename RC, typename RS>
-__global__ void __launch_bounds__(128, 1)
+template <typename RA, typename RC, typename RS, bool SMEM>
+__global__ void __launch_bounds__(32, 4)
 tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restrict__ tl,
                  const __grid_constant__ DevModel M, const __grid_constant__ SimParams P,
                  const __grid_constant__ EnvParams E, const StepIO io, const int mode, const int use_pd,
-                 char* __restrict__ gscratch, const int use_smem) {
+                 char* __restrict__ gscratch) {
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_blk = threadIdx.x >> 5;
@@ -58,9 +58,10 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
   const bool live = env < io.n;
   const int e = live ? env : io.n - 1;
   const size_t warp_bytes = ((size_t)TM.t_total * STM + (size_t)TM.l_total * SL) * 4;
-  char* const wb = use_smem ? smem_raw + warp_in_blk * warp_bytes : gscratch + (size_t)gwarp * warp_bytes;
-  char* const tb = wb;
-  char* const lb = wb + (size_t)TM.t_total * STM * 4;
+  // SMEM is a template parameter so that the compiler keeps the shared address space (LDS/STS, 32-bit addressing)
+  char* tb; char* lb;
+  if (SMEM) { tb = smem_raw + warp_in_blk * warp_bytes; lb = smem_raw + warp_in_blk * warp_bytes + (size_t)TM.t_total * STM * 4; }
+  else { tb = gscratch + (size_t)gwarp * warp_bytes; lb = tb + (size_t)TM.t_total * STM * 4; }
   auto tp = [&](int word, auto tag) { using T = decltype(tag); return (sizeof(T) == 4) ? ((T*)tb) + (size_t)word * STM + team : ((T*)tb) + (size_t)(word >> 1) * STM + team; };
   auto lp = [&](int word, auto tag) { using T = decltype(tag); return (sizeof(T) == 4) ? ((T*)lb) + (size_t)word * SL + lane : ((T*)lb) + (size_t)(word >> 1) * SL + lane; };
   const int ns = io.n_stride;
@@ -893,9 +894,9 @@ extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, con
   const size_t warp_bytes = ((size_t)TM->t_total * teams_per_warp + (size_t)TM->l_total * 32) * 4;
   const size_t smem = use_smem ? warp_bytes : 0;
   cudaError_t err = cudaSuccess;
-#define TDST_LAUNCH(RA, RC, RS)                                                                         \
+#define TDST_LAUNCH(RA, RC, RS, SM)                                                                       \
   do {                                                                                                  \
-    auto k = tds_stept_kernel<RA, RC, RS>;                                                              \
+    auto k = tds_stept_kernel<RA, RC, RS, SM>;                                                              \
     static size_t smem_set = 0;                                                                         \
     if (smem > 48 * 1024 && smem > smem_set) {                                                          \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
@@ -904,13 +905,13 @@ extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, con
       if (err == cudaSuccess) smem_set = smem;                                                          \
     }                                                                                                   \
     if (err == cudaSuccess) {                                                                           \
-      k<<<warps, 32, smem, stream>>>(*TM, tl_dev, *M, *P, *E, *io, mode, use_pd, gscratch, use_smem);   \
+      k<<<warps, 32, smem, stream>>>(*TM, tl_dev, *M, *P, *E, *io, mode, use_pd, gscratch);             \
       err = cudaGetLastError();                                                                         \
     }                                                                                                   \
   } while (0)
-  if (precision == 0) TDST_LAUNCH(float, double, float);
-  else if (precision == 1) TDST_LAUNCH(double, double, double);
-  else TDST_LAUNCH(float, float, float);
+  if (precision == 0) { if (use_smem) TDST_LAUNCH(float, double, float, true); else TDST_LAUNCH(float, double, float, false); }
+  else if (precision == 1) { if (use_smem) TDST_LAUNCH(double, double, double, true); else TDST_LAUNCH(double, double, double, false); }
+  else { if (use_smem) TDST_LAUNCH(float, float, float, true); else TDST_LAUNCH(float, float, float, false); }
 #undef TDST_LAUNCH
   return (int)err;
 }

@@ -317,7 +317,7 @@ static inline void tds_build_team_layout(TeamModel* TM, int size_ra, int size_rc
   w = even(w);
   TM->l_S = w; w += kown * 6 * rc;
   w = even(w);
-  TM->l_xw = w; w += (TM->n_xw_lane > 0 ? TM->n_xw_lane : 1) * 12 * rc;
+  TM->l_xw = w; w += TM->n_xw_lane * 12 * rc;
   w = even(w);
   TM->l_acc = w; w += (TM->n_acc > 0 ? TM->n_acc : 1) * TM->acc_words;
   w = even(w);
@@ -329,8 +329,7 @@ static inline void tds_build_team_layout(TeamModel* TM, int size_ra, int size_rc
   w = even(w);
   TM->l_w = w; w += no3 * rs + 2;
   w = even(w);
-  TM->l_P = w; w += (TM->nbt * (TM->nbt + 1) / 2) * 9 * rs;   // partial Schur complement G^T G
-  w = even(w);
+  TM->l_P = w;   // (partial Schur complement is reduced in registers)
   const int npt = TM->n_pts_max > 0 ? TM->n_pts_max : 1;
   TM->l_con = w; w += npt * 5 * rc;
   w = even(w);
