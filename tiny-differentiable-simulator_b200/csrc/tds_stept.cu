@@ -80,56 +80,38 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
     const char* tbl = (const char*)tl;
     const int lines = (TDS_TEAM_T * TDS_TEAM_MAXK * (int)sizeof(TeamLink) + 127) / 128;
     for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(tbl + (size_t)l * 128));
-    const int nqp = M.n_q > M.n_qd ? M.n_q : M.n_qd;
-    for (int k = role; k < nqp; k += TT) {
-      if (k < M.n_q) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.q_in + (size_t)k * ns + e));
-      if (k < M.n_qd) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.qd_in + (size_t)k * ns + e));
-    }
-    if (io.tau_in) {
-      const int nt = use_pd ? E.n_act : (M.n_qd - (M.floating ? 6 : 0));
-      for (int k = role; k < nt; k += TT) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.tau_in + (size_t)k * ns + e));
-    }
   }
   float* const tq = tp(TM.t_q, 0.f);
   float* const tqd = tp(TM.t_qd, 0.f);
   float* const ttau = tp(TM.t_tau, 0.f);
-  float* const lq = lp(TM.l_q, 0.f);
-  float* const lqd = lp(TM.l_qd, 0.f);
-  float* const ltau = lp(TM.l_tau, 0.f);
   // coordinate accessors of a local link: trunk links -> team region (global index), own links -> lane region
-  auto q_ref = [&](const int k, const int q_idx, const int ldof) -> float& { return k < n_trunk ? tq[q_idx * STM] : lq[(ldof - n_td) * SL]; };
-  auto qd_ref = [&](const int k, const int qd_idx, const int ldof) -> float& { return k < n_trunk ? tqd[qd_idx * STM] : lqd[(ldof - n_td) * SL]; };
-  auto tau_ref = [&](const int k, const int qd_idx, const int ldof) -> float& { return k < n_trunk ? ttau[qd_idx * STM] : ltau[(ldof - n_td) * SL]; };
+  // all coordinates of the environment live in the team region at their global index
+  auto q_ref = [&](const int, const int q_idx, const int) -> float& { return tq[q_idx * STM]; };
+  auto qd_ref = [&](const int, const int qd_idx, const int) -> float& { return tqd[qd_idx * STM]; };
+  auto tau_ref = [&](const int, const int qd_idx, const int) -> float& { return ttau[qd_idx * STM]; };
 
-  // ---- load state, PD torques (locomotion_contact_simulation.h:168-258) ---------------------------
+  // ---- load state (the four lanes of a team share the loads, all independent -> one memory round trip),
+  //      PD torques (locomotion_contact_simulation.h:168-258) ---------------------------------------------
   const int k_first = (role == 0) ? 0 : n_trunk;     // lane 0 also owns the trunk
-  if (role == 0 && M.floating) {
-    for (int k = 0; k < 7; ++k) tq[k * STM] = io.q_in[(size_t)k * ns + e];
-    for (int k = 0; k < 6; ++k) { tqd[k * STM] = io.qd_in[(size_t)k * ns + e]; ttau[k * STM] = 0.f; }
-  }
-  for (int k = k_first; k < n_loc; ++k) {
-    const TeamLink& L = mytl[k];
-    const int fl = __ldg(&L.flags);
-    if (fl & TDS_LF_FIXED) continue;
-    const int qi = __ldg(&L.q_idx), qdi = __ldg(&L.qd_idx), ld = __ldg(&L.ldof);
-    const float qa = io.q_in[(size_t)qi * ns + e];
-    const float qda = io.qd_in[(size_t)qdi * ns + e];
-    q_ref(k, qi, ld) = qa;
-    qd_ref(k, qdi, ld) = qda;
-    float tau = 0.f;
-    if (use_pd) {
-      const int a = __ldg(&L.act_idx);
-      if (a >= 0) {
-        float act = io.tau_in[(size_t)a * ns + e];
-        act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
-        const float q_des = E.initial_poses[a] + act;
-        float f = E.kp * (q_des - qa) + E.kd * (0.f - qda);
-        tau = fminf(fmaxf(f, -E.max_force), E.max_force);
-      }
-    } else if (io.tau_in) {
-      tau = io.tau_in[(size_t)(qdi - (M.floating ? 6 : 0)) * ns + e];
+#pragma unroll 4
+  for (int k = role; k < M.n_q; k += TT) tq[k * STM] = io.q_in[(size_t)k * ns + e];
+#pragma unroll 4
+  for (int k = role; k < M.n_qd; k += TT) { tqd[k * STM] = io.qd_in[(size_t)k * ns + e]; ttau[k * STM] = 0.f; }
+  __syncwarp();
+  if (use_pd) {
+#pragma unroll 4
+    for (int a = role; a < E.n_act; a += TT) {
+      const int li = E.act_link[a];
+      float act = io.tau_in[(size_t)a * ns + e];
+      act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
+      const float q_des = E.initial_poses[a] + act;
+      const float f = E.kp * (q_des - tq[M.q_idx[li] * STM]) + E.kd * (0.f - tqd[M.qd_idx[li] * STM]);
+      ttau[M.qd_idx[li] * STM] = fminf(fmaxf(f, -E.max_force), E.max_force);
     }
-    tau_ref(k, qdi, ld) = tau;
+  } else if (io.tau_in) {
+    const int off = M.floating ? 6 : 0;
+#pragma unroll 4
+    for (int k = off + role; k < M.n_qd; k += TT) ttau[k * STM] = io.tau_in[(size_t)(k - off) * ns + e];
   }
   for (int s = 0; s < TM.n_acc; ++s) {
     RA* pa = lp(TM.l_acc + s * TM.acc_words, RA(0));
@@ -688,7 +670,7 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
         dst[0] = RS(dot(nbv, col)); dst[SL] = RS(dot(f1, col)); dst[2 * SL] = RS(dot(f2, col));
         vel = vel + col * RC(qd_ref(j, __ldg(&mytl[j].qd_idx), lj));
       }
-      RS* const cs = lp(TM.l_conS, RS(0)) + lpt * 6 * SL;   // b[3], x[3]   (mb_constraint_solver.hpp:299-345)
+      RS* const cs = lp(TM.l_conS, RS(0)) + lpt * 12 * SL;   // b[3], x[3], y.y[3], 1/A_ii[3]   (mb_constraint_solver.hpp:299-345)
       cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
       cs[SL] = RS(dot(f1, vel));
       cs[2 * SL] = RS(dot(f2, vel));
@@ -712,10 +694,18 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
         for (int bk = 0; bk < bt; ++bk) gemm_nn_sub(a, ldb<RS>(Bt + btri(bt, bk) * STM, STM), ldb<RS>(Yt + bk * 9 * SL, SL));
         stb<RS>(Yt + bt * 9 * SL, SL, linv_mul(ldl6<RS>(dt_ + bt * 6 * STM, STM), a));
       }
+      // A_ii = y.y + cfm is constant during the sweep: keep y.y and 1 / A_ii per row
+      for (int blk = 0; blk < 3; ++blk) {
+        RS yy = RS(0);
+        for (int k = 0; k < 3 * nbo; ++k) { const RS y = Yo[(3 * k + blk) * SL]; yy += y * y; }
+        for (int k = 0; k < nt3; ++k) { const RS y = Yt[(3 * k + blk) * SL]; yy += y * y; }
+        cs[(6 + blk) * SL] = yy;
+        cs[(9 + blk) * SL] = RS(1) / (yy + RS(P.cfm));
+      }
     }
     TDST_PHASE();  // 6
     // projected Gauss-Seidel in the reference's row order (solve_pgs, mb_constraint_solver.hpp:101-142,417-436)
-    const RS cfm = RS(P.cfm), mu = RS(P.friction);
+    const RS mu = RS(P.friction);
     for (int it = 0; it < P.pgs_iterations; ++it) {
       for (int blk = 0; blk < 3; ++blk) {
         unsigned long long rem = team_active;
@@ -727,23 +717,19 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
           const RS* yt = nullptr;
           if (role == owner) {
             const int lpt = TM.cand_lpt[g];
-            RS* const cs = lp(TM.l_conS, RS(0)) + lpt * 6 * SL;
+            RS* const cs = lp(TM.l_conS, RS(0)) + lpt * 12 * SL;
             const RS* yo = lp(TM.l_Y, RS(0)) + (size_t)lpt * YW * SL + blk * SL;     // element k at yo[3k * SL]
             yt = yo + no3max * 3 * SL;
-            RS yy0 = RS(0), yy1 = RS(0), yy2 = RS(0), yw0 = RS(0), yw1 = RS(0), yw2 = RS(0);
+            RS yw0 = RS(0), yw1 = RS(0), yw2 = RS(0);
             for (int b = 0; b < nbo; ++b) {
-              const RS y0 = yo[(9 * b) * SL], y1 = yo[(9 * b + 3) * SL], y2 = yo[(9 * b + 6) * SL];
-              yy0 += y0 * y0; yy1 += y1 * y1; yy2 += y2 * y2;
-              yw0 += y0 * wk[(3 * b) * SL]; yw1 += y1 * wk[(3 * b + 1) * SL]; yw2 += y2 * wk[(3 * b + 2) * SL];
+              yw0 += yo[(9 * b) * SL] * wk[(3 * b) * SL]; yw1 += yo[(9 * b + 3) * SL] * wk[(3 * b + 1) * SL]; yw2 += yo[(9 * b + 6) * SL] * wk[(3 * b + 2) * SL];
             }
             for (int b = 0; b < nbt; ++b) {
-              const RS y0 = yt[(9 * b) * SL], y1 = yt[(9 * b + 3) * SL], y2 = yt[(9 * b + 6) * SL];
-              yy0 += y0 * y0; yy1 += y1 * y1; yy2 += y2 * y2;
-              yw0 += y0 * wt[(3 * b) * STM]; yw1 += y1 * wt[(3 * b + 1) * STM]; yw2 += y2 * wt[(3 * b + 2) * STM];
+              yw0 += yt[(9 * b) * SL] * wt[(3 * b) * STM]; yw1 += yt[(9 * b + 3) * SL] * wt[(3 * b + 1) * STM]; yw2 += yt[(9 * b + 6) * SL] * wt[(3 * b + 2) * STM];
             }
-            const RS yy = (yy0 + yy1) + yy2, yw = (yw0 + yw1) + yw2;
+            const RS yw = (yw0 + yw1) + yw2;
             const RS x_old = cs[(3 + blk) * SL];
-            RS x = (cs[blk * SL] - yw + yy * x_old) / (yy + cfm);
+            RS x = (cs[blk * SL] - yw + cs[(6 + blk) * SL] * x_old) * cs[(9 + blk) * SL];
             if (blk == 0) {
               x = x < RS(0) ? RS(0) : x;
               x = x > RS(100000) ? RS(100000) : x;
@@ -813,7 +799,10 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
       wk[(3 * bi + 2) * SL] = li.i22 * a2;
     }
     // qd -= z : own dofs by their lane, trunk dofs by lane 0
-    for (int k = 0; k < n_od; ++k) lqd[k * SL] = (float)(RS(lqd[k * SL]) - wk[k * SL]);
+    for (int k = n_trunk; k < n_loc; ++k) {
+      const int lj = __ldg(&mytl[k].ldof);
+      if (lj >= 0) { float& r = tqd[__ldg(&mytl[k].qd_idx) * STM]; r = (float)(RS(r) - wk[(lj - n_td) * SL]); }
+    }
     if (role == 0) {
       if (M.floating) for (int k = 0; k < 6; ++k) tqd[k * STM] = (float)(RS(tqd[k * STM]) - wt[k * STM]);
       for (int k = 0; k < n_trunk; ++k) {
@@ -867,18 +856,12 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
   }
   done_i = __shfl_sync(tmask, done_i, team * TT);
   const bool reset = done_i && E.auto_reset;
+  __syncwarp();
   if (live) {
-    if (role == 0 && M.floating) {
-      for (int k = 0; k < 7; ++k) io.q_out[(size_t)k * ns + e] = reset ? E.reset_q[k] : tq[k * STM];
-      for (int k = 0; k < 6; ++k) io.qd_out[(size_t)k * ns + e] = reset ? 0.f : tqd[k * STM];
-    }
-    for (int k = k_first; k < n_loc; ++k) {
-      const TeamLink& L = mytl[k];
-      if (__ldg(&L.flags) & TDS_LF_FIXED) continue;
-      const int qi = __ldg(&L.q_idx), qdi = __ldg(&L.qd_idx), ld = __ldg(&L.ldof);
-      io.q_out[(size_t)qi * ns + e] = reset ? E.reset_q[qi] : q_ref(k, qi, ld);
-      io.qd_out[(size_t)qdi * ns + e] = reset ? 0.f : qd_ref(k, qdi, ld);
-    }
+#pragma unroll 4
+    for (int k = role; k < M.n_q; k += TT) io.q_out[(size_t)k * ns + e] = reset ? E.reset_q[k] : tq[k * STM];
+#pragma unroll 4
+    for (int k = role; k < M.n_qd; k += TT) io.qd_out[(size_t)k * ns + e] = reset ? 0.f : tqd[k * STM];
   }
   TDST_PHASE();  // 9
 }

@@ -311,10 +311,7 @@ static inline void tds_build_team_layout(TeamModel* TM, int size_ra, int size_rc
   // ---- lane region ----
   w = 0;
   const int kown = TM->kmax - TM->n_trunk;
-  TM->l_q = w; w += TM->n_od_max + 1;        // own coordinates (local order)
-  TM->l_qd = w; w += TM->n_od_max + 1;
-  TM->l_tau = w; w += TM->n_od_max + 1;
-  w = even(w);
+  TM->l_q = TM->l_qd = TM->l_tau = 0;        // (coordinates live in the team region)
   TM->l_S = w; w += kown * 6 * rc;
   w = even(w);
   TM->l_xw = w; w += TM->n_xw_lane * 12 * rc;
@@ -333,7 +330,7 @@ static inline void tds_build_team_layout(TeamModel* TM, int size_ra, int size_rc
   const int npt = TM->n_pts_max > 0 ? TM->n_pts_max : 1;
   TM->l_con = w; w += npt * 5 * rc;
   w = even(w);
-  TM->l_conS = w; w += npt * 6 * rs;
+  TM->l_conS = w; w += npt * 12 * rs;
   w = even(w);
   TM->y_words = (no3 + nt3) * 3 * rs;
   const int link_region = kown * TM->link_words;
