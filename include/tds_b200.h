@@ -24,7 +24,8 @@ typedef struct tds_b200_sim tds_b200_sim;
                                      examples/environments/locomotion_contact_simulation.h:261-269 */
 
 /* arithmetic selector */
-#define TDS_B200_PREC_MIXED 0 /* ABA fp32, kinematics + contact solve fp64 (default) */
+#define TDS_B200_PREC_MIXED 0 /* default: fp32 ABA / factorisation / PGS; fp64 kinematics, contact geometry,
+                                 composite inertias, CRBA products, Jacobians and LCP right-hand side */
 #define TDS_B200_PREC_F64 1
 #define TDS_B200_PREC_F32 2
 
