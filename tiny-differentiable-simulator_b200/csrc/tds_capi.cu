@@ -18,6 +18,10 @@
 extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, const DevModel* M, const SimParams* P,
                                 const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
                                 char* gscratch, int use_smem, cudaStream_t stream);
+extern "C" int tds_launch_stepr(const TeamModel* TM, const TeamLink* tl_host, unsigned long long token, const DevModel* M,
+                                const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
+                                int precision, char* gscratch, int use_smem, cudaStream_t stream);
+extern "C" size_t tds_stepr_tile_bytes(const TeamModel* TM);
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream);
@@ -121,8 +125,13 @@ struct tds_b200_sim {
   DevModel dm[3];         // one layout per precision mode
   bool smem_ok[3] = {false, false, false};
   bool smem_ok_w[3] = {false, false, false};
-  int kernel = 2;          // 2: team kernel (tds_stept.cu), 1: one-lane world-frame kernel (tds_stepw.cu), 0: link-frame kernel
-  int kernel_req = 2;
+  // 3: role-warp kernel (tds_stepr.cu), 2: lane-team kernel (tds_stept.cu), 1: one-lane world-frame kernel
+  // (tds_stepw.cu), 0: link-frame kernel (tds_step.cu).  Requests fall back 3 -> 2 -> 1 when the model has no
+  // tree decomposition (chains) or a tile does not fit in shared memory.
+  int kernel = 3;
+  int kernel_req = 3;
+  bool smem_ok_r[3] = {false, false, false};
+  unsigned long long table_token = 0;
   bool team_ok = false;
   bool smem_ok_t[3] = {false, false, false};
   TeamModel tm[3];
@@ -188,7 +197,10 @@ static int rebuild_team(tds_b200_sim* s) {
     tds_build_team_layout(&s->tm[p], sizes[p][0], sizes[p][1], sizes[p][2]);
     const size_t warp_bytes = ((size_t)s->tm[p].t_total * (32 / TDS_TEAM_T) + (size_t)s->tm[p].l_total * 32) * 4;
     s->smem_ok_t[p] = warp_bytes <= (size_t)s->max_smem_optin;
+    s->smem_ok_r[p] = tds_stepr_tile_bytes(&s->tm[p]) <= (size_t)s->max_smem_optin;
   }
+  static unsigned long long next_token = 1;
+  s->table_token = next_token++;
   if (!s->team_dev) CUDA_TRY(cudaMalloc((void**)&s->team_dev, sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK));
   CUDA_TRY(cudaMemcpy(s->team_dev, s->team_table.data(), sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK, cudaMemcpyHostToDevice));
   s->team_ok = true;
@@ -228,7 +240,8 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     // several warps per block only help when many blocks would otherwise be needed per SM
     s->warps_per_block[p] = 1;
   }
-  if (const char* kv = getenv("TDS_B200_KERNEL")) s->kernel_req = (strcmp(kv, "link") == 0) ? 0 : (strcmp(kv, "world") == 0 ? 1 : 2);
+  if (const char* kv = getenv("TDS_B200_KERNEL"))
+    s->kernel_req = (strcmp(kv, "link") == 0) ? 0 : (strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : 3));
   s->kernel = s->kernel_req;
   s->n_tau = base.n_qd - (base.floating ? 6 : 0);
   s->n_points = base.max_contacts;
@@ -345,7 +358,16 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.phase_clk = s->phase_clk;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
-  const int kern = (s->kernel_req == 2 && !s->team_ok) ? 1 : s->kernel_req;
+  int kern = s->kernel_req;
+  if (kern == 3 && !(s->team_ok && s->smem_ok_r[p])) kern = 2;
+  if (kern == 2 && !s->team_ok) kern = 1;
+  s->kernel = kern;
+  if (kern == 3) {
+    int rcr = tds_launch_stepr(&s->tm[p], s->team_table.data(), s->table_token, &s->dm[p], &s->P, &s->E, &io, mode, use_pd, p,
+                               nullptr, 1, (cudaStream_t)stream);
+    if (rcr) set_err(std::string("role-warp step launch: ") + cudaGetErrorString((cudaError_t)rcr));
+    return rcr;
+  }
   if (kern == 2) {
     const int use_smem_t = s->smem_ok_t[p] ? 1 : 0;
     if (!use_smem_t) {

@@ -316,7 +316,11 @@ static inline void tds_build_team_layout(TeamModel* TM, int size_ra, int size_rc
   w = even(w);
   TM->l_xw = w; w += TM->n_xw_lane * 12 * rc;
   w = even(w);
-  TM->l_acc = w; w += (TM->n_acc > 0 ? TM->n_acc : 1) * TM->acc_words;
+  {   // accumulators; the role-warp kernel reuses the region for its partial Schur complement (l_P)
+    const int acc_region = (TM->n_acc > 0 ? TM->n_acc : 1) * TM->acc_words;
+    const int p_region = (TM->nbt * (TM->nbt + 1) / 2) * 9 * rs;
+    TM->l_acc = w; TM->l_P = w; w += acc_region > p_region ? acc_region : p_region;
+  }
   w = even(w);
   TM->l_M = w; w += (TM->nbo_max * (TM->nbo_max + 1) / 2) * 9 * rs;
   w = even(w);
@@ -326,7 +330,6 @@ static inline void tds_build_team_layout(TeamModel* TM, int size_ra, int size_rc
   w = even(w);
   TM->l_w = w; w += no3 * rs + 2;
   w = even(w);
-  TM->l_P = w;   // (partial Schur complement is reduced in registers)
   const int npt = TM->n_pts_max > 0 ? TM->n_pts_max : 1;
   TM->l_con = w; w += npt * 5 * rc;
   w = even(w);
