@@ -66,6 +66,8 @@ int tds_b200_set_env(tds_b200_sim* sim, int n_act, const double* initial_poses, 
 int tds_b200_set_auto_reset(tds_b200_sim* sim, int enable, const double* reset_q);
 
 int tds_b200_set_precision(tds_b200_sim* sim, int precision);
+/* Name of the step kernel the last tds_b200_step_* call launched (selection: DESIGN.md "Kernel selection"). */
+const char* tds_b200_kernel_name(const tds_b200_sim* sim);
 
 /* dims[0..7] = n_envs, n_stride, n_q (MultiBody::dof), n_qd (dof_qd), n_tau (dof_actuated), n_links,
  *              n_contact_points, n_act */

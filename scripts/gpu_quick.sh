@@ -23,3 +23,8 @@ if [ -n "$RACECHECK" ]; then
   timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python scripts/race_small.py > gpurun_out/${TAG}_racecheck.log 2>&1
   tail -15 gpurun_out/${TAG}_racecheck.log
 fi
+if [ -n "$NCU" ]; then
+  ncu --set full --clock-control none --import-source on -k regex:tds_step -s 262 -c 1 -f -o gpurun_out/${TAG}_step_full \
+      python scripts/profile_step.py > gpurun_out/${TAG}_ncu_full.log 2>&1
+  ls -la gpurun_out/${TAG}_step_full.ncu-rep
+fi

@@ -17,10 +17,26 @@ for _ in range(3):
     sim.env_step_device(act)
 buf = np.zeros((nw, 16), dtype=np.int64)
 L.tds_b200_debug_phase_clocks(sim._h, 1, buf.ctypes.data, nw)
+print("kernel:", sim.kernel_name())
 names = ["load+PD", "pass1 FK+contacts", "pass2 ABA+CRBA", "base+pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate+write"]
 if os.environ.get("TDS_B200_KERNEL") == "link":
     names = ["load+PD", "pass1 FK", "contacts", "pass2 ABA+CRBA", "base", "pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate", "writeback"]
 K = len(names)
+kern = os.environ.get("TDS_B200_KERNEL", "spec")
+if kern in ("role", "spec"):   # one record per (tile, role): show every role, phases are separated by CTA barriers
+    tiles = (n + 31) // 32
+    b = buf[:tiles * 4].reshape(tiles, 4, 16)
+    t0 = b[:, :, 0].min(axis=1, keepdims=True)
+    tot = (b[:, :, K].max(axis=1) - t0[:, 0]).astype(np.float64)
+    print("cycles per tile: total median %.0f (min %.0f max %.0f)" % (np.median(tot), tot.min(), tot.max()))
+    print("  phase end (cycles since tile start), median over tiles:  role0 role1 role2 role3 | role-0 duration")
+    prev = np.zeros(4)
+    for k, nm in enumerate(names):
+        end = np.median((b[:, :, k + 1] - t0).astype(np.float64), axis=0)
+        print(f"  {nm:18s} " + " ".join(f"{x:8.0f}" for x in end) + f" | {end[0] - prev[0]:8.0f}")
+        prev = end
+    sys.exit(0)
+
 d = np.diff(buf[:, :K + 1], axis=1).astype(np.float64)
 tot = (buf[:, K] - buf[:, 0]).astype(np.float64)
 print("cycles per warp: total median %.0f (min %.0f max %.0f)" % (np.median(tot), tot.min(), tot.max()))

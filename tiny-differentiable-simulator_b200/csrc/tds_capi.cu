@@ -22,6 +22,10 @@ extern "C" int tds_launch_stepr(const TeamModel* TM, const TeamLink* tl_host, un
                                 const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
                                 int precision, char* gscratch, int use_smem, cudaStream_t stream);
 extern "C" size_t tds_stepr_tile_bytes(const TeamModel* TM);
+extern "C" int tds_spec_match(const double* model, int n_model, const DevModel* D, const EnvParams* E);
+extern "C" size_t tds_spec_smem_bytes(int precision);
+extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
+                                    cudaStream_t stream);
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream);
@@ -128,8 +132,11 @@ struct tds_b200_sim {
   // 3: role-warp kernel (tds_stepr.cu), 2: lane-team kernel (tds_stept.cu), 1: one-lane world-frame kernel
   // (tds_stepw.cu), 0: link-frame kernel (tds_step.cu).  Requests fall back 3 -> 2 -> 1 when the model has no
   // tree decomposition (chains) or a tile does not fit in shared memory.
-  int kernel = 3;
-  int kernel_req = 3;
+  // 4: ahead-of-time specialised kernel (tds_steps.cu) when the model is one it was generated for, else 3.
+  int kernel = 4;
+  int kernel_req = 4;
+  bool spec_ok = false;
+  std::vector<double> model;   // flat model (identity check of the specialised kernel)
   bool smem_ok_r[3] = {false, false, false};
   unsigned long long table_token = 0;
   bool team_ok = false;
@@ -188,6 +195,7 @@ static int ensure_scratch(tds_b200_sim* s, int prec) {
 // (Re)build the team decomposition: depends on the model and on the action -> link map of the environment.
 static int rebuild_team(tds_b200_sim* s) {
   s->team_ok = false;
+  s->spec_ok = false;
   TeamModel base;
   int rc = tds_build_team(&s->dm[0], &s->E, &base, &s->team_table);
   if (rc != 0) return 0;   // chains etc.: the one-lane kernel is used
@@ -201,6 +209,7 @@ static int rebuild_team(tds_b200_sim* s) {
   }
   static unsigned long long next_token = 1;
   s->table_token = next_token++;
+  s->spec_ok = tds_spec_match(s->model.data(), (int)s->model.size(), &s->dm[0], &s->E) != 0;
   if (!s->team_dev) CUDA_TRY(cudaMalloc((void**)&s->team_dev, sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK));
   CUDA_TRY(cudaMemcpy(s->team_dev, s->team_table.data(), sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK, cudaMemcpyHostToDevice));
   s->team_ok = true;
@@ -240,8 +249,9 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     // several warps per block only help when many blocks would otherwise be needed per SM
     s->warps_per_block[p] = 1;
   }
+  s->model.assign(model, model + n_model);
   if (const char* kv = getenv("TDS_B200_KERNEL"))
-    s->kernel_req = (strcmp(kv, "link") == 0) ? 0 : (strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : 3));
+    s->kernel_req = (strcmp(kv, "link") == 0) ? 0 : (strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : (strcmp(kv, "role") == 0 ? 3 : 4)));
   s->kernel = s->kernel_req;
   s->n_tau = base.n_qd - (base.floating ? 6 : 0);
   s->n_points = base.max_contacts;
@@ -359,6 +369,13 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
+  if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(p) <= (size_t)s->max_smem_optin)) kern = 3;
+  if (kern == 4) {
+    s->kernel = kern;
+    int rcs = tds_launch_step_spec(&s->P, &s->E, &io, mode, use_pd, p, (cudaStream_t)stream);
+    if (rcs) set_err(std::string("specialised step launch: ") + cudaGetErrorString((cudaError_t)rcs));
+    return rcs;
+  }
   if (kern == 3 && !(s->team_ok && s->smem_ok_r[p])) kern = 2;
   if (kern == 2 && !s->team_ok) kern = 1;
   s->kernel = kern;
@@ -481,6 +498,13 @@ int tds_b200_env_step_device(tds_b200_sim* s, const float* actions, float* rewar
 
 // Profiling aid (not part of the drop-in surface): enable per-warp clock64() stamps at the phase
 // boundaries of the step kernel; out (host) receives [n_warps][16] stamps of the last step.
+const char* tds_b200_kernel_name(const tds_b200_sim* s) {
+  static const char* names[5] = {"tds_step_kernel (link frame, lane per environment)", "tds_stepw_kernel (common frame, lane per environment)",
+                                 "tds_stept_kernel (lane team per environment)", "tds_stepr_kernel (warp per tree role)",
+                                 "tds_step_spec_kernel (warp per tree role, model-specialised)"};
+  return (s && s->kernel >= 0 && s->kernel <= 4) ? names[s->kernel] : "";
+}
+
 int tds_b200_debug_phase_clocks(tds_b200_sim* s, int enable, long long* out_host, int cap_warps) {
   if (!s) return -1;
   const int nw = s->ns / (32 / TDS_TEAM_T);   // team kernel: 8 environments per warp

@@ -61,7 +61,7 @@ tds_stepr_kernel(const __grid_constant__ TeamModel TM,
   constexpr int RAW = (int)(sizeof(RA) / 4), RCW = (int)(sizeof(RC) / 4);
   const int LWD = TM.link_words, UOFF = 10 * RCW, VOFF = 10 * RCW + 8 * RAW;
   int phase_id = 0;
-#define TDST_PHASE() do { if (io.phase_clk && threadIdx.x == 0) io.phase_clk[(size_t)gwarp * 16 + phase_id] = clock64(); ++phase_id; } while (0)
+#define TDST_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)gwarp * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
   TDST_PHASE();
 
   float* const tq = tp(TM.t_q, 0.f);

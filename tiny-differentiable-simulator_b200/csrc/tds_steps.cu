@@ -1,0 +1,1018 @@
+// Model-specialised step kernel: the role-warp kernel of tds_stepr.cu (CTA = a tile of 32 environments x 4 warps,
+// warp r = role r of the tree decomposition, lane = environment) instantiated on a COMPILE-TIME model
+// (generated/spec_*.h, written by gen_spec.cpp from the flat model).  Joint types, transforms, inertias, collision
+// shapes, the decomposition and every index are constant expressions; all loops over links, dofs and contacts are
+// unrolled.  What that buys over the table-driven kernel:
+//   * straight-line code per role (sequential instruction fetch, no dead branches for absent joint / shape types);
+//   * per-link state of the subtrees (S, v, c, U, 1/D, u), the mass-matrix blocks M_kk, C -> G and their factors
+//     live in registers; shared memory only carries what crosses roles (attachment transforms / accelerations,
+//     trunk records, attachment accumulators, partial Schur complements, the trunk factor, contact rows);
+//   * massless links, identity transforms and unit axes are folded away;
+//   * projected Gauss-Seidel is one warp's work without barriers: role 0 relaxes all rows, in the reference's
+//     order, from the contact rows the owners left in shared memory.
+// This is the counterpart of the reference's generated cuda_model_<env> (src/utils/cuda_codegen.hpp:156-266),
+// with the compiler's constant folding in place of a CppAD operation tape.  Numerics (scalar types RA / RC / RS,
+// reference quirks, row order) are those of tds_stept.cu / tds_stepr.cu; citations at each stage.
+#include <cuda_runtime.h>
+
+#include "tds_wcommon.cuh"
+#include "tds_team.h"
+#include "generated/spec_laikago.h"
+
+namespace tdss {
+using namespace tds;
+using namespace tdsw;
+
+constexpr int TT = TDS_TEAM_T;
+constexpr int ST = 32;   // element stride of every shared-memory array: [word][environment]
+
+template <int V> struct IC { static constexpr int value = V; };
+// model tables may only be read in constant expressions from device code: force the evaluation
+#define CI(...) (IC<(__VA_ARGS__)>::value)
+#define CD(...) ([]() { constexpr double cd_v_ = (__VA_ARGS__); return cd_v_; }())
+template <int B, int E, class F> TDS_D void sfor(F&& f) {
+  if constexpr (B < E) { f(IC<B>{}); sfor<B + 1, E>(f); }
+}
+template <int B, int E, class F> TDS_D void sfor_rev(F&& f) {   // E-1 down to B
+  if constexpr (B < E) { f(IC<E - 1>{}); sfor_rev<B, E - 1>(f); }
+}
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int ev(int x) { return (x + 1) & ~1; }
+__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+
+// is local link j an ancestor of local link k (same role list)?
+template <class SP, int R> __host__ __device__ constexpr bool is_anc(int j, int k) {
+  for (int a = SP::L_LPAR[R][k]; a >= 0; a = SP::L_LPAR[R][a]) if (a == j) return true;
+  return false;
+}
+template <class SP> __host__ __device__ constexpr int geom_pts(int g) { return SP::G_TYPE[g] == TDSG_SPHERE ? 1 : (SP::G_TYPE[g] == TDSG_CAPSULE ? 2 : 0); }
+template <class SP> __host__ __device__ constexpr int pts_before(int g_begin, int g) { int c = 0; for (int i = g_begin; i < g; ++i) c += geom_pts<SP>(i); return c; }
+template <class SP, int R> __host__ __device__ constexpr int k_of_q(int q_idx) {   // local link of role R holding coordinate q_idx (-1: none)
+  for (int k = 0; k < SP::N_LOC[R]; ++k) if (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED) && SP::L_QIDX[R][k] == q_idx) return k;
+  return -1;
+}
+
+// shared-memory layout of one tile, 4-byte words per environment
+template <class SP, typename RA, typename RC, typename RS> struct Lay {
+  static constexpr int RAW = sizeof(RA) / 4, RCW = sizeof(RC) / 4, RSW = sizeof(RS) / 4;
+  static constexpr int NTD = SP::N_TD, NTRI = NTD * (NTD + 1) / 2, NOD = SP::N_OD_MAX;
+  static constexpr int O = 0;                                        // O[3], plane_off (RC)
+  static constexpr int RB = O + 4 * RCW;                             // Rb[9] (RC), floating base
+  static constexpr int XWW = ev(12 * RCW + 12 * RAW);                // slot: R[9] p[3] (RC) | v[6] a[6] (RA)
+  static constexpr int XW = RB + 10 * RCW;                           // slot 0 = base, then the published trunk links
+  static constexpr int TS = XW + (SP::N_XW_TEAM + 1) * XWW;          // trunk S [N_TRUNK][6] (RC)
+  static constexpr int TLW = ev(10 * RCW + 14 * RAW);                // trunk record: rbi (10 RC) | U[6] 1/D u (8 RA) | v/c/a (6 RA)
+  static constexpr int TL = TS + SP::N_TRUNK * 6 * RCW;
+  static constexpr int TQD = ev(TL + SP::N_TRUNK * TLW);             // trunk qd after the FD update (NTD floats)
+  static constexpr int ACC_IC = ev(27 * RAW);
+  static constexpr int ACCW = ev(ACC_IC + 10 * RCW);                 // attachment accumulator: Ia 21 + pa 6 (RA) | Ic 10 (RC)
+  static constexpr int ACC = ev(TQD + NTD);                          // [T][N_ATT]; later the partial Schur complements [T][NTRI] (RS)
+  static constexpr int PW = ev(NTRI * RSW);
+  static constexpr int ACC_SZ = cmax(TT * cmax(SP::N_ATT, 1) * ACCW, TT * PW);
+  static constexpr int LT = ACC + ACC_SZ;                            // trunk factor, lower triangle with inverted diagonal (RS)
+  static constexpr int CON = ev(LT + NTRI * RSW);                    // contact rows per candidate
+  static constexpr int CONW = ev((3 * (NOD + NTD) + 9) * RSW);       // y_own[3][NOD] y_t[3][NTD] b[3] yy[3] 1/A[3]
+  static constexpr int ZT = CON + cmax(SP::N_CAND, 1) * CONW;        // z_t[NTD] (RS)
+  static constexpr int WO = ev(ZT + NTD * RSW);                      // w_own[T][NOD] (RS)
+  static constexpr int FLG = ev(WO + TT * NOD * RSW);                // active masks (2 words per role), done flag
+  static constexpr int SHARED = ev(FLG + 2 * TT + 2);
+  static constexpr int PRIV = ev(cmax(SP::KMAX - SP::N_TRUNK, 1) * 10 * RCW);   // rigid inertias of the own links (RC)
+  static constexpr int TOTAL = SHARED + TT * PRIV;
+};
+
+template <typename T> TDS_D T* sp(char* base, int lane, int word) {
+  return (sizeof(T) == 4) ? ((T*)base) + (size_t)word * ST + lane : ((T*)base) + (size_t)(word >> 1) * ST + lane;
+}
+template <typename T> TDS_D T negz() { return T(-0.0); }   // additive identity the optimiser folds exactly
+template <typename T> TDS_D Abi<T> abi_nz() {
+  Abi<T> a; const T z = negz<T>();
+  a.I = {z, z, z, z, z, z}; a.M = a.I;
+  a.H.xx = a.H.xy = a.H.xz = a.H.yx = a.H.yy = a.H.yz = a.H.zx = a.H.zy = a.H.zz = z;
+  return a;
+}
+template <typename T> TDS_D Sv<T> sv_nz() { Sv<T> s; const T z = negz<T>(); s.top = v3<T>(z, z, z); s.bot = s.top; return s; }
+template <typename T> TDS_D Rbi<T> rbi_nz() { Rbi<T> r; const T z = negz<T>(); r.m = z; r.h = v3<T>(z, z, z); r.I = {z, z, z, z, z, z}; return r; }
+
+template <class SP, int R, typename RA, typename RC, typename RS>
+TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, const StepIO& io, const int mode, const int use_pd) {
+  using L = Lay<SP, RA, RC, RS>;
+  constexpr int RAW = L::RAW, RCW = L::RCW;
+  constexpr int NT = SP::N_TRUNK, NTD = SP::N_TD, NLOC = SP::N_LOC[R], K0 = (R == 0) ? 0 : NT;
+  constexpr int NOD = SP::N_OD[R], NODA = cmax(NOD, 1), NTDA = cmax(NTD, 1), NTRI = L::NTRI, NTRIA = cmax(NTRI, 1);
+  constexpr int NPT = SP::N_PTS[R], NPTA = cmax(NPT, 1), NACCA = cmax(SP::N_ACC, 1), NXLA = cmax(SP::N_XW_LANE, 1);
+  constexpr bool FLOAT = SP::FLOATING != 0;
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * 32 + lane;
+  const bool live = env < io.n;
+  const int e = live ? env : io.n - 1;
+  const int ns = io.n_stride;
+  char* const priv = smem + (size_t)(L::SHARED + R * L::PRIV) * ST * 4;
+  int phase_id = 0;
+#define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + R) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
+  TDSS_PHASE();
+  auto xw_rc = [&](int slot) { return sp<RC>(smem, lane, L::XW + slot * L::XWW); };                  // R[9], p[3]
+  auto xw_ra = [&](int slot) { return sp<RA>(smem, lane, L::XW + slot * L::XWW + 12 * RCW); };       // v[6], a[6]
+  auto tl_rbi = [&](int k) { return sp<RC>(smem, lane, L::TL + k * L::TLW); };
+  auto tl_u = [&](int k) { return sp<RA>(smem, lane, L::TL + k * L::TLW + 10 * RCW); };
+  auto tl_v = [&](int k) { return sp<RA>(smem, lane, L::TL + k * L::TLW + 10 * RCW + 8 * RAW); };
+  auto ts_S = [&](int k) { return sp<RC>(smem, lane, L::TS + k * 6 * RCW); };
+  float* const tqd = sp<float>(smem, lane, L::TQD);
+  unsigned* const flg = sp<unsigned>(smem, lane, L::FLG);
+
+  // ---- load the coordinates of this role's joints; PD torques (locomotion_contact_simulation.h:168-258) -------------------
+  float qv[SP::KMAX], qdv[SP::KMAX], tauv[SP::KMAX];   // joint coordinate / velocity / torque of local link k
+  float bq[7], bqd[6];                                 // floating base (role 0)
+  sfor<K0, NLOC>([&](auto Kc) {
+    constexpr int k = decltype(Kc)::value;
+    if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED)) {
+      qv[k] = io.q_in[(size_t)CI(SP::L_QIDX[R][k]) * ns + e];
+      qdv[k] = io.qd_in[(size_t)CI(SP::L_QDIDX[R][k]) * ns + e];
+      tauv[k] = 0.f;
+    }
+  });
+  if constexpr (FLOAT && R == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) bq[k] = io.q_in[(size_t)k * ns + e];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bqd[k] = io.qd_in[(size_t)k * ns + e];
+  }
+  if (use_pd) {
+    sfor<K0, NLOC>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      constexpr int a = SP::L_ACT[R][k];
+      if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED) && a >= 0) {
+        float act = io.tau_in[(size_t)a * ns + e];
+        act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
+        const float q_des = E.initial_poses[a] + act;
+        const float f = E.kp * (q_des - qv[k]) + E.kd * (0.f - qdv[k]);
+        tauv[k] = fminf(fmaxf(f, -E.max_force), E.max_force);
+      }
+    });
+  } else if (io.tau_in) {
+    sfor<K0, NLOC>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      constexpr int off = FLOAT ? 6 : 0;
+      if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED) && SP::L_QDIDX[R][k] >= off)
+        tauv[k] = io.tau_in[(size_t)CI(SP::L_QDIDX[R][k] - off) * ns + e];
+    });
+  }
+  const bool want_contacts = (mode == MODE_FULL) && SP::HAS_PLANE;
+  const V3<RC> pn = v3<RC>(RC(CD(SP::PLANE_N[0])), RC(CD(SP::PLANE_N[1])), RC(CD(SP::PLANE_N[2])));
+  TDSS_PHASE();  // 1
+
+  // ---- contact candidates of this role (contact_point.hpp:112-116) -----------------------------------------------------------
+  unsigned long long my_active = 0ull;   // bit = global candidate index
+  V3<RC> cpos[NPTA]; RC cdist[NPTA];
+  auto emit_geoms = [&](auto Gb, auto Ge, auto Cand0, auto Lpt0, const M3<RC>& Rw, const V3<RC>& pw, const RC plane_off) {
+    constexpr int gb = decltype(Gb)::value, ge = decltype(Ge)::value;
+    sfor<gb, ge>([&](auto Gc) {
+      constexpr int g = decltype(Gc)::value;
+      constexpr int ty = SP::G_TYPE[g];
+      if constexpr (ty == TDSG_SPHERE || ty == TDSG_CAPSULE) {
+        constexpr int cand0 = decltype(Cand0)::value + pts_before<SP>(gb, g), lpt0 = decltype(Lpt0)::value + pts_before<SP>(gb, g);
+        const V3<RC> c = pw + mul(Rw, v3<RC>(RC(CD(SP::G_T[3 * g])), RC(CD(SP::G_T[3 * g + 1])), RC(CD(SP::G_T[3 * g + 2]))));
+        const RC rad = RC(CD(SP::G_RADIUS[g]));
+        V3<RC> half = v3<RC>(RC(0), RC(0), RC(0));
+        if constexpr (ty == TDSG_CAPSULE) half = mul(Rw, v3<RC>(RC(CD(SP::G_HALF[3 * g])), RC(CD(SP::G_HALF[3 * g + 1])), RC(CD(SP::G_HALF[3 * g + 2]))));
+        sfor<0, (ty == TDSG_CAPSULE ? 2 : 1)>([&](auto Jc) {
+          constexpr int j = decltype(Jc)::value;
+          const V3<RC> pos = (ty == TDSG_CAPSULE) ? (j == 0 ? c + half : c - half) : c;
+          const RC dist = dot(pos, pn) + plane_off - rad;
+          if (io.contact_dist && live) io.contact_dist[(size_t)(cand0 + j) * ns + e] = (float)dist;
+          cpos[lpt0 + j] = pos - pn * rad;                       // world_point_on_b, relative to O
+          cdist[lpt0 + j] = dist;
+          if (dist < RC(0)) my_active |= 1ull << (cand0 + j);
+        });
+      }
+    });
+  };
+
+  // ---- pass 1 on one link (kinematics.hpp:18-148, link.hpp:229-336) in the common frame ---------------------------------------
+  M3<RC> R_prev; V3<RC> p_prev; Sv<RA> v_prev;                       // carried along chains
+  Sv<RC> Sreg[SP::KMAX]; Sv<RA> vreg[SP::KMAX];                      // own links: S, then v / c / a
+  M3<RC> xwR[NXLA]; V3<RC> xwp[NXLA]; Sv<RA> xwa[NXLA];              // own links with non-adjacent children
+  RC plane_off; V3<RC> O;
+  auto pass1 = [&](auto Kc) {
+    constexpr int k = decltype(Kc)::value;
+    constexpr int fl = SP::L_FLAGS[R][k], lpar = SP::L_LPAR[R][k], jt = SP::L_JTYPE[R][k];
+    M3<RC> Rp; V3<RC> pp; Sv<RA> vp;
+    if constexpr ((fl & TDS_TF_PARENT_ADJ) != 0) { Rp = R_prev; pp = p_prev; vp = v_prev; }
+    else if constexpr (lpar < NT) {      // base (slot 0) or a published trunk link
+      constexpr int slot = lpar < 0 ? 0 : SP::L_XW[R][lpar < 0 ? 0 : lpar] + 1;
+      static_assert(lpar < 0 || slot >= 1, "parent transform not published");
+      Rp = ld9<RC>(xw_rc(slot), ST); pp = ld3<RC>(xw_rc(slot) + 9 * ST, ST); vp = ld6<RA>(xw_ra(slot), ST);
+    } else {                             // own branch parent
+      constexpr int xs = SP::L_XW[R][lpar];
+      Rp = xwR[xs]; pp = xwp[xs]; vp = vreg[lpar];
+    }
+    constexpr double tx = SP::L_XT[R][k][9], ty = SP::L_XT[R][k][10], tz = SP::L_XT[R][k][11];
+    V3<RC> pi = pp;
+    if constexpr (tx != 0.0 || ty != 0.0 || tz != 0.0) pi = pp + mul(Rp, v3<RC>(RC(tx), RC(ty), RC(tz)));
+    M3<RC> Ri = Rp;
+    if constexpr (!(fl & TDS_LF_XT_IDENT)) {
+      M3<RC> r;
+      r.xx = RC(CD(SP::L_XT[R][k][0])); r.xy = RC(CD(SP::L_XT[R][k][1])); r.xz = RC(CD(SP::L_XT[R][k][2]));
+      r.yx = RC(CD(SP::L_XT[R][k][3])); r.yy = RC(CD(SP::L_XT[R][k][4])); r.yz = RC(CD(SP::L_XT[R][k][5]));
+      r.zx = RC(CD(SP::L_XT[R][k][6])); r.zy = RC(CD(SP::L_XT[R][k][7])); r.zz = RC(CD(SP::L_XT[R][k][8]));
+      Ri = mul(Rp, r);
+    }
+    Sv<RC> S; S.top = v3<RC>(RC(0), RC(0), RC(0)); S.bot = S.top;
+    if constexpr (!(fl & TDS_LF_FIXED)) {
+      const RC qi = RC(qv[k]);
+      constexpr double ax = SP::L_AXIS[R][k][0], ay = SP::L_AXIS[R][k][1], az = SP::L_AXIS[R][k][2];
+      auto rot_axis = [&]() -> V3<RC> {    // Ri * axis, unit axes folded to a column
+        if constexpr (ax == 1.0 && ay == 0.0 && az == 0.0) return col_x(Ri);
+        else if constexpr (ax == 0.0 && ay == 1.0 && az == 0.0) return col_y(Ri);
+        else if constexpr (ax == 0.0 && ay == 0.0 && az == 1.0) return col_z(Ri);
+        else return mul(Ri, v3<RC>(RC(ax), RC(ay), RC(az)));
+      };
+      if constexpr ((fl & TDS_LF_PRISMATIC) != 0) {
+        const V3<RC> d = rot_axis();
+        pi = axpy(d, qi, pi);
+        S.bot = d;
+      } else {
+        const V3<RC> w = rot_axis();
+        if constexpr (jt == TDSJ_REVOLUTE_AXIS) {
+          const RC dl = sqrt_t(RC(ax * ax + ay * ay + az * az));
+          RC s, c;
+          sincos_t(qi * RC(0.5), &s, &c);
+          s = s / dl;
+          Ri = mul(Ri, quat_to_matrix<RC>(RC(ax) * s, RC(ay) * s, RC(az) * s, c));
+        } else {
+          RC s, c;
+          sincos_t(qi, &s, &c);
+          const V3<RC> cx = col_x(Ri), cy = col_y(Ri), cz = col_z(Ri);
+          if constexpr (jt == TDSJ_REVOLUTE_X) set_cols(Ri, cx, axpy(cz, s, cy * c), axpy(cy, -s, cz * c));
+          else if constexpr (jt == TDSJ_REVOLUTE_Y) set_cols(Ri, axpy(cz, -s, cx * c), cy, axpy(cx, s, cz * c));
+          else set_cols(Ri, axpy(cy, s, cx * c), axpy(cx, -s, cy * c), cz);
+        }
+        S.top = w;
+        S.bot = cross(pi, w);
+      }
+    }
+    if constexpr (k < NT) st6<RC>(ts_S(k), ST, S); else Sreg[k] = S;
+    {   // rigid-body inertia about O in world axes (own links: private shared memory; massless links: nothing)
+      constexpr bool massless = SP::L_RBIC[R][k][0] == 0.0 && SP::L_RBIC[R][k][4] == 0.0 && SP::L_RBIC[R][k][5] == 0.0 && SP::L_RBIC[R][k][6] == 0.0 &&
+                                SP::L_RBIC[R][k][7] == 0.0 && SP::L_RBIC[R][k][8] == 0.0 && SP::L_RBIC[R][k][9] == 0.0;
+      if constexpr (!massless) {
+        Rbi<RC> r;
+        r.m = RC(CD(SP::L_RBIC[R][k][0]));
+        const V3<RC> c = pi + mul(Ri, v3<RC>(RC(CD(SP::L_RBIC[R][k][1])), RC(CD(SP::L_RBIC[R][k][2])), RC(CD(SP::L_RBIC[R][k][3]))));
+        r.h = c * r.m;
+        S3<RA> Icf;
+        Icf.xx = RA(CD(SP::L_RBIC[R][k][4])); Icf.xy = RA(CD(SP::L_RBIC[R][k][5])); Icf.xz = RA(CD(SP::L_RBIC[R][k][6]));
+        Icf.yy = RA(CD(SP::L_RBIC[R][k][7])); Icf.yz = RA(CD(SP::L_RBIC[R][k][8])); Icf.zz = RA(CD(SP::L_RBIC[R][k][9]));
+        const S3<RA> Irot = rot_sym(cvt<RA>(Ri), Icf);
+        r.I.xx = RC(Irot.xx); r.I.xy = RC(Irot.xy); r.I.xz = RC(Irot.xz); r.I.yy = RC(Irot.yy); r.I.yz = RC(Irot.yz); r.I.zz = RC(Irot.zz);
+        const RC cc = dot(c, c);
+        r.I.xx += r.m * (cc - c.x * c.x); r.I.yy += r.m * (cc - c.y * c.y); r.I.zz += r.m * (cc - c.z * c.z);
+        r.I.xy -= r.m * c.x * c.y; r.I.xz -= r.m * c.x * c.z; r.I.yz -= r.m * c.y * c.z;
+        if constexpr (k < NT) st_rbi<RC>(tl_rbi(k), ST, r);
+        else st_rbi<RC>(sp<RC>(priv, lane, (k - NT) * 10 * RCW), ST, r);
+      }
+    }
+    Sv<RA> v = vp;
+    if constexpr (!(fl & TDS_LF_FIXED)) {
+      const RA qdi = RA(qdv[k]);
+      const Sv<RA> Sf = cvt_sv<RA>(S);
+      v.top = axpy(Sf.top, qdi, v.top);
+      v.bot = axpy(Sf.bot, qdi, v.bot);
+    }
+    if constexpr (k < NT) st6<RA>(tl_v(k), ST, v); else vreg[k] = v;
+    constexpr int xs = SP::L_XW[R][k];
+    if constexpr (xs >= 0) {
+      if constexpr (k < NT) { st9<RC>(xw_rc(xs + 1), ST, Ri); st3<RC>(xw_rc(xs + 1) + 9 * ST, ST, pi); st6<RA>(xw_ra(xs + 1), ST, v); }
+      else { xwR[xs] = Ri; xwp[xs] = pi; }
+    }
+    if (want_contacts) emit_geoms(IC<SP::L_GB[R][k]>{}, IC<SP::L_GE[R][k]>{}, IC<SP::L_CAND[R][k]>{}, IC<SP::L_LPT[R][k]>{}, Ri, pi, plane_off);
+    if (io.link_xf && live) {
+      float* o = io.link_xf + (size_t)CI(SP::L_LINK[R][k]) * 12 * ns + e;
+      o[0] = (float)Ri.xx; o[(size_t)1 * ns] = (float)Ri.xy; o[(size_t)2 * ns] = (float)Ri.xz;
+      o[(size_t)3 * ns] = (float)Ri.yx; o[(size_t)4 * ns] = (float)Ri.yy; o[(size_t)5 * ns] = (float)Ri.yz;
+      o[(size_t)6 * ns] = (float)Ri.zx; o[(size_t)7 * ns] = (float)Ri.zy; o[(size_t)8 * ns] = (float)Ri.zz;
+      o[(size_t)9 * ns] = (float)(pi.x + O.x); o[(size_t)10 * ns] = (float)(pi.y + O.y); o[(size_t)11 * ns] = (float)(pi.z + O.z);
+    }
+    R_prev = Ri; p_prev = pi; v_prev = v;
+  };
+
+  // ---- pass 1a: role 0 computes the origin and walks the trunk --------------------------------------------------------------
+  RC* const sO = sp<RC>(smem, lane, L::O);
+  RC* const sRb = sp<RC>(smem, lane, L::RB);
+  if constexpr (R == 0) {
+    M3<RC> Rb0 = m3_identity<RC>();
+    O = v3<RC>(RC(0), RC(0), RC(0));
+    if constexpr (FLOAT) {
+      Rb0 = quat_to_matrix<RC>(RC(bq[0]), RC(bq[1]), RC(bq[2]), RC(bq[3]));
+      O = v3<RC>(RC(bq[4]), RC(bq[5]), RC(bq[6]));
+    } else {   // end of the translation-only root chain (links 0..N_PREFIX-1, trunk links in model order)
+      M3<RC> Rc = m3_identity<RC>();
+      sfor<0, SP::N_PRE>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        O = O + mul(Rc, v3<RC>(RC(CD(SP::PRE_XT[12 * i + 9])), RC(CD(SP::PRE_XT[12 * i + 10])), RC(CD(SP::PRE_XT[12 * i + 11]))));
+        if constexpr (i < SP::N_PREFIX) {
+          static_assert(SP::L_LINK[0][i] == i && i < NT, "root prefix must be trunk links in model order");
+          if constexpr (!(SP::PRE_FLAGS[i] & TDS_LF_XT_IDENT)) {
+            M3<RC> r;
+            r.xx = RC(CD(SP::PRE_XT[12 * i])); r.xy = RC(CD(SP::PRE_XT[12 * i + 1])); r.xz = RC(CD(SP::PRE_XT[12 * i + 2]));
+            r.yx = RC(CD(SP::PRE_XT[12 * i + 3])); r.yy = RC(CD(SP::PRE_XT[12 * i + 4])); r.yz = RC(CD(SP::PRE_XT[12 * i + 5]));
+            r.zx = RC(CD(SP::PRE_XT[12 * i + 6])); r.zy = RC(CD(SP::PRE_XT[12 * i + 7])); r.zz = RC(CD(SP::PRE_XT[12 * i + 8]));
+            Rc = mul(Rc, r);
+          }
+          if constexpr ((SP::PRE_FLAGS[i] & TDS_LF_PRISMATIC) != 0) {
+            const RC qi = RC(qv[i]);
+            O = O + mul(Rc, v3<RC>(RC(CD(SP::PRE_AXIS[3 * i])) * qi, RC(CD(SP::PRE_AXIS[3 * i + 1])) * qi, RC(CD(SP::PRE_AXIS[3 * i + 2])) * qi));
+          }
+        }
+      });
+    }
+    plane_off = dot(O, pn) - RC(CD(SP::PLANE_C[0]));
+    st3<RC>(sO, ST, O); sO[3 * ST] = plane_off;
+    if constexpr (FLOAT) st9<RC>(sRb, ST, Rb0);
+    R_prev = Rb0;
+    p_prev = FLOAT ? v3<RC>(RC(0), RC(0), RC(0)) : v3<RC>(-O.x, -O.y, -O.z);
+    if constexpr (FLOAT) {
+      const M3<RA> RbA = cvt<RA>(Rb0);
+      v_prev.top = mul(RbA, v3<RA>(RA(bqd[0]), RA(bqd[1]), RA(bqd[2])));
+      v_prev.bot = mul(RbA, v3<RA>(RA(bqd[3]), RA(bqd[4]), RA(bqd[5])));
+    } else { v_prev.top = v3<RA>(RA(0), RA(0), RA(0)); v_prev.bot = v_prev.top; }
+    st9<RC>(xw_rc(0), ST, R_prev); st3<RC>(xw_rc(0) + 9 * ST, ST, p_prev); st6<RA>(xw_ra(0), ST, v_prev);
+    if (want_contacts) emit_geoms(IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{}, R_prev, p_prev, plane_off);
+    sfor<0, NT>(pass1);
+  }
+  __syncthreads();
+  // ---- pass 1b: every role walks its subtree --------------------------------------------------------------------------------------
+  if constexpr (R != 0) { O = ld3<RC>(sO, ST); plane_off = sO[3 * ST]; }
+  M3<RC> Rb = m3_identity<RC>();
+  if constexpr (FLOAT) Rb = ld9<RC>(sRb, ST);
+  sfor<NT, NLOC>(pass1);
+  // set of active candidates of the environment: OR over the roles through shared memory
+  flg[(2 * R) * ST] = (unsigned)my_active;
+  flg[(2 * R + 1) * ST] = (unsigned)(my_active >> 32);
+  const bool cta_contact = __syncthreads_or(my_active != 0ull) != 0;   // uniform: any contact in this tile
+  const bool solve = (mode == MODE_FULL) && cta_contact;
+  unsigned long long team_active = 0ull;
+#pragma unroll
+  for (int r = 0; r < TT; ++r) team_active |= ((unsigned long long)flg[(2 * r + 1) * ST] << 32) | flg[(2 * r) * ST];
+  TDSS_PHASE();  // 2
+
+  // ---- pass 2 on one link: ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ------------------------------------
+  // Own blocks of the joint-space inertia in registers: M_kk (lower triangle), C = coupling with the trunk dofs;
+  // role 0 also holds the trunk block B.
+  RS Mkk[NODA * (NODA + 1) / 2], Cm[NODA * NTDA], Bm[NTRIA];
+#pragma unroll
+  for (int i = 0; i < NODA * (NODA + 1) / 2; ++i) Mkk[i] = RS(0);
+#pragma unroll
+  for (int i = 0; i < NODA * NTDA; ++i) Cm[i] = RS(0);
+#pragma unroll
+  for (int i = 0; i < NTRIA; ++i) Bm[i] = RS(0);
+  Sv<RA> Ureg[SP::KMAX]; RA invDreg[SP::KMAX], ureg[SP::KMAX];
+  Abi<RA> cA = abi_nz<RA>(); Sv<RA> cP = sv_nz<RA>(); Rbi<RC> cC = rbi_nz<RC>();        // carry from the adjacent child
+  Abi<RA> accA[NACCA]; Sv<RA> accP[NACCA]; Rbi<RC> accC[NACCA];                          // accumulators (attachment + internal)
+#pragma unroll
+  for (int s = 0; s < NACCA; ++s) { accA[s] = abi_nz<RA>(); accP[s] = sv_nz<RA>(); accC[s] = rbi_nz<RC>(); }
+  auto S_of = [&](auto Jc) -> Sv<RC> {
+    constexpr int j = decltype(Jc)::value;
+    if constexpr (j < NT) return ld6<RC>(ts_S(j), ST); else return Sreg[j];
+  };
+  auto pass2 = [&](auto Kc) {
+    constexpr int k = decltype(Kc)::value;
+    constexpr int fl = SP::L_FLAGS[R][k];
+    constexpr bool massless = SP::L_RBIC[R][k][0] == 0.0 && SP::L_RBIC[R][k][4] == 0.0 && SP::L_RBIC[R][k][5] == 0.0 && SP::L_RBIC[R][k][6] == 0.0 &&
+                              SP::L_RBIC[R][k][7] == 0.0 && SP::L_RBIC[R][k][8] == 0.0 && SP::L_RBIC[R][k][9] == 0.0;
+    Sv<RA> v;
+    if constexpr (k < NT) v = ld6<RA>(tl_v(k), ST); else v = vreg[k];
+    Rbi<RC> Ic = rbi_nz<RC>();
+    Abi<RA> Ia = abi_nz<RA>();
+    Sv<RA> pA = sv_nz<RA>();
+    if constexpr (!massless) {
+      if constexpr (k < NT) Ic = ld_rbi<RC>(tl_rbi(k), ST); else Ic = ld_rbi<RC>(sp<RC>(priv, lane, (k - NT) * 10 * RCW), ST);
+      const Rbi<RA> rb = cvt_rbi<RA>(Ic);
+      Ia = abi_from_rbi(rb);
+      pA = cross_mf(v, rbi_mul(rb, v));                      // kinematics.hpp:132
+    }
+    if constexpr ((fl & TDS_TF_CHILD_ADJ) != 0) { abi_add(Ia, cA); pA = pA + cP; rbi_add(Ic, cC); }
+    constexpr int as = SP::L_ACC[R][k];
+    if constexpr (as >= 0) {
+      if constexpr (as < SP::N_ATT) {   // attachment slot: this role's part is in registers, the others' in shared memory
+        static_assert(R == 0 || k < 0, "attachment accumulators are consumed by role 0");
+        abi_add(Ia, accA[as]); pA = pA + accP[as]; rbi_add(Ic, accC[as]);
+        sfor<1, TT>([&](auto Rc_) {
+          constexpr int r = decltype(Rc_)::value;
+          Abi<RA> sa; Sv<RA> sv_;
+          acc_ld27<RA>(sp<RA>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW), ST, sa, sv_);
+          abi_add(Ia, sa); pA = pA + sv_;
+          rbi_add(Ic, ld_rbi<RC>(sp<RC>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW + L::ACC_IC), ST));
+        });
+      } else { abi_add(Ia, accA[as]); pA = pA + accP[as]; rbi_add(Ic, accC[as]); }
+    }
+    Sv<RA> pa = pA;
+    if constexpr (!(fl & TDS_LF_FIXED)) {
+      const Sv<RC> Sd = S_of(IC<k>{});
+      const Sv<RA> S = cvt_sv<RA>(Sd);
+      const RA qdj = RA(qdv[k]);
+      Sv<RA> vJ; vJ.top = S.top * qdj; vJ.bot = S.bot * qdj;
+      const Sv<RA> c = cross_mm(v, vJ);                      // kinematics.hpp:96-97
+      const Sv<RA> U = abi_mul(Ia, S);                       // forward_dynamics.hpp:111
+      const RA D = dot(S, U);
+      const RA invD = RA(1) / D;
+      RA tau = RA(tauv[k]);
+      if constexpr (SP::L_SD[R][k][0] != 0.0) tau -= RA(CD(SP::L_SD[R][k][0])) * RA(qv[k]);
+      if constexpr (SP::L_SD[R][k][1] != 0.0) tau -= RA(CD(SP::L_SD[R][k][1])) * qdj;
+      const RA u = tau - dot(S, pA);                         // :129
+      if constexpr (k < NT) { st6<RA>(tl_v(k), ST, c); st6<RA>(tl_u(k), ST, U); tl_u(k)[6 * ST] = invD; tl_u(k)[7 * ST] = u; }
+      else { vreg[k] = c; Ureg[k] = U; invDreg[k] = invD; ureg[k] = u; }
+      const V3<RA> ut = U.top * invD, ub = U.bot * invD;     // Ia -= U (U/D)^T, :160-168
+      Ia.I.xx -= U.top.x * ut.x; Ia.I.xy -= U.top.x * ut.y; Ia.I.xz -= U.top.x * ut.z;
+      Ia.I.yy -= U.top.y * ut.y; Ia.I.yz -= U.top.y * ut.z; Ia.I.zz -= U.top.z * ut.z;
+      Ia.H.xx -= U.top.x * ub.x; Ia.H.xy -= U.top.x * ub.y; Ia.H.xz -= U.top.x * ub.z;
+      Ia.H.yx -= U.top.y * ub.x; Ia.H.yy -= U.top.y * ub.y; Ia.H.yz -= U.top.y * ub.z;
+      Ia.H.zx -= U.top.z * ub.x; Ia.H.zy -= U.top.z * ub.y; Ia.H.zz -= U.top.z * ub.z;
+      Ia.M.xx -= U.bot.x * ub.x; Ia.M.xy -= U.bot.x * ub.y; Ia.M.xz -= U.bot.x * ub.z;
+      Ia.M.yy -= U.bot.y * ub.y; Ia.M.yz -= U.bot.y * ub.z; Ia.M.zz -= U.bot.z * ub.z;
+      const Sv<RA> Iac = abi_mul(Ia, c);                     // :171
+      const RA uD = u * invD;
+      pa.top = pA.top + Iac.top + U.top * uD;                // :173
+      pa.bot = pA.bot + Iac.bot + U.bot * uD;
+      if (solve) {   // CRBA column (mass_matrix.hpp:86-111): M_ij = S_j . (Ic_i S_i)
+        const Sv<RC> F = rbi_mul(Ic, Sd);
+        const RS mii = RS(dot(Sd, F));
+        constexpr int ld = SP::L_LDOF[R][k];
+        if constexpr (k < NT) Bm[tri(ld, ld)] = mii; else Mkk[tri(ld - NTD, ld - NTD)] = mii;
+        sfor<0, k>([&](auto Jc) {
+          constexpr int j = decltype(Jc)::value;
+          constexpr int lj = SP::L_LDOF[R][j];
+          if constexpr (lj >= 0 && is_anc<SP, R>(j, k)) {
+            const RS val = RS(dot(S_of(IC<j>{}), F));
+            if constexpr (k < NT) Bm[tri(ld, lj)] = val;
+            else if constexpr (lj >= NTD) Mkk[tri(ld - NTD, lj - NTD)] = val;
+            else Cm[(ld - NTD) * NTDA + lj] = val;
+          }
+        });
+        if constexpr (FLOAT) {
+          const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
+          if constexpr (k < NT) {
+            Bm[tri(ld, 0)] = RS(ft.x); Bm[tri(ld, 1)] = RS(ft.y); Bm[tri(ld, 2)] = RS(ft.z);
+            Bm[tri(ld, 3)] = RS(fb.x); Bm[tri(ld, 4)] = RS(fb.y); Bm[tri(ld, 5)] = RS(fb.z);
+          } else {
+            RS* row = Cm + (ld - NTD) * NTDA;
+            row[0] = RS(ft.x); row[1] = RS(ft.y); row[2] = RS(ft.z); row[3] = RS(fb.x); row[4] = RS(fb.y); row[5] = RS(fb.z);
+          }
+        }
+      }
+    }
+    if constexpr ((fl & TDS_TF_PARENT_ADJ) != 0) { cA = Ia; cP = pa; cC = Ic; }
+    else {
+      constexpr int slot = SP::L_PAR[R][k];
+      if constexpr (slot >= 0) { abi_add(accA[slot], Ia); accP[slot] = accP[slot] + pa; rbi_add(accC[slot], Ic); }
+    }
+  };
+  // ---- pass 2a: subtrees; publish this role's attachment accumulators ------------------------------------------------------------------
+  sfor_rev<NT, NLOC>(pass2);
+  if constexpr (R != 0) {
+    sfor<0, SP::N_ATT>([&](auto Sc) {
+      constexpr int s = decltype(Sc)::value;
+      RA* pa_ = sp<RA>(smem, lane, L::ACC + (R * cmax(SP::N_ATT, 1) + s) * L::ACCW);
+      const Abi<RA>& a = accA[s]; const Sv<RA>& f = accP[s];
+      pa_[0] = a.I.xx; pa_[ST] = a.I.xy; pa_[2 * ST] = a.I.xz; pa_[3 * ST] = a.I.yy; pa_[4 * ST] = a.I.yz; pa_[5 * ST] = a.I.zz;
+      pa_[6 * ST] = a.H.xx; pa_[7 * ST] = a.H.xy; pa_[8 * ST] = a.H.xz; pa_[9 * ST] = a.H.yx; pa_[10 * ST] = a.H.yy; pa_[11 * ST] = a.H.yz;
+      pa_[12 * ST] = a.H.zx; pa_[13 * ST] = a.H.zy; pa_[14 * ST] = a.H.zz;
+      pa_[15 * ST] = a.M.xx; pa_[16 * ST] = a.M.xy; pa_[17 * ST] = a.M.xz; pa_[18 * ST] = a.M.yy; pa_[19 * ST] = a.M.yz; pa_[20 * ST] = a.M.zz;
+      pa_[21 * ST] = f.top.x; pa_[22 * ST] = f.top.y; pa_[23 * ST] = f.top.z; pa_[24 * ST] = f.bot.x; pa_[25 * ST] = f.bot.y; pa_[26 * ST] = f.bot.z;
+      st_rbi<RC>(sp<RC>(smem, lane, L::ACC + (R * cmax(SP::N_ATT, 1) + s) * L::ACCW + L::ACC_IC), ST, accC[s]);
+    });
+  }
+  __syncthreads();
+
+  // ---- pass 2b + base + pass 3a: role 0 finishes the trunk --------------------------------------------------------------------------------
+  const RA dtA = RA(P.dt);
+  Sv<RA> a_prev;
+  auto pass3 = [&](auto Kc) {
+    constexpr int k = decltype(Kc)::value;
+    constexpr int fl = SP::L_FLAGS[R][k], lpar = SP::L_LPAR[R][k];
+    Sv<RA> a;
+    if constexpr ((fl & TDS_TF_PARENT_ADJ) != 0) a = a_prev;
+    else if constexpr (lpar < NT) {
+      constexpr int slot = lpar < 0 ? 0 : SP::L_XW[R][lpar < 0 ? 0 : lpar] + 1;
+      a = ld6<RA>(xw_ra(slot) + 6 * ST, ST);
+    } else a = xwa[CI(SP::L_XW[R][lpar])];
+    if constexpr (!(fl & TDS_LF_FIXED)) {
+      Sv<RA> c, U; RA invD, u;
+      if constexpr (k < NT) { c = ld6<RA>(tl_v(k), ST); U = ld6<RA>(tl_u(k), ST); invD = tl_u(k)[6 * ST]; u = tl_u(k)[7 * ST]; }
+      else { c = vreg[k]; U = Ureg[k]; invD = invDreg[k]; u = ureg[k]; }
+      a = a + c;
+      const RA qdd = invD * (u - dot(U, a));
+      const Sv<RA> S = cvt_sv<RA>(S_of(IC<k>{}));
+      a.top = axpy(S.top, qdd, a.top);
+      a.bot = axpy(S.bot, qdd, a.bot);
+      if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)CI(SP::L_QDIDX[R][k]) * ns + e] = (float)qdd; }
+      else qdv[k] = (float)(RA(qdv[k]) + qdd * dtA);
+    }
+    constexpr int xs = SP::L_XW[R][k];
+    if constexpr (xs >= 0) {
+      if constexpr (k < NT) st6<RA>(xw_ra(xs + 1) + 6 * ST, ST, a); else xwa[xs] = a;
+    }
+    a_prev = a;
+  };
+  if constexpr (R == 0) {
+    sfor_rev<0, NT>(pass2);
+    // base acceleration (forward_dynamics.hpp:218-243)
+    Sv<RC> base_acc_b; base_acc_b.top = v3<RC>(RC(0), RC(0), RC(0)); base_acc_b.bot = base_acc_b.top;
+    if constexpr (FLOAT) {
+      Abi<RA> Ach = abi_nz<RA>(); Sv<RA> pch = sv_nz<RA>(); Rbi<RC> Icch = rbi_nz<RC>();
+      if constexpr (NT > 0) {
+        if constexpr (SP::L_LPAR[0][0] < 0 && (SP::L_FLAGS[0][0] & TDS_TF_PARENT_ADJ) != 0) { abi_add(Ach, cA); pch = pch + cP; rbi_add(Icch, cC); }
+      }
+      if constexpr (SP::BASE_SLOT >= 0) {
+        constexpr int as = SP::BASE_SLOT;
+        abi_add(Ach, accA[as]); pch = pch + accP[as]; rbi_add(Icch, accC[as]);
+        if constexpr (as < SP::N_ATT) {
+          sfor<1, TT>([&](auto Rc_) {
+            constexpr int r = decltype(Rc_)::value;
+            Abi<RA> sa; Sv<RA> sv_;
+            acc_ld27<RA>(sp<RA>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW), ST, sa, sv_);
+            abi_add(Ach, sa); pch = pch + sv_;
+            rbi_add(Icch, ld_rbi<RC>(sp<RC>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW + L::ACC_IC), ST));
+          });
+        }
+      }
+      const M3<RA> Rt = cvt<RA>(transpose(Rb));
+      Abi<RA> Ab;
+      {
+        Rbi<RA> rbb; rbb.m = RA(CD(SP::BASE_RBI[0])); rbb.h = v3<RA>(RA(CD(SP::BASE_RBI[1])), RA(CD(SP::BASE_RBI[2])), RA(CD(SP::BASE_RBI[3])));
+        rbb.I = {RA(CD(SP::BASE_RBI[4])), RA(CD(SP::BASE_RBI[5])), RA(CD(SP::BASE_RBI[6])), RA(CD(SP::BASE_RBI[7])), RA(CD(SP::BASE_RBI[8])), RA(CD(SP::BASE_RBI[9]))};
+        Ab = abi_from_rbi(rbb);
+        Abi<RA> Arot;
+        Arot.I = rot_sym(Rt, Ach.I); Arot.M = rot_sym(Rt, Ach.M); Arot.H = rot_gen(Rt, Ach.H);
+        abi_add(Ab, Arot);
+      }
+      Sv<RA> pb;
+      {   // gyroscopic bias, kinematics.hpp:54-61
+        const M3<RA> RbA = cvt<RA>(Rb);
+        M3<RA> Ic0;
+        Ic0.xx = RA((float)CD(SP::BASE_INERTIA_COM[0])); Ic0.xy = RA((float)CD(SP::BASE_INERTIA_COM[1])); Ic0.xz = RA((float)CD(SP::BASE_INERTIA_COM[2]));
+        Ic0.yx = RA((float)CD(SP::BASE_INERTIA_COM[3])); Ic0.yy = RA((float)CD(SP::BASE_INERTIA_COM[4])); Ic0.yz = RA((float)CD(SP::BASE_INERTIA_COM[5]));
+        Ic0.zx = RA((float)CD(SP::BASE_INERTIA_COM[6])); Ic0.zy = RA((float)CD(SP::BASE_INERTIA_COM[7])); Ic0.zz = RA((float)CD(SP::BASE_INERTIA_COM[8]));
+        const M3<RA> Iw = rot_gen(RbA, Ic0);
+        const V3<RA> wb = v3<RA>(RA(bqd[0]), RA(bqd[1]), RA(bqd[2]));
+        pb.top = cross(wb, mul(Iw, wb)) + mul(Rt, pch.top);
+        pb.bot = mul(Rt, pch.bot);
+      }
+      if (solve) {   // base block of M (mass_matrix.hpp:114-120) in the base frame
+        Rbi<RC> Ib; Ib.m = RC(CD(SP::BASE_RBI[0])); Ib.h = v3<RC>(RC(CD(SP::BASE_RBI[1])), RC(CD(SP::BASE_RBI[2])), RC(CD(SP::BASE_RBI[3])));
+        Ib.I = {RC(CD(SP::BASE_RBI[4])), RC(CD(SP::BASE_RBI[5])), RC(CD(SP::BASE_RBI[6])), RC(CD(SP::BASE_RBI[7])), RC(CD(SP::BASE_RBI[8])), RC(CD(SP::BASE_RBI[9]))};
+        const M3<RC> RtC = transpose(Rb);
+        Rbi<RC> rot; rot.m = Icch.m; rot.h = mul(RtC, Icch.h); rot.I = rot_sym(RtC, Icch.I);
+        rbi_add(Ib, rot);
+        const RS z = RS(0);
+        Bm[tri(0, 0)] = RS(Ib.I.xx); Bm[tri(1, 0)] = RS(Ib.I.xy); Bm[tri(1, 1)] = RS(Ib.I.yy);
+        Bm[tri(2, 0)] = RS(Ib.I.xz); Bm[tri(2, 1)] = RS(Ib.I.yz); Bm[tri(2, 2)] = RS(Ib.I.zz);
+        Bm[tri(3, 0)] = z;            Bm[tri(3, 1)] = RS(Ib.h.z);  Bm[tri(3, 2)] = RS(-Ib.h.y);
+        Bm[tri(4, 0)] = RS(-Ib.h.z);  Bm[tri(4, 1)] = z;           Bm[tri(4, 2)] = RS(Ib.h.x);
+        Bm[tri(5, 0)] = RS(Ib.h.y);   Bm[tri(5, 1)] = RS(-Ib.h.x); Bm[tri(5, 2)] = z;
+        Bm[tri(3, 3)] = RS(Ib.m); Bm[tri(4, 3)] = z; Bm[tri(4, 4)] = RS(Ib.m); Bm[tri(5, 3)] = z; Bm[tri(5, 4)] = z; Bm[tri(5, 5)] = RS(Ib.m);
+      }
+      {   // -base_abi.inv_mul(bias) with the reference's block inverse (C = -H), inertia.hpp:302-328
+        M3<RC> I3, H3, M3m;
+        I3.xx = Ab.I.xx; I3.xy = Ab.I.xy; I3.xz = Ab.I.xz; I3.yx = Ab.I.xy; I3.yy = Ab.I.yy; I3.yz = Ab.I.yz; I3.zx = Ab.I.xz; I3.zy = Ab.I.yz; I3.zz = Ab.I.zz;
+        H3 = cvt<RC>(Ab.H);
+        M3m.xx = Ab.M.xx; M3m.xy = Ab.M.xy; M3m.xz = Ab.M.xz; M3m.yx = Ab.M.xy; M3m.yy = Ab.M.yy; M3m.yz = Ab.M.yz; M3m.zx = Ab.M.xz; M3m.zy = Ab.M.yz; M3m.zz = Ab.M.zz;
+        auto inv3 = [](const M3<RC>& m) {
+          M3<RC> o;
+          RC c0 = m.yy * m.zz - m.yz * m.zy, c1 = m.yz * m.zx - m.yx * m.zz, c2 = m.yx * m.zy - m.yy * m.zx;
+          RC s = RC(1) / (m.xx * c0 + m.xy * c1 + m.xz * c2);
+          o.xx = c0 * s; o.xy = (m.xz * m.zy - m.xy * m.zz) * s; o.xz = (m.xy * m.yz - m.xz * m.yy) * s;
+          o.yx = c1 * s; o.yy = (m.xx * m.zz - m.xz * m.zx) * s; o.yz = (m.xz * m.yx - m.xx * m.yz) * s;
+          o.zx = c2 * s; o.zy = (m.xy * m.zx - m.xx * m.zy) * s; o.zz = (m.xx * m.yy - m.xy * m.yx) * s;
+          return o;
+        };
+        auto neg = [](M3<RC> m) { m.xx = -m.xx; m.xy = -m.xy; m.xz = -m.xz; m.yx = -m.yx; m.yy = -m.yy; m.yz = -m.yz; m.zx = -m.zx; m.zy = -m.zy; m.zz = -m.zz; return m; };
+        auto sub = [](M3<RC> a, const M3<RC>& b) { a.xx -= b.xx; a.xy -= b.xy; a.xz -= b.xz; a.yx -= b.yx; a.yy -= b.yy; a.yz -= b.yz; a.zx -= b.zx; a.zy -= b.zy; a.zz -= b.zz; return a; };
+        auto add = [](M3<RC> a, const M3<RC>& b) { a.xx += b.xx; a.xy += b.xy; a.xz += b.xz; a.yx += b.yx; a.yy += b.yy; a.yz += b.yz; a.zx += b.zx; a.zy += b.zy; a.zz += b.zz; return a; };
+        M3<RC> Ainv = inv3(I3);
+        M3<RC> C = neg(H3);
+        M3<RC> Dm = inv3(sub(M3m, mul(mul(C, Ainv), H3)));
+        M3<RC> AinvBD = mul(mul(Ainv, H3), Dm);
+        M3<RC> Ii = add(Ainv, mul(mul(AinvBD, C), Ainv));
+        M3<RC> Hi = neg(AinvBD);
+        V3<RC> ft = cvt<RC>(pb.top), fb = cvt<RC>(pb.bot);
+        V3<RC> at = mul(Ii, ft) + mul(Hi, fb);
+        V3<RC> ab = mul(Dm, fb) + mulT(Hi, ft);
+        base_acc_b.top = v3<RC>(-at.x, -at.y, -at.z);
+        base_acc_b.bot = v3<RC>(-ab.x, -ab.y, -ab.z);
+      }
+      a_prev.top = cvt<RA>(mul(Rb, base_acc_b.top));
+      a_prev.bot = cvt<RA>(mul(Rb, base_acc_b.bot));
+    } else {
+      a_prev.top = v3<RA>(RA(0), RA(0), RA(0));
+      a_prev.bot = v3<RA>(RA(-P.gravity[0]), RA(-P.gravity[1]), RA(-P.gravity[2]));
+    }
+    st6<RA>(xw_ra(0) + 6 * ST, ST, a_prev);
+    sfor<0, NT>(pass3);
+    if constexpr (FLOAT) {   // forward_dynamics.hpp:317-322 (gravity added un-rotated), integrator.hpp:153-163
+      const RC qb[6] = {base_acc_b.top.x, base_acc_b.top.y, base_acc_b.top.z, base_acc_b.bot.x + RC(P.gravity[0]),
+                        base_acc_b.bot.y + RC(P.gravity[1]), base_acc_b.bot.z + RC(P.gravity[2])};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
+        else bqd[k] = (float)(RC(bqd[k]) + qb[k] * RC(P.dt));
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tqd[k * ST] = bqd[k];
+    }
+    // publish the updated trunk velocities (contact Jacobian products of every role)
+    sfor<0, NT>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      if constexpr (SP::L_LDOF[0][k] >= 0) tqd[CI(SP::L_LDOF[0][k]) * ST] = qdv[k];
+    });
+  }
+  __syncthreads();
+  TDSS_PHASE();  // 3
+  // ---- pass 3b: subtrees -----------------------------------------------------------------------------------------------------------------------
+  sfor<NT, NLOC>(pass3);
+  TDSS_PHASE();  // 4
+  if (mode == MODE_FD) return;
+
+  // ---- contact solve: leaf-first elimination in registers ---------------------------------------------------------------------------------------
+  //   M_kk = L_k L_k^T, G = L_k^-1 C, S = B - sum_k G^T G = L_t L_t^T, Y = L^-1 Jc^T, PGS on w = Y p, dqd = L^-T w
+  //   (mb_constraint_solver.hpp:299-345, 417-436, 476-497).  Diagonal entries hold the INVERSE of the factor's diagonal.
+  if (solve) {
+    sfor<0, NOD>([&](auto Ic_) {
+      constexpr int i = decltype(Ic_)::value;
+      sfor<0, i + 1>([&](auto Jc) {
+        constexpr int j = decltype(Jc)::value;
+        RS s = Mkk[tri(i, j)];
+        sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(i, k)] * Mkk[tri(j, k)]; });
+        if constexpr (j < i) Mkk[tri(i, j)] = s * Mkk[tri(j, j)];
+        else Mkk[tri(i, i)] = RS(1) / sqrt_t(s);
+      });
+      sfor<0, NTD>([&](auto Tc) {
+        constexpr int t = decltype(Tc)::value;
+        RS s = Cm[i * NTDA + t];
+        sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(i, k)] * Cm[k * NTDA + t]; });
+        Cm[i * NTDA + t] = s * Mkk[tri(i, i)];
+      });
+    });
+    // partial Schur complement of this role -> shared memory (the accumulator region is free now)
+    RS* const Pk = sp<RS>(smem, lane, L::ACC + R * L::PW);
+    sfor<0, NTD>([&](auto T1) {
+      constexpr int t1 = decltype(T1)::value;
+      sfor<0, t1 + 1>([&](auto T2) {
+        constexpr int t2 = decltype(T2)::value;
+        RS s = RS(0);
+        sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; s += Cm[i * NTDA + t1] * Cm[i * NTDA + t2]; });
+        Pk[tri(t1, t2) * ST] = s;
+      });
+    });
+    __syncthreads();
+    RS* const Lt = sp<RS>(smem, lane, L::LT);
+    if constexpr (R == 0) {   // S = B - sum over the roles of G^T G, then S = L_t L_t^T
+      sfor<0, NTRI>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        const RS* p = sp<RS>(smem, lane, L::ACC);
+        Bm[i] -= (p[i * ST] + p[(L::PW / L::RSW + i) * ST]) + (p[(2 * (L::PW / L::RSW) + i) * ST] + p[(3 * (L::PW / L::RSW) + i) * ST]);
+      });
+      sfor<0, NTD>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        sfor<0, i + 1>([&](auto Jc) {
+          constexpr int j = decltype(Jc)::value;
+          RS s = Bm[tri(i, j)];
+          sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Bm[tri(i, k)] * Bm[tri(j, k)]; });
+          if constexpr (j < i) Bm[tri(i, j)] = s * Bm[tri(j, j)];
+          else Bm[tri(i, i)] = RS(1) / sqrt_t(s);
+          Lt[tri(i, j) * ST] = Bm[tri(i, j)];
+        });
+      });
+    }
+    __syncthreads();
+  }
+  TDSS_PHASE();  // 5
+  if (solve) {
+    const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b
+    const V3<RC> f1 = v3<RC>(RC(CD(SP::FR1[0])), RC(CD(SP::FR1[1])), RC(CD(SP::FR1[2])));
+    const V3<RC> f2 = v3<RC>(RC(CD(SP::FR2[0])), RC(CD(SP::FR2[1])), RC(CD(SP::FR2[2])));
+    const RS* const Lt = sp<RS>(smem, lane, L::LT);
+    // contact rows of this role's penetrating points: one row per direction (normal, friction 1, friction 2)
+    auto rows_of = [&](auto Kl, auto Gb, auto Ge, auto Cand0, auto Lpt0) {
+      constexpr int kl = decltype(Kl)::value, gb = decltype(Gb)::value, ge = decltype(Ge)::value;
+      sfor<gb, ge>([&](auto Gc) {
+        constexpr int g = decltype(Gc)::value;
+        constexpr int npt = geom_pts<SP>(g);
+        sfor<0, npt>([&](auto Jc_) {
+          constexpr int cand = decltype(Cand0)::value + pts_before<SP>(gb, g) + decltype(Jc_)::value;
+          constexpr int lpt = decltype(Lpt0)::value + pts_before<SP>(gb, g) + decltype(Jc_)::value;
+          if ((my_active >> cand) & 1ull) {
+            const V3<RC> xc = cpos[lpt];
+            RS ro[3][NODA], rt[3][NTDA];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+#pragma unroll
+              for (int i = 0; i < NODA; ++i) ro[d][i] = RS(0);
+#pragma unroll
+              for (int i = 0; i < NTDA; ++i) rt[d][i] = RS(0);
+            }
+            V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));
+            if constexpr (FLOAT) {   // jacobian.hpp:39-58 with r = x_c
+              const V3<RC> cols[6] = {v3<RC>(RC(0), -xc.z, xc.y), v3<RC>(xc.z, RC(0), -xc.x), v3<RC>(-xc.y, xc.x, RC(0)),
+                                      v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
+#pragma unroll
+              for (int k = 0; k < 6; ++k) {
+                rt[0][k] = RS(dot(nbv, cols[k])); rt[1][k] = RS(dot(f1, cols[k])); rt[2][k] = RS(dot(f2, cols[k]));
+                vel = vel + cols[k] * RC(tqd[k * ST]);
+              }
+            }
+            sfor<0, (kl < 0 ? 0 : kl + 1)>([&](auto Jc) {   // jacobian.hpp:63-80: the link and its ancestors
+              constexpr int j = decltype(Jc)::value;
+              constexpr int lj = SP::L_LDOF[R][j];
+              if constexpr (lj >= 0 && (j == kl || is_anc<SP, R>(j, kl))) {
+                const Sv<RC> S = S_of(IC<j>{});
+                const V3<RC> col = S.bot + cross(S.top, xc);
+                const RS c0 = RS(dot(nbv, col)), c1 = RS(dot(f1, col)), c2 = RS(dot(f2, col));
+                if constexpr (lj >= NTD) { ro[0][lj - NTD] = c0; ro[1][lj - NTD] = c1; ro[2][lj - NTD] = c2; vel = vel + col * RC(qdv[j]); }
+                else { rt[0][lj] = c0; rt[1][lj] = c1; rt[2][lj] = c2; vel = vel + col * RC(tqd[lj * ST]); }
+              }
+            });
+            RS* const row = sp<RS>(smem, lane, L::CON + cand * L::CONW);
+            constexpr int YO = 0, YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);
+            row[(BB + 0) * ST] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * cdist[lpt] / RC(P.dt));
+            row[(BB + 1) * ST] = RS(dot(f1, vel));
+            row[(BB + 2) * ST] = RS(dot(f2, vel));
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              // y_own = L_k^-1 r_own ;  y_t = L_t^-1 (r_t - G^T y_own)
+              sfor<0, NOD>([&](auto Ic_) {
+                constexpr int i = decltype(Ic_)::value;
+                RS s = ro[d][i];
+                sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(i, k)] * ro[d][k]; });
+                ro[d][i] = s * Mkk[tri(i, i)];
+              });
+              RS yy = RS(0);
+              sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; yy += ro[d][i] * ro[d][i]; row[(YO + d * L::NOD + i) * ST] = ro[d][i]; });
+              sfor<0, NTD>([&](auto Tc) {
+                constexpr int t = decltype(Tc)::value;
+                RS s = rt[d][t];
+                sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; s -= Cm[i * NTDA + t] * ro[d][i]; });
+                sfor<0, t>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Lt[tri(t, k) * ST] * rt[d][k]; });
+                rt[d][t] = s * Lt[tri(t, t) * ST];
+                yy += rt[d][t] * rt[d][t];
+                row[(YT + d * L::NTD + t) * ST] = rt[d][t];
+              });
+              // A_ii = y.y + cfm is constant during the sweep: keep y.y and 1 / A_ii per row
+              row[(BB + 3 + d) * ST] = yy;
+              row[(BB + 6 + d) * ST] = RS(1) / (yy + RS(P.cfm));
+            }
+          }
+        });
+      });
+    };
+    if constexpr (R == 0) rows_of(IC<-1>{}, IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{});
+    sfor<K0, NLOC>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      rows_of(IC<k>{}, IC<SP::L_GB[R][k]>{}, IC<SP::L_GE[R][k]>{}, IC<SP::L_CAND[R][k]>{}, IC<SP::L_LPT[R][k]>{});
+    });
+    __syncthreads();
+  }
+  TDSS_PHASE();  // 6
+  if (solve) {
+    RS* const zt = sp<RS>(smem, lane, L::ZT);
+    RS* const wo_s = sp<RS>(smem, lane, L::WO);
+    if constexpr (R == 0) {
+      // projected Gauss-Seidel in the reference's row order (solve_pgs, mb_constraint_solver.hpp:101-142,417-436):
+      // blocks normal | friction 1 | friction 2, contacts in enumeration order.  w = Y p stays in registers.
+      const RS* const Lt = sp<RS>(smem, lane, L::LT);
+      constexpr int NODM = L::NOD, NODMA = cmax(NODM, 1), NCA = cmax(SP::N_CAND, 1);
+      RS wt[NTDA], wo[TT][NODMA], x[NCA][3];
+#pragma unroll
+      for (int i = 0; i < NTDA; ++i) wt[i] = RS(0);
+#pragma unroll
+      for (int r = 0; r < TT; ++r)
+#pragma unroll
+        for (int i = 0; i < NODMA; ++i) wo[r][i] = RS(0);
+#pragma unroll
+      for (int g = 0; g < NCA; ++g) { x[g][0] = RS(0); x[g][1] = RS(0); x[g][2] = RS(0); }
+      const RS mu = RS(P.friction);
+      constexpr int YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);
+      for (int it = 0; it < P.pgs_iterations; ++it) {
+        sfor<0, 3>([&](auto Dc) {
+          constexpr int d = decltype(Dc)::value;
+          sfor<0, SP::N_CAND>([&](auto Gc) {
+            constexpr int g = decltype(Gc)::value;
+            constexpr int owner = SP::CAND_OWNER[g];
+            constexpr int nod = SP::N_OD[owner];
+            if ((team_active >> g) & 1ull) {
+              const RS* const row = sp<RS>(smem, lane, L::CON + g * L::CONW);
+              RS yo[cmax(nod, 1)], yt[NTDA];
+              RS yw = RS(0);
+              sfor<0, nod>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; yo[i] = row[(d * L::NOD + i) * ST]; yw += yo[i] * wo[owner][i]; });
+              sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; yt[t] = row[(YT + d * L::NTD + t) * ST]; yw += yt[t] * wt[t]; });
+              const RS x_old = x[g][d];
+              RS xn = (row[(BB + d) * ST] - yw + row[(BB + 3 + d) * ST] * x_old) * row[(BB + 6 + d) * ST];
+              if constexpr (d == 0) {
+                xn = xn < RS(0) ? RS(0) : xn;
+                xn = xn > RS(100000) ? RS(100000) : xn;
+              } else {
+                RS s = x[g][0];
+                s = s < RS(0) ? RS(0) : s;
+                const RS lim = mu * s;
+                xn = xn < -lim ? -lim : xn;
+                xn = xn > lim ? lim : xn;
+              }
+              x[g][d] = xn;
+              const RS dx = xn - x_old;
+              sfor<0, nod>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; wo[owner][i] += dx * yo[i]; });
+              sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; wt[t] += dx * yt[t]; });
+            }
+          });
+        });
+      }
+      // z_t = L_t^-T w_t ; publish z_t and every role's w_own
+      sfor_rev<0, NTD>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        RS s = wt[i];
+        sfor<i + 1, NTD>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Lt[tri(k, i) * ST] * wt[k]; });
+        wt[i] = s * Lt[tri(i, i) * ST];
+        zt[i * ST] = wt[i];
+      });
+#pragma unroll
+      for (int r = 0; r < TT; ++r)
+#pragma unroll
+        for (int i = 0; i < NODM; ++i) wo_s[(r * NODM + i) * ST] = wo[r][i];
+    }
+    __syncthreads();
+    TDSS_PHASE();  // 7
+    {   // z_k = L_k^-T (w_k - G z_t) ; qd -= z
+      RS w[NODA], z[NTDA];
+      sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; z[t] = zt[t * ST]; });
+      sfor<0, NOD>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        RS s = wo_s[(R * L::NOD + i) * ST];
+        sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; s -= Cm[i * NTDA + t] * z[t]; });
+        w[i] = s;
+      });
+      sfor_rev<0, NOD>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        RS s = w[i];
+        sfor<i + 1, NOD>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(k, i)] * w[k]; });
+        w[i] = s * Mkk[tri(i, i)];
+      });
+      sfor<NT, NLOC>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        constexpr int lj = SP::L_LDOF[R][k];
+        if constexpr (lj >= 0) qdv[k] = (float)(RS(qdv[k]) - w[lj - NTD]);
+      });
+      if constexpr (R == 0) {
+        if constexpr (FLOAT) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) bqd[k] = (float)(RS(bqd[k]) - z[k]);
+        }
+        sfor<0, NT>([&](auto Kc) {
+          constexpr int k = decltype(Kc)::value;
+          constexpr int lj = SP::L_LDOF[0][k];
+          if constexpr (lj >= 0) qdv[k] = (float)(RS(qdv[k]) - z[lj]);
+        });
+      }
+    }
+  } else { TDSS_PHASE(); }
+  TDSS_PHASE();  // 8
+
+  // ---- integrate_euler with qdd = 0 (integrator.hpp:10-133), reward / done, write back ---------------------------------------------------
+  RC up_z = RC(1);
+  if constexpr (R == 0 && FLOAT) {
+    const RC h = RC(0.5) * RC(P.dt);
+    RC qx = RC(bq[0]), qy = RC(bq[1]), qz = RC(bq[2]), qw = RC(bq[3]);
+    const RC w0 = RC(bqd[0]), w1 = RC(bqd[1]), w2 = RC(bqd[2]);
+    const RC dw = (-qx * w0 - qy * w1 - qz * w2) * h;
+    const RC dx = (qw * w0 + qz * w1 - qy * w2) * h;
+    const RC dy = (qw * w1 + qx * w2 - qz * w0) * h;
+    const RC dz = (qw * w2 + qy * w0 - qx * w1) * h;
+    qx += dx; qy += dy; qz += dz; qw += dw;
+    const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx /= len; qy /= len; qz /= len; qw /= len;
+    bq[0] = (float)qx; bq[1] = (float)qy; bq[2] = (float)qz; bq[3] = (float)qw;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bq[4 + k] = (float)(RC(bq[4 + k]) + RC(bqd[3 + k]) * RC(P.dt));
+    up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
+  }
+  sfor<K0, NLOC>([&](auto Kc) {
+    constexpr int k = decltype(Kc)::value;
+    if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED)) qv[k] = (float)(RC(qv[k]) + RC(qdv[k]) * RC(P.dt));
+  });
+  if constexpr (R == 0) {
+    bool done = false;
+    if (E.reward_kind == 1) {   // laikago_environment2.h:130-171 (fixed-base emulation; q0..5 are trunk coordinates)
+      constexpr int k0 = k_of_q<SP, 0>(0), k2 = k_of_q<SP, 0>(2), k3 = k_of_q<SP, 0>(3), k4 = k_of_q<SP, 0>(4);
+      if constexpr (!FLOAT && k0 >= 0 && k2 >= 0 && k3 >= 0 && k4 >= 0) {
+        const float x = qv[k0], z = qv[k2];
+        const float upz = cosf(qv[k3]) * cosf(qv[k4]);
+        done = (upz < 0.6f) || (z < 0.2f);
+        if (io.reward && live) io.reward[e] = done ? 0.f : x;
+      }
+    } else if (E.reward_kind == 2) {
+      if constexpr (FLOAT) {
+        const float x = bq[4], z = bq[6];
+        done = ((float)up_z < 0.6f) || (z < 0.2f);
+        if (io.reward && live) io.reward[e] = done ? 0.f : x;
+      }
+    }
+    if (io.done && E.reward_kind && live) io.done[e] = done ? 1.f : 0.f;
+    flg[(2 * TT) * ST] = done ? 1u : 0u;
+  }
+  __syncthreads();
+  const bool reset = (flg[(2 * TT) * ST] != 0u) && E.auto_reset;
+  if (live) {
+    sfor<K0, NLOC>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED)) {
+        io.q_out[(size_t)CI(SP::L_QIDX[R][k]) * ns + e] = reset ? E.reset_q[CI(SP::L_QIDX[R][k])] : qv[k];
+        io.qd_out[(size_t)CI(SP::L_QDIDX[R][k]) * ns + e] = reset ? 0.f : qdv[k];
+      }
+    });
+    if constexpr (R == 0 && FLOAT) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) io.q_out[(size_t)k * ns + e] = reset ? E.reset_q[k] : bq[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) io.qd_out[(size_t)k * ns + e] = reset ? 0.f : bqd[k];
+    }
+  }
+  TDSS_PHASE();  // 9
+#undef TDSS_PHASE
+}
+
+template <class SP, typename RA, typename RC, typename RS>
+__global__ void __launch_bounds__(32 * TDS_TEAM_T, 1)
+tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode,
+                     const int use_pd) {
+  extern __shared__ __align__(16) char smem_raw[];
+  const int role = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, known uniform to the compiler
+  switch (role) {
+    case 0: role_body<SP, 0, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
+    case 1: role_body<SP, 1, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
+    case 2: role_body<SP, 2, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
+    default: role_body<SP, 3, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
+  }
+}
+
+template <class SP> struct SpecHost {
+  static bool matches(const DevModel* D, const EnvParams* E) {
+    if (D->n_links != SP::N_LINKS || D->n_q != SP::N_Q || D->n_qd != SP::N_QD || D->floating != SP::FLOATING) return false;
+    if (E->n_act != 0) {
+      if (E->n_act != SP::N_ACT) return false;
+      for (int a = 0; a < SP::N_ACT; ++a) if (E->act_link[a] != SP::ACT_LINK[a]) return false;
+    }
+    if (E->reward_kind == 1 && (SP::FLOATING || k_of_q<SP, 0>(0) < 0 || k_of_q<SP, 0>(2) < 0 || k_of_q<SP, 0>(3) < 0 || k_of_q<SP, 0>(4) < 0)) return false;
+    if (E->reward_kind == 2 && !SP::FLOATING) return false;
+    return true;
+  }
+};
+
+}  // namespace tdss
+
+static const double k_spec_laikago_model[] = {
+#include "generated/laikago_model.inc"
+};
+
+// Does the ahead-of-time compiled kernel cover this simulator?  (same flat model, bit for bit, and same actuator map)
+extern "C" int tds_spec_match(const double* model, int n_model, const DevModel* D, const EnvParams* E) {
+  const int n = (int)(sizeof(k_spec_laikago_model) / sizeof(double));
+  if (n_model < n) return 0;
+  // visuals (tail of the flat model) do not enter the step; everything before them must agree
+  const int n_dyn = TDSM_HEADER + TDSM_BASE + SpecLaikago::N_LINKS * TDSM_LINK + SpecLaikago::N_GEOMS * TDSM_GEOM;
+  if (n_dyn > n || n_dyn > n_model) return 0;
+  for (int i = 0; i < n_dyn; ++i) {
+    if (i == TDSM_H_NVIS) continue;
+    if (!(model[i] == k_spec_laikago_model[i])) return 0;
+  }
+  return tdss::SpecHost<SpecLaikago>::matches(D, E) ? 1 : 0;
+}
+
+extern "C" size_t tds_spec_smem_bytes(int precision) {
+  using namespace tdss;
+  if (precision == 0) return (size_t)Lay<SpecLaikago, float, double, float>::TOTAL * 32 * 4;
+  if (precision == 1) return (size_t)Lay<SpecLaikago, double, double, double>::TOTAL * 32 * 4;
+  return (size_t)Lay<SpecLaikago, float, float, float>::TOTAL * 32 * 4;
+}
+
+extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
+                                    cudaStream_t stream) {
+  using namespace tdss;
+  const int tiles = (io->n + 31) / 32;
+  const size_t smem = tds_spec_smem_bytes(precision);
+  cudaError_t err = cudaSuccess;
+#define TDSS_LAUNCH(RA, RC, RS)                                                                         \
+  do {                                                                                                  \
+    auto k = tds_step_spec_kernel<SpecLaikago, RA, RC, RS>;                                             \
+    static bool attr_set = false;                                                                       \
+    if (!attr_set && smem > 48 * 1024) {                                                                \
+      err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      if (err == cudaSuccess) attr_set = true;                                                          \
+    }                                                                                                   \
+    if (err == cudaSuccess) {                                                                           \
+      k<<<tiles, 32 * TDS_TEAM_T, smem, stream>>>(*P, *E, *io, mode, use_pd);                           \
+      err = cudaGetLastError();                                                                         \
+    }                                                                                                   \
+  } while (0)
+  if (precision == 0) TDSS_LAUNCH(float, double, float);
+  else if (precision == 1) TDSS_LAUNCH(double, double, double);
+  else TDSS_LAUNCH(float, float, float);
+#undef TDSS_LAUNCH
+  return (int)err;
+}

@@ -77,6 +77,10 @@ class BatchSim:
             assert rq.size == self.n_q
         self._check(self._L.tds_b200_set_auto_reset(self._h, int(enable), _dp(rq)), "set_auto_reset")
 
+    def kernel_name(self):
+        """Step kernel launched by the last step call (after the library's selection / fallbacks)."""
+        return self._L.tds_b200_kernel_name(self._h).decode()
+
     def set_precision(self, precision):
         self._check(self._L.tds_b200_set_precision(self._h, precision), "set_precision")
         self.precision = precision
