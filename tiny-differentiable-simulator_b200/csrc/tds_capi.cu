@@ -372,7 +372,8 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(p) <= (size_t)s->max_smem_optin)) kern = 3;
   if (kern == 4) {
     s->kernel = kern;
-    int rcs = tds_launch_step_spec(&s->P, &s->E, &io, mode, use_pd, p, (cudaStream_t)stream);
+    static const int solo = getenv("TDS_B200_DEBUG_SOLO") ? 256 : 0;   // profiling aid, see tds_steps.cu
+    int rcs = tds_launch_step_spec(&s->P, &s->E, &io, mode | solo, use_pd, p, (cudaStream_t)stream);
     if (rcs) set_err(std::string("specialised step launch: ") + cudaGetErrorString((cudaError_t)rcs));
     return rcs;
   }

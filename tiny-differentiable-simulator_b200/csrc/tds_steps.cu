@@ -939,10 +939,12 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
 
 template <class SP, typename RA, typename RC, typename RS>
 __global__ void __launch_bounds__(32 * TDS_TEAM_T, 1)
-tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode,
+tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode_flags,
                      const int use_pd) {
   extern __shared__ __align__(16) char smem_raw[];
   const int role = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, known uniform to the compiler
+  if ((mode_flags & 256) && role != 0) return;   // profiling aid (TDS_B200_DEBUG_SOLO): role 0 alone, results are garbage
+  const int mode = mode_flags & 255;
   switch (role) {
     case 0: role_body<SP, 0, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
     case 1: role_body<SP, 1, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
