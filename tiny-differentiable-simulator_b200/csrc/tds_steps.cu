@@ -3,7 +3,12 @@
 // (generated/spec_*.h, written by gen_spec.cpp from the flat model).  Joint types, transforms, inertias, collision
 // shapes, the decomposition and every index are constant expressions; all loops over links, dofs and contacts are
 // unrolled.  What that buys over the table-driven kernel:
-//   * straight-line code per role (sequential instruction fetch, no dead branches for absent joint / shape types);
+//   * straight-line code (no dead branches for absent joint / shape types).  Cold straight-line code is paid at the
+//     SM's instruction-fetch rate from L2 (scripts/ifetch_probe.cu: ~4 cycles / instruction for one stream,
+//     ~3.5 for four warps on the SAME stream, 10-12 when four warps stream four different copies), so the four
+//     subtrees must be one structural class (Cls below; gen_spec.cpp checks it) and run ONE instruction stream:
+//     what differs between them (transforms, axes, inertias, shapes, indices) is read from a per-role table
+//     in constant memory; only role 0 additionally runs the trunk code;
 //   * per-link state of the subtrees (S, v, c, U, 1/D, u), the mass-matrix blocks M_kk, C -> G and their factors
 //     live in registers; shared memory only carries what crosses roles (attachment transforms / accelerations,
 //     trunk records, attachment accumulators, partial Schur complements, the trunk factor, contact rows);
@@ -52,6 +57,106 @@ template <class SP, int R> __host__ __device__ constexpr int k_of_q(int q_idx) {
   return -1;
 }
 
+// Structural class of the four subtrees.  Positions k in [N_TRUNK, N_LOC) of every role's list must agree on
+// topology and joint kind; where the roles differ only numerically the class takes the general form
+// (joint type -> revolute about a run-time axis, transform -> general) and the numbers come from LegTab.
+template <class SP> struct Cls {
+  static constexpr int NT = SP::N_TRUNK, NLOC = SP::N_LOC[0], KO = NLOC - NT > 0 ? NLOC - NT : 1;
+  static constexpr int STRUCT = TDS_LF_FIXED | TDS_LF_REVOLUTE | TDS_LF_PRISMATIC | TDS_TF_PARENT_ADJ | TDS_TF_CHILD_ADJ | TDS_TF_PARENT_TRUNK;
+  __host__ __device__ static constexpr bool zero3(const double* v) { return v[0] == 0.0 && v[1] == 0.0 && v[2] == 0.0; }
+  __host__ __device__ static constexpr int flags(int k) {
+    int f = SP::L_FLAGS[0][k];
+    for (int r = 1; r < SP::T; ++r) if (!(SP::L_FLAGS[r][k] & TDS_LF_XT_IDENT)) f &= ~TDS_LF_XT_IDENT;
+    return f;
+  }
+  __host__ __device__ static constexpr int jtype(int k) {
+    int j = SP::L_JTYPE[0][k];
+    for (int r = 1; r < SP::T; ++r) if (SP::L_JTYPE[r][k] != j) j = TDSJ_REVOLUTE_AXIS;
+    return j;
+  }
+  __host__ __device__ static constexpr bool massless(int k) {
+    for (int r = 0; r < SP::T; ++r) {
+      const double* b = SP::L_RBIC[r][k];
+      if (!(b[0] == 0.0 && b[4] == 0.0 && b[5] == 0.0 && b[6] == 0.0 && b[7] == 0.0 && b[8] == 0.0 && b[9] == 0.0)) return false;
+    }
+    return true;
+  }
+  __host__ __device__ static constexpr bool t_zero(int k) {
+    for (int r = 0; r < SP::T; ++r) if (!zero3(&SP::L_XT[r][k][9])) return false;
+    return true;
+  }
+  __host__ __device__ static constexpr bool axis_same(int k) {
+    for (int r = 1; r < SP::T; ++r)
+      for (int j = 0; j < 3; ++j) if (SP::L_AXIS[r][k][j] != SP::L_AXIS[0][k][j]) return false;
+    return true;
+  }
+  __host__ __device__ static constexpr bool has_sd(int k, int j) {
+    for (int r = 0; r < SP::T; ++r) if (SP::L_SD[r][k][j] != 0.0) return true;
+    return false;
+  }
+  __host__ __device__ static constexpr int geom_pts(int g) { return SP::G_TYPE[g] == TDSG_SPHERE ? 1 : (SP::G_TYPE[g] == TDSG_CAPSULE ? 2 : 0); }
+  // geoms / candidate points of the subtree, numbered locally in link order (role 0 is the template)
+  __host__ __device__ static constexpr int gb_local(int k) { int c = 0; for (int j = NT; j < k; ++j) c += SP::L_GE[0][j] - SP::L_GB[0][j]; return c; }
+  __host__ __device__ static constexpr int n_geoms_own() { return gb_local(NLOC); }
+  __host__ __device__ static constexpr int gtype_local(int k, int i) { return SP::G_TYPE[SP::L_GB[0][k] + i]; }
+  __host__ __device__ static constexpr int pt_local(int k, int i) {   // first point of geom i of link k
+    int c = 0;
+    for (int j = NT; j <= k; ++j)
+      for (int g = SP::L_GB[0][j]; g < (j < k ? SP::L_GE[0][j] : SP::L_GB[0][j] + i); ++g) c += geom_pts(g);
+    return c;
+  }
+  __host__ __device__ static constexpr int n_pts_own() { return pt_local(NLOC - 1, SP::L_GE[0][NLOC - 1] - SP::L_GB[0][NLOC - 1]); }
+  __host__ __device__ static constexpr int n_pts_trunk() { return SP::N_PTS[0] - n_pts_own(); }
+  __host__ __device__ static constexpr bool uniform() {
+    if (NLOC <= NT) return false;
+    for (int r = 1; r < SP::T; ++r) {
+      if (SP::N_LOC[r] != NLOC || SP::N_OD[r] != SP::N_OD[0] || SP::N_PTS[r] != n_pts_own()) return false;
+      for (int k = NT; k < NLOC; ++k) {
+        if ((SP::L_FLAGS[r][k] & STRUCT) != (SP::L_FLAGS[0][k] & STRUCT)) return false;
+        if (SP::L_LPAR[r][k] != SP::L_LPAR[0][k] || SP::L_LDOF[r][k] != SP::L_LDOF[0][k] || SP::L_ACC[r][k] != SP::L_ACC[0][k] ||
+            SP::L_PAR[r][k] != SP::L_PAR[0][k] || SP::L_XW[r][k] != SP::L_XW[0][k]) return false;
+        if ((SP::L_ACT[r][k] >= 0) != (SP::L_ACT[0][k] >= 0)) return false;
+        if (SP::L_JTYPE[r][k] != SP::L_JTYPE[0][k] && !((SP::L_FLAGS[r][k] & TDS_LF_REVOLUTE) && (SP::L_FLAGS[0][k] & TDS_LF_REVOLUTE))) return false;
+        if (SP::L_GE[r][k] - SP::L_GB[r][k] != SP::L_GE[0][k] - SP::L_GB[0][k]) return false;
+        for (int i = 0; i < SP::L_GE[0][k] - SP::L_GB[0][k]; ++i)
+          if (SP::G_TYPE[SP::L_GB[r][k] + i] != SP::G_TYPE[SP::L_GB[0][k] + i]) return false;
+      }
+    }
+    return true;
+  }
+};
+
+// What differs between the subtrees: one record per role in constant memory (uniform index -> broadcast loads).
+template <class SP> struct LegTab {
+  static constexpr int KO = Cls<SP>::KO, NG = Cls<SP>::n_geoms_own() > 0 ? Cls<SP>::n_geoms_own() : 1,
+                       NP = Cls<SP>::n_pts_own() > 0 ? Cls<SP>::n_pts_own() : 1;
+  double xt[KO][12], axis[KO][3], rbic[KO][10], sd[KO][2];
+  double gt[NG][3], ghalf[NG][3], grad[NG];
+  int qidx[KO], qdidx[KO], act[KO], link[KO];
+  int cand[NP];   // global candidate index of the subtree's p-th point
+};
+template <class SP> constexpr LegTab<SP> make_leg(int r) {
+  using C = Cls<SP>;
+  LegTab<SP> t{};
+  for (int k = C::NT; k < C::NLOC; ++k) {
+    const int o = k - C::NT;
+    for (int j = 0; j < 12; ++j) t.xt[o][j] = SP::L_XT[r][k][j];
+    for (int j = 0; j < 3; ++j) t.axis[o][j] = SP::L_AXIS[r][k][j];
+    for (int j = 0; j < 10; ++j) t.rbic[o][j] = SP::L_RBIC[r][k][j];
+    for (int j = 0; j < 2; ++j) t.sd[o][j] = SP::L_SD[r][k][j];
+    t.qidx[o] = SP::L_QIDX[r][k]; t.qdidx[o] = SP::L_QDIDX[r][k]; t.act[o] = SP::L_ACT[r][k]; t.link[o] = SP::L_LINK[r][k];
+    int p = 0;
+    for (int g = SP::L_GB[r][k]; g < SP::L_GE[r][k]; ++g) {
+      const int gl = C::gb_local(k) + (g - SP::L_GB[r][k]);
+      for (int j = 0; j < 3; ++j) { t.gt[gl][j] = SP::G_T[3 * g + j]; t.ghalf[gl][j] = SP::G_HALF[3 * g + j]; }
+      t.grad[gl] = SP::G_RADIUS[g];
+      for (int j = 0; j < C::geom_pts(g); ++j) { t.cand[C::pt_local(k, g - SP::L_GB[r][k]) + j] = SP::L_CAND[r][k] + p; ++p; }
+    }
+  }
+  return t;
+}
+template <class SP> __device__ const LegTab<SP>& leg_tab(int role);
+
 // shared-memory layout of one tile, 4-byte words per environment
 template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int RAW = sizeof(RA) / 4, RCW = sizeof(RC) / 4, RSW = sizeof(RS) / 4;
@@ -93,22 +198,27 @@ template <typename T> TDS_D Abi<T> abi_nz() {
 template <typename T> TDS_D Sv<T> sv_nz() { Sv<T> s; const T z = negz<T>(); s.top = v3<T>(z, z, z); s.bot = s.top; return s; }
 template <typename T> TDS_D Rbi<T> rbi_nz() { Rbi<T> r; const T z = negz<T>(); r.m = z; r.h = v3<T>(z, z, z); r.I = {z, z, z, z, z, z}; return r; }
 
-template <class SP, int R, typename RA, typename RC, typename RS>
-TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, const StepIO& io, const int mode, const int use_pd) {
+template <class SP, typename RA, typename RC, typename RS>
+TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, const StepIO& io, const int mode, const int use_pd,
+                     const int role) {
   using L = Lay<SP, RA, RC, RS>;
+  using C = Cls<SP>;
+  static_assert(C::uniform(), "the subtrees of the model are not one structural class (use the table-driven kernel)");
   constexpr int RAW = L::RAW, RCW = L::RCW;
-  constexpr int NT = SP::N_TRUNK, NTD = SP::N_TD, NLOC = SP::N_LOC[R], K0 = (R == 0) ? 0 : NT;
-  constexpr int NOD = SP::N_OD[R], NODA = cmax(NOD, 1), NTDA = cmax(NTD, 1), NTRI = L::NTRI, NTRIA = cmax(NTRI, 1);
-  constexpr int NPT = SP::N_PTS[R], NPTA = cmax(NPT, 1), NACCA = cmax(SP::N_ACC, 1), NXLA = cmax(SP::N_XW_LANE, 1);
+  constexpr int NT = SP::N_TRUNK, NTD = SP::N_TD, NLOC = SP::N_LOC[0];
+  constexpr int NOD = SP::N_OD[0], NODA = cmax(NOD, 1), NTDA = cmax(NTD, 1), NTRI = L::NTRI, NTRIA = cmax(NTRI, 1);
+  constexpr int NPO = C::n_pts_own(), NPOA = cmax(NPO, 1), NPTR = C::n_pts_trunk(), NPTRA = cmax(NPTR, 1);
+  constexpr int NACCA = cmax(SP::N_ACC, 1), NXLA = cmax(SP::N_XW_LANE, 1), NATT = cmax(SP::N_ATT, 1);
   constexpr bool FLOAT = SP::FLOATING != 0;
   const int lane = threadIdx.x & 31;
   const int env = blockIdx.x * 32 + lane;
   const bool live = env < io.n;
   const int e = live ? env : io.n - 1;
   const int ns = io.n_stride;
-  char* const priv = smem + (size_t)(L::SHARED + R * L::PRIV) * ST * 4;
+  const LegTab<SP>& LG = leg_tab<SP>(role);
+  char* const priv = smem + (size_t)(L::SHARED + role * L::PRIV) * ST * 4;
   int phase_id = 0;
-#define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + R) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
+#define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
   TDSS_PHASE();
   auto xw_rc = [&](int slot) { return sp<RC>(smem, lane, L::XW + slot * L::XWW); };                  // R[9], p[3]
   auto xw_ra = [&](int slot) { return sp<RA>(smem, lane, L::XW + slot * L::XWW + 12 * RCW); };       // v[6], a[6]
@@ -122,25 +232,35 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // ---- load the coordinates of this role's joints; PD torques (locomotion_contact_simulation.h:168-258) -------------------
   float qv[SP::KMAX], qdv[SP::KMAX], tauv[SP::KMAX];   // joint coordinate / velocity / torque of local link k
   float bq[7], bqd[6];                                 // floating base (role 0)
-  sfor<K0, NLOC>([&](auto Kc) {
+  sfor<NT, NLOC>([&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
-    if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED)) {
-      qv[k] = io.q_in[(size_t)CI(SP::L_QIDX[R][k]) * ns + e];
-      qdv[k] = io.qd_in[(size_t)CI(SP::L_QDIDX[R][k]) * ns + e];
+    if constexpr (!(C::flags(k) & TDS_LF_FIXED)) {
+      qv[k] = io.q_in[(size_t)LG.qidx[k - NT] * ns + e];
+      qdv[k] = io.qd_in[(size_t)LG.qdidx[k - NT] * ns + e];
       tauv[k] = 0.f;
     }
   });
-  if constexpr (FLOAT && R == 0) {
+  if (role == 0) {
+    sfor<0, NT>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) {
+        qv[k] = io.q_in[(size_t)CI(SP::L_QIDX[0][k]) * ns + e];
+        qdv[k] = io.qd_in[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e];
+        tauv[k] = 0.f;
+      }
+    });
+    if constexpr (FLOAT) {
 #pragma unroll
-    for (int k = 0; k < 7; ++k) bq[k] = io.q_in[(size_t)k * ns + e];
+      for (int k = 0; k < 7; ++k) bq[k] = io.q_in[(size_t)k * ns + e];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) bqd[k] = io.qd_in[(size_t)k * ns + e];
+      for (int k = 0; k < 6; ++k) bqd[k] = io.qd_in[(size_t)k * ns + e];
+    }
   }
   if (use_pd) {
-    sfor<K0, NLOC>([&](auto Kc) {
+    sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
-      constexpr int a = SP::L_ACT[R][k];
-      if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED) && a >= 0) {
+      if constexpr (!(C::flags(k) & TDS_LF_FIXED) && SP::L_ACT[0][k] >= 0) {
+        const int a = LG.act[k - NT];
         float act = io.tau_in[(size_t)a * ns + e];
         act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
         const float q_des = E.initial_poses[a] + act;
@@ -148,22 +268,52 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
         tauv[k] = fminf(fmaxf(f, -E.max_force), E.max_force);
       }
     });
+    if (role == 0) {
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        constexpr int a = SP::L_ACT[0][k];
+        if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED) && a >= 0) {
+          float act = io.tau_in[(size_t)a * ns + e];
+          act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
+          const float q_des = E.initial_poses[a] + act;
+          const float f = E.kp * (q_des - qv[k]) + E.kd * (0.f - qdv[k]);
+          tauv[k] = fminf(fmaxf(f, -E.max_force), E.max_force);
+        }
+      });
+    }
   } else if (io.tau_in) {
-    sfor<K0, NLOC>([&](auto Kc) {
+    constexpr int off = FLOAT ? 6 : 0;
+    sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
-      constexpr int off = FLOAT ? 6 : 0;
-      if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED) && SP::L_QDIDX[R][k] >= off)
-        tauv[k] = io.tau_in[(size_t)CI(SP::L_QDIDX[R][k] - off) * ns + e];
+      if constexpr (!(C::flags(k) & TDS_LF_FIXED) && SP::L_QDIDX[0][k] >= off)
+        tauv[k] = io.tau_in[(size_t)(LG.qdidx[k - NT] - off) * ns + e];
     });
+    if (role == 0) {
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED) && SP::L_QDIDX[0][k] >= off)
+          tauv[k] = io.tau_in[(size_t)CI(SP::L_QDIDX[0][k] - off) * ns + e];
+      });
+    }
   }
   const bool want_contacts = (mode == MODE_FULL) && SP::HAS_PLANE;
   const V3<RC> pn = v3<RC>(RC(CD(SP::PLANE_N[0])), RC(CD(SP::PLANE_N[1])), RC(CD(SP::PLANE_N[2])));
   TDSS_PHASE();  // 1
 
-  // ---- contact candidates of this role (contact_point.hpp:112-116) -----------------------------------------------------------
+  // ---- contact candidates (contact_point.hpp:112-116): subtree points (every role) and trunk / base points (role 0) ----------
   unsigned long long my_active = 0ull;   // bit = global candidate index
-  V3<RC> cpos[NPTA]; RC cdist[NPTA];
-  auto emit_geoms = [&](auto Gb, auto Ge, auto Cand0, auto Lpt0, const M3<RC>& Rw, const V3<RC>& pw, const RC plane_off) {
+  V3<RC> cpos[NPOA]; RC cdist[NPOA];     // subtree points, local numbering
+  V3<RC> tpos[NPTRA]; RC tdist[NPTRA];   // role 0: points on base / trunk geoms, numbered as in CAND_LPT
+  RC plane_off; V3<RC> O;
+  auto emit_point = [&](const V3<RC>& pos, const RC rad, const int cand, V3<RC>& out_pos, RC& out_dist) {
+    const RC dist = dot(pos, pn) + plane_off - rad;
+    if (io.contact_dist && live) io.contact_dist[(size_t)cand * ns + e] = (float)dist;
+    out_pos = pos - pn * rad;                                // world_point_on_b, relative to O
+    out_dist = dist;
+    if (dist < RC(0)) my_active |= 1ull << cand;
+  };
+  // geoms [gb, ge) of a trunk link / the base (compile-time shapes)
+  auto emit_trunk_geoms = [&](auto Gb, auto Ge, auto Cand0, auto Lpt0, const M3<RC>& Rw, const V3<RC>& pw) {
     constexpr int gb = decltype(Gb)::value, ge = decltype(Ge)::value;
     sfor<gb, ge>([&](auto Gc) {
       constexpr int g = decltype(Gc)::value;
@@ -172,59 +322,83 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
         constexpr int cand0 = decltype(Cand0)::value + pts_before<SP>(gb, g), lpt0 = decltype(Lpt0)::value + pts_before<SP>(gb, g);
         const V3<RC> c = pw + mul(Rw, v3<RC>(RC(CD(SP::G_T[3 * g])), RC(CD(SP::G_T[3 * g + 1])), RC(CD(SP::G_T[3 * g + 2]))));
         const RC rad = RC(CD(SP::G_RADIUS[g]));
-        V3<RC> half = v3<RC>(RC(0), RC(0), RC(0));
-        if constexpr (ty == TDSG_CAPSULE) half = mul(Rw, v3<RC>(RC(CD(SP::G_HALF[3 * g])), RC(CD(SP::G_HALF[3 * g + 1])), RC(CD(SP::G_HALF[3 * g + 2]))));
-        sfor<0, (ty == TDSG_CAPSULE ? 2 : 1)>([&](auto Jc) {
-          constexpr int j = decltype(Jc)::value;
-          const V3<RC> pos = (ty == TDSG_CAPSULE) ? (j == 0 ? c + half : c - half) : c;
-          const RC dist = dot(pos, pn) + plane_off - rad;
-          if (io.contact_dist && live) io.contact_dist[(size_t)(cand0 + j) * ns + e] = (float)dist;
-          cpos[lpt0 + j] = pos - pn * rad;                       // world_point_on_b, relative to O
-          cdist[lpt0 + j] = dist;
-          if (dist < RC(0)) my_active |= 1ull << (cand0 + j);
-        });
+        if constexpr (ty == TDSG_CAPSULE) {
+          const V3<RC> half = mul(Rw, v3<RC>(RC(CD(SP::G_HALF[3 * g])), RC(CD(SP::G_HALF[3 * g + 1])), RC(CD(SP::G_HALF[3 * g + 2]))));
+          emit_point(c + half, rad, cand0, tpos[lpt0], tdist[lpt0]);
+          emit_point(c - half, rad, cand0 + 1, tpos[lpt0 + 1], tdist[lpt0 + 1]);
+        } else emit_point(c, rad, cand0, tpos[lpt0], tdist[lpt0]);
+      }
+    });
+  };
+  // geoms of subtree link k (shape types of the class, numbers from the role's table)
+  auto emit_own_geoms = [&](auto Kc, const M3<RC>& Rw, const V3<RC>& pw) {
+    constexpr int k = decltype(Kc)::value;
+    sfor<0, SP::L_GE[0][k] - SP::L_GB[0][k]>([&](auto Ic_) {
+      constexpr int i = decltype(Ic_)::value;
+      constexpr int ty = C::gtype_local(k, i), gl = C::gb_local(k) + i, p0 = C::pt_local(k, i);
+      if constexpr (ty == TDSG_SPHERE || ty == TDSG_CAPSULE) {
+        const V3<RC> c = pw + mul(Rw, v3<RC>(RC(LG.gt[gl][0]), RC(LG.gt[gl][1]), RC(LG.gt[gl][2])));
+        const RC rad = RC(LG.grad[gl]);
+        if constexpr (ty == TDSG_CAPSULE) {
+          const V3<RC> half = mul(Rw, v3<RC>(RC(LG.ghalf[gl][0]), RC(LG.ghalf[gl][1]), RC(LG.ghalf[gl][2])));
+          emit_point(c + half, rad, LG.cand[p0], cpos[p0], cdist[p0]);
+          emit_point(c - half, rad, LG.cand[p0 + 1], cpos[p0 + 1], cdist[p0 + 1]);
+        } else emit_point(c, rad, LG.cand[p0], cpos[p0], cdist[p0]);
       }
     });
   };
 
   // ---- pass 1 on one link (kinematics.hpp:18-148, link.hpp:229-336) in the common frame ---------------------------------------
+  // Trunk links (k < N_TRUNK, role 0): every constant is an immediate.  Subtree links: structure from Cls, numbers from LG.
   M3<RC> R_prev; V3<RC> p_prev; Sv<RA> v_prev;                       // carried along chains
-  Sv<RC> Sreg[SP::KMAX]; Sv<RA> vreg[SP::KMAX];                      // own links: S, then v / c / a
-  M3<RC> xwR[NXLA]; V3<RC> xwp[NXLA]; Sv<RA> xwa[NXLA];              // own links with non-adjacent children
-  RC plane_off; V3<RC> O;
+  Sv<RC> Sreg[SP::KMAX]; Sv<RA> vreg[SP::KMAX];                      // subtree links: S, then v / c / a
+  M3<RC> xwR[NXLA]; V3<RC> xwp[NXLA]; Sv<RA> xwa[NXLA];              // subtree links with non-adjacent children
   auto pass1 = [&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
-    constexpr int fl = SP::L_FLAGS[R][k], lpar = SP::L_LPAR[R][k], jt = SP::L_JTYPE[R][k];
+    constexpr bool TR = k < NT;
+    constexpr int ko = TR ? 0 : k - NT;
+    constexpr int fl = TR ? SP::L_FLAGS[0][k] : C::flags(k), lpar = SP::L_LPAR[0][k], jt = TR ? SP::L_JTYPE[0][k] : C::jtype(k);
     M3<RC> Rp; V3<RC> pp; Sv<RA> vp;
     if constexpr ((fl & TDS_TF_PARENT_ADJ) != 0) { Rp = R_prev; pp = p_prev; vp = v_prev; }
     else if constexpr (lpar < NT) {      // base (slot 0) or a published trunk link
-      constexpr int slot = lpar < 0 ? 0 : SP::L_XW[R][lpar < 0 ? 0 : lpar] + 1;
+      constexpr int slot = lpar < 0 ? 0 : SP::L_XW[0][lpar < 0 ? 0 : lpar] + 1;
       static_assert(lpar < 0 || slot >= 1, "parent transform not published");
       Rp = ld9<RC>(xw_rc(slot), ST); pp = ld3<RC>(xw_rc(slot) + 9 * ST, ST); vp = ld6<RA>(xw_ra(slot), ST);
-    } else {                             // own branch parent
-      constexpr int xs = SP::L_XW[R][lpar];
+    } else {                             // subtree branch parent
+      constexpr int xs = SP::L_XW[0][lpar];
       Rp = xwR[xs]; pp = xwp[xs]; vp = vreg[lpar];
     }
-    constexpr double tx = SP::L_XT[R][k][9], ty = SP::L_XT[R][k][10], tz = SP::L_XT[R][k][11];
     V3<RC> pi = pp;
-    if constexpr (tx != 0.0 || ty != 0.0 || tz != 0.0) pi = pp + mul(Rp, v3<RC>(RC(tx), RC(ty), RC(tz)));
+    if constexpr (TR) {
+      constexpr double tx = SP::L_XT[0][k][9], ty = SP::L_XT[0][k][10], tz = SP::L_XT[0][k][11];
+      if constexpr (tx != 0.0 || ty != 0.0 || tz != 0.0) pi = pp + mul(Rp, v3<RC>(RC(tx), RC(ty), RC(tz)));
+    } else if constexpr (!C::t_zero(k)) pi = pp + mul(Rp, v3<RC>(RC(LG.xt[ko][9]), RC(LG.xt[ko][10]), RC(LG.xt[ko][11])));
     M3<RC> Ri = Rp;
     if constexpr (!(fl & TDS_LF_XT_IDENT)) {
       M3<RC> r;
-      r.xx = RC(CD(SP::L_XT[R][k][0])); r.xy = RC(CD(SP::L_XT[R][k][1])); r.xz = RC(CD(SP::L_XT[R][k][2]));
-      r.yx = RC(CD(SP::L_XT[R][k][3])); r.yy = RC(CD(SP::L_XT[R][k][4])); r.yz = RC(CD(SP::L_XT[R][k][5]));
-      r.zx = RC(CD(SP::L_XT[R][k][6])); r.zy = RC(CD(SP::L_XT[R][k][7])); r.zz = RC(CD(SP::L_XT[R][k][8]));
+      if constexpr (TR) {
+        r.xx = RC(CD(SP::L_XT[0][k][0])); r.xy = RC(CD(SP::L_XT[0][k][1])); r.xz = RC(CD(SP::L_XT[0][k][2]));
+        r.yx = RC(CD(SP::L_XT[0][k][3])); r.yy = RC(CD(SP::L_XT[0][k][4])); r.yz = RC(CD(SP::L_XT[0][k][5]));
+        r.zx = RC(CD(SP::L_XT[0][k][6])); r.zy = RC(CD(SP::L_XT[0][k][7])); r.zz = RC(CD(SP::L_XT[0][k][8]));
+      } else {
+        r.xx = RC(LG.xt[ko][0]); r.xy = RC(LG.xt[ko][1]); r.xz = RC(LG.xt[ko][2]);
+        r.yx = RC(LG.xt[ko][3]); r.yy = RC(LG.xt[ko][4]); r.yz = RC(LG.xt[ko][5]);
+        r.zx = RC(LG.xt[ko][6]); r.zy = RC(LG.xt[ko][7]); r.zz = RC(LG.xt[ko][8]);
+      }
       Ri = mul(Rp, r);
     }
     Sv<RC> S; S.top = v3<RC>(RC(0), RC(0), RC(0)); S.bot = S.top;
     if constexpr (!(fl & TDS_LF_FIXED)) {
       const RC qi = RC(qv[k]);
-      constexpr double ax = SP::L_AXIS[R][k][0], ay = SP::L_AXIS[R][k][1], az = SP::L_AXIS[R][k][2];
+      constexpr bool axis_ct = TR || C::axis_same(k);        // axis known at compile time
+      constexpr double ax = SP::L_AXIS[0][k][0], ay = SP::L_AXIS[0][k][1], az = SP::L_AXIS[0][k][2];
+      V3<RC> axv;
+      if constexpr (axis_ct) axv = v3<RC>(RC(ax), RC(ay), RC(az)); else axv = v3<RC>(RC(LG.axis[ko][0]), RC(LG.axis[ko][1]), RC(LG.axis[ko][2]));
       auto rot_axis = [&]() -> V3<RC> {    // Ri * axis, unit axes folded to a column
-        if constexpr (ax == 1.0 && ay == 0.0 && az == 0.0) return col_x(Ri);
-        else if constexpr (ax == 0.0 && ay == 1.0 && az == 0.0) return col_y(Ri);
-        else if constexpr (ax == 0.0 && ay == 0.0 && az == 1.0) return col_z(Ri);
-        else return mul(Ri, v3<RC>(RC(ax), RC(ay), RC(az)));
+        if constexpr (axis_ct && ax == 1.0 && ay == 0.0 && az == 0.0) return col_x(Ri);
+        else if constexpr (axis_ct && ax == 0.0 && ay == 1.0 && az == 0.0) return col_y(Ri);
+        else if constexpr (axis_ct && ax == 0.0 && ay == 0.0 && az == 1.0) return col_z(Ri);
+        else return mul(Ri, axv);
       };
       if constexpr ((fl & TDS_LF_PRISMATIC) != 0) {
         const V3<RC> d = rot_axis();
@@ -233,11 +407,11 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       } else {
         const V3<RC> w = rot_axis();
         if constexpr (jt == TDSJ_REVOLUTE_AXIS) {
-          const RC dl = sqrt_t(RC(ax * ax + ay * ay + az * az));
+          const RC dl = sqrt_t(dot(axv, axv));
           RC s, c;
           sincos_t(qi * RC(0.5), &s, &c);
           s = s / dl;
-          Ri = mul(Ri, quat_to_matrix<RC>(RC(ax) * s, RC(ay) * s, RC(az) * s, c));
+          Ri = mul(Ri, quat_to_matrix<RC>(axv.x * s, axv.y * s, axv.z * s, c));
         } else {
           RC s, c;
           sincos_t(qi, &s, &c);
@@ -250,25 +424,33 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
         S.bot = cross(pi, w);
       }
     }
-    if constexpr (k < NT) st6<RC>(ts_S(k), ST, S); else Sreg[k] = S;
-    {   // rigid-body inertia about O in world axes (own links: private shared memory; massless links: nothing)
-      constexpr bool massless = SP::L_RBIC[R][k][0] == 0.0 && SP::L_RBIC[R][k][4] == 0.0 && SP::L_RBIC[R][k][5] == 0.0 && SP::L_RBIC[R][k][6] == 0.0 &&
-                                SP::L_RBIC[R][k][7] == 0.0 && SP::L_RBIC[R][k][8] == 0.0 && SP::L_RBIC[R][k][9] == 0.0;
+    if constexpr (TR) st6<RC>(ts_S(k), ST, S); else Sreg[k] = S;
+    {   // rigid-body inertia about O in world axes (subtree links: private shared memory; massless links: nothing)
+      constexpr bool massless = TR ? (SP::L_RBIC[0][k][0] == 0.0 && SP::L_RBIC[0][k][4] == 0.0 && SP::L_RBIC[0][k][5] == 0.0 && SP::L_RBIC[0][k][6] == 0.0 &&
+                                      SP::L_RBIC[0][k][7] == 0.0 && SP::L_RBIC[0][k][8] == 0.0 && SP::L_RBIC[0][k][9] == 0.0)
+                                   : C::massless(k);
       if constexpr (!massless) {
+        double b[10];
+        if constexpr (TR) {
+          b[0] = CD(SP::L_RBIC[0][k][0]); b[1] = CD(SP::L_RBIC[0][k][1]); b[2] = CD(SP::L_RBIC[0][k][2]); b[3] = CD(SP::L_RBIC[0][k][3]); b[4] = CD(SP::L_RBIC[0][k][4]);
+          b[5] = CD(SP::L_RBIC[0][k][5]); b[6] = CD(SP::L_RBIC[0][k][6]); b[7] = CD(SP::L_RBIC[0][k][7]); b[8] = CD(SP::L_RBIC[0][k][8]); b[9] = CD(SP::L_RBIC[0][k][9]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 10; ++j) b[j] = LG.rbic[ko][j];
+        }
         Rbi<RC> r;
-        r.m = RC(CD(SP::L_RBIC[R][k][0]));
-        const V3<RC> c = pi + mul(Ri, v3<RC>(RC(CD(SP::L_RBIC[R][k][1])), RC(CD(SP::L_RBIC[R][k][2])), RC(CD(SP::L_RBIC[R][k][3]))));
+        r.m = RC(b[0]);
+        const V3<RC> c = pi + mul(Ri, v3<RC>(RC(b[1]), RC(b[2]), RC(b[3])));
         r.h = c * r.m;
         S3<RA> Icf;
-        Icf.xx = RA(CD(SP::L_RBIC[R][k][4])); Icf.xy = RA(CD(SP::L_RBIC[R][k][5])); Icf.xz = RA(CD(SP::L_RBIC[R][k][6]));
-        Icf.yy = RA(CD(SP::L_RBIC[R][k][7])); Icf.yz = RA(CD(SP::L_RBIC[R][k][8])); Icf.zz = RA(CD(SP::L_RBIC[R][k][9]));
+        Icf.xx = RA(b[4]); Icf.xy = RA(b[5]); Icf.xz = RA(b[6]); Icf.yy = RA(b[7]); Icf.yz = RA(b[8]); Icf.zz = RA(b[9]);
         const S3<RA> Irot = rot_sym(cvt<RA>(Ri), Icf);
         r.I.xx = RC(Irot.xx); r.I.xy = RC(Irot.xy); r.I.xz = RC(Irot.xz); r.I.yy = RC(Irot.yy); r.I.yz = RC(Irot.yz); r.I.zz = RC(Irot.zz);
         const RC cc = dot(c, c);
         r.I.xx += r.m * (cc - c.x * c.x); r.I.yy += r.m * (cc - c.y * c.y); r.I.zz += r.m * (cc - c.z * c.z);
         r.I.xy -= r.m * c.x * c.y; r.I.xz -= r.m * c.x * c.z; r.I.yz -= r.m * c.y * c.z;
-        if constexpr (k < NT) st_rbi<RC>(tl_rbi(k), ST, r);
-        else st_rbi<RC>(sp<RC>(priv, lane, (k - NT) * 10 * RCW), ST, r);
+        if constexpr (TR) st_rbi<RC>(tl_rbi(k), ST, r);
+        else st_rbi<RC>(sp<RC>(priv, lane, ko * 10 * RCW), ST, r);
       }
     }
     Sv<RA> v = vp;
@@ -278,15 +460,20 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       v.top = axpy(Sf.top, qdi, v.top);
       v.bot = axpy(Sf.bot, qdi, v.bot);
     }
-    if constexpr (k < NT) st6<RA>(tl_v(k), ST, v); else vreg[k] = v;
-    constexpr int xs = SP::L_XW[R][k];
+    if constexpr (TR) st6<RA>(tl_v(k), ST, v); else vreg[k] = v;
+    constexpr int xs = SP::L_XW[0][k];
     if constexpr (xs >= 0) {
-      if constexpr (k < NT) { st9<RC>(xw_rc(xs + 1), ST, Ri); st3<RC>(xw_rc(xs + 1) + 9 * ST, ST, pi); st6<RA>(xw_ra(xs + 1), ST, v); }
+      if constexpr (TR) { st9<RC>(xw_rc(xs + 1), ST, Ri); st3<RC>(xw_rc(xs + 1) + 9 * ST, ST, pi); st6<RA>(xw_ra(xs + 1), ST, v); }
       else { xwR[xs] = Ri; xwp[xs] = pi; }
     }
-    if (want_contacts) emit_geoms(IC<SP::L_GB[R][k]>{}, IC<SP::L_GE[R][k]>{}, IC<SP::L_CAND[R][k]>{}, IC<SP::L_LPT[R][k]>{}, Ri, pi, plane_off);
+    if (want_contacts) {
+      if constexpr (TR) emit_trunk_geoms(IC<SP::L_GB[0][k]>{}, IC<SP::L_GE[0][k]>{}, IC<SP::L_CAND[0][k]>{}, IC<SP::L_LPT[0][k]>{}, Ri, pi);
+      else emit_own_geoms(IC<k>{}, Ri, pi);
+    }
     if (io.link_xf && live) {
-      float* o = io.link_xf + (size_t)CI(SP::L_LINK[R][k]) * 12 * ns + e;
+      int link;
+      if constexpr (TR) link = CI(SP::L_LINK[0][k]); else link = LG.link[ko];
+      float* o = io.link_xf + (size_t)link * 12 * ns + e;
       o[0] = (float)Ri.xx; o[(size_t)1 * ns] = (float)Ri.xy; o[(size_t)2 * ns] = (float)Ri.xz;
       o[(size_t)3 * ns] = (float)Ri.yx; o[(size_t)4 * ns] = (float)Ri.yy; o[(size_t)5 * ns] = (float)Ri.yz;
       o[(size_t)6 * ns] = (float)Ri.zx; o[(size_t)7 * ns] = (float)Ri.zy; o[(size_t)8 * ns] = (float)Ri.zz;
@@ -298,7 +485,7 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // ---- pass 1a: role 0 computes the origin and walks the trunk --------------------------------------------------------------
   RC* const sO = sp<RC>(smem, lane, L::O);
   RC* const sRb = sp<RC>(smem, lane, L::RB);
-  if constexpr (R == 0) {
+  if (role == 0) {
     M3<RC> Rb0 = m3_identity<RC>();
     O = v3<RC>(RC(0), RC(0), RC(0));
     if constexpr (FLOAT) {
@@ -336,18 +523,18 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       v_prev.bot = mul(RbA, v3<RA>(RA(bqd[3]), RA(bqd[4]), RA(bqd[5])));
     } else { v_prev.top = v3<RA>(RA(0), RA(0), RA(0)); v_prev.bot = v_prev.top; }
     st9<RC>(xw_rc(0), ST, R_prev); st3<RC>(xw_rc(0) + 9 * ST, ST, p_prev); st6<RA>(xw_ra(0), ST, v_prev);
-    if (want_contacts) emit_geoms(IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{}, R_prev, p_prev, plane_off);
+    if (want_contacts) emit_trunk_geoms(IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{}, R_prev, p_prev);
     sfor<0, NT>(pass1);
   }
   __syncthreads();
   // ---- pass 1b: every role walks its subtree --------------------------------------------------------------------------------------
-  if constexpr (R != 0) { O = ld3<RC>(sO, ST); plane_off = sO[3 * ST]; }
+  O = ld3<RC>(sO, ST); plane_off = sO[3 * ST];
   M3<RC> Rb = m3_identity<RC>();
   if constexpr (FLOAT) Rb = ld9<RC>(sRb, ST);
   sfor<NT, NLOC>(pass1);
   // set of active candidates of the environment: OR over the roles through shared memory
-  flg[(2 * R) * ST] = (unsigned)my_active;
-  flg[(2 * R + 1) * ST] = (unsigned)(my_active >> 32);
+  flg[(2 * role) * ST] = (unsigned)my_active;
+  flg[(2 * role + 1) * ST] = (unsigned)(my_active >> 32);
   const bool cta_contact = __syncthreads_or(my_active != 0ull) != 0;   // uniform: any contact in this tile
   const bool solve = (mode == MODE_FULL) && cta_contact;
   unsigned long long team_active = 0ull;
@@ -356,7 +543,7 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
   TDSS_PHASE();  // 2
 
   // ---- pass 2 on one link: ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ------------------------------------
-  // Own blocks of the joint-space inertia in registers: M_kk (lower triangle), C = coupling with the trunk dofs;
+  // Subtree blocks of the joint-space inertia in registers: M_kk (lower triangle), C = coupling with the trunk dofs;
   // role 0 also holds the trunk block B.
   RS Mkk[NODA * (NODA + 1) / 2], Cm[NODA * NTDA], Bm[NTRIA];
 #pragma unroll
@@ -374,36 +561,41 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
     constexpr int j = decltype(Jc)::value;
     if constexpr (j < NT) return ld6<RC>(ts_S(j), ST); else return Sreg[j];
   };
+  auto acc_ptr_ra = [&](int r, int s) { return sp<RA>(smem, lane, L::ACC + (r * NATT + s) * L::ACCW); };
+  auto acc_ptr_rc = [&](int r, int s) { return sp<RC>(smem, lane, L::ACC + (r * NATT + s) * L::ACCW + L::ACC_IC); };
   auto pass2 = [&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
-    constexpr int fl = SP::L_FLAGS[R][k];
-    constexpr bool massless = SP::L_RBIC[R][k][0] == 0.0 && SP::L_RBIC[R][k][4] == 0.0 && SP::L_RBIC[R][k][5] == 0.0 && SP::L_RBIC[R][k][6] == 0.0 &&
-                              SP::L_RBIC[R][k][7] == 0.0 && SP::L_RBIC[R][k][8] == 0.0 && SP::L_RBIC[R][k][9] == 0.0;
+    constexpr bool TR = k < NT;
+    constexpr int ko = TR ? 0 : k - NT;
+    constexpr int fl = TR ? SP::L_FLAGS[0][k] : C::flags(k);
+    constexpr bool massless = TR ? (SP::L_RBIC[0][k][0] == 0.0 && SP::L_RBIC[0][k][4] == 0.0 && SP::L_RBIC[0][k][5] == 0.0 && SP::L_RBIC[0][k][6] == 0.0 &&
+                                    SP::L_RBIC[0][k][7] == 0.0 && SP::L_RBIC[0][k][8] == 0.0 && SP::L_RBIC[0][k][9] == 0.0)
+                                 : C::massless(k);
     Sv<RA> v;
-    if constexpr (k < NT) v = ld6<RA>(tl_v(k), ST); else v = vreg[k];
+    if constexpr (TR) v = ld6<RA>(tl_v(k), ST); else v = vreg[k];
     Rbi<RC> Ic = rbi_nz<RC>();
     Abi<RA> Ia = abi_nz<RA>();
     Sv<RA> pA = sv_nz<RA>();
     if constexpr (!massless) {
-      if constexpr (k < NT) Ic = ld_rbi<RC>(tl_rbi(k), ST); else Ic = ld_rbi<RC>(sp<RC>(priv, lane, (k - NT) * 10 * RCW), ST);
+      if constexpr (TR) Ic = ld_rbi<RC>(tl_rbi(k), ST); else Ic = ld_rbi<RC>(sp<RC>(priv, lane, ko * 10 * RCW), ST);
       const Rbi<RA> rb = cvt_rbi<RA>(Ic);
       Ia = abi_from_rbi(rb);
       pA = cross_mf(v, rbi_mul(rb, v));                      // kinematics.hpp:132
     }
     if constexpr ((fl & TDS_TF_CHILD_ADJ) != 0) { abi_add(Ia, cA); pA = pA + cP; rbi_add(Ic, cC); }
-    constexpr int as = SP::L_ACC[R][k];
+    constexpr int as = SP::L_ACC[0][k];
     if constexpr (as >= 0) {
-      if constexpr (as < SP::N_ATT) {   // attachment slot: this role's part is in registers, the others' in shared memory
-        static_assert(R == 0 || k < 0, "attachment accumulators are consumed by role 0");
-        abi_add(Ia, accA[as]); pA = pA + accP[as]; rbi_add(Ic, accC[as]);
+      abi_add(Ia, accA[as]); pA = pA + accP[as]; rbi_add(Ic, accC[as]);
+      if constexpr (as < SP::N_ATT) {   // attachment slot: role 0's part is in registers, the others' in shared memory
+        static_assert(TR || k < 0, "attachment accumulators are consumed by trunk links");
         sfor<1, TT>([&](auto Rc_) {
           constexpr int r = decltype(Rc_)::value;
           Abi<RA> sa; Sv<RA> sv_;
-          acc_ld27<RA>(sp<RA>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW), ST, sa, sv_);
+          acc_ld27<RA>(acc_ptr_ra(r, as), ST, sa, sv_);
           abi_add(Ia, sa); pA = pA + sv_;
-          rbi_add(Ic, ld_rbi<RC>(sp<RC>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW + L::ACC_IC), ST));
+          rbi_add(Ic, ld_rbi<RC>(acc_ptr_rc(r, as), ST));
         });
-      } else { abi_add(Ia, accA[as]); pA = pA + accP[as]; rbi_add(Ic, accC[as]); }
+      }
     }
     Sv<RA> pa = pA;
     if constexpr (!(fl & TDS_LF_FIXED)) {
@@ -416,10 +608,15 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       const RA D = dot(S, U);
       const RA invD = RA(1) / D;
       RA tau = RA(tauv[k]);
-      if constexpr (SP::L_SD[R][k][0] != 0.0) tau -= RA(CD(SP::L_SD[R][k][0])) * RA(qv[k]);
-      if constexpr (SP::L_SD[R][k][1] != 0.0) tau -= RA(CD(SP::L_SD[R][k][1])) * qdj;
+      if constexpr (TR) {
+        if constexpr (SP::L_SD[0][k][0] != 0.0) tau -= RA(CD(SP::L_SD[0][k][0])) * RA(qv[k]);
+        if constexpr (SP::L_SD[0][k][1] != 0.0) tau -= RA(CD(SP::L_SD[0][k][1])) * qdj;
+      } else {
+        if constexpr (C::has_sd(k, 0)) tau -= RA(LG.sd[ko][0]) * RA(qv[k]);
+        if constexpr (C::has_sd(k, 1)) tau -= RA(LG.sd[ko][1]) * qdj;
+      }
       const RA u = tau - dot(S, pA);                         // :129
-      if constexpr (k < NT) { st6<RA>(tl_v(k), ST, c); st6<RA>(tl_u(k), ST, U); tl_u(k)[6 * ST] = invD; tl_u(k)[7 * ST] = u; }
+      if constexpr (TR) { st6<RA>(tl_v(k), ST, c); st6<RA>(tl_u(k), ST, U); tl_u(k)[6 * ST] = invD; tl_u(k)[7 * ST] = u; }
       else { vreg[k] = c; Ureg[k] = U; invDreg[k] = invD; ureg[k] = u; }
       const V3<RA> ut = U.top * invD, ub = U.bot * invD;     // Ia -= U (U/D)^T, :160-168
       Ia.I.xx -= U.top.x * ut.x; Ia.I.xy -= U.top.x * ut.y; Ia.I.xz -= U.top.x * ut.z;
@@ -436,21 +633,21 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       if (solve) {   // CRBA column (mass_matrix.hpp:86-111): M_ij = S_j . (Ic_i S_i)
         const Sv<RC> F = rbi_mul(Ic, Sd);
         const RS mii = RS(dot(Sd, F));
-        constexpr int ld = SP::L_LDOF[R][k];
-        if constexpr (k < NT) Bm[tri(ld, ld)] = mii; else Mkk[tri(ld - NTD, ld - NTD)] = mii;
+        constexpr int ld = SP::L_LDOF[0][k];
+        if constexpr (TR) Bm[tri(ld, ld)] = mii; else Mkk[tri(ld - NTD, ld - NTD)] = mii;
         sfor<0, k>([&](auto Jc) {
           constexpr int j = decltype(Jc)::value;
-          constexpr int lj = SP::L_LDOF[R][j];
-          if constexpr (lj >= 0 && is_anc<SP, R>(j, k)) {
+          constexpr int lj = SP::L_LDOF[0][j];
+          if constexpr (lj >= 0 && is_anc<SP, 0>(j, k)) {
             const RS val = RS(dot(S_of(IC<j>{}), F));
-            if constexpr (k < NT) Bm[tri(ld, lj)] = val;
+            if constexpr (TR) Bm[tri(ld, lj)] = val;
             else if constexpr (lj >= NTD) Mkk[tri(ld - NTD, lj - NTD)] = val;
             else Cm[(ld - NTD) * NTDA + lj] = val;
           }
         });
         if constexpr (FLOAT) {
           const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
-          if constexpr (k < NT) {
+          if constexpr (TR) {
             Bm[tri(ld, 0)] = RS(ft.x); Bm[tri(ld, 1)] = RS(ft.y); Bm[tri(ld, 2)] = RS(ft.z);
             Bm[tri(ld, 3)] = RS(fb.x); Bm[tri(ld, 4)] = RS(fb.y); Bm[tri(ld, 5)] = RS(fb.z);
           } else {
@@ -462,23 +659,23 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
     }
     if constexpr ((fl & TDS_TF_PARENT_ADJ) != 0) { cA = Ia; cP = pa; cC = Ic; }
     else {
-      constexpr int slot = SP::L_PAR[R][k];
+      constexpr int slot = SP::L_PAR[0][k];
       if constexpr (slot >= 0) { abi_add(accA[slot], Ia); accP[slot] = accP[slot] + pa; rbi_add(accC[slot], Ic); }
     }
   };
-  // ---- pass 2a: subtrees; publish this role's attachment accumulators ------------------------------------------------------------------
+  // ---- pass 2a: subtrees; roles 1.. publish their attachment accumulators ------------------------------------------------------------------
   sfor_rev<NT, NLOC>(pass2);
-  if constexpr (R != 0) {
+  if (role != 0) {
     sfor<0, SP::N_ATT>([&](auto Sc) {
       constexpr int s = decltype(Sc)::value;
-      RA* pa_ = sp<RA>(smem, lane, L::ACC + (R * cmax(SP::N_ATT, 1) + s) * L::ACCW);
+      RA* pa_ = acc_ptr_ra(role, s);
       const Abi<RA>& a = accA[s]; const Sv<RA>& f = accP[s];
       pa_[0] = a.I.xx; pa_[ST] = a.I.xy; pa_[2 * ST] = a.I.xz; pa_[3 * ST] = a.I.yy; pa_[4 * ST] = a.I.yz; pa_[5 * ST] = a.I.zz;
       pa_[6 * ST] = a.H.xx; pa_[7 * ST] = a.H.xy; pa_[8 * ST] = a.H.xz; pa_[9 * ST] = a.H.yx; pa_[10 * ST] = a.H.yy; pa_[11 * ST] = a.H.yz;
       pa_[12 * ST] = a.H.zx; pa_[13 * ST] = a.H.zy; pa_[14 * ST] = a.H.zz;
       pa_[15 * ST] = a.M.xx; pa_[16 * ST] = a.M.xy; pa_[17 * ST] = a.M.xz; pa_[18 * ST] = a.M.yy; pa_[19 * ST] = a.M.yz; pa_[20 * ST] = a.M.zz;
       pa_[21 * ST] = f.top.x; pa_[22 * ST] = f.top.y; pa_[23 * ST] = f.top.z; pa_[24 * ST] = f.bot.x; pa_[25 * ST] = f.bot.y; pa_[26 * ST] = f.bot.z;
-      st_rbi<RC>(sp<RC>(smem, lane, L::ACC + (R * cmax(SP::N_ATT, 1) + s) * L::ACCW + L::ACC_IC), ST, accC[s]);
+      st_rbi<RC>(acc_ptr_rc(role, s), ST, accC[s]);
     });
   }
   __syncthreads();
@@ -488,32 +685,39 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
   Sv<RA> a_prev;
   auto pass3 = [&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
-    constexpr int fl = SP::L_FLAGS[R][k], lpar = SP::L_LPAR[R][k];
+    constexpr bool TR = k < NT;
+    constexpr int ko = TR ? 0 : k - NT;
+    constexpr int fl = TR ? SP::L_FLAGS[0][k] : C::flags(k), lpar = SP::L_LPAR[0][k];
     Sv<RA> a;
     if constexpr ((fl & TDS_TF_PARENT_ADJ) != 0) a = a_prev;
     else if constexpr (lpar < NT) {
-      constexpr int slot = lpar < 0 ? 0 : SP::L_XW[R][lpar < 0 ? 0 : lpar] + 1;
+      constexpr int slot = lpar < 0 ? 0 : SP::L_XW[0][lpar < 0 ? 0 : lpar] + 1;
       a = ld6<RA>(xw_ra(slot) + 6 * ST, ST);
-    } else a = xwa[CI(SP::L_XW[R][lpar])];
+    } else a = xwa[CI(SP::L_XW[0][lpar < NT ? NT : lpar])];
     if constexpr (!(fl & TDS_LF_FIXED)) {
       Sv<RA> c, U; RA invD, u;
-      if constexpr (k < NT) { c = ld6<RA>(tl_v(k), ST); U = ld6<RA>(tl_u(k), ST); invD = tl_u(k)[6 * ST]; u = tl_u(k)[7 * ST]; }
+      if constexpr (TR) { c = ld6<RA>(tl_v(k), ST); U = ld6<RA>(tl_u(k), ST); invD = tl_u(k)[6 * ST]; u = tl_u(k)[7 * ST]; }
       else { c = vreg[k]; U = Ureg[k]; invD = invDreg[k]; u = ureg[k]; }
       a = a + c;
       const RA qdd = invD * (u - dot(U, a));
       const Sv<RA> S = cvt_sv<RA>(S_of(IC<k>{}));
       a.top = axpy(S.top, qdd, a.top);
       a.bot = axpy(S.bot, qdd, a.bot);
-      if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)CI(SP::L_QDIDX[R][k]) * ns + e] = (float)qdd; }
-      else qdv[k] = (float)(RA(qdv[k]) + qdd * dtA);
+      if (mode == MODE_FD) {
+        if (live && io.qdd_out) {
+          int qdi;
+          if constexpr (TR) qdi = CI(SP::L_QDIDX[0][k]); else qdi = LG.qdidx[ko];
+          io.qdd_out[(size_t)qdi * ns + e] = (float)qdd;
+        }
+      } else qdv[k] = (float)(RA(qdv[k]) + qdd * dtA);
     }
-    constexpr int xs = SP::L_XW[R][k];
+    constexpr int xs = SP::L_XW[0][k];
     if constexpr (xs >= 0) {
-      if constexpr (k < NT) st6<RA>(xw_ra(xs + 1) + 6 * ST, ST, a); else xwa[xs] = a;
+      if constexpr (TR) st6<RA>(xw_ra(xs + 1) + 6 * ST, ST, a); else xwa[xs] = a;
     }
     a_prev = a;
   };
-  if constexpr (R == 0) {
+  if (role == 0) {
     sfor_rev<0, NT>(pass2);
     // base acceleration (forward_dynamics.hpp:218-243)
     Sv<RC> base_acc_b; base_acc_b.top = v3<RC>(RC(0), RC(0), RC(0)); base_acc_b.bot = base_acc_b.top;
@@ -529,9 +733,9 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
           sfor<1, TT>([&](auto Rc_) {
             constexpr int r = decltype(Rc_)::value;
             Abi<RA> sa; Sv<RA> sv_;
-            acc_ld27<RA>(sp<RA>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW), ST, sa, sv_);
+            acc_ld27<RA>(acc_ptr_ra(r, as), ST, sa, sv_);
             abi_add(Ach, sa); pch = pch + sv_;
-            rbi_add(Icch, ld_rbi<RC>(sp<RC>(smem, lane, L::ACC + (r * cmax(SP::N_ATT, 1) + as) * L::ACCW + L::ACC_IC), ST));
+            rbi_add(Icch, ld_rbi<RC>(acc_ptr_rc(r, as), ST));
           });
         }
       }
@@ -589,10 +793,10 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
         auto sub = [](M3<RC> a, const M3<RC>& b) { a.xx -= b.xx; a.xy -= b.xy; a.xz -= b.xz; a.yx -= b.yx; a.yy -= b.yy; a.yz -= b.yz; a.zx -= b.zx; a.zy -= b.zy; a.zz -= b.zz; return a; };
         auto add = [](M3<RC> a, const M3<RC>& b) { a.xx += b.xx; a.xy += b.xy; a.xz += b.xz; a.yx += b.yx; a.yy += b.yy; a.yz += b.yz; a.zx += b.zx; a.zy += b.zy; a.zz += b.zz; return a; };
         M3<RC> Ainv = inv3(I3);
-        M3<RC> C = neg(H3);
-        M3<RC> Dm = inv3(sub(M3m, mul(mul(C, Ainv), H3)));
+        M3<RC> Cn = neg(H3);
+        M3<RC> Dm = inv3(sub(M3m, mul(mul(Cn, Ainv), H3)));
         M3<RC> AinvBD = mul(mul(Ainv, H3), Dm);
-        M3<RC> Ii = add(Ainv, mul(mul(AinvBD, C), Ainv));
+        M3<RC> Ii = add(Ainv, mul(mul(AinvBD, Cn), Ainv));
         M3<RC> Hi = neg(AinvBD);
         V3<RC> ft = cvt<RC>(pb.top), fb = cvt<RC>(pb.bot);
         V3<RC> at = mul(Ii, ft) + mul(Hi, fb);
@@ -653,7 +857,7 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       });
     });
     // partial Schur complement of this role -> shared memory (the accumulator region is free now)
-    RS* const Pk = sp<RS>(smem, lane, L::ACC + R * L::PW);
+    RS* const Pk = sp<RS>(smem, lane, L::ACC + role * L::PW);
     sfor<0, NTD>([&](auto T1) {
       constexpr int t1 = decltype(T1)::value;
       sfor<0, t1 + 1>([&](auto T2) {
@@ -665,7 +869,7 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
     });
     __syncthreads();
     RS* const Lt = sp<RS>(smem, lane, L::LT);
-    if constexpr (R == 0) {   // S = B - sum over the roles of G^T G, then S = L_t L_t^T
+    if (role == 0) {   // S = B - sum over the roles of G^T G, then S = L_t L_t^T
       sfor<0, NTRI>([&](auto Ic_) {
         constexpr int i = decltype(Ic_)::value;
         const RS* p = sp<RS>(smem, lane, L::ACC);
@@ -686,96 +890,113 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
     __syncthreads();
   }
   TDSS_PHASE();  // 5
+  constexpr int YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);   // row layout: y_own | y_t | b[3] yy[3] 1/A[3]
   if (solve) {
     const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b
     const V3<RC> f1 = v3<RC>(RC(CD(SP::FR1[0])), RC(CD(SP::FR1[1])), RC(CD(SP::FR1[2])));
     const V3<RC> f2 = v3<RC>(RC(CD(SP::FR2[0])), RC(CD(SP::FR2[1])), RC(CD(SP::FR2[2])));
     const RS* const Lt = sp<RS>(smem, lane, L::LT);
-    // contact rows of this role's penetrating points: one row per direction (normal, friction 1, friction 2)
-    auto rows_of = [&](auto Kl, auto Gb, auto Ge, auto Cand0, auto Lpt0) {
-      constexpr int kl = decltype(Kl)::value, gb = decltype(Gb)::value, ge = decltype(Ge)::value;
-      sfor<gb, ge>([&](auto Gc) {
-        constexpr int g = decltype(Gc)::value;
-        constexpr int npt = geom_pts<SP>(g);
-        sfor<0, npt>([&](auto Jc_) {
-          constexpr int cand = decltype(Cand0)::value + pts_before<SP>(gb, g) + decltype(Jc_)::value;
-          constexpr int lpt = decltype(Lpt0)::value + pts_before<SP>(gb, g) + decltype(Jc_)::value;
-          if ((my_active >> cand) & 1ull) {
-            const V3<RC> xc = cpos[lpt];
-            RS ro[3][NODA], rt[3][NTDA];
+    // contact rows of one penetrating point on local link kl (-1: base): normal, friction 1, friction 2
+    auto point_rows = [&](auto Kl, const int cand, const V3<RC>& xc, const RC dist) {
+      constexpr int kl = decltype(Kl)::value;
+      RS ro[3][NODA], rt[3][NTDA];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
+      for (int d = 0; d < 3; ++d) {
 #pragma unroll
-              for (int i = 0; i < NODA; ++i) ro[d][i] = RS(0);
+        for (int i = 0; i < NODA; ++i) ro[d][i] = RS(0);
 #pragma unroll
-              for (int i = 0; i < NTDA; ++i) rt[d][i] = RS(0);
-            }
-            V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));
-            if constexpr (FLOAT) {   // jacobian.hpp:39-58 with r = x_c
-              const V3<RC> cols[6] = {v3<RC>(RC(0), -xc.z, xc.y), v3<RC>(xc.z, RC(0), -xc.x), v3<RC>(-xc.y, xc.x, RC(0)),
-                                      v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
+        for (int i = 0; i < NTDA; ++i) rt[d][i] = RS(0);
+      }
+      V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));
+      if constexpr (FLOAT) {   // jacobian.hpp:39-58 with r = x_c
+        const V3<RC> cols[6] = {v3<RC>(RC(0), -xc.z, xc.y), v3<RC>(xc.z, RC(0), -xc.x), v3<RC>(-xc.y, xc.x, RC(0)),
+                                v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
 #pragma unroll
-              for (int k = 0; k < 6; ++k) {
-                rt[0][k] = RS(dot(nbv, cols[k])); rt[1][k] = RS(dot(f1, cols[k])); rt[2][k] = RS(dot(f2, cols[k]));
-                vel = vel + cols[k] * RC(tqd[k * ST]);
-              }
-            }
-            sfor<0, (kl < 0 ? 0 : kl + 1)>([&](auto Jc) {   // jacobian.hpp:63-80: the link and its ancestors
-              constexpr int j = decltype(Jc)::value;
-              constexpr int lj = SP::L_LDOF[R][j];
-              if constexpr (lj >= 0 && (j == kl || is_anc<SP, R>(j, kl))) {
-                const Sv<RC> S = S_of(IC<j>{});
-                const V3<RC> col = S.bot + cross(S.top, xc);
-                const RS c0 = RS(dot(nbv, col)), c1 = RS(dot(f1, col)), c2 = RS(dot(f2, col));
-                if constexpr (lj >= NTD) { ro[0][lj - NTD] = c0; ro[1][lj - NTD] = c1; ro[2][lj - NTD] = c2; vel = vel + col * RC(qdv[j]); }
-                else { rt[0][lj] = c0; rt[1][lj] = c1; rt[2][lj] = c2; vel = vel + col * RC(tqd[lj * ST]); }
-              }
-            });
-            RS* const row = sp<RS>(smem, lane, L::CON + cand * L::CONW);
-            constexpr int YO = 0, YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);
-            row[(BB + 0) * ST] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * cdist[lpt] / RC(P.dt));
-            row[(BB + 1) * ST] = RS(dot(f1, vel));
-            row[(BB + 2) * ST] = RS(dot(f2, vel));
+        for (int k = 0; k < 6; ++k) {
+          rt[0][k] = RS(dot(nbv, cols[k])); rt[1][k] = RS(dot(f1, cols[k])); rt[2][k] = RS(dot(f2, cols[k]));
+          vel = vel + cols[k] * RC(tqd[k * ST]);
+        }
+      }
+      sfor<0, (kl < 0 ? 0 : kl + 1)>([&](auto Jc) {   // jacobian.hpp:63-80: the link and its ancestors
+        constexpr int j = decltype(Jc)::value;
+        constexpr int lj = SP::L_LDOF[0][j];
+        if constexpr (lj >= 0 && (j == kl || is_anc<SP, 0>(j, kl))) {
+          const Sv<RC> S = S_of(IC<j>{});
+          const V3<RC> col = S.bot + cross(S.top, xc);
+          const RS c0 = RS(dot(nbv, col)), c1 = RS(dot(f1, col)), c2 = RS(dot(f2, col));
+          if constexpr (lj >= NTD) { ro[0][lj - NTD] = c0; ro[1][lj - NTD] = c1; ro[2][lj - NTD] = c2; vel = vel + col * RC(qdv[j]); }
+          else { rt[0][lj] = c0; rt[1][lj] = c1; rt[2][lj] = c2; vel = vel + col * RC(tqd[lj * ST]); }
+        }
+      });
+      RS* const row = sp<RS>(smem, lane, L::CON) + (size_t)cand * (L::CONW / L::RSW) * ST;
+      row[(BB + 0) * ST] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
+      row[(BB + 1) * ST] = RS(dot(f1, vel));
+      row[(BB + 2) * ST] = RS(dot(f2, vel));
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              // y_own = L_k^-1 r_own ;  y_t = L_t^-1 (r_t - G^T y_own)
-              sfor<0, NOD>([&](auto Ic_) {
-                constexpr int i = decltype(Ic_)::value;
-                RS s = ro[d][i];
-                sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(i, k)] * ro[d][k]; });
-                ro[d][i] = s * Mkk[tri(i, i)];
-              });
-              RS yy = RS(0);
-              sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; yy += ro[d][i] * ro[d][i]; row[(YO + d * L::NOD + i) * ST] = ro[d][i]; });
-              sfor<0, NTD>([&](auto Tc) {
-                constexpr int t = decltype(Tc)::value;
-                RS s = rt[d][t];
-                sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; s -= Cm[i * NTDA + t] * ro[d][i]; });
-                sfor<0, t>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Lt[tri(t, k) * ST] * rt[d][k]; });
-                rt[d][t] = s * Lt[tri(t, t) * ST];
-                yy += rt[d][t] * rt[d][t];
-                row[(YT + d * L::NTD + t) * ST] = rt[d][t];
-              });
-              // A_ii = y.y + cfm is constant during the sweep: keep y.y and 1 / A_ii per row
-              row[(BB + 3 + d) * ST] = yy;
-              row[(BB + 6 + d) * ST] = RS(1) / (yy + RS(P.cfm));
-            }
-          }
+      for (int d = 0; d < 3; ++d) {
+        // y_own = L_k^-1 r_own ;  y_t = L_t^-1 (r_t - G^T y_own)   (a trunk point has no own part)
+        RS yy = RS(0);
+        if constexpr (kl >= NT) {
+          sfor<0, NOD>([&](auto Ic_) {
+            constexpr int i = decltype(Ic_)::value;
+            RS s = ro[d][i];
+            sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(i, k)] * ro[d][k]; });
+            ro[d][i] = s * Mkk[tri(i, i)];
+          });
+        }
+        sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; yy += ro[d][i] * ro[d][i]; row[(d * L::NOD + i) * ST] = ro[d][i]; });
+        sfor<0, NTD>([&](auto Tc) {
+          constexpr int t = decltype(Tc)::value;
+          RS s = rt[d][t];
+          if constexpr (kl >= NT) sfor<0, NOD>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; s -= Cm[i * NTDA + t] * ro[d][i]; });
+          sfor<0, t>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Lt[tri(t, k) * ST] * rt[d][k]; });
+          rt[d][t] = s * Lt[tri(t, t) * ST];
+          yy += rt[d][t] * rt[d][t];
+          row[(YT + d * L::NTD + t) * ST] = rt[d][t];
+        });
+        // A_ii = y.y + cfm is constant during the sweep: keep y.y and 1 / A_ii per row
+        row[(BB + 3 + d) * ST] = yy;
+        row[(BB + 6 + d) * ST] = RS(1) / (yy + RS(P.cfm));
+      }
+    };
+    // subtree points (every role)
+    sfor<NT, NLOC>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      sfor<0, SP::L_GE[0][k] - SP::L_GB[0][k]>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        sfor<0, C::geom_pts(SP::L_GB[0][k] + i)>([&](auto Jc) {
+          constexpr int p = C::pt_local(k, i) + decltype(Jc)::value;
+          const int cand = LG.cand[p];
+          if ((my_active >> cand) & 1ull) point_rows(IC<k>{}, cand, cpos[p], cdist[p]);
         });
       });
-    };
-    if constexpr (R == 0) rows_of(IC<-1>{}, IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{});
-    sfor<K0, NLOC>([&](auto Kc) {
-      constexpr int k = decltype(Kc)::value;
-      rows_of(IC<k>{}, IC<SP::L_GB[R][k]>{}, IC<SP::L_GE[R][k]>{}, IC<SP::L_CAND[R][k]>{}, IC<SP::L_LPT[R][k]>{});
     });
+    // base / trunk points (role 0)
+    if (role == 0) {
+      auto trunk_rows = [&](auto Kl, auto Gb, auto Ge, auto Cand0, auto Lpt0) {
+        constexpr int gb = decltype(Gb)::value, ge = decltype(Ge)::value;
+        sfor<gb, ge>([&](auto Gc) {
+          constexpr int g = decltype(Gc)::value;
+          sfor<0, geom_pts<SP>(g)>([&](auto Jc) {
+            constexpr int cand = decltype(Cand0)::value + pts_before<SP>(gb, g) + decltype(Jc)::value;
+            constexpr int lpt = decltype(Lpt0)::value + pts_before<SP>(gb, g) + decltype(Jc)::value;
+            if ((my_active >> cand) & 1ull) point_rows(Kl, cand, tpos[lpt], tdist[lpt]);
+          });
+        });
+      };
+      trunk_rows(IC<-1>{}, IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{});
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        trunk_rows(IC<k>{}, IC<SP::L_GB[0][k]>{}, IC<SP::L_GE[0][k]>{}, IC<SP::L_CAND[0][k]>{}, IC<SP::L_LPT[0][k]>{});
+      });
+    }
     __syncthreads();
   }
   TDSS_PHASE();  // 6
   if (solve) {
     RS* const zt = sp<RS>(smem, lane, L::ZT);
     RS* const wo_s = sp<RS>(smem, lane, L::WO);
-    if constexpr (R == 0) {
+    if (role == 0) {
       // projected Gauss-Seidel in the reference's row order (solve_pgs, mb_constraint_solver.hpp:101-142,417-436):
       // blocks normal | friction 1 | friction 2, contacts in enumeration order.  w = Y p stays in registers.
       const RS* const Lt = sp<RS>(smem, lane, L::LT);
@@ -790,14 +1011,15 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
 #pragma unroll
       for (int g = 0; g < NCA; ++g) { x[g][0] = RS(0); x[g][1] = RS(0); x[g][2] = RS(0); }
       const RS mu = RS(P.friction);
-      constexpr int YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);
       for (int it = 0; it < P.pgs_iterations; ++it) {
         sfor<0, 3>([&](auto Dc) {
           constexpr int d = decltype(Dc)::value;
           sfor<0, SP::N_CAND>([&](auto Gc) {
             constexpr int g = decltype(Gc)::value;
             constexpr int owner = SP::CAND_OWNER[g];
-            constexpr int nod = SP::N_OD[owner];
+            // a point on a trunk / base geom has no subtree part
+            constexpr bool own_part = !(owner == 0 && SP::CAND_LPT[g] < NPTR);
+            constexpr int nod = own_part ? NOD : 0;
             if ((team_active >> g) & 1ull) {
               const RS* const row = sp<RS>(smem, lane, L::CON + g * L::CONW);
               RS yo[cmax(nod, 1)], yt[NTDA];
@@ -844,7 +1066,7 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; z[t] = zt[t * ST]; });
       sfor<0, NOD>([&](auto Ic_) {
         constexpr int i = decltype(Ic_)::value;
-        RS s = wo_s[(R * L::NOD + i) * ST];
+        RS s = wo_s[(role * L::NOD + i) * ST];
         sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; s -= Cm[i * NTDA + t] * z[t]; });
         w[i] = s;
       });
@@ -856,10 +1078,10 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
       });
       sfor<NT, NLOC>([&](auto Kc) {
         constexpr int k = decltype(Kc)::value;
-        constexpr int lj = SP::L_LDOF[R][k];
+        constexpr int lj = SP::L_LDOF[0][k];
         if constexpr (lj >= 0) qdv[k] = (float)(RS(qdv[k]) - w[lj - NTD]);
       });
-      if constexpr (R == 0) {
+      if (role == 0) {
         if constexpr (FLOAT) {
 #pragma unroll
           for (int k = 0; k < 6; ++k) bqd[k] = (float)(RS(bqd[k]) - z[k]);
@@ -875,32 +1097,36 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
   TDSS_PHASE();  // 8
 
   // ---- integrate_euler with qdd = 0 (integrator.hpp:10-133), reward / done, write back ---------------------------------------------------
-  RC up_z = RC(1);
-  if constexpr (R == 0 && FLOAT) {
-    const RC h = RC(0.5) * RC(P.dt);
-    RC qx = RC(bq[0]), qy = RC(bq[1]), qz = RC(bq[2]), qw = RC(bq[3]);
-    const RC w0 = RC(bqd[0]), w1 = RC(bqd[1]), w2 = RC(bqd[2]);
-    const RC dw = (-qx * w0 - qy * w1 - qz * w2) * h;
-    const RC dx = (qw * w0 + qz * w1 - qy * w2) * h;
-    const RC dy = (qw * w1 + qx * w2 - qz * w0) * h;
-    const RC dz = (qw * w2 + qy * w0 - qx * w1) * h;
-    qx += dx; qy += dy; qz += dz; qw += dw;
-    const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
-    qx /= len; qy /= len; qz /= len; qw /= len;
-    bq[0] = (float)qx; bq[1] = (float)qy; bq[2] = (float)qz; bq[3] = (float)qw;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) bq[4 + k] = (float)(RC(bq[4 + k]) + RC(bqd[3 + k]) * RC(P.dt));
-    up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
-  }
-  sfor<K0, NLOC>([&](auto Kc) {
+  sfor<NT, NLOC>([&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
-    if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED)) qv[k] = (float)(RC(qv[k]) + RC(qdv[k]) * RC(P.dt));
+    if constexpr (!(C::flags(k) & TDS_LF_FIXED)) qv[k] = (float)(RC(qv[k]) + RC(qdv[k]) * RC(P.dt));
   });
-  if constexpr (R == 0) {
+  if (role == 0) {
+    RC up_z = RC(1);
+    if constexpr (FLOAT) {
+      const RC h = RC(0.5) * RC(P.dt);
+      RC qx = RC(bq[0]), qy = RC(bq[1]), qz = RC(bq[2]), qw = RC(bq[3]);
+      const RC w0 = RC(bqd[0]), w1 = RC(bqd[1]), w2 = RC(bqd[2]);
+      const RC dw = (-qx * w0 - qy * w1 - qz * w2) * h;
+      const RC dx = (qw * w0 + qz * w1 - qy * w2) * h;
+      const RC dy = (qw * w1 + qx * w2 - qz * w0) * h;
+      const RC dz = (qw * w2 + qy * w0 - qx * w1) * h;
+      qx += dx; qy += dy; qz += dz; qw += dw;
+      const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
+      qx /= len; qy /= len; qz /= len; qw /= len;
+      bq[0] = (float)qx; bq[1] = (float)qy; bq[2] = (float)qz; bq[3] = (float)qw;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bq[4 + k] = (float)(RC(bq[4 + k]) + RC(bqd[3 + k]) * RC(P.dt));
+      up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
+    }
+    sfor<0, NT>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) qv[k] = (float)(RC(qv[k]) + RC(qdv[k]) * RC(P.dt));
+    });
     bool done = false;
     if (E.reward_kind == 1) {   // laikago_environment2.h:130-171 (fixed-base emulation; q0..5 are trunk coordinates)
       constexpr int k0 = k_of_q<SP, 0>(0), k2 = k_of_q<SP, 0>(2), k3 = k_of_q<SP, 0>(3), k4 = k_of_q<SP, 0>(4);
-      if constexpr (!FLOAT && k0 >= 0 && k2 >= 0 && k3 >= 0 && k4 >= 0) {
+      if constexpr (!FLOAT && k0 >= 0 && k0 < NT && k2 >= 0 && k2 < NT && k3 >= 0 && k3 < NT && k4 >= 0 && k4 < NT) {
         const float x = qv[k0], z = qv[k2];
         const float upz = cosf(qv[k3]) * cosf(qv[k4]);
         done = (upz < 0.6f) || (z < 0.2f);
@@ -919,18 +1145,28 @@ TDS_D void role_body(char* const smem, const SimParams& P, const EnvParams& E, c
   __syncthreads();
   const bool reset = (flg[(2 * TT) * ST] != 0u) && E.auto_reset;
   if (live) {
-    sfor<K0, NLOC>([&](auto Kc) {
+    sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
-      if constexpr (!(SP::L_FLAGS[R][k] & TDS_LF_FIXED)) {
-        io.q_out[(size_t)CI(SP::L_QIDX[R][k]) * ns + e] = reset ? E.reset_q[CI(SP::L_QIDX[R][k])] : qv[k];
-        io.qd_out[(size_t)CI(SP::L_QDIDX[R][k]) * ns + e] = reset ? 0.f : qdv[k];
+      if constexpr (!(C::flags(k) & TDS_LF_FIXED)) {
+        const int qi = LG.qidx[k - NT], qdi = LG.qdidx[k - NT];
+        io.q_out[(size_t)qi * ns + e] = reset ? E.reset_q[qi] : qv[k];
+        io.qd_out[(size_t)qdi * ns + e] = reset ? 0.f : qdv[k];
       }
     });
-    if constexpr (R == 0 && FLOAT) {
+    if (role == 0) {
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) {
+          io.q_out[(size_t)CI(SP::L_QIDX[0][k]) * ns + e] = reset ? E.reset_q[CI(SP::L_QIDX[0][k])] : qv[k];
+          io.qd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = reset ? 0.f : qdv[k];
+        }
+      });
+      if constexpr (FLOAT) {
 #pragma unroll
-      for (int k = 0; k < 7; ++k) io.q_out[(size_t)k * ns + e] = reset ? E.reset_q[k] : bq[k];
+        for (int k = 0; k < 7; ++k) io.q_out[(size_t)k * ns + e] = reset ? E.reset_q[k] : bq[k];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) io.qd_out[(size_t)k * ns + e] = reset ? 0.f : bqd[k];
+        for (int k = 0; k < 6; ++k) io.qd_out[(size_t)k * ns + e] = reset ? 0.f : bqd[k];
+      }
     }
   }
   TDSS_PHASE();  // 9
@@ -944,14 +1180,13 @@ tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant_
   extern __shared__ __align__(16) char smem_raw[];
   const int role = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, known uniform to the compiler
   if ((mode_flags & 256) && role != 0) return;   // profiling aid (TDS_B200_DEBUG_SOLO): role 0 alone, results are garbage
-  const int mode = mode_flags & 255;
-  switch (role) {
-    case 0: role_body<SP, 0, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
-    case 1: role_body<SP, 1, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
-    case 2: role_body<SP, 2, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
-    default: role_body<SP, 3, RA, RC, RS>(smem_raw, P, E, io, mode, use_pd); break;
-  }
+  tile_body<SP, RA, RC, RS>(smem_raw, P, E, io, mode_flags & 255, use_pd, role);
 }
+
+// per-role numbers of the Laikago subtrees
+__constant__ LegTab<SpecLaikago> c_legs_laikago[TDS_TEAM_T] = {make_leg<SpecLaikago>(0), make_leg<SpecLaikago>(1), make_leg<SpecLaikago>(2),
+                                                                make_leg<SpecLaikago>(3)};
+template <> __device__ __forceinline__ const LegTab<SpecLaikago>& leg_tab<SpecLaikago>(int role) { return c_legs_laikago[role]; }
 
 template <class SP> struct SpecHost {
   static bool matches(const DevModel* D, const EnvParams* E) {
@@ -960,7 +1195,8 @@ template <class SP> struct SpecHost {
       if (E->n_act != SP::N_ACT) return false;
       for (int a = 0; a < SP::N_ACT; ++a) if (E->act_link[a] != SP::ACT_LINK[a]) return false;
     }
-    if (E->reward_kind == 1 && (SP::FLOATING || k_of_q<SP, 0>(0) < 0 || k_of_q<SP, 0>(2) < 0 || k_of_q<SP, 0>(3) < 0 || k_of_q<SP, 0>(4) < 0)) return false;
+    auto trunk_q = [](int q) { const int k = k_of_q<SP, 0>(q); return k >= 0 && k < SP::N_TRUNK; };
+    if (E->reward_kind == 1 && (SP::FLOATING || !trunk_q(0) || !trunk_q(2) || !trunk_q(3) || !trunk_q(4))) return false;
     if (E->reward_kind == 2 && !SP::FLOATING) return false;
     return true;
   }
