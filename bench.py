@@ -289,7 +289,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": ["f32 (ABA) + f64 (kinematics, contact solve)", "f64", "f32"][args.precision], "data": "synthetic",
+        "dtype": ["f32 (ABA, factorisation, PGS) + f64 (kinematics, inertias, CRBA, Jacobians, LCP rhs)", "f64", "f32"][args.precision], "data": "synthetic",
         "config": {"workload": "laikago on plane, 4096 envs/GPU, full step + PD actuators (BASELINE.json configs[3])",
                    "envs_per_gpu": n, "global_envs": n * world, "dt": 1e-3, "parallelism": f"env-sharded x{world}, no data-path collective"
                    + (" + all-gather(reward,done)" if gathered is not None else ""),
@@ -303,8 +303,10 @@ def main():
                                     "api": "tds_b200_env_step_host (actions host->device, obs/reward/done device->host, pinned)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "tds_step_kernel<float,double,smem>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                     "note": "path is issue/latency bound (~27 kFLOP and 344 B per env-step); fp32-equivalent GFLOP/s reported beside it",
+                     "kernel": sim.kernel_name(), "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "note": "the step is not bandwidth bound: ~27 kFLOP and 344 B per env-step, one wave of 128 CTAs whose critical path "
+                             "is one warp's instruction stream (instruction fetch + dependent-issue latency, see DESIGN.md and "
+                             "profiles/); fp32-equivalent GFLOP/s reported beside the HBM figure",
                      "gflops": FLOPS_PER_ENV_STEP * n / kernel_s / 1e9},
         "clocks": clocks,
     }

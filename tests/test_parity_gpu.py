@@ -179,3 +179,46 @@ def test_device_auto_reset():
     rp = tds_b200.envs.laikago_reset_pose().astype(np.float32)
     assert np.array_equal(obs[::2, :18], np.tile(rp, (n // 2, 1))) and not obs[::2, 18:].any()
     assert np.abs(obs[1::2, 2] - 0.48).max() < 1e-3
+
+
+@pytest.mark.parametrize("kernel,expect", [("spec", "model-specialised"), ("role", "tds_stepr_kernel"), ("team", "tds_stept_kernel"),
+                                           ("world", "tds_stepw_kernel"), ("link", "tds_step_kernel")])
+def test_laikago_every_kernel_vs_c_oracle(kernel, expect, monkeypatch):
+    """The library picks the ahead-of-time specialised kernel for the Laikago model; the table-driven kernels stay
+    selectable (TDS_B200_KERNEL, read by tds_b200_create) and every one of them meets the same parity bar."""
+    monkeypatch.setenv("TDS_B200_KERNEL", kernel)
+    n = 256
+    model = load_model(fixture_path("laikago"))
+    w = wl.laikago_perturbed(n, seed=4242)
+    sim = tds_b200.BatchSim(model, n, **w["params"])
+    sim.set_env(tds_b200.envs.LAIKAGO_INITIAL_POSES, start_link=6, kp=100.0, kd=2.0, max_force=50.0)
+    out = sim.step_host(2, w["q"], w["qd"], w["action"], use_pd=True, want_contacts=True)
+    assert expect in sim.kernel_name()
+    P = port.make_params(**w["params"])
+    x = np.zeros((n, 51))
+    x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = w["q"], w["qd"], w["action"], [100.0, 2.0, 50.0]
+    ref = port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
+    assert rel_err(out["q"], ref[:, :18]) <= TOL
+    assert rel_err(out["qd"], ref[:, 18:36]) <= TOL
+    # torque-driven step and forward dynamics only (no actuator map needed)
+    tau = np.random.default_rng(1).uniform(-5, 5, size=(n, 18))
+    out2 = sim.step_host(2, w["q"], w["qd"], tau)
+    refs = [port.step(model, P, 2, w["q"][i], w["qd"][i], tau[i]) for i in range(0, n, 8)]
+    assert rel_err(out2["qd"][::8], np.array([r["qd"] for r in refs])) <= TOL
+    sim.set_precision(tds_b200.PREC_F64)
+    out3 = sim.step_host(0, w["q"], w["qd"], tau)
+    refs = [port.step(model, P, 0, w["q"][i], w["qd"][i], tau[i]) for i in range(0, n, 8)]
+    assert rel_err(out3["qdd"][::8], np.array([r["qdd"] for r in refs])) <= TOL
+
+
+def test_kernel_selection_fallbacks():
+    """Models without an ahead-of-time specialisation run on the table-driven kernels (tree: role / team kernel,
+    chain: one lane per environment)."""
+    sim = tds_b200.BatchSim(load_model(fixture_path("humanoid")), 64)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "humanoid.npz"))
+    sim.step_host(1, g["q_in"], g["qd_in"], None)
+    assert "tds_stepr_kernel" in sim.kernel_name() or "tds_stept_kernel" in sim.kernel_name()
+    sim = tds_b200.BatchSim(load_model(fixture_path("pendulum5")), 64)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pendulum5.npz"))
+    sim.step_host(1, g["q_in"], g["qd_in"], None)
+    assert "tds_stepw_kernel" in sim.kernel_name()

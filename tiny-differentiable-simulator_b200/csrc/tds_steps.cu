@@ -296,6 +296,21 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       });
     }
   }
+  // sines / cosines of every revolute joint of this role up front: independent dependency chains the scheduler can
+  // interleave (inside the kinematic chain they would be serialised behind the parent transform)
+  RC snv[SP::KMAX], csv[SP::KMAX];
+  sfor<NT, NLOC>([&](auto Kc) {
+    constexpr int k = decltype(Kc)::value;
+    if constexpr ((C::flags(k) & TDS_LF_REVOLUTE) != 0 && !(C::flags(k) & TDS_LF_FIXED))
+      sincos_t(CI(C::jtype(k)) == TDSJ_REVOLUTE_AXIS ? RC(qv[k]) * RC(0.5) : RC(qv[k]), &snv[k], &csv[k]);
+  });
+  if (role == 0) {
+    sfor<0, NT>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      if constexpr ((SP::L_FLAGS[0][k] & TDS_LF_REVOLUTE) != 0 && !(SP::L_FLAGS[0][k] & TDS_LF_FIXED))
+        sincos_t(CI(SP::L_JTYPE[0][k]) == TDSJ_REVOLUTE_AXIS ? RC(qv[k]) * RC(0.5) : RC(qv[k]), &snv[k], &csv[k]);
+    });
+  }
   const bool want_contacts = (mode == MODE_FULL) && SP::HAS_PLANE;
   const V3<RC> pn = v3<RC>(RC(CD(SP::PLANE_N[0])), RC(CD(SP::PLANE_N[1])), RC(CD(SP::PLANE_N[2])));
   TDSS_PHASE();  // 1
@@ -408,13 +423,11 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         const V3<RC> w = rot_axis();
         if constexpr (jt == TDSJ_REVOLUTE_AXIS) {
           const RC dl = sqrt_t(dot(axv, axv));
-          RC s, c;
-          sincos_t(qi * RC(0.5), &s, &c);
-          s = s / dl;
+          RC s = snv[k] / dl;
+          const RC c = csv[k];
           Ri = mul(Ri, quat_to_matrix<RC>(axv.x * s, axv.y * s, axv.z * s, c));
         } else {
-          RC s, c;
-          sincos_t(qi, &s, &c);
+          const RC s = snv[k], c = csv[k];
           const V3<RC> cx = col_x(Ri), cy = col_y(Ri), cz = col_z(Ri);
           if constexpr (jt == TDSJ_REVOLUTE_X) set_cols(Ri, cx, axpy(cz, s, cy * c), axpy(cy, -s, cz * c));
           else if constexpr (jt == TDSJ_REVOLUTE_Y) set_cols(Ri, axpy(cz, -s, cx * c), cy, axpy(cx, s, cz * c));
@@ -891,12 +904,20 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   }
   TDSS_PHASE();  // 5
   constexpr int YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);   // row layout: y_own | y_t | b[3] yy[3] 1/A[3]
+  // Few candidates: every candidate gets a row (zeros when it does not penetrate: x stays 0) and the sweep below is
+  // branch-free straight-line code; many candidates: only penetrating points are visited.
+  constexpr bool DENSE = SP::N_CAND <= 8;
   if (solve) {
     const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b
     const V3<RC> f1 = v3<RC>(RC(CD(SP::FR1[0])), RC(CD(SP::FR1[1])), RC(CD(SP::FR1[2])));
     const V3<RC> f2 = v3<RC>(RC(CD(SP::FR2[0])), RC(CD(SP::FR2[1])), RC(CD(SP::FR2[2])));
     const RS* const Lt = sp<RS>(smem, lane, L::LT);
     // contact rows of one penetrating point on local link kl (-1: base): normal, friction 1, friction 2
+    auto zero_row = [&](const int cand) {
+      RS* const row = sp<RS>(smem, lane, L::CON) + (size_t)cand * (L::CONW / L::RSW) * ST;
+#pragma unroll
+      for (int i = 0; i < BB + 9; ++i) row[i * ST] = RS(0);
+    };
     auto point_rows = [&](auto Kl, const int cand, const V3<RC>& xc, const RC dist) {
       constexpr int kl = decltype(Kl)::value;
       RS ro[3][NODA], rt[3][NTDA];
@@ -968,6 +989,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           constexpr int p = C::pt_local(k, i) + decltype(Jc)::value;
           const int cand = LG.cand[p];
           if ((my_active >> cand) & 1ull) point_rows(IC<k>{}, cand, cpos[p], cdist[p]);
+          else if constexpr (DENSE) zero_row(cand);
         });
       });
     });
@@ -981,6 +1003,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
             constexpr int cand = decltype(Cand0)::value + pts_before<SP>(gb, g) + decltype(Jc)::value;
             constexpr int lpt = decltype(Lpt0)::value + pts_before<SP>(gb, g) + decltype(Jc)::value;
             if ((my_active >> cand) & 1ull) point_rows(Kl, cand, tpos[lpt], tdist[lpt]);
+            else if constexpr (DENSE) zero_row(cand);
           });
         });
       };
@@ -1020,7 +1043,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
             // a point on a trunk / base geom has no subtree part
             constexpr bool own_part = !(owner == 0 && SP::CAND_LPT[g] < NPTR);
             constexpr int nod = own_part ? NOD : 0;
-            if ((team_active >> g) & 1ull) {
+            if (DENSE || ((team_active >> g) & 1ull)) {
               const RS* const row = sp<RS>(smem, lane, L::CON + g * L::CONW);
               RS yo[cmax(nod, 1)], yt[NTDA];
               RS yw = RS(0);
