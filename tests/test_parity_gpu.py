@@ -222,3 +222,30 @@ def test_kernel_selection_fallbacks():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pendulum5.npz"))
     sim.step_host(1, g["q_in"], g["qd_in"], None)
     assert "tds_stepw_kernel" in sim.kernel_name()
+
+
+def test_env_step_host_graph_replay_matches_eager():
+    """With pinned caller buffers tds_b200_env_step_host replays a captured CUDA graph from the third call on;
+    pageable buffers take the eager path.  Both must produce the same trajectory, bit for bit."""
+    import torch
+    n = 512
+    w = wl.laikago(n)
+    a_sim, b_sim = tds_b200.laikago_sim(n), tds_b200.laikago_sim(n)
+    a_sim.env_set_state(w["q"], w["qd"]); b_sim.env_set_state(w["q"], w["qd"])
+    act_p = torch.zeros((n, 12)).pin_memory(); obs_p = torch.zeros((n, 36)).pin_memory()
+    rew_p = torch.zeros(n).pin_memory(); done_p = torch.zeros(n).pin_memory()
+    obs = np.zeros((n, 36), dtype=np.float32); rew = np.zeros(n, dtype=np.float32); done = np.zeros(n, dtype=np.float32)
+    rng = np.random.default_rng(5)
+    for step in range(7):
+        act = rng.uniform(-0.4, 0.4, size=(n, 12)).astype(np.float32)
+        act_p.copy_(torch.from_numpy(act))
+        a_sim.env_step_host(act_p, obs_p, rew_p, done_p)
+        b_sim.env_step_host(act, obs, rew, done)
+        assert np.array_equal(obs_p.numpy(), obs), step
+        assert np.array_equal(rew_p.numpy(), rew) and np.array_equal(done_p.numpy(), done), step
+    # changing a parameter drops the captured graph (kernel parameters are baked into its nodes)
+    a_sim.set_auto_reset(True, tds_b200.envs.laikago_reset_pose()); b_sim.set_auto_reset(True, tds_b200.envs.laikago_reset_pose())
+    for step in range(4):
+        a_sim.env_step_host(act_p, obs_p, rew_p, done_p)
+        b_sim.env_step_host(act, obs, rew, done)
+        assert np.array_equal(obs_p.numpy(), obs)
