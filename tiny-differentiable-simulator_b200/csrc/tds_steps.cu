@@ -157,6 +157,35 @@ template <class SP> constexpr LegTab<SP> make_leg(int r) {
 }
 template <class SP> __device__ const LegTab<SP>& leg_tab(int role);
 
+// Trunk links of a CHAIN trunk (every trunk link's parent is the previous one) are swept by run-time loops in the
+// leaf->root and root->leaf passes: the loop body is fetched once and then runs out of the instruction caches,
+// which beats the unrolled form on a warp that streams alone (role 0).  What the body needs per link:
+template <class SP> struct TrunkTab {
+  static constexpr int NTA = SP::N_TRUNK > 0 ? SP::N_TRUNK : 1;
+  int fixed[NTA], massless[NTA], acc[NTA], ldof[NTA], qdidx[NTA], xw[NTA];
+  float sd[NTA][2];
+};
+template <class SP> __host__ __device__ constexpr bool trunk_is_chain() {
+  if (SP::N_TRUNK < 2) return false;
+  for (int k = 0; k < SP::N_TRUNK; ++k) {
+    if (SP::L_LPAR[0][k] != k - 1) return false;
+    if (SP::L_ACC[0][k] >= SP::N_ATT) return false;   // trunk-internal accumulators: not a chain
+  }
+  return true;
+}
+template <class SP> constexpr TrunkTab<SP> make_trunk() {
+  TrunkTab<SP> t{};
+  for (int k = 0; k < SP::N_TRUNK; ++k) {
+    const double* b = SP::L_RBIC[0][k];
+    t.fixed[k] = (SP::L_FLAGS[0][k] & TDS_LF_FIXED) ? 1 : 0;
+    t.massless[k] = (b[0] == 0.0 && b[4] == 0.0 && b[5] == 0.0 && b[6] == 0.0 && b[7] == 0.0 && b[8] == 0.0 && b[9] == 0.0) ? 1 : 0;
+    t.acc[k] = SP::L_ACC[0][k]; t.ldof[k] = SP::L_LDOF[0][k]; t.qdidx[k] = SP::L_QDIDX[0][k]; t.xw[k] = SP::L_XW[0][k];
+    t.sd[k][0] = (float)SP::L_SD[0][k][0]; t.sd[k][1] = (float)SP::L_SD[0][k][1];
+  }
+  return t;
+}
+template <class SP> __device__ const TrunkTab<SP>& trunk_tab();
+
 // shared-memory layout of one tile, 4-byte words per environment
 template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int RAW = sizeof(RA) / 4, RCW = sizeof(RC) / 4, RSW = sizeof(RS) / 4;
@@ -168,7 +197,8 @@ template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int TS = XW + (SP::N_XW_TEAM + 1) * XWW;          // trunk S [N_TRUNK][6] (RC)
   static constexpr int TLW = ev(10 * RCW + 14 * RAW);                // trunk record: rbi (10 RC) | U[6] 1/D u (8 RA) | v/c/a (6 RA)
   static constexpr int TL = TS + SP::N_TRUNK * 6 * RCW;
-  static constexpr int TQD = ev(TL + SP::N_TRUNK * TLW);             // trunk qd after the FD update (NTD floats)
+  static constexpr int TKS = ev(TL + SP::N_TRUNK * TLW);             // per trunk link: q, qd, tau (floats) for the run-time loops
+  static constexpr int TQD = ev(TKS + 3 * SP::N_TRUNK);              // trunk qd after the FD update (NTD floats)
   static constexpr int ACC_IC = ev(27 * RAW);
   static constexpr int ACCW = ev(ACC_IC + 10 * RCW);                 // attachment accumulator: Ia 21 + pa 6 (RA) | Ic 10 (RC)
   static constexpr int ACC = ev(TQD + NTD);                          // [T][N_ATT]; later the partial Schur complements [T][NTRI] (RS)
@@ -293,6 +323,18 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         constexpr int k = decltype(Kc)::value;
         if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED) && SP::L_QDIDX[0][k] >= off)
           tauv[k] = io.tau_in[(size_t)CI(SP::L_QDIDX[0][k] - off) * ns + e];
+      });
+    }
+  }
+  constexpr bool TRUNK_LOOP = trunk_is_chain<SP>();
+  float* const tk_q = sp<float>(smem, lane, L::TKS);
+  float* const tk_qd = tk_q + NT * ST;
+  float* const tk_tau = tk_qd + NT * ST;
+  if constexpr (TRUNK_LOOP) {
+    if (role == 0) {
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) { tk_q[k * ST] = qv[k]; tk_qd[k * ST] = qdv[k]; tk_tau[k * ST] = tauv[k]; }
       });
     }
   }
@@ -678,7 +720,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   };
   // ---- pass 2a: subtrees; roles 1.. publish their attachment accumulators ------------------------------------------------------------------
   sfor_rev<NT, NLOC>(pass2);
-  if (role != 0) {
+  if (TRUNK_LOOP || role != 0) {
     sfor<0, SP::N_ATT>([&](auto Sc) {
       constexpr int s = decltype(Sc)::value;
       RA* pa_ = acc_ptr_ra(role, s);
@@ -731,7 +773,79 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     a_prev = a;
   };
   if (role == 0) {
-    sfor_rev<0, NT>(pass2);
+    if constexpr (TRUNK_LOOP) {
+      // chain trunk, leaf -> root, run-time loop (same arithmetic as pass2 above; state in shared memory)
+      const TrunkTab<SP>& TK = trunk_tab<SP>();
+      RS* const Bs = sp<RS>(smem, lane, L::LT);   // trunk block of M, lower triangle (factorised in place later)
+      cA = abi_nz<RA>(); cP = sv_nz<RA>(); cC = rbi_nz<RC>();
+#pragma unroll 1
+      for (int k = NT - 1; k >= 0; --k) {
+        const Sv<RA> v = ld6<RA>(tl_v(k), ST);
+        Rbi<RC> Ic = cC; Abi<RA> Ia = cA; Sv<RA> pA = cP;
+        if (!TK.massless[k]) {
+          const Rbi<RC> own = ld_rbi<RC>(tl_rbi(k), ST);
+          const Rbi<RA> rb = cvt_rbi<RA>(own);
+          abi_add(Ia, abi_from_rbi(rb));
+          pA = pA + cross_mf(v, rbi_mul(rb, v));
+          rbi_add(Ic, own);
+        }
+        const int as = TK.acc[k];
+        if (as >= 0) {
+#pragma unroll
+          for (int r = 0; r < TT; ++r) {
+            Abi<RA> sa; Sv<RA> sv_;
+            acc_ld27<RA>(acc_ptr_ra(r, as), ST, sa, sv_);
+            abi_add(Ia, sa); pA = pA + sv_;
+            rbi_add(Ic, ld_rbi<RC>(acc_ptr_rc(r, as), ST));
+          }
+        }
+        Sv<RA> pa = pA;
+        if (!TK.fixed[k]) {
+          const Sv<RC> Sd = ld6<RC>(ts_S(k), ST);
+          const Sv<RA> S = cvt_sv<RA>(Sd);
+          const RA qdj = RA(tk_qd[k * ST]);
+          Sv<RA> vJ; vJ.top = S.top * qdj; vJ.bot = S.bot * qdj;
+          const Sv<RA> c = cross_mm(v, vJ);
+          const Sv<RA> U = abi_mul(Ia, S);
+          const RA D = dot(S, U);
+          const RA invD = RA(1) / D;
+          RA tau = RA(tk_tau[k * ST]);
+          tau -= RA(TK.sd[k][0]) * RA(tk_q[k * ST]);
+          tau -= RA(TK.sd[k][1]) * qdj;
+          const RA u = tau - dot(S, pA);
+          st6<RA>(tl_v(k), ST, c); st6<RA>(tl_u(k), ST, U); tl_u(k)[6 * ST] = invD; tl_u(k)[7 * ST] = u;
+          const V3<RA> ut = U.top * invD, ub = U.bot * invD;
+          Ia.I.xx -= U.top.x * ut.x; Ia.I.xy -= U.top.x * ut.y; Ia.I.xz -= U.top.x * ut.z;
+          Ia.I.yy -= U.top.y * ut.y; Ia.I.yz -= U.top.y * ut.z; Ia.I.zz -= U.top.z * ut.z;
+          Ia.H.xx -= U.top.x * ub.x; Ia.H.xy -= U.top.x * ub.y; Ia.H.xz -= U.top.x * ub.z;
+          Ia.H.yx -= U.top.y * ub.x; Ia.H.yy -= U.top.y * ub.y; Ia.H.yz -= U.top.y * ub.z;
+          Ia.H.zx -= U.top.z * ub.x; Ia.H.zy -= U.top.z * ub.y; Ia.H.zz -= U.top.z * ub.z;
+          Ia.M.xx -= U.bot.x * ub.x; Ia.M.xy -= U.bot.x * ub.y; Ia.M.xz -= U.bot.x * ub.z;
+          Ia.M.yy -= U.bot.y * ub.y; Ia.M.yz -= U.bot.y * ub.z; Ia.M.zz -= U.bot.z * ub.z;
+          const Sv<RA> Iac = abi_mul(Ia, c);
+          const RA uD = u * invD;
+          pa.top = pA.top + Iac.top + U.top * uD;
+          pa.bot = pA.bot + Iac.bot + U.bot * uD;
+          if (solve) {   // CRBA column: the ancestors of a chain link are all the links before it
+            const Sv<RC> F = rbi_mul(Ic, Sd);
+            const int ld = TK.ldof[k];
+            RS* const brow = Bs + (size_t)(ld * (ld + 1) / 2) * ST;
+            brow[ld * ST] = RS(dot(Sd, F));
+#pragma unroll 1
+            for (int j = k - 1; j >= 0; --j) {
+              const int lj = TK.ldof[j];
+              if (lj >= 0) brow[lj * ST] = RS(dot(ld6<RC>(ts_S(j), ST), F));
+            }
+            if constexpr (FLOAT) {
+              const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
+              brow[0] = RS(ft.x); brow[ST] = RS(ft.y); brow[2 * ST] = RS(ft.z);
+              brow[3 * ST] = RS(fb.x); brow[4 * ST] = RS(fb.y); brow[5 * ST] = RS(fb.z);
+            }
+          }
+        }
+        cA = Ia; cP = pa; cC = Ic;
+      }
+    } else sfor_rev<0, NT>(pass2);
     // base acceleration (forward_dynamics.hpp:218-243)
     Sv<RC> base_acc_b; base_acc_b.top = v3<RC>(RC(0), RC(0), RC(0)); base_acc_b.bot = base_acc_b.top;
     if constexpr (FLOAT) {
@@ -824,7 +938,31 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       a_prev.bot = v3<RA>(RA(-P.gravity[0]), RA(-P.gravity[1]), RA(-P.gravity[2]));
     }
     st6<RA>(xw_ra(0) + 6 * ST, ST, a_prev);
-    sfor<0, NT>(pass3);
+    if constexpr (TRUNK_LOOP) {
+      const TrunkTab<SP>& TK = trunk_tab<SP>();
+      Sv<RA> a = a_prev;
+#pragma unroll 1
+      for (int k = 0; k < NT; ++k) {
+        if (!TK.fixed[k]) {
+          const Sv<RA> c = ld6<RA>(tl_v(k), ST), U = ld6<RA>(tl_u(k), ST);
+          const RA invD = tl_u(k)[6 * ST], u = tl_u(k)[7 * ST];
+          a = a + c;
+          const RA qdd = invD * (u - dot(U, a));
+          const Sv<RA> S = cvt_sv<RA>(ld6<RC>(ts_S(k), ST));
+          a.top = axpy(S.top, qdd, a.top);
+          a.bot = axpy(S.bot, qdd, a.bot);
+          if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)TK.qdidx[k] * ns + e] = (float)qdd; }
+          else tk_qd[k * ST] = (float)(RA(tk_qd[k * ST]) + qdd * dtA);
+        }
+        const int xs = TK.xw[k];
+        if (xs >= 0) st6<RA>(xw_ra(xs + 1) + 6 * ST, ST, a);
+      }
+      a_prev = a;
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) qdv[k] = tk_qd[k * ST];
+      });
+    } else sfor<0, NT>(pass3);
     if constexpr (FLOAT) {   // forward_dynamics.hpp:317-322 (gravity added un-rotated), integrator.hpp:153-163
       const RC qb[6] = {base_acc_b.top.x, base_acc_b.top.y, base_acc_b.top.z, base_acc_b.bot.x + RC(P.gravity[0]),
                         base_acc_b.bot.y + RC(P.gravity[1]), base_acc_b.bot.z + RC(P.gravity[2])};
@@ -883,6 +1021,12 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     __syncthreads();
     RS* const Lt = sp<RS>(smem, lane, L::LT);
     if (role == 0) {   // S = B - sum over the roles of G^T G, then S = L_t L_t^T
+      if constexpr (TRUNK_LOOP) {   // rows of the trunk links were written to shared memory by the run-time loop
+        sfor<(FLOAT ? 6 : 0), NTD>([&](auto Ic_) {
+          constexpr int i = decltype(Ic_)::value;
+          sfor<0, i + 1>([&](auto Jc) { constexpr int j = decltype(Jc)::value; Bm[tri(i, j)] = Lt[tri(i, j) * ST]; });
+        });
+      }
       sfor<0, NTRI>([&](auto Ic_) {
         constexpr int i = decltype(Ic_)::value;
         const RS* p = sp<RS>(smem, lane, L::ACC);
@@ -1210,6 +1354,8 @@ tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant_
 __constant__ LegTab<SpecLaikago> c_legs_laikago[TDS_TEAM_T] = {make_leg<SpecLaikago>(0), make_leg<SpecLaikago>(1), make_leg<SpecLaikago>(2),
                                                                 make_leg<SpecLaikago>(3)};
 template <> __device__ __forceinline__ const LegTab<SpecLaikago>& leg_tab<SpecLaikago>(int role) { return c_legs_laikago[role]; }
+__constant__ TrunkTab<SpecLaikago> c_trunk_laikago = make_trunk<SpecLaikago>();
+template <> __device__ __forceinline__ const TrunkTab<SpecLaikago>& trunk_tab<SpecLaikago>() { return c_trunk_laikago; }
 
 template <class SP> struct SpecHost {
   static bool matches(const DevModel* D, const EnvParams* E) {
