@@ -35,6 +35,9 @@ if kern in ("role", "spec"):   # one record per (tile, role): show every role, p
         end = np.median((b[:, :, k + 1] - t0).astype(np.float64), axis=0)
         print(f"  {nm:18s} " + " ".join(f"{x:8.0f}" for x in end) + f" | {end[0] - prev[0]:8.0f}")
         prev = end
+    if kern == "spec":
+        ex = np.median((b[:, 0, 10:14] - t0).astype(np.float64), axis=0)
+        print("  role 0 extra stamps (cycles since tile start): pass1a start %.0f end %.0f | pass2a end %.0f | trunk leaf->root end %.0f" % (ex[2], ex[3], ex[0], ex[1]))
     sys.exit(0)
 
 d = np.diff(buf[:, :K + 1], axis=1).astype(np.float64)

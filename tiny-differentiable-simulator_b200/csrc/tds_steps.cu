@@ -249,6 +249,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   char* const priv = smem + (size_t)(L::SHARED + role * L::PRIV) * ST * 4;
   int phase_id = 0;
 #define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
+#define TDSS_STAMP(slot) do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + role) * 16 + (slot)] = clock64(); } while (0)
   TDSS_PHASE();
   auto xw_rc = [&](int slot) { return sp<RC>(smem, lane, L::XW + slot * L::XWW); };                  // R[9], p[3]
   auto xw_ra = [&](int slot) { return sp<RA>(smem, lane, L::XW + slot * L::XWW + 12 * RCW); };       // v[6], a[6]
@@ -541,6 +542,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   RC* const sO = sp<RC>(smem, lane, L::O);
   RC* const sRb = sp<RC>(smem, lane, L::RB);
   if (role == 0) {
+    TDSS_STAMP(12);   // role 0: start of pass 1a
     M3<RC> Rb0 = m3_identity<RC>();
     O = v3<RC>(RC(0), RC(0), RC(0));
     if constexpr (FLOAT) {
@@ -580,6 +582,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     st9<RC>(xw_rc(0), ST, R_prev); st3<RC>(xw_rc(0) + 9 * ST, ST, p_prev); st6<RA>(xw_ra(0), ST, v_prev);
     if (want_contacts) emit_trunk_geoms(IC<SP::GEOM_BEGIN[0]>{}, IC<SP::GEOM_BEGIN[1]>{}, IC<0>{}, IC<0>{}, R_prev, p_prev);
     sfor<0, NT>(pass1);
+    TDSS_STAMP(13);   // role 0: end of pass 1a
   }
   __syncthreads();
   // ---- pass 1b: every role walks its subtree --------------------------------------------------------------------------------------
@@ -734,6 +737,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     });
   }
   __syncthreads();
+  TDSS_STAMP(10);   // end of pass 2a (all roles, after the barrier)
 
   // ---- pass 2b + base + pass 3a: role 0 finishes the trunk --------------------------------------------------------------------------------
   const RA dtA = RA(P.dt);
@@ -831,10 +835,10 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
             const int ld = TK.ldof[k];
             RS* const brow = Bs + (size_t)(ld * (ld + 1) / 2) * ST;
             brow[ld * ST] = RS(dot(Sd, F));
-#pragma unroll 1
-            for (int j = k - 1; j >= 0; --j) {
+#pragma unroll
+            for (int j = 0; j < NT - 1; ++j) {   // unrolled: independent dot products, static addresses
               const int lj = TK.ldof[j];
-              if (lj >= 0) brow[lj * ST] = RS(dot(ld6<RC>(ts_S(j), ST), F));
+              if (j < k && lj >= 0) brow[lj * ST] = RS(dot(ld6<RC>(ts_S(j), ST), F));
             }
             if constexpr (FLOAT) {
               const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
@@ -846,6 +850,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         cA = Ia; cP = pa; cC = Ic;
       }
     } else sfor_rev<0, NT>(pass2);
+    TDSS_STAMP(11);   // role 0: end of the trunk's leaf->root pass
     // base acceleration (forward_dynamics.hpp:218-243)
     Sv<RC> base_acc_b; base_acc_b.top = v3<RC>(RC(0), RC(0), RC(0)); base_acc_b.bot = base_acc_b.top;
     if constexpr (FLOAT) {
@@ -1338,6 +1343,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   }
   TDSS_PHASE();  // 9
 #undef TDSS_PHASE
+#undef TDSS_STAMP
 }
 
 template <class SP, typename RA, typename RC, typename RS>
