@@ -249,3 +249,25 @@ def test_env_step_host_graph_replay_matches_eager():
         a_sim.env_step_host(act_p, obs_p, rew_p, done_p)
         b_sim.env_step_host(act, obs, rew, done)
         assert np.array_equal(obs_p.numpy(), obs)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 100])
+def test_ragged_batch_sizes(n):
+    """Batches that do not fill a tile of 32 environments (and the single-environment case the reference's
+    serial stepper uses): the padded lanes must neither be written nor disturb the live ones."""
+    model = load_model(fixture_path("laikago"))
+    w = wl.laikago_perturbed(128, seed=99)
+    sim = tds_b200.BatchSim(model, n, **w["params"])
+    sim.set_env(tds_b200.envs.LAIKAGO_INITIAL_POSES, start_link=6, kp=100.0, kd=2.0, max_force=50.0)
+    q, qd, act = w["q"][:n], w["qd"][:n], w["action"][:n]
+    out = sim.step_host(2, q, qd, act, use_pd=True, want_contacts=True)
+    big = tds_b200.BatchSim(model, 128, **w["params"])
+    big.set_env(tds_b200.envs.LAIKAGO_INITIAL_POSES, start_link=6, kp=100.0, kd=2.0, max_force=50.0)
+    ref = big.step_host(2, w["q"], w["qd"], w["action"], use_pd=True, want_contacts=True)
+    assert np.array_equal(out["q"], ref["q"][:n]) and np.array_equal(out["qd"], ref["qd"][:n])
+    assert np.array_equal(out["contact_dist"], ref["contact_dist"][:n])
+    P = port.make_params(**w["params"])
+    x = np.zeros((n, 51))
+    x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = q, qd, act, [100.0, 2.0, 50.0]
+    o = port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
+    assert rel_err(out["qd"], o[:, 18:36]) <= TOL

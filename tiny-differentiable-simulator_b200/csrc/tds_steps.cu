@@ -35,6 +35,21 @@ template <int V> struct IC { static constexpr int value = V; };
 // model tables may only be read in constant expressions from device code: force the evaluation
 #define CI(...) (IC<(__VA_ARGS__)>::value)
 #define CD(...) ([]() { constexpr double cd_v_ = (__VA_ARGS__); return cd_v_; }())
+// dot product with a compile-time direction: zero components vanish, +-1 components cost no multiply
+#define CDOT3(ax, ay, az, v)                                                                                            \
+  ([&]() {                                                                                                              \
+    using T_ = decltype((v).x);                                                                                         \
+    constexpr double a_ = (ax), b_ = (ay), c_ = (az);                                                                   \
+    T_ s_ = T_(-0.0);                                                                                                   \
+    if constexpr (a_ == 1.0) s_ += (v).x; else if constexpr (a_ == -1.0) s_ -= (v).x; else if constexpr (a_ != 0.0) s_ += T_(a_) * (v).x; \
+    if constexpr (b_ == 1.0) s_ += (v).y; else if constexpr (b_ == -1.0) s_ -= (v).y; else if constexpr (b_ != 0.0) s_ += T_(b_) * (v).y; \
+    if constexpr (c_ == 1.0) s_ += (v).z; else if constexpr (c_ == -1.0) s_ -= (v).z; else if constexpr (c_ != 0.0) s_ += T_(c_) * (v).z; \
+    return s_;                                                                                                          \
+  }())
+#define DOT_PN(v) CDOT3(SP::PLANE_N[0], SP::PLANE_N[1], SP::PLANE_N[2], v)
+#define DOT_NB(v) CDOT3(-SP::PLANE_N[0], -SP::PLANE_N[1], -SP::PLANE_N[2], v)
+#define DOT_F1(v) CDOT3(SP::FR1[0], SP::FR1[1], SP::FR1[2], v)
+#define DOT_F2(v) CDOT3(SP::FR2[0], SP::FR2[1], SP::FR2[2], v)
 template <int B, int E, class F> TDS_D void sfor(F&& f) {
   if constexpr (B < E) { f(IC<B>{}); sfor<B + 1, E>(f); }
 }
@@ -328,6 +343,9 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     }
   }
   constexpr bool TRUNK_LOOP = trunk_is_chain<SP>();
+  // with a looped chain trunk, the rows of the trunk block of M (CRBA) are computed by roles 1.. while role 0 runs the
+  // trunk's ABA sweep: they would idle at the barrier otherwise
+  constexpr bool CRBA_HELPERS = TRUNK_LOOP && TT > 1;
   float* const tk_q = sp<float>(smem, lane, L::TKS);
   float* const tk_qd = tk_q + NT * ST;
   float* const tk_tau = tk_qd + NT * ST;
@@ -364,7 +382,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   V3<RC> tpos[NPTRA]; RC tdist[NPTRA];   // role 0: points on base / trunk geoms, numbered as in CAND_LPT
   RC plane_off; V3<RC> O;
   auto emit_point = [&](const V3<RC>& pos, const RC rad, const int cand, V3<RC>& out_pos, RC& out_dist) {
-    const RC dist = dot(pos, pn) + plane_off - rad;
+    const RC dist = DOT_PN(pos) + plane_off - rad;
     if (io.contact_dist && live) io.contact_dist[(size_t)cand * ns + e] = (float)dist;
     out_pos = pos - pn * rad;                                // world_point_on_b, relative to O
     out_dist = dist;
@@ -569,7 +587,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         }
       });
     }
-    plane_off = dot(O, pn) - RC(CD(SP::PLANE_C[0]));
+    plane_off = DOT_PN(O) - RC(CD(SP::PLANE_C[0]));
     st3<RC>(sO, ST, O); sO[3 * ST] = plane_off;
     if constexpr (FLOAT) st9<RC>(sRb, ST, Rb0);
     R_prev = Rb0;
@@ -776,6 +794,39 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     }
     a_prev = a;
   };
+  if constexpr (CRBA_HELPERS) {
+    if (role != 0 && solve) {
+      const TrunkTab<SP>& TK = trunk_tab<SP>();
+      RS* const Bs = sp<RS>(smem, lane, L::LT);
+      Rbi<RC> Ic = rbi_nz<RC>();   // composite inertia of the chain from link k to the leaves
+#pragma unroll 1
+      for (int k = NT - 1; k >= 0; --k) {
+        if (!TK.massless[k]) rbi_add(Ic, ld_rbi<RC>(tl_rbi(k), ST));
+        const int as = TK.acc[k];
+        if (as >= 0) {
+#pragma unroll
+          for (int r = 0; r < TT; ++r) rbi_add(Ic, ld_rbi<RC>(acc_ptr_rc(r, as), ST));
+        }
+        if (!TK.fixed[k] && (k % (TT - 1)) == role - 1) {   // rows are dealt round-robin to roles 1..
+          const Sv<RC> Sd = ld6<RC>(ts_S(k), ST);
+          const Sv<RC> F = rbi_mul(Ic, Sd);
+          const int ld = TK.ldof[k];
+          RS* const brow = Bs + (size_t)(ld * (ld + 1) / 2) * ST;
+          brow[ld * ST] = RS(dot(Sd, F));
+#pragma unroll
+          for (int j = 0; j < NT - 1; ++j) {
+            const int lj = TK.ldof[j];
+            if (j < k && lj >= 0) brow[lj * ST] = RS(dot(ld6<RC>(ts_S(j), ST), F));
+          }
+          if constexpr (FLOAT) {
+            const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
+            brow[0] = RS(ft.x); brow[ST] = RS(ft.y); brow[2 * ST] = RS(ft.z);
+            brow[3 * ST] = RS(fb.x); brow[4 * ST] = RS(fb.y); brow[5 * ST] = RS(fb.z);
+          }
+        }
+      }
+    }
+  }
   if (role == 0) {
     if constexpr (TRUNK_LOOP) {
       // chain trunk, leaf -> root, run-time loop (same arithmetic as pass2 above; state in shared memory)
@@ -830,7 +881,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           const RA uD = u * invD;
           pa.top = pA.top + Iac.top + U.top * uD;
           pa.bot = pA.bot + Iac.bot + U.bot * uD;
-          if (solve) {   // CRBA column: the ancestors of a chain link are all the links before it
+          if (solve && !CRBA_HELPERS) {   // CRBA column: the ancestors of a chain link are all the links before it
             const Sv<RC> F = rbi_mul(Ic, Sd);
             const int ld = TK.ldof[k];
             RS* const brow = Bs + (size_t)(ld * (ld + 1) / 2) * ST;
@@ -1057,9 +1108,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // branch-free straight-line code; many candidates: only penetrating points are visited.
   constexpr bool DENSE = SP::N_CAND <= 8;
   if (solve) {
-    const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b
-    const V3<RC> f1 = v3<RC>(RC(CD(SP::FR1[0])), RC(CD(SP::FR1[1])), RC(CD(SP::FR1[2])));
-    const V3<RC> f2 = v3<RC>(RC(CD(SP::FR2[0])), RC(CD(SP::FR2[1])), RC(CD(SP::FR2[2])));
+    // contact directions: world_normal_on_b = -plane normal, friction directions from plane_space (compile-time constants)
     const RS* const Lt = sp<RS>(smem, lane, L::LT);
     // contact rows of one penetrating point on local link kl (-1: base): normal, friction 1, friction 2
     auto zero_row = [&](const int cand) {
@@ -1083,7 +1132,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
                                 v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-          rt[0][k] = RS(dot(nbv, cols[k])); rt[1][k] = RS(dot(f1, cols[k])); rt[2][k] = RS(dot(f2, cols[k]));
+          rt[0][k] = RS(DOT_NB(cols[k])); rt[1][k] = RS(DOT_F1(cols[k])); rt[2][k] = RS(DOT_F2(cols[k]));
           vel = vel + cols[k] * RC(tqd[k * ST]);
         }
       }
@@ -1093,15 +1142,15 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         if constexpr (lj >= 0 && (j == kl || is_anc<SP, 0>(j, kl))) {
           const Sv<RC> S = S_of(IC<j>{});
           const V3<RC> col = S.bot + cross(S.top, xc);
-          const RS c0 = RS(dot(nbv, col)), c1 = RS(dot(f1, col)), c2 = RS(dot(f2, col));
+          const RS c0 = RS(DOT_NB(col)), c1 = RS(DOT_F1(col)), c2 = RS(DOT_F2(col));
           if constexpr (lj >= NTD) { ro[0][lj - NTD] = c0; ro[1][lj - NTD] = c1; ro[2][lj - NTD] = c2; vel = vel + col * RC(qdv[j]); }
           else { rt[0][lj] = c0; rt[1][lj] = c1; rt[2][lj] = c2; vel = vel + col * RC(tqd[lj * ST]); }
         }
       });
       RS* const row = sp<RS>(smem, lane, L::CON) + (size_t)cand * (L::CONW / L::RSW) * ST;
-      row[(BB + 0) * ST] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
-      row[(BB + 1) * ST] = RS(dot(f1, vel));
-      row[(BB + 2) * ST] = RS(dot(f2, vel));
+      row[(BB + 0) * ST] = RS((RC(1) + RC(P.restitution)) * DOT_NB(vel) - RC(P.erp) * dist / RC(P.dt));
+      row[(BB + 1) * ST] = RS(DOT_F1(vel));
+      row[(BB + 2) * ST] = RS(DOT_F2(vel));
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         // y_own = L_k^-1 r_own ;  y_t = L_t^-1 (r_t - G^T y_own)   (a trunk point has no own part)
