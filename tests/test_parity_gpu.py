@@ -271,3 +271,23 @@ def test_ragged_batch_sizes(n):
     x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = q, qd, act, [100.0, 2.0, 50.0]
     o = port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
     assert rel_err(out["qd"], o[:, 18:36]) <= TOL
+
+
+def test_env_step_host_packed_outputs():
+    """obs | rewards | dones adjacent in one pinned block take the single-copy path; results equal the three-buffer path."""
+    import torch
+    n = 256
+    w = wl.laikago(n)
+    a_sim, b_sim = tds_b200.laikago_sim(n), tds_b200.laikago_sim(n)
+    a_sim.env_set_state(w["q"], w["qd"]); b_sim.env_set_state(w["q"], w["qd"])
+    blk = torch.zeros(n * 38).pin_memory()
+    obs_p, rew_p, done_p = blk[:n * 36].view(n, 36), blk[n * 36:n * 37], blk[n * 37:]
+    act_p = torch.zeros((n, 12)).pin_memory()
+    obs = np.zeros((n, 36), dtype=np.float32); rew = np.zeros(n, dtype=np.float32); done = np.zeros(n, dtype=np.float32)
+    rng = np.random.default_rng(11)
+    for step in range(6):
+        act = rng.uniform(-0.4, 0.4, size=(n, 12)).astype(np.float32)
+        act_p.copy_(torch.from_numpy(act))
+        a_sim.env_step_host(act_p, obs_p, rew_p, done_p)
+        b_sim.env_step_host(act, obs, rew, done)
+        assert np.array_equal(obs_p.numpy(), obs) and np.array_equal(rew_p.numpy(), rew) and np.array_equal(done_p.numpy(), done), step

@@ -64,6 +64,23 @@ __global__ void soa_to_aos_kernel(const float* __restrict__ in, TO* __restrict__
   for (int k = 0; k < dim; ++k) out[(size_t)e * out_stride + out_off + k] = (TO)in[(size_t)k * ns + e];
 }
 
+// obs[e] = q | qd (AoS), and optionally reward / done appended behind the n observation rows (one contiguous
+// block -> one device->host copy when the caller's three output buffers are adjacent)
+__global__ void pack_env_out_kernel(const float* __restrict__ q, const float* __restrict__ qd, const float* __restrict__ reward,
+                                    const float* __restrict__ done, float* __restrict__ out, int n_q, int n_qd, int n, int ns,
+                                    int with_tail) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float* o = out + (size_t)e * (n_q + n_qd);
+  for (int k = 0; k < n_q; ++k) o[k] = q[(size_t)k * ns + e];
+  for (int k = 0; k < n_qd; ++k) o[n_q + k] = qd[(size_t)k * ns + e];
+  if (with_tail) {
+    float* tail = out + (size_t)n * (n_q + n_qd);
+    tail[e] = reward[e];
+    tail[n + e] = done[e];
+  }
+}
+
 // TinyMatrix3x3::getRotation, src/math/tiny/tiny_matrix3x3.h:434-466 (used for the visual outputs)
 __device__ void matrix_to_quat_dev(const float* m, float* q) {
   float trace = m[0] + m[4] + m[8];
@@ -554,7 +571,9 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   const int n = s->n, ns = s->ns, na = s->E.n_act, nobs = M.n_q + M.n_qd;
   // device staging: actions AoS in | obs AoS out | reward | done
   const size_t in_b = sizeof(float) * (size_t)n * na, obs_b = sizeof(float) * (size_t)n * nobs;
-  int rc = ensure_stage(s, in_b + obs_b, 0);
+  // obs | rewards | dones adjacent in the caller's memory: pack them on the device and copy once
+  const bool packed = obs && rewards == obs + (size_t)n * nobs && dones == rewards + n;
+  int rc = ensure_stage(s, in_b + obs_b + sizeof(float) * 2 * (size_t)n, 0);
   if (rc) return rc;
   float* d_in = (float*)s->stage_dev;
   float* d_obs = (float*)((char*)s->stage_dev + in_b);
@@ -567,12 +586,13 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
                                  nullptr, nullptr, sm);
     if (r) return r;
     if (obs) {
-      soa_to_aos_kernel<float><<<B, T, 0, sm>>>(s->q, d_obs, nobs, 0, M.n_q, n, ns);
-      soa_to_aos_kernel<float><<<B, T, 0, sm>>>(s->qd, d_obs, nobs, M.n_q, M.n_qd, n, ns);
-      CUDA_TRY(cudaMemcpyAsync(obs, d_obs, obs_b, cudaMemcpyDeviceToHost, sm));
+      pack_env_out_kernel<<<B, T, 0, sm>>>(s->q, s->qd, s->reward, s->done, d_obs, M.n_q, M.n_qd, n, ns, packed ? 1 : 0);
+      CUDA_TRY(cudaMemcpyAsync(obs, d_obs, obs_b + (packed ? sizeof(float) * 2 * (size_t)n : 0), cudaMemcpyDeviceToHost, sm));
     }
-    if (rewards) CUDA_TRY(cudaMemcpyAsync(rewards, s->reward, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
-    if (dones) CUDA_TRY(cudaMemcpyAsync(dones, s->done, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
+    if (!packed) {
+      if (rewards) CUDA_TRY(cudaMemcpyAsync(rewards, s->reward, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
+      if (dones) CUDA_TRY(cudaMemcpyAsync(dones, s->done, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
+    }
     return 0;
   };
   const void* key[4] = {actions, obs, rewards, dones};
