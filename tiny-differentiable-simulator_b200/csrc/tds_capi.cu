@@ -181,6 +181,8 @@ struct tds_b200_sim {
   long long* phase_clk = nullptr;  // profiling only (tds_b200_debug_phase_clocks)
   // tds_b200_env_step_host with pinned caller buffers: the copy / transpose / step / copy sequence is captured once
   // per buffer set and replayed (one graph launch instead of nine stream operations)
+  // set around the step launch of tds_b200_env_step_host when the specialised kernel serves the host layouts itself
+  const float* io_act_aos = nullptr; float* io_obs_aos = nullptr; float* io_obs_tail = nullptr;
   const void* g_key[4] = {nullptr, nullptr, nullptr, nullptr};
   int g_seen = 0;
   cudaGraphExec_t g_exec = nullptr;
@@ -406,6 +408,7 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.q_out = q_out; io.qd_out = qd_out; io.qdd_out = qdd_out;
   io.reward = reward; io.done = done; io.contact_dist = contact_dist; io.link_xf = link_xf;
   io.phase_clk = s->phase_clk;
+  io.act_aos = s->io_act_aos; io.obs_aos = s->io_obs_aos; io.obs_tail = s->io_obs_tail;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
@@ -579,13 +582,20 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   float* d_obs = (float*)((char*)s->stage_dev + in_b);
   cudaStream_t sm = s->stream;
   const int T = 128, B = (n + T - 1) / T;
+  // the specialised kernel reads environment-major actions and writes the observation block itself
+  const bool direct = s->kernel_req == 4 && s->spec_ok && tds_spec_smem_bytes(s->precision) <= (size_t)s->max_smem_optin;
   auto enqueue = [&]() -> int {
     CUDA_TRY(cudaMemcpyAsync(d_in, actions, in_b, cudaMemcpyHostToDevice, sm));
-    aos_to_soa_kernel<float><<<B, T, 0, sm>>>(d_in, na, 0, s->act, na, n, ns);
+    if (direct) {
+      s->io_act_aos = d_in; s->io_obs_aos = obs ? d_obs : nullptr; s->io_obs_tail = (obs && packed) ? d_obs + (size_t)n * nobs : nullptr;
+    } else aos_to_soa_kernel<float><<<B, T, 0, sm>>>(d_in, na, 0, s->act, na, n, ns);
     int r = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, s->reward, s->done,
                                  nullptr, nullptr, sm);
+    s->io_act_aos = nullptr; s->io_obs_aos = nullptr; s->io_obs_tail = nullptr;
     if (r) return r;
-    if (obs) {
+    if (obs && direct) {
+      CUDA_TRY(cudaMemcpyAsync(obs, d_obs, obs_b + (packed ? sizeof(float) * 2 * (size_t)n : 0), cudaMemcpyDeviceToHost, sm));
+    } else if (obs) {
       pack_env_out_kernel<<<B, T, 0, sm>>>(s->q, s->qd, s->reward, s->done, d_obs, M.n_q, M.n_qd, n, ns, packed ? 1 : 0);
       CUDA_TRY(cudaMemcpyAsync(obs, d_obs, obs_b + (packed ? sizeof(float) * 2 * (size_t)n : 0), cudaMemcpyDeviceToHost, sm));
     }

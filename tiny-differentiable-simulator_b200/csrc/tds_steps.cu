@@ -175,9 +175,18 @@ template <class SP> __device__ const LegTab<SP>& leg_tab(int role);
 // Trunk links of a CHAIN trunk (every trunk link's parent is the previous one) are swept by run-time loops in the
 // leaf->root and root->leaf passes: the loop body is fetched once and then runs out of the instruction caches,
 // which beats the unrolled form on a warp that streams alone (role 0).  What the body needs per link:
+template <class SP> __host__ __device__ constexpr bool trunk_massless(int k) {
+  const double* b = SP::L_RBIC[0][k];
+  return b[0] == 0.0 && b[4] == 0.0 && b[5] == 0.0 && b[6] == 0.0 && b[7] == 0.0 && b[8] == 0.0 && b[9] == 0.0;
+}
+template <class SP> __host__ __device__ constexpr int trunk_rbi_slot(int k) {   // slot among the massive trunk links
+  int c = 0;
+  for (int j = 0; j < k; ++j) if (!trunk_massless<SP>(j)) ++c;
+  return c;
+}
 template <class SP> struct TrunkTab {
   static constexpr int NTA = SP::N_TRUNK > 0 ? SP::N_TRUNK : 1;
-  int fixed[NTA], massless[NTA], acc[NTA], ldof[NTA], qdidx[NTA], xw[NTA];
+  int fixed[NTA], massless[NTA], acc[NTA], ldof[NTA], qdidx[NTA], xw[NTA], rbi_slot[NTA];
   float sd[NTA][2];
 };
 template <class SP> __host__ __device__ constexpr bool trunk_is_chain() {
@@ -194,6 +203,7 @@ template <class SP> constexpr TrunkTab<SP> make_trunk() {
     const double* b = SP::L_RBIC[0][k];
     t.fixed[k] = (SP::L_FLAGS[0][k] & TDS_LF_FIXED) ? 1 : 0;
     t.massless[k] = (b[0] == 0.0 && b[4] == 0.0 && b[5] == 0.0 && b[6] == 0.0 && b[7] == 0.0 && b[8] == 0.0 && b[9] == 0.0) ? 1 : 0;
+    t.rbi_slot[k] = trunk_rbi_slot<SP>(k);
     t.acc[k] = SP::L_ACC[0][k]; t.ldof[k] = SP::L_LDOF[0][k]; t.qdidx[k] = SP::L_QDIDX[0][k]; t.xw[k] = SP::L_XW[0][k];
     t.sd[k][0] = (float)SP::L_SD[0][k][0]; t.sd[k][1] = (float)SP::L_SD[0][k][1];
   }
@@ -210,19 +220,22 @@ template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int XWW = ev(12 * RCW + 12 * RAW);                // slot: R[9] p[3] (RC) | v[6] a[6] (RA)
   static constexpr int XW = RB + 10 * RCW;                           // slot 0 = base, then the published trunk links
   static constexpr int TS = XW + (SP::N_XW_TEAM + 1) * XWW;          // trunk S [N_TRUNK][6] (RC)
-  static constexpr int TLW = ev(10 * RCW + 14 * RAW);                // trunk record: rbi (10 RC) | U[6] 1/D u (8 RA) | v/c/a (6 RA)
+  static constexpr int TLW = ev(14 * RAW);                           // trunk record: U[6] 1/D u (8 RA) | v/c/a (6 RA)
   static constexpr int TL = TS + SP::N_TRUNK * 6 * RCW;
-  static constexpr int TKS = ev(TL + SP::N_TRUNK * TLW);             // per trunk link: q, qd, tau (floats) for the run-time loops
+  static constexpr int TLR = ev(TL + SP::N_TRUNK * TLW);             // rigid inertias (10 RC) of the trunk links that have mass
+  static constexpr int TKS = ev(TLR + trunk_rbi_slot<SP>(SP::N_TRUNK) * 10 * RCW);   // per trunk link: q, qd, tau (floats)
   static constexpr int TQD = ev(TKS + 3 * SP::N_TRUNK);              // trunk qd after the FD update (NTD floats)
   static constexpr int ACC_IC = ev(27 * RAW);
   static constexpr int ACCW = ev(ACC_IC + 10 * RCW);                 // attachment accumulator: Ia 21 + pa 6 (RA) | Ic 10 (RC)
   static constexpr int ACC = ev(TQD + NTD);                          // [T][N_ATT]; later the partial Schur complements [T][NTRI] (RS)
   static constexpr int PW = ev(NTRI * RSW);
-  static constexpr int ACC_SZ = cmax(TT * cmax(SP::N_ATT, 1) * ACCW, TT * PW);
+  static constexpr int CONW = ev((3 * (NOD + NTD) + 9) * RSW);       // contact row: y_own[3][NOD] y_t[3][NTD] b[3] yy[3] 1/A[3]
+  // one region, three tenants in time: attachment accumulators (until the trunk sweep), partial Schur complements
+  // (until the trunk factorisation), contact rows (from the row phase on); barriers separate the tenants
+  static constexpr int ACC_SZ = cmax(cmax(TT * cmax(SP::N_ATT, 1) * ACCW, TT * PW), cmax(SP::N_CAND, 1) * CONW);
   static constexpr int LT = ACC + ACC_SZ;                            // trunk factor, lower triangle with inverted diagonal (RS)
-  static constexpr int CON = ev(LT + NTRI * RSW);                    // contact rows per candidate
-  static constexpr int CONW = ev((3 * (NOD + NTD) + 9) * RSW);       // y_own[3][NOD] y_t[3][NTD] b[3] yy[3] 1/A[3]
-  static constexpr int ZT = CON + cmax(SP::N_CAND, 1) * CONW;        // z_t[NTD] (RS)
+  static constexpr int CON = ACC;                                    // contact rows per candidate (see ACC_SZ)
+  static constexpr int ZT = ev(LT + NTRI * RSW);                     // z_t[NTD] (RS)
   static constexpr int WO = ev(ZT + NTD * RSW);                      // w_own[T][NOD] (RS)
   static constexpr int FLG = ev(WO + TT * NOD * RSW);                // active masks (2 words per role), done flag
   static constexpr int SHARED = ev(FLG + 2 * TT + 2);
@@ -268,9 +281,9 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   TDSS_PHASE();
   auto xw_rc = [&](int slot) { return sp<RC>(smem, lane, L::XW + slot * L::XWW); };                  // R[9], p[3]
   auto xw_ra = [&](int slot) { return sp<RA>(smem, lane, L::XW + slot * L::XWW + 12 * RCW); };       // v[6], a[6]
-  auto tl_rbi = [&](int k) { return sp<RC>(smem, lane, L::TL + k * L::TLW); };
-  auto tl_u = [&](int k) { return sp<RA>(smem, lane, L::TL + k * L::TLW + 10 * RCW); };
-  auto tl_v = [&](int k) { return sp<RA>(smem, lane, L::TL + k * L::TLW + 10 * RCW + 8 * RAW); };
+  auto tl_rbi_slot = [&](int slot) { return sp<RC>(smem, lane, L::TLR + slot * 10 * RCW); };
+  auto tl_u = [&](int k) { return sp<RA>(smem, lane, L::TL + k * L::TLW); };
+  auto tl_v = [&](int k) { return sp<RA>(smem, lane, L::TL + k * L::TLW + 8 * RAW); };
   auto ts_S = [&](int k) { return sp<RC>(smem, lane, L::TS + k * 6 * RCW); };
   float* const tqd = sp<float>(smem, lane, L::TQD);
   unsigned* const flg = sp<unsigned>(smem, lane, L::FLG);
@@ -302,12 +315,15 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       for (int k = 0; k < 6; ++k) bqd[k] = io.qd_in[(size_t)k * ns + e];
     }
   }
+  // actions: [n_act][n] (device layout) or [n][n_act] (host layout, tds_b200_env_step_host)
+  const float* const act_p = io.act_aos ? io.act_aos + (size_t)e * SP::N_ACT : io.tau_in + e;
+  const size_t act_s = io.act_aos ? (size_t)1 : (size_t)ns;
   if (use_pd) {
     sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
       if constexpr (!(C::flags(k) & TDS_LF_FIXED) && SP::L_ACT[0][k] >= 0) {
         const int a = LG.act[k - NT];
-        float act = io.tau_in[(size_t)a * ns + e];
+        float act = act_p[(size_t)a * act_s];
         act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
         const float q_des = E.initial_poses[a] + act;
         const float f = E.kp * (q_des - qv[k]) + E.kd * (0.f - qdv[k]);
@@ -319,7 +335,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         constexpr int k = decltype(Kc)::value;
         constexpr int a = SP::L_ACT[0][k];
         if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED) && a >= 0) {
-          float act = io.tau_in[(size_t)a * ns + e];
+          float act = act_p[(size_t)a * act_s];
           act = fmaxf(fminf(act, E.action_limit), -E.action_limit);
           const float q_des = E.initial_poses[a] + act;
           const float f = E.kp * (q_des - qv[k]) + E.kd * (0.f - qdv[k]);
@@ -523,7 +539,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         const RC cc = dot(c, c);
         r.I.xx += r.m * (cc - c.x * c.x); r.I.yy += r.m * (cc - c.y * c.y); r.I.zz += r.m * (cc - c.z * c.z);
         r.I.xy -= r.m * c.x * c.y; r.I.xz -= r.m * c.x * c.z; r.I.yz -= r.m * c.y * c.z;
-        if constexpr (TR) st_rbi<RC>(tl_rbi(k), ST, r);
+        if constexpr (TR) st_rbi<RC>(tl_rbi_slot(trunk_rbi_slot<SP>(k)), ST, r);
         else st_rbi<RC>(sp<RC>(priv, lane, ko * 10 * RCW), ST, r);
       }
     }
@@ -653,7 +669,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     Abi<RA> Ia = abi_nz<RA>();
     Sv<RA> pA = sv_nz<RA>();
     if constexpr (!massless) {
-      if constexpr (TR) Ic = ld_rbi<RC>(tl_rbi(k), ST); else Ic = ld_rbi<RC>(sp<RC>(priv, lane, ko * 10 * RCW), ST);
+      if constexpr (TR) Ic = ld_rbi<RC>(tl_rbi_slot(trunk_rbi_slot<SP>(k)), ST); else Ic = ld_rbi<RC>(sp<RC>(priv, lane, ko * 10 * RCW), ST);
       const Rbi<RA> rb = cvt_rbi<RA>(Ic);
       Ia = abi_from_rbi(rb);
       pA = cross_mf(v, rbi_mul(rb, v));                      // kinematics.hpp:132
@@ -801,7 +817,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       Rbi<RC> Ic = rbi_nz<RC>();   // composite inertia of the chain from link k to the leaves
 #pragma unroll 1
       for (int k = NT - 1; k >= 0; --k) {
-        if (!TK.massless[k]) rbi_add(Ic, ld_rbi<RC>(tl_rbi(k), ST));
+        if (!TK.massless[k]) rbi_add(Ic, ld_rbi<RC>(tl_rbi_slot(TK.rbi_slot[k]), ST));
         const int as = TK.acc[k];
         if (as >= 0) {
 #pragma unroll
@@ -838,7 +854,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         const Sv<RA> v = ld6<RA>(tl_v(k), ST);
         Rbi<RC> Ic = cC; Abi<RA> Ia = cA; Sv<RA> pA = cP;
         if (!TK.massless[k]) {
-          const Rbi<RC> own = ld_rbi<RC>(tl_rbi(k), ST);
+          const Rbi<RC> own = ld_rbi<RC>(tl_rbi_slot(TK.rbi_slot[k]), ST);
           const Rbi<RA> rb = cvt_rbi<RA>(own);
           abi_add(Ia, abi_from_rbi(rb));
           pA = pA + cross_mf(v, rbi_mul(rb, v));
@@ -1345,22 +1361,26 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) qv[k] = (float)(RC(qv[k]) + RC(qdv[k]) * RC(P.dt));
     });
     bool done = false;
+    float rew = 0.f;
     if (E.reward_kind == 1) {   // laikago_environment2.h:130-171 (fixed-base emulation; q0..5 are trunk coordinates)
       constexpr int k0 = k_of_q<SP, 0>(0), k2 = k_of_q<SP, 0>(2), k3 = k_of_q<SP, 0>(3), k4 = k_of_q<SP, 0>(4);
       if constexpr (!FLOAT && k0 >= 0 && k0 < NT && k2 >= 0 && k2 < NT && k3 >= 0 && k3 < NT && k4 >= 0 && k4 < NT) {
         const float x = qv[k0], z = qv[k2];
         const float upz = cosf(qv[k3]) * cosf(qv[k4]);
         done = (upz < 0.6f) || (z < 0.2f);
-        if (io.reward && live) io.reward[e] = done ? 0.f : x;
+        rew = done ? 0.f : x;
+        if (io.reward && live) io.reward[e] = rew;
       }
     } else if (E.reward_kind == 2) {
       if constexpr (FLOAT) {
         const float x = bq[4], z = bq[6];
         done = ((float)up_z < 0.6f) || (z < 0.2f);
-        if (io.reward && live) io.reward[e] = done ? 0.f : x;
+        rew = done ? 0.f : x;
+        if (io.reward && live) io.reward[e] = rew;
       }
     }
     if (io.done && E.reward_kind && live) io.done[e] = done ? 1.f : 0.f;
+    if (io.obs_tail && live) { io.obs_tail[e] = rew; io.obs_tail[io.n + e] = done ? 1.f : 0.f; }
     flg[(2 * TT) * ST] = done ? 1u : 0u;
   }
   __syncthreads();
@@ -1370,23 +1390,35 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       constexpr int k = decltype(Kc)::value;
       if constexpr (!(C::flags(k) & TDS_LF_FIXED)) {
         const int qi = LG.qidx[k - NT], qdi = LG.qdidx[k - NT];
-        io.q_out[(size_t)qi * ns + e] = reset ? E.reset_q[qi] : qv[k];
-        io.qd_out[(size_t)qdi * ns + e] = reset ? 0.f : qdv[k];
+        const float qo = reset ? E.reset_q[qi] : qv[k], qdo = reset ? 0.f : qdv[k];
+        io.q_out[(size_t)qi * ns + e] = qo;
+        io.qd_out[(size_t)qdi * ns + e] = qdo;
+        if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[qi] = qo; o[SP::N_Q + qdi] = qdo; }
       }
     });
     if (role == 0) {
       sfor<0, NT>([&](auto Kc) {
         constexpr int k = decltype(Kc)::value;
         if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) {
-          io.q_out[(size_t)CI(SP::L_QIDX[0][k]) * ns + e] = reset ? E.reset_q[CI(SP::L_QIDX[0][k])] : qv[k];
-          io.qd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = reset ? 0.f : qdv[k];
+          const float qo = reset ? E.reset_q[CI(SP::L_QIDX[0][k])] : qv[k], qdo = reset ? 0.f : qdv[k];
+          io.q_out[(size_t)CI(SP::L_QIDX[0][k]) * ns + e] = qo;
+          io.qd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = qdo;
+          if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[CI(SP::L_QIDX[0][k])] = qo; o[SP::N_Q + CI(SP::L_QDIDX[0][k])] = qdo; }
         }
       });
       if constexpr (FLOAT) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) io.q_out[(size_t)k * ns + e] = reset ? E.reset_q[k] : bq[k];
+        for (int k = 0; k < 7; ++k) {
+          const float qo = reset ? E.reset_q[k] : bq[k];
+          io.q_out[(size_t)k * ns + e] = qo;
+          if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + k] = qo;
+        }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) io.qd_out[(size_t)k * ns + e] = reset ? 0.f : bqd[k];
+        for (int k = 0; k < 6; ++k) {
+          const float qdo = reset ? 0.f : bqd[k];
+          io.qd_out[(size_t)k * ns + e] = qdo;
+          if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + SP::N_Q + k] = qdo;
+        }
       }
     }
   }
@@ -1396,7 +1428,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
 }
 
 template <class SP, typename RA, typename RC, typename RS>
-__global__ void __launch_bounds__(32 * TDS_TEAM_T, 1)
+__global__ void __launch_bounds__(32 * TDS_TEAM_T, 2)
 tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode_flags,
                      const int use_pd) {
   extern __shared__ __align__(16) char smem_raw[];
@@ -1465,6 +1497,8 @@ extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, cons
     static bool attr_set = false;                                                                       \
     if (!attr_set && smem > 48 * 1024) {                                                                \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      /* two tiles per SM when the batch has more tiles than SMs: ask for the largest shared-memory carveout */ \
+      if (err == cudaSuccess) err = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
       if (err == cudaSuccess) attr_set = true;                                                          \
     }                                                                                                   \
     if (err == cudaSuccess) {                                                                           \

@@ -100,5 +100,9 @@ struct StepIO {
   float* contact_dist;                  // [n_contact_points][n] or null
   float* link_xf;                       // [n_links*12][n] world transforms of the step's FK, or null
   long long* phase_clk;                 // [n_warps][16] clock64() stamps at phase boundaries (profiling), or null
+  // host-facing layouts served directly by the specialised kernel (other kernels: staged by transposes, tds_capi.cu)
+  const float* act_aos;                 // actions [n][n_act] (environment-major), or null -> tau_in
+  float* obs_aos;                       // observations [n][n_q + n_qd] = q | qd after the step, or null
+  float* obs_tail;                      // reward [n] then done [n] behind the observations, or null
   int n; int n_stride;
 };
