@@ -256,12 +256,16 @@ template <typename T> TDS_D Abi<T> abi_nz() {
 template <typename T> TDS_D Sv<T> sv_nz() { Sv<T> s; const T z = negz<T>(); s.top = v3<T>(z, z, z); s.bot = s.top; return s; }
 template <typename T> TDS_D Rbi<T> rbi_nz() { Rbi<T> r; const T z = negz<T>(); r.m = z; r.h = v3<T>(z, z, z); r.I = {z, z, z, z, z, z}; return r; }
 
-template <class SP, typename RA, typename RC, typename RS>
+// VAR selects what the instance carries besides the step itself (code bytes are paid at the instruction-fetch rate):
+//   0 general: forward-dynamics-only mode, per-link world transforms and contact distances as outputs
+//   1 lean: full / no-contact step on the device layout only      2 lean + host layouts (tds_b200_env_step_host)
+template <class SP, typename RA, typename RC, typename RS, int VAR>
 TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, const StepIO& io, const int mode, const int use_pd,
                      const int role) {
   using L = Lay<SP, RA, RC, RS>;
   using C = Cls<SP>;
   static_assert(C::uniform(), "the subtrees of the model are not one structural class (use the table-driven kernel)");
+  constexpr bool XOUT = VAR == 0, HOSTIO = VAR == 2;
   constexpr int RAW = L::RAW, RCW = L::RCW;
   constexpr int NT = SP::N_TRUNK, NTD = SP::N_TD, NLOC = SP::N_LOC[0];
   constexpr int NOD = SP::N_OD[0], NODA = cmax(NOD, 1), NTDA = cmax(NTD, 1), NTRI = L::NTRI, NTRIA = cmax(NTRI, 1);
@@ -316,8 +320,8 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     }
   }
   // actions: [n_act][n] (device layout) or [n][n_act] (host layout, tds_b200_env_step_host)
-  const float* const act_p = io.act_aos ? io.act_aos + (size_t)e * SP::N_ACT : io.tau_in + e;
-  const size_t act_s = io.act_aos ? (size_t)1 : (size_t)ns;
+  const float* const act_p = HOSTIO ? io.act_aos + (size_t)e * SP::N_ACT : io.tau_in + e;
+  const size_t act_s = HOSTIO ? (size_t)1 : (size_t)ns;
   if (use_pd) {
     sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
@@ -399,7 +403,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   RC plane_off; V3<RC> O;
   auto emit_point = [&](const V3<RC>& pos, const RC rad, const int cand, V3<RC>& out_pos, RC& out_dist) {
     const RC dist = DOT_PN(pos) + plane_off - rad;
-    if (io.contact_dist && live) io.contact_dist[(size_t)cand * ns + e] = (float)dist;
+    if constexpr (XOUT) if (io.contact_dist && live) io.contact_dist[(size_t)cand * ns + e] = (float)dist;
     out_pos = pos - pn * rad;                                // world_point_on_b, relative to O
     out_dist = dist;
     if (dist < RC(0)) my_active |= 1ull << cand;
@@ -560,7 +564,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       if constexpr (TR) emit_trunk_geoms(IC<SP::L_GB[0][k]>{}, IC<SP::L_GE[0][k]>{}, IC<SP::L_CAND[0][k]>{}, IC<SP::L_LPT[0][k]>{}, Ri, pi);
       else emit_own_geoms(IC<k>{}, Ri, pi);
     }
-    if (io.link_xf && live) {
+    if constexpr (XOUT) if (io.link_xf && live) {
       int link;
       if constexpr (TR) link = CI(SP::L_LINK[0][k]); else link = LG.link[ko];
       float* o = io.link_xf + (size_t)link * 12 * ns + e;
@@ -796,7 +800,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       const Sv<RA> S = cvt_sv<RA>(S_of(IC<k>{}));
       a.top = axpy(S.top, qdd, a.top);
       a.bot = axpy(S.bot, qdd, a.bot);
-      if (mode == MODE_FD) {
+      if (XOUT && mode == MODE_FD) {
         if (live && io.qdd_out) {
           int qdi;
           if constexpr (TR) qdi = CI(SP::L_QDIDX[0][k]); else qdi = LG.qdidx[ko];
@@ -1023,7 +1027,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           const Sv<RA> S = cvt_sv<RA>(ld6<RC>(ts_S(k), ST));
           a.top = axpy(S.top, qdd, a.top);
           a.bot = axpy(S.bot, qdd, a.bot);
-          if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)TK.qdidx[k] * ns + e] = (float)qdd; }
+          if (XOUT && mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)TK.qdidx[k] * ns + e] = (float)qdd; }
           else tk_qd[k * ST] = (float)(RA(tk_qd[k * ST]) + qdd * dtA);
         }
         const int xs = TK.xw[k];
@@ -1040,7 +1044,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
                         base_acc_b.bot.y + RC(P.gravity[1]), base_acc_b.bot.z + RC(P.gravity[2])};
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
+        if (XOUT && mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
         else bqd[k] = (float)(RC(bqd[k]) + qb[k] * RC(P.dt));
       }
 #pragma unroll
@@ -1057,7 +1061,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // ---- pass 3b: subtrees -----------------------------------------------------------------------------------------------------------------------
   sfor<NT, NLOC>(pass3);
   TDSS_PHASE();  // 4
-  if (mode == MODE_FD) return;
+  if (XOUT && mode == MODE_FD) return;
 
   // ---- contact solve: leaf-first elimination in registers ---------------------------------------------------------------------------------------
   //   M_kk = L_k L_k^T, G = L_k^-1 C, S = B - sum_k G^T G = L_t L_t^T, Y = L^-1 Jc^T, PGS on w = Y p, dqd = L^-T w
@@ -1380,7 +1384,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       }
     }
     if (io.done && E.reward_kind && live) io.done[e] = done ? 1.f : 0.f;
-    if (io.obs_tail && live) { io.obs_tail[e] = rew; io.obs_tail[io.n + e] = done ? 1.f : 0.f; }
+    if constexpr (HOSTIO) if (io.obs_tail && live) { io.obs_tail[e] = rew; io.obs_tail[io.n + e] = done ? 1.f : 0.f; }
     flg[(2 * TT) * ST] = done ? 1u : 0u;
   }
   __syncthreads();
@@ -1393,7 +1397,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         const float qo = reset ? E.reset_q[qi] : qv[k], qdo = reset ? 0.f : qdv[k];
         io.q_out[(size_t)qi * ns + e] = qo;
         io.qd_out[(size_t)qdi * ns + e] = qdo;
-        if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[qi] = qo; o[SP::N_Q + qdi] = qdo; }
+        if constexpr (HOSTIO) if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[qi] = qo; o[SP::N_Q + qdi] = qdo; }
       }
     });
     if (role == 0) {
@@ -1403,7 +1407,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           const float qo = reset ? E.reset_q[CI(SP::L_QIDX[0][k])] : qv[k], qdo = reset ? 0.f : qdv[k];
           io.q_out[(size_t)CI(SP::L_QIDX[0][k]) * ns + e] = qo;
           io.qd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = qdo;
-          if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[CI(SP::L_QIDX[0][k])] = qo; o[SP::N_Q + CI(SP::L_QDIDX[0][k])] = qdo; }
+          if constexpr (HOSTIO) if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[CI(SP::L_QIDX[0][k])] = qo; o[SP::N_Q + CI(SP::L_QDIDX[0][k])] = qdo; }
         }
       });
       if constexpr (FLOAT) {
@@ -1411,13 +1415,13 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         for (int k = 0; k < 7; ++k) {
           const float qo = reset ? E.reset_q[k] : bq[k];
           io.q_out[(size_t)k * ns + e] = qo;
-          if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + k] = qo;
+          if constexpr (HOSTIO) if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + k] = qo;
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           const float qdo = reset ? 0.f : bqd[k];
           io.qd_out[(size_t)k * ns + e] = qdo;
-          if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + SP::N_Q + k] = qdo;
+          if constexpr (HOSTIO) if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + SP::N_Q + k] = qdo;
         }
       }
     }
@@ -1427,14 +1431,14 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
 #undef TDSS_STAMP
 }
 
-template <class SP, typename RA, typename RC, typename RS>
+template <class SP, typename RA, typename RC, typename RS, int VAR>
 __global__ void __launch_bounds__(32 * TDS_TEAM_T, 2)
 tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode_flags,
                      const int use_pd) {
   extern __shared__ __align__(16) char smem_raw[];
   const int role = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, known uniform to the compiler
   if ((mode_flags & 256) && role != 0) return;   // profiling aid (TDS_B200_DEBUG_SOLO): role 0 alone, results are garbage
-  tile_body<SP, RA, RC, RS>(smem_raw, P, E, io, mode_flags & 255, use_pd, role);
+  tile_body<SP, RA, RC, RS, VAR>(smem_raw, P, E, io, mode_flags & 255, use_pd, role);
 }
 
 // per-role numbers of the Laikago subtrees
@@ -1491,9 +1495,9 @@ extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, cons
   const int tiles = (io->n + 31) / 32;
   const size_t smem = tds_spec_smem_bytes(precision);
   cudaError_t err = cudaSuccess;
-#define TDSS_LAUNCH(RA, RC, RS)                                                                         \
+#define TDSS_LAUNCH(RA, RC, RS, VAR)                                                                    \
   do {                                                                                                  \
-    auto k = tds_step_spec_kernel<SpecLaikago, RA, RC, RS>;                                             \
+    auto k = tds_step_spec_kernel<SpecLaikago, RA, RC, RS, VAR>;                                        \
     static bool attr_set = false;                                                                       \
     if (!attr_set && smem > 48 * 1024) {                                                                \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
@@ -1506,9 +1510,17 @@ extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, cons
       err = cudaGetLastError();                                                                         \
     }                                                                                                   \
   } while (0)
-  if (precision == 0) TDSS_LAUNCH(float, double, float);
-  else if (precision == 1) TDSS_LAUNCH(double, double, double);
-  else TDSS_LAUNCH(float, float, float);
+  // instance: general (extra outputs / forward dynamics only), lean, lean + host layouts
+  const int var = ((mode & 255) == 0 || io->link_xf || io->contact_dist || io->qdd_out) ? 0 : ((io->act_aos && use_pd) ? 2 : 1);
+  if (var != 2 && io->act_aos) return (int)cudaErrorInvalidValue;   // host layouts are only served by the lean instance
+#define TDSS_PREC(VAR)                                                      \
+  do {                                                                      \
+    if (precision == 0) TDSS_LAUNCH(float, double, float, VAR);             \
+    else if (precision == 1) TDSS_LAUNCH(double, double, double, VAR);      \
+    else TDSS_LAUNCH(float, float, float, VAR);                             \
+  } while (0)
+  if (var == 0) TDSS_PREC(0); else if (var == 1) TDSS_PREC(1); else TDSS_PREC(2);
+#undef TDSS_PREC
 #undef TDSS_LAUNCH
   return (int)err;
 }
