@@ -107,6 +107,27 @@ int tds_b200_env_step_host(tds_b200_sim* sim, const float* actions, float* obs, 
 /* Same, device-resident: actions/reward/done are device SoA arrays; advances the resident state. */
 int tds_b200_env_step_device(tds_b200_sim* sim, const float* actions, float* reward, float* done, void* stream);
 /* Device pointers of the resident state (SoA fp32 [n_q][ns], [n_qd][ns]). */
+/* ---- environment layer on the device (what surrounds the step in the reference's ARS loop) ---------------------
+ * Episode reset, LaikagoContactSimulation::reset (examples/environments/laikago_environment2.h:63-116): environments with
+ * mask[e] != 0 (all when mask is NULL) are set to the reset pose of tds_b200_set_auto_reset plus noise on the actuated
+ * joints (noise: device [n_act][n_stride], or NULL -> U(-noise_amp, noise_amp) from a counter-based generator keyed by
+ * (seed, env, joint); the reference draws std::rand() * 0.05), qd = 0, then settle_steps env-steps with zero actions;
+ * the other environments keep their state. */
+int tds_b200_env_reset_device(tds_b200_sim* sim, const float* mask, const float* noise, float noise_amp,
+                              unsigned long long seed, int settle_steps, void* stream);
+/* rollout_length steps of ARSVectorizedWorker::rollouts (examples/ars/ars_vectorized_worker.h:51-141) without leaving
+ * the GPU: per environment a linear policy with bias (VectorizedEnvironment::policy, ars_vectorized_environment.h:293-300;
+ * parameters = weights [n_act][n_q+n_qd] row-major | biases [n_act], device layout [n_params][n_stride]) on the observation
+ * (q | qd, x and y zeroed), the env-step, sticky done; total_rewards[e] = sum of (reward - shift) and steps[e] over the
+ * steps the environment was alive.  Device pointers; asynchronous on `stream` (NULL: the simulator's own stream, the one
+ * the host-buffer entry points use; the same holds for tds_b200_env_reset_device). */
+int tds_b200_env_rollout_device(tds_b200_sim* sim, const float* policy, int n_params, int rollout_length, float shift,
+                                float* total_rewards, int* steps, void* stream);
+/* reset + rollout with host buffers: policy [n_envs][n_params], noise [n_envs][n_act] or NULL, results to host. */
+int tds_b200_env_rollout_host(tds_b200_sim* sim, const double* policy, int n_params, int rollout_length, double shift,
+                              const double* noise, double noise_amp, unsigned long long seed, int settle_steps,
+                              double* total_rewards, int* steps);
+
 float* tds_b200_env_q(tds_b200_sim* sim);
 float* tds_b200_env_qd(tds_b200_sim* sim);
 

@@ -47,6 +47,12 @@ def lib():
     L.tds_b200_set_auto_reset.argtypes = [vp, ci, dp]
     L.tds_b200_set_precision.restype = ci
     L.tds_b200_set_precision.argtypes = [vp, ci]
+    L.tds_b200_env_reset_device.restype = ci
+    L.tds_b200_env_reset_device.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_ulonglong, ci, vp]
+    L.tds_b200_env_rollout_device.restype = ci
+    L.tds_b200_env_rollout_device.argtypes = [vp, vp, ci, ci, ctypes.c_float, vp, vp, vp]
+    L.tds_b200_env_rollout_host.restype = ci
+    L.tds_b200_env_rollout_host.argtypes = [vp, vp, ci, ci, ctypes.c_double, vp, ctypes.c_double, ctypes.c_ulonglong, ci, vp, vp]
     L.tds_b200_kernel_name.restype = ctypes.c_char_p
     L.tds_b200_kernel_name.argtypes = [vp]
     L.tds_b200_get_dims.restype = ci
@@ -81,7 +87,8 @@ def last_error():
 # every symbol include/tds_b200.h declares (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
     "tds_b200_last_error", "tds_b200_urdf_to_model", "tds_b200_create", "tds_b200_destroy",
-    "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_set_precision", "tds_b200_kernel_name", "tds_b200_get_dims",
+    "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_set_precision", "tds_b200_kernel_name", "tds_b200_get_dims", "tds_b200_env_reset_device",
+    "tds_b200_env_rollout_device", "tds_b200_env_rollout_host",
     "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
     "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
     "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",

@@ -138,6 +138,67 @@ __global__ void pack_v1_output_kernel(const __grid_constant__ DevVisuals V, cons
   o[j++] = upz;
 }
 
+// ---- environment layer on the device ---------------------------------------------------------------
+// counter-based uniform in [0, 1): splitmix64 of (seed, environment, joint)
+__device__ inline float unit_uniform(unsigned long long seed, unsigned e, unsigned a) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((unsigned long long)e << 8) + a + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+// LaikagoContactSimulation::reset, laikago_environment2.h:63-89: reset pose, joint noise on the actuated joints, qd = 0
+__global__ void env_reset_fill_kernel(float* __restrict__ q, float* __restrict__ qd, const float* __restrict__ noise, float amp,
+                                      unsigned long long seed, EnvParams E, int n_q, int n_qd, const int* __restrict__ act_qidx,
+                                      int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  for (int k = 0; k < n_q; ++k) q[(size_t)k * ns + e] = E.reset_q[k];
+  for (int k = 0; k < n_qd; ++k) qd[(size_t)k * ns + e] = 0.f;
+  for (int a = 0; a < E.n_act; ++a) {
+    const float d = noise ? noise[(size_t)a * ns + e] : amp * (2.f * unit_uniform(seed, (unsigned)e, (unsigned)a) - 1.f);
+    q[(size_t)act_qidx[a] * ns + e] += d;
+  }
+}
+__global__ void env_select_kernel(const float* __restrict__ mask, const float* __restrict__ q_src, const float* __restrict__ qd_src,
+                                  float* __restrict__ q, float* __restrict__ qd, int n_q, int n_qd, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || (mask && mask[e] == 0.f)) return;
+  for (int k = 0; k < n_q; ++k) q[(size_t)k * ns + e] = q_src[(size_t)k * ns + e];
+  for (int k = 0; k < n_qd; ++k) qd[(size_t)k * ns + e] = qd_src[(size_t)k * ns + e];
+}
+// VectorizedEnvironment::policy (ars_vectorized_environment.h:293-300): one linear layer with bias per environment
+// (neural_network.hpp:223-265, parameters = weights [n_act][n_obs] row-major | biases [n_act]); the observation is
+// q | qd with x and y zeroed (ars_vectorized_environment.h:285-287).  params: [n_params][ns] on the device.
+__global__ void policy_linear_kernel(const float* __restrict__ q, const float* __restrict__ qd, const float* __restrict__ params,
+                                     float* __restrict__ act, int n_q, int n_qd, int n_act, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int n_obs = n_q + n_qd;
+  for (int a = 0; a < n_act; ++a) {
+    float s = params[(size_t)(n_act * n_obs + a) * ns + e];
+    const float* w = params + (size_t)a * n_obs * ns + e;
+    for (int k = 2; k < n_q; ++k) s += q[(size_t)k * ns + e] * w[(size_t)k * ns];
+    for (int k = 0; k < n_qd; ++k) s += qd[(size_t)k * ns + e] * w[(size_t)(n_q + k) * ns];
+    act[(size_t)a * ns + e] = s;
+  }
+}
+// ARSVectorizedWorker::rollouts bookkeeping (ars_vectorized_worker.h:117-139): done is sticky, rewards and step counts
+// accumulate only while the environment is alive
+__global__ void rollout_accum_kernel(const float* __restrict__ reward, const float* __restrict__ done, float shift,
+                                     float* __restrict__ sticky, float* __restrict__ total, int* __restrict__ steps, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (sticky[e] != 0.f) return;
+  if (done[e] != 0.f) { sticky[e] = 1.f; return; }
+  total[e] += reward[e] - shift;
+  steps[e] += 1;
+}
+__global__ void rollout_init_kernel(float* sticky, float* total, int* steps, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) { sticky[e] = 0.f; total[e] = 0.f; steps[e] = 0; }
+}
+
 }  // namespace
 
 struct tds_b200_sim {
@@ -181,6 +242,10 @@ struct tds_b200_sim {
   long long* phase_clk = nullptr;  // profiling only (tds_b200_debug_phase_clocks)
   // tds_b200_env_step_host with pinned caller buffers: the copy / transpose / step / copy sequence is captured once
   // per buffer set and replayed (one graph launch instead of nine stream operations)
+  // environment layer scratch: reset staging, zero actions, actuated coordinate map, rollout bookkeeping
+  float *rq = nullptr, *rqd = nullptr, *zero_act = nullptr, *pol_act = nullptr, *sticky = nullptr, *r_total = nullptr, *pol_params = nullptr;
+  int *act_qidx = nullptr, *r_steps = nullptr;
+  size_t pol_params_rows = 0;
   // set around the step launch of tds_b200_env_step_host when the specialised kernel serves the host layouts itself
   const float* io_act_aos = nullptr; float* io_obs_aos = nullptr; float* io_obs_tail = nullptr;
   const void* g_key[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -330,6 +395,8 @@ void tds_b200_destroy(tds_b200_sim* s) {
   cudaSetDevice(s->device);
   cudaFree(s->q); cudaFree(s->qd); cudaFree(s->act); cudaFree(s->qdd); cudaFree(s->reward); cudaFree(s->done);
   drop_host_graph(s);
+  cudaFree(s->rq); cudaFree(s->rqd); cudaFree(s->zero_act); cudaFree(s->pol_act); cudaFree(s->sticky); cudaFree(s->r_total);
+  cudaFree(s->pol_params); cudaFree(s->act_qidx); cudaFree(s->r_steps);
   cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk); cudaFree(s->team_dev);
   if (s->stage_host) cudaFreeHost(s->stage_host);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -538,6 +605,114 @@ int tds_b200_env_step_device(tds_b200_sim* s, const float* actions, float* rewar
   if (!s) return -1;
   return tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, actions, s->q, s->qd, nullptr, reward, done,
                               nullptr, nullptr, stream);
+}
+
+static int ensure_env_layer(tds_b200_sim* s) {
+  if (s->rq) return 0;
+  const DevModel& M = s->dm[0];
+  const size_t ns = s->ns;
+  CUDA_TRY(cudaMalloc((void**)&s->rq, sizeof(float) * ns * (M.n_q > 0 ? M.n_q : 1)));
+  CUDA_TRY(cudaMalloc((void**)&s->rqd, sizeof(float) * ns * (M.n_qd > 0 ? M.n_qd : 1)));
+  CUDA_TRY(cudaMalloc((void**)&s->zero_act, sizeof(float) * ns * TDS_MAX_ACT));
+  CUDA_TRY(cudaMemset(s->zero_act, 0, sizeof(float) * ns * TDS_MAX_ACT));
+  CUDA_TRY(cudaMalloc((void**)&s->pol_act, sizeof(float) * ns * TDS_MAX_ACT));
+  CUDA_TRY(cudaMalloc((void**)&s->sticky, sizeof(float) * ns));
+  CUDA_TRY(cudaMalloc((void**)&s->r_total, sizeof(float) * ns));
+  CUDA_TRY(cudaMalloc((void**)&s->r_steps, sizeof(int) * ns));
+  CUDA_TRY(cudaMalloc((void**)&s->act_qidx, sizeof(int) * TDS_MAX_ACT));
+  return 0;
+}
+
+int tds_b200_env_reset_device(tds_b200_sim* s, const float* mask, const float* noise, float noise_amp, unsigned long long seed,
+                              int settle_steps, void* stream) {
+  if (!s) return -1;
+  if (s->E.n_act == 0) { set_err("env reset without tds_b200_set_env"); return -3; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  int rc = ensure_env_layer(s);
+  if (rc) return rc;
+  const DevModel& M = s->dm[0];
+  cudaStream_t sm = stream ? (cudaStream_t)stream : s->stream;   // NULL: the simulator's own stream (as the host paths)
+  int qidx[TDS_MAX_ACT];
+  for (int a = 0; a < s->E.n_act; ++a) qidx[a] = M.q_idx[s->E.act_link[a]];
+  CUDA_TRY(cudaMemcpyAsync(s->act_qidx, qidx, sizeof(int) * s->E.n_act, cudaMemcpyHostToDevice, sm));
+  const int T = 128, B = (s->n + T - 1) / T;
+  env_reset_fill_kernel<<<B, T, 0, sm>>>(s->rq, s->rqd, noise, noise_amp, seed, s->E, M.n_q, M.n_qd, s->act_qidx, s->n, s->ns);
+  // settle with zero actions on the staging copy (laikago_environment2.h:92-110); no auto-reset inside
+  const int saved_auto = s->E.auto_reset;
+  s->E.auto_reset = 0;
+  for (int i = 0; i < settle_steps && rc == 0; ++i)
+    rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->rq, s->rqd, s->zero_act, s->rq, s->rqd, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, sm);
+  s->E.auto_reset = saved_auto;
+  if (rc) return rc;
+  env_select_kernel<<<B, T, 0, sm>>>(mask, s->rq, s->rqd, s->q, s->qd, M.n_q, M.n_qd, s->n, s->ns);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_env_rollout_device(tds_b200_sim* s, const float* policy, int n_params, int rollout_length, float shift,
+                                float* total_rewards, int* steps, void* stream) {
+  if (!s || !policy || !total_rewards || !steps) return -1;
+  if (s->E.n_act == 0) { set_err("rollout without tds_b200_set_env"); return -3; }
+  const DevModel& M = s->dm[0];
+  if (n_params != s->E.n_act * (M.n_q + M.n_qd) + s->E.n_act) { set_err("policy size must be n_act * (n_q + n_qd) + n_act"); return -2; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  int rc = ensure_env_layer(s);
+  if (rc) return rc;
+  cudaStream_t sm = stream ? (cudaStream_t)stream : s->stream;
+  const int T = 128, B = (s->n + T - 1) / T;
+  rollout_init_kernel<<<B, T, 0, sm>>>(s->sticky, total_rewards, steps, s->n);
+  const int saved_auto = s->E.auto_reset;
+  s->E.auto_reset = 0;   // an episode ends at done (ars_vectorized_worker.h:121-133)
+  for (int r = 0; r < rollout_length && rc == 0; ++r) {
+    policy_linear_kernel<<<B, T, 0, sm>>>(s->q, s->qd, policy, s->pol_act, M.n_q, M.n_qd, s->E.n_act, s->n, s->ns);
+    rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->pol_act, s->q, s->qd, nullptr, s->reward, s->done, nullptr,
+                              nullptr, sm);
+    rollout_accum_kernel<<<B, T, 0, sm>>>(s->reward, s->done, shift, s->sticky, total_rewards, steps, s->n);
+  }
+  s->E.auto_reset = saved_auto;
+  if (rc) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_env_rollout_host(tds_b200_sim* s, const double* policy, int n_params, int rollout_length, double shift,
+                              const double* noise, double noise_amp, unsigned long long seed, int settle_steps,
+                              double* total_rewards, int* steps) {
+  if (!s || !policy) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  int rc = ensure_env_layer(s);
+  if (rc) return rc;
+  const int n = s->n, ns = s->ns, na = s->E.n_act;
+  cudaStream_t sm = s->stream;
+  const int T = 128, B = (n + T - 1) / T;
+  const size_t rows = (size_t)n_params > (size_t)na ? (size_t)n_params : (size_t)na;
+  if (rows > s->pol_params_rows) {
+    cudaFree(s->pol_params); s->pol_params = nullptr; s->pol_params_rows = 0;
+    CUDA_TRY(cudaMalloc((void**)&s->pol_params, sizeof(float) * rows * ns));
+    s->pol_params_rows = rows;
+  }
+  rc = ensure_stage(s, sizeof(double) * (size_t)n * rows, 0);
+  if (rc) return rc;
+  double* st = (double*)s->stage_dev;
+  const float* d_noise = nullptr;
+  if (noise) {   // [n][n_act] -> [n_act][ns]
+    CUDA_TRY(cudaMemcpyAsync(st, noise, sizeof(double) * n * na, cudaMemcpyHostToDevice, sm));
+    aos_to_soa_kernel<double><<<B, T, 0, sm>>>(st, na, 0, s->pol_params, na, n, ns);
+    d_noise = s->pol_params;
+  }
+  rc = tds_b200_env_reset_device(s, nullptr, d_noise, (float)noise_amp, seed, settle_steps, sm);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(st, policy, sizeof(double) * n * n_params, cudaMemcpyHostToDevice, sm));
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(st, n_params, 0, s->pol_params, n_params, n, ns);
+  rc = tds_b200_env_rollout_device(s, s->pol_params, n_params, rollout_length, (float)shift, s->r_total, s->r_steps, sm);
+  if (rc) return rc;
+  std::vector<float> tot(n);
+  CUDA_TRY(cudaMemcpyAsync(tot.data(), s->r_total, sizeof(float) * n, cudaMemcpyDeviceToHost, sm));
+  if (steps) CUDA_TRY(cudaMemcpyAsync(steps, s->r_steps, sizeof(int) * n, cudaMemcpyDeviceToHost, sm));
+  CUDA_TRY(cudaStreamSynchronize(sm));
+  if (total_rewards) for (int i = 0; i < n; ++i) total_rewards[i] = (double)tot[i];
+  return 0;
 }
 
 // Profiling aid (not part of the drop-in surface): enable per-warp clock64() stamps at the phase

@@ -34,8 +34,7 @@ def laikago_sim(n_envs, device=0, model=None, auto_reset=False, **kw):
     sim = BatchSim(model, n_envs, device=device, dt=1e-3, friction=1.0, keep_all_points=True, **kw)
     sim.set_env(LAIKAGO_INITIAL_POSES, start_link=6, kp=LAIKAGO_KP, kd=LAIKAGO_KD, max_force=LAIKAGO_MAX_FORCE,
                 action_limit=0.4, reward_kind=1)
-    if auto_reset:
-        sim.set_auto_reset(True, laikago_reset_pose())
+    sim.set_auto_reset(bool(auto_reset), laikago_reset_pose())   # the pose is also what env_reset_device starts from
     return sim
 
 
@@ -83,6 +82,14 @@ class VectorizedLaikagoEnv:
         self.sim.env_set_state(q, qd)
         self._settle()
         return self._obs.copy()
+
+    def rollouts(self, policies, rollout_length, shift=0.0, noise=None):
+        """ARSVectorizedWorker::rollouts (examples/ars/ars_vectorized_worker.h:51-141) on the device: reset with joint
+        noise (given [n][12], else drawn from this env's generator), 10 settle steps, then rollout_length steps of the
+        per-environment linear policies [n][12*36 + 12].  Returns (total_rewards, steps)."""
+        if noise is None:
+            noise = 0.05 * (self.rng.random((self.num_envs, 12)) - 0.5) * 2.0
+        return self.sim.env_rollout_host(policies, rollout_length, shift=shift, noise=noise)
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float32)

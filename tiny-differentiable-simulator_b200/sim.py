@@ -145,6 +145,34 @@ class BatchSim:
         self._check(self._L.tds_b200_env_step_host(self._h, hp(actions), hp(obs), hp(rewards), hp(dones)),
                     "env_step_host")
 
+    # ---- environment layer on the device (reset with noise + settle steps, policy rollouts) ----
+    def env_reset_device(self, mask=None, noise=None, noise_amp=0.05, seed=0, settle_steps=10, stream=None):
+        """mask: float32 CUDA tensor [n] (None = all); noise: float32 CUDA tensor [n_act][n_stride] (None = generated).
+        stream None = the simulator's own stream (the one the host-buffer calls use)."""
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
+        self._check(self._L.tds_b200_env_reset_device(self._h, _ptr(mask), _ptr(noise), float(noise_amp), int(seed),
+                                                      int(settle_steps), st), "env_reset_device")
+
+    def env_rollout_device(self, policy, rollout_length, shift, total_rewards, steps, stream=None):
+        """policy: float32 CUDA tensor [n_params][n_stride]; total_rewards float32 [n], steps int32 [n] CUDA tensors.
+        stream None = the simulator's own stream."""
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
+        self._check(self._L.tds_b200_env_rollout_device(self._h, _ptr(policy), int(policy.shape[0]), int(rollout_length),
+                                                        float(shift), _ptr(total_rewards), _ptr(steps), st), "env_rollout_device")
+
+    def env_rollout_host(self, policy, rollout_length, shift=0.0, noise=None, noise_amp=0.05, seed=0, settle_steps=10):
+        """Reset (noise [n][n_act] or generated) + rollout of per-environment linear policies [n][n_params] (host arrays).
+        Returns (total_rewards float64 [n], steps int32 [n])."""
+        pol = np.ascontiguousarray(policy, dtype=np.float64)
+        assert pol.shape[0] == self.n_envs
+        nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        tot = np.zeros(self.n_envs)
+        steps = np.zeros(self.n_envs, dtype=np.int32)
+        self._check(self._L.tds_b200_env_rollout_host(self._h, _dp(pol), int(pol.shape[1]), int(rollout_length), float(shift), _dp(nz),
+                                                      float(noise_amp), int(seed), int(settle_steps), _dp(tot),
+                                                      ctypes.c_void_p(steps.ctypes.data)), "env_rollout_host")
+        return tot, steps
+
     def env_step_device(self, actions, reward=None, done=None, stream=None):
         import torch
         st = ctypes.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream)
