@@ -30,3 +30,4 @@ ls -la gpurun_out/${TAG}_step_full.ncu-rep
 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python scripts/race_small.py > gpurun_out/${TAG}_racecheck.log 2>&1
 tail -3 gpurun_out/${TAG}_racecheck.log
 ./scripts/ifetch_probe.bin > gpurun_out/${TAG}_ifetch_probe.txt 2>&1; tail -4 gpurun_out/${TAG}_ifetch_probe.txt
+python scripts/bench_rollout.py > gpurun_out/${TAG}_rollout.txt 2>&1; tail -2 gpurun_out/${TAG}_rollout.txt

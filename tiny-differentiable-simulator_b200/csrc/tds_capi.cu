@@ -245,6 +245,7 @@ struct tds_b200_sim {
   // environment layer scratch: reset staging, zero actions, actuated coordinate map, rollout bookkeeping
   float *rq = nullptr, *rqd = nullptr, *zero_act = nullptr, *pol_act = nullptr, *sticky = nullptr, *r_total = nullptr, *pol_params = nullptr;
   int *act_qidx = nullptr, *r_steps = nullptr;
+  bool act_qidx_valid = false;
   size_t pol_params_rows = 0;
   // set around the step launch of tds_b200_env_step_host when the specialised kernel serves the host layouts itself
   const float* io_act_aos = nullptr; float* io_obs_aos = nullptr; float* io_obs_tail = nullptr;
@@ -436,6 +437,7 @@ int tds_b200_set_env(tds_b200_sim* s, int n_act, const double* initial_poses, in
   E.auto_reset = s->E.auto_reset;
   memcpy(E.reset_q, s->E.reset_q, sizeof(E.reset_q));
   s->E = E;
+  s->act_qidx_valid = false;
   return rebuild_team(s);
 }
 
@@ -632,9 +634,12 @@ int tds_b200_env_reset_device(tds_b200_sim* s, const float* mask, const float* n
   if (rc) return rc;
   const DevModel& M = s->dm[0];
   cudaStream_t sm = stream ? (cudaStream_t)stream : s->stream;   // NULL: the simulator's own stream (as the host paths)
-  int qidx[TDS_MAX_ACT];
-  for (int a = 0; a < s->E.n_act; ++a) qidx[a] = M.q_idx[s->E.act_link[a]];
-  CUDA_TRY(cudaMemcpyAsync(s->act_qidx, qidx, sizeof(int) * s->E.n_act, cudaMemcpyHostToDevice, sm));
+  if (!s->act_qidx_valid) {   // once per actuator map (synchronous: keeps the reset itself capturable into a CUDA graph)
+    int qidx[TDS_MAX_ACT];
+    for (int a = 0; a < s->E.n_act; ++a) qidx[a] = M.q_idx[s->E.act_link[a]];
+    CUDA_TRY(cudaMemcpy(s->act_qidx, qidx, sizeof(int) * s->E.n_act, cudaMemcpyHostToDevice));
+    s->act_qidx_valid = true;
+  }
   const int T = 128, B = (s->n + T - 1) / T;
   env_reset_fill_kernel<<<B, T, 0, sm>>>(s->rq, s->rqd, noise, noise_amp, seed, s->E, M.n_q, M.n_qd, s->act_qidx, s->n, s->ns);
   // settle with zero actions on the staging copy (laikago_environment2.h:92-110); no auto-reset inside
