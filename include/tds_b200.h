@@ -54,7 +54,7 @@ int tds_b200_set_params(tds_b200_sim* sim, double dt, const double gravity[3], d
 /* PD / environment parameters of LocomotionContactSimulation
  * (examples/environments/locomotion_contact_simulation.h:28-48,168-258): action k drives the k-th
  * non-fixed link at or after `start_link` (base_dof_) towards initial_poses[k] + clamp(action, +-limit).
- * reward_kind: 0 none, 1 Laikago fixed-base emulation, 2 floating
+ * reward_kind: 0 none, 1 Laikago fixed-base emulation, 2 floating, 3 Ant fixed-base emulation (ant_environment2.h:75-105)
  * (examples/environments/laikago_environment2.h:130-171). */
 int tds_b200_set_env(tds_b200_sim* sim, int n_act, const double* initial_poses, int start_link, double kp,
                      double kd, double max_force, double action_limit, int reward_kind);

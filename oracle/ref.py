@@ -71,6 +71,16 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.tdsref_laikago_step.argtypes = [vp, ctypes.c_int, ctypes.c_int, dp, dp]
         L.tdsref_laikago_reward_done.argtypes = [vp, dp, dp, ip]
+        if hasattr(L, "tdsref_ant_create"):
+            L.tdsref_ant_create.restype = vp
+            L.tdsref_ant_create.argtypes = [ctypes.c_int]
+            L.tdsref_ant_destroy.argtypes = [vp]
+            for f in ("tdsref_ant_input_dim", "tdsref_ant_output_dim", "tdsref_ant_state_dim", "tdsref_ant_action_dim",
+                      "tdsref_ant_num_threads"):
+                getattr(L, f).restype = ctypes.c_int
+                getattr(L, f).argtypes = [vp]
+            L.tdsref_ant_step.argtypes = [vp, ctypes.c_int, ctypes.c_int, dp, dp]
+            L.tdsref_ant_reward_done.argtypes = [vp, dp, dp, dp, ip]
         _lib = L
     return _lib
 
@@ -209,4 +219,48 @@ class LaikagoRef:
         r = ctypes.c_double(0)
         d = ctypes.c_int(0)
         lib().tdsref_laikago_reward_done(self._h, _dp(s), ctypes.byref(r), ctypes.byref(d))
+        return r.value, bool(d.value)
+
+
+class AntRef:
+    """The reference's Ant env step (AntContactSimulation2, examples/environments/ant_environment2.h), both CPU paths."""
+
+    IMPL_TEMPLATED, IMPL_CODEGEN = 0, 1
+
+    def __init__(self, num_threads=1):
+        L = lib()
+        with _quiet_stdout():
+            self._h = L.tdsref_ant_create(num_threads)
+        self.input_dim = L.tdsref_ant_input_dim(self._h)
+        self.output_dim = L.tdsref_ant_output_dim(self._h)
+        self.state_dim = L.tdsref_ant_state_dim(self._h)
+        self.action_dim = L.tdsref_ant_action_dim(self._h)
+        self.num_threads = L.tdsref_ant_num_threads(self._h)
+
+    def close(self):
+        if self._h:
+            lib().tdsref_ant_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, inputs, impl=0, out=None):
+        x = np.ascontiguousarray(inputs, dtype=np.float64)
+        n = x.shape[0]
+        assert x.shape[1] == self.input_dim
+        if out is None:
+            out = np.zeros((n, self.output_dim))
+        lib().tdsref_ant_step(self._h, impl, n, _dp(x), _dp(out))
+        return out
+
+    def reward_done(self, prev_state, cur_state):
+        a = np.ascontiguousarray(prev_state, dtype=np.float64)
+        b = np.ascontiguousarray(cur_state, dtype=np.float64)
+        r = ctypes.c_double(0)
+        d = ctypes.c_int(0)
+        lib().tdsref_ant_reward_done(self._h, _dp(a), _dp(b), ctypes.byref(r), ctypes.byref(d))
         return r.value, bool(d.value)

@@ -30,7 +30,10 @@ CONFIGS = {
     "sphere2": (D + "plane_implicit.urdf", D + "sphere2.urdf", True, wl.sphere2),
     "laikago": (D + "plane_implicit.urdf", D + "laikago/laikago_toes_zup_xyz_xyzrot.urdf", False, wl.laikago_perturbed),
     "humanoid": (D + "plane_implicit.urdf", D + "humanoid.urdf", True, wl.humanoid),
+    "ant": (D + "plane_implicit.urdf", D + "gym/ant_org_xyz_xyzrot.urdf", False, wl.ant_perturbed),
 }
+
+ANT_POSES, ANT_KP, ANT_KD, ANT_MAX = np.array([0.0, -0.5] * 4), 15.0, 0.3, 3.0   # ant_environment2.h:43-66
 
 
 def pd_tau(w):
@@ -65,6 +68,9 @@ def main():
         tau = w.get("tau")
         if name == "laikago":
             tau = pd_tau(w)
+        if name == "ant":   # PD torques of the env (host restatement only to feed the raw reference step)
+            f = ANT_KP * (ANT_POSES + np.clip(w["action"], -0.4, 0.4) - w["q"][:, 6:14]) + ANT_KD * (0.0 - w["qd"][:, 6:14])
+            tau = np.zeros((N, 14)); tau[:, 6:14] = np.clip(f, -ANT_MAX, ANT_MAX)
         outs = dict(q=[], qd=[], qdd=[], dist=[], link_b=[], n_contacts=[])
         for i in range(N):
             o = sim.step(mode, w["q"][i], w["qd"][i], None if tau is None else tau[i], contact_cap=64)
@@ -90,6 +96,18 @@ def main():
             save["env_output_templated"] = L.step(x, ref.LaikagoRef.IMPL_TEMPLATED)
             save["env_output_codegen"] = L.step(x, ref.LaikagoRef.IMPL_CODEGEN)
             rd = [L.reward_done(o) for o in save["env_output_templated"]]
+            save["env_reward"] = np.array([r for r, _ in rd])
+            save["env_done"] = np.array([float(d) for _, d in rd])
+        if name == "ant":
+            save["action"] = w["action"]
+            A = ref.AntRef(1)
+            x = np.zeros((N, A.input_dim))
+            x[:, :14], x[:, 14:28], x[:, 28:36] = w["q"], w["qd"], w["action"]
+            x[:, 36:39] = [ANT_KP, ANT_KD, ANT_MAX]
+            save["env_input"] = x
+            save["env_output_templated"] = A.step(x, ref.AntRef.IMPL_TEMPLATED)
+            save["env_output_codegen"] = A.step(x, ref.AntRef.IMPL_CODEGEN)
+            rd = [A.reward_done(x[i, :28], save["env_output_templated"][i, :28]) for i in range(N)]
             save["env_reward"] = np.array([r for r, _ in rd])
             save["env_done"] = np.array([float(d) for _, d in rd])
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)

@@ -68,7 +68,8 @@ def test_errors(bad, msg):
     ("cartpole", "cartpole.urdf", None, False), ("pendulum5", "pendulum5.urdf", None, False),
     ("sphere2", "sphere2.urdf", "plane_implicit.urdf", True),
     ("laikago", "laikago/laikago_toes_zup_xyz_xyzrot.urdf", "plane_implicit.urdf", False),
-    ("humanoid", "humanoid.urdf", "plane_implicit.urdf", True)])
+    ("humanoid", "humanoid.urdf", "plane_implicit.urdf", True),
+    ("ant", "gym/ant_org_xyz_xyzrot.urdf", "plane_implicit.urdf", False)])
 def test_matches_reference_loader(name, urdf, plane, floating):
     """Our compiler on the reference's URDFs == the flat export of the reference's own loader
     (fixtures were exported from UrdfCache::construct by tests/golden/make_golden.py)."""

@@ -13,7 +13,7 @@ from oracle import port, ref
 from tds_b200.model import fixture_path, load_model
 import tds_b200.workloads as wl
 
-CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid"]
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant"]
 
 
 def params_of(g):
@@ -58,13 +58,29 @@ def test_c_oracle_laikago_env_step_matches_reference_env(golden_dir):
     assert np.abs(out[:, :36] - g["env_output_codegen"][:, :36]).max() < 1e-10
 
 
+def test_c_oracle_ant_env_step_matches_reference_env(golden_dir):
+    """Second locomotion env of the reference (AntContactSimulation2: dt 0.01, kp 15, kd 0.3, max 3, 8 actions)."""
+    g = np.load(os.path.join(golden_dir, "ant.npz"))
+    model = load_model(fixture_path("ant"))
+    P = port.make_params(dt=0.01, friction=1.0, keep_all_points=True)
+    out = port.locomotion_step(model, P, np.array([0.0, -0.5] * 4), 6, g["env_input"], 155)
+    assert np.abs(out[:, :28] - g["env_output_templated"][:, :28]).max() < 1e-10
+    # the reference's own generated kernel (omp_model_ant_forward_zero.h) deviates from its templated path by 1e-5 on
+    # a few velocities (generated from a slightly different setup); the templated World::step path is the spec
+    assert np.abs(g["env_output_templated"][:, :28] - g["env_output_codegen"][:, :28]).max() < 2e-5
+    # reward = (x' - x) / dt equals the post-step x velocity (integrate_euler), done = z < 0.26 (ant_environment2.h:75-105)
+    alive = g["env_done"] == 0
+    assert np.abs(out[alive, 14] - g["env_reward"][alive]).max() < 1e-9
+    assert np.array_equal(out[:, 2] < 0.26, g["env_done"] == 1)
+
+
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libtds_ref.so not built (needs /root/reference)")
 @pytest.mark.parametrize("name", CONFIGS)
 def test_c_oracle_matches_live_reference(name):
     model = load_model(fixture_path(name))
     rs = ref.RefSim.from_model(model)            # reference MultiBody rebuilt from the flat model
     gen = dict(cartpole=wl.cartpole, pendulum5=wl.pendulum5, sphere2=wl.sphere2, laikago=wl.laikago_perturbed,
-               humanoid=wl.humanoid)[name]
+               humanoid=wl.humanoid, ant=wl.ant_perturbed)[name]
     w = gen(24, seed=31337)
     if name == "humanoid":
         w["q"][:, 6] = np.random.default_rng(5).uniform(0.05, 0.4, 24)   # deep, violent contacts too
@@ -74,6 +90,9 @@ def test_c_oracle_matches_live_reference(name):
     if name == "laikago":
         tau = np.zeros((24, 18))
         tau[:, 6:] = np.clip(100 * (np.array([0.2, 0, -0.7] * 4) + np.clip(w["action"], -.4, .4) - w["q"][:, 6:]) - 2 * w["qd"][:, 6:], -50, 50)
+    if name == "ant":
+        tau = np.zeros((24, 14))
+        tau[:, 6:] = np.clip(15 * (np.array([0.0, -0.5] * 4) + np.clip(w["action"], -.4, .4) - w["q"][:, 6:]) - 0.3 * w["qd"][:, 6:], -3, 3)
     for i in range(24):
         t = None if tau is None else tau[i]
         a = rs.step(w["mode"], w["q"][i], w["qd"][i], t, contact_cap=64)

@@ -19,7 +19,7 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid"]
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant"]
 
 
 def rel_err(a, ref):
@@ -356,3 +356,24 @@ def test_device_rollout_matches_cpu_rollout():
     torch.cuda.synchronize()
     after, _ = sim.env_get_state()
     assert np.array_equal(after[1::2], before[1::2]) and not np.array_equal(after[::2], before[::2])
+
+
+def test_ant_env_step_vs_reference_env(golden_dir):
+    """Second vectorized environment of the reference (AntContactSimulation2 / pytinydiffsim.VectorizedAntEnv):
+    PD + full step + reward (forward velocity) / done (torso below 0.26) against the reference's own env step."""
+    g = np.load(os.path.join(golden_dir, "ant.npz"))
+    n = g["env_input"].shape[0]
+    sim = tds_b200.ant_sim(n)
+    sim.env_set_state(g["q_in"], g["qd_in"])
+    obs = np.zeros((n, 28), dtype=np.float32); rew = np.zeros(n, dtype=np.float32); done = np.zeros(n, dtype=np.float32)
+    sim.env_step_host(g["action"].astype(np.float32), obs, rew, done)
+    ref = g["env_output_templated"]
+    assert rel_err(obs.astype(np.float64), ref[:, :28]) <= TOL
+    assert np.array_equal(done, g["env_done"])
+    assert np.max(np.abs(rew - g["env_reward"])) <= 1e-5 * max(1.0, np.max(np.abs(g["env_reward"])))
+    # the mirror of pytinydiffsim.VectorizedAntEnv: shapes, zeroed x / y, reset leaves the torso standing
+    env = tds_b200.VectorizedAntEnv(32, auto_reset_when_done=False)
+    o = env.reset()
+    assert o.shape == (32, 28) and env.action_dim() == 8 and env.obs_dim() == 28
+    out = env.step(np.zeros((32, 8)))
+    assert np.all(out.obs[:, 0] == 0) and np.all(out.obs[:, 1] == 0) and np.all(out.dones == 0)

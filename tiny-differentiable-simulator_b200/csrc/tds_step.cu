@@ -723,6 +723,9 @@ tds_step_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimP
       const float x = qv[4 * ST], z = qv[6 * ST];
       done = ((float)up_z < 0.6f) || (z < 0.2f);
       if (io.reward) io.reward[e] = done ? 0.f : x;
+    } else if (E.reward_kind == 3) {   // ant_environment2.h:75-105: done = z < 0.26, reward = (x' - x)/dt, which integrate_euler makes the x velocity
+      done = qv[2 * ST] < 0.26f;
+      if (io.reward) io.reward[e] = done ? 0.f : qdv[0];
     }
     if (io.done && E.reward_kind) io.done[e] = done ? 1.f : 0.f;
     if (done && E.auto_reset) {

@@ -1375,6 +1375,13 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         rew = done ? 0.f : x;
         if (io.reward && live) io.reward[e] = rew;
       }
+    } else if (E.reward_kind == 3) {   // ant_environment2.h:75-105: done = z < 0.26, reward = (x' - x)/dt, which integrate_euler makes the x velocity
+      constexpr int k0 = k_of_q<SP, 0>(0), k2 = k_of_q<SP, 0>(2);
+      if constexpr (!FLOAT && k0 >= 0 && k0 < NT && k2 >= 0 && k2 < NT) {
+        done = qv[k2] < 0.26f;
+        rew = done ? 0.f : qdv[k0];
+        if (io.reward && live) io.reward[e] = rew;
+      }
     } else if (E.reward_kind == 2) {
       if constexpr (FLOAT) {
         const float x = bq[4], z = bq[6];
@@ -1458,6 +1465,7 @@ template <class SP> struct SpecHost {
     auto trunk_q = [](int q) { const int k = k_of_q<SP, 0>(q); return k >= 0 && k < SP::N_TRUNK; };
     if (E->reward_kind == 1 && (SP::FLOATING || !trunk_q(0) || !trunk_q(2) || !trunk_q(3) || !trunk_q(4))) return false;
     if (E->reward_kind == 2 && !SP::FLOATING) return false;
+    if (E->reward_kind == 3 && (SP::FLOATING || !trunk_q(0) || !trunk_q(2))) return false;
     return true;
   }
 };

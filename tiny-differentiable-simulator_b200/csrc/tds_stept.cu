@@ -850,6 +850,9 @@ tds_stept_kernel(const __grid_constant__ TeamModel TM, const TeamLink* __restric
       const float x = tq[4 * STM], z = tq[6 * STM];
       done = ((float)up_z < 0.6f) || (z < 0.2f);
       if (io.reward && live) io.reward[e] = done ? 0.f : x;
+    } else if (E.reward_kind == 3) {   // ant_environment2.h:75-105: done = z < 0.26, reward = (x' - x)/dt, which integrate_euler makes the x velocity
+      done = tq[2 * STM] < 0.26f;
+      if (io.reward && live) io.reward[e] = done ? 0.f : tqd[0];
     }
     if (io.done && E.reward_kind && live) io.done[e] = done ? 1.f : 0.f;
     done_i = done ? 1 : 0;

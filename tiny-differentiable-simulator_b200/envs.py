@@ -73,7 +73,7 @@ class VectorizedLaikagoEnv:
         return q, np.zeros((n, self.sim.n_qd))
 
     def _settle(self, steps=10):
-        zero = np.zeros((self.num_envs, 12), dtype=np.float32)
+        zero = np.zeros((self.num_envs, self.action_dim()), dtype=np.float32)
         for _ in range(steps):
             self.sim.env_step_host(zero, self._obs, self._rew, self._done)
 
@@ -88,12 +88,12 @@ class VectorizedLaikagoEnv:
         noise (given [n][12], else drawn from this env's generator), 10 settle steps, then rollout_length steps of the
         per-environment linear policies [n][12*36 + 12].  Returns (total_rewards, steps)."""
         if noise is None:
-            noise = 0.05 * (self.rng.random((self.num_envs, 12)) - 0.5) * 2.0
+            noise = 0.05 * (self.rng.random((self.num_envs, self.action_dim())) - 0.5) * 2.0
         return self.sim.env_rollout_host(policies, rollout_length, shift=shift, noise=noise)
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float32)
-        assert a.shape == (self.num_envs, 12)
+        assert a.shape == (self.num_envs, self.action_dim())
         self.sim.env_step_host(a, self._obs, self._rew, self._done)
         obs = self._obs.copy()
         rewards, dones = self._rew.copy(), self._done.copy()
@@ -108,6 +108,55 @@ class VectorizedLaikagoEnv:
         obs[:, 0] = 0.0  # ars_vectorized_environment.h:285-287
         obs[:, 1] = 0.0
         return VectorizedLaikagoEnvOutput(obs, rewards, dones)
+
+
+ANT_INITIAL_POSES = np.array([0.0, -0.5] * 4)        # ant_environment2.h:43-54
+ANT_KP, ANT_KD, ANT_MAX_FORCE, ANT_DT = 15.0, 0.3, 3.0, 0.01   # ant_environment2.h:62-66
+ANT_START_Z = 0.48
+
+
+def ant_reset_pose():
+    q = np.zeros(14)
+    q[2] = ANT_START_Z
+    q[6:14] = ANT_INITIAL_POSES
+    return q
+
+
+def ant_sim(n_envs, device=0, model=None, auto_reset=False, **kw):
+    """BatchSim configured like AntContactSimulation2 (gym/ant_org_xyz_xyzrot.urdf, fixed-base emulation, dt 0.01,
+    friction 1, keep_all_points; ant_environment2.h:28-70): reward = forward velocity, done = torso below 0.26."""
+    if model is None:
+        model = load_model(fixture_path("ant"))
+    sim = BatchSim(model, n_envs, device=device, dt=ANT_DT, friction=1.0, keep_all_points=True, **kw)
+    sim.set_env(ANT_INITIAL_POSES, start_link=6, kp=ANT_KP, kd=ANT_KD, max_force=ANT_MAX_FORCE, action_limit=0.4, reward_kind=3)
+    sim.set_auto_reset(bool(auto_reset), ant_reset_pose())
+    return sim
+
+
+class VectorizedAntEnv(VectorizedLaikagoEnv):
+    """pytinydiffsim.VectorizedAntEnv (python/pytinydiffsim_includes.h:58-141): same vectorized environment template
+    as the Laikago one, over AntContactSimulation2 (8 actions, 28 observations)."""
+
+    def __init__(self, num_envs, auto_reset_when_done=True, device=0, seed=12345, model=None):
+        self.num_envs = num_envs
+        self.auto_reset = auto_reset_when_done
+        self.sim = ant_sim(num_envs, device=device, model=model)
+        self.rng = np.random.default_rng(seed)
+        self._obs = np.zeros((num_envs, self.obs_dim()), dtype=np.float32)
+        self._rew = np.zeros(num_envs, dtype=np.float32)
+        self._done = np.zeros(num_envs, dtype=np.float32)
+
+    def action_dim(self):
+        return 8
+
+    def urdf_filename(self):
+        return "gym/ant_org_xyz_xyzrot.urdf"
+
+    def _initial_state(self, n):
+        q = np.zeros((n, self.sim.n_q))
+        q[:, 2] = ANT_START_Z
+        q[:, 6:14] = ANT_INITIAL_POSES + 0.05 * (self.rng.random((n, 8)) - 0.5) * 2.0   # ant_environment2.h:124-134
+        return q, np.zeros((n, self.sim.n_qd))
 
 
 class CudaModelV1:

@@ -63,6 +63,20 @@ def laikago_perturbed(n, seed=SEED):
     return dict(q=_f32(q), qd=_f32(qd), action=_f32(act), params=dict(friction=1.0, keep_all_points=True), mode=2)
 
 
+def ant_perturbed(n, seed=SEED):
+    """Ant (gym/ant_org_xyz_xyzrot.urdf, fixed-base emulation; AntContactSimulation2: dt 0.01, kp 15, kd 0.3, max 3):
+    torso height such that 0-4 legs touch, tilted torso, non-zero velocities."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 14))
+    q[:, 0:2] = r.uniform(-0.5, 0.5, (n, 2))
+    q[:, 2] = r.uniform(0.30, 0.55, n)
+    q[:, 3:6] = r.uniform(-0.2, 0.2, (n, 3))
+    q[:, 6:14] = np.array([0.0, -0.5] * 4) + r.uniform(-0.2, 0.2, (n, 8))
+    qd = r.uniform(-0.5, 0.5, (n, 14))
+    act = r.uniform(-0.5, 0.5, (n, 8))
+    return dict(q=_f32(q), qd=_f32(qd), action=_f32(act), params=dict(dt=0.01, friction=1.0, keep_all_points=True), mode=2)
+
+
 def humanoid(n, seed=SEED, z_range=(0.9, 1.45)):
     """C5: humanoid.urdf floating base; identity-ish base orientation, joints U(+-0.05)."""
     r = np.random.default_rng(seed)
