@@ -80,6 +80,17 @@ def test_matches_reference_loader(name, urdf, plane, floating):
     assert np.abs(mine - ref).max() < 1e-15
 
 
+def test_generated_ant_table_is_the_fixture():
+    """The Ant model the specialised kernel was generated from equals the reference-exported Ant model."""
+    inc = os.path.join(os.path.dirname(tds_b200.lib_path()), "csrc", "generated", "ant_model.inc")
+    vals = []
+    for line in open(inc):
+        if line.startswith("//"):
+            continue
+        vals += [float(x) for x in line.strip().rstrip(",").split(",") if x.strip()]
+    assert np.array_equal(np.array(vals), load_model(fixture_path("ant")))
+
+
 def test_generated_laikago_table_is_the_fixture():
     """The model table embedded in the C-ABI v1 drop-in equals the reference-exported Laikago model."""
     inc = os.path.join(os.path.dirname(tds_b200.lib_path()), "csrc", "generated", "laikago_model.inc")

@@ -377,3 +377,25 @@ def test_ant_env_step_vs_reference_env(golden_dir):
     assert o.shape == (32, 28) and env.action_dim() == 8 and env.obs_dim() == 28
     out = env.step(np.zeros((32, 8)))
     assert np.all(out.obs[:, 0] == 0) and np.all(out.obs[:, 1] == 0) and np.all(out.dones == 0)
+
+
+@pytest.mark.parametrize("kernel,expect", [("spec", "model-specialised"), ("role", "tds_stepr_kernel"), ("team", "tds_stept_kernel"),
+                                           ("world", "tds_stepw_kernel")])
+def test_ant_every_kernel_vs_reference_env(kernel, expect, monkeypatch, golden_dir):
+    """Ant has geoms on the trunk (torso sphere) and capsules on the legs: 17 candidate points, sparse PGS path of the
+    specialised kernel.  Every kernel against the reference's env step, contact distances included."""
+    monkeypatch.setenv("TDS_B200_KERNEL", kernel)
+    g = np.load(os.path.join(golden_dir, "ant.npz"))
+    n = g["env_input"].shape[0]
+    sim = tds_b200.ant_sim(n)
+    out = sim.step_host(2, g["q_in"], g["qd_in"], g["action"], use_pd=True, want_contacts=True)
+    assert expect in sim.kernel_name()
+    ref = g["env_output_templated"]
+    assert rel_err(out["q"], ref[:, :14]) <= TOL and rel_err(out["qd"], ref[:, 14:28]) <= TOL
+    ref_d = np.stack(list(g["contact_dist"]))
+    assert out["contact_dist"].shape == ref_d.shape and np.max(np.abs(out["contact_dist"] - ref_d)) < 2e-6
+    sim.env_set_state(g["q_in"], g["qd_in"])
+    obs = np.zeros((n, 28), dtype=np.float32); rew = np.zeros(n, dtype=np.float32); done = np.zeros(n, dtype=np.float32)
+    sim.env_step_host(g["action"].astype(np.float32), obs, rew, done)
+    assert rel_err(obs.astype(np.float64), ref[:, :28]) <= TOL and np.array_equal(done, g["env_done"])
+    assert np.max(np.abs(rew - g["env_reward"])) <= 1e-5 * max(1.0, np.max(np.abs(g["env_reward"])))

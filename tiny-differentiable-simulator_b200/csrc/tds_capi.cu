@@ -22,10 +22,11 @@ extern "C" int tds_launch_stepr(const TeamModel* TM, const TeamLink* tl_host, un
                                 const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
                                 int precision, char* gscratch, int use_smem, cudaStream_t stream);
 extern "C" size_t tds_stepr_tile_bytes(const TeamModel* TM);
-extern "C" int tds_spec_match(const double* model, int n_model, const DevModel* D, const EnvParams* E);
-extern "C" size_t tds_spec_smem_bytes(int precision);
-extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
-                                    cudaStream_t stream);
+extern "C" int tds_spec_find(const double* model, int n_model, const DevModel* D, const EnvParams* E);
+extern "C" size_t tds_spec_smem_bytes(int spec, int precision);
+extern "C" const char* tds_spec_name(int spec);
+extern "C" int tds_launch_step_spec(int spec, const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
+                                    int precision, cudaStream_t stream);
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream);
@@ -170,18 +171,21 @@ __global__ void env_select_kernel(const float* __restrict__ mask, const float* _
 // VectorizedEnvironment::policy (ars_vectorized_environment.h:293-300): one linear layer with bias per environment
 // (neural_network.hpp:223-265, parameters = weights [n_act][n_obs] row-major | biases [n_act]); the observation is
 // q | qd with x and y zeroed (ars_vectorized_environment.h:285-287).  params: [n_params][ns] on the device.
+// One thread per (environment, action): blockIdx.y = action; consecutive threads = consecutive environments, so every
+// parameter / state row is read coalesced.
 __global__ void policy_linear_kernel(const float* __restrict__ q, const float* __restrict__ qd, const float* __restrict__ params,
                                      float* __restrict__ act, int n_q, int n_qd, int n_act, int n, int ns) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
   if (e >= n) return;
   const int n_obs = n_q + n_qd;
-  for (int a = 0; a < n_act; ++a) {
-    float s = params[(size_t)(n_act * n_obs + a) * ns + e];
-    const float* w = params + (size_t)a * n_obs * ns + e;
-    for (int k = 2; k < n_q; ++k) s += q[(size_t)k * ns + e] * w[(size_t)k * ns];
-    for (int k = 0; k < n_qd; ++k) s += qd[(size_t)k * ns + e] * w[(size_t)(n_q + k) * ns];
-    act[(size_t)a * ns + e] = s;
-  }
+  float s = params[(size_t)(n_act * n_obs + a) * ns + e];
+  const float* w = params + (size_t)a * n_obs * ns + e;
+#pragma unroll 4
+  for (int k = 2; k < n_q; ++k) s += q[(size_t)k * ns + e] * w[(size_t)k * ns];
+#pragma unroll 4
+  for (int k = 0; k < n_qd; ++k) s += qd[(size_t)k * ns + e] * w[(size_t)(n_q + k) * ns];
+  act[(size_t)a * ns + e] = s;
 }
 // ARSVectorizedWorker::rollouts bookkeeping (ars_vectorized_worker.h:117-139): done is sticky, rewards and step counts
 // accumulate only while the environment is alive
@@ -214,6 +218,7 @@ struct tds_b200_sim {
   int kernel = 4;
   int kernel_req = 4;
   bool spec_ok = false;
+  int spec_idx = -1;       // which compiled model (tds_steps.cu) equals this simulator's, -1: none
   std::vector<double> model;   // flat model (identity check of the specialised kernel)
   bool smem_ok_r[3] = {false, false, false};
   unsigned long long table_token = 0;
@@ -298,7 +303,7 @@ static int ensure_scratch(tds_b200_sim* s, int prec) {
 // (Re)build the team decomposition: depends on the model and on the action -> link map of the environment.
 static int rebuild_team(tds_b200_sim* s) {
   s->team_ok = false;
-  s->spec_ok = false;
+  s->spec_ok = false; s->spec_idx = -1;
   TeamModel base;
   int rc = tds_build_team(&s->dm[0], &s->E, &base, &s->team_table);
   if (rc != 0) return 0;   // chains etc.: the one-lane kernel is used
@@ -312,7 +317,8 @@ static int rebuild_team(tds_b200_sim* s) {
   }
   static unsigned long long next_token = 1;
   s->table_token = next_token++;
-  s->spec_ok = tds_spec_match(s->model.data(), (int)s->model.size(), &s->dm[0], &s->E) != 0;
+  s->spec_idx = tds_spec_find(s->model.data(), (int)s->model.size(), &s->dm[0], &s->E);
+  s->spec_ok = s->spec_idx >= 0;
   if (!s->team_dev) CUDA_TRY(cudaMalloc((void**)&s->team_dev, sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK));
   CUDA_TRY(cudaMemcpy(s->team_dev, s->team_table.data(), sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK, cudaMemcpyHostToDevice));
   s->team_ok = true;
@@ -481,11 +487,11 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
-  if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(p) <= (size_t)s->max_smem_optin)) kern = 3;
+  if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(s->spec_idx, p) <= (size_t)s->max_smem_optin)) kern = 3;
   if (kern == 4) {
     s->kernel = kern;
     static const int solo = getenv("TDS_B200_DEBUG_SOLO") ? 256 : 0;   // profiling aid, see tds_steps.cu
-    int rcs = tds_launch_step_spec(&s->P, &s->E, &io, mode | solo, use_pd, p, (cudaStream_t)stream);
+    int rcs = tds_launch_step_spec(s->spec_idx, &s->P, &s->E, &io, mode | solo, use_pd, p, (cudaStream_t)stream);
     if (rcs) set_err(std::string("specialised step launch: ") + cudaGetErrorString((cudaError_t)rcs));
     return rcs;
   }
@@ -670,7 +676,7 @@ int tds_b200_env_rollout_device(tds_b200_sim* s, const float* policy, int n_para
   const int saved_auto = s->E.auto_reset;
   s->E.auto_reset = 0;   // an episode ends at done (ars_vectorized_worker.h:121-133)
   for (int r = 0; r < rollout_length && rc == 0; ++r) {
-    policy_linear_kernel<<<B, T, 0, sm>>>(s->q, s->qd, policy, s->pol_act, M.n_q, M.n_qd, s->E.n_act, s->n, s->ns);
+    policy_linear_kernel<<<dim3(B, s->E.n_act), T, 0, sm>>>(s->q, s->qd, policy, s->pol_act, M.n_q, M.n_qd, s->E.n_act, s->n, s->ns);
     rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->pol_act, s->q, s->qd, nullptr, s->reward, s->done, nullptr,
                               nullptr, sm);
     rollout_accum_kernel<<<B, T, 0, sm>>>(s->reward, s->done, shift, s->sticky, total_rewards, steps, s->n);
@@ -763,7 +769,7 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   cudaStream_t sm = s->stream;
   const int T = 128, B = (n + T - 1) / T;
   // the specialised kernel reads environment-major actions and writes the observation block itself
-  const bool direct = s->kernel_req == 4 && s->spec_ok && tds_spec_smem_bytes(s->precision) <= (size_t)s->max_smem_optin;
+  const bool direct = s->kernel_req == 4 && s->spec_ok && tds_spec_smem_bytes(s->spec_idx, s->precision) <= (size_t)s->max_smem_optin;
   auto enqueue = [&]() -> int {
     CUDA_TRY(cudaMemcpyAsync(d_in, actions, in_b, cudaMemcpyHostToDevice, sm));
     if (direct) {

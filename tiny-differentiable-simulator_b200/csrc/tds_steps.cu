@@ -23,6 +23,7 @@
 #include "tds_wcommon.cuh"
 #include "tds_team.h"
 #include "generated/spec_laikago.h"
+#include "generated/spec_ant.h"
 
 namespace tdss {
 using namespace tds;
@@ -1448,13 +1449,6 @@ tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant_
   tile_body<SP, RA, RC, RS, VAR>(smem_raw, P, E, io, mode_flags & 255, use_pd, role);
 }
 
-// per-role numbers of the Laikago subtrees
-__constant__ LegTab<SpecLaikago> c_legs_laikago[TDS_TEAM_T] = {make_leg<SpecLaikago>(0), make_leg<SpecLaikago>(1), make_leg<SpecLaikago>(2),
-                                                                make_leg<SpecLaikago>(3)};
-template <> __device__ __forceinline__ const LegTab<SpecLaikago>& leg_tab<SpecLaikago>(int role) { return c_legs_laikago[role]; }
-__constant__ TrunkTab<SpecLaikago> c_trunk_laikago = make_trunk<SpecLaikago>();
-template <> __device__ __forceinline__ const TrunkTab<SpecLaikago>& trunk_tab<SpecLaikago>() { return c_trunk_laikago; }
-
 template <class SP> struct SpecHost {
   static bool matches(const DevModel* D, const EnvParams* E) {
     if (D->n_links != SP::N_LINKS || D->n_q != SP::N_Q || D->n_qd != SP::N_QD || D->floating != SP::FLOATING) return false;
@@ -1468,44 +1462,28 @@ template <class SP> struct SpecHost {
     if (E->reward_kind == 3 && (SP::FLOATING || !trunk_q(0) || !trunk_q(2))) return false;
     return true;
   }
-};
-
-}  // namespace tdss
-
-static const double k_spec_laikago_model[] = {
-#include "generated/laikago_model.inc"
-};
-
-// Does the ahead-of-time compiled kernel cover this simulator?  (same flat model, bit for bit, and same actuator map)
-extern "C" int tds_spec_match(const double* model, int n_model, const DevModel* D, const EnvParams* E) {
-  const int n = (int)(sizeof(k_spec_laikago_model) / sizeof(double));
-  if (n_model < n) return 0;
-  // visuals (tail of the flat model) do not enter the step; everything before them must agree
-  const int n_dyn = TDSM_HEADER + TDSM_BASE + SpecLaikago::N_LINKS * TDSM_LINK + SpecLaikago::N_GEOMS * TDSM_GEOM;
-  if (n_dyn > n || n_dyn > n_model) return 0;
-  for (int i = 0; i < n_dyn; ++i) {
-    if (i == TDSM_H_NVIS) continue;
-    if (!(model[i] == k_spec_laikago_model[i])) return 0;
+  // the dynamic part of the caller's flat model (everything but the visuals) must equal the compiled one bit for bit
+  static bool same_model(const double* model, int n_model, const double* mine, int n_mine) {
+    const int n_dyn = TDSM_HEADER + TDSM_BASE + SP::N_LINKS * TDSM_LINK + SP::N_GEOMS * TDSM_GEOM;
+    if (n_dyn > n_mine || n_dyn > n_model) return false;
+    for (int i = 0; i < n_dyn; ++i) {
+      if (i == TDSM_H_NVIS) continue;
+      if (!(model[i] == mine[i])) return false;
+    }
+    return true;
   }
-  return tdss::SpecHost<SpecLaikago>::matches(D, E) ? 1 : 0;
-}
-
-extern "C" size_t tds_spec_smem_bytes(int precision) {
-  using namespace tdss;
-  if (precision == 0) return (size_t)Lay<SpecLaikago, float, double, float>::TOTAL * 32 * 4;
-  if (precision == 1) return (size_t)Lay<SpecLaikago, double, double, double>::TOTAL * 32 * 4;
-  return (size_t)Lay<SpecLaikago, float, float, float>::TOTAL * 32 * 4;
-}
-
-extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
-                                    cudaStream_t stream) {
-  using namespace tdss;
-  const int tiles = (io->n + 31) / 32;
-  const size_t smem = tds_spec_smem_bytes(precision);
-  cudaError_t err = cudaSuccess;
+  static size_t smem_bytes(int precision) {
+    if (precision == 0) return (size_t)Lay<SP, float, double, float>::TOTAL * 32 * 4;
+    if (precision == 1) return (size_t)Lay<SP, double, double, double>::TOTAL * 32 * 4;
+    return (size_t)Lay<SP, float, float, float>::TOTAL * 32 * 4;
+  }
+  static int launch(const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision, cudaStream_t stream) {
+    const int tiles = (io->n + 31) / 32;
+    const size_t smem = smem_bytes(precision);
+    cudaError_t err = cudaSuccess;
 #define TDSS_LAUNCH(RA, RC, RS, VAR)                                                                    \
   do {                                                                                                  \
-    auto k = tds_step_spec_kernel<SpecLaikago, RA, RC, RS, VAR>;                                        \
+    auto k = tds_step_spec_kernel<SP, RA, RC, RS, VAR>;                                                 \
     static bool attr_set = false;                                                                       \
     if (!attr_set && smem > 48 * 1024) {                                                                \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
@@ -1518,17 +1496,65 @@ extern "C" int tds_launch_step_spec(const SimParams* P, const EnvParams* E, cons
       err = cudaGetLastError();                                                                         \
     }                                                                                                   \
   } while (0)
-  // instance: general (extra outputs / forward dynamics only), lean, lean + host layouts
-  const int var = ((mode & 255) == 0 || io->link_xf || io->contact_dist || io->qdd_out) ? 0 : ((io->act_aos && use_pd) ? 2 : 1);
-  if (var != 2 && io->act_aos) return (int)cudaErrorInvalidValue;   // host layouts are only served by the lean instance
+    // instance: general (extra outputs / forward dynamics only), lean, lean + host layouts
+    const int var = ((mode & 255) == 0 || io->link_xf || io->contact_dist || io->qdd_out) ? 0 : ((io->act_aos && use_pd) ? 2 : 1);
+    if (var != 2 && io->act_aos) return (int)cudaErrorInvalidValue;   // host layouts are only served by the lean instance
 #define TDSS_PREC(VAR)                                                      \
   do {                                                                      \
     if (precision == 0) TDSS_LAUNCH(float, double, float, VAR);             \
     else if (precision == 1) TDSS_LAUNCH(double, double, double, VAR);      \
     else TDSS_LAUNCH(float, float, float, VAR);                             \
   } while (0)
-  if (var == 0) TDSS_PREC(0); else if (var == 1) TDSS_PREC(1); else TDSS_PREC(2);
+    if (var == 0) TDSS_PREC(0); else if (var == 1) TDSS_PREC(1); else TDSS_PREC(2);
 #undef TDSS_PREC
 #undef TDSS_LAUNCH
-  return (int)err;
+    return (int)err;
+  }
+};
+
+}  // namespace tdss
+
+// ---- the models compiled into this library -----------------------------------------------------------------------------
+// per-role / trunk constant tables + table accessors of one spec
+#define TDS_SPEC_TABLES(SP, sym)                                                                                          \
+  namespace tdss {                                                                                                        \
+  __constant__ LegTab<SP> c_legs_##sym[TDS_TEAM_T] = {make_leg<SP>(0), make_leg<SP>(1), make_leg<SP>(2), make_leg<SP>(3)}; \
+  template <> __device__ __forceinline__ const LegTab<SP>& leg_tab<SP>(int role) { return c_legs_##sym[role]; }            \
+  __constant__ TrunkTab<SP> c_trunk_##sym = make_trunk<SP>();                                                             \
+  template <> __device__ __forceinline__ const TrunkTab<SP>& trunk_tab<SP>() { return c_trunk_##sym; }                    \
+  }
+TDS_SPEC_TABLES(SpecLaikago, laikago)
+TDS_SPEC_TABLES(SpecAnt, ant)
+
+static const double k_spec_laikago_model[] = {
+#include "generated/laikago_model.inc"
+};
+static const double k_spec_ant_model[] = {
+#include "generated/ant_model.inc"
+};
+
+// Which ahead-of-time compiled kernel covers this simulator?  (same flat model, bit for bit, and same actuator map)
+// Returns the spec index (0 Laikago, 1 Ant) or -1.
+extern "C" int tds_spec_find(const double* model, int n_model, const DevModel* D, const EnvParams* E) {
+  using namespace tdss;
+  if (SpecHost<SpecLaikago>::same_model(model, n_model, k_spec_laikago_model, (int)(sizeof(k_spec_laikago_model) / sizeof(double))) &&
+      SpecHost<SpecLaikago>::matches(D, E)) return 0;
+  if (SpecHost<SpecAnt>::same_model(model, n_model, k_spec_ant_model, (int)(sizeof(k_spec_ant_model) / sizeof(double))) &&
+      SpecHost<SpecAnt>::matches(D, E)) return 1;
+  return -1;
+}
+
+extern "C" size_t tds_spec_smem_bytes(int spec, int precision) {
+  using namespace tdss;
+  return spec == 0 ? SpecHost<SpecLaikago>::smem_bytes(precision) : SpecHost<SpecAnt>::smem_bytes(precision);
+}
+
+extern "C" const char* tds_spec_name(int spec) { return spec == 0 ? "laikago" : (spec == 1 ? "ant" : ""); }
+
+extern "C" int tds_launch_step_spec(int spec, const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
+                                    int precision, cudaStream_t stream) {
+  using namespace tdss;
+  if (spec == 0) return SpecHost<SpecLaikago>::launch(P, E, io, mode, use_pd, precision, stream);
+  if (spec == 1) return SpecHost<SpecAnt>::launch(P, E, io, mode, use_pd, precision, stream);
+  return (int)cudaErrorInvalidValue;
 }
