@@ -128,6 +128,14 @@ int tds_b200_env_rollout_host(tds_b200_sim* sim, const double* policy, int n_par
                               const double* noise, double noise_amp, unsigned long long seed, int settle_steps,
                               double* total_rewards, int* steps);
 
+/* Env step + visual-transform stream in the instancing renderer's layout (instance = env * n_visuals + v):
+ * positions[4 i] = x, y, z, 1 and orientations[4 i] = quaternion xyzw (device float arrays of 4 * n_envs * n_visuals),
+ * the two arrays TinyGLInstancingRenderer holds (src/visualizer/opengl/tiny_gl_instancing_renderer.cpp:366-367,440-457);
+ * same per-visual transforms as the records of the v1 output (locomotion_contact_simulation.h:281-299). */
+int tds_b200_num_visuals(const tds_b200_sim* sim);
+int tds_b200_env_step_visual_device(tds_b200_sim* sim, const float* actions, float* reward, float* done, float* positions,
+                                    float* orientations, void* stream);
+
 float* tds_b200_env_q(tds_b200_sim* sim);
 float* tds_b200_env_qd(tds_b200_sim* sim);
 

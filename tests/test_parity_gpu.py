@@ -400,3 +400,25 @@ def test_ant_every_kernel_vs_reference_env(kernel, expect, monkeypatch, golden_d
     sim.env_step_host(g["action"].astype(np.float32), obs, rew, done)
     assert rel_err(obs.astype(np.float64), ref[:, :28]) <= TOL and np.array_equal(done, g["env_done"])
     assert np.max(np.abs(rew - g["env_reward"])) <= 1e-5 * max(1.0, np.max(np.abs(g["env_reward"])))
+
+
+def test_visual_transform_stream_matches_reference_records(golden_dir):
+    """the per-visual (position, quaternion) stream in the instancing renderer's layout against the 17 x 7
+    records the reference's env step writes (locomotion_contact_simulation.h:281-299)."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "laikago.npz"))
+    n = g["env_input"].shape[0]
+    sim = tds_b200.laikago_sim(n)
+    nv = sim.num_visuals()
+    assert nv == 17
+    sim.env_set_state(g["q_in"], g["qd_in"])
+    act = sim.alloc(12)
+    act[:, :n] = torch.tensor(g["action"].T, dtype=torch.float32)
+    pos = torch.zeros((n * nv, 4), device="cuda"); quat = torch.zeros((n * nv, 4), device="cuda")
+    torch.cuda.synchronize()
+    sim.env_step_visual_device(act, pos, quat)
+    torch.cuda.synchronize()
+    rec = g["env_output_templated"][:, 36:36 + nv * 7].reshape(n, nv, 7)
+    p = pos.cpu().numpy().reshape(n, nv, 4); q = quat.cpu().numpy().reshape(n, nv, 4)
+    assert np.max(np.abs(p[..., :3] - rec[..., :3])) < 5e-6 and np.all(p[..., 3] == 1.0)
+    assert np.max(np.abs(q - rec[..., 3:])) < 5e-6

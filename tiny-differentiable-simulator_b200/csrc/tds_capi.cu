@@ -139,6 +139,30 @@ __global__ void pack_v1_output_kernel(const __grid_constant__ DevVisuals V, cons
   o[j++] = upz;
 }
 
+// Visual-transform stream in the instancing renderer's layout: instance i = env * n_vis + v;
+// positions[4 i + {0,1,2,3}] = x, y, z, 1 and orientations[4 i + {0..3}] = quaternion xyzw, the two arrays
+// TinyGLInstancingRenderer keeps (src/visualizer/opengl/tiny_gl_instancing_renderer.cpp:366-367, 440-457).  Same
+// per-visual transform as the v1 output records (locomotion_contact_simulation.h:281-299).
+__global__ void pack_visual_instances_kernel(const __grid_constant__ DevVisuals V, const float* __restrict__ link_xf,
+                                             float4* __restrict__ positions, float4* __restrict__ orientations, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (e >= n) return;
+  const float* x = link_xf + (size_t)V.v_link[v] * 12 * ns + e;
+  float R[9], t[3], Rv[9], q4[4], p[3];
+  for (int k = 0; k < 9; ++k) R[k] = x[(size_t)k * ns];
+  for (int k = 0; k < 3; ++k) t[k] = x[(size_t)(9 + k) * ns];
+  for (int r = 0; r < 3; ++r) {
+    p[r] = t[r] + R[r * 3] * V.v_t[v][0] + R[r * 3 + 1] * V.v_t[v][1] + R[r * 3 + 2] * V.v_t[v][2];
+    for (int c = 0; c < 3; ++c)
+      Rv[r * 3 + c] = R[r * 3] * V.v_R[v][c] + R[r * 3 + 1] * V.v_R[v][3 + c] + R[r * 3 + 2] * V.v_R[v][6 + c];
+  }
+  matrix_to_quat_dev(Rv, q4);
+  const size_t i = (size_t)e * V.n_vis + v;
+  positions[i] = make_float4(p[0], p[1], p[2], 1.f);
+  orientations[i] = make_float4(q4[0], q4[1], q4[2], q4[3]);
+}
+
 // ---- environment layer on the device ---------------------------------------------------------------
 // counter-based uniform in [0, 1): splitmix64 of (seed, environment, joint)
 __device__ inline float unit_uniform(unsigned long long seed, unsigned e, unsigned a) {
@@ -613,6 +637,22 @@ int tds_b200_env_step_device(tds_b200_sim* s, const float* actions, float* rewar
   if (!s) return -1;
   return tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, actions, s->q, s->qd, nullptr, reward, done,
                               nullptr, nullptr, stream);
+}
+
+int tds_b200_num_visuals(const tds_b200_sim* s) { return s ? s->vis.n_vis : -1; }
+
+int tds_b200_env_step_visual_device(tds_b200_sim* s, const float* actions, float* reward, float* done, float* positions,
+                                    float* orientations, void* stream) {
+  if (!s || !positions || !orientations) return -1;
+  if (s->vis.n_vis <= 0) { set_err("model has no link visuals"); return -2; }
+  int rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, actions, s->q, s->qd, nullptr, reward, done, nullptr,
+                                s->link_xf, stream);
+  if (rc) return rc;
+  const int T = 128, B = (s->n + T - 1) / T;
+  pack_visual_instances_kernel<<<dim3(B, s->vis.n_vis), T, 0, (cudaStream_t)stream>>>(s->vis, s->link_xf, (float4*)positions,
+                                                                                     (float4*)orientations, s->n, s->ns);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 static int ensure_env_layer(tds_b200_sim* s) {

@@ -145,6 +145,17 @@ class BatchSim:
         self._check(self._L.tds_b200_env_step_host(self._h, hp(actions), hp(obs), hp(rewards), hp(dones)),
                     "env_step_host")
 
+    def num_visuals(self):
+        return self._L.tds_b200_num_visuals(self._h)
+
+    def env_step_visual_device(self, actions, positions, orientations, reward=None, done=None, stream=None):
+        """Env step that also streams the visual transforms in the instancing renderer's layout:
+        positions / orientations are float32 CUDA tensors [n_envs * n_visuals, 4] (xyz1 / quaternion xyzw)."""
+        import torch
+        st = ctypes.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        self._check(self._L.tds_b200_env_step_visual_device(self._h, _ptr(actions), _ptr(reward), _ptr(done), _ptr(positions),
+                                                            _ptr(orientations), st), "env_step_visual_device")
+
     # ---- environment layer on the device (reset with noise + settle steps, policy rollouts) ----
     def env_reset_device(self, mask=None, noise=None, noise_amp=0.05, seed=0, settle_steps=10, stream=None):
         """mask: float32 CUDA tensor [n] (None = all); noise: float32 CUDA tensor [n_act][n_stride] (None = generated).
