@@ -198,6 +198,20 @@ template <class SP> __host__ __device__ constexpr bool trunk_is_chain() {
   }
   return true;
 }
+// Fixed-base emulation (the reference's locomotion models): a chain of MASSLESS joints carrying one body.  Massless
+// links transmit the joint force unchanged in the common frame, so the trunk's forward dynamics is one dense SPD solve
+//   (S^T Ia S) qdd = tau - S^T (Ia (a0 + sum_j c_j) + pA),   a_body = a0 + sum_j c_j + S qdd
+// with Ia / pA the articulated inertia / bias of the body (own + attached subtrees) -- what the leaf->root sweep of ABA
+// computes by six successive rank-1 eliminations of the same matrix.
+template <class SP> __host__ __device__ constexpr bool trunk_direct() {
+  if (!trunk_is_chain<SP>() || SP::FLOATING) return false;
+  for (int k = 0; k < SP::N_TRUNK; ++k) {
+    if (SP::L_FLAGS[0][k] & TDS_LF_FIXED) return false;
+    if (SP::L_SD[0][k][0] != 0.0 || SP::L_SD[0][k][1] != 0.0) return false;
+    if (k < SP::N_TRUNK - 1 && (!trunk_massless<SP>(k) || SP::L_ACC[0][k] >= 0 || SP::L_XW[0][k] >= 0)) return false;
+  }
+  return true;
+}
 template <class SP> constexpr TrunkTab<SP> make_trunk() {
   TrunkTab<SP> t{};
   for (int k = 0; k < SP::N_TRUNK; ++k) {
@@ -367,6 +381,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // with a looped chain trunk, the rows of the trunk block of M (CRBA) are computed by roles 1.. while role 0 runs the
   // trunk's ABA sweep: they would idle at the barrier otherwise
   constexpr bool CRBA_HELPERS = TRUNK_LOOP && TT > 1;
+  constexpr bool DIRECT_TRUNK = trunk_direct<SP>();
   float* const tk_q = sp<float>(smem, lane, L::TKS);
   float* const tk_qd = tk_q + NT * ST;
   float* const tk_tau = tk_qd + NT * ST;
@@ -849,7 +864,9 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     }
   }
   if (role == 0) {
-    if constexpr (TRUNK_LOOP) {
+    if constexpr (DIRECT_TRUNK) {
+      // (massless chain trunk: solved in one piece below, after the base acceleration)
+    } else if constexpr (TRUNK_LOOP) {
       // chain trunk, leaf -> root, run-time loop (same arithmetic as pass2 above; state in shared memory)
       const TrunkTab<SP>& TK = trunk_tab<SP>();
       RS* const Bs = sp<RS>(smem, lane, L::LT);   // trunk block of M, lower triangle (factorised in place later)
@@ -1015,7 +1032,74 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       a_prev.bot = v3<RA>(RA(-P.gravity[0]), RA(-P.gravity[1]), RA(-P.gravity[2]));
     }
     st6<RA>(xw_ra(0) + 6 * ST, ST, a_prev);
-    if constexpr (TRUNK_LOOP) {
+    if constexpr (DIRECT_TRUNK) {
+      constexpr int kb = NT - 1;   // the body
+      const Sv<RA> v_b = ld6<RA>(tl_v(kb), ST);
+      Abi<RA> Ia = abi_nz<RA>(); Sv<RA> pA = sv_nz<RA>();
+      if constexpr (!trunk_massless<SP>(kb)) {
+        const Rbi<RA> rb = cvt_rbi<RA>(ld_rbi<RC>(tl_rbi_slot(trunk_rbi_slot<SP>(kb)), ST));
+        Ia = abi_from_rbi(rb);
+        pA = cross_mf(v_b, rbi_mul(rb, v_b));                  // kinematics.hpp:132
+      }
+      constexpr int as = SP::L_ACC[0][kb];
+      if constexpr (as >= 0) {
+        sfor<0, TT>([&](auto Rc_) {
+          constexpr int r = decltype(Rc_)::value;
+          Abi<RA> sa; Sv<RA> sv_;
+          acc_ld27<RA>(acc_ptr_ra(r, as), ST, sa, sv_);
+          abi_add(Ia, sa); pA = pA + sv_;
+        });
+      }
+      Sv<RA> Sk[NT], Uk[NT];
+      Sv<RA> acc = a_prev;                                       // a0 + sum_j c_j
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        Sk[k] = cvt_sv<RA>(ld6<RC>(ts_S(k), ST));
+        const RA qdk = RA(qdv[k]);
+        Sv<RA> vJ; vJ.top = Sk[k].top * qdk; vJ.bot = Sk[k].bot * qdk;
+        acc = acc + cross_mm(ld6<RA>(tl_v(k), ST), vJ);          // kinematics.hpp:96-97
+        Uk[k] = abi_mul(Ia, Sk[k]);                              // forward_dynamics.hpp:111
+      });
+      const Sv<RA> w = abi_mul(Ia, acc) + pA;
+      RC Dm[NT * (NT + 1) / 2], x[NT];
+      sfor<0, NT>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        x[i] = RC(RA(tauv[i]) - dot(Sk[i], w));
+        sfor<0, i + 1>([&](auto Jc) { constexpr int j = decltype(Jc)::value; Dm[tri(i, j)] = RC(dot(Sk[i], Uk[j])); });
+      });
+      // D = L L^T (diagonal stored inverted), L y = rhs, L^T qdd = y
+      sfor<0, NT>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        sfor<0, i + 1>([&](auto Jc) {
+          constexpr int j = decltype(Jc)::value;
+          RC sacc = Dm[tri(i, j)];
+          sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sacc -= Dm[tri(i, k)] * Dm[tri(j, k)]; });
+          if constexpr (j < i) Dm[tri(i, j)] = sacc * Dm[tri(j, j)];
+          else Dm[tri(i, i)] = RC(1) / sqrt_t(sacc);
+        });
+        RC sy = x[i];
+        sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sy -= Dm[tri(i, k)] * x[k]; });
+        x[i] = sy * Dm[tri(i, i)];
+      });
+      sfor_rev<0, NT>([&](auto Ic_) {
+        constexpr int i = decltype(Ic_)::value;
+        RC sy = x[i];
+        sfor<i + 1, NT>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sy -= Dm[tri(k, i)] * x[k]; });
+        x[i] = sy * Dm[tri(i, i)];
+      });
+      Sv<RA> a = acc;
+      sfor<0, NT>([&](auto Kc) {
+        constexpr int k = decltype(Kc)::value;
+        const RA qdd = RA(x[k]);
+        a.top = axpy(Sk[k].top, qdd, a.top);
+        a.bot = axpy(Sk[k].bot, qdd, a.bot);
+        if (XOUT && mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = (float)qdd; }
+        else qdv[k] = (float)(RA(qdv[k]) + qdd * dtA);
+      });
+      constexpr int xsb = SP::L_XW[0][kb];
+      if constexpr (xsb >= 0) st6<RA>(xw_ra(xsb + 1) + 6 * ST, ST, a);
+      a_prev = a;
+    } else if constexpr (TRUNK_LOOP) {
       const TrunkTab<SP>& TK = trunk_tab<SP>();
       Sv<RA> a = a_prev;
 #pragma unroll 1
