@@ -226,6 +226,21 @@ template <class SP> constexpr TrunkTab<SP> make_trunk() {
 }
 template <class SP> __device__ const TrunkTab<SP>& trunk_tab();
 
+// contact candidates for the looped Gauss-Seidel sweep (models with many candidates): owner role, has a subtree part
+template <class SP> struct CandTab {
+  static constexpr int NC = SP::N_CAND > 0 ? SP::N_CAND : 1;
+  int owner[NC], own[NC];
+};
+template <class SP> constexpr CandTab<SP> make_cand() {
+  CandTab<SP> t{};
+  for (int g = 0; g < SP::N_CAND; ++g) {
+    t.owner[g] = SP::CAND_OWNER[g];
+    t.own[g] = (SP::CAND_OWNER[g] == 0 && SP::CAND_LPT[g] < Cls<SP>::n_pts_trunk()) ? 0 : 1;
+  }
+  return t;
+}
+template <class SP> __device__ const CandTab<SP>& cand_tab();
+
 // shared-memory layout of one tile, 4-byte words per environment
 template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int RAW = sizeof(RA) / 4, RCW = sizeof(RC) / 4, RSW = sizeof(RS) / 4;
@@ -252,7 +267,8 @@ template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int CON = ACC;                                    // contact rows per candidate (see ACC_SZ)
   static constexpr int ZT = ev(LT + NTRI * RSW);                     // z_t[NTD] (RS)
   static constexpr int WO = ev(ZT + NTD * RSW);                      // w_own[T][NOD] (RS)
-  static constexpr int FLG = ev(WO + TT * NOD * RSW);                // active masks (2 words per role), done flag
+  static constexpr int XS = ev(WO + TT * NOD * RSW);                 // impulses x[N_CAND][3] (RS) of the looped PGS sweep
+  static constexpr int FLG = ev(XS + (SP::N_CAND > 8 ? 3 * SP::N_CAND * RSW : 0));   // active masks (2 words per role), done flag
   static constexpr int SHARED = ev(FLG + 2 * TT + 2);
   static constexpr int PRIV = ev(cmax(SP::KMAX - SP::N_TRUNK, 1) * 10 * RCW);   // rigid inertias of the own links (RC)
   static constexpr int TOTAL = SHARED + TT * PRIV;
@@ -1061,36 +1077,37 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         Uk[k] = abi_mul(Ia, Sk[k]);                              // forward_dynamics.hpp:111
       });
       const Sv<RA> w = abi_mul(Ia, acc) + pA;
-      RC Dm[NT * (NT + 1) / 2], x[NT];
+      // (the sweep it replaces eliminates the same matrix in RA arithmetic, one pivot per link)
+      RA Dm[NT * (NT + 1) / 2], x[NT];
       sfor<0, NT>([&](auto Ic_) {
         constexpr int i = decltype(Ic_)::value;
-        x[i] = RC(RA(tauv[i]) - dot(Sk[i], w));
-        sfor<0, i + 1>([&](auto Jc) { constexpr int j = decltype(Jc)::value; Dm[tri(i, j)] = RC(dot(Sk[i], Uk[j])); });
+        x[i] = RA(tauv[i]) - dot(Sk[i], w);
+        sfor<0, i + 1>([&](auto Jc) { constexpr int j = decltype(Jc)::value; Dm[tri(i, j)] = dot(Sk[i], Uk[j]); });
       });
       // D = L L^T (diagonal stored inverted), L y = rhs, L^T qdd = y
       sfor<0, NT>([&](auto Ic_) {
         constexpr int i = decltype(Ic_)::value;
         sfor<0, i + 1>([&](auto Jc) {
           constexpr int j = decltype(Jc)::value;
-          RC sacc = Dm[tri(i, j)];
+          RA sacc = Dm[tri(i, j)];
           sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sacc -= Dm[tri(i, k)] * Dm[tri(j, k)]; });
           if constexpr (j < i) Dm[tri(i, j)] = sacc * Dm[tri(j, j)];
-          else Dm[tri(i, i)] = RC(1) / sqrt_t(sacc);
+          else Dm[tri(i, i)] = RA(1) / sqrt_t(sacc);
         });
-        RC sy = x[i];
+        RA sy = x[i];
         sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sy -= Dm[tri(i, k)] * x[k]; });
         x[i] = sy * Dm[tri(i, i)];
       });
       sfor_rev<0, NT>([&](auto Ic_) {
         constexpr int i = decltype(Ic_)::value;
-        RC sy = x[i];
+        RA sy = x[i];
         sfor<i + 1, NT>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sy -= Dm[tri(k, i)] * x[k]; });
         x[i] = sy * Dm[tri(i, i)];
       });
       Sv<RA> a = acc;
       sfor<0, NT>([&](auto Kc) {
         constexpr int k = decltype(Kc)::value;
-        const RA qdd = RA(x[k]);
+        const RA qdd = x[k];
         a.top = axpy(Sk[k].top, qdd, a.top);
         a.bot = axpy(Sk[k].bot, qdd, a.bot);
         if (XOUT && mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = (float)qdd; }
@@ -1337,6 +1354,46 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
 #pragma unroll
       for (int g = 0; g < NCA; ++g) { x[g][0] = RS(0); x[g][1] = RS(0); x[g][2] = RS(0); }
       const RS mu = RS(P.friction);
+      if constexpr (!DENSE) {
+        // many candidates: run-time loop over the rows (body fetched once), impulses and subtree parts of w in shared
+        // memory, only penetrating candidates are visited
+        const CandTab<SP>& CT = cand_tab<SP>();
+        RS* const xs = sp<RS>(smem, lane, L::XS);
+        for (int i = 0; i < 3 * SP::N_CAND; ++i) xs[i * ST] = RS(0);
+        for (int i = 0; i < TT * NODM; ++i) wo_s[i * ST] = RS(0);
+        for (int it = 0; it < P.pgs_iterations; ++it) {
+          sfor<0, 3>([&](auto Dc) {
+            constexpr int d = decltype(Dc)::value;
+#pragma unroll 1
+            for (int g = 0; g < SP::N_CAND; ++g) {
+              if (!((team_active >> g) & 1ull)) continue;
+              const RS* const row = sp<RS>(smem, lane, L::CON) + (size_t)g * (L::CONW / L::RSW) * ST;
+              RS* const wog = wo_s + (size_t)CT.owner[g] * NODM * ST;
+              const bool own = CT.own[g] != 0;
+              RS yo[NODMA], yt[NTDA];
+              RS yw = RS(0);
+              sfor<0, NODM>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; yo[i] = own ? row[(d * L::NOD + i) * ST] : RS(0); yw += yo[i] * wog[i * ST]; });
+              sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; yt[t] = row[(YT + d * L::NTD + t) * ST]; yw += yt[t] * wt[t]; });
+              const RS x_old = xs[(3 * g + d) * ST];
+              RS xn = (row[(BB + d) * ST] - yw + row[(BB + 3 + d) * ST] * x_old) * row[(BB + 6 + d) * ST];
+              if constexpr (d == 0) {
+                xn = xn < RS(0) ? RS(0) : xn;
+                xn = xn > RS(100000) ? RS(100000) : xn;
+              } else {
+                RS sn = xs[(3 * g) * ST];
+                sn = sn < RS(0) ? RS(0) : sn;
+                const RS lim = mu * sn;
+                xn = xn < -lim ? -lim : xn;
+                xn = xn > lim ? lim : xn;
+              }
+              xs[(3 * g + d) * ST] = xn;
+              const RS dx = xn - x_old;
+              sfor<0, NODM>([&](auto Ic_) { constexpr int i = decltype(Ic_)::value; wog[i * ST] += dx * yo[i]; });
+              sfor<0, NTD>([&](auto Tc) { constexpr int t = decltype(Tc)::value; wt[t] += dx * yt[t]; });
+            }
+          });
+        }
+      } else
       for (int it = 0; it < P.pgs_iterations; ++it) {
         sfor<0, 3>([&](auto Dc) {
           constexpr int d = decltype(Dc)::value;
@@ -1380,10 +1437,12 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         wt[i] = s * Lt[tri(i, i) * ST];
         zt[i * ST] = wt[i];
       });
+      if constexpr (DENSE) {
 #pragma unroll
-      for (int r = 0; r < TT; ++r)
+        for (int r = 0; r < TT; ++r)
 #pragma unroll
-        for (int i = 0; i < NODM; ++i) wo_s[(r * NODM + i) * ST] = wo[r][i];
+          for (int i = 0; i < NODM; ++i) wo_s[(r * NODM + i) * ST] = wo[r][i];
+      }
     }
     __syncthreads();
     TDSS_PHASE();  // 7
@@ -1606,6 +1665,8 @@ template <class SP> struct SpecHost {
   template <> __device__ __forceinline__ const LegTab<SP>& leg_tab<SP>(int role) { return c_legs_##sym[role]; }            \
   __constant__ TrunkTab<SP> c_trunk_##sym = make_trunk<SP>();                                                             \
   template <> __device__ __forceinline__ const TrunkTab<SP>& trunk_tab<SP>() { return c_trunk_##sym; }                    \
+  __constant__ CandTab<SP> c_cand_##sym = make_cand<SP>();                                                                \
+  template <> __device__ __forceinline__ const CandTab<SP>& cand_tab<SP>() { return c_cand_##sym; }                       \
   }
 TDS_SPEC_TABLES(SpecLaikago, laikago)
 TDS_SPEC_TABLES(SpecAnt, ant)
