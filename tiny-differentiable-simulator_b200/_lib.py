@@ -11,7 +11,8 @@ class LibraryMissing(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libtds_b200.so")
+    # TDS_B200_LIB: an alternative in-tree build of the same library (A/B experiments of kernel variants)
+    return os.environ.get("TDS_B200_LIB") or os.path.join(_HERE, "libtds_b200.so")
 
 
 class CudaFunctionMetaData(ctypes.Structure):

@@ -29,6 +29,9 @@ namespace tdss {
 using namespace tds;
 using namespace tdsw;
 
+#ifndef TDS_DENSE_MAX_CAND
+#define TDS_DENSE_MAX_CAND 8   // up to this many contact candidates: every candidate gets a row, unrolled branch-free PGS
+#endif
 constexpr int TT = TDS_TEAM_T;
 constexpr int ST = 32;   // element stride of every shared-memory array: [word][environment]
 
@@ -268,7 +271,7 @@ template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int ZT = ev(LT + NTRI * RSW);                     // z_t[NTD] (RS)
   static constexpr int WO = ev(ZT + NTD * RSW);                      // w_own[T][NOD] (RS)
   static constexpr int XS = ev(WO + TT * NOD * RSW);                 // impulses x[N_CAND][3] (RS) of the looped PGS sweep
-  static constexpr int FLG = ev(XS + (SP::N_CAND > 8 ? 3 * SP::N_CAND * RSW : 0));   // active masks (2 words per role), done flag
+  static constexpr int FLG = ev(XS + (SP::N_CAND > TDS_DENSE_MAX_CAND ? 3 * SP::N_CAND * RSW : 0));   // active masks (2 words per role), done flag
   static constexpr int SHARED = ev(FLG + 2 * TT + 2);
   static constexpr int PRIV = ev(cmax(SP::KMAX - SP::N_TRUNK, 1) * 10 * RCW);   // rigid inertias of the own links (RC)
   static constexpr int TOTAL = SHARED + TT * PRIV;
@@ -1228,7 +1231,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   constexpr int YT = 3 * L::NOD, BB = 3 * (L::NOD + L::NTD);   // row layout: y_own | y_t | b[3] yy[3] 1/A[3]
   // Few candidates: every candidate gets a row (zeros when it does not penetrate: x stays 0) and the sweep below is
   // branch-free straight-line code; many candidates: only penetrating points are visited.
-  constexpr bool DENSE = SP::N_CAND <= 8;
+  constexpr bool DENSE = SP::N_CAND <= TDS_DENSE_MAX_CAND;
   if (solve) {
     // contact directions: world_normal_on_b = -plane normal, friction directions from plane_space (compile-time constants)
     const RS* const Lt = sp<RS>(smem, lane, L::LT);
