@@ -100,3 +100,19 @@ def test_generated_laikago_table_is_the_fixture():
             continue
         vals += [float(x) for x in line.strip().rstrip(",").split(",") if x.strip()]
     assert np.array_equal(np.array(vals), load_model(fixture_path("laikago")))
+
+
+@pytest.mark.parametrize("name,inc,n_act", [("SpecLaikago", "laikago_model.inc", 12), ("SpecAnt", "ant_model.inc", 8)])
+def test_committed_spec_headers_are_what_gen_spec_emits(name, inc, n_act, tmp_path):
+    """The constexpr model tables the specialised kernel is compiled from are reproducible: gen_spec on the committed
+    flat model gives the committed header byte for byte."""
+    import subprocess
+    csrc = os.path.join(os.path.dirname(tds_b200.lib_path()), "csrc")
+    inc_dir = os.path.join(os.path.dirname(os.path.dirname(tds_b200.lib_path())), "include")
+    exe = str(tmp_path / "gen_spec")
+    subprocess.check_call([os.environ.get("TDS_CXX", "/usr/bin/g++"), "-std=c++17", "-O1", "-I", csrc, "-I", inc_dir,
+                           os.path.join(csrc, "gen_spec.cpp"), "-o", exe])
+    out = str(tmp_path / "spec.h")
+    subprocess.check_call([exe, name, os.path.join(csrc, "generated", inc), str(n_act), "6", out])
+    committed = os.path.join(csrc, "generated", "spec_" + name[4:].lower() + ".h")
+    assert open(out).read() == open(committed).read()
