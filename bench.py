@@ -299,7 +299,7 @@ def main():
                           if ring >= 700 else f"ring of {ring} action tensors (L2-resident)"),
                    "wall_s_timed_region": t_wall},
         "gpu_launches": K, "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4,
-                                    "d2h_bytes_per_step": n * 36 * 4 + n * 4 + n * 4, "steps": Ke, "gpu_launches_per_step": 3, "graph": "one CUDA-graph launch per step: H2D, transpose, step, pack, D2H",
+                                    "d2h_bytes_per_step": n * 36 * 4 + n * 4 + n * 4, "steps": Ke, "gpu_launches_per_step": 1, "path": "zero-copy: the step kernel reads the pinned host actions and writes obs / reward / done to pinned host memory itself (PCIe traffic inside the timed kernel)",
                                     "api": "tds_b200_env_step_host (actions host->device, obs/reward/done device->host, pinned)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,

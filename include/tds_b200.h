@@ -98,9 +98,11 @@ int tds_b200_step_host(tds_b200_sim* sim, int mode, int use_pd, const double* q,
  * (examples/ars/ars_vectorized_environment.h:214-291) minus the policy: actions [n_envs][n_act] fp32
  * host (pinned for speed) -> obs [n_envs][n_q+n_qd], rewards [n_envs], dones [n_envs] fp32 host.
  * State stays on the device between calls.  Synchronous.
- * Fast paths (same results): pinned buffers -> the copy/transpose/step/pack/copy sequence is replayed from a CUDA
- * graph captured on the third call with the same pointers; obs, rewards, dones adjacent in memory
- * (rewards == obs + n_envs*(n_q+n_qd), dones == rewards + n_envs) -> one device->host copy instead of three. */
+ * Fast paths (same results): with pinned (mapped) buffers and a model the library holds a specialised kernel for, the
+ * step kernel itself reads the actions from and writes obs / rewards / dones to host memory (one launch, no copies);
+ * otherwise pinned buffers -> the copy/transpose/step/pack/copy sequence is replayed from a CUDA graph captured on the
+ * third call with the same pointers, and obs, rewards, dones adjacent in memory (rewards == obs + n_envs*(n_q+n_qd),
+ * dones == rewards + n_envs) -> one device->host copy instead of three. */
 int tds_b200_env_set_state_host(tds_b200_sim* sim, const double* q, const double* qd);
 int tds_b200_env_get_state_host(tds_b200_sim* sim, double* q, double* qd);
 int tds_b200_env_step_host(tds_b200_sim* sim, const float* actions, float* obs, float* rewards, float* dones);

@@ -224,10 +224,14 @@ def test_kernel_selection_fallbacks():
     assert "tds_stepw_kernel" in sim.kernel_name()
 
 
-def test_env_step_host_graph_replay_matches_eager():
-    """With pinned caller buffers tds_b200_env_step_host replays a captured CUDA graph from the third call on;
-    pageable buffers take the eager path.  Both must produce the same trajectory, bit for bit."""
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_env_step_host_graph_replay_matches_eager(zero_copy, monkeypatch):
+    """With pinned caller buffers tds_b200_env_step_host either lets the step kernel read / write the host buffers itself
+    (zero-copy, specialised kernel) or replays a captured CUDA graph from the third call on; pageable buffers take the
+    eager path.  All must produce the same trajectory, bit for bit."""
     import torch
+    if not zero_copy:
+        monkeypatch.setenv("TDS_B200_NO_ZEROCOPY", "1")
     n = 512
     w = wl.laikago(n)
     a_sim, b_sim = tds_b200.laikago_sim(n), tds_b200.laikago_sim(n)

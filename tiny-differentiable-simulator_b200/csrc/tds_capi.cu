@@ -831,6 +831,28 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
     }
     return 0;
   };
+  // Zero-copy: pinned (mapped) caller buffers and the specialised kernel -> the step kernel itself reads the actions
+  // from host memory and writes observations / rewards / dones there (coalesced, staged through shared memory): one
+  // launch, no staging copies.
+  if (direct && !s->phase_clk && !getenv("TDS_B200_NO_ZEROCOPY")) {
+    void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr;
+    bool ok = is_pinned(actions) && is_pinned(obs) && is_pinned(rewards) && is_pinned(dones);
+    ok = ok && cudaHostGetDevicePointer(&da, (void*)actions, 0) == cudaSuccess;
+    if (ok && obs) ok = cudaHostGetDevicePointer(&dob, obs, 0) == cudaSuccess;
+    if (ok && rewards) ok = cudaHostGetDevicePointer(&dr, rewards, 0) == cudaSuccess;
+    if (ok && dones) ok = cudaHostGetDevicePointer(&dd, dones, 0) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    else {
+      s->io_act_aos = (const float*)da; s->io_obs_aos = (float*)dob; s->io_obs_tail = nullptr;
+      rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, dr ? (float*)dr : s->reward,
+                                dd ? (float*)dd : s->done, nullptr, nullptr, sm);
+      s->io_act_aos = nullptr; s->io_obs_aos = nullptr;
+      if (rc) return rc;
+      CUDA_TRY(cudaStreamSynchronize(sm));
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
   const void* key[4] = {actions, obs, rewards, dones};
   const bool same = s->g_key[0] == key[0] && s->g_key[1] == key[1] && s->g_key[2] == key[2] && s->g_key[3] == key[3];
   if (same && s->g_exec) {

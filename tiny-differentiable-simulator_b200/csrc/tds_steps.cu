@@ -270,7 +270,8 @@ template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int CON = ACC;                                    // contact rows per candidate (see ACC_SZ)
   static constexpr int ZT = ev(LT + NTRI * RSW);                     // z_t[NTD] (RS)
   static constexpr int WO = ev(ZT + NTD * RSW);                      // w_own[T][NOD] (RS)
-  static constexpr int XS = ev(WO + TT * NOD * RSW);                 // impulses x[N_CAND][3] (RS) of the looped PGS sweep
+  static constexpr int ASTG = ev(WO + TT * NOD * RSW);               // host-layout instance: the tile's actions, linear [env][n_act] floats
+  static constexpr int XS = ev(ASTG + SP::N_ACT);                    // impulses x[N_CAND][3] (RS) of the looped PGS sweep
   static constexpr int FLG = ev(XS + (SP::N_CAND > TDS_DENSE_MAX_CAND ? 3 * SP::N_CAND * RSW : 0));   // active masks (2 words per role), done flag
   static constexpr int SHARED = ev(FLG + 2 * TT + 2);
   static constexpr int PRIV = ev(cmax(SP::KMAX - SP::N_TRUNK, 1) * 10 * RCW);   // rigid inertias of the own links (RC)
@@ -353,10 +354,25 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       for (int k = 0; k < 6; ++k) bqd[k] = io.qd_in[(size_t)k * ns + e];
     }
   }
-  // actions: [n_act][n] (device layout) or [n][n_act] (host layout, tds_b200_env_step_host)
-  const float* const act_p = HOSTIO ? io.act_aos + (size_t)e * SP::N_ACT : io.tau_in + e;
+  // actions: [n_act][n] (device layout); the host-layout instance ([n][n_act], possibly mapped HOST memory read over
+  // PCIe) fetches the tile's block with coalesced loads now, parks it in registers during the kinematics pass, stages
+  // it in shared memory before the next barrier and computes the PD torques after it
+  constexpr int NACT_TILE = 32 * SP::N_ACT, AREG = (NACT_TILE + 32 * TT - 1) / (32 * TT);
+  float areg[AREG];
+  if constexpr (HOSTIO) {
+    const float* const ta = io.act_aos + (size_t)blockIdx.x * NACT_TILE;
+    const int rows = io.n - (int)blockIdx.x * 32;
+    const int valid = (rows < 32 ? rows : 32) * SP::N_ACT;
+#pragma unroll
+    for (int j = 0; j < AREG; ++j) {
+      const int idx = (int)threadIdx.x + 32 * TT * j;
+      areg[j] = idx < valid ? ta[idx] : 0.f;
+    }
+  }
+  float* const astg = (float*)smem + (size_t)L::ASTG * ST;
+  const float* const act_p = HOSTIO ? astg + lane * SP::N_ACT : io.tau_in + e;
   const size_t act_s = HOSTIO ? (size_t)1 : (size_t)ns;
-  if (use_pd) {
+  auto pd_torques = [&]() {
     sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
       if constexpr (!(C::flags(k) & TDS_LF_FIXED) && SP::L_ACT[0][k] >= 0) {
@@ -381,6 +397,9 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         }
       });
     }
+  };
+  if (use_pd) {
+    if constexpr (!HOSTIO) pd_torques();
   } else if (io.tau_in) {
     constexpr int off = FLOAT ? 6 : 0;
     sfor<NT, NLOC>([&](auto Kc) {
@@ -666,7 +685,25 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // set of active candidates of the environment: OR over the roles through shared memory
   flg[(2 * role) * ST] = (unsigned)my_active;
   flg[(2 * role + 1) * ST] = (unsigned)(my_active >> 32);
+  if constexpr (HOSTIO) {
+#pragma unroll
+    for (int j = 0; j < AREG; ++j) {
+      const int idx = (int)threadIdx.x + 32 * TT * j;
+      if (idx < NACT_TILE) astg[idx] = areg[j];
+    }
+  }
   const bool cta_contact = __syncthreads_or(my_active != 0ull) != 0;   // uniform: any contact in this tile
+  if constexpr (HOSTIO) {
+    pd_torques();
+    if constexpr (TRUNK_LOOP && !DIRECT_TRUNK) {
+      if (role == 0) {
+        sfor<0, NT>([&](auto Kc) {
+          constexpr int k = decltype(Kc)::value;
+          if constexpr (!(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) tk_tau[k * ST] = tauv[k];
+        });
+      }
+    }
+  }
   const bool solve = (mode == MODE_FULL) && cta_contact;
   unsigned long long team_active = 0ull;
 #pragma unroll
@@ -1543,6 +1580,10 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   }
   __syncthreads();
   const bool reset = (flg[(2 * TT) * ST] != 0u) && E.auto_reset;
+  // host-layout instance: the tile's observation block [env][n_q + n_qd] is assembled in shared memory (the contact-row
+  // region is free now) and written with coalesced stores - the destination may be mapped host memory
+  float* const ostg = (float*)smem + (size_t)L::ACC * ST;
+  static_assert(!HOSTIO || (SP::N_Q + SP::N_QD) <= L::ACC_SZ, "observation staging does not fit the reused region");
   if (live) {
     sfor<NT, NLOC>([&](auto Kc) {
       constexpr int k = decltype(Kc)::value;
@@ -1551,7 +1592,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         const float qo = reset ? E.reset_q[qi] : qv[k], qdo = reset ? 0.f : qdv[k];
         io.q_out[(size_t)qi * ns + e] = qo;
         io.qd_out[(size_t)qdi * ns + e] = qdo;
-        if constexpr (HOSTIO) if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[qi] = qo; o[SP::N_Q + qdi] = qdo; }
+        if constexpr (HOSTIO) { float* o = ostg + lane * (SP::N_Q + SP::N_QD); o[qi] = qo; o[SP::N_Q + qdi] = qdo; }
       }
     });
     if (role == 0) {
@@ -1561,7 +1602,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           const float qo = reset ? E.reset_q[CI(SP::L_QIDX[0][k])] : qv[k], qdo = reset ? 0.f : qdv[k];
           io.q_out[(size_t)CI(SP::L_QIDX[0][k]) * ns + e] = qo;
           io.qd_out[(size_t)CI(SP::L_QDIDX[0][k]) * ns + e] = qdo;
-          if constexpr (HOSTIO) if (io.obs_aos) { float* o = io.obs_aos + (size_t)e * (SP::N_Q + SP::N_QD); o[CI(SP::L_QIDX[0][k])] = qo; o[SP::N_Q + CI(SP::L_QDIDX[0][k])] = qdo; }
+          if constexpr (HOSTIO) { float* o = ostg + lane * (SP::N_Q + SP::N_QD); o[CI(SP::L_QIDX[0][k])] = qo; o[SP::N_Q + CI(SP::L_QDIDX[0][k])] = qdo; }
         }
       });
       if constexpr (FLOAT) {
@@ -1569,14 +1610,28 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         for (int k = 0; k < 7; ++k) {
           const float qo = reset ? E.reset_q[k] : bq[k];
           io.q_out[(size_t)k * ns + e] = qo;
-          if constexpr (HOSTIO) if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + k] = qo;
+          if constexpr (HOSTIO) ostg[lane * (SP::N_Q + SP::N_QD) + k] = qo;
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           const float qdo = reset ? 0.f : bqd[k];
           io.qd_out[(size_t)k * ns + e] = qdo;
-          if constexpr (HOSTIO) if (io.obs_aos) io.obs_aos[(size_t)e * (SP::N_Q + SP::N_QD) + SP::N_Q + k] = qdo;
+          if constexpr (HOSTIO) ostg[lane * (SP::N_Q + SP::N_QD) + SP::N_Q + k] = qdo;
         }
+      }
+    }
+  }
+  if constexpr (HOSTIO) {
+    if (io.obs_aos) {
+      __syncthreads();
+      constexpr int NOBS = SP::N_Q + SP::N_QD;
+      const int rows = io.n - (int)blockIdx.x * 32;
+      const int valid = (rows < 32 ? rows : 32) * NOBS;
+      float* const dst = io.obs_aos + (size_t)blockIdx.x * 32 * NOBS;
+      if (valid == 32 * NOBS && (NOBS % 4) == 0) {
+        for (int i = (int)threadIdx.x; i < 8 * NOBS; i += 32 * TT) ((float4*)dst)[i] = ((const float4*)ostg)[i];
+      } else {
+        for (int i = (int)threadIdx.x; i < valid; i += 32 * TT) dst[i] = ostg[i];
       }
     }
   }
