@@ -21,6 +21,16 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version banner, the
+# reference's "Loading URDF" chatter) is sent to stderr by pointing fd 1 at fd 2; the result goes to the saved fd.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -130,7 +140,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "reference",
                              "sample": f"{steps} steps x {sample} envs"},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -320,7 +330,7 @@ def main():
                                             "sample": sample2, "path": "omp_model_laikago_forward_zero_kernel (reference's codegen CPU path)"}
         except Exception as ex:  # the oracle library did not travel: report it, do not fake it
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
