@@ -26,8 +26,10 @@ typedef struct tds_b200_sim tds_b200_sim;
 /* arithmetic selector */
 #define TDS_B200_PREC_MIXED 0 /* default: fp32 ABA / factorisation / PGS; fp64 kinematics, contact geometry,
                                  composite inertias, CRBA products, Jacobians and LCP right-hand side */
-#define TDS_B200_PREC_F64 1
-#define TDS_B200_PREC_F32 2
+#define TDS_B200_PREC_F64 1   /* strict: every stage fp64; meets 1e-5 on every model of the parity suite */
+#define TDS_B200_PREC_F32 2   /* comparison only (the reference's own fp32 build misses the tolerance) */
+#define TDS_B200_PREC_AUTO (-1) /* default: MIXED for a model the library holds a compiled, parity-validated instance of
+                                   (Laikago, Ant), F64 otherwise */
 
 const char* tds_b200_last_error(void);
 
@@ -66,6 +68,7 @@ int tds_b200_set_env(tds_b200_sim* sim, int n_act, const double* initial_poses, 
 int tds_b200_set_auto_reset(tds_b200_sim* sim, int enable, const double* reset_q);
 
 int tds_b200_set_precision(tds_b200_sim* sim, int precision);
+int tds_b200_get_precision(const tds_b200_sim* sim);   /* the resolved selector (never AUTO) */
 /* Name of the step kernel the last tds_b200_step_* call launched (selection: DESIGN.md "Kernel selection"). */
 const char* tds_b200_kernel_name(const tds_b200_sim* sim);
 

@@ -211,6 +211,16 @@ def test_laikago_every_kernel_vs_c_oracle(kernel, expect, monkeypatch):
     assert rel_err(out3["qdd"][::8], np.array([r["qdd"] for r in refs])) <= TOL
 
 
+def test_default_precision_is_strict_unless_validated():
+    """PREC_AUTO: mixed arithmetic only for the models whose compiled instance is parity-validated in it."""
+    assert tds_b200.laikago_sim(32).precision == tds_b200.PREC_MIXED
+    assert tds_b200.ant_sim(32).precision == tds_b200.PREC_MIXED
+    assert tds_b200.BatchSim(load_model(fixture_path("humanoid")), 32).precision == tds_b200.PREC_F64
+    assert tds_b200.BatchSim(load_model(fixture_path("pendulum5")), 32).precision == tds_b200.PREC_F64
+    s = tds_b200.BatchSim(load_model(fixture_path("humanoid")), 32, precision=tds_b200.PREC_MIXED)
+    assert s.precision == tds_b200.PREC_MIXED
+
+
 def test_kernel_selection_fallbacks():
     """Models without an ahead-of-time specialisation run on the table-driven kernels (tree: role / team kernel,
     chain: one lane per environment)."""

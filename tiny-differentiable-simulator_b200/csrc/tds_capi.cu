@@ -255,7 +255,9 @@ struct tds_b200_sim {
   DevVisuals vis;
   SimParams P;
   EnvParams E;
-  int precision = TDS_B200_PREC_MIXED;
+  int precision_req = TDS_B200_PREC_AUTO;   // what the caller asked for
+  int precision = TDS_B200_PREC_F64;        // what runs: AUTO resolves to MIXED for a model with a compiled (validated)
+                                            // instance, else to the strict F64 (rebuild_team)
   int n_tau = 0, n_points = 0;
   // resident state + staging
   float *q = nullptr, *qd = nullptr, *act = nullptr, *qdd = nullptr, *reward = nullptr, *done = nullptr;
@@ -329,6 +331,7 @@ static int rebuild_team(tds_b200_sim* s) {
   s->team_ok = false;
   s->spec_ok = false; s->spec_idx = -1;
   TeamModel base;
+  if (s->precision_req == TDS_B200_PREC_AUTO) s->precision = TDS_B200_PREC_F64;
   int rc = tds_build_team(&s->dm[0], &s->E, &base, &s->team_table);
   if (rc != 0) return 0;   // chains etc.: the one-lane kernel is used
   const int sizes[3][3] = {{4, 8, 4}, {8, 8, 8}, {4, 4, 4}};
@@ -343,6 +346,7 @@ static int rebuild_team(tds_b200_sim* s) {
   s->table_token = next_token++;
   s->spec_idx = tds_spec_find(s->model.data(), (int)s->model.size(), &s->dm[0], &s->E);
   s->spec_ok = s->spec_idx >= 0;
+  if (s->precision_req == TDS_B200_PREC_AUTO) s->precision = s->spec_ok ? TDS_B200_PREC_MIXED : TDS_B200_PREC_F64;
   if (!s->team_dev) CUDA_TRY(cudaMalloc((void**)&s->team_dev, sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK));
   CUDA_TRY(cudaMemcpy(s->team_dev, s->team_table.data(), sizeof(TeamLink) * TDS_TEAM_T * TDS_TEAM_MAXK, cudaMemcpyHostToDevice));
   s->team_ok = true;
@@ -483,9 +487,10 @@ int tds_b200_set_auto_reset(tds_b200_sim* s, int enable, const double* reset_q) 
 }
 
 int tds_b200_set_precision(tds_b200_sim* s, int precision) {
-  if (!s || precision < 0 || precision > 2) return -1;
+  if (!s || precision < TDS_B200_PREC_AUTO || precision > 2) return -1;
   drop_host_graph(s);
-  s->precision = precision;
+  s->precision_req = precision;
+  s->precision = precision != TDS_B200_PREC_AUTO ? precision : (s->spec_ok ? TDS_B200_PREC_MIXED : TDS_B200_PREC_F64);
   return 0;
 }
 
@@ -768,6 +773,8 @@ int tds_b200_env_rollout_host(tds_b200_sim* s, const double* policy, int n_param
 
 // Profiling aid (not part of the drop-in surface): enable per-warp clock64() stamps at the phase
 // boundaries of the step kernel; out (host) receives [n_warps][16] stamps of the last step.
+int tds_b200_get_precision(const tds_b200_sim* s) { return s ? s->precision : -1; }
+
 const char* tds_b200_kernel_name(const tds_b200_sim* s) {
   static const char* names[5] = {"tds_step_kernel (link frame, lane per environment)", "tds_stepw_kernel (common frame, lane per environment)",
                                  "tds_stept_kernel (lane team per environment)", "tds_stepr_kernel (warp per tree role)",

@@ -13,7 +13,7 @@ from . import _lib
 from .model import model_dims
 
 MODE_FD, MODE_NOCONTACT, MODE_FULL = 0, 1, 2
-PREC_MIXED, PREC_F64, PREC_F32 = 0, 1, 2
+PREC_MIXED, PREC_F64, PREC_F32, PREC_AUTO = 0, 1, 2, -1
 
 
 def _dp(a):
@@ -27,7 +27,7 @@ def _ptr(t):
 class BatchSim:
     def __init__(self, model, n_envs, device=0, dt=1e-3, gravity=(0.0, 0.0, -9.81), friction=0.5,
                  restitution=0.0, erp=0.2, cfm=1e-5, pgs_iterations=1, keep_all_points=False,
-                 precision=PREC_MIXED):
+                 precision=PREC_AUTO):
         self._L = _lib.lib()
         self.model = np.ascontiguousarray(model, dtype=np.float64)
         self.info = model_dims(self.model)
@@ -83,7 +83,11 @@ class BatchSim:
 
     def set_precision(self, precision):
         self._check(self._L.tds_b200_set_precision(self._h, precision), "set_precision")
-        self.precision = precision
+
+    @property
+    def precision(self):
+        """The arithmetic selector that runs (PREC_AUTO resolved: mixed for a compiled model, else fp64)."""
+        return self._L.tds_b200_get_precision(self._h)
 
     # ---- device-resident fast path (torch CUDA tensors, SoA [dim, n_stride] float32) ----
     def alloc(self, dim):
