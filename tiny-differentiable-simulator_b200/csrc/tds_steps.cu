@@ -257,8 +257,7 @@ template <class SP, typename RA, typename RC, typename RS> struct Lay {
   static constexpr int TL = TS + SP::N_TRUNK * 6 * RCW;
   static constexpr int TLR = ev(TL + SP::N_TRUNK * TLW);             // rigid inertias (10 RC) of the trunk links that have mass
   static constexpr int TKS = ev(TLR + trunk_rbi_slot<SP>(SP::N_TRUNK) * 10 * RCW);   // per trunk link: q, qd, tau (floats)
-  static constexpr int TSC = ev(TKS + 3 * SP::N_TRUNK);              // sin / cos of the trunk's revolute joints (RC), computed by roles 1..
-  static constexpr int TQD = ev(TSC + 2 * SP::N_TRUNK * RCW);        // trunk qd after the FD update (NTD floats)
+  static constexpr int TQD = ev(TKS + 3 * SP::N_TRUNK);              // trunk qd after the FD update (NTD floats)
   static constexpr int ACC_IC = ev(27 * RAW);
   static constexpr int ACCW = ev(ACC_IC + 10 * RCW);                 // attachment accumulator: Ia 21 + pa 6 (RA) | Ic 10 (RC)
   static constexpr int ACC = ev(TQD + NTD);                          // [T][N_ATT]; later the partial Schur complements [T][NTRI] (RS)
@@ -331,14 +330,6 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // ---- load the coordinates of this role's joints; PD torques (locomotion_contact_simulation.h:168-258) -------------------
   float qv[SP::KMAX], qdv[SP::KMAX], tauv[SP::KMAX];   // joint coordinate / velocity / torque of local link k
   float bq[7], bqd[6];                                 // floating base (role 0)
-  float tqh[cmax(NT, 1)];                              // roles 1..: the trunk angle whose sine / cosine this role computes
-  if (role != 0) {
-    sfor<0, NT>([&](auto Kc) {
-      constexpr int k = decltype(Kc)::value;
-      if constexpr ((SP::L_FLAGS[0][k] & TDS_LF_REVOLUTE) != 0 && !(SP::L_FLAGS[0][k] & TDS_LF_FIXED))
-        if (role == 1 + (k % (TT - 1))) tqh[k] = io.q_in[(size_t)CI(SP::L_QIDX[0][k]) * ns + e];
-    });
-  }
   sfor<NT, NLOC>([&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
     if constexpr (!(C::flags(k) & TDS_LF_FIXED)) {
@@ -440,24 +431,6 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       });
     }
   }
-  // the trunk's sines / cosines come from roles 1.. (they would wait for role 0's trunk walk anyway): one joint each,
-  // round robin, through shared memory
-  {
-    RC* const tsc = sp<RC>(smem, lane, L::TSC);
-    if (role != 0) {
-      sfor<0, NT>([&](auto Kc) {
-        constexpr int k = decltype(Kc)::value;
-        if constexpr ((SP::L_FLAGS[0][k] & TDS_LF_REVOLUTE) != 0 && !(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) {
-          if (role == 1 + (k % (TT - 1))) {
-            const RC qk = RC(tqh[k]);
-            RC sk, ck;
-            sincos_t(CI(SP::L_JTYPE[0][k]) == TDSJ_REVOLUTE_AXIS ? qk * RC(0.5) : qk, &sk, &ck);
-            tsc[(2 * k) * ST] = sk; tsc[(2 * k + 1) * ST] = ck;
-          }
-        }
-      });
-    }
-  }
   // sines / cosines of every revolute joint of this role up front: independent dependency chains the scheduler can
   // interleave (inside the kinematic chain they would be serialised behind the parent transform)
   RC snv[SP::KMAX], csv[SP::KMAX];
@@ -466,17 +439,12 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     if constexpr ((C::flags(k) & TDS_LF_REVOLUTE) != 0 && !(C::flags(k) & TDS_LF_FIXED))
       sincos_t(CI(C::jtype(k)) == TDSJ_REVOLUTE_AXIS ? RC(qv[k]) * RC(0.5) : RC(qv[k]), &snv[k], &csv[k]);
   });
-  {
-    RC* const tsc = sp<RC>(smem, lane, L::TSC);
-    __syncthreads();
-    if (role == 0) {
-      sfor<0, NT>([&](auto Kc) {
-        constexpr int k = decltype(Kc)::value;
-        if constexpr ((SP::L_FLAGS[0][k] & TDS_LF_REVOLUTE) != 0 && !(SP::L_FLAGS[0][k] & TDS_LF_FIXED)) {
-          snv[k] = tsc[(2 * k) * ST]; csv[k] = tsc[(2 * k + 1) * ST];
-        }
-      });
-    }
+  if (role == 0) {
+    sfor<0, NT>([&](auto Kc) {
+      constexpr int k = decltype(Kc)::value;
+      if constexpr ((SP::L_FLAGS[0][k] & TDS_LF_REVOLUTE) != 0 && !(SP::L_FLAGS[0][k] & TDS_LF_FIXED))
+        sincos_t(CI(SP::L_JTYPE[0][k]) == TDSJ_REVOLUTE_AXIS ? RC(qv[k]) * RC(0.5) : RC(qv[k]), &snv[k], &csv[k]);
+    });
   }
   const bool want_contacts = (mode == MODE_FULL) && SP::HAS_PLANE;
   const V3<RC> pn = v3<RC>(RC(CD(SP::PLANE_N[0])), RC(CD(SP::PLANE_N[1])), RC(CD(SP::PLANE_N[2])));
