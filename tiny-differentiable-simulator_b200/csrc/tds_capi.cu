@@ -280,6 +280,10 @@ struct tds_b200_sim {
   size_t pol_params_rows = 0;
   // set around the step launch of tds_b200_env_step_host when the specialised kernel serves the host layouts itself
   const float* io_act_aos = nullptr; float* io_obs_aos = nullptr; float* io_obs_tail = nullptr;
+  const void* zc_key[4] = {nullptr, nullptr, nullptr, nullptr};   // zero-copy path: last buffer set and its device aliases
+  void* zc_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool zc_ok = false;
+  unsigned zc_calls = 0;          // the cached classification is re-validated every 64 calls
   const void* g_key[4] = {nullptr, nullptr, nullptr, nullptr};
   int g_seen = 0;
   cudaGraphExec_t g_exec = nullptr;
@@ -841,15 +845,25 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   // Zero-copy: pinned (mapped) caller buffers and the specialised kernel -> the step kernel itself reads the actions
   // from host memory and writes observations / rewards / dones there (coalesced, staged through shared memory): one
   // launch, no staging copies.
-  if (direct && !s->phase_clk && !getenv("TDS_B200_NO_ZEROCOPY")) {
+  static const bool no_zero_copy = getenv("TDS_B200_NO_ZEROCOPY") != nullptr;
+  if (direct && !s->phase_clk && !no_zero_copy) {
     void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr;
-    bool ok = is_pinned(actions) && is_pinned(obs) && is_pinned(rewards) && is_pinned(dones);
-    ok = ok && cudaHostGetDevicePointer(&da, (void*)actions, 0) == cudaSuccess;
-    if (ok && obs) ok = cudaHostGetDevicePointer(&dob, obs, 0) == cudaSuccess;
-    if (ok && rewards) ok = cudaHostGetDevicePointer(&dr, rewards, 0) == cudaSuccess;
-    if (ok && dones) ok = cudaHostGetDevicePointer(&dd, dones, 0) == cudaSuccess;
-    if (!ok) cudaGetLastError();
-    else {
+    bool ok;
+    if ((++s->zc_calls & 63u) != 0 && s->zc_key[0] == actions && s->zc_key[1] == obs && s->zc_key[2] == rewards && s->zc_key[3] == dones) {
+      ok = s->zc_ok;   // same buffers as the last call: the pointer queries (a microsecond each) are cached
+      da = s->zc_dev[0]; dob = s->zc_dev[1]; dr = s->zc_dev[2]; dd = s->zc_dev[3];
+    } else {
+      ok = is_pinned(actions) && is_pinned(obs) && is_pinned(rewards) && is_pinned(dones);
+      ok = ok && cudaHostGetDevicePointer(&da, (void*)actions, 0) == cudaSuccess;
+      if (ok && obs) ok = cudaHostGetDevicePointer(&dob, obs, 0) == cudaSuccess;
+      if (ok && rewards) ok = cudaHostGetDevicePointer(&dr, rewards, 0) == cudaSuccess;
+      if (ok && dones) ok = cudaHostGetDevicePointer(&dd, dones, 0) == cudaSuccess;
+      if (!ok) cudaGetLastError();
+      s->zc_key[0] = actions; s->zc_key[1] = obs; s->zc_key[2] = rewards; s->zc_key[3] = dones;
+      s->zc_dev[0] = da; s->zc_dev[1] = dob; s->zc_dev[2] = dr; s->zc_dev[3] = dd;
+      s->zc_ok = ok;
+    }
+    if (ok) {
       s->io_act_aos = (const float*)da; s->io_obs_aos = (float*)dob; s->io_obs_tail = nullptr;
       rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, dr ? (float*)dr : s->reward,
                                 dd ? (float*)dd : s->done, nullptr, nullptr, sm);
