@@ -53,3 +53,17 @@ def test_product_does_not_import_oracle():
             assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
             assert not re.search(r"#include\s*[\"<][^\n]*oracle", txt), f
             assert "libtds_oracle" not in txt and "libtds_ref" not in txt and "tdso_" not in txt and "tdsref_" not in txt, f
+
+
+def test_specialised_kernels_fit_two_tiles_per_sm():
+    """Shared memory of a tile of the compiled models in the default (mixed) arithmetic: for the headline model two tiles
+    must be co-resident on an SM (228 KB, 1 KB reserved per CTA) for batches with more tiles than SMs."""
+    L = ctypes.CDLL(tds_b200.lib_path())
+    L.tds_spec_smem_bytes.restype = ctypes.c_size_t
+    L.tds_spec_smem_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.tds_spec_name.restype = ctypes.c_char_p
+    assert L.tds_spec_name(0) == b"laikago" and L.tds_spec_name(1) == b"ant"
+    assert 2 * (L.tds_spec_smem_bytes(0, 0) + 1024) <= 228 * 1024          # headline model: two tiles per SM
+    for spec in (0, 1):
+        assert L.tds_spec_smem_bytes(spec, 0) <= 227 * 1024                 # default arithmetic fits one CTA
+    # (an instance that does not fit - Ant in all-fp64: 235 KB - is not launched: the table-driven kernels take over)
