@@ -11,6 +11,9 @@
  */
 #ifndef TDS_B200_H
 #define TDS_B200_H
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -162,6 +165,18 @@ void cuda_model_laikago_forward_zero(int num_total_threads, int num_blocks, int 
 CudaFunctionMetaData cuda_model_laikago_forward_zero_meta(void);
 void cuda_model_laikago_forward_zero_allocate(int num_total_threads);
 void cuda_model_laikago_forward_zero_deallocate(void);
+
+/* ---- C-ABI v2 (alt): what tds::CudaLibrary / CudaModel / CudaFunction load (src/utils/cuda/cuda_library.hpp:51-68,
+ * cuda_model.hpp:14-25, cuda_function.hpp:78-100; emitted at src/utils/cuda/cuda_codegen.hpp:32-231).  One model,
+ * "b200_laikago" (same 51 -> 411 function as cuda_model_laikago); <model>_jacobian is absent -> reported unavailable. */
+typedef struct { int output_dim; int local_input_dim; int global_input_dim; bool accumulated_output; } CudaFunctionMetaDataV2;
+void model_info(char const* const** names, int* count);
+CudaFunctionMetaDataV2 b200_laikago_forward_zero_meta(void);
+void b200_laikago_forward_zero_allocate(int num_total_threads);
+void b200_laikago_forward_zero_deallocate(void);
+bool b200_laikago_forward_zero_send_local(int num_total_threads, const double* input);
+bool b200_laikago_forward_zero_send_global(const double* input);
+void b200_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_in_header():
     text = open(os.path.join(ROOT, "include", "tds_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:tds_b200|cuda_model_laikago)_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:tds_b200|cuda_model_laikago|b200_laikago)_\w+|model_info)\s*\(", text)))
 
 
 def test_header_symbols_exported():

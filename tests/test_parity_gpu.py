@@ -436,3 +436,38 @@ def test_visual_transform_stream_matches_reference_records(golden_dir):
     p = pos.cpu().numpy().reshape(n, nv, 4); q = quat.cpu().numpy().reshape(n, nv, 4)
     assert np.max(np.abs(p[..., :3] - rec[..., :3])) < 5e-6 and np.all(p[..., 3] == 1.0)
     assert np.max(np.abs(q - rec[..., 3:])) < 5e-6
+
+
+def test_v2_abi_library_loader_sequence(golden_dir):
+    """C-ABI v2 (what tds::CudaLibrary / CudaFunction do, src/utils/cuda/cuda_library.hpp:51-68, cuda_function.hpp:78-140):
+    model_info -> <model>_forward_zero_meta / _allocate / _send_global / _send_local / launch / _deallocate."""
+    import ctypes
+
+    class MetaV2(ctypes.Structure):
+        _fields_ = [("output_dim", ctypes.c_int), ("local_input_dim", ctypes.c_int), ("global_input_dim", ctypes.c_int),
+                    ("accumulated_output", ctypes.c_bool)]
+
+    L = tds_b200.lib()
+    names = ctypes.POINTER(ctypes.c_char_p)()
+    count = ctypes.c_int(0)
+    L.model_info(ctypes.byref(names), ctypes.byref(count))
+    assert count.value == 1 and names[0] == b"b200_laikago"
+    f = names[0].decode() + "_forward_zero"
+    meta_fn = getattr(L, f + "_meta"); meta_fn.restype = MetaV2
+    meta = meta_fn()
+    assert (meta.output_dim, meta.local_input_dim, meta.global_input_dim, meta.accumulated_output) == (411, 51, 0, False)
+    assert not hasattr(L, names[0].decode() + "_jacobian")       # CudaFunction reports it unavailable
+    g = np.load(os.path.join(golden_dir, "laikago.npz"))
+    x = np.ascontiguousarray(g["env_input"])
+    n = x.shape[0]
+    dp = ctypes.POINTER(ctypes.c_double)
+    getattr(L, f + "_allocate")(n)
+    send_g = getattr(L, f + "_send_global"); send_g.restype = ctypes.c_bool
+    send_l = getattr(L, f + "_send_local"); send_l.restype = ctypes.c_bool
+    assert send_g(x.ctypes.data_as(dp)) and send_l(n, x[:, meta.global_input_dim:].ctypes.data_as(dp))
+    out = np.zeros((n, 411))
+    getattr(L, f)(n, (n + 63) // 64, 64, out.ctypes.data_as(dp))
+    getattr(L, f + "_deallocate")()
+    ref = g["env_output_templated"]
+    assert rel_err(out[:, :36], ref[:, :36]) <= TOL
+    assert np.max(np.abs(out[:, 36:155] - ref[:, 36:155])) < 5e-6 and np.array_equal(out[:, 155], ref[:, 155])

@@ -992,4 +992,53 @@ void cuda_model_laikago_forward_zero(int num_total_threads, int num_blocks, int 
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); v1_fail("forward_zero"); }
 }
 
+// ---- C-ABI v2 (src/utils/cuda/cuda_codegen.hpp:32-231, loaded by tds::CudaLibrary / CudaModel / CudaFunction,
+// src/utils/cuda/cuda_{library,model,function}.hpp): model_info + <model>_forward_zero{,_meta,_allocate,_deallocate,
+// _send_local,_send_global}.  The model is exported as "b200_laikago" (the v1 symbols keep the name cuda_model_laikago:
+// the two generations use the same symbol names with different meta structs, so they cannot share a model name).
+// <model>_jacobian is not exported: CudaFunction marks it unavailable (cuda_function.hpp:80-86).
+static std::vector<double> g_v2_local;   // thread-local inputs as last sent ([n][51], host)
+static int g_v2_sent = 0;
+
+void model_info(char const* const** names, int* count) {
+  static const char* k_names[1] = {"b200_laikago"};
+  *names = k_names;
+  *count = 1;
+}
+
+CudaFunctionMetaDataV2 b200_laikago_forward_zero_meta(void) {
+  CudaFunctionMetaDataV2 d;
+  d.output_dim = k_laikago_out; d.local_input_dim = k_laikago_in; d.global_input_dim = 0; d.accumulated_output = false;
+  return d;
+}
+
+void b200_laikago_forward_zero_allocate(int num_total_threads) {
+  cuda_model_laikago_forward_zero_allocate(num_total_threads);
+  g_v2_local.assign((size_t)num_total_threads * k_laikago_in, 0.0);
+  g_v2_sent = 0;
+}
+
+void b200_laikago_forward_zero_deallocate(void) {
+  cuda_model_laikago_forward_zero_deallocate();
+  g_v2_local.clear(); g_v2_local.shrink_to_fit();
+  g_v2_sent = 0;
+}
+
+bool b200_laikago_forward_zero_send_local(int num_total_threads, const double* input) {
+  if (!input || (size_t)num_total_threads * k_laikago_in > g_v2_local.size()) {
+    fprintf(stderr, "Error while sending thread-local input data to GPU: %d threads exceed the allocation.\n", num_total_threads);
+    return false;
+  }
+  memcpy(g_v2_local.data(), input, sizeof(double) * (size_t)num_total_threads * k_laikago_in);
+  g_v2_sent = num_total_threads;
+  return true;
+}
+
+bool b200_laikago_forward_zero_send_global(const double* input) { (void)input; return true; }   // global_input_dim = 0
+
+void b200_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output) {
+  if (num_total_threads > g_v2_sent) { fprintf(stderr, "b200_laikago_forward_zero: launch before send_local\n"); exit(1); }
+  cuda_model_laikago_forward_zero(num_total_threads, num_blocks, num_threads_per_block, output, g_v2_local.data());
+}
+
 }  // extern "C"
