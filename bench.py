@@ -49,38 +49,73 @@ def _measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: through NVML (sub-millisecond per sample, so that a
+    15 ms timed region still yields a handful of samples), falling back to polling nvidia-smi."""
+
+    _NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        try:
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(self._handle))
+            for bit, nm in self._NVML_REASONS.items():
+                if mask & bit:
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for nm, v in zip(names, f[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for nm, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._halt.wait(0.1)
+                if self._nvml is not None:   # NVML stopped answering: fall back for the rest of the run
+                    self._nvml = None
+                    self.source = "nvidia-smi"
+            self._halt.wait(0.001 if self._nvml is not None else 0.1)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": self.source}
 
 
 def cpu_reference_rate(seconds=12.0, envs=ENVS_PER_GPU, impl=0, threads=None, seed=12345):
