@@ -67,3 +67,28 @@ def test_specialised_kernels_fit_two_tiles_per_sm():
     for spec in (0, 1):
         assert L.tds_spec_smem_bytes(spec, 0) <= 227 * 1024                 # default arithmetic fits one CTA
     # (an instance that does not fit - Ant in all-fp64: 235 KB - is not launched: the table-driven kernels take over)
+
+
+def test_unsupported_models_are_refused_loudly():
+    """Host-only model check: shapes / joints the step does not implement must fail the create, never be skipped silently."""
+    import numpy as np
+    L = tds_b200.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.tds_b200_last_error.restype = ctypes.c_char_p
+
+    def check(m):
+        m = np.ascontiguousarray(m, dtype=np.float64)
+        return L.tds_b200_validate_model(m.ctypes.data_as(dp), int(m.size)), L.tds_b200_last_error().decode()
+
+    for name in ("cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant"):
+        assert check(load_model(fixture_path(name)))[0] == 0, name
+    # cartpole has box collision shapes; with a ground plane the reference would collide them (contact_plane_box)
+    m = np.array(load_model(fixture_path("cartpole")), dtype=np.float64)
+    m[7] = 1.0                                     # TDSM_H_HASPLANE
+    rc, msg = check(m)
+    assert rc == -6 and "box" in msg
+    m = np.array(load_model(fixture_path("laikago")), dtype=np.float64)
+    m[16 + 13 + 1] = 8.0                           # first link's joint type -> spherical
+    rc, msg = check(m)
+    assert rc == -3 and "spherical" in msg
+    assert check(m[:10])[0] == -1

@@ -60,6 +60,8 @@ def lib():
     L.tds_b200_env_step_visual_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.tds_b200_get_precision.restype = ci
     L.tds_b200_get_precision.argtypes = [vp]
+    L.tds_b200_validate_model.restype = ci
+    L.tds_b200_validate_model.argtypes = [ctypes.POINTER(ctypes.c_double), ci]
     L.tds_b200_kernel_name.restype = ctypes.c_char_p
     L.tds_b200_kernel_name.argtypes = [vp]
     L.tds_b200_get_dims.restype = ci
@@ -94,7 +96,7 @@ def last_error():
 # every symbol include/tds_b200.h declares (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
     "tds_b200_last_error", "tds_b200_urdf_to_model", "tds_b200_create", "tds_b200_destroy",
-    "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_set_precision", "tds_b200_get_precision", "tds_b200_kernel_name", "tds_b200_get_dims", "tds_b200_env_reset_device",
+    "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_validate_model", "tds_b200_set_precision", "tds_b200_get_precision", "tds_b200_kernel_name", "tds_b200_get_dims", "tds_b200_env_reset_device",
     "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
     "model_info", "b200_laikago_forward_zero", "b200_laikago_forward_zero_meta", "b200_laikago_forward_zero_allocate",
     "b200_laikago_forward_zero_deallocate", "b200_laikago_forward_zero_send_local", "b200_laikago_forward_zero_send_global",

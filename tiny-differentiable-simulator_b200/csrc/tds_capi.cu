@@ -359,6 +359,29 @@ static int rebuild_team(tds_b200_sim* s) {
 
 extern "C" {
 
+static const char* tds_model_error(int rc) {
+  switch (rc) {
+    case -1: return "not a flat model of this layout version (magic / size mismatch)";
+    case -2: return "too many links or collision geoms (TDS_MAX_LINKS / TDS_MAX_GEOMS)";
+    case -3: return "spherical (or unknown) joint type: not implemented";
+    case -4: return "links are not ordered parent before child";
+    case -5: return "collision geoms are not grouped by link";
+    case -6: return "box / mesh collision shape against the ground plane: the contact stage implements sphere and capsule only";
+    default: return "unknown error";
+  }
+}
+
+// Host-only check (no GPU needed): 0 when tds_b200_create would accept the model, else the negative code; the reason
+// is left in tds_b200_last_error().
+int tds_b200_validate_model(const double* model, int n_model) {
+  if (!model) { set_err("null model"); return -1; }
+  DevModel* D = new DevModel;
+  const int rc = tds_build_dev_model(model, n_model, D);
+  delete D;
+  if (rc) set_err(std::string("unsupported model: ") + tds_model_error(rc));
+  return rc;
+}
+
 tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int device) {
   if (!model || n_envs <= 0) { set_err("bad arguments"); return nullptr; }
   int ndev = 0;
@@ -374,7 +397,7 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
   DevModel base;
   int rc = tds_build_dev_model(model, n_model, &base);
   if (rc) {
-    set_err("unsupported model (rc=" + std::to_string(rc) + "): magic/size mismatch, too many links/geoms, or spherical joints");
+    set_err(std::string("unsupported model: ") + tds_model_error(rc));
     delete s;
     return nullptr;
   }

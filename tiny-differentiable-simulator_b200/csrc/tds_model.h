@@ -143,6 +143,9 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     for (int k = 0; k < 3; ++k) D->g_half[g][k] = gg[TDSM_G_R + k * 3 + 2] * hl;  // R_local * (0,0,L/2)
     if (D->g_type[g] == TDSG_SPHERE) n_points += 1;
     if (D->g_type[g] == TDSG_CAPSULE) n_points += 2;
+    // the contact stage implements plane x sphere and plane x capsule; a box / mesh against the ground plane would be
+    // silently contact-free here while the reference collides it (contact_point.hpp:164-198): refuse the model
+    if (D->has_plane && D->g_type[g] != TDSG_SPHERE && D->g_type[g] != TDSG_CAPSULE) return -6;
   }
   D->max_contacts = D->has_plane ? n_points : 0;
   {  // geoms are enumerated base first, then link 0, 1, ...: ranges per link
