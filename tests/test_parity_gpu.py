@@ -471,3 +471,19 @@ def test_v2_abi_library_loader_sequence(golden_dir):
     ref = g["env_output_templated"]
     assert rel_err(out[:, :36], ref[:, :36]) <= TOL
     assert np.max(np.abs(out[:, 36:155] - ref[:, 36:155])) < 5e-6 and np.array_equal(out[:, 155], ref[:, 155])
+
+
+def test_reference_vectorized_environment_with_our_stepper_plugin(tmp_path):
+    """SURVEY 8b, C++ plugin row: the reference's own VectorizedEnvironment (compiled from /root/reference headers in the
+    build container, tests/integration/stepper_check.cpp) steps once with its serial CPU stepper and once with a
+    CustomForwardDynamicsStepper that forwards to libtds_b200.so, installed in default_stepper_; outputs must agree."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "integration", "stepper_check.bin")
+    if not os.path.exists(exe):
+        pytest.skip("tests/integration/stepper_check.bin not built (needs /root/reference in the build container)")
+    model = np.asarray(load_model(fixture_path("laikago")), dtype=np.float64)
+    path = str(tmp_path / "laikago_model.bin")
+    model.tofile(path)
+    r = subprocess.run([exe, path, "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max rel err" in r.stdout
