@@ -681,7 +681,21 @@ static int compute_contacts(const Model* M, const State* st, Contact* out, int c
           ++nc;
         }
       }
-      /* boxes / meshes vs plane: not in scope for the configs (cartpole has no plane). */
+      else if (type == TDSG_BOX) { /* contact_plane_box, contact_point.hpp:164-198: a sphere at each of the 8 corners */
+        double orn[4], len, r = 1e-2; /* max(1e-2, Box::radius); the URDF loader leaves the box radius at 0 */
+        matrix_to_quat(tr.R, orn);
+        len = sqrt(orn[0] * orn[0] + orn[1] * orn[1] + orn[2] * orn[2] + orn[3] * orn[3]);
+        for (int k = 0; k < 4; ++k) orn[k] /= len;
+        const double d[3] = {0.5 * gg[TDSM_G_P] - r, 0.5 * gg[TDSM_G_P + 1] - r, 0.5 * gg[TDSM_G_P + 2] - r};
+        for (int c = 0; c < 8; ++c) { /* Box::get_corner_points order, geometry.hpp:244-260: x outermost, z innermost */
+          double off[3] = {(c & 4) ? -d[0] : d[0], (c & 2) ? -d[1] : d[1], (c & 1) ? -d[2] : d[2]}, ro[3], pos[3];
+          quat_rotate(orn, off, ro);
+          for (int k = 0; k < 3; ++k) pos[k] = tr.t[k] + ro[k];
+          if (nc < cap) { plane_sphere(pn, pc, pos, r, &out[nc]); out[nc].link_b = jj; out[nc].geom = g; }
+          ++nc;
+        }
+      }
+      /* meshes vs plane: not restated (no config uses them). */
     }
   }
   return nc;

@@ -106,3 +106,29 @@ def test_c_oracle_matches_live_reference(name):
             assert np.array_equal(a["contact_idx"], b["contact_idx"])
     Ma, Mb = rs.mass_matrix(w["q"][0]), port.mass_matrix(model, w["q"][0])
     assert np.abs(Ma - Mb).max() < 1e-10
+
+
+@pytest.mark.skipif(not ref.available() or not os.path.isdir(os.environ.get("TDS_REFERENCE_ROOT", "/root/reference") + "/data"),
+                    reason="needs the reference tree (URDF data) and oracle/_ref")
+def test_c_oracle_plane_box_contacts_match_live_reference():
+    """Groundwork for SURVEY 8f.3: plane x box (a sphere of radius max(1e-2, r) at each corner, contact_point.hpp:164-198)
+    restated in the C oracle, pinned against the reference on cartpole.urdf (two boxes) dropped onto the ground plane.
+    The product refuses such models for now (tds_b200_validate_model: -6)."""
+    D = os.environ.get("TDS_REFERENCE_ROOT", "/root/reference") + "/data/"
+    rs = ref.RefSim.from_urdf(D + "cartpole.urdf", D + "plane_implicit.urdf", False)
+    model = rs.export_model()
+    params = dict(dt=1e-3, friction=0.5, keep_all_points=True)
+    rs.set_params(**params)
+    P = port.make_params(**params)
+    rng = np.random.default_rng(8)
+    for _ in range(12):
+        q = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-1.0, 1.0)])
+        qd = rng.uniform(-1, 1, 2)
+        tau = np.array([rng.uniform(-5, 5), 0.0])
+        a = rs.step(2, q, qd, tau, contact_cap=64)
+        b = port.step(model, P, 2, q, qd, tau)
+        assert a["n_contacts"] == b["n_contacts"] == 16
+        assert np.array_equal(a["contact_idx"], b["contact_idx"])
+        assert np.abs(a["contact_data"][:, 9] - b["contact_data"][:, 9]).max() < 1e-12
+        scale = max(1.0, np.abs(a["qd"]).max())
+        assert np.abs(a["q"] - b["q"]).max() < 1e-9 and np.abs(a["qd"] - b["qd"]).max() / scale < 1e-9
