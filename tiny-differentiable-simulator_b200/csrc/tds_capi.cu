@@ -284,11 +284,6 @@ struct tds_b200_sim {
   void* zc_dev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool zc_ok = false;
   unsigned zc_calls = 0;          // the cached classification is re-validated every 64 calls
-  unsigned* zc_counter = nullptr;           // device: tiles finished (reset by the last one)
-  volatile unsigned* zc_flag = nullptr;     // pinned + mapped host word the last tile writes the sequence number to
-  unsigned* zc_flag_dev = nullptr;
-  unsigned zc_seq = 0;
-  bool io_flag_on = false;
   const void* g_key[4] = {nullptr, nullptr, nullptr, nullptr};
   int g_seen = 0;
   cudaGraphExec_t g_exec = nullptr;
@@ -462,8 +457,6 @@ void tds_b200_destroy(tds_b200_sim* s) {
   cudaSetDevice(s->device);
   cudaFree(s->q); cudaFree(s->qd); cudaFree(s->act); cudaFree(s->qdd); cudaFree(s->reward); cudaFree(s->done);
   drop_host_graph(s);
-  cudaFree(s->zc_counter);
-  if (s->zc_flag) cudaFreeHost((void*)s->zc_flag);
   cudaFree(s->rq); cudaFree(s->rqd); cudaFree(s->zero_act); cudaFree(s->pol_act); cudaFree(s->sticky); cudaFree(s->r_total);
   cudaFree(s->pol_params); cudaFree(s->act_qidx); cudaFree(s->r_steps);
   cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk); cudaFree(s->team_dev);
@@ -547,7 +540,6 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.reward = reward; io.done = done; io.contact_dist = contact_dist; io.link_xf = link_xf;
   io.phase_clk = s->phase_clk;
   io.act_aos = s->io_act_aos; io.obs_aos = s->io_obs_aos; io.obs_tail = s->io_obs_tail;
-  io.done_counter = s->io_flag_on ? s->zc_counter : nullptr; io.host_flag = s->io_flag_on ? s->zc_flag_dev : nullptr; io.seq = s->zc_seq;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
@@ -895,38 +887,11 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
       s->zc_ok = ok;
     }
     if (ok) {
-      static const bool use_flag = !getenv("TDS_B200_NO_DONE_FLAG");
-      if (use_flag && !s->zc_flag) {   // completion flag (see StepIO): one mapped host word + a device counter
-        void* hp = nullptr; void* dp = nullptr;
-        if (cudaHostAlloc(&hp, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess &&
-            cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess && cudaMalloc((void**)&s->zc_counter, sizeof(unsigned)) == cudaSuccess &&
-            cudaMemset(s->zc_counter, 0, sizeof(unsigned)) == cudaSuccess) {
-          *(unsigned*)hp = 0u;
-          s->zc_flag = (volatile unsigned*)hp; s->zc_flag_dev = (unsigned*)dp;
-        } else { cudaGetLastError(); if (hp) cudaFreeHost(hp); }
-      }
-      const bool flag = use_flag && s->zc_flag && s->zc_counter;
       s->io_act_aos = (const float*)da; s->io_obs_aos = (float*)dob; s->io_obs_tail = nullptr;
-      s->io_flag_on = flag;
-      if (flag) { ++s->zc_seq; if (s->zc_seq == 0) s->zc_seq = 1; }
       rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, dr ? (float*)dr : s->reward,
                                 dd ? (float*)dd : s->done, nullptr, nullptr, sm);
-      s->io_act_aos = nullptr; s->io_obs_aos = nullptr; s->io_flag_on = false;
+      s->io_act_aos = nullptr; s->io_obs_aos = nullptr;
       if (rc) return rc;
-      if (flag) {
-        // spin on the host word the last tile writes; a bounded number of polls, then fall back to the stream
-        const unsigned want = s->zc_seq;
-        for (long long spins = 0; *s->zc_flag != want; ++spins) {
-          if (spins > 200000000LL || ((spins & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(sm) != cudaErrorNotReady)) {
-            CUDA_TRY(cudaStreamSynchronize(sm));
-            break;
-          }
-#if defined(__x86_64__)
-          __builtin_ia32_pause();
-#endif
-        }
-        return 0;
-      }
       CUDA_TRY(cudaStreamSynchronize(sm));
       CUDA_TRY(cudaGetLastError());
       return 0;

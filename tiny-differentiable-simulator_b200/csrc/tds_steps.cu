@@ -1635,20 +1635,6 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       }
     }
   }
-  if constexpr (HOSTIO) {
-    if (io.host_flag) {
-      __threadfence_system();   // this thread's writes to host memory (observations, reward, done) are performed system-wide
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(io.done_counter, 1u);
-        if (prev == gridDim.x - 1) {   // last tile: every other tile fenced its writes before its increment
-          *io.done_counter = 0u;
-          __threadfence_system();
-          *(volatile unsigned*)io.host_flag = io.seq;
-        }
-      }
-    }
-  }
   TDSS_PHASE();  // 9
 #undef TDSS_PHASE
 #undef TDSS_STAMP

@@ -104,10 +104,5 @@ struct StepIO {
   const float* act_aos;                 // actions [n][n_act] (environment-major), or null -> tau_in
   float* obs_aos;                       // observations [n][n_q + n_qd] = q | qd after the step, or null
   float* obs_tail;                      // reward [n] then done [n] behind the observations, or null
-  // completion flag of the zero-copy host path: the last CTA to finish writes `seq` to a mapped host word, so that the
-  // host can return as soon as its buffers are complete instead of paying a stream synchronisation
-  unsigned* done_counter;               // device, zero between launches; or null
-  unsigned* host_flag;                  // mapped host memory
-  unsigned seq;
   int n; int n_stride;
 };
