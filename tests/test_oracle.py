@@ -132,3 +132,27 @@ def test_c_oracle_plane_box_contacts_match_live_reference():
         assert np.abs(a["contact_data"][:, 9] - b["contact_data"][:, 9]).max() < 1e-12
         scale = max(1.0, np.abs(a["qd"]).max())
         assert np.abs(a["q"] - b["q"]).max() < 1e-9 and np.abs(a["qd"] - b["qd"]).max() / scale < 1e-9
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libtds_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["laikago", "ant", "humanoid", "sphere2"])
+def test_c_oracle_solver_parameters_match_live_reference(name):
+    """Non-default solver settings (several PGS sweeps, restitution, other erp / cfm / friction, keep_all_points off):
+    the oracle must follow the reference beyond the configuration the goldens were generated with."""
+    model = load_model(fixture_path(name))
+    rs = ref.RefSim.from_model(model)
+    gen = dict(laikago=wl.laikago_perturbed, ant=wl.ant_perturbed, humanoid=wl.humanoid, sphere2=wl.sphere2)[name]
+    w = gen(8, seed=2718)
+    if name == "humanoid":
+        w["q"][:, 6] = np.random.default_rng(6).uniform(0.1, 0.5, 8)
+    params = dict(w["params"])
+    params.update(pgs_iterations=4, restitution=0.3, erp=0.1, cfm=1e-4, friction=0.7, keep_all_points=False)
+    rs.set_params(**params)
+    P = port.make_params(**params)
+    for i in range(8):
+        tau = w["tau"][i] if w.get("tau") is not None else None
+        a = rs.step(2, w["q"][i], w["qd"][i], tau, contact_cap=64)
+        b = port.step(model, P, 2, w["q"][i], w["qd"][i], tau)
+        scale = max(1.0, np.abs(a["qd"]).max())
+        assert np.abs(a["q"] - b["q"]).max() < 1e-9
+        assert np.abs(a["qd"] - b["qd"]).max() / scale < 1e-9
