@@ -116,3 +116,61 @@ def test_committed_spec_headers_are_what_gen_spec_emits(name, inc, n_act, tmp_pa
     subprocess.check_call([exe, name, os.path.join(csrc, "generated", inc), str(n_act), "6", out])
     committed = os.path.join(csrc, "generated", "spec_" + name[4:].lower() + ".h")
     assert open(out).read() == open(committed).read()
+
+
+def _random_urdf(rng, n_links):
+    """A random tree of links: every joint type the step supports, unit / negative / oblique axes, joint and inertial
+    origins with rotations, sphere / capsule / box collision shapes with their own origins, link visuals."""
+    def v3(lo, hi):
+        return " ".join("%.6g" % x for x in rng.uniform(lo, hi, 3))
+    parts = ['<?xml version="1.0"?>', '<robot name="rnd">']
+    for i in range(n_links):
+        # (the reference's loader exits on a massless floating base: the root always has mass)
+        mass = 0.0 if (i > 0 and rng.random() < 0.15) else rng.uniform(0.1, 5.0)
+        ixx, iyy, izz = (rng.uniform(1e-3, 0.5, 3) if mass > 0 else np.zeros(3))
+        s = [f'<link name="l{i}">',
+             f'<inertial><origin xyz="{v3(-0.2, 0.2)}" rpy="{v3(-1, 1)}"/><mass value="{mass:.6g}"/>'
+             f'<inertia ixx="{ixx:.6g}" iyy="{iyy:.6g}" izz="{izz:.6g}" ixy="0" ixz="0" iyz="0"/></inertial>']
+        for _ in range(rng.integers(0, 3)):
+            kind = rng.integers(0, 3)
+            geo = (f'<sphere radius="{rng.uniform(0.02, 0.2):.6g}"/>' if kind == 0 else
+                   f'<capsule radius="{rng.uniform(0.02, 0.1):.6g}" length="{rng.uniform(0.1, 0.6):.6g}"/>' if kind == 1 else
+                   f'<box size="{v3(0.05, 0.4)}"/>')
+            s.append(f'<collision><origin xyz="{v3(-0.3, 0.3)}" rpy="{v3(-1.5, 1.5)}"/><geometry>{geo}</geometry></collision>')
+        if rng.random() < 0.6:
+            s.append(f'<visual><origin xyz="{v3(-0.1, 0.1)}" rpy="{v3(-1, 1)}"/><geometry><sphere radius="0.1"/></geometry></visual>')
+        s.append('</link>')
+        parts.append("".join(s))
+    axes = ["1 0 0", "0 1 0", "0 0 1", "-1 0 0", "0 0 -1", "0.6 0 0.8", "0.3 -0.4 0.5", None]
+    order = list(range(1, n_links))
+    rng.shuffle(order)                       # joints in a random document order
+    for i in order:
+        parent = int(rng.integers(0, i))
+        jt = ["revolute", "continuous", "prismatic", "fixed"][rng.integers(0, 4)]
+        ax = axes[rng.integers(0, len(axes))]
+        axis = f'<axis xyz="{ax}"/>' if (ax is not None and jt != "fixed") else ""
+        lim = '<limit lower="-1" upper="1" effort="10" velocity="10"/>' if jt in ("revolute", "prismatic") else ""
+        parts.append(f'<joint name="j{i}" type="{jt}"><parent link="l{parent}"/><child link="l{i}"/>'
+                     f'<origin xyz="{v3(-0.5, 0.5)}" rpy="{v3(-2, 2)}"/>{axis}{lim}</joint>')
+    parts.append("</robot>")
+    return "\n".join(parts)
+
+
+@pytest.mark.skipif(not have_reference_tree(), reason="differential test against the reference's own URDF loader")
+@pytest.mark.parametrize("seed", range(24))
+def test_random_urdfs_match_reference_loader(seed, tmp_path):
+    """Our URDF -> flat-model compiler against UrdfCache::construct + UrdfToMultiBody (through oracle/_ref) on random trees:
+    link order, joint typing (axis exactly +1 -> REVOLUTE_X/Y/Z, otherwise *_AXIS), transforms, inertias, shapes, visuals."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(1000 + seed)
+    text = _random_urdf(rng, int(rng.integers(2, 12)))
+    path = tmp_path / "rnd.urdf"
+    path.write_text(text)
+    floating = bool(seed % 2)
+    plane = os.path.join(REFERENCE_ROOT, "data", "plane_implicit.urdf") if seed % 3 else None
+    theirs = ref.RefSim.from_urdf(str(path), plane, floating).export_model()
+    mine = compile_urdf(str(path), plane, floating)
+    assert mine.shape == theirs.shape, text
+    assert np.abs(mine - theirs).max() < 1e-14, text
