@@ -118,7 +118,7 @@ def test_committed_spec_headers_are_what_gen_spec_emits(name, inc, n_act, tmp_pa
     assert open(out).read() == open(committed).read()
 
 
-def _random_urdf(rng, n_links):
+def _random_urdf(rng, n_links, massless_links=True, boxes=True):
     """A random tree of links: every joint type the step supports, unit / negative / oblique axes, joint and inertial
     origins with rotations, sphere / capsule / box collision shapes with their own origins, link visuals."""
     def v3(lo, hi):
@@ -126,13 +126,13 @@ def _random_urdf(rng, n_links):
     parts = ['<?xml version="1.0"?>', '<robot name="rnd">']
     for i in range(n_links):
         # (the reference's loader exits on a massless floating base: the root always has mass)
-        mass = 0.0 if (i > 0 and rng.random() < 0.15) else rng.uniform(0.1, 5.0)
+        mass = 0.0 if (massless_links and i > 0 and rng.random() < 0.15) else rng.uniform(0.1, 5.0)
         ixx, iyy, izz = (rng.uniform(1e-3, 0.5, 3) if mass > 0 else np.zeros(3))
         s = [f'<link name="l{i}">',
              f'<inertial><origin xyz="{v3(-0.2, 0.2)}" rpy="{v3(-1, 1)}"/><mass value="{mass:.6g}"/>'
              f'<inertia ixx="{ixx:.6g}" iyy="{iyy:.6g}" izz="{izz:.6g}" ixy="0" ixz="0" iyz="0"/></inertial>']
         for _ in range(rng.integers(0, 3)):
-            kind = rng.integers(0, 3)
+            kind = rng.integers(0, 3 if boxes else 2)
             geo = (f'<sphere radius="{rng.uniform(0.02, 0.2):.6g}"/>' if kind == 0 else
                    f'<capsule radius="{rng.uniform(0.02, 0.1):.6g}" length="{rng.uniform(0.1, 0.6):.6g}"/>' if kind == 1 else
                    f'<box size="{v3(0.05, 0.4)}"/>')

@@ -156,3 +156,40 @@ def test_c_oracle_solver_parameters_match_live_reference(name):
         scale = max(1.0, np.abs(a["qd"]).max())
         assert np.abs(a["q"] - b["q"]).max() < 1e-9
         assert np.abs(a["qd"] - b["qd"]).max() / scale < 1e-9
+
+
+@pytest.mark.skipif(not ref.available() or not os.path.isdir(os.environ.get("TDS_REFERENCE_ROOT", "/root/reference") + "/data"),
+                    reason="needs the reference tree and oracle/_ref")
+@pytest.mark.parametrize("seed", range(12))
+def test_c_oracle_matches_live_reference_on_random_models(seed, tmp_path):
+    """Beyond the six named configurations: random trees (all joint kinds, oblique axes, rotated origins, spheres and
+    capsules on the plane, fixed or floating base) stepped by the reference and by the C oracle."""
+    from test_model_compiler import _random_urdf
+    rng = np.random.default_rng(5000 + seed)
+    text = _random_urdf(rng, int(rng.integers(2, 9)), massless_links=False, boxes=False)
+    path = tmp_path / "rnd.urdf"
+    path.write_text(text)
+    floating = bool(seed % 2)
+    plane = os.environ.get("TDS_REFERENCE_ROOT", "/root/reference") + "/data/plane_implicit.urdf"
+    rs = ref.RefSim.from_urdf(str(path), plane, floating)
+    model = rs.export_model()
+    params = dict(dt=1e-3, friction=0.8, keep_all_points=bool(seed % 3 == 0))
+    rs.set_params(**params)
+    P = port.make_params(**params)
+    nq, nqd = rs.n_q, rs.n_qd
+    for _ in range(4):
+        q = rng.uniform(-0.8, 0.8, nq)
+        if floating:
+            quat = rng.normal(size=4); quat /= np.linalg.norm(quat)
+            q[:4] = quat
+            q[4:7] = [rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.0, 0.6)]
+        qd = rng.uniform(-1, 1, nqd)
+        tau = rng.uniform(-2, 2, rs.n_tau)
+        for mode in (0, 2):
+            a = rs.step(mode, q, qd, tau, contact_cap=64)
+            b = port.step(model, P, mode, q, qd, tau)
+            scale = max(1.0, np.abs(a["qd"]).max(), np.abs(a["qdd"]).max())
+            assert np.abs(a["qdd"] - b["qdd"]).max() / scale < 1e-8
+            if mode == 2:
+                assert a["n_contacts"] == b["n_contacts"]
+                assert np.abs(a["q"] - b["q"]).max() < 1e-8 and np.abs(a["qd"] - b["qd"]).max() / scale < 1e-8
