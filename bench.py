@@ -239,13 +239,207 @@ def run_reference_arm(args, rank, world):
     emit(line)
 
 
+# ---- the other BASELINE.json configurations (the headline one, laikago4096, is main() below) --------------------------
+# bytes = SURVEY.md section 8d, ALGORITHMIC bytes per env-step (fp32 state in, fp32 state out)
+CONFIGS = {
+    "laikago4096": dict(envs=4096, bytes=344, model="laikago", workload=WORKLOAD),
+    "cartpole64": dict(envs=64, bytes=36, model="cartpole", gen="cartpole",
+                       workload="cartpole.urdf, 64 parallel envs, no contacts: FD -> integrate_euler (BASELINE.json configs[0])"),
+    "pendulum5_fd": dict(envs=4096, bytes=80, model="pendulum5", gen="pendulum5",
+                         workload="pendulum5.urdf, 4096 envs, forward_dynamics only (BASELINE.json configs[1])"),
+    "sphere2_16384": dict(envs=16384, bytes=124, model="sphere2", gen="sphere2",
+                          workload="sphere2.urdf on plane_implicit, 16384 envs, contact LCP solve + contact record (BASELINE.json configs[2])"),
+    "humanoid4096": dict(envs=4096, bytes=532, model="humanoid", gen="humanoid",
+                         workload="humanoid.urdf on plane, 4096 envs/GPU (32768 on 8 GPUs), full step, LCP contacts (BASELINE.json configs[4])"),
+}
+
+
+def _config_reference_rate(name, w, model, seconds):
+    """The reference's own CPU implementation of the same pipeline (oracle/_ref: forward_dynamics / World::step, templated
+    path), one host thread, batches stepped inside one foreign call."""
+    from oracle import ref
+    sim = ref.RefSim.from_model(model)
+    sim.set_params(**w["params"])
+    n, mode = w["q"].shape[0], w["mode"]
+    tau = w.get("tau")
+    full = None
+    if tau is not None:
+        full = np.zeros((n, sim.n_tau)); full[:, -tau.shape[1]:] = tau
+    b = min(n, 256)
+    sim.step_batch(mode, w["q"][:b], w["qd"][:b], None if full is None else full[:b])
+    k, t0 = 0, time.perf_counter()
+    while True:
+        sim.step_batch(mode, w["q"][:b], w["qd"][:b], None if full is None else full[:b])
+        k += b
+        if time.perf_counter() - t0 >= seconds:
+            break
+    el = time.perf_counter() - t0
+    return k / el, f"{k} env-steps in {el:.1f} s on 1 thread"
+
+
+def run_config(args, rank, world, local_rank):
+    """cartpole64 / pendulum5_fd / sphere2_16384 / humanoid4096: same metric, same JSON contract, through the generic
+    device entry point tds_b200_step_device (value) and the host-buffer entry point tds_b200_step_host (e2e)."""
+    C = CONFIGS[args.config]
+    import tds_b200
+    import tds_b200.workloads as wl
+    from tds_b200.model import fixture_path, load_model
+    n, K, W = args.envs, args.steps, max(args.warmup, 3)
+    model = load_model(fixture_path(C["model"]))
+    w = getattr(wl, C["gen"])(n, seed=wl.SEED + rank)
+    mode = w["mode"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_s = 4.0
+        v, sample = _config_reference_rate(args.config, w, model, sample_s)
+        per = max(16, int(v * 60.0 / (K + W)))          # a step of this arm = a bounded sample of the batch
+        per = min(per, n)
+        from oracle import ref
+        sim = ref.RefSim.from_model(model); sim.set_params(**w["params"])
+        tau = w.get("tau"); full = None
+        if tau is not None:
+            full = np.zeros((n, sim.n_tau)); full[:, -tau.shape[1]:] = tau
+        def batch():
+            sim.step_batch(mode, w["q"][:per], w["qd"][:per], None if full is None else full[:per])
+        for _ in range(W):
+            batch()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            batch()
+        el = time.perf_counter() - t0
+        val = per * K / el
+        emit({"metric": METRIC, "value": val, "unit": "env-steps/s", "impl": "reference", "n_gpus": args.gpus, "steps": K, "warmup": W,
+              "ms_per_step": 1e3 * el / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+              "data": "synthetic", "config": {"workload": C["workload"], "envs_per_gpu": n, "envs_per_step": per,
+                                              "path": "forward_dynamics / World::step (templated CPU path), one thread"},
+              "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": 1, "kind": "reference", "sample": f"{K} steps x {per} envs"},
+              "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    prec = {0: tds_b200.PREC_AUTO, 1: tds_b200.PREC_F64, 2: tds_b200.PREC_F32, 3: tds_b200.PREC_MIXED}[args.precision]
+    sim = tds_b200.BatchSim(model, n, device=local_rank, precision=prec, **w["params"])
+    ns = sim.n_stride
+    def soa(a, dim):
+        t = torch.zeros((max(dim, 1), ns), device=dev)
+        if a is not None and dim:
+            t[:dim, :n] = torch.tensor(np.ascontiguousarray(a.T), dtype=torch.float32)
+        return t
+    q, qd = soa(w["q"], sim.n_q), soa(w["qd"], sim.n_qd)
+    tau = w.get("tau")
+    ring = 16
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    taus = None
+    if tau is not None and sim.n_tau:
+        base = soa(tau[:, -sim.n_tau:], sim.n_tau)
+        taus = [base * float(s) for s in (0.5 + torch.rand(ring, generator=g))]
+    qdd = sim.alloc(sim.n_qd) if mode == 0 else None
+    cdist = sim.alloc(sim.n_contact_points) if (mode == 2 and sim.n_contact_points) else None
+    ccount = torch.zeros(ns, dtype=torch.int32, device=dev) if cdist is not None else None
+    clinks = torch.zeros((2 * max(sim.n_contact_points, 1), ns), dtype=torch.int32, device=dev) if cdist is not None else None
+    L, st = sim._L, torch.cuda.current_stream().cuda_stream
+    import ctypes
+
+    def one_step(i):
+        sim.step_device(mode, q, qd, None if taus is None else taus[i % ring], qdd_out=qdd, contact_dist=cdist)
+        if cdist is not None:   # the contact record of SURVEY 8d: count + (link_a, link_b) list of the step, on the device
+            L.tds_b200_contact_list_device(sim._h, ctypes.c_void_p(cdist.data_ptr()), ctypes.c_void_p(ccount.data_ptr()),
+                                           ctypes.c_void_p(clinks.data_ptr()), ctypes.c_void_p(st))
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > the 126 MB L2
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        ev[i][0].record()
+        one_step(W + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    if not bool(torch.isfinite(q).all()):
+        raise SystemExit("bench.py: non-finite state after the timed region")
+    # end to end through tds_b200_step_host: fp64 AoS host buffers in and out (the MultiBody-style arrays a
+    # VectorizedEnvironment caller holds), copies + layout conversion + step inside the timed region
+    hq, hqd = w["q"].copy(), w["qd"].copy()
+    htau = None if tau is None or not sim.n_tau else np.ascontiguousarray(tau[:, -sim.n_tau:])
+    Ke = min(K, 100)
+    for _ in range(3):
+        sim.step_host(mode, hq, hqd, htau)
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        o = sim.step_host(mode, hq, hqd, htau)
+        if mode != 0:
+            hq, hqd = o["q"], o["qd"]
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = n * world * K / (total_ms * 1e-3)
+    peaks, peak_src = _measured_peaks()
+    achieved = C["bytes"] * n / ((total_ms * 1e-3) / K) / 1e9
+    in_b = 8 * n * (sim.n_q + sim.n_qd + (sim.n_tau if htau is not None else 0))
+    out_b = 8 * n * (sim.n_qd if mode == 0 else sim.n_q + sim.n_qd)
+    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": ["f32 + f64 (mixed)", "f64", "f32"][sim.precision], "data": "synthetic",
+            "config": {"workload": C["workload"], "envs_per_gpu": n, "global_envs": n * world, "mode": int(mode),
+                       "parallelism": f"env-sharded x{world}, no data-path collective",
+                       "timing": "CUDA events around each of the K steps (individual launches), summed, max over ranks",
+                       "l2": "flushed between timed steps (192 MiB written outside the event pairs)"},
+            "gpu_launches": K * (2 if cdist is not None else 1),
+            "e2e": {"value": n * world * Ke / float(te.item()), "unit": "env-steps/s", "h2d_bytes_per_step": in_b, "d2h_bytes_per_step": out_b,
+                    "steps": Ke, "api": "tds_b200_step_host (fp64 AoS host arrays in / out, pageable)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peak_src, "kernel": sim.kernel_name(),
+                         "algorithmic_bytes_per_env_step": C["bytes"]},
+            "clocks": clocks}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, sample = _config_reference_rate(args.config, w, model, 5.0)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "reference", "sample": sample}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default: the size the config names)")
+    ap.add_argument("--config", default="laikago4096", choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration; the default is the one the metric is quoted on (configs[3])")
     ap.add_argument("--precision", type=int, default=0, help="0 mixed (fp32 ABA + fp64 contact), 1 fp64, 2 fp32")
     ap.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying a CUDA graph")
     ap.add_argument("--small-ring", action="store_true", help="16 action buffers (L2-resident) instead of 768 (> L2)")
@@ -258,6 +452,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.envs is None:
+        args.envs = CONFIGS[args.config]["envs"]
+    if args.config != "laikago4096":
+        run_config(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return

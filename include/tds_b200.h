@@ -112,6 +112,20 @@ int tds_b200_step_host(tds_b200_sim* sim, int mode, int use_pd, const double* q,
  * otherwise pinned buffers -> the copy/transpose/step/pack/copy sequence is replayed from a CUDA graph captured on the
  * third call with the same pointers, and obs, rewards, dones adjacent in memory (rewards == obs + n_envs*(n_q+n_qd),
  * dones == rewards + n_envs) -> one device->host copy instead of three. */
+/* ---- contact-pair index lists (World::compute_contacts_multi_body_internal, src/world.hpp:212-281;
+ * MultiBodyContactPoint::{multi_body_a, link_a, multi_body_b, link_b}, src/mb_constraint_solver.hpp:29-40) -------------
+ * The candidate points of a model are static: plane (body 0, base link -1) x every sphere / capsule end of the robot
+ * (body 1) in the reference's enumeration order.  tds_b200_contact_pairs writes one tuple (body_a, link_a, body_b, link_b)
+ * per candidate (the list World::mb_contacts_ holds after every step) and returns their number.
+ * tds_b200_contact_list_*: the list the constraint solver keeps in a step (all candidates with keep_all_points, else
+ * those with distance < 0: resolve_collision, mb_constraint_solver.hpp:169-180), computed on the device from the
+ * contact distances of that step: count[e] and (link_a, link_b) of the k-th kept point, -9 beyond count.
+ *   device: contact_dist [n_points][ns] (output of tds_b200_step_device), count [ns], links [2 * n_points][ns]
+ *   host:   uses the distances of the last tds_b200_step_host(..., contact_dist != NULL); count [n], links [n][n_points][2] */
+int tds_b200_contact_pairs(const tds_b200_sim* sim, int* tuples, int cap);
+int tds_b200_contact_list_device(tds_b200_sim* sim, const float* contact_dist, int* count, int* links, void* stream);
+int tds_b200_contact_list_host(tds_b200_sim* sim, int* count, int* links);
+
 int tds_b200_env_set_state_host(tds_b200_sim* sim, const double* q, const double* qd);
 int tds_b200_env_get_state_host(tds_b200_sim* sim, double* q, double* qd);
 int tds_b200_env_step_host(tds_b200_sim* sim, const float* actions, float* obs, float* rewards, float* dones);

@@ -60,6 +60,8 @@ def lib():
         L.tdsref_set_params.argtypes = [vp, ctypes.c_double, dp, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]
         L.tdsref_step.argtypes = [vp, ctypes.c_int, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, ctypes.c_int]
+        if hasattr(L, "tdsref_step_batch"):
+            L.tdsref_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp]
         L.tdsref_link_transforms.argtypes = [vp, dp]
         L.tdsref_mass_matrix.argtypes = [vp, dp, dp]
         L.tdsref_point_jacobian.argtypes = [vp, dp, ctypes.c_int, dp, dp]
@@ -161,6 +163,16 @@ class RefSim:
         out["contact_idx"] = cidx[:n].copy()
         out["contact_data"] = cdat[:n].copy()
         return out
+
+    def step_batch(self, mode, q, qd, tau=None):
+        """n independent steps in one foreign call (bench.py's reference arm); returns (q', qd', qdd)."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qd = np.ascontiguousarray(qd, dtype=np.float64)
+        n = q.shape[0]
+        t = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+        qo, qdo, qddo = np.zeros_like(q), np.zeros_like(qd), np.zeros_like(qd)
+        lib().tdsref_step_batch(self._h, mode, n, _dp(q), _dp(qd), _dp(t), _dp(qo), _dp(qdo), _dp(qddo))
+        return qo, qdo, qddo
 
     def link_transforms(self):
         out = np.zeros((self.n_links, 12))

@@ -405,6 +405,20 @@ void tdsref_step(void* hv, int mode, const double* q, const double* qd, const do
     h->s32->step(mode, q, qd, tau, q_out, qd_out, qdd_out, qd_pre_contact, n_contacts, contact_idx, contact_data, contact_cap);
 }
 
+// n steps back to back (timing loops of bench.py's reference arm: no per-step foreign-call overhead); fp64 instance.
+// q [n][dof], qd [n][dof_qd], tau [n][dof_actuated] or NULL; outputs [n][...] or NULL.
+void tdsref_step_batch(void* hv, int mode, int n, const double* q, const double* qd, const double* tau, double* q_out,
+                       double* qd_out, double* qdd_out) {
+  Handle* h = (Handle*)hv;
+  auto* s = h->s64;
+  if (!s) return;
+  const int nq = s->mb->dof(), nqd = s->mb->dof_qd(), nt = s->mb->dof_actuated();
+  for (int i = 0; i < n; ++i)
+    s->step(mode, q + (size_t)i * nq, qd + (size_t)i * nqd, tau ? tau + (size_t)i * nt : nullptr,
+            q_out ? q_out + (size_t)i * nq : nullptr, qd_out ? qd_out + (size_t)i * nqd : nullptr,
+            qdd_out ? qdd_out + (size_t)i * nqd : nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
 void tdsref_link_transforms(void* hv, double* out) {
   Handle* h = (Handle*)hv;
   if (h->prec == 64) h->s64->link_transforms(out); else h->s32->link_transforms(out);

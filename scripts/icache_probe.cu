@@ -60,7 +60,7 @@ template <int KB4> __global__ void __launch_bounds__(128) probe_streams(int pass
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-static float* g_out; static long long* g_clk; static long long h[148 * 4 * 8];
+static float* g_out; static long long* g_clk; static long long h[592 * 4 * 8];
 template <class K> static void run(const char* name, K kern, int kb, int grid, int threads, int passes, int nstream, int launches) {
   for (int l = 0; l < launches; ++l) {
     cudaMemset(g_clk, 0, sizeof(h));
@@ -80,7 +80,7 @@ template <class K> static void run(const char* name, K kern, int kb, int grid, i
 }
 #define SWEEP(KB4) run("same stream", probe<KB4, 0>, KB4 * 4, 148, 128, 5, 1, 2); run("same stream", probe<KB4, 0>, KB4 * 4, 148, 32, 5, 1, 1);
 int main() {
-  cudaMalloc(&g_out, 148 * 128 * 4); cudaMalloc(&g_clk, sizeof(h));
+  cudaMalloc(&g_out, 592 * 128 * 4); cudaMalloc(&g_clk, sizeof(h));
   SWEEP(1) SWEEP(2) SWEEP(4) SWEEP(6) SWEEP(8) SWEEP(10) SWEEP(12) SWEEP(16) SWEEP(24) SWEEP(32)
   // distinct streams on one SM: 2 and 4 copies, 16 KB and 64 KB each
   run("2 streams (4 warps)", probe_streams<4>, 16, 148, 128, 5, 2, 1);

@@ -19,8 +19,6 @@ buf = np.zeros((nw, 16), dtype=np.int64)
 L.tds_b200_debug_phase_clocks(sim._h, 1, buf.ctypes.data, nw)
 print("kernel:", sim.kernel_name())
 names = ["load+PD", "pass1 FK+contacts", "pass2 ABA+CRBA", "base+pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate+write"]
-if os.environ.get("TDS_B200_KERNEL") == "link":
-    names = ["load+PD", "pass1 FK", "contacts", "pass2 ABA+CRBA", "base", "pass3", "cholesky", "J+Y", "PGS", "backsub", "integrate", "writeback"]
 K = len(names)
 kern = os.environ.get("TDS_B200_KERNEL", "spec")
 if kern in ("role", "spec"):   # one record per (tile, role): show every role, phases are separated by CTA barriers

@@ -71,17 +71,18 @@ def main():
         if name == "ant":   # PD torques of the env (host restatement only to feed the raw reference step)
             f = ANT_KP * (ANT_POSES + np.clip(w["action"], -0.4, 0.4) - w["q"][:, 6:14]) + ANT_KD * (0.0 - w["qd"][:, 6:14])
             tau = np.zeros((N, 14)); tau[:, 6:14] = np.clip(f, -ANT_MAX, ANT_MAX)
-        outs = dict(q=[], qd=[], qdd=[], dist=[], link_b=[], n_contacts=[])
+        outs = dict(q=[], qd=[], qdd=[], dist=[], link_a=[], link_b=[], n_contacts=[])
         for i in range(N):
             o = sim.step(mode, w["q"][i], w["qd"][i], None if tau is None else tau[i], contact_cap=64)
             outs["q"].append(o["q"]); outs["qd"].append(o["qd"]); outs["qdd"].append(o["qdd"])
             outs["n_contacts"].append(o["n_contacts"])
             outs["dist"].append(o["contact_data"][:, 9] if o["n_contacts"] else np.zeros(0))
+            outs["link_a"].append(o["contact_idx"][:, 0] if o["n_contacts"] else np.zeros(0, dtype=np.int32))
             outs["link_b"].append(o["contact_idx"][:, 1] if o["n_contacts"] else np.zeros(0, dtype=np.int32))
         save = dict(q_in=w["q"], qd_in=w["qd"], mode=mode,
                     q_out=np.array(outs["q"]), qd_out=np.array(outs["qd"]), qdd=np.array(outs["qdd"]),
                     n_contacts=np.array(outs["n_contacts"]), contact_dist=np.array(outs["dist"]),
-                    contact_link_b=np.array(outs["link_b"]))
+                    contact_link_a=np.array(outs["link_a"]), contact_link_b=np.array(outs["link_b"]))
         if tau is not None:
             save["tau"] = tau
         for k, v in w["params"].items():

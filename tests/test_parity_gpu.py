@@ -62,6 +62,24 @@ def test_golden_vectors(name, precision, golden_dir):
         assert out["contact_dist"].shape == ref_d.shape          # same number of candidate points
         assert np.array_equal(out["contact_dist"] < 0, ref_d < 0)  # same penetrating set
         assert np.max(np.abs(out["contact_dist"] - ref_d)) < 1e-6
+    # contact-pair index lists, bit-exact (north_star): the list World::mb_contacts_ holds after the step (every emitted
+    # point, enumeration order of src/world.hpp:212-281) and the list the constraint solver keeps
+    # (resolve_collision, mb_constraint_solver.hpp:169-180), both as (link_a, link_b) tuples from the reference's own run
+    if mode == 2:
+        la, lb = np.stack(list(g["contact_link_a"])).astype(np.int32), np.stack(list(g["contact_link_b"])).astype(np.int32)
+        pairs = sim.contact_pairs()
+        assert pairs.shape == (la.shape[1], 4) and np.array_equal(g["n_contacts"], np.full(n, pairs.shape[0]))
+        for e in range(n):
+            assert np.array_equal(pairs[:, 1], la[e]) and np.array_equal(pairs[:, 3], lb[e])
+        assert np.all(pairs[:, 0] == 0) and np.all(pairs[:, 2] == 1)
+        ref_d = np.stack(list(g["contact_dist"])) if la.shape[1] else np.zeros((n, 0))
+        keep = np.ones_like(ref_d, dtype=bool) if bool(g["param_keep_all_points"]) else ref_d < 0
+        assert np.array_equal(out["contact_count"], keep.sum(axis=1).astype(np.int32))
+        for e in range(n):
+            k = int(keep[e].sum())
+            want = np.stack([la[e][keep[e]], lb[e][keep[e]]], axis=1) if k else np.zeros((0, 2), dtype=np.int32)
+            assert np.array_equal(out["contact_links"][e, :k], want)
+            assert np.all(out["contact_links"][e, k:] == -9)
 
 
 def test_laikago_env_step_vs_reference_env(golden_dir):
@@ -182,7 +200,7 @@ def test_device_auto_reset():
 
 
 @pytest.mark.parametrize("kernel,expect", [("spec", "model-specialised"), ("role", "tds_stepr_kernel"), ("team", "tds_stept_kernel"),
-                                           ("world", "tds_stepw_kernel"), ("link", "tds_step_kernel")])
+                                           ("world", "tds_stepw_kernel")])
 def test_laikago_every_kernel_vs_c_oracle(kernel, expect, monkeypatch):
     """The library picks the ahead-of-time specialised kernel for the Laikago model; the table-driven kernels stay
     selectable (TDS_B200_KERNEL, read by tds_b200_create) and every one of them meets the same parity bar."""
@@ -209,6 +227,110 @@ def test_laikago_every_kernel_vs_c_oracle(kernel, expect, monkeypatch):
     out3 = sim.step_host(0, w["q"], w["qd"], tau)
     refs = [port.step(model, P, 0, w["q"][i], w["qd"][i], tau[i]) for i in range(0, n, 8)]
     assert rel_err(out3["qdd"][::8], np.array([r["qdd"] for r in refs])) <= TOL
+
+
+SOLVER_SWEEP = [dict(pgs_iterations=4), dict(restitution=0.3), dict(erp=0.1), dict(cfm=1e-4), dict(friction=0.7),
+                dict(pgs_iterations=4, restitution=0.3, erp=0.1, cfm=1e-4, friction=0.7)]
+
+
+@pytest.mark.parametrize("kernel", ["spec", "role", "team", "world"])
+@pytest.mark.parametrize("over", SOLVER_SWEEP, ids=lambda d: "+".join(f"{k}={v}" for k, v in d.items()))
+def test_laikago_solver_parameters_every_kernel(kernel, over, monkeypatch):
+    """Non-default MultiBodyConstraintSolver parameters (pgs_iterations_, erp_, cfm_; World::default_restitution / friction)
+    on every kernel: more than one Gauss-Seidel sweep exercises the sweep loops, restitution / erp the right-hand side, cfm
+    the diagonal, friction the bounds (mb_constraint_solver.hpp:101-142, 285-436)."""
+    monkeypatch.setenv("TDS_B200_KERNEL", kernel)
+    n = 128
+    model = load_model(fixture_path("laikago"))
+    w = wl.laikago_perturbed(n, seed=31337)
+    params = dict(w["params"]); params.update(over)
+    sim = tds_b200.BatchSim(model, n, **params)
+    sim.set_env(tds_b200.envs.LAIKAGO_INITIAL_POSES, start_link=6, kp=100.0, kd=2.0, max_force=50.0)
+    qd = w["qd"].copy()
+    qd[:, 2] -= 0.5                      # approaching the ground: restitution and the normal rows matter
+    qd = qd.astype(np.float32).astype(np.float64)
+    out = sim.step_host(2, w["q"], qd, w["action"], use_pd=True)
+    P = port.make_params(**params)
+    x = np.zeros((n, 51))
+    x[:, :18], x[:, 18:36], x[:, 36:48], x[:, 48:] = w["q"], qd, w["action"], [100.0, 2.0, 50.0]
+    ref = port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
+    base = port.locomotion_step(model, port.make_params(**w["params"]), tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, x, 411)
+    assert np.max(np.abs(ref[:, 18:36] - base[:, 18:36])) > 1e-4      # the parameter does change the answer
+    assert rel_err(out["q"], ref[:, :18]) <= TOL
+    assert rel_err(out["qd"], ref[:, 18:36]) <= TOL
+
+
+@pytest.mark.parametrize("name,gen", [("sphere2", wl.sphere2), ("ant", wl.ant_perturbed), ("humanoid", wl.humanoid)])
+@pytest.mark.parametrize("over", SOLVER_SWEEP[::5] + [dict(keep_all_points=True), dict(keep_all_points=False)],
+                         ids=lambda d: "+".join(f"{k}={v}" for k, v in d.items()))
+def test_other_models_solver_parameters(name, gen, over, golden_dir):
+    """Solver-parameter sweep and both settings of keep_all_points_ (humanoid: 35 candidates = the 105-row LCP) on the
+    models served by the table-driven kernels and the Ant instance, against the C oracle."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = load_model(fixture_path(name))
+    n = g["q_in"].shape[0]
+    params = params_from_golden(g); params.update(over)
+    sim = tds_b200.BatchSim(model, n, precision=tds_b200.PREC_F64 if name == "humanoid" else tds_b200.PREC_AUTO, **params)
+    tau = g["tau"] if "tau" in g.files else None
+    if tau is not None and tau.shape[1] != sim.n_tau:
+        tau = tau[:, -sim.n_tau:]
+    out = sim.step_host(2, g["q_in"], g["qd_in"], tau, want_contacts=True)
+    P = port.make_params(**params)
+    full_tau = g["tau"] if "tau" in g.files else [None] * n
+    refs = [port.step(model, P, 2, g["q_in"][i], g["qd_in"][i], full_tau[i]) for i in range(n)]
+    assert rel_err(out["q"], np.array([r["q"] for r in refs])) <= TOL
+    assert rel_err(out["qd"], np.array([r["qd"] for r in refs])) <= TOL
+    keep_all = bool(params.get("keep_all_points", False))
+    for e in range(0, n, 7):
+        d = refs[e]["contact_data"][:, 9]
+        k = d.size if keep_all else int((d < 0).sum())
+        assert out["contact_count"][e] == k
+        want = refs[e]["contact_idx"] if keep_all else refs[e]["contact_idx"][d < 0]
+        assert np.array_equal(out["contact_links"][e, :k], want)
+
+
+def test_sphere2_at_16384_subset_vs_oracle():
+    """BASELINE.json configs[2] at its full size: sphere2 on the plane, 16384 environments, contact LCP; every 64th
+    environment against the C oracle, the whole batch for determinism and finiteness."""
+    n = 16384
+    model = load_model(fixture_path("sphere2"))
+    w = wl.sphere2(n, seed=5)
+    sim = tds_b200.BatchSim(model, n, **w["params"])
+    a = sim.step_host(2, w["q"], w["qd"], w["tau"], want_contacts=True)
+    b = sim.step_host(2, w["q"], w["qd"], w["tau"])
+    assert np.array_equal(a["q"], b["q"]) and np.array_equal(a["qd"], b["qd"]) and np.all(np.isfinite(a["qd"]))
+    P = port.make_params(**w["params"])
+    idx = np.arange(0, n, 64)
+    refs = [port.step(model, P, 2, w["q"][i], w["qd"][i], None) for i in idx]
+    assert rel_err(a["q"][idx], np.array([r["q"] for r in refs])) <= TOL
+    assert rel_err(a["qd"][idx], np.array([r["qd"] for r in refs])) <= TOL
+    pen = np.array([int((r["contact_data"][:, 9] < 0).sum()) for r in refs])
+    assert np.array_equal(a["contact_count"][idx], pen) and 0 < pen.sum() < idx.size   # ~half of them touch
+
+
+def test_humanoid_at_4096_subset_vs_oracle(golden_dir):
+    """BASELINE.json configs[4] per-GPU size: humanoid on the plane, 4096 environments (LCP solver, both filters);
+    the golden batch of 64 tiled over the batch with perturbed joints, every 128th environment against the C oracle."""
+    n = 4096
+    g = np.load(os.path.join(golden_dir, "humanoid.npz"))
+    model = load_model(fixture_path("humanoid"))
+    rng = np.random.default_rng(17)
+    reps = n // g["q_in"].shape[0]
+    q = np.tile(g["q_in"], (reps, 1)); qd = np.tile(g["qd_in"], (reps, 1)); tau = np.tile(g["tau"], (reps, 1))
+    q[:, 7:] += rng.uniform(-0.02, 0.02, size=q[:, 7:].shape)
+    q = q.astype(np.float32).astype(np.float64)
+    for keep_all in (False, True):
+        params = params_from_golden(g); params["keep_all_points"] = keep_all
+        sim = tds_b200.BatchSim(model, n, precision=tds_b200.PREC_F64, **params)
+        t = tau[:, -sim.n_tau:] if tau.shape[1] != sim.n_tau else tau
+        out = sim.step_host(2, q, qd, t, want_contacts=True)
+        assert np.all(np.isfinite(out["qd"]))
+        P = port.make_params(**params)
+        idx = np.arange(0, n, 128)
+        refs = [port.step(model, P, 2, q[i], qd[i], tau[i]) for i in idx]
+        assert rel_err(out["q"][idx], np.array([r["q"] for r in refs])) <= TOL
+        assert rel_err(out["qd"][idx], np.array([r["qd"] for r in refs])) <= TOL
+        assert np.array_equal(out["contact_count"][idx], np.array([r["n_contacts"] if keep_all else int((r["contact_data"][:, 9] < 0).sum()) for r in refs]))
 
 
 def test_default_precision_is_strict_unless_validated():

@@ -70,6 +70,12 @@ def lib():
     L.tds_b200_step_device.argtypes = [vp, ci, ci] + [fp] * 10 + [vp]
     L.tds_b200_step_host.restype = ci
     L.tds_b200_step_host.argtypes = [vp, ci, ci, dp, dp, dp, dp, dp, dp, dp]
+    L.tds_b200_contact_pairs.restype = ci
+    L.tds_b200_contact_pairs.argtypes = [vp, vp, ci]
+    L.tds_b200_contact_list_device.restype = ci
+    L.tds_b200_contact_list_device.argtypes = [vp, fp, vp, vp, vp]
+    L.tds_b200_contact_list_host.restype = ci
+    L.tds_b200_contact_list_host.argtypes = [vp, vp, vp]
     L.tds_b200_env_set_state_host.restype = ci
     L.tds_b200_env_set_state_host.argtypes = [vp, dp, dp]
     L.tds_b200_env_get_state_host.restype = ci
@@ -100,6 +106,7 @@ DECLARED_SYMBOLS = [
     "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
     "model_info", "b200_laikago_forward_zero", "b200_laikago_forward_zero_meta", "b200_laikago_forward_zero_allocate",
     "b200_laikago_forward_zero_deallocate", "b200_laikago_forward_zero_send_local", "b200_laikago_forward_zero_send_global",
+    "tds_b200_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",
     "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
     "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
     "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",

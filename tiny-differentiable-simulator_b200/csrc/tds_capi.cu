@@ -30,9 +30,12 @@ extern "C" int tds_launch_step_spec(int spec, const SimParams* P, const EnvParam
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream);
-extern "C" int tds_launch_step(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
-                               int mode, int use_pd, int precision, char* gscratch, int use_smem,
-                               int warps_per_block, cudaStream_t stream);
+
+// candidate contact points of a model, reference enumeration order: (link_a, link_b) per point
+struct ContactCandTable {
+  int n_points;
+  signed char link_a[2 * TDS_MAX_GEOMS], link_b[2 * TDS_MAX_GEOMS];
+};
 
 namespace {
 
@@ -222,6 +225,27 @@ __global__ void rollout_accum_kernel(const float* __restrict__ reward, const flo
   total[e] += reward[e] - shift;
   steps[e] += 1;
 }
+// Contact-pair index list of one step, in the reference's enumeration order (World::compute_contacts_multi_body_internal,
+// src/world.hpp:212-281: bodies i < j, links of A, geoms of A, links of B, geoms of B, points in emission order).  The
+// candidate points of a model are static (every sphere / capsule end emits one point, contact_point.hpp:112-124,149-158);
+// what varies per environment is which of them the constraint solver keeps: all with keep_all_points_, else those with
+// distance < 0 (MultiBodyConstraintSolver::resolve_collision, src/mb_constraint_solver.hpp:169-180).
+// links: [2 * n_points][ns] = (link_a, link_b) of the k-th kept point (MultiBodyContactPoint::link_a/b, :29-40), -9 beyond count.
+__global__ void contact_list_kernel(const float* __restrict__ dist, ContactCandTable T, int keep_all, int* __restrict__ count,
+                                    int* __restrict__ links, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int k = 0;
+  for (int c = 0; c < T.n_points; ++c) {
+    if (keep_all || dist[(size_t)c * ns + e] < 0.f) {
+      links[(size_t)(2 * k) * ns + e] = T.link_a[c];
+      links[(size_t)(2 * k + 1) * ns + e] = T.link_b[c];
+      ++k;
+    }
+  }
+  count[e] = k;
+  for (; k < T.n_points; ++k) { links[(size_t)(2 * k) * ns + e] = -9; links[(size_t)(2 * k + 1) * ns + e] = -9; }
+}
 __global__ void rollout_init_kernel(float* sticky, float* total, int* steps, int n) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) { sticky[e] = 0.f; total[e] = 0.f; steps[e] = 0; }
@@ -236,7 +260,7 @@ struct tds_b200_sim {
   bool smem_ok[3] = {false, false, false};
   bool smem_ok_w[3] = {false, false, false};
   // 3: role-warp kernel (tds_stepr.cu), 2: lane-team kernel (tds_stept.cu), 1: one-lane world-frame kernel
-  // (tds_stepw.cu), 0: link-frame kernel (tds_step.cu).  Requests fall back 3 -> 2 -> 1 when the model has no
+  // (tds_stepw.cu).  Requests fall back 3 -> 2 -> 1 when the model has no
   // tree decomposition (chains) or a tile does not fit in shared memory.
   // 4: ahead-of-time specialised kernel (tds_steps.cu) when the model is one it was generated for, else 3.
   int kernel = 4;
@@ -259,6 +283,8 @@ struct tds_b200_sim {
   int precision = TDS_B200_PREC_F64;        // what runs: AUTO resolves to MIXED for a model with a compiled (validated)
                                             // instance, else to the strict F64 (rebuild_team)
   int n_tau = 0, n_points = 0;
+  ContactCandTable cand;              // static candidate table (reference enumeration order)
+  int *c_count = nullptr, *c_links = nullptr;   // device: per-environment contact list of the last tds_b200_contact_list_* call
   // resident state + staging
   float *q = nullptr, *qd = nullptr, *act = nullptr, *qdd = nullptr, *reward = nullptr, *done = nullptr;
   float *cdist = nullptr, *link_xf = nullptr;
@@ -304,6 +330,8 @@ static bool is_pinned(const void* p) {
 
 static int ensure_stage(tds_b200_sim* s, size_t dev_bytes, size_t host_bytes) {
   if (dev_bytes > s->stage_dev_bytes) {
+    // the graph of tds_b200_env_step_host holds addresses inside the staging buffer: it dies with the buffer
+    drop_host_graph(s);
     if (s->stage_dev) cudaFree(s->stage_dev);
     s->stage_dev = nullptr; s->stage_dev_bytes = 0;
     CUDA_TRY(cudaMalloc(&s->stage_dev, dev_bytes));
@@ -415,10 +443,19 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
   }
   s->model.assign(model, model + n_model);
   if (const char* kv = getenv("TDS_B200_KERNEL"))
-    s->kernel_req = (strcmp(kv, "link") == 0) ? 0 : (strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : (strcmp(kv, "role") == 0 ? 3 : 4)));
+    s->kernel_req = strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : (strcmp(kv, "role") == 0 ? 3 : 4));
   s->kernel = s->kernel_req;
   s->n_tau = base.n_qd - (base.floating ? 6 : 0);
   s->n_points = base.max_contacts;
+  memset(&s->cand, 0, sizeof(s->cand));
+  if (base.has_plane) {   // plane (body A, base link -1) x every geom of the robot (body B), geoms grouped by link, base first
+    int c = 0;
+    for (int g = 0; g < base.n_geoms; ++g) {
+      const int pts = base.g_type[g] == TDSG_SPHERE ? 1 : (base.g_type[g] == TDSG_CAPSULE ? 2 : 0);
+      for (int j = 0; j < pts; ++j) { s->cand.link_a[c] = -1; s->cand.link_b[c] = (signed char)base.g_link[g]; ++c; }
+    }
+    s->cand.n_points = c;
+  }
   // visuals for the v1 output packing
   memset(&s->vis, 0, sizeof(s->vis));
   {
@@ -459,6 +496,7 @@ void tds_b200_destroy(tds_b200_sim* s) {
   drop_host_graph(s);
   cudaFree(s->rq); cudaFree(s->rqd); cudaFree(s->zero_act); cudaFree(s->pol_act); cudaFree(s->sticky); cudaFree(s->r_total);
   cudaFree(s->pol_params); cudaFree(s->act_qidx); cudaFree(s->r_steps);
+  cudaFree(s->c_count); cudaFree(s->c_links);
   cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk); cudaFree(s->team_dev);
   if (s->stage_host) cudaFreeHost(s->stage_host);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -577,12 +615,10 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
     if (rct) set_err(std::string("team step launch: ") + cudaGetErrorString((cudaError_t)rct));
     return rct;
   }
-  const int use_smem = (kern ? s->smem_ok_w[p] : s->smem_ok[p]) ? 1 : 0;
+  const int use_smem = s->smem_ok_w[p] ? 1 : 0;
   if (!use_smem) { int rc = ensure_scratch(s, p); if (rc) return rc; }
-  int rc = kern ? tds_launch_stepw(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
-                                        s->warps_per_block[p], (cudaStream_t)stream)
-                     : tds_launch_step(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
-                                       s->warps_per_block[p], (cudaStream_t)stream);
+  int rc = tds_launch_stepw(&s->dm[p], &s->P, &s->E, &io, mode, use_pd, p, s->scratch, use_smem,
+                            s->warps_per_block[p], (cudaStream_t)stream);
   if (rc) set_err(std::string("step launch: ") + cudaGetErrorString((cudaError_t)rc));
   return rc;
 }
@@ -627,6 +663,45 @@ int tds_b200_step_host(tds_b200_sim* s, int mode, int use_pd, const double* q, c
   if ((rc = down(s->cdist, s->n_points, contact_dist))) return rc;
   CUDA_TRY(cudaStreamSynchronize(sm));
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_contact_pairs(const tds_b200_sim* s, int* tuples, int cap) {
+  if (!s) return -1;
+  for (int c = 0; c < s->cand.n_points && c < cap && tuples; ++c) {
+    tuples[4 * c + 0] = 0; tuples[4 * c + 1] = s->cand.link_a[c];     // body A = the plane (created first), its base link
+    tuples[4 * c + 2] = 1; tuples[4 * c + 3] = s->cand.link_b[c];     // body B = the robot
+  }
+  return s->cand.n_points;
+}
+
+int tds_b200_contact_list_device(tds_b200_sim* s, const float* contact_dist, int* count, int* links, void* stream) {
+  if (!s || !contact_dist || !count || !links) return -1;
+  if (s->cand.n_points == 0) return 0;
+  const int T = 128, B = (s->n + T - 1) / T;
+  contact_list_kernel<<<B, T, 0, (cudaStream_t)stream>>>(contact_dist, s->cand, s->P.keep_all_points, count, links, s->n, s->ns);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_contact_list_host(tds_b200_sim* s, int* count, int* links) {
+  if (!s || !count) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int n = s->n, ns = s->ns, np = s->cand.n_points;
+  if (np == 0) { for (int e = 0; e < n; ++e) count[e] = 0; return 0; }
+  if (!s->c_count) {
+    CUDA_TRY(cudaMalloc((void**)&s->c_count, sizeof(int) * ns));
+    CUDA_TRY(cudaMalloc((void**)&s->c_links, sizeof(int) * (size_t)ns * 2 * np));
+  }
+  int rc = tds_b200_contact_list_device(s, s->cdist, s->c_count, s->c_links, s->stream);
+  if (rc) return rc;
+  std::vector<int> tmp((size_t)ns * 2 * np);
+  CUDA_TRY(cudaMemcpyAsync(count, s->c_count, sizeof(int) * n, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(tmp.data(), s->c_links, sizeof(int) * tmp.size(), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (links)
+    for (int e = 0; e < n; ++e)
+      for (int k = 0; k < 2 * np; ++k) links[(size_t)e * 2 * np + k] = tmp[(size_t)k * ns + e];
   return 0;
 }
 
@@ -803,7 +878,7 @@ int tds_b200_env_rollout_host(tds_b200_sim* s, const double* policy, int n_param
 int tds_b200_get_precision(const tds_b200_sim* s) { return s ? s->precision : -1; }
 
 const char* tds_b200_kernel_name(const tds_b200_sim* s) {
-  static const char* names[5] = {"tds_step_kernel (link frame, lane per environment)", "tds_stepw_kernel (common frame, lane per environment)",
+  static const char* names[5] = {"", "tds_stepw_kernel (common frame, lane per environment)",
                                  "tds_stept_kernel (lane team per environment)", "tds_stepr_kernel (warp per tree role)",
                                  "tds_step_spec_kernel (warp per tree role, model-specialised)"};
   return (s && s->kernel >= 0 && s->kernel <= 4) ? names[s->kernel] : "";

@@ -66,11 +66,12 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
   D->n_geoms = (int)m[TDSM_H_NGEOMS];
   D->n_vis = (int)m[TDSM_H_NVIS];
   D->has_plane = (int)m[TDSM_H_HASPLANE];
+  if (D->n_links < 0 || D->n_geoms < 0 || D->n_vis < 0 || D->n_q < 0 || D->n_qd < 0) return -1;
   if (D->n_links > TDS_MAX_LINKS || D->n_geoms > TDS_MAX_GEOMS) return -2;
   const double* base = m + TDSM_HEADER;
   const double* links = base + TDSM_BASE;
   const double* geoms = links + (size_t)D->n_links * TDSM_LINK;
-  if (n_doubles < TDSM_HEADER + TDSM_BASE + D->n_links * TDSM_LINK + D->n_geoms * TDSM_GEOM) return -1;
+  if (n_doubles < TDSM_HEADER + TDSM_BASE + D->n_links * TDSM_LINK + D->n_geoms * TDSM_GEOM + D->n_vis * TDSM_VIS) return -1;
   tds_rbi_pack(base, D->base_rbi);
   tds_rbic_pack(base, D->base_rbic);
   for (int k = 0; k < 9; ++k) D->base_inertia_com[k] = (float)base[4 + k];
@@ -86,6 +87,7 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     D->jtype[i] = jt;
     D->q_idx[i] = (int)l[TDSM_L_QIDX];
     D->qd_idx[i] = (int)l[TDSM_L_QDIDX];
+    if (jt != TDSJ_FIXED && (D->q_idx[i] < 0 || D->q_idx[i] >= D->n_q || D->qd_idx[i] < 0 || D->qd_idx[i] >= D->n_qd)) return -1;
     int fl = 0;
     if (jt == TDSJ_FIXED) fl |= TDS_LF_FIXED;
     else if (jt <= TDSJ_PRISMATIC_AXIS) fl |= TDS_LF_PRISMATIC;

@@ -19,6 +19,7 @@
 // with the compiler's constant folding in place of a CppAD operation tape.  Numerics (scalar types RA / RC / RS,
 // reference quirks, row order) are those of tds_stept.cu / tds_stepr.cu; citations at each stage.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "tds_wcommon.cuh"
 #include "tds_team.h"
@@ -296,7 +297,7 @@ template <typename T> TDS_D Rbi<T> rbi_nz() { Rbi<T> r; const T z = negz<T>(); r
 //   1 lean: full / no-contact step on the device layout only      2 lean + host layouts (tds_b200_env_step_host)
 template <class SP, typename RA, typename RC, typename RS, int VAR>
 TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, const StepIO& io, const int mode, const int use_pd,
-                     const int role) {
+                     const int role, const int tile, const int tid) {
   using L = Lay<SP, RA, RC, RS>;
   using C = Cls<SP>;
   static_assert(C::uniform(), "the subtrees of the model are not one structural class (use the table-driven kernel)");
@@ -307,16 +308,16 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   constexpr int NPO = C::n_pts_own(), NPOA = cmax(NPO, 1), NPTR = C::n_pts_trunk(), NPTRA = cmax(NPTR, 1);
   constexpr int NACCA = cmax(SP::N_ACC, 1), NXLA = cmax(SP::N_XW_LANE, 1), NATT = cmax(SP::N_ATT, 1);
   constexpr bool FLOAT = SP::FLOATING != 0;
-  const int lane = threadIdx.x & 31;
-  const int env = blockIdx.x * 32 + lane;
+  const int lane = tid & 31;
+  const int env = tile * 32 + lane;   // (a tile past the end of the batch computes on the last environment and stores nothing)
   const bool live = env < io.n;
   const int e = live ? env : io.n - 1;
   const int ns = io.n_stride;
   const LegTab<SP>& LG = leg_tab<SP>(role);
   char* const priv = smem + (size_t)(L::SHARED + role * L::PRIV) * ST * 4;
   int phase_id = 0;
-#define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
-#define TDSS_STAMP(slot) do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)blockIdx.x * TT + role) * 16 + (slot)] = clock64(); } while (0)
+#define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)tile * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
+#define TDSS_STAMP(slot) do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)tile * TT + role) * 16 + (slot)] = clock64(); } while (0)
   TDSS_PHASE();
   auto xw_rc = [&](int slot) { return sp<RC>(smem, lane, L::XW + slot * L::XWW); };                  // R[9], p[3]
   auto xw_ra = [&](int slot) { return sp<RA>(smem, lane, L::XW + slot * L::XWW + 12 * RCW); };       // v[6], a[6]
@@ -360,12 +361,12 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   constexpr int NACT_TILE = 32 * SP::N_ACT, AREG = (NACT_TILE + 32 * TT - 1) / (32 * TT);
   float areg[AREG];
   if constexpr (HOSTIO) {
-    const float* const ta = io.act_aos + (size_t)blockIdx.x * NACT_TILE;
-    const int rows = io.n - (int)blockIdx.x * 32;
+    const float* const ta = io.act_aos + (size_t)tile * NACT_TILE;
+    const int rows = io.n - tile * 32;
     const int valid = (rows < 32 ? rows : 32) * SP::N_ACT;
 #pragma unroll
     for (int j = 0; j < AREG; ++j) {
-      const int idx = (int)threadIdx.x + 32 * TT * j;
+      const int idx = tid + 32 * TT * j;
       areg[j] = idx < valid ? ta[idx] : 0.f;
     }
   }
@@ -688,7 +689,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   if constexpr (HOSTIO) {
 #pragma unroll
     for (int j = 0; j < AREG; ++j) {
-      const int idx = (int)threadIdx.x + 32 * TT * j;
+      const int idx = tid + 32 * TT * j;
       if (idx < NACT_TILE) astg[idx] = areg[j];
     }
   }
@@ -1625,13 +1626,13 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
     if (io.obs_aos) {
       __syncthreads();
       constexpr int NOBS = SP::N_Q + SP::N_QD;
-      const int rows = io.n - (int)blockIdx.x * 32;
+      const int rows = io.n - tile * 32;
       const int valid = (rows < 32 ? rows : 32) * NOBS;
-      float* const dst = io.obs_aos + (size_t)blockIdx.x * 32 * NOBS;
+      float* const dst = io.obs_aos + (size_t)tile * 32 * NOBS;
       if (valid == 32 * NOBS && (NOBS % 4) == 0) {
-        for (int i = (int)threadIdx.x; i < 8 * NOBS; i += 32 * TT) ((float4*)dst)[i] = ((const float4*)ostg)[i];
+        for (int i = tid; i < 8 * NOBS; i += 32 * TT) ((float4*)dst)[i] = ((const float4*)ostg)[i];
       } else {
-        for (int i = (int)threadIdx.x; i < valid; i += 32 * TT) dst[i] = ostg[i];
+        for (int i = tid; i < valid; i += 32 * TT) dst[i] = ostg[i];
       }
     }
   }
@@ -1640,14 +1641,27 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
 #undef TDSS_STAMP
 }
 
-template <class SP, typename RA, typename RC, typename RS, int VAR>
-__global__ void __launch_bounds__(32 * TDS_TEAM_T, 2)
+// TPC tiles per CTA.  1: one tile per CTA, two CTAs may share an SM (latency mode, a batch of at most one wave).
+// 2: two tiles in one CTA of 8 warps, barriers shared: the tiles run the SAME instruction stream in lockstep, so the SM's
+// instruction fetches serve both (scripts/icache_probe.cu: two co-resident CTAs that drift apart are two streams over
+// 100+ KB of code and pay 3.7-4.6 cycles per instruction each; in lockstep 2.4).  Throughput mode, batches of many waves.
+template <class SP, typename RA, typename RC, typename RS, int VAR, int TPC>
+__global__ void __launch_bounds__(32 * TDS_TEAM_T * TPC, TPC == 1 ? 2 : 1)
 tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode_flags,
                      const int use_pd) {
   extern __shared__ __align__(16) char smem_raw[];
-  const int role = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, known uniform to the compiler
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp index, known uniform to the compiler
+  const int role = warp % TDS_TEAM_T, sub = warp / TDS_TEAM_T;
   if ((mode_flags & 256) && role != 0) return;   // profiling aid (TDS_B200_DEBUG_SOLO): role 0 alone, results are garbage
-  tile_body<SP, RA, RC, RS, VAR>(smem_raw, P, E, io, mode_flags & 255, use_pd, role);
+  // Programmatic dependent launch (back-to-back steps of one stream / graph): let the next step's grid be scheduled now
+  // (single-wave batches: its CTAs take the second slot of every SM and park at their own wait), then wait for the
+  // previous step's grid to complete and flush before the first read of the state.  Both are no-ops without the attribute.
+  if (mode_flags & 512) asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  char* const smem = smem_raw + (size_t)sub * ((size_t)Lay<SP, RA, RC, RS>::TOTAL * 32 * 4);
+  tile_body<SP, RA, RC, RS, VAR>(smem, P, E, io, mode_flags & 255, use_pd, role, (int)blockIdx.x * TPC + sub,
+                                 (int)threadIdx.x - sub * 32 * TDS_TEAM_T);
+  if (!(mode_flags & 512)) asm volatile("griddepcontrol.launch_dependents;");
 }
 
 template <class SP> struct SpecHost {
@@ -1680,12 +1694,21 @@ template <class SP> struct SpecHost {
   }
   static int launch(const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision, cudaStream_t stream) {
     const int tiles = (io->n + 31) / 32;
-    const size_t smem = smem_bytes(precision);
+    const size_t smem1 = smem_bytes(precision);
     cudaError_t err = cudaSuccess;
-#define TDSS_LAUNCH(RA, RC, RS, VAR)                                                                    \
+    int dev_ = 0; cudaGetDevice(&dev_);
+    static int sm_count[64] = {0};
+    if (!sm_count[dev_ & 63]) cudaDeviceGetAttribute(&sm_count[dev_ & 63], cudaDevAttrMultiProcessorCount, dev_);
+    // throughput mode: more tiles than two waves of single-tile CTAs and two tiles fit one CTA's shared memory
+    static const int tpc_env = getenv("TDS_B200_TPC") ? atoi(getenv("TDS_B200_TPC")) : 0;
+    static const bool pdl = getenv("TDS_B200_PDL") ? atoi(getenv("TDS_B200_PDL")) != 0 : false;
+    int tpc = (tiles > 2 * sm_count[dev_ & 63] && 2 * smem1 <= 227 * 1024) ? 2 : 1;
+    if (tpc_env == 1 || tpc_env == 2) tpc = (tpc_env == 2 && 2 * smem1 <= 227 * 1024) ? 2 : 1;
+#define TDSS_LAUNCH(RA, RC, RS, VAR, TPC)                                                               \
   do {                                                                                                  \
-    auto k = tds_step_spec_kernel<SP, RA, RC, RS, VAR>;                                                 \
-    static bool attr_set = false;                                                                       \
+    auto k = tds_step_spec_kernel<SP, RA, RC, RS, VAR, TPC>;                                            \
+    const size_t smem = smem1 * TPC;                                                                    \
+    static bool attr_set_dev[64] = {false}; bool& attr_set = attr_set_dev[dev_ & 63]; /* the attribute is per device */ \
     if (!attr_set && smem > 48 * 1024) {                                                                \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
       /* two tiles per SM when the batch has more tiles than SMs: ask for the largest shared-memory carveout */ \
@@ -1693,20 +1716,29 @@ template <class SP> struct SpecHost {
       if (err == cudaSuccess) attr_set = true;                                                          \
     }                                                                                                   \
     if (err == cudaSuccess) {                                                                           \
-      k<<<tiles, 32 * TDS_TEAM_T, smem, stream>>>(*P, *E, *io, mode, use_pd);                           \
-      err = cudaGetLastError();                                                                         \
+      cudaLaunchConfig_t cfg = {};                                                                      \
+      cfg.gridDim = dim3((tiles + TPC - 1) / TPC); cfg.blockDim = dim3(32 * TDS_TEAM_T * TPC);          \
+      cfg.dynamicSmemBytes = smem; cfg.stream = stream;                                                 \
+      cudaLaunchAttribute at[1];                                                                        \
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                    \
+      at[0].val.programmaticStreamSerializationAllowed = 1;                                             \
+      cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;                                                       \
+      const int mode_k = mode | ((pdl && tiles <= sm_count[dev_ & 63]) ? 512 : 0);                      \
+      err = cudaLaunchKernelEx(&cfg, k, *P, *E, *io, mode_k, use_pd);                                   \
     }                                                                                                   \
   } while (0)
     // instance: general (extra outputs / forward dynamics only), lean, lean + host layouts
     const int var = ((mode & 255) == 0 || io->link_xf || io->contact_dist || io->qdd_out) ? 0 : ((io->act_aos && use_pd) ? 2 : 1);
     if (var != 2 && io->act_aos) return (int)cudaErrorInvalidValue;   // host layouts are only served by the lean instance
-#define TDSS_PREC(VAR)                                                      \
-  do {                                                                      \
-    if (precision == 0) TDSS_LAUNCH(float, double, float, VAR);             \
-    else if (precision == 1) TDSS_LAUNCH(double, double, double, VAR);      \
-    else TDSS_LAUNCH(float, float, float, VAR);                             \
+#define TDSS_PREC(VAR, TPC)                                                      \
+  do {                                                                           \
+    if (precision == 0) TDSS_LAUNCH(float, double, float, VAR, TPC);             \
+    else if (precision == 1) TDSS_LAUNCH(double, double, double, VAR, TPC);      \
+    else TDSS_LAUNCH(float, float, float, VAR, TPC);                             \
   } while (0)
-    if (var == 0) TDSS_PREC(0); else if (var == 1) TDSS_PREC(1); else TDSS_PREC(2);
+    if (var == 0) TDSS_PREC(0, 1);
+    else if (var == 1) { if (tpc == 2 && precision != 1) { if (precision == 0) TDSS_LAUNCH(float, double, float, 1, 2); else TDSS_LAUNCH(float, float, float, 1, 2); } else TDSS_PREC(1, 1); }
+    else { if (tpc == 2 && precision != 1) { if (precision == 0) TDSS_LAUNCH(float, double, float, 2, 2); else TDSS_LAUNCH(float, float, float, 2, 2); } else TDSS_PREC(2, 1); }
 #undef TDSS_PREC
 #undef TDSS_LAUNCH
     return (int)err;

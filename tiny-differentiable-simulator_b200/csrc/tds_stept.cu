@@ -883,7 +883,7 @@ extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, con
 #define TDST_LAUNCH(RA, RC, RS, SM)                                                                       \
   do {                                                                                                  \
     auto k = tds_stept_kernel<RA, RC, RS, SM>;                                                              \
-    static size_t smem_set = 0;                                                                         \
+    static size_t smem_set_dev[64] = {0}; int dev_ = 0; cudaGetDevice(&dev_); size_t& smem_set = smem_set_dev[dev_ & 63]; \
     if (smem > 48 * 1024 && smem > smem_set) {                                                          \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
       /* several one-warp CTAs must be co-resident per SM: ask for the largest shared-memory carveout */ \

@@ -659,7 +659,7 @@ extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const Env
 #define TDSW_LAUNCH(RA, RC, RS, SM)                                                                     \
   do {                                                                                                  \
     auto k = tds_stepw_kernel<RA, RC, RS, SM>;                                                          \
-    static size_t smem_set = 0;                                                                         \
+    static size_t smem_set_dev[64] = {0}; int dev_ = 0; cudaGetDevice(&dev_); size_t& smem_set = smem_set_dev[dev_ & 63]; \
     if (smem > 48 * 1024 && smem > smem_set) {                                                          \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
       if (err == cudaSuccess) smem_set = smem;                                                          \

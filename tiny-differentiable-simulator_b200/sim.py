@@ -125,7 +125,21 @@ class BatchSim:
             out["qdd"] = qdd
         if cd is not None:
             out["contact_dist"] = cd[:, :self.n_contact_points]
+            # the contact-pair index list the constraint solver keeps in this step (computed on the device)
+            cnt = np.zeros(n, dtype=np.int32)
+            links = np.full((n, max(self.n_contact_points, 1), 2), -9, dtype=np.int32)
+            self._check(self._L.tds_b200_contact_list_host(self._h, ctypes.c_void_p(cnt.ctypes.data),
+                                                           ctypes.c_void_p(links.ctypes.data)), "contact_list_host")
+            out["contact_count"] = cnt
+            out["contact_links"] = links[:, :self.n_contact_points]
         return out
+
+    def contact_pairs(self):
+        """(body_a, link_a, body_b, link_b) of every candidate contact point, reference enumeration order
+        (World::compute_contacts_multi_body_internal, src/world.hpp:212-281): what World::mb_contacts_ lists each step."""
+        t = np.zeros((max(self.n_contact_points, 1), 4), dtype=np.int32)
+        k = self._L.tds_b200_contact_pairs(self._h, ctypes.c_void_p(t.ctypes.data), t.shape[0])
+        return t[:k]
 
     # ---- resident environment state ----
     def env_set_state(self, q, qd):
