@@ -446,7 +446,10 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=1.0, help="keep the GPU busy this long for clock sampling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-reward", action="store_true",
-                    help="all-gather {reward, done} per step (only needed by a single centralized policy)")
+                    help="all-gather {reward, done} per step (only needed by a single centralized policy): the step kernel "
+                         "writes into the NCCL send buffer, the collective is captured in the same CUDA graph")
+    ap.add_argument("--gather-overlap", action="store_true", help="with --gather-reward: the gather of step k runs on a side stream under step k+1")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the config's environments are divided over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -474,6 +477,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     n = args.envs
+    if args.strong:   # strong scaling: the 4096 environments of the config are divided over the ranks
+        from tds_b200.parallel import shard_range
+        lo, hi = shard_range(args.envs, rank, world)
+        n = hi - lo
     K, W = args.steps, max(args.warmup, 3)
 
     sim = tds_b200.laikago_sim(n, device=local_rank, precision=args.precision, auto_reset=True)
@@ -486,24 +493,30 @@ def main():
     ring = 768 if not args.small_ring else 16
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     actions = (torch.rand((ring, 12, ns), generator=g) * 0.8 - 0.4).to(dev)
-    reward = torch.zeros(ns, device=dev)
-    done = torch.zeros(ns, device=dev)
-    gathered = torch.zeros((world, 2, ns), device=dev) if (args.gather_reward and world > 1) else None
+    gathered = None
+    if args.gather_reward and world > 1:
+        from tds_b200.parallel import RewardDoneExchange
+        gathered = RewardDoneExchange(ns, world, dev, depth=2 if args.gather_overlap else 1)
+    reward = torch.zeros(ns, device=dev) if gathered is None else gathered.reward(0)
+    done = torch.zeros(ns, device=dev) if gathered is None else gathered.done(0)
 
     zero = torch.zeros((12, ns), device=dev)
     for _ in range(10):  # settle like LaikagoContactSimulation::reset (laikago_environment2.h:96-104)
         sim.env_step_device(zero, reward, done)
 
     def one_step(i):
-        sim.env_step_device(actions[i % ring], reward, done)
-        if gathered is not None:
-            dist.all_gather_into_tensor(gathered.view(-1), torch.stack([reward, done]).view(-1))
+        if gathered is None:
+            sim.env_step_device(actions[i % ring], reward, done)
+        else:   # the kernel's reward / done stores fill the send buffer; the collective follows in stream order
+            gathered.before_step(i)
+            sim.env_step_device(actions[i % ring], gathered.reward(i), gathered.done(i))
+            gathered.gather(i)
 
     for i in range(W):
         one_step(i)
     torch.cuda.synchronize()
     graph = None
-    if not args.no_graph and gathered is None:
+    if not args.no_graph:
         # the K timed steps are captured once into a CUDA graph (K kernel nodes) and replayed: launch-bound
         # inner loops belong in graphs; the work per step is unchanged
         side = torch.cuda.Stream(device=dev)
@@ -515,6 +528,10 @@ def main():
         with torch.cuda.graph(graph, stream=side):
             for i in range(K):
                 one_step(W + 1 + i)
+            if gathered is not None:
+                gathered.join()
+        torch.cuda.synchronize()
+        graph.replay()            # one untimed replay: the timed one is not the first launch of a fresh graph
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -538,6 +555,8 @@ def main():
         ev0.record()
         for i in range(K):
             one_step(W + 1 + i)
+        if gathered is not None:
+            gathered.join()
         ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -594,11 +613,11 @@ def main():
             pass
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": ["f32 (ABA, factorisation, PGS) + f64 (kinematics, inertias, CRBA, Jacobians, LCP rhs)", "f64", "f32"][args.precision], "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "envs_per_gpu": n, "global_envs": n * world, "dt": 1e-3, "parallelism": f"env-sharded x{world}, no data-path collective"
-                   + (" + all-gather(reward,done)" if gathered is not None else ""),
+                   + ((" + all-gather(reward,done) in the graph, step kernel writes the send buffer" + (", overlapped with the next step" if args.gather_overlap else "")) if gathered is not None else ""),
                    "state": "SoA fp32 resident in HBM",
                    "timing": "CUDA events around exactly K steps (" + ("one CUDA-graph replay of K kernel nodes" if graph is not None else "K individual launches") + "), max over ranks",
                    "l2": (f"inputs larger than L2: ring of {ring} action tensors = {ring * 12 * ns * 4 / 2**20:.0f} MiB, one per step"

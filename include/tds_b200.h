@@ -182,6 +182,13 @@ void cuda_model_laikago_forward_zero(int num_total_threads, int num_blocks, int 
 CudaFunctionMetaData cuda_model_laikago_forward_zero_meta(void);
 void cuda_model_laikago_forward_zero_allocate(int num_total_threads);
 void cuda_model_laikago_forward_zero_deallocate(void);
+/* "cuda_model_" + AntContactSimulation2::env_name() (examples/ars/ars_train_policy_cuda.cpp:507, ant_environment2.h):
+ * input_dim 39 = q14|qd14|action8|kp,kd,max_force, output_dim 155 = q14|qd14|9x(pos3,quat4)|up.z|zeros */
+void cuda_model_ant_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block,
+                                 double* output, const double* input);
+CudaFunctionMetaData cuda_model_ant_forward_zero_meta(void);
+void cuda_model_ant_forward_zero_allocate(int num_total_threads);
+void cuda_model_ant_forward_zero_deallocate(void);
 
 /* ---- C-ABI v2 (alt): what tds::CudaLibrary / CudaModel / CudaFunction load (src/utils/cuda/cuda_library.hpp:51-68,
  * cuda_model.hpp:14-25, cuda_function.hpp:78-100; emitted at src/utils/cuda/cuda_codegen.hpp:32-231).  One model,

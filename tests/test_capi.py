@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_in_header():
     text = open(os.path.join(ROOT, "include", "tds_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:tds_b200|cuda_model_laikago|b200_laikago)_\w+|model_info)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:tds_b200|cuda_model_laikago|cuda_model_ant|b200_laikago)_\w+|model_info)\s*\(", text)))
 
 
 def test_header_symbols_exported():
@@ -31,6 +31,8 @@ def test_header_symbols_exported():
 def test_v1_meta_matches_reference_dims():
     m = tds_b200.lib().cuda_model_laikago_forward_zero_meta()
     assert (m.input_dim, m.output_dim, m.global_dim) == (51, 411, 0)
+    m = tds_b200.lib().cuda_model_ant_forward_zero_meta()
+    assert (m.input_dim, m.output_dim, m.global_dim) == (39, 155, 0)
 
 
 def test_no_cpu_fallback():

@@ -120,6 +120,27 @@ def test_v1_abi_dropin(golden_dir):
     assert np.all(out[:, 156:] == sentinel)   # never written, like the reference's kernel
 
 
+def test_v1_abi_ant(golden_dir):
+    """cuda_model_ant_forward_zero{,_meta,_allocate,_deallocate} ("cuda_model_" + env_name(),
+    examples/ars/ars_train_policy_cuda.cpp:507): 39 doubles in, 155 out, against the reference's own Ant env step."""
+    g = np.load(os.path.join(golden_dir, "ant.npz"))
+    m = tds_b200.CudaModelV1("cuda_model_ant")
+    assert (m.input_dim, m.output_dim, m.global_dim) == (39, 155, 0)
+    x = g["env_input"]
+    m.allocate(x.shape[0])
+    out = np.full((x.shape[0], 155), 123.0)
+    m.forward_zero(x, out)
+    m.deallocate()
+    ref = g["env_output_templated"]
+    assert rel_err(out[:, :28], ref[:, :28]) <= TOL
+    vis, rvis = out[:, 28:91].reshape(-1, 9, 7), ref[:, 28:91].reshape(-1, 9, 7)
+    assert np.max(np.abs(vis[..., :3] - rvis[..., :3])) < 5e-6
+    # quaternion sign: the reference normalises nothing here either; compare up to fp32 accuracy
+    assert np.max(np.abs(vis[..., 3:] - rvis[..., 3:])) < 5e-6
+    assert np.array_equal(out[:, 91], ref[:, 91])
+    assert np.all(out[:, 92:] == 123.0)
+
+
 @pytest.mark.parametrize("name,gen,n", [("laikago", wl.laikago_perturbed, 512), ("sphere2", wl.sphere2, 1024),
                                         ("pendulum5", wl.pendulum5, 512), ("cartpole", wl.cartpole, 64)])
 def test_fresh_inputs_vs_c_oracle(name, gen, n):

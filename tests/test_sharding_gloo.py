@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from tds_b200.parallel import shard_range, gather_reward_done
+from tds_b200.parallel import shard_range, gather_reward_done, RewardDoneExchange
 
 
 def _free_port():
@@ -26,6 +26,18 @@ def _worker(rank, world, port, total, q):
     reward = torch.arange(lo, hi, dtype=torch.float32)
     done = (torch.arange(lo, hi) % 3 == 0).float()
     r, d = gather_reward_done(reward, done, total, world)
+    # the preallocated exchange the bench / rollouts use: reward and done ARE the send buffer's rows
+    ns = 64
+    ex = RewardDoneExchange(ns, world, "cpu", depth=2)
+    sizes = [b - a for a, b in (shard_range(total, k, world) for k in range(world))]
+    for step in range(3):
+        ex.before_step(step)
+        ex.reward(step)[:hi - lo] = reward + step
+        ex.done(step)[:hi - lo] = done
+        ex.gather(step)
+        ex.join()
+        r2, d2 = ex.full(sizes, step)
+        assert torch.equal(r2, r + step) and torch.equal(d2, d)
     q.put((rank, lo, hi, r.numpy(), d.numpy()))
     dist.destroy_process_group()
 

@@ -91,6 +91,9 @@ def lib():
     L.cuda_model_laikago_forward_zero.argtypes = [ci, ci, ci, dp, dp]
     L.cuda_model_laikago_forward_zero_meta.restype = CudaFunctionMetaData
     L.cuda_model_laikago_forward_zero_allocate.argtypes = [ci]
+    L.cuda_model_ant_forward_zero.argtypes = [ci, ci, ci, dp, dp]
+    L.cuda_model_ant_forward_zero_meta.restype = CudaFunctionMetaData
+    L.cuda_model_ant_forward_zero_allocate.argtypes = [ci]
     _LIB = L
     return L
 
@@ -112,4 +115,6 @@ DECLARED_SYMBOLS = [
     "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",
     "cuda_model_laikago_forward_zero_meta", "cuda_model_laikago_forward_zero_allocate",
     "cuda_model_laikago_forward_zero_deallocate",
+    "cuda_model_ant_forward_zero", "cuda_model_ant_forward_zero_meta", "cuda_model_ant_forward_zero_allocate",
+    "cuda_model_ant_forward_zero_deallocate",
 ]

@@ -1005,90 +1005,111 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   return 0;
 }
 
-// ---- C-ABI v1 drop-in for "cuda_model_laikago" (src/utils/cuda_codegen.hpp:156-266) -------------------
+// ---- C-ABI v1 drop-in (src/utils/cuda_codegen.hpp:156-266) for the models ars_train_policy_cuda loads by name
+// "cuda_model_" + env_name() (examples/ars/ars_train_policy_cuda.cpp:507): cuda_model_laikago and cuda_model_ant -------
 static const double k_laikago_model[] = {
 #include "generated/laikago_model.inc"
 };
-static const int k_laikago_in = 51, k_laikago_out = 411, k_laikago_written = 156;
-static tds_b200_sim* g_v1 = nullptr;
-static double* g_v1_dev_in = nullptr;
-static double* g_v1_dev_out = nullptr;
-static int g_v1_n = 0;
-static std::mutex g_v1_mu;
+static const double k_ant_model[] = {
+#include "generated/ant_model.inc"
+};
+struct V1Spec {
+  const char* name;
+  const double* model; int n_model;
+  int in_dim, out_dim, written;       // written = n_q + n_qd + 7 * n_visuals + 1 (the rest of output_dim is never written)
+  int n_q, n_act;
+  double dt, init[TDS_MAX_ACT], kp, kd, max_force;
+  int reward_kind;
+};
+// LaikagoContactSimulation: laikago_environment2.h:36-61, locomotion_contact_simulation.h:131-135 (51 -> 411)
+static const V1Spec k_v1_laikago = {"cuda_model_laikago", k_laikago_model, (int)(sizeof(k_laikago_model) / sizeof(double)), 51, 411, 156, 18, 12,
+                                    1e-3, {0.2, 0, -0.7, 0.2, 0, -0.7, 0.2, 0, -0.7, 0.2, 0, -0.7}, 100.0, 2.0, 50.0, 1};
+// AntContactSimulation2: ant_environment2.h:28-70 (39 = q14|qd14|action8|kp,kd,max_force -> 155 = 28 + 14 links x 9 visuals + 1)
+static const V1Spec k_v1_ant = {"cuda_model_ant", k_ant_model, (int)(sizeof(k_ant_model) / sizeof(double)), 39, 155, 92, 14, 8,
+                                0.01, {0.0, -0.5, 0.0, -0.5, 0.0, -0.5, 0.0, -0.5}, 15.0, 0.3, 3.0, 3};
+struct V1Instance {
+  tds_b200_sim* sim = nullptr;
+  double *dev_in = nullptr, *dev_out = nullptr;
+  int n = 0;
+  std::mutex mu;
+};
+static V1Instance g_v1_laikago, g_v1_ant;
 
-static void v1_fail(const char* what) {
+static void v1_fail(const V1Spec& S, const char* what) {
   // the reference prints and exits on allocation failure (cuda_codegen.hpp:201-208)
-  fprintf(stderr, "cuda_model_laikago (tds_b200): %s: %s\n", what, g_err.c_str());
+  fprintf(stderr, "%s (tds_b200): %s: %s\n", S.name, what, g_err.c_str());
   exit(1);
 }
 
-CudaFunctionMetaData cuda_model_laikago_forward_zero_meta(void) {
-  CudaFunctionMetaData d;
-  d.output_dim = k_laikago_out;
-  d.input_dim = k_laikago_in;
-  d.global_dim = 0;
-  return d;
+static void v1_release(V1Instance& I) {
+  if (I.sim) tds_b200_destroy(I.sim);
+  I.sim = nullptr;
+  cudaFree(I.dev_in); cudaFree(I.dev_out);
+  I.dev_in = I.dev_out = nullptr;
+  I.n = 0;
 }
 
-void cuda_model_laikago_forward_zero_allocate(int num_total_threads) {
-  std::lock_guard<std::mutex> lk(g_v1_mu);
-  if (g_v1) { tds_b200_destroy(g_v1); g_v1 = nullptr; cudaFree(g_v1_dev_in); cudaFree(g_v1_dev_out); }
+static void v1_allocate(V1Instance& I, const V1Spec& S, int num_total_threads) {
+  std::lock_guard<std::mutex> lk(I.mu);
+  v1_release(I);
   int dev = 0;
   cudaGetDevice(&dev);
-  g_v1 = tds_b200_create(k_laikago_model, (int)(sizeof(k_laikago_model) / sizeof(double)), num_total_threads, dev);
-  if (!g_v1) v1_fail("allocate");
-  // LaikagoContactSimulation parameters: laikago_environment2.h:36-61, locomotion_contact_simulation.h:131-135
+  I.sim = tds_b200_create(S.model, S.n_model, num_total_threads, dev);
+  if (!I.sim) v1_fail(S, "allocate");
   const double g[3] = {0, 0, -9.81};
-  tds_b200_set_params(g_v1, 1e-3, g, 1.0, 0.0, 0.2, 1e-5, 1, 1);
-  const double init[12] = {0.2, 0, -0.7, 0.2, 0, -0.7, 0.2, 0, -0.7, 0.2, 0, -0.7};
-  tds_b200_set_env(g_v1, 12, init, 6, 100.0, 2.0, 50.0, 0.4, 1);
-  g_v1_n = num_total_threads;
-  if (cudaMalloc((void**)&g_v1_dev_in, sizeof(double) * (size_t)num_total_threads * k_laikago_in) != cudaSuccess ||
-      cudaMalloc((void**)&g_v1_dev_out, sizeof(double) * (size_t)num_total_threads * k_laikago_written) != cudaSuccess) {
+  tds_b200_set_params(I.sim, S.dt, g, 1.0, 0.0, 0.2, 1e-5, 1, 1);
+  tds_b200_set_env(I.sim, S.n_act, S.init, 6, S.kp, S.kd, S.max_force, 0.4, S.reward_kind);
+  I.n = num_total_threads;
+  if (cudaMalloc((void**)&I.dev_in, sizeof(double) * (size_t)num_total_threads * S.in_dim) != cudaSuccess ||
+      cudaMalloc((void**)&I.dev_out, sizeof(double) * (size_t)num_total_threads * S.written) != cudaSuccess) {
     set_err("cudaMalloc failed");
-    v1_fail("allocate");
+    v1_fail(S, "allocate");
   }
 }
 
-void cuda_model_laikago_forward_zero_deallocate(void) {
-  std::lock_guard<std::mutex> lk(g_v1_mu);
-  if (g_v1) tds_b200_destroy(g_v1);
-  g_v1 = nullptr;
-  cudaFree(g_v1_dev_in); cudaFree(g_v1_dev_out);
-  g_v1_dev_in = g_v1_dev_out = nullptr;
-  g_v1_n = 0;
-}
-
-void cuda_model_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output,
-                                     const double* input) {
-  (void)num_blocks; (void)num_threads_per_block;
-  std::lock_guard<std::mutex> lk(g_v1_mu);
-  if (!g_v1 || num_total_threads > g_v1_n) { set_err("forward_zero called before allocate (or with more threads)"); v1_fail("forward_zero"); }
-  tds_b200_sim* s = g_v1;
+static void v1_forward_zero(V1Instance& I, const V1Spec& S, int num_total_threads, double* output, const double* input) {
+  std::lock_guard<std::mutex> lk(I.mu);
+  if (!I.sim || num_total_threads > I.n) { set_err("forward_zero called before allocate (or with more threads)"); v1_fail(S, "forward_zero"); }
+  tds_b200_sim* s = I.sim;
   const int n = num_total_threads, ns = s->ns;
   cudaStream_t sm = s->stream;
   const int T = 128, B = (n + T - 1) / T;
   const int saved_n = s->n;
   s->n = n;
-  cudaMemcpyAsync(g_v1_dev_in, input, sizeof(double) * (size_t)n * k_laikago_in, cudaMemcpyHostToDevice, sm);
-  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(g_v1_dev_in, k_laikago_in, 0, s->q, 18, n, ns);
-  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(g_v1_dev_in, k_laikago_in, 18, s->qd, 18, n, ns);
-  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(g_v1_dev_in, k_laikago_in, 36, s->act, 12, n, ns);
+  cudaMemcpyAsync(I.dev_in, input, sizeof(double) * (size_t)n * S.in_dim, cudaMemcpyHostToDevice, sm);
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(I.dev_in, S.in_dim, 0, s->q, S.n_q, n, ns);
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(I.dev_in, S.in_dim, S.n_q, s->qd, S.n_q, n, ns);
+  aos_to_soa_kernel<double><<<B, T, 0, sm>>>(I.dev_in, S.in_dim, 2 * S.n_q, s->act, S.n_act, n, ns);
   // kp, kd, max_force travel in the input vector (locomotion_contact_simulation.h:164-166); the v1 ABI is
   // called with one value for the whole batch (ars_vectorized_environment.h:223-236): read env 0's.
-  s->E.kp = (float)input[48]; s->E.kd = (float)input[49]; s->E.max_force = (float)input[50];
+  const int v0 = 2 * S.n_q + S.n_act;
+  s->E.kp = (float)input[v0]; s->E.kd = (float)input[v0 + 1]; s->E.max_force = (float)input[v0 + 2];
   int rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->act, s->q, s->qd, nullptr, nullptr, nullptr,
                                 nullptr, s->link_xf, sm);
-  if (rc) v1_fail("step");
-  pack_v1_output_kernel<<<B, T, 0, sm>>>(s->vis, s->q, s->qd, s->link_xf, g_v1_dev_out, k_laikago_written, n, ns,
-                                         s->dm[0].floating);
-  // entries >= 156 are never written by the reference either (they keep the caller's values)
-  cudaMemcpy2DAsync(output, sizeof(double) * k_laikago_out, g_v1_dev_out, sizeof(double) * k_laikago_written,
-                    sizeof(double) * k_laikago_written, n, cudaMemcpyDeviceToHost, sm);
+  if (rc) v1_fail(S, "step");
+  pack_v1_output_kernel<<<B, T, 0, sm>>>(s->vis, s->q, s->qd, s->link_xf, I.dev_out, S.written, n, ns, s->dm[0].floating);
+  // entries >= written are never written by the reference either (they keep the caller's values)
+  cudaMemcpy2DAsync(output, sizeof(double) * S.out_dim, I.dev_out, sizeof(double) * S.written, sizeof(double) * S.written, n,
+                    cudaMemcpyDeviceToHost, sm);
   cudaError_t e = cudaStreamSynchronize(sm);
   s->n = saved_n;
-  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); v1_fail("forward_zero"); }
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); v1_fail(S, "forward_zero"); }
 }
+
+#define TDS_V1_SYMBOLS(model, inst, spec)                                                                              \
+  CudaFunctionMetaData model##_forward_zero_meta(void) {                                                               \
+    CudaFunctionMetaData d; d.output_dim = spec.out_dim; d.input_dim = spec.in_dim; d.global_dim = 0; return d;        \
+  }                                                                                                                    \
+  void model##_forward_zero_allocate(int num_total_threads) { v1_allocate(inst, spec, num_total_threads); }            \
+  void model##_forward_zero_deallocate(void) { std::lock_guard<std::mutex> lk(inst.mu); v1_release(inst); }            \
+  void model##_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output,          \
+                            const double* input) {                                                                     \
+    (void)num_blocks; (void)num_threads_per_block;                                                                     \
+    v1_forward_zero(inst, spec, num_total_threads, output, input);                                                     \
+  }
+TDS_V1_SYMBOLS(cuda_model_laikago, g_v1_laikago, k_v1_laikago)
+TDS_V1_SYMBOLS(cuda_model_ant, g_v1_ant, k_v1_ant)
+static const int k_laikago_in = 51, k_laikago_out = 411;
 
 // ---- C-ABI v2 (src/utils/cuda/cuda_codegen.hpp:32-231, loaded by tds::CudaLibrary / CudaModel / CudaFunction,
 // src/utils/cuda/cuda_{library,model,function}.hpp): model_info + <model>_forward_zero{,_meta,_allocate,_deallocate,
