@@ -31,6 +31,9 @@ CONFIGS = {
     "laikago": (D + "plane_implicit.urdf", D + "laikago/laikago_toes_zup_xyz_xyzrot.urdf", False, wl.laikago_perturbed),
     "humanoid": (D + "plane_implicit.urdf", D + "humanoid.urdf", True, wl.humanoid),
     "ant": (D + "plane_implicit.urdf", D + "gym/ant_org_xyz_xyzrot.urdf", False, wl.ant_perturbed),
+    # box shapes against the plane (contact_plane_box): our own one-box fixture and the reference's cartpole on the plane
+    "box": (D + "plane_implicit.urdf", os.path.join(HERE, "urdf", "box.urdf"), True, wl.box),
+    "cartpole_plane": (D + "plane_implicit.urdf", D + "cartpole.urdf", False, wl.cartpole_plane),
 }
 
 ANT_POSES, ANT_KP, ANT_KD, ANT_MAX = np.array([0.0, -0.5] * 4), 15.0, 0.3, 3.0   # ant_environment2.h:43-66
@@ -52,7 +55,7 @@ def main():
         sim = ref.RefSim.from_urdf(urdf, plane, floating)
         model = sim.export_model()
         save_model(os.path.join(HERE, "models", name + ".json"), model,
-                   meta=dict(source=os.path.relpath(urdf, D), plane=bool(plane), floating=floating,
+                   meta=dict(source=os.path.relpath(urdf, D) if urdf.startswith(D) else os.path.relpath(urdf, HERE), plane=bool(plane), floating=floating,
                              exported_by="reference UrdfCache::construct via oracle/_ref"))
         w = gen(N)
         sim.set_params(**w["params"])

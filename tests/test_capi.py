@@ -82,13 +82,13 @@ def test_unsupported_models_are_refused_loudly():
         m = np.ascontiguousarray(m, dtype=np.float64)
         return L.tds_b200_validate_model(m.ctypes.data_as(dp), int(m.size)), L.tds_b200_last_error().decode()
 
-    for name in ("cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant"):
+    for name in ("cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane"):
         assert check(load_model(fixture_path(name)))[0] == 0, name
-    # cartpole has box collision shapes; with a ground plane the reference would collide them (contact_plane_box)
-    m = np.array(load_model(fixture_path("cartpole")), dtype=np.float64)
-    m[7] = 1.0                                     # TDSM_H_HASPLANE
+    # a mesh shape against the ground plane: the reference collides it, the contact stage here does not -> refused
+    m = np.array(load_model(fixture_path("box")), dtype=np.float64)
+    m[16 + 13 + 1] = 3.0                           # the geom's type -> TDSG_MESH (no links: geoms follow the base record)
     rc, msg = check(m)
-    assert rc == -6 and "box" in msg
+    assert rc == -6 and "mesh" in msg
     m = np.array(load_model(fixture_path("laikago")), dtype=np.float64)
     m[16 + 13 + 1] = 8.0                           # first link's joint type -> spherical
     rc, msg = check(m)

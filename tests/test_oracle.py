@@ -13,7 +13,7 @@ from oracle import port, ref
 from tds_b200.model import fixture_path, load_model
 import tds_b200.workloads as wl
 
-CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant"]
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane"]
 
 
 def params_of(g):
@@ -80,7 +80,7 @@ def test_c_oracle_matches_live_reference(name):
     model = load_model(fixture_path(name))
     rs = ref.RefSim.from_model(model)            # reference MultiBody rebuilt from the flat model
     gen = dict(cartpole=wl.cartpole, pendulum5=wl.pendulum5, sphere2=wl.sphere2, laikago=wl.laikago_perturbed,
-               humanoid=wl.humanoid, ant=wl.ant_perturbed)[name]
+               humanoid=wl.humanoid, ant=wl.ant_perturbed, box=wl.box, cartpole_plane=wl.cartpole_plane)[name]
     w = gen(24, seed=31337)
     if name == "humanoid":
         w["q"][:, 6] = np.random.default_rng(5).uniform(0.05, 0.4, 24)   # deep, violent contacts too

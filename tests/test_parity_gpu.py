@@ -19,7 +19,7 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant"]
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane"]
 
 
 def rel_err(a, ref):

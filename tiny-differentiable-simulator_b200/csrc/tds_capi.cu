@@ -34,7 +34,7 @@ extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const Env
 // candidate contact points of a model, reference enumeration order: (link_a, link_b) per point
 struct ContactCandTable {
   int n_points;
-  signed char link_a[2 * TDS_MAX_GEOMS], link_b[2 * TDS_MAX_GEOMS];
+  signed char link_a[TDS_MAX_POINTS], link_b[TDS_MAX_POINTS];
 };
 
 namespace {
@@ -390,11 +390,11 @@ extern "C" {
 static const char* tds_model_error(int rc) {
   switch (rc) {
     case -1: return "not a flat model of this layout version (magic / size mismatch)";
-    case -2: return "too many links or collision geoms (TDS_MAX_LINKS / TDS_MAX_GEOMS)";
+    case -2: return "too many links, collision geoms or candidate contact points (TDS_MAX_LINKS / TDS_MAX_GEOMS / TDS_MAX_POINTS)";
     case -3: return "spherical (or unknown) joint type: not implemented";
     case -4: return "links are not ordered parent before child";
     case -5: return "collision geoms are not grouped by link";
-    case -6: return "box / mesh collision shape against the ground plane: the contact stage implements sphere and capsule only";
+    case -6: return "mesh collision shape against the ground plane: the contact stage implements sphere, capsule and box";
     default: return "unknown error";
   }
 }
@@ -451,7 +451,7 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
   if (base.has_plane) {   // plane (body A, base link -1) x every geom of the robot (body B), geoms grouped by link, base first
     int c = 0;
     for (int g = 0; g < base.n_geoms; ++g) {
-      const int pts = base.g_type[g] == TDSG_SPHERE ? 1 : (base.g_type[g] == TDSG_CAPSULE ? 2 : 0);
+      const int pts = base.g_type[g] == TDSG_SPHERE ? 1 : (base.g_type[g] == TDSG_CAPSULE ? 2 : (base.g_type[g] == TDSG_BOX ? 8 : 0));
       for (int j = 0; j < pts; ++j) { s->cand.link_a[c] = -1; s->cand.link_b[c] = (signed char)base.g_link[g]; ++c; }
     }
     s->cand.n_points = c;
@@ -581,6 +581,7 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
+  if (s->dm[0].world_only) kern = 1;   // box shapes / spherical joints: served by the generic world-frame kernel only
   if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(s->spec_idx, p) <= (size_t)s->max_smem_optin)) kern = 3;
   if (kern == 4) {
     s->kernel = kern;

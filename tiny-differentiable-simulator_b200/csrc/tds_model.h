@@ -145,10 +145,23 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     for (int k = 0; k < 3; ++k) D->g_half[g][k] = gg[TDSM_G_R + k * 3 + 2] * hl;  // R_local * (0,0,L/2)
     if (D->g_type[g] == TDSG_SPHERE) n_points += 1;
     if (D->g_type[g] == TDSG_CAPSULE) n_points += 2;
-    // the contact stage implements plane x sphere and plane x capsule; a box / mesh against the ground plane would be
-    // silently contact-free here while the reference collides it (contact_point.hpp:164-198): refuse the model
-    if (D->has_plane && D->g_type[g] != TDSG_SPHERE && D->g_type[g] != TDSG_CAPSULE) return -6;
+    if (D->g_type[g] == TDSG_BOX) {
+      // contact_plane_box, src/contact_point.hpp:164-198: a sphere of radius max(1e-2, Box::radius = 0) at each of the 8
+      // corner points (+-dx, +-dy, +-dz), d = extent / 2 - radius (Box::get_corner_points, src/geometry.hpp:244-260)
+      n_points += 8;
+      const double r = 1e-2;
+      for (int a = 0; a < 3; ++a) {
+        const double d = 0.5 * gg[TDSM_G_P + a] - r;
+        for (int k = 0; k < 3; ++k) D->g_box[g][a * 3 + k] = gg[TDSM_G_R + k * 3 + a] * d;   // column a of R_local, scaled
+      }
+      D->g_radius[g] = r;
+      if (D->has_plane) D->world_only = 1;
+    }
+    // the contact stage implements plane x {sphere, capsule, box}; a mesh against the ground plane would be silently
+    // contact-free here while the reference collides it: refuse the model
+    if (D->has_plane && D->g_type[g] != TDSG_SPHERE && D->g_type[g] != TDSG_CAPSULE && D->g_type[g] != TDSG_BOX) return -6;
   }
+  if (D->has_plane && n_points > TDS_MAX_POINTS) return -2;
   D->max_contacts = D->has_plane ? n_points : 0;
   {  // geoms are enumerated base first, then link 0, 1, ...: ranges per link
     int g = 0;

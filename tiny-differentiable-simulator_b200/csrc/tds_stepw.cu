@@ -123,26 +123,39 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   const V3<RC> pn = v3<RC>(RC(M.plane_n[0]), RC(M.plane_n[1]), RC(M.plane_n[2]));
   const RC plane_off = dot(O, pn) - RC(M.plane_c);   // n.(O + x) - c = n.x + plane_off
   int n_active = 0, pt_index = 0;
+  auto emit_point = [&](int li, const V3<RC>& pos, const RC rad) {
+    const RC dist = dot(pos, pn) + plane_off - rad;       // contact_plane_sphere, contact_point.hpp:112-116
+    if (io.contact_dist && live) io.contact_dist[(size_t)pt_index * ns + e] = (float)dist;
+    ++pt_index;
+    if (dist < RC(0) && n_active < M.max_contacts) {
+      RC* pc = A.ptr<RC>(M.x_con + n_active * 5 * RCW);
+      st3<RC>(pc, ST, pos - pn * rad);                     // world_point_on_b, relative to O
+      pc[3 * ST] = dist;
+      pc[4 * ST] = RC(li);
+      ++n_active;
+    }
+  };
   auto emit_geoms = [&](int li, const M3<RC>& R, const V3<RC>& pr) {
     for (int g = M.geom_begin[li + 1]; g < M.geom_begin[li + 2]; ++g) {
       const int ty = M.g_type[g];
-      if (ty != TDSG_SPHERE && ty != TDSG_CAPSULE) continue;
+      if (ty != TDSG_SPHERE && ty != TDSG_CAPSULE && ty != TDSG_BOX) continue;
       const V3<RC> c = pr + mul(R, v3<RC>(RC(M.g_t[g][0]), RC(M.g_t[g][1]), RC(M.g_t[g][2])));
       const RC rad = RC(M.g_radius[g]);
-      const int npts = (ty == TDSG_CAPSULE) ? 2 : 1;
-      V3<RC> half = v3<RC>(RC(0), RC(0), RC(0));
-      if (ty == TDSG_CAPSULE) half = mul(R, v3<RC>(RC(M.g_half[g][0]), RC(M.g_half[g][1]), RC(M.g_half[g][2])));
-      for (int k = 0; k < npts; ++k) {
-        const V3<RC> pos = (ty == TDSG_CAPSULE) ? (k == 0 ? c + half : c - half) : c;
-        const RC dist = dot(pos, pn) + plane_off - rad;       // contact_point.hpp:112-116
-        if (io.contact_dist && live) io.contact_dist[(size_t)pt_index * ns + e] = (float)dist;
-        ++pt_index;
-        if (dist < RC(0) && n_active < M.max_contacts) {
-          RC* pc = A.ptr<RC>(M.x_con + n_active * 5 * RCW);
-          st3<RC>(pc, ST, pos - pn * rad);                     // world_point_on_b, relative to O
-          pc[3 * ST] = dist;
-          pc[4 * ST] = RC(li);
-          ++n_active;
+      if (ty == TDSG_SPHERE) emit_point(li, c, rad);
+      else if (ty == TDSG_CAPSULE) {   // contact_plane_capsule, contact_point.hpp:128-161: end spheres at +L/2, then -L/2
+        const V3<RC> half = mul(R, v3<RC>(RC(M.g_half[g][0]), RC(M.g_half[g][1]), RC(M.g_half[g][2])));
+        emit_point(li, c + half, rad);
+        emit_point(li, c - half, rad);
+      } else {                         // contact_plane_box, contact_point.hpp:164-198: corner spheres, x outermost, z innermost
+        const double* b = M.g_box[g];
+        const V3<RC> ex = mul(R, v3<RC>(RC(b[0]), RC(b[1]), RC(b[2])));
+        const V3<RC> ey = mul(R, v3<RC>(RC(b[3]), RC(b[4]), RC(b[5])));
+        const V3<RC> ez = mul(R, v3<RC>(RC(b[6]), RC(b[7]), RC(b[8])));
+        for (int k = 0; k < 8; ++k) {
+          V3<RC> pos = (k & 4) ? c - ex : c + ex;
+          pos = (k & 2) ? pos - ey : pos + ey;
+          pos = (k & 1) ? pos - ez : pos + ez;
+          emit_point(li, pos, rad);
         }
       }
     }

@@ -6,6 +6,7 @@
 #define TDS_MAX_GEOMS 24
 #define TDS_MAX_VIS 24
 #define TDS_MAX_ACT 32
+#define TDS_MAX_POINTS 64   // candidate contact points of a model (sphere 1, capsule 2, box 8 per geom)
 
 // link flags
 #define TDS_LF_PARENT_ADJ 1   // parent == i-1  -> deltas are carried in registers
@@ -57,6 +58,9 @@ struct DevModel {
   double g_t[TDS_MAX_GEOMS][3];     // local translation
   double g_half[TDS_MAX_GEOMS][3];  // capsule: local half-axis R_local * (0,0,L/2)
   double g_radius[TDS_MAX_GEOMS];
+  double g_box[TDS_MAX_GEOMS][9];   // box: the three local half-axes R_local * diag(extent / 2 - r), columns x | y | z
+  int world_only;   // the model uses features only the generic world-frame kernel (tds_stepw.cu) implements
+                    // (box shapes, spherical joints): the decomposed / specialised kernels refuse it
   // static ground plane (multibody 0)
   double plane_n[3];
   double plane_c;

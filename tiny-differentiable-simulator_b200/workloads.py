@@ -93,3 +93,28 @@ def humanoid(n, seed=SEED, z_range=(0.9, 1.45)):
     # re-normalise after fp32 rounding so the reference's unit-quaternion assert holds
     q = _f32(q)
     return dict(q=q, qd=_f32(qd), tau=_f32(tau), params=dict(friction=1.0, keep_all_points=False), mode=2)
+
+
+def box(n, seed=SEED):
+    """A free box (tests/golden/urdf/box.urdf) over the plane: random orientation, height such that 0-4 corner spheres
+    penetrate (contact_plane_box)."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 7))
+    quat = r.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    q[:, :4] = quat
+    q[:, 4:6] = r.uniform(-1, 1, (n, 2))
+    q[:, 6] = r.uniform(0.08, 0.27, n)
+    qd = r.uniform(-1, 1, (n, 6))
+    return dict(q=_f32(q), qd=_f32(qd), tau=None, params=dict(friction=0.6, keep_all_points=False), mode=2)
+
+
+def cartpole_plane(n, seed=SEED):
+    """cartpole.urdf (box shapes) with the ground plane: the cart rests in the plane, the pole swings."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 2))
+    q[:, 0] = r.uniform(-0.5, 0.5, n)
+    q[:, 1] = r.uniform(-1.0, 1.0, n)
+    qd = r.uniform(-1, 1, (n, 2))
+    tau = np.zeros((n, 2)); tau[:, 0] = r.uniform(-10, 10, n)
+    return dict(q=_f32(q), qd=_f32(qd), tau=_f32(tau), params=dict(friction=0.5, keep_all_points=True), mode=2)
