@@ -26,6 +26,11 @@ typedef struct tds_b200_sim tds_b200_sim;
 #define TDS_B200_MODE_FULL 2      /* FD -> integrate_euler_qdd -> World::step -> integrate_euler,
                                      examples/environments/locomotion_contact_simulation.h:261-269 */
 
+#define TDS_B200_MODE_WORLD 3     /* World::step(dt) alone, src/world.hpp:302-363: contact detection + constraint solve on the
+                                     given (q, qd); qd out, q unchanged.  Stage of the fine-grained pytinydiffsim sequence
+                                     forward_dynamics -> integrate_euler_qdd -> world.step -> integrate_euler
+                                     (python/pytinydiffsim.inl:659-663,857-876) */
+
 /* arithmetic selector */
 #define TDS_B200_PREC_MIXED 0 /* default: fp32 ABA / factorisation / PGS; fp64 kinematics, contact geometry,
                                  composite inertias, CRBA products, Jacobians and LCP right-hand side */
@@ -93,6 +98,12 @@ int tds_b200_get_dims(const tds_b200_sim* sim, int dims[8]);
 int tds_b200_step_device(tds_b200_sim* sim, int mode, int use_pd, const float* q_in, const float* qd_in,
                          const float* tau_or_action, float* q_out, float* qd_out, float* qdd_out, float* reward,
                          float* done, float* contact_dist, float* link_xf, void* stream);
+
+/* Stand-alone integration stages of the fine-grained surface (device SoA arrays as above):
+ * integrate_euler (src/dynamics/integrator.hpp:10-133): qd += qdd dt (qdd may be NULL = zero), q += qd dt, floating base
+ * quaternion increment + normalisation; integrate_euler_qdd (:141-195): qd += qdd dt only. */
+int tds_b200_integrate_euler_device(tds_b200_sim* sim, float* q, float* qd, const float* qdd, void* stream);
+int tds_b200_integrate_euler_qdd_device(tds_b200_sim* sim, float* qd, const float* qdd, void* stream);
 
 /* ---- host-buffer path (what VectorizedEnvironment-style callers use) --------------------------------
  * Replaces the per-call loop of SerialForwardStepper / OpenMPForwardStepper::step

@@ -630,3 +630,37 @@ def test_reference_vectorized_environment_with_our_stepper_plugin(tmp_path):
     r = subprocess.run([exe, path, "64"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "max rel err" in r.stdout
+
+
+def test_pytinydiffsim_fine_grained_sequence(golden_dir):
+    """The reference's Python surface for the path (python/pytinydiffsim.inl:659-663,857-876): a script that calls
+    forward_dynamics -> integrate_euler_qdd -> world.step -> integrate_euler on one MultiBody, here on the free-box fixture,
+    must reproduce the reference's own step (golden) - every stage runs on the GPU (MODE_FD, the integration kernels,
+    MODE_WORLD)."""
+    import pytinydiffsim as pd
+    g = np.load(os.path.join(golden_dir, "box.npz"))
+    here = os.path.join(os.path.dirname(__file__), "golden", "urdf")
+    world = pd.TinyWorld()
+    world.friction = float(g["param_friction"])
+    parser = pd.TinyUrdfParser()
+    plane_mb, mb = pd.TinyMultiBody(False), pd.TinyMultiBody(True)
+    conv = pd.UrdfToMultiBody2()
+    assert conv.convert2(parser.load_urdf(os.path.join(here, "plane.urdf")), world, plane_mb)
+    assert conv.convert2(parser.load_urdf(os.path.join(here, "box.urdf")), world, mb)
+    assert mb.is_floating() and mb.num_dofs == 7
+    worst = 0.0
+    for i in range(0, g["q_in"].shape[0], 4):
+        mb.set_q(g["q_in"][i]); mb.qd[:] = g["qd_in"][i]; mb.tau[:] = 0.0
+        pd.forward_dynamics(mb, world.gravity)
+        mb.clear_forces()
+        pd.integrate_euler_qdd(mb, 1e-3)
+        world.step(1e-3)
+        pd.integrate_euler(mb, 1e-3)
+        worst = max(worst, rel_err(mb.q, g["q_out"][i]), rel_err(mb.qd, g["qd_out"][i]))
+    assert worst <= TOL
+    env = pd.CartpoleEnv()
+    o = env.reset()
+    out = env.step(3.0)
+    ref = port.step(load_model(fixture_path("cartpole")), port.make_params(dt=1.0 / 60.0, gravity=(0.0, 0.0, -10.0)), 1,
+                    np.float32(o[:2]).astype(np.float64), np.float32(o[2:]).astype(np.float64), np.array([3.0, 0.0]))
+    assert rel_err(np.array(out.obs), np.concatenate([ref["q"], ref["qd"]])) <= TOL and out.reward == 1.0 and out.done is False

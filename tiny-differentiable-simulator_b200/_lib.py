@@ -70,6 +70,10 @@ def lib():
     L.tds_b200_step_device.argtypes = [vp, ci, ci] + [fp] * 10 + [vp]
     L.tds_b200_step_host.restype = ci
     L.tds_b200_step_host.argtypes = [vp, ci, ci, dp, dp, dp, dp, dp, dp, dp]
+    L.tds_b200_integrate_euler_device.restype = ci
+    L.tds_b200_integrate_euler_device.argtypes = [vp, fp, fp, fp, vp]
+    L.tds_b200_integrate_euler_qdd_device.restype = ci
+    L.tds_b200_integrate_euler_qdd_device.argtypes = [vp, fp, fp, vp]
     L.tds_b200_contact_pairs.restype = ci
     L.tds_b200_contact_pairs.argtypes = [vp, vp, ci]
     L.tds_b200_contact_list_device.restype = ci
@@ -109,7 +113,7 @@ DECLARED_SYMBOLS = [
     "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
     "model_info", "b200_laikago_forward_zero", "b200_laikago_forward_zero_meta", "b200_laikago_forward_zero_allocate",
     "b200_laikago_forward_zero_deallocate", "b200_laikago_forward_zero_send_local", "b200_laikago_forward_zero_send_global",
-    "tds_b200_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",
+    "tds_b200_integrate_euler_device", "tds_b200_integrate_euler_qdd_device", "tds_b200_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",
     "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
     "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
     "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",

@@ -246,6 +246,32 @@ __global__ void contact_list_kernel(const float* __restrict__ dist, ContactCandT
   count[e] = k;
   for (; k < T.n_points; ++k) { links[(size_t)(2 * k) * ns + e] = -9; links[(size_t)(2 * k + 1) * ns + e] = -9; }
 }
+// integrate_euler (src/dynamics/integrator.hpp:10-133) and integrate_euler_qdd (:141-195) as stand-alone stages of the
+// fine-grained pytinydiffsim surface (forward_dynamics -> integrate_euler_qdd -> World::step -> integrate_euler): the fused
+// step kernels do the same arithmetic in their epilogues.  qdd may be null (= the zero vector integrate_euler_qdd leaves).
+struct IntegrateTable { int n_links, floating, n_q, n_qd; signed char q_idx[TDS_MAX_LINKS], qd_idx[TDS_MAX_LINKS], fixed[TDS_MAX_LINKS]; };
+__global__ void integrate_euler_kernel(float* __restrict__ q, float* __restrict__ qd, const float* __restrict__ qdd, double dt,
+                                       IntegrateTable T, int update_q, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  auto Q = [&](int k) -> float& { return q[(size_t)k * ns + e]; };
+  auto QD = [&](int k) -> float& { return qd[(size_t)k * ns + e]; };
+  if (qdd) for (int k = 0; k < T.n_qd; ++k) QD(k) = (float)((double)QD(k) + (double)qdd[(size_t)k * ns + e] * dt);
+  if (!update_q) return;
+  if (T.floating) {   // quat_velocity + quat_increment + normalize (tiny_algebra.hpp:604-614)
+    const double h = 0.5 * dt;
+    double qx = Q(0), qy = Q(1), qz = Q(2), qw = Q(3);
+    const double w0 = QD(0), w1 = QD(1), w2 = QD(2);
+    const double dw = (-qx * w0 - qy * w1 - qz * w2) * h, dx = (qw * w0 + qz * w1 - qy * w2) * h;
+    const double dy = (qw * w1 + qx * w2 - qz * w0) * h, dz = (qw * w2 + qy * w0 - qx * w1) * h;
+    qx += dx; qy += dy; qz += dz; qw += dw;
+    const double len = sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    Q(0) = (float)(qx / len); Q(1) = (float)(qy / len); Q(2) = (float)(qz / len); Q(3) = (float)(qw / len);
+    for (int k = 0; k < 3; ++k) Q(4 + k) = (float)((double)Q(4 + k) + (double)QD(3 + k) * dt);
+  }
+  for (int i = 0; i < T.n_links; ++i)
+    if (!T.fixed[i]) Q(T.q_idx[i]) = (float)((double)Q(T.q_idx[i]) + (double)QD(T.qd_idx[i]) * dt);
+}
 __global__ void rollout_init_kernel(float* sticky, float* total, int* steps, int n) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) { sticky[e] = 0.f; total[e] = 0.f; steps[e] = 0; }
@@ -581,7 +607,7 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
-  if (s->dm[0].world_only) kern = 1;   // box shapes / spherical joints: served by the generic world-frame kernel only
+  if (s->dm[0].world_only || mode == 3) kern = 1;   // (mode 3 = TDS_B200_MODE_WORLD)   // box shapes / spherical joints: served by the generic world-frame kernel only
   if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(s->spec_idx, p) <= (size_t)s->max_smem_optin)) kern = 3;
   if (kern == 4) {
     s->kernel = kern;
@@ -663,6 +689,34 @@ int tds_b200_step_host(tds_b200_sim* s, int mode, int use_pd, const double* q, c
   if (mode == TDS_B200_MODE_FD && (rc = down(s->qdd, M.n_qd, qdd_out))) return rc;
   if ((rc = down(s->cdist, s->n_points, contact_dist))) return rc;
   CUDA_TRY(cudaStreamSynchronize(sm));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static IntegrateTable integrate_table(const tds_b200_sim* s) {
+  const DevModel& M = s->dm[0];
+  IntegrateTable T;
+  memset(&T, 0, sizeof(T));
+  T.n_links = M.n_links; T.floating = M.floating; T.n_q = M.n_q; T.n_qd = M.n_qd;
+  for (int i = 0; i < M.n_links; ++i) {
+    T.fixed[i] = (M.flags[i] & TDS_LF_FIXED) ? 1 : 0;
+    T.q_idx[i] = (signed char)(T.fixed[i] ? 0 : M.q_idx[i]); T.qd_idx[i] = (signed char)(T.fixed[i] ? 0 : M.qd_idx[i]);
+  }
+  return T;
+}
+
+int tds_b200_integrate_euler_device(tds_b200_sim* s, float* q, float* qd, const float* qdd, void* stream) {
+  if (!s || !q || !qd) return -1;
+  const int T = 128, B = (s->n + T - 1) / T;
+  integrate_euler_kernel<<<B, T, 0, (cudaStream_t)stream>>>(q, qd, qdd, s->P.dt, integrate_table(s), 1, s->n, s->ns);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_integrate_euler_qdd_device(tds_b200_sim* s, float* qd, const float* qdd, void* stream) {
+  if (!s || !qd || !qdd) return -1;
+  const int T = 128, B = (s->n + T - 1) / T;
+  integrate_euler_kernel<<<B, T, 0, (cudaStream_t)stream>>>(qd, qd, qdd, s->P.dt, integrate_table(s), 0, s->n, s->ns);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

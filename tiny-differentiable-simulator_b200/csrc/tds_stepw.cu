@@ -91,7 +91,8 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     RC* pc = A.ptr<RC>(M.x_acc + s * M.x_acc_words + M.x_acc_ic_word);
     for (int k = 0; k < 10; ++k) pc[k * ST] = RC(0);
   }
-  const bool want_contacts = (mode == MODE_FULL) && M.has_plane;
+  const bool world_step = mode == MODE_WORLD;   // World::step(dt) on its own (src/world.hpp:302-363): q, qd in -> qd out
+  const bool want_contacts = (mode == MODE_FULL || world_step) && M.has_plane;
   TDSW_PHASE();  // 1
 
   // ---- common-frame origin O (world coordinates) -----------------------------------------------------
@@ -468,7 +469,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       a.bot = axpy(S.bot, qdd, a.bot);
       const int qdi = M.qd_idx[i];
       if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)qdi * ns + e] = (float)qdd; }
-      else qdv[qdi * ST] = (float)(RA(qdv[qdi * ST]) + qdd * dtA);
+      else if (!world_step) qdv[qdi * ST] = (float)(RA(qdv[qdi * ST]) + qdd * dtA);
     }
     st6<RA>(vrec, ST, a);
     a_prev = a;
@@ -479,7 +480,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
-      else qdv[k * ST] = (float)(RC(qdv[k * ST]) + qb[k] * RC(P.dt));
+      else if (!world_step) qdv[k * ST] = (float)(RC(qdv[k * ST]) + qb[k] * RC(P.dt));
     }
   }
   TDSW_PHASE();  // 4
@@ -487,7 +488,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
 
   // ---- contact solve -------------------------------------------------------------------------------------------
   __syncwarp();   // the Y rows below reuse the per-link records with another lane interleave
-  if (mode == MODE_FULL && any_contact) {
+  if ((mode == MODE_FULL || world_step) && any_contact) {
     // blocked Cholesky M = L L^T (3x3 blocks, lower): off-diagonal blocks of L overwrite M, diagonal blocks are
     // kept as their inverses.  (The reference inverts M, tiny_matrix_x.h:240-344; only M^-1 products are needed.)
     for (int bi = 0; bi < nb; ++bi) {
@@ -609,7 +610,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
 
   // ---- integrate_euler with qdd = 0 (integrator.hpp:10-133) -----------------------------------------------------
   RC up_z = RC(1);
-  if (M.floating) {
+  if (M.floating && !world_step) {
     const RC h = RC(0.5) * RC(P.dt);
     RC qx = RC(qv[0]), qy = RC(qv[ST]), qz = RC(qv[2 * ST]), qw = RC(qv[3 * ST]);
     const RC w0 = RC(qdv[0]), w1 = RC(qdv[ST]), w2 = RC(qdv[2 * ST]);
@@ -625,7 +626,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       qv[(4 + k) * ST] = (float)(RC(qv[(4 + k) * ST]) + RC(qdv[(3 + k) * ST]) * RC(P.dt));
     up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
   }
-  for (int i = 0; i < n_links; ++i) {
+  for (int i = 0; i < n_links && !world_step; ++i) {
     if (M.flags[i] & TDS_LF_FIXED) continue;
     const int qi = M.q_idx[i];
     qv[qi * ST] = (float)(RC(qv[qi * ST]) + RC(qdv[M.qd_idx[i] * ST]) * RC(P.dt));

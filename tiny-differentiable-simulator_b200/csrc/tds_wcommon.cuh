@@ -168,6 +168,7 @@ template <typename T> TDS_D Sv<T> link_axis(const DevModel& M, int i, V3<T>& ax)
   return z;
 }
 
-enum StepMode { MODE_FD = 0, MODE_NOCONTACT = 1, MODE_FULL = 2 };
+enum StepMode { MODE_FD = 0, MODE_NOCONTACT = 1, MODE_FULL = 2,
+                MODE_WORLD = 3 };   // World::step alone (contact detection + constraint solve on the given q, qd): world-frame kernel only
 
 }  // namespace tdsw

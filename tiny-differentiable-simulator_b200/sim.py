@@ -134,6 +134,29 @@ class BatchSim:
             out["contact_links"] = links[:, :self.n_contact_points]
         return out
 
+    def integrate_host(self, q, qd, qdd, update_q=True):
+        """integrate_euler (update_q) / integrate_euler_qdd of one state vector per environment, on the device
+        (tds_b200_integrate_euler{,_qdd}_device); host arrays [n_q], [n_qd] for a one-environment simulator or [n, dim]."""
+        import torch
+        dev = f"cuda:{self.device}"
+        def up(a, dim):
+            t = torch.zeros((max(dim, 1), self.n_stride), dtype=torch.float32, device=dev)
+            a = np.asarray(a, dtype=np.float64).reshape(-1, dim) if dim else np.zeros((self.n_envs, 0))
+            if dim:
+                t[:dim, :self.n_envs] = torch.tensor(np.ascontiguousarray(a.T), dtype=torch.float32)
+            return t
+        tq, tqd, tqdd = up(q, self.n_q), up(qd, self.n_qd), up(qdd, self.n_qd)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if update_q:
+            self._check(self._L.tds_b200_integrate_euler_device(self._h, _ptr(tq), _ptr(tqd), _ptr(tqdd), st), "integrate_euler")
+        else:
+            self._check(self._L.tds_b200_integrate_euler_qdd_device(self._h, _ptr(tqd), _ptr(tqdd), st), "integrate_euler_qdd")
+        torch.cuda.synchronize()
+        qo = tq[:self.n_q, :self.n_envs].T.cpu().numpy().astype(np.float64)
+        qdo = tqd[:self.n_qd, :self.n_envs].T.cpu().numpy().astype(np.float64)
+        single = np.asarray(q).ndim == 1
+        return (qo[0], qdo[0]) if single else (qo, qdo)
+
     def contact_pairs(self):
         """(body_a, link_a, body_b, link_b) of every candidate contact point, reference enumeration order
         (World::compute_contacts_multi_body_internal, src/world.hpp:212-281): what World::mb_contacts_ lists each step."""
