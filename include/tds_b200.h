@@ -159,6 +159,18 @@ int tds_b200_env_reset_device(tds_b200_sim* sim, const float* mask, const float*
  * the host-buffer entry points use; the same holds for tds_b200_env_reset_device). */
 int tds_b200_env_rollout_device(tds_b200_sim* sim, const float* policy, int n_params, int rollout_length, float shift,
                                 float* total_rewards, int* steps, void* stream);
+/* Observation-filter statistics of the rollouts (ars_vectorized_worker.h:93-110, running_stat.h): with a non-NULL buffer
+ * (device, [3 * (n_q + n_qd)][n_stride] = count | mean | S per component, caller-owned, zero to clear) every rollout step
+ * pushes the observation the policy saw into a per-environment Welford accumulator.  NULL switches it off. */
+int tds_b200_env_set_obs_stats(tds_b200_sim* sim, float* stats);
+/* ARS on the device (ARSVectorizedWorker::do_rollouts, ars_vectorized_worker.h:205-262; ARSLearner::weighted_sum_custom and
+ * train_step, ars_learner.h:67-91,185-189).  w [n_params] device; deltas [n_params][n_stride] unit normals, one direction
+ * per environment; perturb: params[p][e] = w[p] + scale * deltas[p][e] (scale = +-delta_std) in the rollout layout;
+ * update: w[p] += step_size * delta_std / n * sum_e (r_pos[e] - r_neg[e]) * deltas[p][e]. */
+int tds_b200_ars_perturb_device(tds_b200_sim* sim, const float* w, const float* deltas, float scale, float* params, int n_params,
+                                void* stream);
+int tds_b200_ars_update_device(tds_b200_sim* sim, float* w, const float* deltas, const float* r_pos, const float* r_neg,
+                               float delta_std, float step_size, int n_params, void* stream);
 /* reset + rollout with host buffers: policy [n_envs][n_params], noise [n_envs][n_act] or NULL, results to host. */
 int tds_b200_env_rollout_host(tds_b200_sim* sim, const double* policy, int n_params, int rollout_length, double shift,
                               const double* noise, double noise_amp, unsigned long long seed, int settle_steps,

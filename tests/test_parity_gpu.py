@@ -664,3 +664,40 @@ def test_pytinydiffsim_fine_grained_sequence(golden_dir):
     ref = port.step(load_model(fixture_path("cartpole")), port.make_params(dt=1.0 / 60.0, gravity=(0.0, 0.0, -10.0)), 1,
                     np.float32(o[:2]).astype(np.float64), np.float32(o[2:]).astype(np.float64), np.array([3.0, 0.0]))
     assert rel_err(np.array(out.obs), np.concatenate([ref["q"], ref["qd"]])) <= TOL and out.reward == 1.0 and out.done is False
+
+
+def test_ars_iteration_on_the_device():
+    """SURVEY 8f.1, the rest of the ARS loop on the GPU: perturbed per-environment policies, positive / negative rollouts,
+    the observation-filter statistics (Welford, running_stat.h) and the policy update (ars_learner.h:67-91,185-189), against
+    the same formulas in numpy on the rollout returns the device produced."""
+    import torch
+    n, horizon = 64, 12
+    sim = tds_b200.laikago_sim(n)
+    n_params = 12 * 36 + 12
+    g = torch.Generator().manual_seed(3)
+    w = (0.01 * torch.randn(n_params, generator=g)).cuda()
+    deltas = torch.zeros((n_params, sim.n_stride))
+    deltas[:, :n] = torch.randn((n_params, n), generator=g)
+    deltas = deltas.cuda()
+    n_obs = 36
+    stats = torch.zeros((3 * n_obs, sim.n_stride), device="cuda")
+    w0 = w.clone()
+    r_pos, r_neg = sim.ars_train_step(w, deltas, horizon, delta_std=0.03, step_size=0.02, shift=0.0, seed=11, obs_stats=stats)
+    torch.cuda.synchronize()
+    rp, rn, d = r_pos[:n].cpu().numpy().astype(np.float64), r_neg[:n].cpu().numpy().astype(np.float64), deltas[:, :n].cpu().numpy().astype(np.float64)
+    g_hat = (d * (rp - rn)[None, :]).sum(axis=1) * 0.03 / n
+    assert np.allclose(w.cpu().numpy(), w0.cpu().numpy() + 0.02 * g_hat, rtol=1e-4, atol=1e-7)
+    assert not np.allclose(rp, rn)                                    # the two perturbations do differ
+    # positive rollout alone, on a second simulator, reproduces r_pos (same reset noise by seed)
+    sim2 = tds_b200.laikago_sim(n)
+    params = (w0[:, None] + 0.03 * deltas).contiguous()
+    tot = torch.zeros(sim2.n_stride, device="cuda"); steps = torch.zeros(sim2.n_stride, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream()
+    sim2.env_reset_device(seed=11, settle_steps=10, stream=st)
+    sim2.env_rollout_device(params, horizon, 0.0, tot, steps, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(tot[:n].cpu().numpy(), r_pos[:n].cpu().numpy())
+    # observation statistics: two rollouts x horizon pushes per component, x / y zeroed, Welford mean = plain mean
+    s = stats[:, :n].cpu().numpy()
+    assert np.all(s[:n_obs] == 2 * horizon) and np.all(s[n_obs:n_obs + 2] == 0) and np.all(s[2 * n_obs:] >= -1e-6)
+    assert np.all(np.abs(s[n_obs + 2] - 0.45) < 0.1)                 # mean base height over the rollouts

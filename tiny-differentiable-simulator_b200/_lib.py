@@ -54,6 +54,12 @@ def lib():
     L.tds_b200_env_rollout_device.argtypes = [vp, vp, ci, ci, ctypes.c_float, vp, vp, vp]
     L.tds_b200_env_rollout_host.restype = ci
     L.tds_b200_env_rollout_host.argtypes = [vp, vp, ci, ci, ctypes.c_double, vp, ctypes.c_double, ctypes.c_ulonglong, ci, vp, vp]
+    L.tds_b200_env_set_obs_stats.restype = ci
+    L.tds_b200_env_set_obs_stats.argtypes = [vp, vp]
+    L.tds_b200_ars_perturb_device.restype = ci
+    L.tds_b200_ars_perturb_device.argtypes = [vp, vp, vp, ctypes.c_float, vp, ci, vp]
+    L.tds_b200_ars_update_device.restype = ci
+    L.tds_b200_ars_update_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, ci, vp]
     L.tds_b200_num_visuals.restype = ci
     L.tds_b200_num_visuals.argtypes = [vp]
     L.tds_b200_env_step_visual_device.restype = ci
@@ -110,7 +116,7 @@ def last_error():
 DECLARED_SYMBOLS = [
     "tds_b200_last_error", "tds_b200_urdf_to_model", "tds_b200_create", "tds_b200_destroy",
     "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_validate_model", "tds_b200_set_precision", "tds_b200_get_precision", "tds_b200_kernel_name", "tds_b200_get_dims", "tds_b200_env_reset_device",
-    "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
+    "tds_b200_env_set_obs_stats", "tds_b200_ars_perturb_device", "tds_b200_ars_update_device", "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
     "model_info", "b200_laikago_forward_zero", "b200_laikago_forward_zero_meta", "b200_laikago_forward_zero_allocate",
     "b200_laikago_forward_zero_deallocate", "b200_laikago_forward_zero_send_local", "b200_laikago_forward_zero_send_global",
     "tds_b200_integrate_euler_device", "tds_b200_integrate_euler_qdd_device", "tds_b200_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",

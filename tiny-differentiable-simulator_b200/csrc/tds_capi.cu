@@ -272,6 +272,52 @@ __global__ void integrate_euler_kernel(float* __restrict__ q, float* __restrict_
   for (int i = 0; i < T.n_links; ++i)
     if (!T.fixed[i]) Q(T.q_idx[i]) = (float)((double)Q(T.q_idx[i]) + (double)QD(T.qd_idx[i]) * dt);
 }
+// ---- ARS on the device (examples/ars/ars_vectorized_worker.h, ars_learner.h) --------------------------------------
+// Observation filter statistics, ars_vectorized_worker.h:93-110: every rollout step pushes the observation the policy saw
+// (q | qd with x, y zeroed) into a per-(environment, component) RunningStat (running_stat.h:17-37, Welford).
+// stats: [3 * n_obs][ns] = count | mean | S per component; sticky (may be null): finished environments stop pushing -
+// the reference keeps pushing the frozen observation of a done environment, which only inflates its count; documented.
+__global__ void obs_stat_push_kernel(const float* __restrict__ q, const float* __restrict__ qd, float* __restrict__ stats,
+                                     int n_q, int n_qd, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y;
+  if (e >= n) return;
+  const int n_obs = n_q + n_qd;
+  float x = o < n_q ? q[(size_t)o * ns + e] : qd[(size_t)(o - n_q) * ns + e];
+  if (o < 2) x = 0.f;                                   // ars_vectorized_environment.h:285-287
+  float* cnt = stats + (size_t)o * ns + e;
+  float* mean = stats + (size_t)(n_obs + o) * ns + e;
+  float* S = stats + (size_t)(2 * n_obs + o) * ns + e;
+  const float c = *cnt + 1.f;
+  if (c == 1.f) { *mean = x; *S = 0.f; }
+  else { const float m0 = *mean, m1 = m0 + (x - m0) / c; *S += (x - m0) * (x - m1); *mean = m1; }
+  *cnt = c;
+}
+// per-environment policy parameters of a perturbed rollout: params[p][e] = w[p] + sign * delta_std * delta[p][e]
+// (ARSVectorizedWorker::do_rollouts, ars_vectorized_worker.h:205-262)
+__global__ void ars_perturb_kernel(const float* __restrict__ w, const float* __restrict__ deltas, float scale,
+                                   float* __restrict__ params, int n, int ns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (e >= n) return;
+  params[(size_t)p * ns + e] = w[p] + scale * deltas[(size_t)p * ns + e];
+}
+// ARSLearner::weighted_sum_custom + train_step (ars_learner.h:67-91,185-189): g_hat[p] = (1 / N) sum_e (r+ - r-)[e]
+// delta[p][e] delta_std ; w[p] += step_size g_hat[p].  One block per parameter, tree reduction over the environments.
+__global__ void ars_update_kernel(float* __restrict__ w, const float* __restrict__ deltas, const float* __restrict__ r_pos,
+                                  const float* __restrict__ r_neg, float delta_std, float step_size, int n, int ns) {
+  __shared__ float red[256];
+  const int p = blockIdx.x;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) acc += (r_pos[e] - r_neg[e]) * deltas[(size_t)p * ns + e];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) w[p] += step_size * (red[0] * delta_std / (float)n);
+}
 __global__ void rollout_init_kernel(float* sticky, float* total, int* steps, int n) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) { sticky[e] = 0.f; total[e] = 0.f; steps[e] = 0; }
@@ -328,6 +374,7 @@ struct tds_b200_sim {
   // environment layer scratch: reset staging, zero actions, actuated coordinate map, rollout bookkeeping
   float *rq = nullptr, *rqd = nullptr, *zero_act = nullptr, *pol_act = nullptr, *sticky = nullptr, *r_total = nullptr, *pol_params = nullptr;
   int *act_qidx = nullptr, *r_steps = nullptr;
+  float* obs_stats = nullptr;      // caller-owned [3 * n_obs][ns] running statistics of the observation filter, or null
   bool act_qidx_valid = false;
   size_t pol_params_rows = 0;
   // set around the step launch of tds_b200_env_step_host when the specialised kernel serves the host layouts itself
@@ -863,6 +910,29 @@ int tds_b200_env_reset_device(tds_b200_sim* s, const float* mask, const float* n
   return 0;
 }
 
+int tds_b200_ars_perturb_device(tds_b200_sim* s, const float* w, const float* deltas, float scale, float* params, int n_params,
+                                void* stream) {
+  if (!s || !w || !deltas || !params || n_params <= 0) return -1;
+  const int T = 128, B = (s->n + T - 1) / T;
+  ars_perturb_kernel<<<dim3(B, n_params), T, 0, (cudaStream_t)stream>>>(w, deltas, scale, params, s->n, s->ns);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_ars_update_device(tds_b200_sim* s, float* w, const float* deltas, const float* r_pos, const float* r_neg,
+                               float delta_std, float step_size, int n_params, void* stream) {
+  if (!s || !w || !deltas || !r_pos || !r_neg || n_params <= 0) return -1;
+  ars_update_kernel<<<n_params, 256, 0, (cudaStream_t)stream>>>(w, deltas, r_pos, r_neg, delta_std, step_size, s->n, s->ns);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tds_b200_env_set_obs_stats(tds_b200_sim* s, float* stats) {
+  if (!s) return -1;
+  s->obs_stats = stats;
+  return 0;
+}
+
 int tds_b200_env_rollout_device(tds_b200_sim* s, const float* policy, int n_params, int rollout_length, float shift,
                                 float* total_rewards, int* steps, void* stream) {
   if (!s || !policy || !total_rewards || !steps) return -1;
@@ -879,6 +949,7 @@ int tds_b200_env_rollout_device(tds_b200_sim* s, const float* policy, int n_para
   s->E.auto_reset = 0;   // an episode ends at done (ars_vectorized_worker.h:121-133)
   for (int r = 0; r < rollout_length && rc == 0; ++r) {
     policy_linear_kernel<<<dim3(B, s->E.n_act), T, 0, sm>>>(s->q, s->qd, policy, s->pol_act, M.n_q, M.n_qd, s->E.n_act, s->n, s->ns);
+    if (s->obs_stats) obs_stat_push_kernel<<<dim3(B, M.n_q + M.n_qd), T, 0, sm>>>(s->q, s->qd, s->obs_stats, M.n_q, M.n_qd, s->n, s->ns);
     rc = tds_b200_step_device(s, TDS_B200_MODE_FULL, 1, s->q, s->qd, s->pol_act, s->q, s->qd, nullptr, s->reward, s->done, nullptr,
                               nullptr, sm);
     rollout_accum_kernel<<<B, T, 0, sm>>>(s->reward, s->done, shift, s->sticky, total_rewards, steps, s->n);

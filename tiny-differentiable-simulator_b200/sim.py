@@ -212,6 +212,31 @@ class BatchSim:
         self._check(self._L.tds_b200_env_rollout_device(self._h, _ptr(policy), int(policy.shape[0]), int(rollout_length),
                                                         float(shift), _ptr(total_rewards), _ptr(steps), st), "env_rollout_device")
 
+    def ars_train_step(self, w, deltas, rollout_length, delta_std=0.025, step_size=0.02, shift=0.0, seed=0, settle_steps=10,
+                       obs_stats=None):
+        """One ARS iteration without leaving the GPU (ARSLearner::train_step, examples/ars/ars_learner.h:162-190): for the
+        directions deltas [n_params][n_stride] (one per environment) a positive and a negative rollout of the linear policy
+        w +- delta_std * delta from the same reset (noise keyed by `seed`), then w += step_size * g_hat.  w: float32 CUDA
+        tensor [n_params], updated in place.  Returns (r_pos, r_neg) CUDA tensors."""
+        import torch
+        dev = w.device
+        n_params = int(w.numel())
+        params = torch.empty((n_params, self.n_stride), dtype=torch.float32, device=dev)
+        r = [torch.zeros(self.n_stride, dtype=torch.float32, device=dev) for _ in range(2)]
+        steps = torch.zeros(self.n_stride, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream()
+        sp = ctypes.c_void_p(st.cuda_stream)
+        self._check(self._L.tds_b200_env_set_obs_stats(self._h, _ptr(obs_stats)), "env_set_obs_stats")
+        for k, sign in enumerate((1.0, -1.0)):
+            self._check(self._L.tds_b200_ars_perturb_device(self._h, _ptr(w), _ptr(deltas), sign * delta_std, _ptr(params), n_params, sp),
+                        "ars_perturb")
+            self.env_reset_device(seed=seed, settle_steps=settle_steps, stream=st)
+            self.env_rollout_device(params, rollout_length, shift, r[k], steps, stream=st)
+        self._check(self._L.tds_b200_ars_update_device(self._h, _ptr(w), _ptr(deltas), _ptr(r[0]), _ptr(r[1]), delta_std, step_size,
+                                                       n_params, sp), "ars_update")
+        self._check(self._L.tds_b200_env_set_obs_stats(self._h, None), "env_set_obs_stats")
+        return r[0], r[1]
+
     def env_rollout_host(self, policy, rollout_length, shift=0.0, noise=None, noise_amp=0.05, seed=0, settle_steps=10):
         """Reset (noise [n][n_act] or generated) + rollout of per-environment linear policies [n][n_params] (host arrays).
         Returns (total_rewards float64 [n], steps int32 [n])."""
