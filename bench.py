@@ -251,6 +251,9 @@ CONFIGS = {
                           workload="sphere2.urdf on plane_implicit, 16384 envs, contact LCP solve + contact record (BASELINE.json configs[2])"),
     "humanoid4096": dict(envs=4096, bytes=532, model="humanoid", gen="humanoid",
                          workload="humanoid.urdf on plane, 4096 envs/GPU (32768 on 8 GPUs), full step, LCP contacts (BASELINE.json configs[4])"),
+    "humanoid4096_spring": dict(envs=4096, bytes=532, model="humanoid", gen="humanoid", spring=True,
+                                workload="humanoid.urdf on plane, 4096 envs/GPU (32768 on 8 GPUs), full step, spring-damper contacts "
+                                         "(BASELINE.json configs[4]; law of DESIGN.md, parity unpinned: no reference source)"),
 }
 
 
@@ -291,6 +294,10 @@ def run_config(args, rank, world, local_rank):
     if args.impl == "reference":
         if rank != 0:
             return
+        if C.get("spring"):
+            emit({"impl": "reference", "unavailable": "the reference snapshot has no spring-damper solver source (MultiBodyConstraintSolverSpring absent); "
+                                                      "compare with --config humanoid4096 (LCP)"})
+            return
         sample_s = 4.0
         v, sample = _config_reference_rate(args.config, w, model, sample_s)
         per = max(16, int(v * 60.0 / (K + W)))          # a step of this arm = a bounded sample of the batch
@@ -327,6 +334,8 @@ def run_config(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     prec = {0: tds_b200.PREC_AUTO, 1: tds_b200.PREC_F64, 2: tds_b200.PREC_F32, 3: tds_b200.PREC_MIXED}[args.precision]
     sim = tds_b200.BatchSim(model, n, device=local_rank, precision=prec, **w["params"])
+    if C.get("spring"):
+        sim.set_contact_model(1)
     ns = sim.n_stride
     def soa(a, dim):
         t = torch.zeros((max(dim, 1), ns), device=dev)

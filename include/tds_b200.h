@@ -64,6 +64,16 @@ void tds_b200_destroy(tds_b200_sim* sim);
 int tds_b200_set_params(tds_b200_sim* sim, double dt, const double gravity[3], double friction, double restitution,
                         double erp, double cfm, int pgs_iterations, int keep_all_points);
 
+/* Contact law.  0 (default): the reference's impulse-level LCP solved by projected Gauss-Seidel
+ * (MultiBodyConstraintSolver, src/mb_constraint_solver.hpp).  1: spring-damper contacts - the reference's
+ * MultiBodyConstraintSolverSpring, whose SOURCE IS ABSENT from the snapshot (only the parameter names survive,
+ * python/pytinydiffsim.inl:825-856: spring_k, damper_d, exponent_n, hard_contact_condition, v_transition, ...), so the law
+ * is the one written down in DESIGN.md "Spring-damper contacts" (Hunt-Crossley normal force k x^n + d x^n xdot, clamped at
+ * 0 with hard_contact_condition; friction mu f_n tanh(|v_t| / v_transition) against the tangential velocity; applied as
+ * impulses f dt through M^-1 Jc^T): PARITY UNPINNED, self-consistent with oracle/tds_oracle.c. */
+int tds_b200_set_contact_model(tds_b200_sim* sim, int contact_model, double spring_k, double damper_d, double exponent_n,
+                               double v_transition, int hard_contact_condition);
+
 /* PD / environment parameters of LocomotionContactSimulation
  * (examples/environments/locomotion_contact_simulation.h:28-48,168-258): action k drives the k-th
  * non-fixed link at or after `start_link` (base_dof_) towards initial_poses[k] + clamp(action, +-limit).

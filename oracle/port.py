@@ -21,16 +21,21 @@ MAX_CONTACTS = 48
 class Params(ctypes.Structure):
     _fields_ = [("dt", ctypes.c_double), ("gravity", ctypes.c_double * 3), ("friction", ctypes.c_double),
                 ("restitution", ctypes.c_double), ("erp", ctypes.c_double), ("cfm", ctypes.c_double),
-                ("pgs_iterations", ctypes.c_int), ("keep_all_points", ctypes.c_int)]
+                ("pgs_iterations", ctypes.c_int), ("keep_all_points", ctypes.c_int),
+                ("contact_model", ctypes.c_int), ("spring_k", ctypes.c_double), ("damper_d", ctypes.c_double),
+                ("exponent_n", ctypes.c_double), ("v_transition", ctypes.c_double), ("hard_contact_condition", ctypes.c_int)]
 
 
 def make_params(dt=1e-3, gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, erp=0.2, cfm=1e-5,
-                pgs_iterations=1, keep_all_points=False):
+                pgs_iterations=1, keep_all_points=False, contact_model=0, spring_k=50000.0, damper_d=5000.0, exponent_n=1.5,
+                v_transition=0.01, hard_contact_condition=True):
     p = Params()
     p.dt = dt
     p.gravity[:] = gravity
     p.friction, p.restitution, p.erp, p.cfm = friction, restitution, erp, cfm
     p.pgs_iterations, p.keep_all_points = pgs_iterations, int(keep_all_points)
+    p.contact_model, p.spring_k, p.damper_d, p.exponent_n = int(contact_model), spring_k, damper_d, exponent_n
+    p.v_transition, p.hard_contact_condition = v_transition, int(hard_contact_condition)
     return p
 
 

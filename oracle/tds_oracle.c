@@ -744,6 +744,40 @@ static void resolve_collision(const Model* M, State* st, const TdsoParams* P, co
       Jc[(2 * n_c + i) * n + c] = J[c] * f2[0] + J[n + c] * f2[1] + J[2 * n + c] * f2[2];
     }
   }
+  if (P->contact_model == 1) {
+    /* Spring-damper law (DESIGN.md "Spring-damper contacts"; PARITY UNPINNED, no reference source): per penetrating
+     * point, Hunt-Crossley normal force f_n = k x^n + d x^n xdot (x = -distance, xdot = n_b . v_b = approach speed),
+     * clamped at 0 with hard_contact_condition; friction mu f_n tanh(|v_t| / v_transition) against the tangential
+     * velocity; applied as the impulse f dt through qd -= M^-1 Jc^T p, like the LCP impulses above. */
+    double jtp[MAXD];
+    memset(jtp, 0, sizeof jtp);
+    for (int i = 0; i < n_c; ++i) {
+      const Contact* cp = &cps[i];
+      if (!(cp->dist < 0.0)) continue;
+      double J[3 * MAXD], f1[3], f2[3], vel_b[3] = {0, 0, 0};
+      point_jacobian(M, st, cp->link_b, cp->pb, J);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < n; ++c) vel_b[r] += J[r * n + c] * qd[c];
+      plane_space(cp->normal, f1, f2);
+      const double x = -cp->dist, vn = dot3(cp->normal, vel_b), v1 = dot3(f1, vel_b), v2 = dot3(f2, vel_b);
+      const double xn = pow(x, P->exponent_n);
+      double fn = P->spring_k * xn + P->damper_d * xn * vn;
+      if (P->hard_contact_condition && fn < 0.0) fn = 0.0;
+      const double vt = sqrt(v1 * v1 + v2 * v2);
+      const double sc = vt > 1e-12 ? P->friction * fn * tanh(vt / P->v_transition) / vt * P->dt : 0.0;
+      const double p0 = fn * P->dt, p1 = sc * v1, p2 = sc * v2;
+      for (int c = 0; c < n; ++c)
+        jtp[c] += (J[c] * cp->normal[0] + J[n + c] * cp->normal[1] + J[2 * n + c] * cp->normal[2]) * p0 +
+                  (J[c] * f1[0] + J[n + c] * f1[1] + J[2 * n + c] * f1[2]) * p1 +
+                  (J[c] * f2[0] + J[n + c] * f2[1] + J[2 * n + c] * f2[2]) * p2;
+    }
+    for (int r = 0; r < n; ++r) {
+      double s_ = 0;
+      for (int c = 0; c < n; ++c) s_ += Minv[r * n + c] * jtp[c];
+      qd[r] -= s_;
+    }
+    return;
+  }
   /* lcp_A = jac_con * mass_matrix_inv * jac_con^T + cfm, :392-412 */
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < n; ++c) {

@@ -25,6 +25,12 @@ typedef struct {
   double cfm;         /* ::cfm_ :65 */
   int pgs_iterations; /* ::pgs_iterations_ :60 */
   int keep_all_points; /* ::keep_all_points_ :59 */
+  /* Spring-damper contact law (contact_model = 1).  PARITY UNPINNED: MultiBodyConstraintSolverSpring is absent from the
+   * reference snapshot (only its parameter names survive, python/pytinydiffsim.inl:825-856); this restates the law
+   * specified in DESIGN.md "Spring-damper contacts", not a reference source. */
+  int contact_model;     /* 0: LCP / PGS (the reference's solver), 1: spring-damper */
+  double spring_k, damper_d, exponent_n, v_transition;
+  int hard_contact_condition;
 } TdsoParams;
 
 int tdso_step(const double* model, const TdsoParams* P, int mode, const double* q, const double* qd,

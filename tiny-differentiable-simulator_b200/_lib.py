@@ -42,6 +42,8 @@ def lib():
     L.tds_b200_destroy.argtypes = [vp]
     L.tds_b200_set_params.restype = ci
     L.tds_b200_set_params.argtypes = [vp, cd, dp, cd, cd, cd, cd, ci, ci]
+    L.tds_b200_set_contact_model.restype = ci
+    L.tds_b200_set_contact_model.argtypes = [vp, ci, cd, cd, cd, cd, ci]
     L.tds_b200_set_env.restype = ci
     L.tds_b200_set_env.argtypes = [vp, ci, dp, ci, cd, cd, cd, cd, ci]
     L.tds_b200_set_auto_reset.restype = ci
@@ -115,7 +117,7 @@ def last_error():
 # every symbol include/tds_b200.h declares (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
     "tds_b200_last_error", "tds_b200_urdf_to_model", "tds_b200_create", "tds_b200_destroy",
-    "tds_b200_set_params", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_validate_model", "tds_b200_set_precision", "tds_b200_get_precision", "tds_b200_kernel_name", "tds_b200_get_dims", "tds_b200_env_reset_device",
+    "tds_b200_set_params", "tds_b200_set_contact_model", "tds_b200_set_env", "tds_b200_set_auto_reset", "tds_b200_validate_model", "tds_b200_set_precision", "tds_b200_get_precision", "tds_b200_kernel_name", "tds_b200_get_dims", "tds_b200_env_reset_device",
     "tds_b200_env_set_obs_stats", "tds_b200_ars_perturb_device", "tds_b200_ars_update_device", "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
     "model_info", "b200_laikago_forward_zero", "b200_laikago_forward_zero_meta", "b200_laikago_forward_zero_allocate",
     "b200_laikago_forward_zero_deallocate", "b200_laikago_forward_zero_send_local", "b200_laikago_forward_zero_send_global",

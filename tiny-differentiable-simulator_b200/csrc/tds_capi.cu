@@ -547,6 +547,8 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
   s->P.gravity[0] = 0; s->P.gravity[1] = 0; s->P.gravity[2] = -9.81;
   s->P.friction = 0.5; s->P.restitution = 0.0; s->P.erp = 0.2; s->P.cfm = 1e-5;
   s->P.pgs_iterations = 1; s->P.keep_all_points = 0;
+  s->P.contact_model = 0; s->P.hard_contact_condition = 1;
+  s->P.spring_k = 50000.0; s->P.damper_d = 5000.0; s->P.exponent_n = 1.5; s->P.v_transition = 0.01;
   memset(&s->E, 0, sizeof(s->E));
   const size_t ns = s->ns;
   auto alloc = [&](float** p, size_t rows) { return cudaMalloc((void**)p, sizeof(float) * rows * ns) == cudaSuccess && cudaMemset(*p, 0, sizeof(float) * rows * ns) == cudaSuccess; };
@@ -584,6 +586,18 @@ int tds_b200_set_params(tds_b200_sim* s, double dt, const double gravity[3], dou
   for (int k = 0; k < 3; ++k) s->P.gravity[k] = gravity[k];
   s->P.friction = friction; s->P.restitution = restitution; s->P.erp = erp; s->P.cfm = cfm;
   s->P.pgs_iterations = pgs_iterations; s->P.keep_all_points = keep_all_points;
+  return 0;
+}
+
+int tds_b200_set_contact_model(tds_b200_sim* s, int contact_model, double spring_k, double damper_d, double exponent_n,
+                               double v_transition, int hard_contact_condition) {
+  if (!s || contact_model < 0 || contact_model > 1) { set_err("contact_model must be 0 (LCP) or 1 (spring-damper)"); return -1; }
+  if (contact_model == 1 && !(spring_k >= 0.0 && damper_d >= 0.0 && exponent_n > 0.0 && v_transition > 0.0)) {
+    set_err("spring-damper parameters out of range"); return -2;
+  }
+  drop_host_graph(s);
+  s->P.contact_model = contact_model; s->P.hard_contact_condition = hard_contact_condition ? 1 : 0;
+  s->P.spring_k = spring_k; s->P.damper_d = damper_d; s->P.exponent_n = exponent_n; s->P.v_transition = v_transition;
   return 0;
 }
 
@@ -654,7 +668,7 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
-  if (s->dm[0].world_only || mode == 3) kern = 1;   // (mode 3 = TDS_B200_MODE_WORLD)   // box shapes / spherical joints: served by the generic world-frame kernel only
+  if (s->dm[0].world_only || mode == 3 || s->P.contact_model != 0) kern = 1;   // (mode 3 = TDS_B200_MODE_WORLD)   // box shapes / spherical joints: served by the generic world-frame kernel only
   if (kern == 4 && !(s->spec_ok && tds_spec_smem_bytes(s->spec_idx, p) <= (size_t)s->max_smem_optin)) kern = 3;
   if (kern == 4) {
     s->kernel = kern;
@@ -1044,7 +1058,7 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   cudaStream_t sm = s->stream;
   const int T = 128, B = (n + T - 1) / T;
   // the specialised kernel reads environment-major actions and writes the observation block itself
-  const bool direct = s->kernel_req == 4 && s->spec_ok && tds_spec_smem_bytes(s->spec_idx, s->precision) <= (size_t)s->max_smem_optin;
+  const bool direct = s->kernel_req == 4 && s->spec_ok && s->P.contact_model == 0 && tds_spec_smem_bytes(s->spec_idx, s->precision) <= (size_t)s->max_smem_optin;
   auto enqueue = [&]() -> int {
     CUDA_TRY(cudaMemcpyAsync(d_in, actions, in_b, cudaMemcpyHostToDevice, sm));
     if (direct) {

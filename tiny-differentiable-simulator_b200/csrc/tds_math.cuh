@@ -249,6 +249,10 @@ TDS_D void sincos_t(double a, double* s, double* c) {
   *s = (q & 2) ? -ss : ss;
   *c = ((q + 1) & 2) ? -cc : cc;
 }
+TDS_D float pow_t(float a, float b) { return powf(a, b); }
+TDS_D double pow_t(double a, double b) { return pow(a, b); }
+TDS_D float tanh_t(float a) { return tanhf(a); }
+TDS_D double tanh_t(double a) { return tanh(a); }
 TDS_D float sqrt_t(float a) { return sqrtf(a); }
 TDS_D double sqrt_t(double a) { return sqrt(a); }
 

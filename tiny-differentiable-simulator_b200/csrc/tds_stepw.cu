@@ -533,7 +533,8 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
         }
         // rel_vel = vel_a - vel_b = -vel ; mb_constraint_solver.hpp:299-345
         RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;   // b[3], x[3]
-        cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
+        if (P.contact_model == 1) cs[0] = RS(dot(nbv, vel));   // spring-damper: approach speed n_b . v_b
+        else cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
         cs[ST] = RS(dot(f1, vel));
         cs[2 * ST] = RS(dot(f2, vel));
         cs[3 * ST] = RS(0); cs[4 * ST] = RS(0); cs[5 * ST] = RS(0);
@@ -550,6 +551,28 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     // (solve_pgs, mb_constraint_solver.hpp:101-142; bounds :417-436)
     for (int k = 0; k < n3; ++k) wv[k * ST] = RS(0);
     const RS cfm = RS(P.cfm), mu = RS(P.friction);
+    if (P.contact_model == 1) {
+      // Spring-damper law instead of the LCP (DESIGN.md "Spring-damper contacts"; parity unpinned): closed-form impulses
+      //   p_n = dt max(0, k x^n + d x^n xdot),  x = -distance, xdot = n_b . v_b
+      //   p_t = dt mu f_n tanh(|v_t| / v_transition) v_t / |v_t|   along the two friction directions
+      // accumulated into w = Y p like the Gauss-Seidel impulses; the back substitution below is shared.
+      for (int c = 0; c < max_active; ++c) {
+        if (c < n_active) {
+          const RS* cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;
+          const RS x = RS(-A.ptr<RC>(M.x_con + c * 5 * RCW)[3 * ST]);
+          const RS vn = cs[0], v1 = cs[ST], v2 = cs[2 * ST];
+          const RS xn = pow_t(x, RS(P.exponent_n));
+          RS fn = RS(P.spring_k) * xn + RS(P.damper_d) * xn * vn;
+          if (P.hard_contact_condition && fn < RS(0)) fn = RS(0);
+          const RS vt = sqrt_t(v1 * v1 + v2 * v2);
+          const RS sc = vt > RS(1e-12) ? mu * fn * tanh_t(vt / RS(P.v_transition)) / vt * RS(P.dt) : RS(0);
+          const RS p[3] = {fn * RS(P.dt), sc * v1, sc * v2};
+          const RS* y = A.ptr<RS>(M.x_Y) + (c * n3 * 3) * ST;
+          for (int k = 0; k < n3; ++k)
+            wv[k * ST] += p[0] * y[(3 * k) * ST] + p[1] * y[(3 * k + 1) * ST] + p[2] * y[(3 * k + 2) * ST];
+        }
+      }
+    } else
     for (int it = 0; it < P.pgs_iterations; ++it) {
       for (int blk = 0; blk < 3; ++blk) {
         for (int c = 0; c < max_active; ++c) {

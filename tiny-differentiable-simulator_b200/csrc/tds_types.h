@@ -82,6 +82,12 @@ struct SimParams {
   double friction, restitution, erp, cfm;
   int pgs_iterations;
   int keep_all_points;
+  // contact law: 0 = the reference's impulse-level LCP / PGS; 1 = spring-damper (Hunt-Crossley normal force + smoothed
+  // Coulomb friction, DESIGN.md "Spring-damper contacts"; parameter names of the reference's absent
+  // MultiBodyConstraintSolverSpring, python/pytinydiffsim.inl:825-856).  World-frame kernel only.
+  int contact_model;
+  int hard_contact_condition;
+  double spring_k, damper_d, exponent_n, v_transition;
 };
 
 struct EnvParams {

@@ -64,6 +64,12 @@ class BatchSim:
         self._check(self._L.tds_b200_set_params(self._h, dt, _dp(g), friction, restitution, erp, cfm,
                                                 pgs_iterations, int(keep_all_points)), "set_params")
 
+    def set_contact_model(self, contact_model=1, spring_k=50000.0, damper_d=5000.0, exponent_n=1.5, v_transition=0.01,
+                          hard_contact_condition=True):
+        """0: LCP / PGS (reference solver); 1: spring-damper law (parity unpinned, see include/tds_b200.h)."""
+        self._check(self._L.tds_b200_set_contact_model(self._h, int(contact_model), spring_k, damper_d, exponent_n, v_transition,
+                                                       int(hard_contact_condition)), "set_contact_model")
+
     def set_env(self, initial_poses, start_link=0, kp=0.0, kd=0.0, max_force=0.0, action_limit=0.4,
                 reward_kind=0):
         ip = np.ascontiguousarray(initial_poses, dtype=np.float64)
