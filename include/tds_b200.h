@@ -109,6 +109,20 @@ int tds_b200_step_device(tds_b200_sim* sim, int mode, int use_pd, const float* q
                          const float* tau_or_action, float* q_out, float* qd_out, float* qdd_out, float* reward,
                          float* done, float* contact_dist, float* link_xf, void* stream);
 
+/* ---- differentiable step (the role of <model>_jacobian in the reference's generated libraries,
+ * src/utils/cuda/cuda_codegen.hpp:303-426, there produced by CppAD from the recorded tape) -----------------------------
+ * Dense Jacobian of one step per environment by forward-mode dual numbers (fp64) through the step kernel: rows = q' | qd'
+ * (modes NOCONTACT / FULL) or qdd (mode FD); columns = q | qd | tau (use_pd == 0) or q | qd | action | kp, kd, max_force
+ * (use_pd == 1: the input vector of LocomotionContactSimulation, locomotion_contact_simulation.h:160-166).  Derivatives
+ * are those of the branch taken (contact set, clamps).  dims[0..1] = rows, columns.
+ *   device: q, qd, tau_or_action as in tds_b200_step_device; jac [rows * cols][n_stride] fp64 (row-major per environment)
+ *   host:   q [n][n_q], qd [n][n_qd], tau_or_action [n][..] fp64; jac [n][rows][cols] fp64 */
+int tds_b200_jacobian_dims(const tds_b200_sim* sim, int mode, int use_pd, int dims[2]);
+int tds_b200_step_jacobian_device(tds_b200_sim* sim, int mode, int use_pd, const float* q, const float* qd,
+                                  const float* tau_or_action, double* jac, void* stream);
+int tds_b200_step_jacobian_host(tds_b200_sim* sim, int mode, int use_pd, const double* q, const double* qd,
+                                const double* tau_or_action, double* jac);
+
 /* Stand-alone integration stages of the fine-grained surface (device SoA arrays as above):
  * integrate_euler (src/dynamics/integrator.hpp:10-133): qd += qdd dt (qdd may be NULL = zero), q += qd dt, floating base
  * quaternion increment + normalisation; integrate_euler_qdd (:141-195): qd += qdd dt only. */
@@ -225,7 +239,7 @@ void cuda_model_ant_forward_zero_deallocate(void);
 
 /* ---- C-ABI v2 (alt): what tds::CudaLibrary / CudaModel / CudaFunction load (src/utils/cuda/cuda_library.hpp:51-68,
  * cuda_model.hpp:14-25, cuda_function.hpp:78-100; emitted at src/utils/cuda/cuda_codegen.hpp:32-231).  One model,
- * "b200_laikago" (same 51 -> 411 function as cuda_model_laikago); <model>_jacobian is absent -> reported unavailable. */
+ * "b200_laikago" (same 51 -> 411 function as cuda_model_laikago) with its <model>_jacobian. */
 typedef struct { int output_dim; int local_input_dim; int global_input_dim; bool accumulated_output; } CudaFunctionMetaDataV2;
 void model_info(char const* const** names, int* count);
 CudaFunctionMetaDataV2 b200_laikago_forward_zero_meta(void);
@@ -234,6 +248,14 @@ void b200_laikago_forward_zero_deallocate(void);
 bool b200_laikago_forward_zero_send_local(int num_total_threads, const double* input);
 bool b200_laikago_forward_zero_send_global(const double* input);
 void b200_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output);
+/* <model>_jacobian of the same generation (src/utils/cuda/cuda_codegen.hpp:303-426): rows = the 36 state outputs q' | qd'
+ * (output sparsity, :283-288), columns = the 51 local inputs; output_dim = 36 * 51 per thread, row-major, not accumulated. */
+CudaFunctionMetaDataV2 b200_laikago_jacobian_meta(void);
+void b200_laikago_jacobian_allocate(int num_total_threads);
+void b200_laikago_jacobian_deallocate(void);
+bool b200_laikago_jacobian_send_local(int num_total_threads, const double* input);
+bool b200_laikago_jacobian_send_global(const double* input);
+void b200_laikago_jacobian(int num_total_threads, int num_blocks, int num_threads_per_block, double* output);
 
 #ifdef __cplusplus
 }

@@ -731,3 +731,82 @@ def test_spring_damper_contacts_vs_oracle(name, golden_dir):
     sim.set_contact_model(0)
     lcp = sim.step_host(2, g["q_in"], g["qd_in"], t)
     assert rel_err(lcp["qd"], g["qd_out"]) <= TOL            # and switching back restores the reference's solver
+
+
+def _central_differences(f, x, h=1e-6):
+    """J[:, j] = (f(x + h e_j) - f(x - h e_j)) / 2h of the fp64 oracle."""
+    y0 = f(x)
+    J = np.zeros((y0.size, x.size))
+    for j in range(x.size):
+        xp, xm = x.copy(), x.copy()
+        xp[j] += h; xm[j] -= h
+        J[:, j] = (f(xp) - f(xm)) / (2 * h)
+    return J
+
+
+@pytest.mark.parametrize("name,gen", [("pendulum5", wl.pendulum5), ("cartpole", wl.cartpole), ("sphere2", wl.sphere2), ("box", wl.box),
+                                      ("humanoid", wl.humanoid)])
+def test_step_jacobian_vs_central_differences(name, gen):
+    """the batched step Jacobian (forward-mode dual numbers through the CUDA step kernel) against central
+    differences of the fp64 C oracle.  The step is piecewise smooth (contact set, clamps): an environment whose finite-
+    difference stencil straddles a kink is not comparable, so the bar is 1e-4 (relative to max(1, |J|)) on at least 90 %
+    of the environments, and on ALL of them for the contact-free pipelines."""
+    n = 24
+    model = load_model(fixture_path(name))
+    w = gen(n, seed=2718)
+    mode = w["mode"]
+    sim = tds_b200.BatchSim(model, n, **w["params"])
+    tau = w.get("tau")
+    t_dev = None if tau is None or not sim.n_tau else tau[:, -sim.n_tau:]
+    J = sim.step_jacobian_host(mode, w["q"], w["qd"], t_dev)
+    P = port.make_params(**w["params"])
+    n_q, n_qd, n_tau = sim.n_q, sim.n_qd, sim.n_tau
+    assert J.shape == (n, n_qd if mode == 0 else n_q + n_qd, n_q + n_qd + n_tau)
+    worst = []
+    for e in range(n):
+        def f(x):
+            full = np.zeros(max(tau.shape[1], 1)) if tau is not None else None
+            if full is not None:
+                full[:] = tau[e]; full[full.size - n_tau:] = x[n_q + n_qd:]
+            r = port.step(model, P, mode, x[:n_q], x[n_q:n_q + n_qd], full)
+            return r["qdd"] if mode == 0 else np.concatenate([r["q"], r["qd"]])
+        x0 = np.concatenate([w["q"][e], w["qd"][e], t_dev[e] if t_dev is not None else np.zeros(0)])
+        Jr = _central_differences(f, x0)
+        worst.append(np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))))
+    worst = np.array(worst)
+    ok = worst <= 1e-4
+    assert ok.mean() >= (1.0 if mode != 2 else 0.9), (worst.max(), ok.mean())
+
+
+def test_laikago_jacobian_v2_abi(golden_dir):
+    """b200_laikago_jacobian{,_meta,_allocate,_deallocate,_send_local,_send_global}: the <model>_jacobian function of the
+    reference's generated libraries (src/utils/cuda/cuda_codegen.hpp:303-426), 36 state rows x 51 local inputs per thread,
+    against central differences of the oracle's locomotion step (PD gains are inputs 48..50)."""
+    import ctypes
+    g = np.load(os.path.join(golden_dir, "laikago.npz"))
+    L = tds_b200.lib()
+
+    class MetaV2(ctypes.Structure):
+        _fields_ = [("output_dim", ctypes.c_int), ("local_input_dim", ctypes.c_int), ("global_input_dim", ctypes.c_int),
+                    ("accumulated_output", ctypes.c_bool)]
+    L.b200_laikago_jacobian_meta.restype = MetaV2
+    m = L.b200_laikago_jacobian_meta()
+    assert (m.output_dim, m.local_input_dim, m.global_input_dim, m.accumulated_output) == (36 * 51, 51, 0, False)
+    n = 16
+    x = np.ascontiguousarray(g["env_input"][:n])
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.b200_laikago_jacobian_send_local.restype = ctypes.c_bool
+    L.b200_laikago_jacobian_allocate(n)
+    assert L.b200_laikago_jacobian_send_local(n, x.ctypes.data_as(dp))
+    out = np.zeros((n, 36, 51))
+    L.b200_laikago_jacobian(ctypes.c_int(n), ctypes.c_int(1), ctypes.c_int(32), out.ctypes.data_as(dp))
+    L.b200_laikago_jacobian_deallocate()
+    model = load_model(fixture_path("laikago"))
+    P = port.make_params(friction=1.0, keep_all_points=True)
+    worst = []
+    for e in range(n):
+        f = lambda v: port.locomotion_step(model, P, tds_b200.envs.LAIKAGO_INITIAL_POSES, 6, v[None, :], 411)[0, :36]
+        Jr = _central_differences(f, x[e].copy())
+        worst.append(np.max(np.abs(out[e] - Jr) / np.maximum(1.0, np.abs(Jr))))
+    worst = np.array(worst)
+    assert (worst <= 1e-4).mean() >= 0.8, worst

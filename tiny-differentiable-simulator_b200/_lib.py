@@ -78,6 +78,12 @@ def lib():
     L.tds_b200_step_device.argtypes = [vp, ci, ci] + [fp] * 10 + [vp]
     L.tds_b200_step_host.restype = ci
     L.tds_b200_step_host.argtypes = [vp, ci, ci, dp, dp, dp, dp, dp, dp, dp]
+    L.tds_b200_jacobian_dims.restype = ci
+    L.tds_b200_jacobian_dims.argtypes = [vp, ci, ci, ctypes.POINTER(ci)]
+    L.tds_b200_step_jacobian_device.restype = ci
+    L.tds_b200_step_jacobian_device.argtypes = [vp, ci, ci, fp, fp, fp, vp, vp]
+    L.tds_b200_step_jacobian_host.restype = ci
+    L.tds_b200_step_jacobian_host.argtypes = [vp, ci, ci, dp, dp, dp, dp]
     L.tds_b200_integrate_euler_device.restype = ci
     L.tds_b200_integrate_euler_device.argtypes = [vp, fp, fp, fp, vp]
     L.tds_b200_integrate_euler_qdd_device.restype = ci
@@ -121,7 +127,9 @@ DECLARED_SYMBOLS = [
     "tds_b200_env_set_obs_stats", "tds_b200_ars_perturb_device", "tds_b200_ars_update_device", "tds_b200_env_rollout_device", "tds_b200_env_rollout_host", "tds_b200_num_visuals", "tds_b200_env_step_visual_device",
     "model_info", "b200_laikago_forward_zero", "b200_laikago_forward_zero_meta", "b200_laikago_forward_zero_allocate",
     "b200_laikago_forward_zero_deallocate", "b200_laikago_forward_zero_send_local", "b200_laikago_forward_zero_send_global",
-    "tds_b200_integrate_euler_device", "tds_b200_integrate_euler_qdd_device", "tds_b200_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",
+    "b200_laikago_jacobian", "b200_laikago_jacobian_meta", "b200_laikago_jacobian_allocate", "b200_laikago_jacobian_deallocate",
+    "b200_laikago_jacobian_send_local", "b200_laikago_jacobian_send_global",
+    "tds_b200_jacobian_dims", "tds_b200_step_jacobian_device", "tds_b200_step_jacobian_host", "tds_b200_integrate_euler_device", "tds_b200_integrate_euler_qdd_device", "tds_b200_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",
     "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
     "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
     "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",

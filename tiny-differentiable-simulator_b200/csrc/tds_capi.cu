@@ -27,6 +27,8 @@ extern "C" size_t tds_spec_smem_bytes(int spec, int precision);
 extern "C" const char* tds_spec_name(int spec);
 extern "C" int tds_launch_step_spec(int spec, const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
                                     int precision, cudaStream_t stream);
+extern "C" int tds_launch_stepw_jacobian(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io, int mode,
+                                         int use_pd, int n_dirs, char* gscratch, cudaStream_t stream);
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream);
@@ -329,6 +331,9 @@ struct tds_b200_sim {
   int device = 0;
   int n = 0, ns = 0;
   DevModel dm[3];         // one layout per precision mode
+  DevModel dm_ad;         // layout of the differentiable instance (dual numbers, 16-byte scalars)
+  char* jac_scratch = nullptr; size_t jac_scratch_bytes = 0;
+  double* jac_dev = nullptr; size_t jac_dev_bytes = 0;
   bool smem_ok[3] = {false, false, false};
   bool smem_ok_w[3] = {false, false, false};
   // 3: role-warp kernel (tds_stepr.cu), 2: lane-team kernel (tds_stept.cu), 1: one-lane world-frame kernel
@@ -514,6 +519,8 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     // several warps per block only help when many blocks would otherwise be needed per SM
     s->warps_per_block[p] = 1;
   }
+  s->dm_ad = base;
+  tds_build_layout_w(&s->dm_ad, 16, 16, 16, -1, 16);
   s->model.assign(model, model + n_model);
   if (const char* kv = getenv("TDS_B200_KERNEL"))
     s->kernel_req = strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : (strcmp(kv, "role") == 0 ? 3 : 4));
@@ -571,7 +578,7 @@ void tds_b200_destroy(tds_b200_sim* s) {
   drop_host_graph(s);
   cudaFree(s->rq); cudaFree(s->rqd); cudaFree(s->zero_act); cudaFree(s->pol_act); cudaFree(s->sticky); cudaFree(s->r_total);
   cudaFree(s->pol_params); cudaFree(s->act_qidx); cudaFree(s->r_steps);
-  cudaFree(s->c_count); cudaFree(s->c_links);
+  cudaFree(s->c_count); cudaFree(s->c_links); cudaFree(s->jac_scratch); cudaFree(s->jac_dev);
   cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk); cudaFree(s->team_dev);
   if (s->stage_host) cudaFreeHost(s->stage_host);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -665,6 +672,7 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
   io.reward = reward; io.done = done; io.contact_dist = contact_dist; io.link_xf = link_xf;
   io.phase_clk = s->phase_clk;
   io.act_aos = s->io_act_aos; io.obs_aos = s->io_obs_aos; io.obs_tail = s->io_obs_tail;
+  io.jac = nullptr; io.jac_n_in = 0; io.jac_dir0 = 0;
   io.n = s->n; io.n_stride = s->ns;
   if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
   int kern = s->kernel_req;
@@ -709,6 +717,94 @@ int tds_b200_step_device(tds_b200_sim* s, int mode, int use_pd, const float* q_i
                             s->warps_per_block[p], (cudaStream_t)stream);
   if (rc) set_err(std::string("step launch: ") + cudaGetErrorString((cudaError_t)rc));
   return rc;
+}
+
+// ---- differentiable step: d(q', qd') / d(q, qd, tau | action, kp, kd, max_force), or d qdd / d(...) in
+// forward-dynamics mode, by forward-mode dual numbers through the world-frame step kernel (tds_stepw.cu, tds_dual.cuh).
+int tds_b200_jacobian_dims(const tds_b200_sim* s, int mode, int use_pd, int dims[2]) {
+  if (!s || !dims) return -1;
+  const DevModel& M = s->dm[0];
+  dims[0] = mode == TDS_B200_MODE_FD ? M.n_qd : M.n_q + M.n_qd;
+  dims[1] = M.n_q + M.n_qd + (use_pd ? s->E.n_act + 3 : s->n_tau);
+  return 0;
+}
+
+int tds_b200_step_jacobian_device(tds_b200_sim* s, int mode, int use_pd, const float* q, const float* qd, const float* tau_or_action,
+                                  double* jac, void* stream) {
+  if (!s || !q || !qd || !jac) return -1;
+  if (mode == 3) { set_err("jacobian: modes FD, NOCONTACT, FULL"); return -2; }
+  if (use_pd && s->E.n_act == 0) { set_err("use_pd without tds_b200_set_env"); return -3; }
+  int dims[2];
+  tds_b200_jacobian_dims(s, mode, use_pd, dims);
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.q_in = q; io.qd_in = qd; io.tau_in = tau_or_action;
+  io.jac = jac; io.jac_n_in = dims[1];
+  io.n = s->n; io.n_stride = s->ns;
+  const size_t warps = (size_t)(s->n + 31) / 32;
+  const size_t per_dir = warps * (size_t)s->dm_ad.x_total * 32 * 4;
+  const size_t cap = (size_t)2 << 30;                       // scratch bound: directions are processed in chunks
+  int chunk = (int)(cap / per_dir);
+  if (chunk < 1) chunk = 1;
+  if (chunk > dims[1]) chunk = dims[1];
+  if (per_dir * chunk > s->jac_scratch_bytes) {
+    if (s->jac_scratch) cudaFree(s->jac_scratch);
+    s->jac_scratch = nullptr; s->jac_scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&s->jac_scratch, per_dir * chunk));
+    s->jac_scratch_bytes = per_dir * chunk;
+  }
+  for (int d0 = 0; d0 < dims[1]; d0 += chunk) {
+    io.jac_dir0 = d0;
+    const int nd = dims[1] - d0 < chunk ? dims[1] - d0 : chunk;
+    int rc = tds_launch_stepw_jacobian(&s->dm_ad, &s->P, &s->E, &io, mode, use_pd, nd, s->jac_scratch, (cudaStream_t)stream);
+    if (rc) { set_err(std::string("jacobian launch: ") + cudaGetErrorString((cudaError_t)rc)); return rc; }
+  }
+  return 0;
+}
+
+int tds_b200_step_jacobian_host(tds_b200_sim* s, int mode, int use_pd, const double* q, const double* qd,
+                                const double* tau_or_action, double* jac) {
+  if (!s || !q || !qd || !jac) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const DevModel& M = s->dm[0];
+  const int n = s->n, ns = s->ns;
+  int dims[2];
+  tds_b200_jacobian_dims(s, mode, use_pd, dims);
+  const int n_in = use_pd ? s->E.n_act : s->n_tau;
+  const size_t maxdim = (size_t)(M.n_q > M.n_qd ? M.n_q : M.n_qd) + 1;
+  int rc = ensure_stage(s, sizeof(double) * n * maxdim, 0);
+  if (rc) return rc;
+  const size_t jb = sizeof(double) * (size_t)dims[0] * dims[1] * ns;
+  if (jb > s->jac_dev_bytes) {
+    if (s->jac_dev) cudaFree(s->jac_dev);
+    s->jac_dev = nullptr; s->jac_dev_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&s->jac_dev, jb));
+    s->jac_dev_bytes = jb;
+  }
+  double* st = (double*)s->stage_dev;
+  const int T = 128, B = (n + T - 1) / T;
+  cudaStream_t sm = s->stream;
+  auto up = [&](const double* src, int dim, float* dst) -> int {
+    if (dim == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(st, src, sizeof(double) * n * dim, cudaMemcpyHostToDevice, sm));
+    aos_to_soa_kernel<double><<<B, T, 0, sm>>>(st, dim, 0, dst, dim, n, ns);
+    return 0;
+  };
+  if ((rc = up(q, M.n_q, s->q))) return rc;
+  if ((rc = up(qd, M.n_qd, s->qd))) return rc;
+  if (tau_or_action) { if ((rc = up(tau_or_action, n_in, s->act))) return rc; }
+  else CUDA_TRY(cudaMemsetAsync(s->act, 0, sizeof(float) * ns * (n_in > 0 ? n_in : 1), sm));
+  CUDA_TRY(cudaMemsetAsync(s->jac_dev, 0, jb, sm));
+  rc = tds_b200_step_jacobian_device(s, mode, use_pd, s->q, s->qd, s->act, s->jac_dev, sm);
+  if (rc) return rc;
+  std::vector<double> tmp((size_t)dims[0] * dims[1] * ns);
+  CUDA_TRY(cudaMemcpyAsync(tmp.data(), s->jac_dev, jb, cudaMemcpyDeviceToHost, sm));
+  CUDA_TRY(cudaStreamSynchronize(sm));
+  CUDA_TRY(cudaGetLastError());
+  const size_t rc_n = (size_t)dims[0] * dims[1];
+  for (int e = 0; e < n; ++e)
+    for (size_t k = 0; k < rc_n; ++k) jac[(size_t)e * rc_n + k] = tmp[k * ns + e];
+  return 0;
 }
 
 int tds_b200_step_host(tds_b200_sim* s, int mode, int use_pd, const double* q, const double* qd,
@@ -1255,7 +1351,7 @@ static const int k_laikago_in = 51, k_laikago_out = 411;
 // src/utils/cuda/cuda_{library,model,function}.hpp): model_info + <model>_forward_zero{,_meta,_allocate,_deallocate,
 // _send_local,_send_global}.  The model is exported as "b200_laikago" (the v1 symbols keep the name cuda_model_laikago:
 // the two generations use the same symbol names with different meta structs, so they cannot share a model name).
-// <model>_jacobian is not exported: CudaFunction marks it unavailable (cuda_function.hpp:80-86).
+// <model>_jacobian: b200_laikago_jacobian below (forward-mode dual numbers through the step kernel).
 static std::vector<double> g_v2_local;   // thread-local inputs as last sent ([n][51], host)
 static int g_v2_sent = 0;
 
@@ -1298,6 +1394,60 @@ bool b200_laikago_forward_zero_send_global(const double* input) { (void)input; r
 void b200_laikago_forward_zero(int num_total_threads, int num_blocks, int num_threads_per_block, double* output) {
   if (num_total_threads > g_v2_sent) { fprintf(stderr, "b200_laikago_forward_zero: launch before send_local\n"); exit(1); }
   cuda_model_laikago_forward_zero(num_total_threads, num_blocks, num_threads_per_block, output, g_v2_local.data());
+}
+
+// <model>_jacobian of the v2 generation (CudaModelSourceGen::jacobian_source, src/utils/cuda/cuda_codegen.hpp:303-426;
+// loaded by tds::CudaModel as the function named "<model>_jacobian", src/utils/cuda/cuda_model.hpp:14-25): dense rows
+// (output_i, input_i) in row-major order per thread.  Output sparsity (set_jac_output_sparsity, :283-288): the 36 state
+// rows q' | qd' of the 411 outputs; all 51 local inputs (q | qd | action | kp, kd, max_force) as columns; no accumulation.
+static V1Instance g_v2_jac;
+static std::vector<double> g_v2_jac_local;
+static int g_v2_jac_sent = 0;
+static const int k_jac_rows = 36, k_jac_cols = 51;
+
+CudaFunctionMetaDataV2 b200_laikago_jacobian_meta(void) {
+  CudaFunctionMetaDataV2 d;
+  d.output_dim = k_jac_rows * k_jac_cols; d.local_input_dim = k_laikago_in; d.global_input_dim = 0; d.accumulated_output = false;
+  return d;
+}
+void b200_laikago_jacobian_allocate(int num_total_threads) {
+  v1_allocate(g_v2_jac, k_v1_laikago, num_total_threads);
+  g_v2_jac_local.assign((size_t)num_total_threads * k_laikago_in, 0.0);
+  g_v2_jac_sent = 0;
+}
+void b200_laikago_jacobian_deallocate(void) {
+  { std::lock_guard<std::mutex> lk(g_v2_jac.mu); v1_release(g_v2_jac); }
+  g_v2_jac_local.clear(); g_v2_jac_local.shrink_to_fit();
+  g_v2_jac_sent = 0;
+}
+bool b200_laikago_jacobian_send_local(int num_total_threads, const double* input) {
+  if (!input || (size_t)num_total_threads * k_laikago_in > g_v2_jac_local.size()) {
+    fprintf(stderr, "Error while sending thread-local input data to GPU: %d threads exceed the allocation.\n", num_total_threads);
+    return false;
+  }
+  memcpy(g_v2_jac_local.data(), input, sizeof(double) * (size_t)num_total_threads * k_laikago_in);
+  g_v2_jac_sent = num_total_threads;
+  return true;
+}
+bool b200_laikago_jacobian_send_global(const double* input) { (void)input; return true; }
+void b200_laikago_jacobian(int num_total_threads, int num_blocks, int num_threads_per_block, double* output) {
+  (void)num_blocks; (void)num_threads_per_block;
+  std::lock_guard<std::mutex> lk(g_v2_jac.mu);
+  if (!g_v2_jac.sim || num_total_threads > g_v2_jac_sent) { fprintf(stderr, "b200_laikago_jacobian: launch before allocate / send_local\n"); exit(1); }
+  tds_b200_sim* s = g_v2_jac.sim;
+  const int n = num_total_threads;
+  std::vector<double> q((size_t)n * 18), qd((size_t)n * 18), act((size_t)n * 12);
+  for (int e = 0; e < n; ++e) {
+    const double* x = g_v2_jac_local.data() + (size_t)e * k_laikago_in;
+    memcpy(&q[(size_t)e * 18], x, 18 * sizeof(double)); memcpy(&qd[(size_t)e * 18], x + 18, 18 * sizeof(double));
+    memcpy(&act[(size_t)e * 12], x + 36, 12 * sizeof(double));
+  }
+  s->E.kp = (float)g_v2_jac_local[48]; s->E.kd = (float)g_v2_jac_local[49]; s->E.max_force = (float)g_v2_jac_local[50];
+  const int saved_n = s->n;
+  s->n = n;
+  const int rc = tds_b200_step_jacobian_host(s, TDS_B200_MODE_FULL, 1, q.data(), qd.data(), act.data(), output);
+  s->n = saved_n;
+  if (rc) { fprintf(stderr, "b200_laikago_jacobian: %s\n", g_err.c_str()); exit(1); }
 }
 
 }  // extern "C"

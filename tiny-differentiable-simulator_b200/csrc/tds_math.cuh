@@ -249,6 +249,13 @@ TDS_D void sincos_t(double a, double* s, double* c) {
   *s = (q & 2) ? -ss : ss;
   *c = ((q + 1) & 2) ? -cc : cc;
 }
+// value / derivative accessors that also accept the forward-mode dual numbers of tds_dual.cuh
+TDS_D double val_of(float a) { return (double)a; }
+TDS_D double val_of(double a) { return a; }
+TDS_D float min_t(float a, float b) { return fminf(a, b); }
+TDS_D float max_t(float a, float b) { return fmaxf(a, b); }
+TDS_D double min_t(double a, double b) { return fmin(a, b); }
+TDS_D double max_t(double a, double b) { return fmax(a, b); }
 TDS_D float pow_t(float a, float b) { return powf(a, b); }
 TDS_D double pow_t(double a, double b) { return pow(a, b); }
 TDS_D float tanh_t(float a) { return tanhf(a); }

@@ -221,17 +221,17 @@ TDS_HOST_INLINE void tds_build_layout(DevModel* D, int size_ra, int size_rc, int
 }
 
 // Scratch layout of the world-frame kernel (tds_stepw.cu).
-TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, int size_rs, int max_contacts) {
-  const int ra = size_ra / 4, rc = size_rc / 4, rs = size_rs / 4;
+TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, int size_rs, int max_contacts, int size_rq = 4) {
+  const int ra = size_ra / 4, rc = size_rc / 4, rs = size_rs / 4, rq = size_rq / 4;   // rq: words of a state scalar (q, qd, tau)
   const int n = D->n_qd;
   if (max_contacts >= 0 && max_contacts < D->max_contacts) D->max_contacts = max_contacts;
   D->nb = (n + 2) / 3;
   const int n3 = 3 * D->nb;
   int w = 0;
   auto even = [](int x) { return (x + 1) & ~1; };
-  D->x_q = w; w += D->n_q;
-  D->x_qd = w; w += n;
-  D->x_tau = w; w += n;
+  D->x_q = w; w += D->n_q * rq;
+  D->x_qd = w; w += n * rq;
+  D->x_tau = w; w += n * rq;
   w = even(w);
   D->x_S = w; w += D->n_links * 6 * rc;                     // motion subspace in the common frame
   w = even(w);

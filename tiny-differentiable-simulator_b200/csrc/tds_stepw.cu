@@ -33,7 +33,9 @@ namespace tdsw {
 
 // per-link region, element offsets: [rigid inertia (10 RC) | later U (6 RA), invD, u] then v / c / a (6 RA)
 
-template <typename RA, typename RC, typename RS, bool SMEM>
+// RQ: scalar of the state vectors (q, qd, tau): float, or the dual number type in the differentiable instance
+// (RA = RC = RS = RQ = Dual<double>: blockIdx.y + io.jac_dir0 is the input direction of the lane, see tds_dual.cuh).
+template <typename RA, typename RC, typename RS, typename RQ, bool SMEM>
 __global__ void __launch_bounds__(128, 1)
 tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ SimParams P,
                  const __grid_constant__ EnvParams E, const StepIO io, const int mode, const int use_pd,
@@ -44,9 +46,12 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = env < io.n;
   const int e = live ? env : io.n - 1;
+  constexpr bool AD = is_dual<RQ>::value;
+  const int dir = AD ? (int)blockIdx.y + io.jac_dir0 : -1;     // differentiable instance: this lane's input direction
   Arena A;
   if (SMEM) { A.blk = smem_raw + (size_t)warp_in_blk * M.x_total * 32 * 4; A.stride = 32; A.col = lane; }
-  else { A.blk = gscratch + (size_t)(env >> 5) * M.x_total * 32 * 4; A.stride = 32; A.col = lane; }  // per-warp block, same addressing as shared memory
+  else { A.blk = gscratch + ((size_t)blockIdx.y * ((size_t)gridDim.x * (blockDim.x >> 5)) + (size_t)(env >> 5)) * M.x_total * 32 * 4; A.stride = 32; A.col = lane; }  // per-warp block, same addressing as shared memory
+  auto seed = [&](RQ x, int idx) -> RQ { if constexpr (AD) { if (idx == dir) x.d = 1.0; } return x; };   // d input_idx / d direction
   const int ST = A.stride;
   const int ns = io.n_stride;
   const int n_links = M.n_links;
@@ -57,9 +62,9 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
 #define TDSW_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[(size_t)(env >> 5) * 16 + (phase_id++)] = clock64(); } while (0)
   TDSW_PHASE();
   constexpr int RAW = (int)(sizeof(RA) / 4), RCW = (int)(sizeof(RC) / 4);
-  float* const qv = A.ptr<float>(M.x_q);
-  float* const qdv = A.ptr<float>(M.x_qd);
-  float* const tauv = A.ptr<float>(M.x_tau);
+  RQ* const qv = A.ptr<RQ>(M.x_q);
+  RQ* const qdv = A.ptr<RQ>(M.x_qd);
+  RQ* const tauv = A.ptr<RQ>(M.x_tau);
   RC* const Sw = A.ptr<RC>(M.x_S);                 // S of link i at Sw + i*6*ST
   const int LWD = M.x_link_words;
   const int VOFF = LWD - 6 * RAW;                  // word offset of v/c/a inside a link record
@@ -68,22 +73,25 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   RS* const wv = A.ptr<RS>(M.x_w);
 
   // ---- load state, PD torques (locomotion_contact_simulation.h:168-258) ---------------------------
-  for (int k = 0; k < M.n_q; ++k) qv[k * ST] = io.q_in[(size_t)k * ns + e];
-  for (int k = 0; k < n; ++k) qdv[k * ST] = io.qd_in[(size_t)k * ns + e];
-  for (int k = 0; k < n; ++k) tauv[k * ST] = 0.f;
+  // input directions of the differentiable instance: q | qd | tau or action | kp, kd, max_force (with PD)
+  const int in0 = M.n_q + n;
+  for (int k = 0; k < M.n_q; ++k) qv[k * ST] = seed(RQ(io.q_in[(size_t)k * ns + e]), k);
+  for (int k = 0; k < n; ++k) qdv[k * ST] = seed(RQ(io.qd_in[(size_t)k * ns + e]), M.n_q + k);
+  for (int k = 0; k < n; ++k) tauv[k * ST] = RQ(0.f);
   if (use_pd) {
+    const RQ kp = seed(RQ(E.kp), in0 + E.n_act), kd = seed(RQ(E.kd), in0 + E.n_act + 1), fmax_ = seed(RQ(E.max_force), in0 + E.n_act + 2);
     for (int k = 0; k < E.n_act; ++k) {
       const int li = E.act_link[k];
-      float a = io.tau_in[(size_t)k * ns + e];
-      a = fmaxf(fminf(a, E.action_limit), -E.action_limit);
-      const float q_des = E.initial_poses[k] + a;
-      float f = E.kp * (q_des - qv[M.q_idx[li] * ST]) + E.kd * (0.f - qdv[M.qd_idx[li] * ST]);
-      f = fminf(fmaxf(f, -E.max_force), E.max_force);
+      RQ a = seed(RQ(io.tau_in[(size_t)k * ns + e]), in0 + k);
+      a = max_t(min_t(a, RQ(E.action_limit)), RQ(-E.action_limit));
+      const RQ q_des = RQ(E.initial_poses[k]) + a;
+      RQ f = kp * (q_des - qv[M.q_idx[li] * ST]) + kd * (RQ(0.f) - qdv[M.qd_idx[li] * ST]);
+      f = min_t(max_t(f, -fmax_), fmax_);
       tauv[M.qd_idx[li] * ST] = f;
     }
   } else if (io.tau_in) {
     const int off = M.floating ? 6 : 0;
-    for (int k = off; k < n; ++k) tauv[k * ST] = io.tau_in[(size_t)(k - off) * ns + e];
+    for (int k = off; k < n; ++k) tauv[k * ST] = seed(RQ(io.tau_in[(size_t)(k - off) * ns + e]), in0 + k - off);
   }
   for (int s = 0; s < M.n_acc; ++s) {
     RA* pa = A.ptr<RA>(M.x_acc + s * M.x_acc_words);
@@ -126,7 +134,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   int n_active = 0, pt_index = 0;
   auto emit_point = [&](int li, const V3<RC>& pos, const RC rad) {
     const RC dist = dot(pos, pn) + plane_off - rad;       // contact_plane_sphere, contact_point.hpp:112-116
-    if (io.contact_dist && live) io.contact_dist[(size_t)pt_index * ns + e] = (float)dist;
+    if (io.contact_dist && live) io.contact_dist[(size_t)pt_index * ns + e] = (float)val_of(dist);
     ++pt_index;
     if (dist < RC(0) && n_active < M.max_contacts) {
       RC* pc = A.ptr<RC>(M.x_con + n_active * 5 * RCW);
@@ -252,10 +260,10 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     if (want_contacts) emit_geoms(i, Ri, pi);
     if (io.link_xf && live) {
       float* o = io.link_xf + (size_t)i * 12 * ns + e;
-      o[0] = (float)Ri.xx; o[(size_t)1 * ns] = (float)Ri.xy; o[(size_t)2 * ns] = (float)Ri.xz;
-      o[(size_t)3 * ns] = (float)Ri.yx; o[(size_t)4 * ns] = (float)Ri.yy; o[(size_t)5 * ns] = (float)Ri.yz;
-      o[(size_t)6 * ns] = (float)Ri.zx; o[(size_t)7 * ns] = (float)Ri.zy; o[(size_t)8 * ns] = (float)Ri.zz;
-      o[(size_t)9 * ns] = (float)(pi.x + O.x); o[(size_t)10 * ns] = (float)(pi.y + O.y); o[(size_t)11 * ns] = (float)(pi.z + O.z);
+      o[0] = (float)val_of(Ri.xx); o[(size_t)1 * ns] = (float)val_of(Ri.xy); o[(size_t)2 * ns] = (float)val_of(Ri.xz);
+      o[(size_t)3 * ns] = (float)val_of(Ri.yx); o[(size_t)4 * ns] = (float)val_of(Ri.yy); o[(size_t)5 * ns] = (float)val_of(Ri.yz);
+      o[(size_t)6 * ns] = (float)val_of(Ri.zx); o[(size_t)7 * ns] = (float)val_of(Ri.zy); o[(size_t)8 * ns] = (float)val_of(Ri.zz);
+      o[(size_t)9 * ns] = (float)val_of(pi.x + O.x); o[(size_t)10 * ns] = (float)val_of(pi.y + O.y); o[(size_t)11 * ns] = (float)val_of(pi.z + O.z);
     }
     R_prev = Ri; p_prev = pi; v_prev = v;
   }
@@ -468,8 +476,10 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       a.top = axpy(S.top, qdd, a.top);
       a.bot = axpy(S.bot, qdd, a.bot);
       const int qdi = M.qd_idx[i];
-      if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)qdi * ns + e] = (float)qdd; }
-      else if (!world_step) qdv[qdi * ST] = (float)(RA(qdv[qdi * ST]) + qdd * dtA);
+      if (mode == MODE_FD) {
+        if constexpr (AD) { if (live && io.jac) io.jac[((size_t)qdi * io.jac_n_in + dir) * ns + e] = qdd.d; }
+        else if (live && io.qdd_out) io.qdd_out[(size_t)qdi * ns + e] = (float)val_of(qdd);
+      } else if (!world_step) qdv[qdi * ST] = RQ(RA(qdv[qdi * ST]) + qdd * dtA);
     }
     st6<RA>(vrec, ST, a);
     a_prev = a;
@@ -479,8 +489,10 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
                       base_acc_b.bot.y + RC(P.gravity[1]), base_acc_b.bot.z + RC(P.gravity[2])};
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      if (mode == MODE_FD) { if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)qb[k]; }
-      else if (!world_step) qdv[k * ST] = (float)(RC(qdv[k * ST]) + qb[k] * RC(P.dt));
+      if (mode == MODE_FD) {
+        if constexpr (AD) { if (live && io.jac) io.jac[((size_t)k * io.jac_n_in + dir) * ns + e] = qb[k].d; }
+        else if (live && io.qdd_out) io.qdd_out[(size_t)k * ns + e] = (float)val_of(qb[k]);
+      } else if (!world_step) qdv[k * ST] = RQ(RC(qdv[k * ST]) + qb[k] * RC(P.dt));
     }
   }
   TDSW_PHASE();  // 4
@@ -511,7 +523,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
         RS* const Y = A.ptr<RS>(M.x_Y) + c * n3 * 3 * ST;       // [dof k][rhs] : element (3k + rhs)
         const V3<RC> xc = ld3<RC>(pc, ST);
         const RC dist = pc[3 * ST];
-        const int L = (int)pc[4 * ST];
+        const int L = (int)val_of(pc[4 * ST]);
         for (int k = 0; k < 3 * n3; ++k) Y[k * ST] = RS(0);
         V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));                  // vel_b = J qd
         if (M.floating) {  // jacobian.hpp:39-58 with r = x_c (O is the base origin)
@@ -627,7 +639,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       wv[(3 * bi) * ST] = z0; wv[(3 * bi + 1) * ST] = z1; wv[(3 * bi + 2) * ST] = z2;
     }
     if (n_active > 0)
-      for (int k = 0; k < n; ++k) qdv[k * ST] = (float)(RS(qdv[k * ST]) - wv[k * ST]);
+      for (int k = 0; k < n; ++k) qdv[k * ST] = RQ(RS(qdv[k * ST]) - wv[k * ST]);
   }
   TDSW_PHASE();  // 8
 
@@ -644,40 +656,47 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     qx += dx; qy += dy; qz += dz; qw += dw;
     const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
     qx /= len; qy /= len; qz /= len; qw /= len;
-    qv[0] = (float)qx; qv[ST] = (float)qy; qv[2 * ST] = (float)qz; qv[3 * ST] = (float)qw;
+    qv[0] = RQ(qx); qv[ST] = RQ(qy); qv[2 * ST] = RQ(qz); qv[3 * ST] = RQ(qw);
     for (int k = 0; k < 3; ++k)
-      qv[(4 + k) * ST] = (float)(RC(qv[(4 + k) * ST]) + RC(qdv[(3 + k) * ST]) * RC(P.dt));
+      qv[(4 + k) * ST] = RQ(RC(qv[(4 + k) * ST]) + RC(qdv[(3 + k) * ST]) * RC(P.dt));
     up_z = RC(1) - RC(2) * (qx * qx + qy * qy) / (qx * qx + qy * qy + qz * qz + qw * qw);
   }
   for (int i = 0; i < n_links && !world_step; ++i) {
     if (M.flags[i] & TDS_LF_FIXED) continue;
     const int qi = M.q_idx[i];
-    qv[qi * ST] = (float)(RC(qv[qi * ST]) + RC(qdv[M.qd_idx[i] * ST]) * RC(P.dt));
+    qv[qi * ST] = RQ(RC(qv[qi * ST]) + RC(qdv[M.qd_idx[i] * ST]) * RC(P.dt));
   }
 
   // ---- reward / done / auto-reset, write back ------------------------------------------------------------------------
+  if constexpr (AD) {   // the Jacobian column of this lane's direction: rows q' | qd'
+    if (live && io.jac) {
+      for (int k = 0; k < M.n_q; ++k) io.jac[((size_t)k * io.jac_n_in + dir) * ns + e] = qv[k * ST].d;
+      for (int k = 0; k < n; ++k) io.jac[((size_t)(M.n_q + k) * io.jac_n_in + dir) * ns + e] = qdv[k * ST].d;
+    }
+    return;
+  }
   if (live) {
     bool done = false;
     if (E.reward_kind == 1) {   // laikago_environment2.h:130-171 (fixed-base emulation)
-      const float x = qv[0], z = qv[2 * ST];
-      const float upz = cosf(qv[3 * ST]) * cosf(qv[4 * ST]);
+      const float x = (float)val_of(qv[0]), z = (float)val_of(qv[2 * ST]);
+      const float upz = cosf((float)val_of(qv[3 * ST])) * cosf((float)val_of(qv[4 * ST]));
       done = (upz < 0.6f) || (z < 0.2f);
       if (io.reward) io.reward[e] = done ? 0.f : x;
     } else if (E.reward_kind == 2) {
-      const float x = qv[4 * ST], z = qv[6 * ST];
-      done = ((float)up_z < 0.6f) || (z < 0.2f);
+      const float x = (float)val_of(qv[4 * ST]), z = (float)val_of(qv[6 * ST]);
+      done = ((float)val_of(up_z) < 0.6f) || (z < 0.2f);
       if (io.reward) io.reward[e] = done ? 0.f : x;
     } else if (E.reward_kind == 3) {   // ant_environment2.h:75-105: done = z < 0.26, reward = (x' - x)/dt, which integrate_euler makes the x velocity
-      done = qv[2 * ST] < 0.26f;
-      if (io.reward) io.reward[e] = done ? 0.f : qdv[0];
+      done = (float)val_of(qv[2 * ST]) < 0.26f;
+      if (io.reward) io.reward[e] = done ? 0.f : (float)val_of(qdv[0]);
     }
     if (io.done && E.reward_kind) io.done[e] = done ? 1.f : 0.f;
     if (done && E.auto_reset) {   // ars_vectorized_environment.h:262-283
       for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = E.reset_q[k];
       for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = 0.f;
     } else {
-      for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = qv[k * ST];
-      for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = qdv[k * ST];
+      for (int k = 0; k < M.n_q; ++k) io.q_out[(size_t)k * ns + e] = (float)val_of(qv[k * ST]);
+      for (int k = 0; k < n; ++k) io.qd_out[(size_t)k * ns + e] = (float)val_of(qdv[k * ST]);
     }
   }
   TDSW_PHASE();  // 9
@@ -695,7 +714,7 @@ extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const Env
   cudaError_t err = cudaSuccess;
 #define TDSW_LAUNCH(RA, RC, RS, SM)                                                                     \
   do {                                                                                                  \
-    auto k = tds_stepw_kernel<RA, RC, RS, SM>;                                                          \
+    auto k = tds_stepw_kernel<RA, RC, RS, float, SM>;                                                   \
     static size_t smem_set_dev[64] = {0}; int dev_ = 0; cudaGetDevice(&dev_); size_t& smem_set = smem_set_dev[dev_ & 63]; \
     if (smem > 48 * 1024 && smem > smem_set) {                                                          \
       err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
@@ -711,4 +730,16 @@ extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const Env
   else { if (use_smem) TDSW_LAUNCH(float, float, float, true); else TDSW_LAUNCH(float, float, float, false); }
 #undef TDSW_LAUNCH
   return (int)err;
+}
+
+// Differentiable step: the same kernel on forward-mode dual numbers (fp64), one lane per (environment, input direction).
+// M must carry the 16-byte layout (tds_build_layout_w(..., 16, 16, 16, -1, 16)); gscratch: n_dirs * ceil(n / 32) blocks of
+// x_total * 128 bytes; directions [io->jac_dir0, io->jac_dir0 + n_dirs) are computed by this launch.
+extern "C" int tds_launch_stepw_jacobian(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io, int mode,
+                                         int use_pd, int n_dirs, char* gscratch, cudaStream_t stream) {
+  using namespace tdsw;
+  typedef tds::Dual<double> D;
+  const dim3 grid((io->n + 31) / 32, n_dirs);
+  tds_stepw_kernel<D, D, D, D, false><<<grid, 32, 0, stream>>>(*M, *P, *E, *io, mode, use_pd, gscratch);
+  return (int)cudaGetLastError();
 }

@@ -114,5 +114,8 @@ struct StepIO {
   const float* act_aos;                 // actions [n][n_act] (environment-major), or null -> tau_in
   float* obs_aos;                       // observations [n][n_q + n_qd] = q | qd after the step, or null
   float* obs_tail;                      // reward [n] then done [n] behind the observations, or null
+  // differentiable step (tds_stepw.cu instantiated on dual numbers): Jacobian [n_rows * jac_n_in][n_stride], fp64;
+  // rows = q' | qd' (or qdd in forward-dynamics mode), columns = q | qd | tau or action (| kp, kd, max_force with PD)
+  double* jac; int jac_n_in; int jac_dir0;
   int n; int n_stride;
 };

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "tds_math.cuh"
+#include "tds_dual.cuh"
 #include "tds_types.h"
 #include "tds_b200_model.h"
 
@@ -17,6 +18,7 @@ struct Arena {
   int col;
   template <typename T> TDS_D T* ptr(int word) const {
     if (sizeof(T) == 4) return ((T*)blk) + (size_t)word * stride + col;
+    if (sizeof(T) == 16) return ((T*)blk) + (size_t)(word >> 2) * stride + col;   // dual numbers (tds_dual.cuh)
     return ((T*)blk) + (size_t)(word >> 1) * stride + col;
   }
 };

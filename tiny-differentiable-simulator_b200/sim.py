@@ -140,6 +140,18 @@ class BatchSim:
             out["contact_links"] = links[:, :self.n_contact_points]
         return out
 
+    def step_jacobian_host(self, mode, q, qd, tau_or_action=None, use_pd=False):
+        """Dense Jacobian of one step per environment (forward-mode dual numbers on the GPU): [n, rows, cols] float64,
+        rows = q' | qd' (qdd for MODE_FD), cols = q | qd | tau, or q | qd | action | kp, kd, max_force with use_pd."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qd = np.ascontiguousarray(qd, dtype=np.float64)
+        t = None if tau_or_action is None else np.ascontiguousarray(tau_or_action, dtype=np.float64)
+        dims = (ctypes.c_int * 2)()
+        self._check(self._L.tds_b200_jacobian_dims(self._h, mode, int(use_pd), dims), "jacobian_dims")
+        jac = np.zeros((self.n_envs, dims[0], dims[1]))
+        self._check(self._L.tds_b200_step_jacobian_host(self._h, mode, int(use_pd), _dp(q), _dp(qd), _dp(t), _dp(jac)), "step_jacobian_host")
+        return jac
+
     def integrate_host(self, q, qd, qdd, update_q=True):
         """integrate_euler (update_q) / integrate_euler_qdd of one state vector per environment, on the device
         (tds_b200_integrate_euler{,_qdd}_device); host arrays [n_q], [n_qd] for a one-environment simulator or [n, dim]."""
