@@ -316,8 +316,8 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   const LegTab<SP>& LG = leg_tab<SP>(role);
   char* const priv = smem + (size_t)(L::SHARED + role * L::PRIV) * ST * 4;
   int phase_id = 0;
-#define TDSS_PHASE() do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)tile * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
-#define TDSS_STAMP(slot) do { if (io.phase_clk && lane == 0) io.phase_clk[((size_t)tile * TT + role) * 16 + (slot)] = clock64(); } while (0)
+#define TDSS_PHASE() do { if (io.phase_clk && lane == 0 && tile * 32 < io.n_stride) io.phase_clk[((size_t)tile * TT + role) * 16 + phase_id] = clock64(); ++phase_id; } while (0)
+#define TDSS_STAMP(slot) do { if (io.phase_clk && lane == 0 && tile * 32 < io.n_stride) io.phase_clk[((size_t)tile * TT + role) * 16 + (slot)] = clock64(); } while (0)
   TDSS_PHASE();
   auto xw_rc = [&](int slot) { return sp<RC>(smem, lane, L::XW + slot * L::XWW); };                  // R[9], p[3]
   auto xw_ra = [&](int slot) { return sp<RA>(smem, lane, L::XW + slot * L::XWW + 12 * RCW); };       // v[6], a[6]
