@@ -158,6 +158,7 @@ int tds_b200_step_host(tds_b200_sim* sim, int mode, int use_pd, const double* q,
  *   device: contact_dist [n_points][ns] (output of tds_b200_step_device), count [ns], links [2 * n_points][ns]
  *   host:   uses the distances of the last tds_b200_step_host(..., contact_dist != NULL); count [n], links [n][n_points][2] */
 int tds_b200_contact_pairs(const tds_b200_sim* sim, int* tuples, int cap);
+int tds_b200_model_contact_pairs(const double* model, int n_model, int* tuples, int cap);   /* host-only, from a flat model */
 int tds_b200_contact_list_device(tds_b200_sim* sim, const float* contact_dist, int* count, int* links, void* stream);
 int tds_b200_contact_list_host(tds_b200_sim* sim, int* count, int* links);
 

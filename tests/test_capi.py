@@ -94,3 +94,22 @@ def test_unsupported_models_are_refused_loudly():
     rc, msg = check(m)
     assert rc == -3 and "spherical" in msg
     assert check(m[:10])[0] == -1
+
+
+def test_contact_pair_lists_match_reference_goldens():
+    """Host-only: the candidate contact-pair list of every fixture model (enumeration order of
+    World::compute_contacts_multi_body_internal, src/world.hpp:212-281) equals, bit for bit, the (link_a, link_b) list the
+    reference itself produced for the golden vectors.  (The per-step lists come from the device: tests/test_parity_gpu.py.)"""
+    import numpy as np
+    L = tds_b200.lib()
+    golden = os.path.join(ROOT, "tests", "golden")
+    for name in ("sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "cartpole", "pendulum5"):
+        m = np.ascontiguousarray(load_model(fixture_path(name)), dtype=np.float64)
+        t = np.zeros((64, 4), dtype=np.int32)
+        k = L.tds_b200_model_contact_pairs(m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(m.size), ctypes.c_void_p(t.ctypes.data), 64)
+        g = np.load(os.path.join(golden, name + ".npz"))
+        la, lb = np.stack(list(g["contact_link_a"])), np.stack(list(g["contact_link_b"]))
+        assert k == la.shape[1] == int(g["n_contacts"][0]), name
+        for e in range(la.shape[0]):
+            assert np.array_equal(t[:k, 1], la[e]) and np.array_equal(t[:k, 3], lb[e]), name
+        assert np.all(t[:k, 0] == 0) and np.all(t[:k, 2] == 1)

@@ -878,6 +878,24 @@ int tds_b200_integrate_euler_qdd_device(tds_b200_sim* s, float* qd, const float*
   return 0;
 }
 
+// Host-only variant (no GPU needed): the candidate list of a flat model.
+int tds_b200_model_contact_pairs(const double* model, int n_model, int* tuples, int cap) {
+  if (!model) { set_err("null model"); return -1; }
+  DevModel* D = new DevModel;
+  const int rc = tds_build_dev_model(model, n_model, D);
+  int c = 0;
+  if (rc == 0 && D->has_plane) {
+    for (int g = 0; g < D->n_geoms; ++g) {
+      const int pts = D->g_type[g] == TDSG_SPHERE ? 1 : (D->g_type[g] == TDSG_CAPSULE ? 2 : (D->g_type[g] == TDSG_BOX ? 8 : 0));
+      for (int j = 0; j < pts; ++j, ++c)
+        if (tuples && c < cap) { tuples[4 * c] = 0; tuples[4 * c + 1] = -1; tuples[4 * c + 2] = 1; tuples[4 * c + 3] = D->g_link[g]; }
+    }
+  }
+  delete D;
+  if (rc) { set_err(std::string("unsupported model: ") + tds_model_error(rc)); return rc; }
+  return c;
+}
+
 int tds_b200_contact_pairs(const tds_b200_sim* s, int* tuples, int cap) {
   if (!s) return -1;
   for (int c = 0; c < s->cand.n_points && c < cap && tuples; ++c) {
