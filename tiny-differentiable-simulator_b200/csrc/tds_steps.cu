@@ -1702,8 +1702,10 @@ template <class SP> struct SpecHost {
     // throughput mode: more tiles than two waves of single-tile CTAs and two tiles fit one CTA's shared memory
     static const int tpc_env = getenv("TDS_B200_TPC") ? atoi(getenv("TDS_B200_TPC")) : 0;
     static const bool pdl = getenv("TDS_B200_PDL") ? atoi(getenv("TDS_B200_PDL")) != 0 : false;
-    int tpc = (tiles > 2 * sm_count[dev_ & 63] && 2 * smem1 <= 227 * 1024) ? 2 : 1;
-    if (tpc_env == 1 || tpc_env == 2) tpc = (tpc_env == 2 && 2 * smem1 <= 227 * 1024) ? 2 : 1;
+    // (opt-in until measured on the target: TDS_B200_TPC=2; TDS_B200_TPC=-1 = automatic for batches of more than two waves)
+    int tpc = 1;
+    if (tpc_env == -1) tpc = (tiles > 2 * sm_count[dev_ & 63] && 2 * smem1 <= 227 * 1024) ? 2 : 1;
+    if (tpc_env == 2) tpc = 2 * smem1 <= 227 * 1024 ? 2 : 1;
 #define TDSS_LAUNCH(RA, RC, RS, VAR, TPC)                                                               \
   do {                                                                                                  \
     auto k = tds_step_spec_kernel<SP, RA, RC, RS, VAR, TPC>;                                            \
