@@ -613,13 +613,15 @@ def main():
     kernel_s = (total_ms * 1e-3) / K
     achieved = ALGO_BYTES_PER_ENV_STEP * n / kernel_s / 1e9
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_step_kernel_ncu.json")
-    if os.path.exists(prof):
-        try:
-            with open(prof) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    for prof in ("r02_step_kernel_ncu.json", "r01_step_kernel_ncu.json"):   # one `ncu --set full` capture of the step kernel
+        prof = os.path.join(ROOT, "profiles", prof)
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+                break
+            except Exception:
+                pass
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
