@@ -6,6 +6,6 @@ for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun --timeout "$T" -- "$@" > "$LOG" 2>&1
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
-  sleep 45
+  sleep 8
 done
 exit 3

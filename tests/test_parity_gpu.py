@@ -199,8 +199,10 @@ def test_full_size_properties():
     act[:, :n] = torch.tensor(w["action"].T, dtype=torch.float32)
     sim.step_device(2, q, qd, act, use_pd=True)
     torch.cuda.synchronize()
-    assert np.array_equal(q[:, :n].T.cpu().numpy().astype(np.float64), a["q"])
-    assert np.array_equal(qd[:, :n].T.cpu().numpy().astype(np.float64), a["qd"])
+    # (the host path asks for the extra outputs and runs the kernel's general instance, the device path its lean one:
+    # two compilations of the same arithmetic, equal up to the last bits of fp32)
+    assert np.allclose(q[:, :n].T.cpu().numpy().astype(np.float64), a["q"], rtol=2e-6, atol=1e-9)
+    assert np.allclose(qd[:, :n].T.cpu().numpy().astype(np.float64), a["qd"], rtol=2e-6, atol=2e-6)
 
 
 def test_device_auto_reset():
@@ -599,7 +601,7 @@ def test_v2_abi_library_loader_sequence(golden_dir):
     meta_fn = getattr(L, f + "_meta"); meta_fn.restype = MetaV2
     meta = meta_fn()
     assert (meta.output_dim, meta.local_input_dim, meta.global_input_dim, meta.accumulated_output) == (411, 51, 0, False)
-    assert not hasattr(L, names[0].decode() + "_jacobian")       # CudaFunction reports it unavailable
+    assert hasattr(L, names[0].decode() + "_jacobian")           # CudaModel finds <model>_jacobian (tested below)
     g = np.load(os.path.join(golden_dir, "laikago.npz"))
     x = np.ascontiguousarray(g["env_input"])
     n = x.shape[0]

@@ -260,6 +260,19 @@ TDS_D float pow_t(float a, float b) { return powf(a, b); }
 TDS_D double pow_t(double a, double b) { return pow(a, b); }
 TDS_D float tanh_t(float a) { return tanhf(a); }
 TDS_D double tanh_t(double a) { return tanh(a); }
+// reciprocal / reciprocal square root of the fp32 solver quantities (1 / D of ABA, inverted Cholesky diagonals, 1 / A_ii):
+// IEEE division and sqrt + division cost ~8-10 instructions each with a slow-path call; with TDS_B200_APPROX_RCP the
+// single-instruction MUFU approximations (<= 1 ulp / 2 ulp) are used instead - an A/B build option, parity-checked like
+// the default build.  fp64 keeps the exact forms.
+#ifdef TDS_B200_APPROX_RCP
+TDS_D float inv_t(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+TDS_D float rsqrt_t(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+#else
+TDS_D float inv_t(float a) { return 1.0f / a; }
+TDS_D float rsqrt_t(float a) { return 1.0f / sqrtf(a); }
+#endif
+TDS_D double inv_t(double a) { return 1.0 / a; }
+TDS_D double rsqrt_t(double a) { return 1.0 / sqrt(a); }
 TDS_D float sqrt_t(float a) { return sqrtf(a); }
 TDS_D double sqrt_t(double a) { return sqrt(a); }
 

@@ -775,7 +775,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
       const Sv<RA> c = cross_mm(v, vJ);                      // kinematics.hpp:96-97
       const Sv<RA> U = abi_mul(Ia, S);                       // forward_dynamics.hpp:111
       const RA D = dot(S, U);
-      const RA invD = RA(1) / D;
+      const RA invD = inv_t(D);
       RA tau = RA(tauv[k]);
       if constexpr (TR) {
         if constexpr (SP::L_SD[0][k][0] != 0.0) tau -= RA(CD(SP::L_SD[0][k][0])) * RA(qv[k]);
@@ -958,7 +958,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           const Sv<RA> c = cross_mm(v, vJ);
           const Sv<RA> U = abi_mul(Ia, S);
           const RA D = dot(S, U);
-          const RA invD = RA(1) / D;
+          const RA invD = inv_t(D);
           RA tau = RA(tk_tau[k * ST]);
           tau -= RA(TK.sd[k][0]) * RA(tk_q[k * ST]);
           tau -= RA(TK.sd[k][1]) * qdj;
@@ -1133,7 +1133,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           RA sacc = Dm[tri(i, j)];
           sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sacc -= Dm[tri(i, k)] * Dm[tri(j, k)]; });
           if constexpr (j < i) Dm[tri(i, j)] = sacc * Dm[tri(j, j)];
-          else Dm[tri(i, i)] = RA(1) / sqrt_t(sacc);
+          else Dm[tri(i, i)] = rsqrt_t(sacc);
         });
         RA sy = x[i];
         sfor<0, i>([&](auto Kc) { constexpr int k = decltype(Kc)::value; sy -= Dm[tri(i, k)] * x[k]; });
@@ -1217,7 +1217,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         RS s = Mkk[tri(i, j)];
         sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Mkk[tri(i, k)] * Mkk[tri(j, k)]; });
         if constexpr (j < i) Mkk[tri(i, j)] = s * Mkk[tri(j, j)];
-        else Mkk[tri(i, i)] = RS(1) / sqrt_t(s);
+        else Mkk[tri(i, i)] = rsqrt_t(s);
       });
       sfor<0, NTD>([&](auto Tc) {
         constexpr int t = decltype(Tc)::value;
@@ -1258,7 +1258,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
           RS s = Bm[tri(i, j)];
           sfor<0, j>([&](auto Kc) { constexpr int k = decltype(Kc)::value; s -= Bm[tri(i, k)] * Bm[tri(j, k)]; });
           if constexpr (j < i) Bm[tri(i, j)] = s * Bm[tri(j, j)];
-          else Bm[tri(i, i)] = RS(1) / sqrt_t(s);
+          else Bm[tri(i, i)] = rsqrt_t(s);
           Lt[tri(i, j) * ST] = Bm[tri(i, j)];
         });
       });
@@ -1338,7 +1338,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         });
         // A_ii = y.y + cfm is constant during the sweep: keep y.y and 1 / A_ii per row
         row[(BB + 3 + d) * ST] = yy;
-        row[(BB + 6 + d) * ST] = RS(1) / (yy + RS(P.cfm));
+        row[(BB + 6 + d) * ST] = inv_t(yy + RS(P.cfm));
       }
     };
     // subtree points (every role)
