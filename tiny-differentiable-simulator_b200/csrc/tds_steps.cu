@@ -1641,10 +1641,11 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
 #undef TDSS_STAMP
 }
 
-// TPC tiles per CTA.  1: one tile per CTA, two CTAs may share an SM (latency mode, a batch of at most one wave).
-// 2: two tiles in one CTA of 8 warps, barriers shared: the tiles run the SAME instruction stream in lockstep, so the SM's
-// instruction fetches serve both (scripts/icache_probe.cu: two co-resident CTAs that drift apart are two streams over
-// 100+ KB of code and pay 3.7-4.6 cycles per instruction each; in lockstep 2.4).  Throughput mode, batches of many waves.
+// TPC tiles per CTA.  1 (shipped): one tile per CTA, two CTAs may share an SM.
+// 2 (experiment, -DTDS_B200_WITH_TPC2 + TDS_B200_TPC=2): two tiles in one CTA of 8 warps with shared barriers, so that both
+// run ONE instruction stream (scripts/icache_probe.cu: two streams over 100+ KB of code pay 3.7-4.6 cycles per instruction
+// each, one stream 2.6).  Measured SLOWER (65536 envs: 0.63 vs 0.68 G env-steps/s): in lockstep both tiles sit in their
+// single-warp serial sections at the same time, while independent CTAs drift apart and fill each other's idle slots.
 template <class SP, typename RA, typename RC, typename RS, int VAR, int TPC>
 __global__ void __launch_bounds__(32 * TDS_TEAM_T * TPC, TPC == 1 ? 2 : 1)
 tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant__ EnvParams E, const StepIO io, const int mode_flags,
@@ -1739,8 +1740,12 @@ template <class SP> struct SpecHost {
     else TDSS_LAUNCH(float, float, float, VAR, TPC);                             \
   } while (0)
     if (var == 0) TDSS_PREC(0, 1);
-    else if (var == 1) { if (tpc == 2 && precision != 1) { if (precision == 0) TDSS_LAUNCH(float, double, float, 1, 2); else TDSS_LAUNCH(float, float, float, 1, 2); } else TDSS_PREC(1, 1); }
-    else { if (tpc == 2 && precision != 1) { if (precision == 0) TDSS_LAUNCH(float, double, float, 2, 2); else TDSS_LAUNCH(float, float, float, 2, 2); } else TDSS_PREC(2, 1); }
+#ifdef TDS_B200_WITH_TPC2   // measured slower than independent CTAs (profiles/r02_experiments.md): compiled on request only
+    else if (var == 1 && tpc == 2 && precision != 1) { if (precision == 0) TDSS_LAUNCH(float, double, float, 1, 2); else TDSS_LAUNCH(float, float, float, 1, 2); }
+    else if (var == 2 && tpc == 2 && precision != 1) { if (precision == 0) TDSS_LAUNCH(float, double, float, 2, 2); else TDSS_LAUNCH(float, float, float, 2, 2); }
+#endif
+    else if (var == 1) TDSS_PREC(1, 1);
+    else TDSS_PREC(2, 1);
 #undef TDSS_PREC
 #undef TDSS_LAUNCH
     return (int)err;
