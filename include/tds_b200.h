@@ -209,6 +209,9 @@ int tds_b200_num_visuals(const tds_b200_sim* sim);
 int tds_b200_env_step_visual_device(tds_b200_sim* sim, const float* actions, float* reward, float* done, float* positions,
                                     float* orientations, void* stream);
 
+/* The simulator's own (non-blocking) cudaStream_t: what the host-buffer entry points and the env-layer calls with a NULL
+ * stream run on.  Work enqueued by the caller on other streams is NOT ordered against it. */
+void* tds_b200_stream(tds_b200_sim* sim);
 float* tds_b200_env_q(tds_b200_sim* sim);
 float* tds_b200_env_qd(tds_b200_sim* sim);
 

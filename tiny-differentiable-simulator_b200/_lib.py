@@ -104,6 +104,8 @@ def lib():
     L.tds_b200_env_step_host.argtypes = [vp, fp, fp, fp, fp]
     L.tds_b200_env_step_device.restype = ci
     L.tds_b200_env_step_device.argtypes = [vp, fp, fp, fp, vp]
+    L.tds_b200_stream.restype = vp
+    L.tds_b200_stream.argtypes = [vp]
     L.tds_b200_env_q.restype = vp
     L.tds_b200_env_q.argtypes = [vp]
     L.tds_b200_env_qd.restype = vp
@@ -134,7 +136,7 @@ DECLARED_SYMBOLS = [
     "tds_b200_jacobian_dims", "tds_b200_step_jacobian_device", "tds_b200_step_jacobian_host", "tds_b200_integrate_euler_device", "tds_b200_integrate_euler_qdd_device", "tds_b200_contact_pairs", "tds_b200_model_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host",
     "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
     "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
-    "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",
+    "tds_b200_stream", "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",
     "cuda_model_laikago_forward_zero_meta", "cuda_model_laikago_forward_zero_allocate",
     "cuda_model_laikago_forward_zero_deallocate",
     "cuda_model_ant_forward_zero", "cuda_model_ant_forward_zero_meta", "cuda_model_ant_forward_zero_allocate",

@@ -1153,6 +1153,7 @@ int tds_b200_debug_phase_clocks(tds_b200_sim* s, int enable, long long* out_host
   return nw;
 }
 
+void* tds_b200_stream(tds_b200_sim* s) { return s ? (void*)s->stream : nullptr; }
 float* tds_b200_env_q(tds_b200_sim* s) { return s ? s->q : nullptr; }
 float* tds_b200_env_qd(tds_b200_sim* s) { return s ? s->qd : nullptr; }
 

@@ -261,10 +261,12 @@ TDS_D double pow_t(double a, double b) { return pow(a, b); }
 TDS_D float tanh_t(float a) { return tanhf(a); }
 TDS_D double tanh_t(double a) { return tanh(a); }
 // reciprocal / reciprocal square root of the fp32 solver quantities (1 / D of ABA, inverted Cholesky diagonals, 1 / A_ii):
-// IEEE division and sqrt + division cost ~8-10 instructions each with a slow-path call; with TDS_B200_APPROX_RCP the
-// single-instruction MUFU approximations (<= 1 ulp / 2 ulp) are used instead - an A/B build option, parity-checked like
-// the default build.  fp64 keeps the exact forms.
-#ifdef TDS_B200_APPROX_RCP
+// IEEE division and sqrt + division cost ~8-10 instructions each with a slow-path call; the single-instruction MUFU
+// approximations (<= 1 ulp / 2 ulp, far inside the fp32 round-off the mixed arithmetic already carries) shrink the
+// specialised kernel from 7528 to 6944 instructions - and the kernel is instruction-fetch bound, so 13.5 instead of
+// 14.5 us / step at 4096 environments, 750 instead of 677 M env-steps/s at 65536 (profiles/r02_experiments.md #28).
+// -DTDS_B200_EXACT_RCP restores the IEEE forms.  fp64 always keeps the exact forms.
+#ifndef TDS_B200_EXACT_RCP
 TDS_D float inv_t(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 TDS_D float rsqrt_t(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 #else

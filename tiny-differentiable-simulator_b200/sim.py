@@ -239,20 +239,25 @@ class BatchSim:
         import torch
         dev = w.device
         n_params = int(w.numel())
-        params = torch.empty((n_params, self.n_stride), dtype=torch.float32, device=dev)
-        r = [torch.zeros(self.n_stride, dtype=torch.float32, device=dev) for _ in range(2)]
-        steps = torch.zeros(self.n_stride, dtype=torch.int32, device=dev)
-        st = torch.cuda.current_stream()
-        sp = ctypes.c_void_p(st.cuda_stream)
+        # everything runs on the simulator's own stream (a NULL stream argument of the env-layer calls means exactly that
+        # stream, which is non-blocking: work on torch's default stream would not be ordered against it)
+        torch.cuda.current_stream().synchronize()          # w, deltas, obs_stats were produced on the caller's stream
+        own = torch.cuda.ExternalStream(self._L.tds_b200_stream(self._h), device=dev)
+        sp = ctypes.c_void_p(own.cuda_stream)
+        with torch.cuda.stream(own):
+            params = torch.empty((n_params, self.n_stride), dtype=torch.float32, device=dev)
+            r = [torch.zeros(self.n_stride, dtype=torch.float32, device=dev) for _ in range(2)]
+            steps = torch.zeros(self.n_stride, dtype=torch.int32, device=dev)
         self._check(self._L.tds_b200_env_set_obs_stats(self._h, _ptr(obs_stats)), "env_set_obs_stats")
         for k, sign in enumerate((1.0, -1.0)):
             self._check(self._L.tds_b200_ars_perturb_device(self._h, _ptr(w), _ptr(deltas), sign * delta_std, _ptr(params), n_params, sp),
                         "ars_perturb")
-            self.env_reset_device(seed=seed, settle_steps=settle_steps, stream=st)
-            self.env_rollout_device(params, rollout_length, shift, r[k], steps, stream=st)
+            self.env_reset_device(seed=seed, settle_steps=settle_steps, stream=own)
+            self.env_rollout_device(params, rollout_length, shift, r[k], steps, stream=own)
         self._check(self._L.tds_b200_ars_update_device(self._h, _ptr(w), _ptr(deltas), _ptr(r[0]), _ptr(r[1]), delta_std, step_size,
                                                        n_params, sp), "ars_update")
         self._check(self._L.tds_b200_env_set_obs_stats(self._h, None), "env_set_obs_stats")
+        own.synchronize()
         return r[0], r[1]
 
     def env_rollout_host(self, policy, rollout_length, shift=0.0, noise=None, noise_amp=0.05, seed=0, settle_steps=10):
