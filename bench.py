@@ -555,13 +555,19 @@ def main():
     t_wall0 = time.perf_counter()
     reps = 1
     if graph is not None:
-        reps = max(1, int(args.min_seconds / max(1e-6, K * 60e-6)))  # repeat the K-step graph so clocks can be sampled
+        # The K-step graph is replayed for about min_seconds so that the clocks can be sampled around the timed region
+        # and so that a short run (K = 20 is 0.3 ms) is not timed while the GPU is still ramping up from its idle clocks:
+        # half of the replays run before the timed one (extra warm-up, untimed), half after; exactly ONE replay = exactly K
+        # steps lies between the two events.
+        reps = max(2, int(args.min_seconds / max(1e-6, K * 60e-6)))
+        for _ in range(reps // 2):
+            graph.replay()
         ev0.record()
         graph.replay()
         ev1.record()
-        torch.cuda.synchronize()
-        for _ in range(reps - 1):    # extra replays only feed the clock sampler; the reported time is the first K steps
+        for _ in range(reps - reps // 2 - 1):
             graph.replay()
+        torch.cuda.synchronize()
     else:
         ev0.record()
         for i in range(K):
@@ -632,7 +638,7 @@ def main():
                    "envs_per_gpu": n, "global_envs": n * world, "dt": 1e-3, "parallelism": f"env-sharded x{world}, no data-path collective"
                    + ((" + all-gather(reward,done) in the graph, step kernel writes the send buffer" + (", overlapped with the next step" if args.gather_overlap else "")) if gathered is not None else ""),
                    "state": "SoA fp32 resident in HBM",
-                   "timing": "CUDA events around exactly K steps (" + ("one CUDA-graph replay of K kernel nodes" if graph is not None else "K individual launches") + "), max over ranks",
+                   "timing": "CUDA events around exactly K steps (" + (f"one CUDA-graph replay of K kernel nodes, preceded and followed by untimed replays of the same graph for the clock sampler: {reps} replays in all" if graph is not None else "K individual launches") + "), max over ranks",
                    "l2": (f"inputs larger than L2: ring of {ring} action tensors = {ring * 12 * ns * 4 / 2**20:.0f} MiB, one per step"
                           if ring >= 700 else f"ring of {ring} action tensors (L2-resident)"),
                    "wall_s_timed_region": t_wall},

@@ -550,7 +550,7 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     }
   }
   // defaults = the reference's (world.hpp:65-72, mb_constraint_solver.hpp:59-70)
-  s->P.dt = 1e-3;
+  s->P.dt = 1e-3; s->P.inv_dt = 1.0 / s->P.dt;
   s->P.gravity[0] = 0; s->P.gravity[1] = 0; s->P.gravity[2] = -9.81;
   s->P.friction = 0.5; s->P.restitution = 0.0; s->P.erp = 0.2; s->P.cfm = 1e-5;
   s->P.pgs_iterations = 1; s->P.keep_all_points = 0;
@@ -589,7 +589,7 @@ int tds_b200_set_params(tds_b200_sim* s, double dt, const double gravity[3], dou
                         double erp, double cfm, int pgs_iterations, int keep_all_points) {
   if (!s) return -1;
   drop_host_graph(s);
-  s->P.dt = dt;
+  s->P.dt = dt; s->P.inv_dt = 1.0 / dt;
   for (int k = 0; k < 3; ++k) s->P.gravity[k] = gravity[k];
   s->P.friction = friction; s->P.restitution = restitution; s->P.erp = erp; s->P.cfm = cfm;
   s->P.pgs_iterations = pgs_iterations; s->P.keep_all_points = keep_all_points;

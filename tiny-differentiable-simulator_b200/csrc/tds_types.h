@@ -88,6 +88,7 @@ struct SimParams {
   int contact_model;
   int hard_contact_condition;
   double spring_k, damper_d, exponent_n, v_transition;
+  double inv_dt;   // 1 / dt, computed once on the host (the specialised kernel multiplies instead of dividing per contact row)
 };
 
 struct EnvParams {
