@@ -110,27 +110,6 @@ template <class SP> struct Cls {
       for (int j = 0; j < 3; ++j) if (SP::L_AXIS[r][k][j] != SP::L_AXIS[0][k][j]) return false;
     return true;
   }
-  // Revolute joints whose axes are, in every role, +-(the same coordinate axis): the rotation is a plain X / Y / Z rotation
-  // by +-q (link.hpp:262-266 builds it as an axis-angle quaternion: equal up to fp64 round-off), the sign comes from
-  // the role's table.  Returns the coordinate index or -1.
-  __host__ __device__ static constexpr int axis_dir(int k) {
-    int d = -1;
-    for (int r = 0; r < SP::T; ++r) {
-      if (!(SP::L_FLAGS[r][k] & TDS_LF_REVOLUTE)) return -1;
-      const double* a = SP::L_AXIS[r][k];
-      int dr = -1;
-      for (int j = 0; j < 3; ++j) {
-        if (a[j] == 1.0 || a[j] == -1.0) { if (dr >= 0) return -1; dr = j; }
-        else if (a[j] != 0.0) return -1;
-      }
-      if (dr < 0 || (d >= 0 && dr != d)) return -1;
-      d = dr;
-      const int jt = SP::L_JTYPE[r][k];
-      if (jt != TDSJ_REVOLUTE_AXIS && jt != TDSJ_REVOLUTE_X + dr) return -1;
-      if (jt != TDSJ_REVOLUTE_AXIS && a[dr] != 1.0) return -1;
-    }
-    return d;
-  }
   __host__ __device__ static constexpr bool has_sd(int k, int j) {
     for (int r = 0; r < SP::T; ++r) if (SP::L_SD[r][k][j] != 0.0) return true;
     return false;
@@ -172,7 +151,6 @@ template <class SP> struct LegTab {
   static constexpr int KO = Cls<SP>::KO, NG = Cls<SP>::n_geoms_own() > 0 ? Cls<SP>::n_geoms_own() : 1,
                        NP = Cls<SP>::n_pts_own() > 0 ? Cls<SP>::n_pts_own() : 1;
   double xt[KO][12], axis[KO][3], rbic[KO][10], sd[KO][2];
-  double asign[KO];   // Cls::axis_dir(k) >= 0: sign of the role's axis along that coordinate
   double gt[NG][3], ghalf[NG][3], grad[NG];
   int qidx[KO], qdidx[KO], act[KO], link[KO];
   int cand[NP];   // global candidate index of the subtree's p-th point
@@ -184,7 +162,6 @@ template <class SP> constexpr LegTab<SP> make_leg(int r) {
     const int o = k - C::NT;
     for (int j = 0; j < 12; ++j) t.xt[o][j] = SP::L_XT[r][k][j];
     for (int j = 0; j < 3; ++j) t.axis[o][j] = SP::L_AXIS[r][k][j];
-    t.asign[o] = C::axis_dir(k) >= 0 ? SP::L_AXIS[r][k][C::axis_dir(k)] : 1.0;
     for (int j = 0; j < 10; ++j) t.rbic[o][j] = SP::L_RBIC[r][k][j];
     for (int j = 0; j < 2; ++j) t.sd[o][j] = SP::L_SD[r][k][j];
     t.qidx[o] = SP::L_QIDX[r][k]; t.qdidx[o] = SP::L_QDIDX[r][k]; t.act[o] = SP::L_ACT[r][k]; t.link[o] = SP::L_LINK[r][k];
@@ -461,7 +438,7 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   sfor<NT, NLOC>([&](auto Kc) {
     constexpr int k = decltype(Kc)::value;
     if constexpr ((C::flags(k) & TDS_LF_REVOLUTE) != 0 && !(C::flags(k) & TDS_LF_FIXED))
-      sincos_t((CI(C::jtype(k)) == TDSJ_REVOLUTE_AXIS && CI(C::axis_dir(k)) < 0) ? RC(qv[k]) * RC(0.5) : RC(qv[k]), &snv[k], &csv[k]);
+      sincos_t(CI(C::jtype(k)) == TDSJ_REVOLUTE_AXIS ? RC(qv[k]) * RC(0.5) : RC(qv[k]), &snv[k], &csv[k]);
   });
   if (role == 0) {
     sfor<0, NT>([&](auto Kc) {
@@ -579,20 +556,8 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
         pi = axpy(d, qi, pi);
         S.bot = d;
       } else {
-        constexpr int adir = TR ? -1 : C::axis_dir(k);
-        V3<RC> w;
-        if constexpr (adir >= 0 && !axis_ct) {   // +-coordinate axis: the column of Ri, signed
-          const RC sg = RC(LG.asign[ko]);
-          const V3<RC> cd = adir == 0 ? col_x(Ri) : (adir == 1 ? col_y(Ri) : col_z(Ri));
-          w = cd * sg;
-        } else w = rot_axis();
-        if constexpr (jt == TDSJ_REVOLUTE_AXIS && adir >= 0) {
-          const RC s = snv[k] * RC(LG.asign[ko]), c = csv[k];   // rotation by q about -e_d = rotation by -q about e_d
-          const V3<RC> cx = col_x(Ri), cy = col_y(Ri), cz = col_z(Ri);
-          if constexpr (adir == 0) set_cols(Ri, cx, axpy(cz, s, cy * c), axpy(cy, -s, cz * c));
-          else if constexpr (adir == 1) set_cols(Ri, axpy(cz, -s, cx * c), cy, axpy(cx, s, cz * c));
-          else set_cols(Ri, axpy(cy, s, cx * c), axpy(cx, -s, cy * c), cz);
-        } else if constexpr (jt == TDSJ_REVOLUTE_AXIS) {
+        const V3<RC> w = rot_axis();
+        if constexpr (jt == TDSJ_REVOLUTE_AXIS) {
           const RC dl = sqrt_t(dot(axv, axv));
           RC s = snv[k] / dl;
           const RC c = csv[k];
