@@ -535,6 +535,11 @@ def main():
         with torch.cuda.stream(side):
             one_step(W)          # first launch on the capture stream outside capture
         torch.cuda.synchronize()
+        if gathered is not None:   # nothing recorded outside the capture may be waited on inside it
+            with torch.cuda.stream(side):
+                gathered.join()
+            torch.cuda.synchronize()
+            gathered.reset()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             for i in range(K):
@@ -614,6 +619,10 @@ def main():
 
     if rank != 0:
         if world > 1:
+            if gathered is not None:   # collectives captured in a CUDA graph: leave without the process-group teardown
+                torch.cuda.synchronize()
+                dist.barrier()
+                os._exit(0)
             dist.destroy_process_group()
         return
     value = n * world * K / (total_ms * 1e-3)
@@ -668,6 +677,10 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
     emit(line)
     if world > 1:
+        if gathered is not None:       # (round 2: the teardown hung for the full timeout after the line was printed)
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
         dist.destroy_process_group()
 
 

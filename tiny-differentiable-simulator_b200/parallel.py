@@ -82,6 +82,11 @@ class RewardDoneExchange:
             torch.cuda.current_stream().wait_stream(self.comm)
             self._pending = [None] * self.depth
 
+    def reset(self):
+        """Forget events of gathers already joined (call after join() + a synchronisation, e.g. before stream capture:
+        an event recorded outside a capture cannot be waited on inside it)."""
+        self._pending = [None] * self.depth
+
     def full(self, sizes, k=0):
         """(reward, done) of all environments, rank-major, trimmed to the shard sizes."""
         r = self.recv[k % self.depth]
