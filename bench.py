@@ -650,7 +650,7 @@ def main():
                    "timing": "CUDA events around exactly K steps (" + (f"one CUDA-graph replay of K kernel nodes, preceded and followed by untimed replays of the same graph for the clock sampler: {reps} replays in all" if graph is not None else "K individual launches") + "), max over ranks",
                    "l2": (f"inputs larger than L2: ring of {ring} action tensors = {ring * 12 * ns * 4 / 2**20:.0f} MiB, one per step"
                           if ring >= 700 else f"ring of {ring} action tensors (L2-resident)"),
-                   "wall_s_timed_region": t_wall},
+                   "wall_s_all_replays": t_wall},
         "gpu_launches": K, "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4,
                                     "d2h_bytes_per_step": n * 36 * 4 + n * 4 + n * 4, "steps": Ke, "gpu_launches_per_step": 1, "path": "zero-copy: the step kernel reads the pinned host actions and writes obs / reward / done to pinned host memory itself (PCIe traffic inside the timed kernel)",
                                     "api": "tds_b200_env_step_host (actions host->device, obs/reward/done device->host, pinned)"},

@@ -54,9 +54,10 @@ def main():
     for name, (plane, urdf, floating, gen) in CONFIGS.items():
         sim = ref.RefSim.from_urdf(urdf, plane, floating)
         model = sim.export_model()
-        save_model(os.path.join(HERE, "models", name + ".json"), model,
-                   meta=dict(source=os.path.relpath(urdf, D) if urdf.startswith(D) else os.path.relpath(urdf, HERE), plane=bool(plane), floating=floating,
-                             exported_by="reference UrdfCache::construct via oracle/_ref"))
+        meta = dict(source=os.path.relpath(urdf, D) if urdf.startswith(D) else os.path.relpath(urdf, HERE), plane=bool(plane),
+                    floating=floating, exported_by="reference UrdfCache::construct via oracle/_ref")
+        for dest in (os.path.join(HERE, "models"), os.path.join(ROOT, "tiny-differentiable-simulator_b200", "models")):
+            save_model(os.path.join(dest, name + ".json"), model, meta=meta)
         w = gen(N)
         sim.set_params(**w["params"])
         if name == "humanoid":

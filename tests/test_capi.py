@@ -113,3 +113,14 @@ def test_contact_pair_lists_match_reference_goldens():
         for e in range(la.shape[0]):
             assert np.array_equal(t[:k, 1], la[e]) and np.array_equal(t[:k, 3], lb[e]), name
         assert np.all(t[:k, 0] == 0) and np.all(t[:k, 2] == 1)
+
+
+def test_packaged_models_equal_the_golden_fixtures():
+    """The models the package ships (tds_b200/models) are the fixtures exported from the reference (tests/golden/models)."""
+    import filecmp
+    pkg = os.path.join(os.path.dirname(tds_b200.lib_path()), "models")
+    gold = os.path.join(ROOT, "tests", "golden", "models")
+    names = sorted(f for f in os.listdir(gold) if f.endswith(".json"))
+    assert names and sorted(f for f in os.listdir(pkg) if f.endswith(".json")) == names
+    for f in names:
+        assert filecmp.cmp(os.path.join(pkg, f), os.path.join(gold, f), shallow=False), f

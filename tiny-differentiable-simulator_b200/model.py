@@ -50,6 +50,10 @@ def load_model(path):
 
 
 def fixture_path(name):
-    """Compiled models committed as fixtures (generated by tests/golden/make_golden.py)."""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    return os.path.join(root, "tests", "golden", "models", name + ".json")
+    """Compiled models shipped with the package (`models/<name>.json`: flat models exported from the reference's own URDF
+    loader by tests/golden/make_golden.py, which also keeps the copy under tests/golden/models the tests compare against)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = os.path.join(here, "models", name + ".json")
+    if os.path.exists(p):
+        return p
+    return os.path.join(os.path.dirname(here), "tests", "golden", "models", name + ".json")
