@@ -54,7 +54,7 @@ int tds_b200_urdf_to_model(const char* urdf, const char* plane_urdf, int floatin
  * resident on CUDA device `device`.  Returns NULL on error (see tds_b200_last_error). */
 tds_b200_sim* tds_b200_create(const double* model, int n_model_doubles, int n_envs, int device);
 /* Host-only acceptance check of a flat model (no GPU needed): 0, or the negative code tds_b200_create would fail with
- * (spherical joints, box / mesh shapes against the plane, capacity); the reason is in tds_b200_last_error(). */
+ * (mesh shapes against the plane, spherical joints with a stiffness, capacity); the reason is in tds_b200_last_error(). */
 int tds_b200_validate_model(const double* model, int n_model);
 void tds_b200_destroy(tds_b200_sim* sim);
 

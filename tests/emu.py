@@ -1,0 +1,71 @@
+"""TEST INFRASTRUCTURE: ctypes binding of tests/cpp/_stepw_host.so - the product's generic step kernel (csrc/tds_stepw.cu)
+compiled for the host (see tests/cpp/stepw_host.cpp).  Used only by the CPU test-suite to execute the kernel SOURCE without a
+GPU; the package never loads it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "cpp", "_stepw_host.so")
+SRC = os.path.join(HERE, "cpp", "stepw_host.cpp")
+CSRC = os.path.join(ROOT, "tiny-differentiable-simulator_b200", "csrc")
+_lib = None
+
+
+def build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("tds_stepw.cu", "tds_wcommon.cuh", "tds_math.cuh", "tds_dual.cuh", "tds_model.h", "tds_types.h")]
+    if os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
+        return
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-w", "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                           "-I/usr/local/cuda/include", SRC, "-o", SO])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(SO)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.tdsemu_stepw.restype = ctypes.c_int
+        L.tdsemu_stepw.argtypes = [dp, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 8
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def step(model, mode, q, qd, tau=None, precision=1, use_pd=False, env=None, jacobian=False, dt=1e-3, gravity=(0.0, 0.0, -9.81),
+         friction=0.5, restitution=0.0, erp=0.2, cfm=1e-5, pgs_iterations=1, keep_all_points=False, contact_model=0,
+         spring_k=50000.0, damper_d=5000.0, exponent_n=1.5, v_transition=0.01, hard_contact_condition=True):
+    """One step of every row of q / qd through the host-compiled kernel.  env = (n_act, start_link, kp, kd, max_force,
+    action_limit, poses...) for use_pd.  Returns dict(q, qd, qdd, contact_dist[, jac])."""
+    m = np.ascontiguousarray(model, dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+    n, n_q, n_qd = q.shape[0], int(m[3]), int(m[4])
+    t = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+    params = np.array([dt, *gravity, friction, restitution, erp, cfm, pgs_iterations, int(keep_all_points), contact_model, spring_k,
+                       damper_d, exponent_n, v_transition, int(hard_contact_condition)], dtype=np.float64)
+    e = None if env is None else np.ascontiguousarray(env, dtype=np.float64)
+    out = dict(q=np.zeros((n, n_q)), qd=np.zeros((n, n_qd)), qdd=np.zeros((n, n_qd)), contact_dist=np.zeros((n, 64)))
+    n_tau = n_qd - (6 if int(m[2]) else 0)
+    rows = n_qd if mode == 0 else n_q + n_qd
+    cols = n_q + n_qd + ((int(e[0]) + 3) if use_pd else n_tau)
+    jac = np.zeros((n, rows, cols)) if jacobian else None
+    cd = np.zeros((n, 64))
+    # contact_dist is written [n][n_points]: size it after the call from the return value
+    cdbuf = np.zeros(n * 64)
+    rc = lib().tdsemu_stepw(_dp(m), m.size, _dp(params), _dp(e), precision, mode, int(use_pd), n, _dp(q), _dp(qd), _dp(t),
+                            _dp(out["q"]), _dp(out["qd"]), _dp(out["qdd"]), _dp(cdbuf), _dp(jac))
+    if rc < 0:
+        raise RuntimeError(f"tdsemu_stepw rc={rc}")
+    if jacobian:
+        out["jac"] = jac
+        del out["contact_dist"]
+    else:
+        out["contact_dist"] = cdbuf[:n * rc].reshape(n, rc) if rc else np.zeros((n, 0))
+    return out

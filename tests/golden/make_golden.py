@@ -34,6 +34,9 @@ CONFIGS = {
     # box shapes against the plane (contact_plane_box): our own one-box fixture and the reference's cartpole on the plane
     "box": (D + "plane_implicit.urdf", os.path.join(HERE, "urdf", "box.urdf"), True, wl.box),
     "cartpole_plane": (D + "plane_implicit.urdf", D + "cartpole.urdf", False, wl.cartpole_plane),
+    # spherical joints (forward_dynamics.hpp:56-109, integrator.hpp:97-122)
+    "pendulum5spherical": (None, D + "pendulum5spherical.urdf", False, wl.pendulum5spherical),
+    "humanoid_spherical": (D + "plane_implicit.urdf", D + "humanoid_xyz_spherical.urdf", False, wl.humanoid_spherical),
 }
 
 ANT_POSES, ANT_KP, ANT_KD, ANT_MAX = np.array([0.0, -0.5] * 4), 15.0, 0.3, 3.0   # ant_environment2.h:43-66

@@ -82,17 +82,21 @@ def test_unsupported_models_are_refused_loudly():
         m = np.ascontiguousarray(m, dtype=np.float64)
         return L.tds_b200_validate_model(m.ctypes.data_as(dp), int(m.size)), L.tds_b200_last_error().decode()
 
-    for name in ("cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane"):
+    for name in ("cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "pendulum5spherical",
+                 "humanoid_spherical"):
         assert check(load_model(fixture_path(name)))[0] == 0, name
     # a mesh shape against the ground plane: the reference collides it, the contact stage here does not -> refused
     m = np.array(load_model(fixture_path("box")), dtype=np.float64)
     m[16 + 13 + 1] = 3.0                           # the geom's type -> TDSG_MESH (no links: geoms follow the base record)
     rc, msg = check(m)
     assert rc == -6 and "mesh" in msg
-    m = np.array(load_model(fixture_path("laikago")), dtype=np.float64)
-    m[16 + 13 + 1] = 8.0                           # first link's joint type -> spherical
+    m = np.array(load_model(fixture_path("pendulum5spherical")), dtype=np.float64)
+    m[16 + 13 + 32] = 5.0                          # a joint stiffness on a spherical joint (needs the quaternion's axis-angle)
     rc, msg = check(m)
     assert rc == -3 and "spherical" in msg
+    m = np.array(load_model(fixture_path("laikago")), dtype=np.float64)
+    m[16 + 13 + 1] = 9.0                           # unknown joint type
+    assert check(m)[0] == -3
     assert check(m[:10])[0] == -1
 
 
@@ -103,7 +107,8 @@ def test_contact_pair_lists_match_reference_goldens():
     import numpy as np
     L = tds_b200.lib()
     golden = os.path.join(ROOT, "tests", "golden")
-    for name in ("sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "cartpole", "pendulum5"):
+    for name in ("sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "cartpole", "pendulum5", "humanoid_spherical",
+                 "pendulum5spherical"):
         m = np.ascontiguousarray(load_model(fixture_path(name)), dtype=np.float64)
         t = np.zeros((64, 4), dtype=np.int32)
         k = L.tds_b200_model_contact_pairs(m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(m.size), ctypes.c_void_p(t.ctypes.data), 64)

@@ -1,0 +1,90 @@
+"""The product's generic step kernel (csrc/tds_stepw.cu) executed on the CPU by compiling its SOURCE for the host
+(tests/cpp/stepw_host.cpp): the golden vectors of the reference, the spring-damper branch against the oracle and the
+dual-number Jacobian against central differences, without a GPU.  The GPU tests (tests/test_parity_gpu.py) check the same
+kernel as nvcc builds it; this file keeps the kernel source honest in a container that has no GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import tds_b200.workloads as wl
+from tds_b200.model import fixture_path, load_model
+from oracle import port
+import emu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "pendulum5spherical", "humanoid_spherical"]
+TOL = 1e-5
+
+
+def rel_err(a, ref):
+    return float(np.max(np.abs(a - ref) / np.maximum(1.0, np.abs(ref)))) if ref.size else 0.0
+
+
+def params_from_golden(g):
+    kw = {}
+    for k in g.files:
+        if k.startswith("param_"):
+            v = g[k]
+            kw[k[6:]] = tuple(v.tolist()) if v.ndim else (bool(v) if k == "param_keep_all_points" else float(v))
+    return kw
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("precision", [0, 1])
+def test_golden_vectors_through_the_kernel_source(name, precision):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    model = load_model(fixture_path(name))
+    mode = int(g["mode"])
+    tau = g["tau"] if "tau" in g.files else None
+    n_tau = int(model[4]) - (6 if int(model[2]) else 0)
+    if tau is not None and tau.shape[1] != n_tau:
+        tau = tau[:, -n_tau:]
+    out = emu.step(model, mode, g["q_in"], g["qd_in"], tau, precision=precision, **params_from_golden(g))
+    if mode == 0:
+        assert rel_err(out["qdd"], g["qdd"]) <= (TOL if precision == 1 else 5e-5)
+        return
+    tol = 5e-4 if (name in ("humanoid", "humanoid_spherical", "pendulum5spherical") and precision == 0) else TOL
+    assert rel_err(out["q"], g["q_out"]) <= tol and rel_err(out["qd"], g["qd_out"]) <= tol
+    if mode == 2:
+        ref_d = np.stack(list(g["contact_dist"]))
+        assert out["contact_dist"].shape == ref_d.shape and np.max(np.abs(out["contact_dist"] - ref_d)) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["sphere2", "laikago", "box"])
+def test_spring_damper_branch_vs_oracle(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    model = load_model(fixture_path(name))
+    params = params_from_golden(g)
+    law = dict(spring_k=40000.0, damper_d=3000.0, exponent_n=1.5, v_transition=0.02, hard_contact_condition=True)
+    tau = g["tau"] if "tau" in g.files else None
+    out = emu.step(model, 2, g["q_in"], g["qd_in"], tau, precision=1, contact_model=1, **law, **params)
+    P = port.make_params(contact_model=1, **law, **params)
+    refs = [port.step(model, P, 2, g["q_in"][i], g["qd_in"][i], None if tau is None else tau[i]) for i in range(g["q_in"].shape[0])]
+    assert rel_err(out["qd"], np.array([r["qd"] for r in refs])) <= TOL
+
+
+@pytest.mark.parametrize("name,gen", [("pendulum5", wl.pendulum5), ("cartpole", wl.cartpole), ("sphere2", wl.sphere2)])
+def test_dual_number_jacobian_vs_central_differences(name, gen):
+    n = 6
+    model = load_model(fixture_path(name))
+    w = gen(n, seed=2718)
+    mode, tau = w["mode"], w.get("tau")
+    n_q, n_qd = int(model[3]), int(model[4])
+    n_tau = n_qd - (6 if int(model[2]) else 0)
+    t = None if tau is None or not n_tau else tau[:, -n_tau:]
+    J = emu.step(model, mode, w["q"], w["qd"], t, jacobian=True, **w["params"])["jac"]
+    P = port.make_params(**w["params"])
+    ok = []
+    for e in range(n):
+        def f(x):
+            r = port.step(model, P, mode, x[:n_q], x[n_q:n_q + n_qd], x[n_q + n_qd:] if n_tau else None)
+            return r["qdd"] if mode == 0 else np.concatenate([r["q"], r["qd"]])
+        x0 = np.concatenate([w["q"][e], w["qd"][e], t[e] if t is not None else np.zeros(0)])
+        y0 = f(x0)
+        Jr = np.zeros((y0.size, x0.size))
+        for j in range(x0.size):
+            xp, xm = x0.copy(), x0.copy(); xp[j] += 1e-6; xm[j] -= 1e-6
+            Jr[:, j] = (f(xp) - f(xm)) / 2e-6
+        ok.append(np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-4)
+    assert np.mean(ok) >= (1.0 if mode != 2 else 0.8)

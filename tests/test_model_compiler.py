@@ -50,11 +50,23 @@ def test_floating_indices_and_default_axis():
     assert links[0, 1] == 6 and links[0, 2] == 7 and links[0, 3] == 6           # default axis (0,0,1) -> REVOLUTE_Z; q starts at 7
 
 
+def test_spherical_joint_indices():
+    """A spherical joint takes 4 coordinates (quaternion) and 3 velocities (MultiBody::initialize, multi_body.hpp:324-349)."""
+    m = compile_urdf(TINY_URDF.replace('type="continuous"', 'type="spherical"'), None, floating=False)
+    d = model_dims(m)
+    links = m[16 + 13:][:d["n_links"] * 34].reshape(d["n_links"], 34)
+    sph = np.nonzero(links[:, 1] == 8)[0]
+    assert sph.size >= 1 and d["n_q"] - d["n_qd"] == sph.size
+    for i in sph:
+        later = links[i + 1:][links[i + 1:, 1] != -1]
+        if later.size:
+            assert later[0, 2] == links[i, 2] + 4 and later[0, 3] == links[i, 3] + 3
+
+
 @pytest.mark.parametrize("bad,msg", [
     ("<robot name='x'><link name='a'/><link name='b'/></robot>", "multiple parent links"),
     ("<robot name='x'><link name='a'></robot>", "XML error"),
     (TINY_URDF.replace('type="continuous"', 'type="planar"'), "unsupported type"),
-    (TINY_URDF.replace('type="continuous"', 'type="spherical"'), "spherical"),
     ("<robot><link name='a'/></robot>", "name"),
 ])
 def test_errors(bad, msg):
@@ -69,7 +81,10 @@ def test_errors(bad, msg):
     ("sphere2", "sphere2.urdf", "plane_implicit.urdf", True),
     ("laikago", "laikago/laikago_toes_zup_xyz_xyzrot.urdf", "plane_implicit.urdf", False),
     ("humanoid", "humanoid.urdf", "plane_implicit.urdf", True),
-    ("ant", "gym/ant_org_xyz_xyzrot.urdf", "plane_implicit.urdf", False)])
+    ("ant", "gym/ant_org_xyz_xyzrot.urdf", "plane_implicit.urdf", False),
+    ("cartpole_plane", "cartpole.urdf", "plane_implicit.urdf", False),
+    ("pendulum5spherical", "pendulum5spherical.urdf", None, False),
+    ("humanoid_spherical", "humanoid_xyz_spherical.urdf", "plane_implicit.urdf", False)])
 def test_matches_reference_loader(name, urdf, plane, floating):
     """Our compiler on the reference's URDFs == the flat export of the reference's own loader
     (fixtures were exported from UrdfCache::construct by tests/golden/make_golden.py)."""

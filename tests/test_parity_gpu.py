@@ -19,7 +19,7 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane"]
+CONFIGS = ["cartpole", "pendulum5", "sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "pendulum5spherical", "humanoid_spherical"]
 
 
 def rel_err(a, ref):
@@ -54,7 +54,7 @@ def test_golden_vectors(name, precision, golden_dir):
     # the fp32 block factorisation of the mixed mode, both taken about the common origin at the base, are good
     # to ~2e-4 on qd' (measured 1.8e-4).  The 1e-5 bar is met in PREC_F64, which is the mode DESIGN.md
     # prescribes for that model; the headline Laikago workload meets 1e-5 in the mixed mode.
-    tol = 5e-4 if (name == "humanoid" and precision == tds_b200.PREC_MIXED) else TOL
+    tol = 5e-4 if (name in ("humanoid", "humanoid_spherical", "pendulum5spherical") and precision == tds_b200.PREC_MIXED) else TOL
     assert rel_err(out["q"], g["q_out"]) <= tol
     assert rel_err(out["qd"], g["qd_out"]) <= tol
     if mode == 2 and sim.n_contact_points:

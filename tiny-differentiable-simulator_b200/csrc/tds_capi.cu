@@ -442,6 +442,7 @@ static int rebuild_team(tds_b200_sim* s) {
   s->spec_ok = false; s->spec_idx = -1;
   TeamModel base;
   if (s->precision_req == TDS_B200_PREC_AUTO) s->precision = TDS_B200_PREC_F64;
+  if (s->dm[0].world_only) return 0;   // box shapes / spherical joints: the generic world-frame kernel serves the model
   int rc = tds_build_team(&s->dm[0], &s->E, &base, &s->team_table);
   if (rc != 0) return 0;   // chains etc.: the one-lane kernel is used
   const int sizes[3][3] = {{4, 8, 4}, {8, 8, 8}, {4, 4, 4}};
@@ -469,7 +470,7 @@ static const char* tds_model_error(int rc) {
   switch (rc) {
     case -1: return "not a flat model of this layout version (magic / size mismatch)";
     case -2: return "too many links, collision geoms or candidate contact points (TDS_MAX_LINKS / TDS_MAX_GEOMS / TDS_MAX_POINTS)";
-    case -3: return "spherical (or unknown) joint type: not implemented";
+    case -3: return "unknown joint type, or a spherical joint with a stiffness (not implemented)";
     case -4: return "links are not ordered parent before child";
     case -5: return "collision geoms are not grouped by link";
     case -6: return "mesh collision shape against the ground plane: the contact stage implements sphere, capsule and box";
@@ -864,6 +865,7 @@ static IntegrateTable integrate_table(const tds_b200_sim* s) {
 
 int tds_b200_integrate_euler_device(tds_b200_sim* s, float* q, float* qd, const float* qdd, void* stream) {
   if (!s || !q || !qd) return -1;
+  if (s->dm[0].n_sph) { set_err("stand-alone integrate_euler: spherical joints are integrated by the step kernel only"); return -3; }
   const int T = 128, B = (s->n + T - 1) / T;
   integrate_euler_kernel<<<B, T, 0, (cudaStream_t)stream>>>(q, qd, qdd, s->P.dt, integrate_table(s), 1, s->n, s->ns);
   CUDA_TRY(cudaGetLastError());

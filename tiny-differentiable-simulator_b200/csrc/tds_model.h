@@ -81,16 +81,22 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
   for (int i = 0; i < D->n_links; ++i) {
     const double* l = links + (size_t)i * TDSM_LINK;
     int jt = (int)l[TDSM_L_JTYPE];
-    if (jt == TDSJ_SPHERICAL || jt < TDSJ_FIXED || jt > TDSJ_SPHERICAL) return -3;  // spherical joints: not supported
+    if (jt < TDSJ_FIXED || jt > TDSJ_SPHERICAL) return -3;
+    // spherical joints (forward_dynamics.hpp:56-109): the stiffness term needs the quaternion's axis-angle
+    // (tiny_algebra.hpp:509-527); the URDF loader never sets a stiffness, so it is required to be 0 here
+    if (jt == TDSJ_SPHERICAL && l[TDSM_L_STIFFNESS] != 0.0) return -3;
     D->parent[i] = (int)l[TDSM_L_PARENT];
     if (D->parent[i] >= i) return -4;
     D->jtype[i] = jt;
     D->q_idx[i] = (int)l[TDSM_L_QIDX];
     D->qd_idx[i] = (int)l[TDSM_L_QDIDX];
     if (jt != TDSJ_FIXED && (D->q_idx[i] < 0 || D->q_idx[i] >= D->n_q || D->qd_idx[i] < 0 || D->qd_idx[i] >= D->n_qd)) return -1;
+    if (jt == TDSJ_SPHERICAL && (D->q_idx[i] + 3 >= D->n_q || D->qd_idx[i] + 2 >= D->n_qd)) return -1;
     int fl = 0;
+    D->s3_slot[i] = -1;
     if (jt == TDSJ_FIXED) fl |= TDS_LF_FIXED;
     else if (jt <= TDSJ_PRISMATIC_AXIS) fl |= TDS_LF_PRISMATIC;
+    else if (jt == TDSJ_SPHERICAL) { fl |= TDS_LF_SPHERICAL; D->s3_slot[i] = D->n_sph++; D->world_only = 1; }
     else fl |= TDS_LF_REVOLUTE;
     if (D->parent[i] == i - 1) fl |= TDS_LF_PARENT_ADJ;
     D->flags[i] = fl;
@@ -235,6 +241,8 @@ TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, i
   w = even(w);
   D->x_S = w; w += D->n_links * 6 * rc;                     // motion subspace in the common frame
   w = even(w);
+  D->x_S3 = w; w += D->n_sph * 18 * rc;                     // the three columns of every spherical joint
+  w = even(w);
   D->x_xw = w; w += (D->n_xw + 1) * 12 * rc;                // slot 0: base
   w = even(w);
   D->x_acc_ic_word = even(27 * ra);
@@ -252,7 +260,8 @@ TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, i
   D->x_conS = w; w += D->max_contacts * 6 * rs;
   w = even(w);
   // per-link: rigid inertia about the origin (10 RC), later reused for U (6 RA), invD, u ; v / c / a (6 RA)
-  const int first = 10 * rc > 8 * ra ? 10 * rc : 8 * ra;
+  const int urec = (D->n_sph ? 30 : 8) * ra;                // spherical: U (18), D^-1 (9), u (3)
+  const int first = 10 * rc > urec ? 10 * rc : urec;
   D->x_link_words = even(first + 6 * ra);
   const int link_region = D->n_links * D->x_link_words;
   const int y_region = D->max_contacts * n3 * 3 * rs;

@@ -66,6 +66,12 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   RQ* const qdv = A.ptr<RQ>(M.x_qd);
   RQ* const tauv = A.ptr<RQ>(M.x_tau);
   RC* const Sw = A.ptr<RC>(M.x_S);                 // S of link i at Sw + i*6*ST
+  RC* const S3w = A.ptr<RC>(M.x_S3);               // spherical joints: three columns at S3w + s3_slot*18*ST
+  // column c of link j's motion subspace (1 column, or 3 for a spherical joint)
+  auto S_col = [&](int j, int c) -> Sv<RC> {
+    return (M.flags[j] & TDS_LF_SPHERICAL) ? ld6<RC>(S3w + (M.s3_slot[j] * 3 + c) * 6 * ST, ST) : ld6<RC>(Sw + j * 6 * ST, ST);
+  };
+  auto n_cols = [&](int j) -> int { return (M.flags[j] & TDS_LF_FIXED) ? 0 : ((M.flags[j] & TDS_LF_SPHERICAL) ? 3 : 1); };
   const int LWD = M.x_link_words;
   const int VOFF = LWD - 6 * RAW;                  // word offset of v/c/a inside a link record
   RS* const Mb = A.ptr<RS>(M.x_M);
@@ -206,7 +212,17 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       const RC qi = RC(qv[M.q_idx[i] * ST]);
       const int jt = M.jtype[i];
       const V3<RC> ax = v3<RC>(RC(M.axis[i][0]), RC(M.axis[i][1]), RC(M.axis[i][2]));
-      if (fl & TDS_LF_PRISMATIC) {
+      if (fl & TDS_LF_SPHERICAL) {   // X_J = quat_to_matrix(q[0..3]) (link.hpp:268-272); S = [1 0]^T in the link frame
+        const int q0 = M.q_idx[i];
+        Ri = mul(Ri, quat_to_matrix<RC>(RC(qv[q0 * ST]), RC(qv[(q0 + 1) * ST]), RC(qv[(q0 + 2) * ST]), RC(qv[(q0 + 3) * ST])));
+        RC* const s3 = S3w + M.s3_slot[i] * 18 * ST;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const V3<RC> w = a == 0 ? col_x(Ri) : (a == 1 ? col_y(Ri) : col_z(Ri));
+          Sv<RC> Sa; Sa.top = w; Sa.bot = cross(pi, w);
+          st6<RC>(s3 + a * 6 * ST, ST, Sa);
+        }
+      } else if (fl & TDS_LF_PRISMATIC) {
         const V3<RC> d = mul(Ri, ax);
         pi = axpy(d, qi, pi);
         S.bot = d;
@@ -250,7 +266,14 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       st_rbi<RC>(A.ptr<RC>(M.x_link + i * LWD), ST, r);
     }
     Sv<RA> v = vp;
-    if (!(fl & TDS_LF_FIXED)) {
+    if (fl & TDS_LF_SPHERICAL) {
+      for (int a = 0; a < 3; ++a) {
+        const RA qda = RA(qdv[(M.qd_idx[i] + a) * ST]);
+        const Sv<RA> Sf = cvt_sv<RA>(S_col(i, a));
+        v.top = axpy(Sf.top, qda, v.top);
+        v.bot = axpy(Sf.bot, qda, v.bot);
+      }
+    } else if (!(fl & TDS_LF_FIXED)) {
       const RA qdi = RA(qdv[M.qd_idx[i] * ST]);
       const Sv<RA> Sf = cvt_sv<RA>(S);
       v.top = axpy(Sf.top, qdi, v.top);
@@ -277,6 +300,30 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     for (int k = n; k < n3; ++k) Mb[(btri(k / 3, k / 3) + (k % 3) * 4) * ST] = RS(1);   // padding dofs: identity
   }
   Abi<RA> cA; Sv<RA> cP; Rbi<RC> cC;
+  // M(r, c) = S_c . F for every dof column c of the ancestors of link i (and of the floating base), F = Ic S_r
+  // (mass_matrix.hpp:58-111); r > c always: links are ordered parent first
+  auto Mset = [&](int r, int c, RS val) { Mb[(btri(r / 3, c / 3) + (r % 3) * 3 + (c % 3)) * ST] = val; };
+  auto crba_ancestors = [&](int i, int row, const Sv<RC>& F) {
+    for (int j = M.parent[i]; j >= 0; j = M.parent[j]) {
+      const int nc = n_cols(j);
+      for (int c = 0; c < nc; ++c) Mset(row, M.qd_idx[j] + c, RS(dot(S_col(j, c), F)));
+    }
+    if (M.floating) {  // base columns: F in the base frame (:107-111); O is the base origin
+      const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
+      Mset(row, 0, RS(ft.x)); Mset(row, 1, RS(ft.y)); Mset(row, 2, RS(ft.z));
+      Mset(row, 3, RS(fb.x)); Mset(row, 4, RS(fb.y)); Mset(row, 5, RS(fb.z));
+    }
+  };
+  // Ia -= a b^T in the block form of the 1-dof update below (I: top-top, H: top-bot, M: bot-bot)
+  auto abi_sub_outer = [&](Abi<RA>& Ia, const Sv<RA>& a, const Sv<RA>& b) {
+    Ia.I.xx -= a.top.x * b.top.x; Ia.I.xy -= a.top.x * b.top.y; Ia.I.xz -= a.top.x * b.top.z;
+    Ia.I.yy -= a.top.y * b.top.y; Ia.I.yz -= a.top.y * b.top.z; Ia.I.zz -= a.top.z * b.top.z;
+    Ia.H.xx -= a.top.x * b.bot.x; Ia.H.xy -= a.top.x * b.bot.y; Ia.H.xz -= a.top.x * b.bot.z;
+    Ia.H.yx -= a.top.y * b.bot.x; Ia.H.yy -= a.top.y * b.bot.y; Ia.H.yz -= a.top.y * b.bot.z;
+    Ia.H.zx -= a.top.z * b.bot.x; Ia.H.zy -= a.top.z * b.bot.y; Ia.H.zz -= a.top.z * b.bot.z;
+    Ia.M.xx -= a.bot.x * b.bot.x; Ia.M.xy -= a.bot.x * b.bot.y; Ia.M.xz -= a.bot.x * b.bot.z;
+    Ia.M.yy -= a.bot.y * b.bot.y; Ia.M.yz -= a.bot.y * b.bot.z; Ia.M.zz -= a.bot.z * b.bot.z;
+  };
   for (int i = n_links - 1; i >= 0; --i) {
     const int p = M.parent[i];
     const int fl = M.flags[i];
@@ -304,6 +351,63 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       st6<RA>(vrec, ST, z);
       st6<RA>(urec, ST, z);
       urec[6 * ST] = RA(0); urec[7 * ST] = RA(0);
+    } else if (fl & TDS_LF_SPHERICAL) {
+      // 3-dof joint (forward_dynamics.hpp:56-109): U = Ia S, D = S^T U (3 x 3), u = tau - damping qd - S^T pA,
+      // Ia -= U D^-1 U^T, pa = pA + Ia c + U D^-1 u.  Record: U (18) | D^-1 (9) | u (3), then c.
+      const int d0 = M.qd_idx[i];
+      Sv<RC> Sd[3]; Sv<RA> S[3], U[3];
+      RA qdj[3];
+      Sv<RA> vJ; vJ.top = v3<RA>(RA(0), RA(0), RA(0)); vJ.bot = vJ.top;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        Sd[a] = S_col(i, a); S[a] = cvt_sv<RA>(Sd[a]);
+        qdj[a] = RA(qdv[(d0 + a) * ST]);
+        vJ.top = axpy(S[a].top, qdj[a], vJ.top); vJ.bot = axpy(S[a].bot, qdj[a], vJ.bot);
+        U[a] = abi_mul(Ia, S[a]);
+      }
+      const Sv<RA> c = cross_mm(v, vJ);                      // kinematics.hpp:96-97
+      RA Dm[3][3], u[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Dm[a][b] = dot(S[a], U[b]);
+        u[a] = RA(tauv[(d0 + a) * ST]) - RA(M.damping[i]) * qdj[a] - dot(S[a], pA);
+      }
+      RA Di[3][3];   // general 3 x 3 inverse (Matrix3::inverse)
+      {
+        const RA c0 = Dm[1][1] * Dm[2][2] - Dm[1][2] * Dm[2][1], c1 = Dm[1][2] * Dm[2][0] - Dm[1][0] * Dm[2][2], c2 = Dm[1][0] * Dm[2][1] - Dm[1][1] * Dm[2][0];
+        const RA sdet = RA(1) / (Dm[0][0] * c0 + Dm[0][1] * c1 + Dm[0][2] * c2);
+        Di[0][0] = c0 * sdet; Di[0][1] = (Dm[0][2] * Dm[2][1] - Dm[0][1] * Dm[2][2]) * sdet; Di[0][2] = (Dm[0][1] * Dm[1][2] - Dm[0][2] * Dm[1][1]) * sdet;
+        Di[1][0] = c1 * sdet; Di[1][1] = (Dm[0][0] * Dm[2][2] - Dm[0][2] * Dm[2][0]) * sdet; Di[1][2] = (Dm[0][2] * Dm[1][0] - Dm[0][0] * Dm[1][2]) * sdet;
+        Di[2][0] = c2 * sdet; Di[2][1] = (Dm[0][1] * Dm[2][0] - Dm[0][0] * Dm[2][1]) * sdet; Di[2][2] = (Dm[0][0] * Dm[1][1] - Dm[0][1] * Dm[1][0]) * sdet;
+      }
+      st6<RA>(vrec, ST, c);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        st6<RA>(urec + a * 6 * ST, ST, U[a]);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) urec[(18 + a * 3 + b) * ST] = Di[a][b];
+        urec[(27 + a) * ST] = u[a];
+      }
+      Sv<RA> V[3];   // V = U D^-1
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        V[b].top = U[0].top * Di[0][b] + U[1].top * Di[1][b] + U[2].top * Di[2][b];
+        V[b].bot = U[0].bot * Di[0][b] + U[1].bot * Di[1][b] + U[2].bot * Di[2][b];
+      }
+#pragma unroll
+      for (int b = 0; b < 3; ++b) abi_sub_outer(Ia, V[b], U[b]);
+      const Sv<RA> Iac = abi_mul(Ia, c);
+      pa.top = pA.top + Iac.top + V[0].top * u[0] + V[1].top * u[1] + V[2].top * u[2];
+      pa.bot = pA.bot + Iac.bot + V[0].bot * u[0] + V[1].bot * u[1] + V[2].bot * u[2];
+      if (any_contact) {   // mass_matrix.hpp:58-84
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const Sv<RC> F = rbi_mul(Ic, Sd[a]);
+          for (int b = 0; b <= a; ++b) Mset(d0 + a, d0 + b, RS(dot(Sd[b], F)));
+          crba_ancestors(i, d0 + a, F);
+        }
+      }
     } else {
       const Sv<RC> Sd = ld6<RC>(Sw + i * 6 * ST, ST);
       const Sv<RA> S = cvt_sv<RA>(Sd);
@@ -335,21 +439,8 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       pa.bot = pA.bot + Iac.bot + U.bot * uD;
       if (any_contact) {   // CRBA column, mass_matrix.hpp:86-111: M_ij = S_j . (Ic_i S_i), no transforms needed
         const Sv<RC> F = rbi_mul(Ic, Sd);
-        const int bi = qdi / 3, ri = qdi - 3 * bi;
-        Mb[(btri(bi, bi) + ri * 4) * ST] = RS(dot(Sd, F));
-        for (int j = M.parent[i]; j >= 0; j = M.parent[j]) {
-          if (M.flags[j] & TDS_LF_FIXED) continue;
-          const int qj = M.qd_idx[j];
-          const int bj = qj / 3, cj = qj - 3 * bj;
-          Mb[(btri(bi, bj) + ri * 3 + cj) * ST] = RS(dot(ld6<RC>(Sw + j * 6 * ST, ST), F));
-        }
-        if (M.floating) {  // base columns: F in the base frame (:107-111); O is the base origin
-          const V3<RC> ft = mulT(Rb, F.top), fb = mulT(Rb, F.bot);
-          RS* row0 = Mb + (btri(bi, 0) + ri * 3) * ST;
-          RS* row1 = Mb + (btri(bi, 1) + ri * 3) * ST;
-          row0[0] = RS(ft.x); row0[ST] = RS(ft.y); row0[2 * ST] = RS(ft.z);
-          row1[0] = RS(fb.x); row1[ST] = RS(fb.y); row1[2 * ST] = RS(fb.z);
-        }
+        Mset(qdi, qdi, RS(dot(Sd, F)));
+        crba_ancestors(i, qdi, F);
       }
     }
     // hand (Ia, pa, Ic) to the parent: plain sums in the common frame
@@ -466,7 +557,25 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     if (fl & TDS_LF_PARENT_ADJ) a = a_prev;
     else if (p >= 0) a = ld6<RA>(A.ptr<RA>(M.x_link + p * LWD + VOFF), ST);
     else a = a_base;
-    if (!(fl & TDS_LF_FIXED)) {
+    if (fl & TDS_LF_SPHERICAL) {   // forward_dynamics.hpp:272-284: qdd = D^-1 (u - U^T a)
+      const RA* urec = A.ptr<RA>(M.x_link + i * LWD);
+      const int d0 = M.qd_idx[i];
+      a = a + ld6<RA>(vrec, ST);
+      RA t[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = urec[(27 + k) * ST] - dot(ld6<RA>(urec + k * 6 * ST, ST), a);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const RA qdd = urec[(18 + j * 3) * ST] * t[0] + urec[(18 + j * 3 + 1) * ST] * t[1] + urec[(18 + j * 3 + 2) * ST] * t[2];
+        const Sv<RA> S = cvt_sv<RA>(S_col(i, j));
+        a.top = axpy(S.top, qdd, a.top);
+        a.bot = axpy(S.bot, qdd, a.bot);
+        if (mode == MODE_FD) {
+          if constexpr (AD) { if (live && io.jac) io.jac[((size_t)(d0 + j) * io.jac_n_in + dir) * ns + e] = qdd.d; }
+          else if (live && io.qdd_out) io.qdd_out[(size_t)(d0 + j) * ns + e] = (float)val_of(qdd);
+        } else if (!world_step) qdv[(d0 + j) * ST] = RQ(RA(qdv[(d0 + j) * ST]) + qdd * dtA);
+      }
+    } else if (!(fl & TDS_LF_FIXED)) {
       const RA* urec = A.ptr<RA>(M.x_link + i * LWD);
       const Sv<RA> c = ld6<RA>(vrec, ST);
       const Sv<RA> U = ld6<RA>(urec, ST);
@@ -536,12 +645,14 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
           }
         }
         for (int j = L; j >= 0; j = M.parent[j]) {  // jacobian.hpp:63-80: column = S_j evaluated at the contact point
-          if (M.flags[j] & TDS_LF_FIXED) continue;
-          const Sv<RC> S = ld6<RC>(Sw + j * 6 * ST, ST);
-          const V3<RC> col = S.bot + cross(S.top, xc);
-          const int qj = M.qd_idx[j];
-          Y[(3 * qj) * ST] = RS(dot(nbv, col)); Y[(3 * qj + 1) * ST] = RS(dot(f1, col)); Y[(3 * qj + 2) * ST] = RS(dot(f2, col));
-          vel = vel + col * RC(qdv[qj * ST]);
+          const int nc = n_cols(j);
+          for (int cj = 0; cj < nc; ++cj) {
+            const Sv<RC> S = S_col(j, cj);
+            const V3<RC> col = S.bot + cross(S.top, xc);
+            const int qj = M.qd_idx[j] + cj;
+            Y[(3 * qj) * ST] = RS(dot(nbv, col)); Y[(3 * qj + 1) * ST] = RS(dot(f1, col)); Y[(3 * qj + 2) * ST] = RS(dot(f2, col));
+            vel = vel + col * RC(qdv[qj * ST]);
+          }
         }
         // rel_vel = vel_a - vel_b = -vel ; mb_constraint_solver.hpp:299-345
         RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;   // b[3], x[3]
@@ -663,6 +774,24 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   }
   for (int i = 0; i < n_links && !world_step; ++i) {
     if (M.flags[i] & TDS_LF_FIXED) continue;
+    if (M.flags[i] & TDS_LF_SPHERICAL) {
+      // integrator.hpp:97-122: the joint velocity is damped by MultiBody::joint_damping_ ^ (1000 dt) (default 0.995,
+      // multi_body.hpp:51) in every integrate_euler, then q += quat_velocity_spherical(q, qd, dt), normalised
+      const int q0 = M.q_idx[i], d0 = M.qd_idx[i];
+      const RC damp = RC(pow(0.995, P.dt * 1000.0));
+      RC w[3];
+      for (int k = 0; k < 3; ++k) { w[k] = RC(qdv[(d0 + k) * ST]) * damp; qdv[(d0 + k) * ST] = RQ(w[k]); }
+      const RC h = RC(0.5) * RC(P.dt);
+      RC qx = RC(qv[q0 * ST]), qy = RC(qv[(q0 + 1) * ST]), qz = RC(qv[(q0 + 2) * ST]), qw = RC(qv[(q0 + 3) * ST]);
+      const RC dw = (-qx * w[0] - qy * w[1] - qz * w[2]) * h;      // tiny_algebra.hpp:616-627
+      const RC dx = (qw * w[0] + qy * w[2] - qz * w[1]) * h;
+      const RC dy = (qw * w[1] + qz * w[0] - qx * w[2]) * h;
+      const RC dz = (qw * w[2] + qx * w[1] - qy * w[0]) * h;
+      qx += dx; qy += dy; qz += dz; qw += dw;
+      const RC len = sqrt_t(qx * qx + qy * qy + qz * qz + qw * qw);
+      qv[q0 * ST] = RQ(qx / len); qv[(q0 + 1) * ST] = RQ(qy / len); qv[(q0 + 2) * ST] = RQ(qz / len); qv[(q0 + 3) * ST] = RQ(qw / len);
+      continue;
+    }
     const int qi = M.q_idx[i];
     qv[qi * ST] = RQ(RC(qv[qi * ST]) + RC(qdv[M.qd_idx[i] * ST]) * RC(P.dt));
   }
@@ -704,6 +833,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
 
 }  // namespace tdsw
 
+#ifndef TDS_STEPW_KERNEL_ONLY   // (tests/cpp/stepw_host.cpp compiles the kernel above for the host, without the launchers)
 extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const EnvParams* E, const StepIO* io,
                                 int mode, int use_pd, int precision, char* gscratch, int use_smem,
                                 int warps_per_block, cudaStream_t stream) {
@@ -743,3 +873,4 @@ extern "C" int tds_launch_stepw_jacobian(const DevModel* M, const SimParams* P, 
   tds_stepw_kernel<D, D, D, D, false><<<grid, 32, 0, stream>>>(*M, *P, *E, *io, mode, use_pd, gscratch);
   return (int)cudaGetLastError();
 }
+#endif  // TDS_STEPW_KERNEL_ONLY

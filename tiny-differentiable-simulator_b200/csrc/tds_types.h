@@ -15,6 +15,7 @@
 #define TDS_LF_PRISMATIC 8
 #define TDS_LF_FIXED 16
 #define TDS_LF_XT_IDENT 32     // X_T rotation is the identity
+#define TDS_LF_SPHERICAL 64    // JOINT_SPHERICAL: 4 coordinates (quaternion xyzw), 3 velocities; world-frame kernel only
 
 // Device model: constant for all environments, passed as a __grid_constant__ kernel parameter
 // (lives in the constant bank; every lane reads the same entry -> broadcast).
@@ -59,6 +60,9 @@ struct DevModel {
   double g_half[TDS_MAX_GEOMS][3];  // capsule: local half-axis R_local * (0,0,L/2)
   double g_radius[TDS_MAX_GEOMS];
   double g_box[TDS_MAX_GEOMS][9];   // box: the three local half-axes R_local * diag(extent / 2 - r), columns x | y | z
+  int n_sph;                        // spherical joints; S columns of the s-th one at x_S3 + s * 18 RC words
+  int s3_slot[TDS_MAX_LINKS];
+  int x_S3;
   int world_only;   // the model uses features only the generic world-frame kernel (tds_stepw.cu) implements
                     // (box shapes, spherical joints): the decomposed / specialised kernels refuse it
   // static ground plane (multibody 0)

@@ -388,7 +388,6 @@ extern "C" int tds_b200_urdf_to_model(const char* urdf, const char* plane_urdf, 
   const int total = TDSM_HEADER + TDSM_BASE + n_links * TDSM_LINK + n_geoms * TDSM_GEOM + n_vis * TDSM_VIS;
   for (int i = 0; i < n_links; ++i) {  // validate before sizing so that errors surface on the first call
     const UJoint& j = *ojoints[i];
-    if (j.type == TDSJ_SPHERICAL) { g_error = "spherical joints are not supported (joint " + j.name + ")"; return -7; }
     if ((j.type == TDSJ_REVOLUTE_AXIS || j.type == TDSJ_PRISMATIC_AXIS) &&
         j.axis.v[0] == 0.0 && j.axis.v[1] == 0.0 && j.axis.v[2] == 0.0) { g_error = "zero joint axis on " + j.name; return -6; }
   }
@@ -415,11 +414,13 @@ extern "C" int tds_b200_urdf_to_model(const char* urdf, const char* plane_urdf, 
         memcpy(r + TDSM_L_AXIS, j.axis.v, sizeof j.axis.v);
       }
     }
-    if (jt == TDSJ_SPHERICAL) { g_error = "spherical joints are not supported (joint " + j.name + ")"; return -7; }
     r[TDSM_L_PARENT] = index[j.parent];
     r[TDSM_L_JTYPE] = jt;
     if (jt == TDSJ_FIXED) { r[TDSM_L_QIDX] = -2; r[TDSM_L_QDIDX] = -2; }
-    else { r[TDSM_L_QIDX] = q_index++; r[TDSM_L_QDIDX] = qd_index++; }
+    else if (jt == TDSJ_SPHERICAL) {   // quaternion xyzw: 4 coordinates, 3 velocities (multi_body.hpp:324-349)
+      r[TDSM_L_QIDX] = q_index; r[TDSM_L_QDIDX] = qd_index;
+      q_index += 4; qd_index += 3;
+    } else { r[TDSM_L_QIDX] = q_index++; r[TDSM_L_QDIDX] = qd_index++; }
     rpy_matrix(j.rpy.v, r + TDSM_L_XT_R);
     memcpy(r + TDSM_L_XT_T, j.xyz.v, sizeof j.xyz.v);
     pack_rbi(ordered[i]->inertial, r + TDSM_L_MASS);

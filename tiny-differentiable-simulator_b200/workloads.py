@@ -118,3 +118,28 @@ def cartpole_plane(n, seed=SEED):
     qd = r.uniform(-1, 1, (n, 2))
     tau = np.zeros((n, 2)); tau[:, 0] = r.uniform(-10, 10, n)
     return dict(q=_f32(q), qd=_f32(qd), tau=_f32(tau), params=dict(friction=0.5, keep_all_points=True), mode=2)
+
+
+def _unit_quats(r, n, spread=None):
+    q = r.normal(size=(n, 4)) if spread is None else np.concatenate([r.uniform(-spread, spread, (n, 3)), np.ones((n, 1))], axis=1)
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def pendulum5spherical(n, seed=SEED):
+    """pendulum5spherical.urdf: five spherical joints (quaternion xyzw each: n_q 20, n_qd 15), FD -> integrate_euler."""
+    r = np.random.default_rng(seed)
+    q = np.concatenate([_unit_quats(r, n) for _ in range(5)], axis=1)
+    return dict(q=_f32(q), qd=_f32(r.uniform(-1, 1, (n, 15))), tau=_f32(r.uniform(-1, 1, (n, 15))), params=dict(), mode=1)
+
+
+def humanoid_spherical(n, seed=SEED):
+    """humanoid_xyz_spherical.urdf on the plane: xyz prismatic root + one spherical joint (fixed-base emulation of a free
+    torso), the limbs revolute; heights such that 0-14 candidate points penetrate."""
+    r = np.random.default_rng(seed)
+    q = np.zeros((n, 28))
+    q[:, 0:2] = r.uniform(-0.3, 0.3, (n, 2))
+    q[:, 2] = r.uniform(0.6, 1.3, n)
+    q[:, 3:7] = _unit_quats(r, n, spread=0.2)
+    q[:, 7:] = r.uniform(-0.1, 0.1, (n, 21))
+    return dict(q=_f32(q), qd=_f32(r.uniform(-0.5, 0.5, (n, 27))), tau=_f32(r.uniform(-1, 1, (n, 27))),
+                params=dict(friction=1.0, keep_all_points=False), mode=2)
