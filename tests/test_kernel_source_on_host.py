@@ -88,3 +88,53 @@ def test_dual_number_jacobian_vs_central_differences(name, gen):
             Jr[:, j] = (f(xp) - f(xm)) / 2e-6
         ok.append(np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-4)
     assert np.mean(ok) >= (1.0 if mode != 2 else 0.8)
+
+
+def _stiff_spherical_model():
+    m = np.array(load_model(fixture_path("pendulum5spherical")))
+    for i in range(5):
+        m[16 + 13 + i * 34 + 32] = 3.0 + i        # Link::stiffness (acts through the quaternion's axis-angle, tiny_algebra.hpp:509-527)
+        m[16 + 13 + i * 34 + 33] = 0.2 + 0.1 * i  # Link::damping
+    return m
+
+
+def test_spherical_joint_stiffness_and_damping_vs_reference():
+    """forward_dynamics.hpp:56-109 with non-zero Link::stiffness / damping on spherical joints, incl. the small-angle branch of
+    quaternion_axis_angle, against the reference itself (the C oracle does not restate spherical joints)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    m = _stiff_spherical_model()
+    rs = ref.RefSim.from_model(m)
+    w = wl.pendulum5spherical(10, seed=5)
+    q = w["q"].copy()
+    q[0, :4] = [0, 0, 0, 1]
+    q[1, :4] = np.array([1e-5, 0, 0, 1]) / np.sqrt(1 + 1e-10)
+    q = q.astype(np.float32).astype(np.float64)
+    for mode in (0, 1):
+        out = emu.step(m, mode, q, w["qd"], w["tau"], precision=1)
+        for i in range(10):
+            r = rs.step(mode, q[i], w["qd"][i], w["tau"][i])
+            a, b = (out["qdd"][i], r["qdd"]) if mode == 0 else (np.concatenate([out["q"][i], out["qd"][i]]), np.concatenate([r["q"], r["qd"]]))
+            assert rel_err(a, b) <= TOL
+
+
+def test_spherical_dual_number_jacobian_vs_reference_differences():
+    """The differentiable step through spherical joints (quaternion coordinates as inputs): dual numbers in the kernel
+    source against central differences of the reference's own forward dynamics."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    m = _stiff_spherical_model()
+    rs = ref.RefSim.from_model(m)
+    w = wl.pendulum5spherical(3, seed=9)
+    J = emu.step(m, 0, w["q"], w["qd"], w["tau"], jacobian=True)["jac"]
+    assert J.shape == (3, 15, 20 + 15 + 15)
+    for e in range(3):
+        x0 = np.concatenate([w["q"][e], w["qd"][e], w["tau"][e]])
+        f = lambda x: rs.step(0, x[:20], x[20:35], x[35:])["qdd"]
+        Jr = np.zeros((15, x0.size))
+        for j in range(x0.size):
+            xp, xm = x0.copy(), x0.copy(); xp[j] += 1e-6; xm[j] -= 1e-6
+            Jr[:, j] = (f(xp) - f(xm)) / 2e-6
+        assert np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-4

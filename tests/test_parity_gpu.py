@@ -813,3 +813,36 @@ def test_laikago_jacobian_v2_abi(golden_dir):
         worst.append(np.max(np.abs(out[e] - Jr) / np.maximum(1.0, np.abs(Jr))))
     worst = np.array(worst)
     assert (worst <= 1e-4).mean() >= 0.8, worst
+
+
+def test_spherical_joints_stiffness_damping_and_jacobian(golden_dir):
+    """Spherical joints on the GPU beyond the goldens: non-zero Link::stiffness / damping (axis-angle of the joint quaternion,
+    forward_dynamics.hpp:69-75) against the reference compiled in place, and the dual-number Jacobian of the
+    forward dynamics against its central differences."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref did not travel")
+    m = np.array(load_model(fixture_path("pendulum5spherical")))
+    for i in range(5):
+        m[16 + 13 + i * 34 + 32] = 3.0 + i
+        m[16 + 13 + i * 34 + 33] = 0.2 + 0.1 * i
+    rs = ref.RefSim.from_model(m)
+    n = 16
+    w = wl.pendulum5spherical(n, seed=5)
+    sim = tds_b200.BatchSim(m, n)
+    assert sim.n_q == 20 and sim.n_qd == 15 and sim.precision == tds_b200.PREC_F64
+    fd = sim.step_host(0, w["q"], w["qd"], w["tau"])
+    st = sim.step_host(1, w["q"], w["qd"], w["tau"])
+    assert "tds_stepw_kernel" in sim.kernel_name()
+    for i in range(n):
+        r0 = rs.step(0, w["q"][i], w["qd"][i], w["tau"][i])
+        r1 = rs.step(1, w["q"][i], w["qd"][i], w["tau"][i])
+        assert rel_err(fd["qdd"][i], r0["qdd"]) <= TOL
+        assert rel_err(st["q"][i], r1["q"]) <= TOL and rel_err(st["qd"][i], r1["qd"]) <= TOL
+    J = sim.step_jacobian_host(0, w["q"][:], w["qd"], w["tau"])
+    assert J.shape == (n, 15, 50)
+    for e in range(2):
+        x0 = np.concatenate([w["q"][e], w["qd"][e], w["tau"][e]])
+        f = lambda x: rs.step(0, x[:20], x[20:35], x[35:])["qdd"]
+        Jr = _central_differences(f, x0)
+        assert np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-4

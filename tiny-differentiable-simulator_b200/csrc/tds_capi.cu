@@ -470,7 +470,7 @@ static const char* tds_model_error(int rc) {
   switch (rc) {
     case -1: return "not a flat model of this layout version (magic / size mismatch)";
     case -2: return "too many links, collision geoms or candidate contact points (TDS_MAX_LINKS / TDS_MAX_GEOMS / TDS_MAX_POINTS)";
-    case -3: return "unknown joint type, or a spherical joint with a stiffness (not implemented)";
+    case -3: return "unknown joint type";
     case -4: return "links are not ordered parent before child";
     case -5: return "collision geoms are not grouped by link";
     case -6: return "mesh collision shape against the ground plane: the contact stage implements sphere, capsule and box";

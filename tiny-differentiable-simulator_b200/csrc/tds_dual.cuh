@@ -53,6 +53,10 @@ template <typename T> TDS_D Dual<T> pow_t(Dual<T> a, Dual<T> b) {   // exponent:
   const T p = pow_t(a.v, b.v);
   return Dual<T>(p, a.v > T(0) ? b.v * p / a.v * a.d : T(0));
 }
+template <typename T> TDS_D Dual<T> atan2_t(Dual<T> y, Dual<T> x) {
+  const T r2 = x.v * x.v + y.v * y.v;
+  return Dual<T>(atan2_t(y.v, x.v), r2 > T(0) ? (x.v * y.d - y.v * x.d) / r2 : T(0));
+}
 template <typename T> TDS_D Dual<T> tanh_t(Dual<T> a) {
   const T t = tanh_t(a.v);
   return Dual<T>(t, (T(1) - t * t) * a.d);

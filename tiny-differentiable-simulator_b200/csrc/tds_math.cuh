@@ -258,6 +258,8 @@ TDS_D double min_t(double a, double b) { return fmin(a, b); }
 TDS_D double max_t(double a, double b) { return fmax(a, b); }
 TDS_D float pow_t(float a, float b) { return powf(a, b); }
 TDS_D double pow_t(double a, double b) { return pow(a, b); }
+TDS_D float atan2_t(float y, float x) { return atan2f(y, x); }
+TDS_D double atan2_t(double y, double x) { return atan2(y, x); }
 TDS_D float tanh_t(float a) { return tanhf(a); }
 TDS_D double tanh_t(double a) { return tanh(a); }
 // reciprocal / reciprocal square root of the fp32 solver quantities (1 / D of ABA, inverted Cholesky diagonals, 1 / A_ii):

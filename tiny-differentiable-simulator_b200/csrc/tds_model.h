@@ -82,9 +82,6 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     const double* l = links + (size_t)i * TDSM_LINK;
     int jt = (int)l[TDSM_L_JTYPE];
     if (jt < TDSJ_FIXED || jt > TDSJ_SPHERICAL) return -3;
-    // spherical joints (forward_dynamics.hpp:56-109): the stiffness term needs the quaternion's axis-angle
-    // (tiny_algebra.hpp:509-527); the URDF loader never sets a stiffness, so it is required to be 0 here
-    if (jt == TDSJ_SPHERICAL && l[TDSM_L_STIFFNESS] != 0.0) return -3;
     D->parent[i] = (int)l[TDSM_L_PARENT];
     if (D->parent[i] >= i) return -4;
     D->jtype[i] = jt;

@@ -373,6 +373,15 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
         for (int b = 0; b < 3; ++b) Dm[a][b] = dot(S[a], U[b]);
         u[a] = RA(tauv[(d0 + a) * ST]) - RA(M.damping[i]) * qdj[a] - dot(S[a], pA);
       }
+      if (M.stiffness[i] != 0.f) {   // tau -= stiffness * quaternion_axis_angle(q), forward_dynamics.hpp:69-74, tiny_algebra.hpp:509-527
+        const int q0 = M.q_idx[i];
+        const RC qx = RC(qv[q0 * ST]), qy = RC(qv[(q0 + 1) * ST]), qz = RC(qv[(q0 + 2) * ST]), qw = RC(qv[(q0 + 3) * ST]);
+        const RC nrm = sqrt_t(qx * qx + qy * qy + qz * qz);
+        const RC theta = RC(2) * atan2_t(nrm, qw);
+        const RC scaling = nrm < RC(1.220703125e-4) ? RC(1) / (RC(0.5) + theta * theta * RC(1.0 / 48.0)) : theta / nrm;   // eps^(1/4)
+        const RA k = RA(M.stiffness[i]);
+        u[0] -= k * RA(scaling * qx); u[1] -= k * RA(scaling * qy); u[2] -= k * RA(scaling * qz);
+      }
       RA Di[3][3];   // general 3 x 3 inverse (Matrix3::inverse)
       {
         const RA c0 = Dm[1][1] * Dm[2][2] - Dm[1][2] * Dm[2][1], c1 = Dm[1][2] * Dm[2][0] - Dm[1][0] * Dm[2][2], c2 = Dm[1][0] * Dm[2][1] - Dm[1][1] * Dm[2][0];
