@@ -1,0 +1,137 @@
+// TEST INFRASTRUCTURE - NOT PRODUCT CODE, never loaded by the package.
+//
+// The product's headline kernel, tiny-differentiable-simulator_b200/csrc/tds_steps.cu (model-specialised, one warp per tree
+// role, lane = environment), compiled FOR THE HOST.  A tile is executed environment by environment: for one lane, four host
+// threads play the four role warps and meet at a host barrier wherever the kernel has __syncthreads / __syncthreads_or
+// (the kernel's lanes never talk to each other, only its roles do, through shared memory).  As for tests/cpp/stepw_host.cpp:
+// a checker of the kernel SOURCE for a container without a GPU, not a fallback - nothing outside tests/ builds or loads it.
+//   g++ -std=c++17 -O1 -pthread -shared -fPIC -I<csrc> -I<include> -I/usr/local/cuda/include tests/cpp/steps_host.cpp -o tests/cpp/_steps_host.so
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define TDS_B200_EXACT_RCP 1
+#define TDS_STEPS_KERNEL_ONLY 1
+
+namespace emu {
+struct Dim { unsigned x, y, z; };
+thread_local Dim tIdx, bIdx;
+struct Barrier {   // reusable barrier for the four role threads, with an OR-reduction
+  std::mutex m; std::condition_variable cv; int count = 0, gen = 0, n = 4; int acc = 0, result = 0;
+  int sync_or(int pred) {
+    std::unique_lock<std::mutex> lk(m);
+    acc |= pred ? 1 : 0;
+    const int g = gen;
+    if (++count == n) { result = acc; acc = 0; count = 0; ++gen; cv.notify_all(); return result; }
+    cv.wait(lk, [&] { return gen != g; });
+    return result;
+  }
+};
+Barrier* g_bar = nullptr;
+int g_force_or = 0;   // 1: every __syncthreads_or is true, as when ANOTHER lane of the tile has a contact
+alignas(16) char* g_smem = nullptr;
+}  // namespace emu
+#define threadIdx emu::tIdx
+#define blockIdx emu::bIdx
+#define __syncthreads() ((void)emu::g_bar->sync_or(0))
+#define __syncthreads_or(p) (emu::g_bar->sync_or(((p) ? 1 : 0) | emu::g_force_or))
+#define __shfl_sync(mask, v, lane) (v)
+#define clock64() (0LL)
+#undef __shared__
+#define __shared__
+#undef __constant__
+#define __constant__
+#undef __grid_constant__
+#define __grid_constant__
+#undef __global__
+#define __global__
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#define smem_raw emu_smem_raw
+
+#include "../../tiny-differentiable-simulator_b200/csrc/tds_steps.cu"
+
+namespace tdss { alignas(16) char emu_smem_raw[256 * 1024]; }   // the tile's shared memory (block-scope extern in the kernel)
+
+namespace {
+template <class SP, typename RA, typename RC, typename RS, int VAR>
+void run(const SimParams& P, const EnvParams& E, const StepIO& io, int mode, int use_pd) {
+  const int tiles = (io.n + 31) / 32;
+  for (int t = 0; t < tiles; ++t)
+    for (int lane = 0; lane < 32; ++lane) {
+      if (t * 32 + lane >= io.n) continue;
+      emu::Barrier bar;
+      emu::g_bar = &bar;
+      std::thread th[4];
+      for (int role = 0; role < 4; ++role)
+        th[role] = std::thread([&, role] {
+          emu::tIdx = {(unsigned)(role * 32 + lane), 0, 0};
+          emu::bIdx = {(unsigned)t, 0, 0};
+          tdss::tds_step_spec_kernel<SP, RA, RC, RS, VAR, 1>(P, E, io, mode, use_pd);
+        });
+      for (auto& x : th) x.join();
+    }
+}
+}  // namespace
+
+extern "C" {
+// spec: 0 Laikago, 1 Ant.  params as in stepw_host.cpp (16 doubles); env: n_act, start_link, kp, kd, max_force, action_limit,
+// reward_kind, poses[n_act].  force_or: see emu::g_force_or.  precision 0 mixed / 1 fp64 / 2 fp32.  var: 0 general, 1 lean (full / no-contact step only).
+int tdsemu_steps(int spec, const double* params, const double* env, int precision, int var, int mode, int use_pd, int force_or, int n,
+                 const double* q, const double* qd, const double* tau, double* q_out, double* qd_out, double* qdd_out,
+                 double* reward, double* done) {
+  emu::g_force_or = force_or;
+  SimParams P;
+  memset(&P, 0, sizeof(P));
+  P.dt = params[0]; P.inv_dt = 1.0 / params[0];
+  for (int k = 0; k < 3; ++k) P.gravity[k] = params[1 + k];
+  P.friction = params[4]; P.restitution = params[5]; P.erp = params[6]; P.cfm = params[7];
+  P.pgs_iterations = (int)params[8]; P.keep_all_points = (int)params[9];
+  EnvParams E;
+  memset(&E, 0, sizeof(E));
+  const int n_q = spec == 0 ? SpecLaikago::N_Q : SpecAnt::N_Q, n_qd = spec == 0 ? SpecLaikago::N_QD : SpecAnt::N_QD;
+  const int n_act_model = spec == 0 ? SpecLaikago::N_ACT : SpecAnt::N_ACT;
+  if (env) {
+    E.n_act = (int)env[0]; E.start_link = (int)env[1];
+    E.kp = (float)env[2]; E.kd = (float)env[3]; E.max_force = (float)env[4]; E.action_limit = (float)env[5];
+    E.reward_kind = (int)env[6];
+    for (int k = 0; k < E.n_act; ++k) { E.initial_poses[k] = (float)env[7 + k]; E.act_link[k] = spec == 0 ? SpecLaikago::ACT_LINK[k] : SpecAnt::ACT_LINK[k]; }
+  }
+  const int floating = spec == 0 ? SpecLaikago::FLOATING : SpecAnt::FLOATING;
+  const int ns = (n + 31) & ~31, n_in = use_pd ? n_act_model : n_qd - (floating ? 6 : 0);
+  std::vector<float> sq((size_t)n_q * ns), sqd((size_t)n_qd * ns), st((size_t)n_in * ns, 0.f), oq(sq.size()), oqd(sqd.size()), oqdd(sqd.size()), orew(ns), odone(ns);
+  for (int e = 0; e < n; ++e) {
+    for (int k = 0; k < n_q; ++k) sq[(size_t)k * ns + e] = (float)q[(size_t)e * n_q + k];
+    for (int k = 0; k < n_qd; ++k) sqd[(size_t)k * ns + e] = (float)qd[(size_t)e * n_qd + k];
+    if (tau) for (int k = 0; k < n_in; ++k) st[(size_t)k * ns + e] = (float)tau[(size_t)e * n_in + k];
+  }
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.q_in = sq.data(); io.qd_in = sqd.data(); io.tau_in = st.data();
+  io.q_out = oq.data(); io.qd_out = oqd.data(); io.qdd_out = var == 0 ? oqdd.data() : nullptr;
+  io.reward = orew.data(); io.done = odone.data();
+  io.n = n; io.n_stride = ns;
+#define RUN(SP)                                                                                         \
+  do {                                                                                                  \
+    if (precision == 0) { if (var == 0) run<SP, float, double, float, 0>(P, E, io, mode, use_pd); else run<SP, float, double, float, 1>(P, E, io, mode, use_pd); }   \
+    else if (precision == 1) { if (var == 0) run<SP, double, double, double, 0>(P, E, io, mode, use_pd); else run<SP, double, double, double, 1>(P, E, io, mode, use_pd); } \
+    else { if (var == 0) run<SP, float, float, float, 0>(P, E, io, mode, use_pd); else run<SP, float, float, float, 1>(P, E, io, mode, use_pd); }                      \
+  } while (0)
+  if (spec == 0) RUN(SpecLaikago); else RUN(SpecAnt);
+#undef RUN
+  for (int e = 0; e < n; ++e) {
+    if (q_out) for (int k = 0; k < n_q; ++k) q_out[(size_t)e * n_q + k] = oq[(size_t)k * ns + e];
+    if (qd_out) for (int k = 0; k < n_qd; ++k) qd_out[(size_t)e * n_qd + k] = oqd[(size_t)k * ns + e];
+    if (qdd_out && var == 0) for (int k = 0; k < n_qd; ++k) qdd_out[(size_t)e * n_qd + k] = oqdd[(size_t)k * ns + e];
+    if (reward) reward[e] = orew[e];
+    if (done) done[e] = odone[e];
+  }
+  return 0;
+}
+}  // extern "C"

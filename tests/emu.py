@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE: ctypes binding of tests/cpp/_stepw_host.so - the product's generic step kernel (csrc/tds_stepw.cu)
-compiled for the host (see tests/cpp/stepw_host.cpp).  Used only by the CPU test-suite to execute the kernel SOURCE without a
+compiled for the host (see tests/cpp/stepw_host.cpp) and of tests/cpp/_steps_host.so - the same for the model-specialised kernel
+(csrc/tds_steps.cu, tests/cpp/steps_host.cpp).  Used only by the CPU test-suite to execute the kernel SOURCE without a
 GPU; the package never loads it."""
 import ctypes
 import os
@@ -68,4 +69,52 @@ def step(model, mode, q, qd, tau=None, precision=1, use_pd=False, env=None, jaco
         del out["contact_dist"]
     else:
         out["contact_dist"] = cdbuf[:n * rc].reshape(n, rc) if rc else np.zeros((n, 0))
+    return out
+
+
+# ---- the model-specialised kernel (csrc/tds_steps.cu) ------------------------------------------------------------------------------
+SO_S = os.path.join(HERE, "cpp", "_steps_host.so")
+SRC_S = os.path.join(HERE, "cpp", "steps_host.cpp")
+_lib_s = None
+SPEC = {"laikago": 0, "ant": 1}
+
+
+def build_spec():
+    gen = os.path.join(CSRC, "generated")
+    deps = [SRC_S] + [os.path.join(CSRC, f) for f in ("tds_steps.cu", "tds_math.cuh", "tds_types.h")] + \
+        [os.path.join(gen, f) for f in os.listdir(gen)]
+    if os.path.exists(SO_S) and all(os.path.getmtime(d) <= os.path.getmtime(SO_S) for d in deps):
+        return
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                           "-I/usr/local/cuda/include", SRC_S, "-o", SO_S + ".tmp"])
+    os.replace(SO_S + ".tmp", SO_S)
+
+
+def lib_spec():
+    global _lib_s
+    if _lib_s is None:
+        build_spec()
+        L = ctypes.CDLL(SO_S)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.tdsemu_steps.restype = ctypes.c_int
+        L.tdsemu_steps.argtypes = [ctypes.c_int, dp, dp] + [ctypes.c_int] * 6 + [dp] * 8
+        _lib_s = L
+    return _lib_s
+
+
+def step_spec(name, mode, q, qd, tau=None, precision=0, var=0, use_pd=False, env=None, other_lane_in_contact=False, dt=1e-3,
+              gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, erp=0.2, cfm=1e-5, pgs_iterations=1, keep_all_points=False):
+    """One step of every row of q / qd through the host-compiled specialised kernel of model `name` (state is carried in fp32
+    as on the device).  env = (n_act, start_link, kp, kd, max_force, action_limit, reward_kind, poses...) for use_pd; tau then
+    holds the actions.  var 0: general instance (qdd out), 1: lean instance.  Returns dict(q, qd, qdd, reward, done)."""
+    q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+    n, n_q, n_qd = q.shape[0], q.shape[1], qd.shape[1]
+    t = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+    params = np.array([dt, *gravity, friction, restitution, erp, cfm, pgs_iterations, int(keep_all_points)], dtype=np.float64)
+    e = None if env is None else np.ascontiguousarray(env, dtype=np.float64)
+    out = dict(q=np.zeros((n, n_q)), qd=np.zeros((n, n_qd)), qdd=np.zeros((n, n_qd)), reward=np.zeros(n), done=np.zeros(n))
+    rc = lib_spec().tdsemu_steps(SPEC[name], _dp(params), _dp(e), precision, var, mode, int(use_pd), int(other_lane_in_contact), n,
+                                 _dp(q), _dp(qd), _dp(t), _dp(out["q"]), _dp(out["qd"]), _dp(out["qdd"]), _dp(out["reward"]), _dp(out["done"]))
+    if rc:
+        raise RuntimeError(f"tdsemu_steps rc={rc}")
     return out

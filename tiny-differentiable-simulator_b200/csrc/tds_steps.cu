@@ -714,11 +714,19 @@ TDS_D void tile_body(char* const smem, const SimParams& P, const EnvParams& E, c
   // ---- pass 2 on one link: ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ------------------------------------
   // Subtree blocks of the joint-space inertia in registers: M_kk (lower triangle), C = coupling with the trunk dofs;
   // role 0 also holds the trunk block B.
-  RS Mkk[NODA * (NODA + 1) / 2], Cm[NODA * NTDA], Bm[NTRIA];
+  constexpr int NMKK = NODA * (NODA + 1) / 2, NCM = NODA * NTDA;
+  RS Mkk[NMKK];
+#ifdef TDS_STEPS_KERNEL_ONLY   // (g++ 13 mis-sizes the capture of this array in the nested generic lambdas of the host-compiled copy)
+  RS Cm_store[NCM];
+  RS* const Cm = Cm_store;
+#else
+  RS Cm[NCM];
+#endif
+  RS Bm[NTRIA];
 #pragma unroll
-  for (int i = 0; i < NODA * (NODA + 1) / 2; ++i) Mkk[i] = RS(0);
+  for (int i = 0; i < NMKK; ++i) Mkk[i] = RS(0);
 #pragma unroll
-  for (int i = 0; i < NODA * NTDA; ++i) Cm[i] = RS(0);
+  for (int i = 0; i < NCM; ++i) Cm[i] = RS(0);
 #pragma unroll
   for (int i = 0; i < NTRIA; ++i) Bm[i] = RS(0);
   Sv<RA> Ureg[SP::KMAX]; RA invDreg[SP::KMAX], ureg[SP::KMAX];
@@ -1657,14 +1665,19 @@ tds_step_spec_kernel(const __grid_constant__ SimParams P, const __grid_constant_
   // Programmatic dependent launch (back-to-back steps of one stream / graph): let the next step's grid be scheduled now
   // (single-wave batches: its CTAs take the second slot of every SM and park at their own wait), then wait for the
   // previous step's grid to complete and flush before the first read of the state.  Both are no-ops without the attribute.
+#ifndef TDS_STEPS_KERNEL_ONLY   // (the host-compiled copy of the kernel source in tests/cpp has no PTX)
   if (mode_flags & 512) asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   char* const smem = smem_raw + (size_t)sub * ((size_t)Lay<SP, RA, RC, RS>::TOTAL * 32 * 4);
   tile_body<SP, RA, RC, RS, VAR>(smem, P, E, io, mode_flags & 255, use_pd, role, (int)blockIdx.x * TPC + sub,
                                  (int)threadIdx.x - sub * 32 * TDS_TEAM_T);
+#ifndef TDS_STEPS_KERNEL_ONLY
   if (!(mode_flags & 512)) asm volatile("griddepcontrol.launch_dependents;");
+#endif
 }
 
+#ifndef TDS_STEPS_KERNEL_ONLY   // launchers / registry: not part of the host-compiled kernel source (tests/cpp/steps_host.cpp)
 template <class SP> struct SpecHost {
   static bool matches(const DevModel* D, const EnvParams* E) {
     if (D->n_links != SP::N_LINKS || D->n_q != SP::N_Q || D->n_qd != SP::N_QD || D->floating != SP::FLOATING) return false;
@@ -1751,6 +1764,7 @@ template <class SP> struct SpecHost {
     return (int)err;
   }
 };
+#endif  // TDS_STEPS_KERNEL_ONLY
 
 }  // namespace tdss
 
@@ -1768,6 +1782,7 @@ template <class SP> struct SpecHost {
 TDS_SPEC_TABLES(SpecLaikago, laikago)
 TDS_SPEC_TABLES(SpecAnt, ant)
 
+#ifndef TDS_STEPS_KERNEL_ONLY
 static const double k_spec_laikago_model[] = {
 #include "generated/laikago_model.inc"
 };
@@ -1800,3 +1815,4 @@ extern "C" int tds_launch_step_spec(int spec, const SimParams* P, const EnvParam
   if (spec == 1) return SpecHost<SpecAnt>::launch(P, E, io, mode, use_pd, precision, stream);
   return (int)cudaErrorInvalidValue;
 }
+#endif  // TDS_STEPS_KERNEL_ONLY
