@@ -1,9 +1,8 @@
 // TEST INFRASTRUCTURE - NOT PRODUCT CODE, never loaded by the package.
 //
 // The product's headline kernel, tiny-differentiable-simulator_b200/csrc/tds_steps.cu (model-specialised, one warp per tree
-// role, lane = environment), compiled FOR THE HOST.  A tile is executed environment by environment: for one lane, four host
-// threads play the four role warps and meet at a host barrier wherever the kernel has __syncthreads / __syncthreads_or
-// (the kernel's lanes never talk to each other, only its roles do, through shared memory).  As for tests/cpp/stepw_host.cpp:
+// role, lane = environment), compiled FOR THE HOST.  A tile (CTA) is executed by 128 host threads - four role warps x 32 lanes - that meet at a
+// host barrier wherever the kernel has __syncthreads / __syncthreads_or; shared memory is one static array.  As for tests/cpp/stepw_host.cpp:
 // a checker of the kernel SOURCE for a container without a GPU, not a fallback - nothing outside tests/ builds or loads it.
 //   g++ -std=c++17 -O1 -pthread -shared -fPIC -I<csrc> -I<include> -I/usr/local/cuda/include tests/cpp/steps_host.cpp -o tests/cpp/_steps_host.so
 #include <cuda_runtime.h>
@@ -60,33 +59,46 @@ alignas(16) char* g_smem = nullptr;
 namespace tdss { alignas(16) char emu_smem_raw[256 * 1024]; }   // the tile's shared memory (block-scope extern in the kernel)
 
 namespace {
+int g_whole_tile = 0;
+// whole_tile 1: a tile = one CTA of 128 host threads, all alive at once - exact (the host-layout instance stages the tile's actions /
+// observations cooperatively; __syncthreads_or is tile-wide) but slow on the host.  0: one lane at a time, its four role threads only
+// (the lanes of the device-layout instances never talk to each other, only the roles do; the tile-wide OR is covered by force_or).
 template <class SP, typename RA, typename RC, typename RS, int VAR>
 void run(const SimParams& P, const EnvParams& E, const StepIO& io, int mode, int use_pd) {
   const int tiles = (io.n + 31) / 32;
   for (int t = 0; t < tiles; ++t)
-    for (int lane = 0; lane < 32; ++lane) {
-      if (t * 32 + lane >= io.n) continue;
+    for (int lane0 = 0; lane0 < (g_whole_tile ? 1 : 32); ++lane0) {
+      if (!g_whole_tile && t * 32 + lane0 >= io.n) continue;
       emu::Barrier bar;
+      bar.n = g_whole_tile ? 128 : 4;
       emu::g_bar = &bar;
-      std::thread th[4];
-      for (int role = 0; role < 4; ++role)
-        th[role] = std::thread([&, role] {
-          emu::tIdx = {(unsigned)(role * 32 + lane), 0, 0};
+      std::vector<std::thread> th;
+      th.reserve(bar.n);
+      for (int i = 0; i < bar.n; ++i) {
+        const int tid = g_whole_tile ? i : i * 32 + lane0;
+        th.emplace_back([&, tid] {
+          emu::tIdx = {(unsigned)tid, 0, 0};
           emu::bIdx = {(unsigned)t, 0, 0};
           tdss::tds_step_spec_kernel<SP, RA, RC, RS, VAR, 1>(P, E, io, mode, use_pd);
         });
+      }
       for (auto& x : th) x.join();
     }
 }
 }  // namespace
 
 extern "C" {
-// spec: 0 Laikago, 1 Ant.  params as in stepw_host.cpp (16 doubles); env: n_act, start_link, kp, kd, max_force, action_limit,
-// reward_kind, poses[n_act].  force_or: see emu::g_force_or.  precision 0 mixed / 1 fp64 / 2 fp32.  var: 0 general, 1 lean (full / no-contact step only).
-int tdsemu_steps(int spec, const double* params, const double* env, int precision, int var, int mode, int use_pd, int force_or, int n,
+// spec: 0 Laikago, 1 Ant.  params: dt, g[3], friction, restitution, erp, cfm, pgs_iterations, keep_all (10 doubles);
+// env (null without PD): n_act, start_link, kp, kd, max_force, action_limit, reward_kind, auto_reset, poses[n_act], reset_q[n_q].
+// precision 0 mixed / 1 fp64 / 2 fp32.  var: 0 general (qdd, contact distances, link transforms), 1 lean, 2 lean with the host
+// layouts (actions [n][n_act] in, observations [n][n_q + n_qd] | reward [n] | done [n] out; needs whole_tile).
+// flags: bit 0 force_or (see emu::g_force_or), bit 1 whole_tile (see run()).  Outputs may be null.
+int tdsemu_steps(int spec, const double* params, const double* env, int precision, int var, int mode, int use_pd, int flags, int n,
                  const double* q, const double* qd, const double* tau, double* q_out, double* qd_out, double* qdd_out,
-                 double* reward, double* done) {
-  emu::g_force_or = force_or;
+                 double* reward, double* done, double* contact_dist, double* link_xf, double* obs_aos, double* obs_tail) {
+  emu::g_force_or = flags & 1;
+  g_whole_tile = (flags >> 1) & 1;
+  if (var == 2 && !g_whole_tile) return -1;
   SimParams P;
   memset(&P, 0, sizeof(P));
   P.dt = params[0]; P.inv_dt = 1.0 / params[0];
@@ -97,41 +109,57 @@ int tdsemu_steps(int spec, const double* params, const double* env, int precisio
   memset(&E, 0, sizeof(E));
   const int n_q = spec == 0 ? SpecLaikago::N_Q : SpecAnt::N_Q, n_qd = spec == 0 ? SpecLaikago::N_QD : SpecAnt::N_QD;
   const int n_act_model = spec == 0 ? SpecLaikago::N_ACT : SpecAnt::N_ACT;
+  const int n_cand = spec == 0 ? SpecLaikago::N_CAND : SpecAnt::N_CAND, n_links = spec == 0 ? SpecLaikago::N_LINKS : SpecAnt::N_LINKS;
   if (env) {
     E.n_act = (int)env[0]; E.start_link = (int)env[1];
     E.kp = (float)env[2]; E.kd = (float)env[3]; E.max_force = (float)env[4]; E.action_limit = (float)env[5];
-    E.reward_kind = (int)env[6];
-    for (int k = 0; k < E.n_act; ++k) { E.initial_poses[k] = (float)env[7 + k]; E.act_link[k] = spec == 0 ? SpecLaikago::ACT_LINK[k] : SpecAnt::ACT_LINK[k]; }
+    E.reward_kind = (int)env[6]; E.auto_reset = (int)env[7];
+    for (int k = 0; k < E.n_act; ++k) { E.initial_poses[k] = (float)env[8 + k]; E.act_link[k] = spec == 0 ? SpecLaikago::ACT_LINK[k] : SpecAnt::ACT_LINK[k]; }
+    for (int k = 0; k < n_q; ++k) E.reset_q[k] = (float)env[8 + E.n_act + k];
   }
   const int floating = spec == 0 ? SpecLaikago::FLOATING : SpecAnt::FLOATING;
-  const int ns = (n + 31) & ~31, n_in = use_pd ? n_act_model : n_qd - (floating ? 6 : 0);
+  const int ns = (n + 31) & ~31, n_in = use_pd ? n_act_model : n_qd - (floating ? 6 : 0), n_obs = n_q + n_qd;
   std::vector<float> sq((size_t)n_q * ns), sqd((size_t)n_qd * ns), st((size_t)n_in * ns, 0.f), oq(sq.size()), oqd(sqd.size()), oqdd(sqd.size()), orew(ns), odone(ns);
+  std::vector<float> ocd((size_t)n_cand * ns), oxf((size_t)n_links * 12 * ns), aos((size_t)n_in * ns, 0.f), oobs((size_t)n_obs * ns), otail(2 * (size_t)ns);
   for (int e = 0; e < n; ++e) {
     for (int k = 0; k < n_q; ++k) sq[(size_t)k * ns + e] = (float)q[(size_t)e * n_q + k];
     for (int k = 0; k < n_qd; ++k) sqd[(size_t)k * ns + e] = (float)qd[(size_t)e * n_qd + k];
-    if (tau) for (int k = 0; k < n_in; ++k) st[(size_t)k * ns + e] = (float)tau[(size_t)e * n_in + k];
+    if (tau) for (int k = 0; k < n_in; ++k) { st[(size_t)k * ns + e] = (float)tau[(size_t)e * n_in + k]; aos[(size_t)e * n_in + k] = (float)tau[(size_t)e * n_in + k]; }
   }
   StepIO io;
   memset(&io, 0, sizeof(io));
   io.q_in = sq.data(); io.qd_in = sqd.data(); io.tau_in = st.data();
   io.q_out = oq.data(); io.qd_out = oqd.data(); io.qdd_out = var == 0 ? oqdd.data() : nullptr;
   io.reward = orew.data(); io.done = odone.data();
+  if (var == 0) { io.contact_dist = contact_dist ? ocd.data() : nullptr; io.link_xf = link_xf ? oxf.data() : nullptr; }
+  if (var == 2) { io.act_aos = aos.data(); io.obs_aos = oobs.data(); io.obs_tail = otail.data(); }
   io.n = n; io.n_stride = ns;
-#define RUN(SP)                                                                                         \
-  do {                                                                                                  \
-    if (precision == 0) { if (var == 0) run<SP, float, double, float, 0>(P, E, io, mode, use_pd); else run<SP, float, double, float, 1>(P, E, io, mode, use_pd); }   \
-    else if (precision == 1) { if (var == 0) run<SP, double, double, double, 0>(P, E, io, mode, use_pd); else run<SP, double, double, double, 1>(P, E, io, mode, use_pd); } \
-    else { if (var == 0) run<SP, float, float, float, 0>(P, E, io, mode, use_pd); else run<SP, float, float, float, 1>(P, E, io, mode, use_pd); }                      \
+#define RUN3(SP, A, C, S)                                                                         \
+  do {                                                                                            \
+    if (var == 0) run<SP, A, C, S, 0>(P, E, io, mode, use_pd);                                    \
+    else if (var == 1) run<SP, A, C, S, 1>(P, E, io, mode, use_pd);                               \
+    else run<SP, A, C, S, 2>(P, E, io, mode, use_pd);                                             \
+  } while (0)
+#define RUN(SP)                                                                                   \
+  do {                                                                                            \
+    if (precision == 0) RUN3(SP, float, double, float);                                           \
+    else if (precision == 1) RUN3(SP, double, double, double);                                    \
+    else RUN3(SP, float, float, float);                                                           \
   } while (0)
   if (spec == 0) RUN(SpecLaikago); else RUN(SpecAnt);
 #undef RUN
+#undef RUN3
   for (int e = 0; e < n; ++e) {
     if (q_out) for (int k = 0; k < n_q; ++k) q_out[(size_t)e * n_q + k] = oq[(size_t)k * ns + e];
     if (qd_out) for (int k = 0; k < n_qd; ++k) qd_out[(size_t)e * n_qd + k] = oqd[(size_t)k * ns + e];
     if (qdd_out && var == 0) for (int k = 0; k < n_qd; ++k) qdd_out[(size_t)e * n_qd + k] = oqdd[(size_t)k * ns + e];
     if (reward) reward[e] = orew[e];
     if (done) done[e] = odone[e];
+    if (contact_dist && var == 0) for (int k = 0; k < n_cand; ++k) contact_dist[(size_t)e * n_cand + k] = ocd[(size_t)k * ns + e];
+    if (link_xf && var == 0) for (int k = 0; k < n_links * 12; ++k) link_xf[(size_t)e * n_links * 12 + k] = oxf[(size_t)k * ns + e];
+    if (obs_aos && var == 2) for (int k = 0; k < n_obs; ++k) obs_aos[(size_t)e * n_obs + k] = oobs[(size_t)e * n_obs + k];
+    if (obs_tail && var == 2) { obs_tail[e] = otail[e]; obs_tail[n + e] = otail[n + e]; }
   }
-  return 0;
+  return n_cand;
 }
 }  // extern "C"

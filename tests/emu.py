@@ -97,24 +97,47 @@ def lib_spec():
         L = ctypes.CDLL(SO_S)
         dp = ctypes.POINTER(ctypes.c_double)
         L.tdsemu_steps.restype = ctypes.c_int
-        L.tdsemu_steps.argtypes = [ctypes.c_int, dp, dp] + [ctypes.c_int] * 6 + [dp] * 8
+        L.tdsemu_steps.argtypes = [ctypes.c_int, dp, dp] + [ctypes.c_int] * 6 + [dp] * 12
         _lib_s = L
     return _lib_s
 
 
-def step_spec(name, mode, q, qd, tau=None, precision=0, var=0, use_pd=False, env=None, other_lane_in_contact=False, dt=1e-3,
-              gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, erp=0.2, cfm=1e-5, pgs_iterations=1, keep_all_points=False):
+def step_spec(name, mode, q, qd, tau=None, precision=0, var=0, use_pd=False, env=None, other_lane_in_contact=False, whole_tile=False,
+              auto_reset=False, reset_q=None, dt=1e-3, gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, erp=0.2, cfm=1e-5,
+              pgs_iterations=1, keep_all_points=False):
     """One step of every row of q / qd through the host-compiled specialised kernel of model `name` (state is carried in fp32
     as on the device).  env = (n_act, start_link, kp, kd, max_force, action_limit, reward_kind, poses...) for use_pd; tau then
-    holds the actions.  var 0: general instance (qdd out), 1: lean instance.  Returns dict(q, qd, qdd, reward, done)."""
+    holds the actions.  var 0: general instance (qdd, contact distances, link transforms), 1: lean instance, 2: lean instance
+    with the host layouts (whole_tile only).  whole_tile: 128 host threads per tile (exact, slow) instead of 4 per lane.
+    Returns dict(q, qd, qdd, reward, done[, contact_dist, link_xf][, obs, obs_reward, obs_done])."""
     q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
     n, n_q, n_qd = q.shape[0], q.shape[1], qd.shape[1]
     t = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
     params = np.array([dt, *gravity, friction, restitution, erp, cfm, pgs_iterations, int(keep_all_points)], dtype=np.float64)
-    e = None if env is None else np.ascontiguousarray(env, dtype=np.float64)
+    e = None
+    if env is not None:
+        env = np.asarray(env, dtype=np.float64)
+        rq = np.zeros(n_q) if reset_q is None else np.asarray(reset_q, dtype=np.float64)
+        e = np.ascontiguousarray(np.concatenate([env[:7], [float(auto_reset)], env[7:], rq]))
     out = dict(q=np.zeros((n, n_q)), qd=np.zeros((n, n_qd)), qdd=np.zeros((n, n_qd)), reward=np.zeros(n), done=np.zeros(n))
-    rc = lib_spec().tdsemu_steps(SPEC[name], _dp(params), _dp(e), precision, var, mode, int(use_pd), int(other_lane_in_contact), n,
-                                 _dp(q), _dp(qd), _dp(t), _dp(out["q"]), _dp(out["qd"]), _dp(out["qdd"]), _dp(out["reward"]), _dp(out["done"]))
-    if rc:
+    cd = np.zeros((n, 64)) if var == 0 else None
+    xf = np.zeros((n, 64 * 12)) if var == 0 else None
+    obs = np.zeros((n, n_q + n_qd)) if var == 2 else None
+    tail = np.zeros(2 * n) if var == 2 else None
+    rc = lib_spec().tdsemu_steps(SPEC[name], _dp(params), _dp(e), precision, var, mode, int(use_pd),
+                                 int(other_lane_in_contact) | (int(whole_tile or var == 2) << 1), n,
+                                 _dp(q), _dp(qd), _dp(t), _dp(out["q"]), _dp(out["qd"]), _dp(out["qdd"]), _dp(out["reward"]), _dp(out["done"]),
+                                 _dp(cd), _dp(xf), _dp(obs), _dp(tail))
+    if rc < 0:
         raise RuntimeError(f"tdsemu_steps rc={rc}")
+    if var == 0:
+        out["contact_dist"] = cd.ravel()[:n * rc].reshape(n, rc)
+        out["_xf_flat"] = xf.ravel()
+    if var == 2:
+        out.update(obs=obs, obs_reward=tail[:n], obs_done=tail[n:])
     return out
+
+
+def link_xf_of(out, n, n_links):
+    """[n][n_links][12] world transforms (R row-major 9, p 3) from step_spec(var=0)."""
+    return out["_xf_flat"][:n * n_links * 12].reshape(n, n_links, 12)

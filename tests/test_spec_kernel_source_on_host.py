@@ -121,3 +121,71 @@ def test_rollout_of_the_kernel_source_tracks_the_oracle():
         worst = max(worst, rel_err(out["q"], ref[:, :18]), rel_err(out["qd"], ref[:, 18:36]))
         q, qd = out["q"], out["qd"]
     assert worst <= 2 * TOL and np.all(np.isfinite(q))
+
+
+@pytest.mark.parametrize("name", ["laikago", "ant"])
+def test_contact_distances_and_link_transforms_of_the_general_instance(name):
+    """The general instance also reports what the reference exposes after a step: the signed distance of every candidate point
+    (golden contact_dist, from the reference's own contact list) and the world transform of every link (forward kinematics of
+    the step, against the oracle)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    model = load_model(fixture_path(name))
+    n, n_links = 16, int(model[1])
+    params = params_from_golden(g)
+    tau = g["tau"][:n, -int(model[4]):]
+    out = emu.step_spec(name, 2, g["q_in"][:n], g["qd_in"][:n], tau, precision=0, **params)
+    ref_d = np.stack(list(g["contact_dist"]))[:n]
+    assert out["contact_dist"].shape == ref_d.shape and np.max(np.abs(out["contact_dist"] - ref_d)) < 2e-6
+    xf = emu.link_xf_of(out, n, n_links)
+    P = port.make_params(**params)
+    q32, qd32, t32 = (a.astype(np.float32).astype(np.float64) for a in (g["q_in"][:n], g["qd_in"][:n], tau))
+    for i in range(n):
+        r = port.step(model, P, 2, q32[i], qd32[i], t32[i])
+        assert np.max(np.abs(xf[i] - r["link_xf"])) < 5e-6
+
+
+@pytest.mark.parametrize("name,n", [("laikago", 40), ("ant", 32)])
+def test_host_layout_instance_on_whole_tiles(name, n):
+    """The instance behind tds_b200_env_step_host: actions arrive environment-major, the tile stages them through shared memory,
+    and observations | reward | done leave environment-major with coalesced (float4 on full tiles, scalar on the ragged last tile)
+    stores - 128 host threads per tile.  Must equal the lean device-layout instance bit for bit."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    kw = dict(precision=0, use_pd=True, env=env_vector(name), **ENV[name]["params"])
+    a = emu.step_spec(name, 2, g["q_in"][:n], g["qd_in"][:n], g["action"][:n], var=1, whole_tile=True, **kw)
+    b = emu.step_spec(name, 2, g["q_in"][:n], g["qd_in"][:n], g["action"][:n], var=2, **kw)
+    n_q = g["q_in"].shape[1]
+    assert np.array_equal(b["obs"][:, :n_q], a["q"]) and np.array_equal(b["obs"][:, n_q:], a["qd"])
+    assert np.array_equal(b["q"], a["q"]) and np.array_equal(b["qd"], a["qd"])   # the SoA state is written as well
+    assert np.array_equal(b["obs_reward"], a["reward"]) and np.array_equal(b["obs_done"], a["done"])
+    ref = g["env_output_templated"][:n]
+    assert rel_err(b["obs"], ref[:, :2 * n_q]) <= TOL and np.array_equal(b["obs_done"], g["env_done"][:n].astype(np.float64))
+
+
+def test_tile_wide_contact_flag_whole_tile_equals_lane_by_lane():
+    """A tile mixing environments in contact with environments in the air: the tile-uniform "any contact" branch (whole tile, exact
+    __syncthreads_or) against each environment on its own."""
+    g = np.load(os.path.join(GOLDEN, "laikago.npz"))
+    n = 32
+    q = g["q_in"][:n].copy(); q[::2, 2] += 1.0   # every other robot lifted a metre: no contact
+    kw = dict(precision=0, var=1, use_pd=True, env=env_vector("laikago"), **ENV["laikago"]["params"])
+    a = emu.step_spec("laikago", 2, q, g["qd_in"][:n], g["action"][:n], whole_tile=True, **kw)
+    b = emu.step_spec("laikago", 2, q, g["qd_in"][:n], g["action"][:n], **kw)
+    assert np.max(np.abs(a["qd"] - b["qd"])) <= 1e-6 and np.max(np.abs(a["q"] - b["q"])) <= 1e-7
+
+
+def test_auto_reset_inside_the_kernel():
+    """laikago_environment2.h:130-171 + VectorizedEnvironment auto-reset: a robot reported done leaves the step at the reset pose
+    with zero velocity (the reward / done of the finished step are still reported)."""
+    g = np.load(os.path.join(GOLDEN, "laikago.npz"))
+    n = 8
+    q = g["q_in"][:n].copy(); qd = g["qd_in"][:n].copy()
+    q[:3, 3:6] = [1.2, 0.0, 0.0]   # rolled over: the up axis leaves the done cone
+    reset_q = envs.laikago_reset_pose()
+    kw = dict(precision=0, var=1, use_pd=True, env=env_vector("laikago"), **ENV["laikago"]["params"])
+    keep = emu.step_spec("laikago", 2, q, qd, g["action"][:n], **kw)
+    out = emu.step_spec("laikago", 2, q, qd, g["action"][:n], auto_reset=True, reset_q=reset_q, **kw)
+    assert np.array_equal(out["done"], keep["done"]) and np.array_equal(out["reward"], keep["reward"])
+    d = out["done"] > 0
+    assert d[:3].all() and not d.all()
+    assert np.allclose(out["q"][d], reset_q.astype(np.float32)) and np.all(out["qd"][d] == 0)
+    assert np.array_equal(out["q"][~d], keep["q"][~d]) and np.array_equal(out["qd"][~d], keep["qd"][~d])
