@@ -31,6 +31,9 @@
 #define TDSM_H_HASPLANE 7 /* static ground plane = multibody 0 (body A of every contact) */
 #define TDSM_H_PLANE_N 8  /* plane normal [3] (normalised, geometry.hpp:179) */
 #define TDSM_H_PLANE_C 11 /* plane constant (always 0: urdf_to_multi_body.hpp:266-271) */
+#define TDSM_H_NBODIES 12 /* 0 / 1: the links are ONE multibody.  K > 1: a world of K fixed-base multibodies, every root link
+                             (parent -1) starts one, links and coordinates of a multibody contiguous; geoms of different
+                             multibodies collide (src/world.hpp:206-282), geoms of one multibody never do */
 
 /* ---- floating/fixed base rigid-body inertia (MultiBody::base_rbi_) ---- */
 #define TDSM_BASE 13 /* mass, com[3], inertia[9] */

@@ -65,6 +65,15 @@ def lib():
         L.tdsref_link_transforms.argtypes = [vp, dp]
         L.tdsref_mass_matrix.argtypes = [vp, dp, dp]
         L.tdsref_point_jacobian.argtypes = [vp, dp, ctypes.c_int, dp, dp]
+        if hasattr(L, "tdsrefw_create"):
+            L.tdsrefw_create.restype = vp
+            L.tdsrefw_create.argtypes = [dp, ctypes.c_int]
+            L.tdsrefw_destroy.argtypes = [vp]
+            L.tdsrefw_num_bodies.restype = ctypes.c_int
+            L.tdsrefw_num_bodies.argtypes = [vp]
+            L.tdsrefw_set_params.argtypes = [vp, ctypes.c_double, dp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_double]
+            L.tdsrefw_step.argtypes = [vp, ctypes.c_int, dp, dp, dp, dp, dp, ip, ip, dp, ctypes.c_int]
         L.tdsref_laikago_create.restype = vp
         L.tdsref_laikago_create.argtypes = [ctypes.c_int]
         L.tdsref_laikago_destroy.argtypes = [vp]
@@ -191,6 +200,50 @@ class RefSim:
         J = np.zeros((3, self.n_qd))
         lib().tdsref_point_jacobian(self._h, _dp(q), link, _dp(p), _dp(J))
         return J
+
+
+class RefWorld:
+    """A reference World of several fixed-base multibodies (+ the plane) built from a merged flat model
+    (tds_b200.model.merge_models; oracle/ref/ref_world.cpp)."""
+
+    def __init__(self, model):
+        m = np.ascontiguousarray(model, dtype=np.float64)
+        self._L = lib()
+        self._h = self._L.tdsrefw_create(_dp(m), m.size)
+        if not self._h:
+            raise RuntimeError("tdsrefw_create failed")
+        self.n_q, self.n_qd = int(m[3]), int(m[4])
+        self.set_params()
+
+    def close(self):
+        if self._h:
+            self._L.tdsrefw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, dt=1e-3, gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, keep_all_points=False,
+                   pgs_iterations=1, erp=0.2, cfm=1e-5):
+        g = np.asarray(gravity, dtype=np.float64)
+        self._L.tdsrefw_set_params(self._h, dt, _dp(g), friction, restitution, int(keep_all_points), pgs_iterations, erp, cfm)
+
+    def step(self, mode, q, qd, tau=None, contact_cap=128):
+        """mode 2: full step of every multibody; 3: World::step alone.  Returns dict(q, qd, n_contacts, contact_idx
+        [(list, link_a, link_b)], contact_data [normal on b, point on a, point on b, distance])."""
+        q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+        t = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+        qo, qdo = np.zeros(self.n_q), np.zeros(self.n_qd)
+        nc = ctypes.c_int(0)
+        idx = np.zeros((contact_cap, 3), dtype=np.int32)
+        dat = np.zeros((contact_cap, 10))
+        with _quiet_stdout():
+            self._L.tdsrefw_step(self._h, mode, _dp(q), _dp(qd), _dp(t), _dp(qo), _dp(qdo), ctypes.byref(nc), _ip(idx), _dp(dat), contact_cap)
+        n = min(nc.value, contact_cap)
+        return dict(q=qo, qd=qdo, n_contacts=nc.value, contact_idx=idx[:n].copy(), contact_data=dat[:n].copy())
 
 
 class LaikagoRef:

@@ -1,0 +1,114 @@
+"""Worlds of several multibodies (contacts between multibodies, src/world.hpp:206-282 - sphere-sphere and
+capsule-sphere through the dispatcher, one LCP per list of World::mb_contacts_ solved one after the other, :351-355): the
+contact stage of the world-frame kernel csrc/tds_stepw.cu, executed on the CPU from its SOURCE (tests/cpp/stepw_host.cpp),
+against golden vectors of the reference (tests/golden/mb_*.npz, tests/golden/make_golden_multibody.py) and the live reference
+(oracle/_ref, oracle/ref/ref_world.cpp).  The GPU twins are in tests/test_parity_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+
+import tds_b200.workloads as wl
+from tds_b200.model import merge_models, model_dims
+from oracle import port
+import emu
+from test_kernel_source_on_host import GOLDEN, TOL, params_from_golden, rel_err
+
+
+@pytest.mark.parametrize("kind", wl.MULTIBODY_WORLDS)
+@pytest.mark.parametrize("precision", [0, 1])
+def test_multibody_golden_vectors_through_the_kernel_source(kind, precision):
+    g = np.load(os.path.join(GOLDEN, "mb_" + kind + ".npz"))
+    assert np.array_equal(g["model"], wl.multibody_world_model(kind))   # the committed model is the one the package builds
+    params = params_from_golden(g)
+    tol = TOL if precision == 1 else 3e-5
+    out = emu.step(g["model"], 2, g["q_in"], g["qd_in"], g["tau"], precision=precision, **params)
+    assert rel_err(out["q"], g["q_out"]) <= tol and rel_err(out["qd"], g["qd_out"]) <= tol
+    out = emu.step(g["model"], 3, g["q_in"], g["qd_in"], None, precision=precision, **params)   # World::step alone
+    assert rel_err(out["qd"], g["qd_world_step"]) <= tol
+    # the fixtures do exercise what they are for: contacts between multibodies, with and without plane contacts around them
+    pen = g["contact_data"][..., 9] < 0
+    lists = g["contact_idx"][..., 0]
+    n_plane_lists = int(g["model"][12])
+    assert np.any(pen & (lists >= n_plane_lists)) and np.any(pen & (lists >= 0) & (lists < n_plane_lists))
+
+
+@pytest.mark.parametrize("kind", wl.MULTIBODY_WORLDS)
+@pytest.mark.parametrize("sweep", [dict(), dict(pgs_iterations=5), dict(keep_all_points=True, friction=0.3),
+                                   dict(restitution=0.4, erp=0.1, cfm=1e-3, pgs_iterations=3), dict(dt=4e-3, gravity=(0.3, 0.0, -9.0))])
+def test_multibody_fresh_states_and_solver_parameters_vs_live_reference(kind, sweep):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    n = 48
+    w = wl.multibody_world(kind, n, seed=2024)
+    params = dict(w["params"]); params.update(sweep)
+    rw = ref.RefWorld(w["model"])
+    rw.set_params(**params)
+    for mode in (2, 3):
+        out = emu.step(w["model"], mode, w["q"], w["qd"], w["tau"], precision=1, **params)
+        for i in range(n):
+            r = rw.step(mode, w["q"][i], w["qd"][i], w["tau"][i])
+            assert rel_err(out["qd"][i], r["qd"]) <= TOL
+            if mode == 2:
+                assert rel_err(out["q"][i], r["q"]) <= TOL
+
+
+def test_multibodies_far_apart_step_like_separate_worlds():
+    """No contact between the multibodies: the merged world must reproduce each multibody stepped alone on the plane (the C
+    oracle, single multibody) - forest handling of the dynamics passes and the plane LCP shared by uncoupled multibodies."""
+    n = 32
+    a = wl.free_body_model(1.0, (0.036,) * 3, [("sphere", 0.3, (0, 0, 0))])
+    b = wl.free_body_model(2.0, (0.05, 0.05, 0.01), [("capsule", 0.15, 0.6, (0, 0, 0.05), wl._rot_y(0.3))], arm=(0.5, 0.3, 0.12))
+    world = merge_models([a, b])
+    assert model_dims(world)["n_links"] == 13 and int(world[12]) == 2
+    r = np.random.default_rng(5)
+    q = np.zeros((n, 13)); qd = r.uniform(-1, 1, (n, 13)); tau = r.uniform(-1, 1, (n, 13))
+    q[:, 0:2] = r.uniform(-0.3, 0.3, (n, 2)); q[:, 2] = r.uniform(0.2, 0.4, n); q[:, 3:6] = r.uniform(-1, 1, (n, 3))
+    q[:, 6:8] = 5.0 + r.uniform(-0.3, 0.3, (n, 2)); q[:, 8] = r.uniform(0.1, 0.5, n); q[:, 9:13] = r.uniform(-1, 1, (n, 4))
+    q, qd, tau = wl._f32(q), wl._f32(qd), wl._f32(tau)
+    params = dict(friction=0.7, keep_all_points=False)
+    out = emu.step(world, 2, q, qd, tau, precision=1, **params)
+    P = port.make_params(**params)
+    for i in range(n):
+        ra = port.step(a, P, 2, q[i, :6], qd[i, :6], tau[i, :6])
+        rb = port.step(b, P, 2, q[i, 6:], qd[i, 6:], tau[i, 6:])
+        assert rel_err(out["q"][i], np.concatenate([ra["q"], rb["q"]])) <= TOL
+        assert rel_err(out["qd"][i], np.concatenate([ra["qd"], rb["qd"]])) <= TOL
+
+
+def test_dual_number_jacobian_through_contacts_between_multibodies():
+    """d(q', qd') / d(q, qd, tau) of the full step by forward-mode dual numbers in the kernel against central differences of the
+    reference's step (environments whose contact set changes inside the difference stencil are excluded by the 80 % bar)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    n = 6
+    w = wl.multibody_world("capsule_sphere", n, seed=77)
+    rw = ref.RefWorld(w["model"])
+    rw.set_params(**w["params"])
+    J = emu.step(w["model"], 2, w["q"], w["qd"], w["tau"], jacobian=True, **w["params"])["jac"]
+    ok = []
+    for e in range(n):
+        def f(x):
+            r = rw.step(2, x[:12], x[12:24], x[24:])
+            return np.concatenate([r["q"], r["qd"]])
+        x0 = np.concatenate([w["q"][e], w["qd"][e], w["tau"][e]])
+        Jr = np.zeros((24, 36))
+        for j in range(36):
+            xp, xm = x0.copy(), x0.copy(); xp[j] += 1e-6; xm[j] -= 1e-6
+            Jr[:, j] = (f(xp) - f(xm)) / 2e-6
+        ok.append(np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-4)
+    assert np.mean(ok) >= 0.8
+
+
+def test_merge_models_refuses_what_the_reference_world_cannot_mean():
+    a = wl.free_body_model(1.0, (0.036,) * 3, [("sphere", 0.3, (0, 0, 0))])
+    with pytest.raises(ValueError):
+        merge_models([a])
+    floating = a.copy(); floating[2] = 1
+    with pytest.raises(ValueError):
+        merge_models([a, floating])
+    two_roots = merge_models([a, a])   # a world is not a multibody: it cannot be merged again as one
+    with pytest.raises(ValueError):
+        merge_models([two_roots, a])

@@ -474,6 +474,7 @@ static const char* tds_model_error(int rc) {
     case -4: return "links are not ordered parent before child";
     case -5: return "collision geoms are not grouped by link";
     case -6: return "mesh collision shape against the ground plane: the contact stage implements sphere, capsule and box";
+    case -7: return "world of several multibodies (TDSM_H_NBODIES): fixed base only, links of a multibody contiguous, as many root links as multibodies";
     default: return "unknown error";
   }
 }

@@ -175,6 +175,56 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     D->geom_begin[D->n_links + 1] = g;
     if (g != D->n_geoms) return -5;  // geoms not grouped by link
   }
+  {  // several multibodies in one world: candidate points between geoms of different multibodies, in the enumeration order of
+     // World::compute_contacts_multi_body_internal (src/world.hpp:212-281): pairs (a < b), links of a, geoms, links of b, geoms
+    const int want = (int)m[TDSM_H_NBODIES];
+    D->n_bodies = 1;
+    for (int i = 0; i < D->n_links; ++i) D->body_of[i] = 0;
+    for (int g = 0; g < D->n_geoms; ++g) D->g_wslot[g] = -1;
+    if (want > 1) {
+      if (D->floating) return -7;
+      int nbod = 0;
+      for (int i = 0; i < D->n_links; ++i) {
+        if (D->parent[i] < 0) D->body_of[i] = nbod++;
+        else D->body_of[i] = D->body_of[D->parent[i]];
+        if (i > 0 && D->body_of[i] < D->body_of[i - 1]) return -7;   // multibodies must be contiguous
+      }
+      if (nbod != want) return -7;
+      D->n_bodies = nbod;
+      int np = 0, ng = 0;
+      for (int a = 0; a < nbod; ++a)
+        for (int b = a + 1; b < nbod; ++b) {
+          const int before = np;
+          for (int ga = 0; ga < D->n_geoms; ++ga) {
+            if (D->g_link[ga] < 0 || D->body_of[D->g_link[ga]] != a) continue;
+            for (int gb = 0; gb < D->n_geoms; ++gb) {
+              if (D->g_link[gb] < 0 || D->body_of[D->g_link[gb]] != b) continue;
+              const int ta = D->g_type[ga], tb = D->g_type[gb];
+              // CollisionDispatcher, src/contact_point.hpp:468-501: sphere x sphere, capsule x sphere, and sphere x capsule through
+              // the swapped call; every other pair of shapes has no contact function
+              int kinds[2], nk = 0;
+              if (ta == TDSG_SPHERE && tb == TDSG_SPHERE) { kinds[0] = 0; nk = 1; }
+              else if (ta == TDSG_CAPSULE && tb == TDSG_SPHERE) { kinds[0] = 1; kinds[1] = -1; nk = 2; }
+              else if (ta == TDSG_SPHERE && tb == TDSG_CAPSULE) { kinds[0] = 2; kinds[1] = -2; nk = 2; }
+              for (int k = 0; k < nk; ++k) {
+                if (np >= TDS_MAX_PAIR_POINTS) return -2;
+                D->pp_ga[np] = ga; D->pp_gb[np] = gb; D->pp_kind[np] = kinds[k]; ++np;
+                if (D->g_wslot[ga] < 0) D->g_wslot[ga] = D->n_gw++;
+                if (D->g_wslot[gb] < 0) D->g_wslot[gb] = D->n_gw++;
+              }
+            }
+          }
+          if (np > before) {
+            if (ng >= TDS_MAX_PAIR_GROUPS) return -2;
+            D->pg_begin[ng++] = before;
+            if (np - before > D->max_pair_rows) D->max_pair_rows = np - before;
+          }
+        }
+      D->pg_begin[ng] = np;
+      D->n_pair_points = np; D->n_pair_groups = ng;
+      D->world_only = 1;   // a forest of multibodies: the tree decompositions of the other kernels assume one root chain
+    }
+  }
   for (int k = 0; k < 3; ++k) D->plane_n[k] = m[TDSM_H_PLANE_N + k];
   D->plane_c = m[TDSM_H_PLANE_C];
   double nb[3] = {-D->plane_n[0], -D->plane_n[1], -D->plane_n[2]};
@@ -248,20 +298,24 @@ TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, i
   w = even(w);
   D->x_con = w; w += D->max_contacts * 5 * rc;
   w = even(w);
+  D->x_gw = w; w += D->n_gw * 6 * rc;                       // world centre (+ capsule half axis) of the geoms of the pair stage
+  D->x_pcon = w; w += D->n_pair_points * 9 * rc;            // pair contacts: point on a [3], normal on b [3], distance, link a, link b
+  w = even(w);
   D->x_M = w; w += (D->nb * (D->nb + 1) / 2) * 9 * rs;
   w = even(w);
   D->x_dinv = w; w += D->nb * 6 * rs;
   w = even(w);
   D->x_w = w; w += n3 * rs;
   w = even(w);
-  D->x_conS = w; w += D->max_contacts * 6 * rs;
+  const int rows = D->max_contacts > D->max_pair_rows ? D->max_contacts : D->max_pair_rows;   // rows of the largest LCP
+  D->x_conS = w; w += rows * 6 * rs;
   w = even(w);
   // per-link: rigid inertia about the origin (10 RC), later reused for U (6 RA), invD, u ; v / c / a (6 RA)
   const int urec = (D->n_sph ? 30 : 8) * ra;                // spherical: U (18), D^-1 (9), u (3)
   const int first = 10 * rc > urec ? 10 * rc : urec;
   D->x_link_words = even(first + 6 * ra);
   const int link_region = D->n_links * D->x_link_words;
-  const int y_region = D->max_contacts * n3 * 3 * rs;
+  const int y_region = rows * n3 * 3 * rs;
   D->x_link = w;
   D->x_Y = w;
   w += link_region > y_region ? link_region : y_region;

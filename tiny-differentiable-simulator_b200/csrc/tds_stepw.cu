@@ -106,7 +106,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     for (int k = 0; k < 10; ++k) pc[k * ST] = RC(0);
   }
   const bool world_step = mode == MODE_WORLD;   // World::step(dt) on its own (src/world.hpp:302-363): q, qd in -> qd out
-  const bool want_contacts = (mode == MODE_FULL || world_step) && M.has_plane;
+  const bool want_contacts = (mode == MODE_FULL || world_step) && (M.has_plane || M.n_pair_points > 0);
   TDSW_PHASE();  // 1
 
   // ---- common-frame origin O (world coordinates) -----------------------------------------------------
@@ -139,6 +139,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
   const RC plane_off = dot(O, pn) - RC(M.plane_c);   // n.(O + x) - c = n.x + plane_off
   int n_active = 0, pt_index = 0;
   auto emit_point = [&](int li, const V3<RC>& pos, const RC rad) {
+    if (!M.has_plane) return;
     const RC dist = dot(pos, pn) + plane_off - rad;       // contact_plane_sphere, contact_point.hpp:112-116
     if (io.contact_dist && live) io.contact_dist[(size_t)pt_index * ns + e] = (float)val_of(dist);
     ++pt_index;
@@ -156,6 +157,11 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       if (ty != TDSG_SPHERE && ty != TDSG_CAPSULE && ty != TDSG_BOX) continue;
       const V3<RC> c = pr + mul(R, v3<RC>(RC(M.g_t[g][0]), RC(M.g_t[g][1]), RC(M.g_t[g][2])));
       const RC rad = RC(M.g_radius[g]);
+      if (M.g_wslot[g] >= 0) {         // kept for the contacts between multibodies (after this pass)
+        RC* pw = A.ptr<RC>(M.x_gw + M.g_wslot[g] * 6 * RCW);
+        st3<RC>(pw, ST, c);
+        if (ty == TDSG_CAPSULE) st3<RC>(pw + 3 * ST, ST, mul(R, v3<RC>(RC(M.g_half[g][0]), RC(M.g_half[g][1]), RC(M.g_half[g][2]))));
+      }
       if (ty == TDSG_SPHERE) emit_point(li, c, rad);
       else if (ty == TDSG_CAPSULE) {   // contact_plane_capsule, contact_point.hpp:128-161: end spheres at +L/2, then -L/2
         const V3<RC> half = mul(R, v3<RC>(RC(M.g_half[g][0]), RC(M.g_half[g][1]), RC(M.g_half[g][2])));
@@ -290,7 +296,43 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     }
     R_prev = Ri; p_prev = pi; v_prev = v;
   }
-  const bool any_contact = __any_sync(0xffffffffu, n_active > 0);
+  // ---- contacts between the multibodies of the world (world.hpp:206-282), group = ordered pair of multibodies -----------------------
+  // contact_sphere_sphere (contact_point.hpp:44-94) on sphere centres / capsule end spheres (contact_capsule_sphere, :406-438);
+  // sphere A x capsule B goes through the dispatcher's swapped call (:478-492): points exchanged, normal negated.
+  // Record: point on a [3] (relative to O), normal on b [3], distance, link a, link b; point on b = point on a - distance * normal.
+  int pgc[TDS_MAX_PAIR_GROUPS];
+  int n_pair_active = 0;
+  if (want_contacts && M.n_pair_points > 0) {
+    for (int g = 0; g < M.n_pair_groups; ++g) {
+      int cnt = 0;
+      for (int pt = M.pg_begin[g]; pt < M.pg_begin[g + 1]; ++pt) {
+        const int ga = M.pp_ga[pt], gb = M.pp_gb[pt], kind = M.pp_kind[pt];
+        const RC* wa = A.ptr<RC>(M.x_gw + M.g_wslot[ga] * 6 * RCW);
+        const RC* wb = A.ptr<RC>(M.x_gw + M.g_wslot[gb] * 6 * RCW);
+        V3<RC> ca = ld3<RC>(wa, ST), cb = ld3<RC>(wb, ST);
+        if (kind == 1) ca = ca + ld3<RC>(wa + 3 * ST, ST); else if (kind == -1) ca = ca - ld3<RC>(wa + 3 * ST, ST);
+        if (kind == 2) cb = cb + ld3<RC>(wb + 3 * ST, ST); else if (kind == -2) cb = cb - ld3<RC>(wb + 3 * ST, ST);
+        const bool swapped = kind == 2 || kind == -2;          // the contact function ran with (capsule on b, sphere on a)
+        const RC r1 = RC(swapped ? M.g_radius[gb] : M.g_radius[ga]), r2 = RC(swapped ? M.g_radius[ga] : M.g_radius[gb]);
+        const V3<RC> diff = swapped ? cb - ca : ca - cb;       // poseA.position - poseB.position of the call
+        const RC len = sqrt_t(dot(diff, diff));
+        const RC dist = len - (r1 + r2);
+        if (len > RC(1e-5) && dist < RC(0)) {                  // CONTACT_EPSILON; resolve_collision keeps distance < 0 (the others are zero rows)
+          const V3<RC> nrm = diff * (RC(1) / len);
+          const V3<RC> p1 = (swapped ? cb : ca) - nrm * r1;    // point_a_world of the call
+          RC* pr = A.ptr<RC>(M.x_pcon + n_pair_active * 9 * RCW);
+          if (swapped) { st3<RC>(pr, ST, p1 - nrm * dist); st3<RC>(pr + 3 * ST, ST, v3<RC>(-nrm.x, -nrm.y, -nrm.z)); }
+          else { st3<RC>(pr, ST, p1); st3<RC>(pr + 3 * ST, ST, nrm); }
+          pr[6 * ST] = dist;
+          pr[7 * ST] = RC(M.g_link[ga]);
+          pr[8 * ST] = RC(M.g_link[gb]);
+          ++n_pair_active; ++cnt;
+        }
+      }
+      pgc[g] = cnt;
+    }
+  }
+  const bool any_contact = __any_sync(0xffffffffu, n_active > 0 || n_pair_active > 0);
   TDSW_PHASE();  // 2
 
   // ---- pass 2: leaf -> root.  ABA (forward_dynamics.hpp:50-216) + CRBA (mass_matrix.hpp:39-125) ----------
@@ -631,45 +673,100 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       }
     }
     TDSW_PHASE();  // 5
-    const int max_active = __reduce_max_sync(0xffffffffu, n_active);
-    const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b
+    const V3<RC> nbv = v3<RC>(-pn.x, -pn.y, -pn.z);                     // world_normal_on_b of every plane contact
     const V3<RC> f1 = v3<RC>(RC(M.fr1[0]), RC(M.fr1[1]), RC(M.fr1[2]));
     const V3<RC> f2 = v3<RC>(RC(M.fr2[0]), RC(M.fr2[1]), RC(M.fr2[2]));
+    // One LCP per list of World::mb_contacts_, solved one after the other, each from the velocities the previous one left
+    // (world.hpp:351-355).  Group 0: every plane contact (the plane is multibody 0; its lists (plane, b) share no dof, so
+    // their Gauss-Seidel sweeps do not see each other and one LCP over all of them is the same arithmetic).  Groups 1..: the
+    // pairs of multibodies (a, b) in lexicographic order, rows J_b - J_a over the dofs of both.
+    int pbase = 0;   // first record of the current pair group
+    for (int grp = 0; grp <= M.n_pair_groups; ++grp) {
+    const int n_act = grp == 0 ? n_active : pgc[grp - 1];
+    const RC* const prec = A.ptr<RC>(M.x_pcon + pbase * 9 * RCW);       // records of this pair group
+    if (grp > 0) pbase += n_act;
+    const int max_active = __reduce_max_sync(0xffffffffu, n_act);
+    if (max_active == 0) {
+      if (grp == 0) { TDSW_PHASE(); TDSW_PHASE(); }
+      continue;
+    }
     for (int c = 0; c < max_active; ++c) {
-      if (c < n_active) {
-        const RC* pc = A.ptr<RC>(M.x_con + c * 5 * RCW);
-        RS* const Y = A.ptr<RS>(M.x_Y) + c * n3 * 3 * ST;       // [dof k][rhs] : element (3k + rhs)
-        const V3<RC> xc = ld3<RC>(pc, ST);
-        const RC dist = pc[3 * ST];
-        const int L = (int)val_of(pc[4 * ST]);
-        for (int k = 0; k < 3 * n3; ++k) Y[k * ST] = RS(0);
-        V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));                  // vel_b = J qd
-        if (M.floating) {  // jacobian.hpp:39-58 with r = x_c (O is the base origin)
-          const V3<RC> cols[6] = {v3<RC>(RC(0), -xc.z, xc.y), v3<RC>(xc.z, RC(0), -xc.x), v3<RC>(-xc.y, xc.x, RC(0)),
-                                  v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            Y[(3 * k) * ST] = RS(dot(nbv, cols[k])); Y[(3 * k + 1) * ST] = RS(dot(f1, cols[k])); Y[(3 * k + 2) * ST] = RS(dot(f2, cols[k]));
-            vel = vel + cols[k] * RC(qdv[k * ST]);
+      if (c < n_act) {
+        if (grp == 0) {
+          const RC* pc = A.ptr<RC>(M.x_con + c * 5 * RCW);
+          RS* const Y = A.ptr<RS>(M.x_Y) + c * n3 * 3 * ST;       // [dof k][rhs] : element (3k + rhs)
+          const V3<RC> xc = ld3<RC>(pc, ST);
+          const RC dist = pc[3 * ST];
+          const int L = (int)val_of(pc[4 * ST]);
+          for (int k = 0; k < 3 * n3; ++k) Y[k * ST] = RS(0);
+          V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));                  // vel_b = J qd
+          if (M.floating) {  // jacobian.hpp:39-58 with r = x_c (O is the base origin)
+            const V3<RC> cols[6] = {v3<RC>(RC(0), -xc.z, xc.y), v3<RC>(xc.z, RC(0), -xc.x), v3<RC>(-xc.y, xc.x, RC(0)),
+                                    v3<RC>(RC(1), RC(0), RC(0)), v3<RC>(RC(0), RC(1), RC(0)), v3<RC>(RC(0), RC(0), RC(1))};
+  #pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              Y[(3 * k) * ST] = RS(dot(nbv, cols[k])); Y[(3 * k + 1) * ST] = RS(dot(f1, cols[k])); Y[(3 * k + 2) * ST] = RS(dot(f2, cols[k]));
+              vel = vel + cols[k] * RC(qdv[k * ST]);
+            }
           }
-        }
-        for (int j = L; j >= 0; j = M.parent[j]) {  // jacobian.hpp:63-80: column = S_j evaluated at the contact point
-          const int nc = n_cols(j);
-          for (int cj = 0; cj < nc; ++cj) {
-            const Sv<RC> S = S_col(j, cj);
-            const V3<RC> col = S.bot + cross(S.top, xc);
-            const int qj = M.qd_idx[j] + cj;
-            Y[(3 * qj) * ST] = RS(dot(nbv, col)); Y[(3 * qj + 1) * ST] = RS(dot(f1, col)); Y[(3 * qj + 2) * ST] = RS(dot(f2, col));
-            vel = vel + col * RC(qdv[qj * ST]);
+          for (int j = L; j >= 0; j = M.parent[j]) {  // jacobian.hpp:63-80: column = S_j evaluated at the contact point
+            const int nc = n_cols(j);
+            for (int cj = 0; cj < nc; ++cj) {
+              const Sv<RC> S = S_col(j, cj);
+              const V3<RC> col = S.bot + cross(S.top, xc);
+              const int qj = M.qd_idx[j] + cj;
+              Y[(3 * qj) * ST] = RS(dot(nbv, col)); Y[(3 * qj + 1) * ST] = RS(dot(f1, col)); Y[(3 * qj + 2) * ST] = RS(dot(f2, col));
+              vel = vel + col * RC(qdv[qj * ST]);
+            }
           }
+          // rel_vel = vel_a - vel_b = -vel ; mb_constraint_solver.hpp:299-345
+          RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;   // b[3], x[3]
+          if (P.contact_model == 1) cs[0] = RS(dot(nbv, vel));   // spring-damper: approach speed n_b . v_b
+          else cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
+          cs[ST] = RS(dot(f1, vel));
+          cs[2 * ST] = RS(dot(f2, vel));
+          cs[3 * ST] = RS(0); cs[4 * ST] = RS(0); cs[5 * ST] = RS(0);
+        } else {
+          // a contact between two multibodies: point on a / on b at the links la / lb, normal on b, friction directions of
+          // plane_space(normal) (mb_constraint_solver.hpp:359-363, 506-520)
+          const RC* pc = prec + c * 9 * ST;
+          RS* const Y = A.ptr<RS>(M.x_Y) + c * n3 * 3 * ST;
+          const V3<RC> xa = ld3<RC>(pc, ST), nrm = ld3<RC>(pc + 3 * ST, ST);
+          const RC dist = pc[6 * ST];
+          const int la = (int)val_of(pc[7 * ST]), lb = (int)val_of(pc[8 * ST]);
+          const V3<RC> xb = xa - nrm * dist;
+          V3<RC> g1, g2;
+          plane_space_t(nrm, g1, g2);
+          for (int k = 0; k < 3 * n3; ++k) Y[k * ST] = RS(0);
+          V3<RC> vel = v3<RC>(RC(0), RC(0), RC(0));                  // vel_b - vel_a = -rel_vel
+          for (int j = lb; j >= 0; j = M.parent[j]) {
+            const int nc = n_cols(j);
+            for (int cj = 0; cj < nc; ++cj) {
+              const Sv<RC> S = S_col(j, cj);
+              const V3<RC> col = S.bot + cross(S.top, xb);
+              const int qj = M.qd_idx[j] + cj;
+              Y[(3 * qj) * ST] = RS(dot(nrm, col)); Y[(3 * qj + 1) * ST] = RS(dot(g1, col)); Y[(3 * qj + 2) * ST] = RS(dot(g2, col));
+              vel = vel + col * RC(qdv[qj * ST]);
+            }
+          }
+          for (int j = la; j >= 0; j = M.parent[j]) {
+            const int nc = n_cols(j);
+            for (int cj = 0; cj < nc; ++cj) {
+              const Sv<RC> S = S_col(j, cj);
+              const V3<RC> col = S.bot + cross(S.top, xa);
+              const int qj = M.qd_idx[j] + cj;
+              Y[(3 * qj) * ST] = RS(-dot(nrm, col)); Y[(3 * qj + 1) * ST] = RS(-dot(g1, col)); Y[(3 * qj + 2) * ST] = RS(-dot(g2, col));
+              vel = vel - col * RC(qdv[qj * ST]);
+            }
+          }
+          RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;   // b[3], x[3]
+          if (P.contact_model == 1) cs[0] = RS(dot(nrm, vel));
+          else cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nrm, vel) - RC(P.erp) * dist / RC(P.dt));
+          cs[ST] = RS(dot(g1, vel));
+          cs[2 * ST] = RS(dot(g2, vel));
+          cs[3 * ST] = RS(0); cs[4 * ST] = RS(0); cs[5 * ST] = RS(0);
         }
-        // rel_vel = vel_a - vel_b = -vel ; mb_constraint_solver.hpp:299-345
-        RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;   // b[3], x[3]
-        if (P.contact_model == 1) cs[0] = RS(dot(nbv, vel));   // spring-damper: approach speed n_b . v_b
-        else cs[0] = RS((RC(1) + RC(P.restitution)) * dot(nbv, vel) - RC(P.erp) * dist / RC(P.dt));
-        cs[ST] = RS(dot(f1, vel));
-        cs[2 * ST] = RS(dot(f2, vel));
-        cs[3 * ST] = RS(0); cs[4 * ST] = RS(0); cs[5 * ST] = RS(0);
+        RS* const Y = A.ptr<RS>(M.x_Y) + c * n3 * 3 * ST;
         // Y <- L^-1 Y (blocked forward substitution, 3 right-hand sides)
         for (int bi = 0; bi < nb; ++bi) {
           B9<RS> a = ldb<RS>(Y + bi * 9 * ST, ST);
@@ -678,7 +775,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
         }
       }
     }
-    TDSW_PHASE();  // 6
+    if (grp == 0) TDSW_PHASE();  // 6
     // matrix-free projected Gauss-Seidel on w = Y p; row order normals | friction-1 | friction-2
     // (solve_pgs, mb_constraint_solver.hpp:101-142; bounds :417-436)
     for (int k = 0; k < n3; ++k) wv[k * ST] = RS(0);
@@ -689,9 +786,9 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       //   p_t = dt mu f_n tanh(|v_t| / v_transition) v_t / |v_t|   along the two friction directions
       // accumulated into w = Y p like the Gauss-Seidel impulses; the back substitution below is shared.
       for (int c = 0; c < max_active; ++c) {
-        if (c < n_active) {
+        if (c < n_act) {
           const RS* cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;
-          const RS x = RS(-A.ptr<RC>(M.x_con + c * 5 * RCW)[3 * ST]);
+          const RS x = RS(-(grp == 0 ? A.ptr<RC>(M.x_con + c * 5 * RCW)[3 * ST] : prec[(c * 9 + 6) * ST]));
           const RS vn = cs[0], v1 = cs[ST], v2 = cs[2 * ST];
           const RS xn = pow_t(x, RS(P.exponent_n));
           RS fn = RS(P.spring_k) * xn + RS(P.damper_d) * xn * vn;
@@ -708,7 +805,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
     for (int it = 0; it < P.pgs_iterations; ++it) {
       for (int blk = 0; blk < 3; ++blk) {
         for (int c = 0; c < max_active; ++c) {
-          if (c < n_active) {
+          if (c < n_act) {
             RS* const cs = A.ptr<RS>(M.x_conS) + c * 6 * ST;
             const RS* y = A.ptr<RS>(M.x_Y) + (c * n3 * 3 + blk) * ST;     // element k at y[3k * ST]
             RS yy0 = RS(0), yy1 = RS(0), yy2 = RS(0), yw0 = RS(0), yw1 = RS(0), yw2 = RS(0);
@@ -741,7 +838,7 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
         }
       }
     }
-    TDSW_PHASE();  // 7
+    if (grp == 0) TDSW_PHASE();  // 7
     // qd_b -= M^-1 Jc^T p = L^-T w   (mb_constraint_solver.hpp:476-497), blocked back substitution
     for (int bi = nb - 1; bi >= 0; --bi) {
       RS a0 = wv[(3 * bi) * ST], a1 = wv[(3 * bi + 1) * ST], a2 = wv[(3 * bi + 2) * ST];
@@ -758,8 +855,9 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       const RS z2 = li.i22 * a2;
       wv[(3 * bi) * ST] = z0; wv[(3 * bi + 1) * ST] = z1; wv[(3 * bi + 2) * ST] = z2;
     }
-    if (n_active > 0)
+    if (n_act > 0)
       for (int k = 0; k < n; ++k) qdv[k * ST] = RQ(RS(qdv[k * ST]) - wv[k * ST]);
+    }   // groups
   }
   TDSW_PHASE();  // 8
 

@@ -7,6 +7,8 @@
 #define TDS_MAX_VIS 24
 #define TDS_MAX_ACT 32
 #define TDS_MAX_POINTS 64   // candidate contact points of a model (sphere 1, capsule 2, box 8 per geom)
+#define TDS_MAX_PAIR_POINTS 64   // candidate contact points between geoms of DIFFERENT multibodies of one world
+#define TDS_MAX_PAIR_GROUPS 10   // ordered multibody pairs (a < b) that have such candidates (5 multibodies: 10 pairs)
 
 // link flags
 #define TDS_LF_PARENT_ADJ 1   // parent == i-1  -> deltas are carried in registers
@@ -64,7 +66,20 @@ struct DevModel {
   int s3_slot[TDS_MAX_LINKS];
   int x_S3;
   int world_only;   // the model uses features only the generic world-frame kernel (tds_stepw.cu) implements
-                    // (box shapes, spherical joints): the decomposed / specialised kernels refuse it
+                    // (box shapes, spherical joints, several multibodies): the decomposed / specialised kernels refuse it
+  // ---- several multibodies in one world (header field TDSM_H_NBODIES > 1): every root link starts a multibody ------------
+  // Contacts between geoms of different multibodies (world.hpp:206-282) are solved pair of multibodies after pair of
+  // multibodies, after the plane contacts (the plane is multibody 0 of the reference's world): world.hpp:351-355.
+  int n_bodies;
+  int body_of[TDS_MAX_LINKS];            // multibody of a link
+  int n_pair_points, n_pair_groups;
+  int pg_begin[TDS_MAX_PAIR_GROUPS + 1]; // candidate points of group g: [pg_begin[g], pg_begin[g + 1]), groups in (a, b) lexicographic order
+  int pp_ga[TDS_MAX_PAIR_POINTS];        // geom on the lower-indexed multibody (body A of the contact)
+  int pp_gb[TDS_MAX_PAIR_POINTS];        // geom on the other one (body B)
+  int pp_kind[TDS_MAX_PAIR_POINTS];      // 0 sphere-sphere; +-1 capsule A (end +-L/2) x sphere B; +-2 sphere A x capsule B (dispatcher swap)
+  int g_wslot[TDS_MAX_GEOMS];            // slot of the geom's world centre (+ capsule half axis) kept for the pair stage, -1: none
+  int n_gw, max_pair_rows;               // slots; largest group (rows of the pair LCP)
+  int x_gw, x_pcon;                      // arena: [n_gw][6] RC, [n_pair_points][9] RC
   // static ground plane (multibody 0)
   double plane_n[3];
   double plane_c;

@@ -23,6 +23,21 @@ struct Arena {
   }
 };
 
+// MultiBodyConstraintSolver::plane_space (src/mb_constraint_solver.hpp:506-520) for a per-contact normal, as the reference
+// evaluates it: k = sqrt(a) (not its reciprocal) and p.z = n.y k in both branches.
+template <typename T> TDS_D void plane_space_t(const V3<T>& n, V3<T>& p, V3<T>& q) {
+  const T n_sqr = n.z * n.z;
+  const bool mz = n_sqr > T(0.5);
+  const T a = n.y * n.y + (mz ? n_sqr : n.x * n.x);
+  const T k = sqrt_t(a);
+  p.x = mz ? T(0) : -n.y * k;
+  p.y = mz ? -n.z * k : n.x * k;
+  p.z = n.y * k;
+  q.x = mz ? a * k : -n.z * p.y;
+  q.y = mz ? -n.x * p.z : n.z * p.x;
+  q.z = mz ? n.x * p.y : a * k;
+}
+
 template <typename T> TDS_D void st3(T* p, int s, const V3<T>& v) { p[0] = v.x; p[s] = v.y; p[2 * s] = v.z; }
 template <typename T> TDS_D V3<T> ld3(const T* p, int s) { return v3<T>(p[0], p[s], p[2 * s]); }
 template <typename T> TDS_D void st6(T* p, int s, const Sv<T>& v) { st3(p, s, v.top); st3(p + 3 * s, s, v.bot); }

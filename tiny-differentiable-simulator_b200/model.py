@@ -38,6 +38,52 @@ def model_dims(model):
                 n_vis=int(m[6]), has_plane=int(m[7]))
 
 
+def merge_models(models):
+    """A world of several multibodies: the flat models of K fixed-base multibodies (each ONE root link, e.g. the reference's
+    `*_xyz_xyzrot.urdf` free-body emulations) -> one flat model with header field TDSM_H_NBODIES = K
+    (include/tds_b200_model.h).  Mirrors a reference World holding the plane (if any model has one: multibody 0) and the K
+    multibodies in the order given: geoms of different multibodies collide (src/world.hpp:206-282: sphere-sphere,
+    capsule-sphere), geoms of one multibody never do; coordinates q / qd are the concatenation in the same order."""
+    ms = [np.asarray(m, dtype=np.float64) for m in models]
+    if len(ms) < 2:
+        raise ValueError("merge_models needs at least two multibodies")
+    dims = [model_dims(m) for m in ms]
+    if any(d["floating"] for d in dims):
+        raise ValueError("merge_models: fixed-base multibodies only (emulate a free body by prismatic + revolute / spherical joints)")
+    head = np.zeros(HEADER)
+    head[0] = MAGIC
+    links, base_geoms, link_geoms, vis = [], [], [], []
+    lo = qo = qdo = 0
+    for m, d in zip(ms, dims):
+        L0 = HEADER + BASE
+        G0 = L0 + d["n_links"] * LINK
+        V0 = G0 + d["n_geoms"] * GEOM
+        l = m[L0:G0].reshape(d["n_links"], LINK).copy()
+        if int(np.sum(l[:, 0] < 0)) != 1:
+            raise ValueError("merge_models: every multibody must have exactly one root link")
+        l[:, 0] = np.where(l[:, 0] >= 0, l[:, 0] + lo, -1)
+        moving = l[:, 1] >= 0          # JOINT_FIXED = -1 carries no coordinate
+        l[moving, 2] += qo
+        l[moving, 3] += qdo
+        links.append(l)
+        g = m[G0:V0].reshape(d["n_geoms"], GEOM).copy()
+        base_geoms.append(g[g[:, 0] < 0])
+        gl = g[g[:, 0] >= 0]
+        gl[:, 0] += lo
+        link_geoms.append(gl)
+        v = m[V0:V0 + d["n_vis"] * VIS].reshape(d["n_vis"], VIS).copy()
+        v[:, 0] = np.where(v[:, 0] >= 0, v[:, 0] + lo, -1)
+        vis.append(v)
+        lo += d["n_links"]; qo += d["n_q"]; qdo += d["n_qd"]
+        if d["has_plane"] and not head[7]:
+            head[7] = 1
+            head[8:12] = m[8:12]
+    geoms = np.concatenate(base_geoms + link_geoms) if (base_geoms or link_geoms) else np.zeros((0, GEOM))
+    vis = np.concatenate(vis) if vis else np.zeros((0, VIS))
+    head[1], head[2], head[3], head[4], head[5], head[6], head[12] = lo, 0, qo, qdo, len(geoms), len(vis), len(ms)
+    return np.concatenate([head, ms[0][HEADER:HEADER + BASE], np.concatenate(links).ravel(), geoms.ravel(), vis.ravel()])
+
+
 def save_model(path, model, meta=None):
     with open(path, "w") as f:
         json.dump({"layout": "tds_b200_model.h", "meta": meta or {}, "model": [float(v) for v in model]}, f)

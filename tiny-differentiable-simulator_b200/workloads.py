@@ -143,3 +143,113 @@ def humanoid_spherical(n, seed=SEED):
     q[:, 7:] = r.uniform(-0.1, 0.1, (n, 21))
     return dict(q=_f32(q), qd=_f32(r.uniform(-0.5, 0.5, (n, 27))), tau=_f32(r.uniform(-1, 1, (n, 27))),
                 params=dict(friction=1.0, keep_all_points=False), mode=2)
+
+
+# ---- worlds of several multibodies (contacts between multibodies: src/world.hpp:206-282) ----------------------------------------
+def free_body_model(mass, inertia_diag, geoms, plane=True, arm=None, spherical=False):
+    """Flat model (include/tds_b200_model.h) of one fixed-base multibody emulating a free rigid body the way the reference's
+    `*_xyz_xyzrot.urdf` files do: three massless prismatic links (x, y, z), then three revolute links (x, y, z) - or ONE
+    spherical joint - the last of which carries the mass and the collision shapes.
+    geoms: ("sphere", radius, (x, y, z)) or ("capsule", radius, length, (x, y, z), R 3x3 row-major).
+    arm: optional (length, mass, radius): a further link on a revolute y joint at the body origin carrying a sphere at its tip."""
+    from .model import GEOM, HEADER, BASE, LINK, MAGIC
+    links, gl = [], []
+    eye = np.eye(3).ravel()
+
+    def link(parent, jtype, qi, qdi, axis, t=(0, 0, 0), m=0.0, com=(0, 0, 0), inertia=(0, 0, 0)):
+        r = np.zeros(LINK)
+        r[0], r[1], r[2], r[3] = parent, jtype, qi, qdi
+        r[4:7], r[7:16], r[16:19] = axis, eye, t
+        r[19], r[20:23] = m, com
+        r[23:32] = np.diag(inertia).ravel()
+        links.append(r)
+
+    for k in range(3):
+        link(k - 1, k, k, k, np.eye(3)[k])                       # JOINT_PRISMATIC_X / Y / Z
+    if spherical:
+        link(2, 8, 3, 3, (0, 0, 0), m=mass, inertia=inertia_diag)   # JOINT_SPHERICAL: q = quaternion xyzw
+        nq, nqd = 7, 6
+    else:
+        for k in range(3):
+            last = k == 2
+            link(2 + k, 4 + k, 3 + k, 3 + k, np.eye(3)[k], m=mass if last else 0.0, inertia=inertia_diag if last else (0, 0, 0))
+        nq, nqd = 6, 6
+    body = len(links) - 1
+    for g in geoms:
+        r = np.zeros(GEOM)
+        r[0] = body
+        if g[0] == "sphere":
+            r[1], r[2], r[5:14], r[14:17] = 0, g[1], eye, g[2]
+        else:
+            r[1], r[2], r[3], r[14:17] = 2, g[1], g[2], g[3]
+            r[5:14] = np.asarray(g[4], dtype=np.float64).ravel() if len(g) > 4 else eye
+        gl.append(r)
+    if arm is not None:
+        length, am, ar = arm
+        link(body, 5, nq, nqd, (0, 1, 0), m=am, com=(length, 0, 0), inertia=(0.4 * am * ar * ar,) * 3)   # JOINT_REVOLUTE_Y
+        r = np.zeros(GEOM)
+        r[0], r[1], r[2], r[5:14], r[14:17] = len(links) - 1, 0, ar, eye, (length, 0, 0)
+        gl.append(r)
+        nq += 1; nqd += 1
+    head = np.zeros(HEADER)
+    head[0], head[1], head[3], head[4], head[5] = MAGIC, len(links), nq, nqd, len(gl)
+    if plane:
+        head[7], head[8:11] = 1, (0, 0, 1)
+    return np.concatenate([head, np.zeros(BASE), np.concatenate(links), np.concatenate(gl) if gl else np.zeros(0)])
+
+
+def _rot_y(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+MULTIBODY_WORLDS = ("spheres2", "capsule_sphere", "sphere_capsule", "three_bodies", "spherical_pair")
+
+
+def multibody_world_model(kind):
+    """Merged flat model of one of the test worlds (every multibody a free body on the ground plane)."""
+    from .model import merge_models
+    sph = lambda r, m: free_body_model(m, (0.4 * m * r * r,) * 3, [("sphere", r, (0, 0, 0))])
+    cap = lambda: free_body_model(2.0, (0.05, 0.05, 0.01), [("capsule", 0.15, 0.6, (0, 0, 0.05), _rot_y(0.3))])
+    if kind == "spheres2":
+        return merge_models([sph(0.3, 1.0), sph(0.2, 0.5)])
+    if kind == "capsule_sphere":
+        return merge_models([cap(), sph(0.25, 1.0)])
+    if kind == "sphere_capsule":       # the dispatcher's swapped call (src/contact_point.hpp:478-492)
+        return merge_models([sph(0.25, 1.0), cap()])
+    if kind == "three_bodies":         # three lists of contacts between multibodies, solved one after the other; an articulated one
+        a = free_body_model(1.5, (0.06, 0.06, 0.06), [("sphere", 0.3, (0, 0, 0)), ("sphere", 0.15, (0.35, 0, 0))], arm=(0.5, 0.3, 0.12))
+        return merge_models([a, cap(), sph(0.2, 0.5)])
+    if kind == "spherical_pair":       # free bodies on xyz + one spherical joint
+        a = free_body_model(1.0, (0.04, 0.05, 0.06), [("sphere", 0.3, (0.05, 0, 0))], spherical=True)
+        b = free_body_model(2.0, (0.05, 0.05, 0.01), [("capsule", 0.15, 0.6, (0, 0, 0), _rot_y(0.2))], spherical=True)
+        return merge_models([a, b])
+    raise ValueError(kind)
+
+
+def multibody_world(kind, n, seed=SEED):
+    """States of the test worlds: the multibodies are dropped close enough to each other and to the ground that every kind of
+    contact list occurs (none, plane only, multibody pair only, both)."""
+    r = np.random.default_rng(seed)
+    model = multibody_world_model(kind)
+    n_q, n_qd = int(model[3]), int(model[4])
+    nb = int(model[12])
+    spherical = kind == "spherical_pair"
+    q = np.zeros((n, n_q)); qd = r.uniform(-1.0, 1.0, (n, n_qd))
+    centre = r.uniform(-0.5, 0.5, (n, 2))
+    off = 0
+    arm_extra = {"three_bodies": (1, 0, 0)}.get(kind, (0,) * nb)
+    for b in range(nb):
+        q[:, off:off + 2] = centre + r.uniform(-0.3, 0.3, (n, 2))
+        q[:, off + 2] = r.uniform(0.1, 0.6, n)
+        if spherical:
+            q[:, off + 3:off + 7] = _unit_quats(r, n)
+            off += 7
+        else:
+            q[:, off + 3:off + 6] = r.uniform(-1.0, 1.0, (n, 3))
+            off += 6
+        if arm_extra[b]:
+            q[:, off] = r.uniform(-1.0, 1.0, n)
+            off += 1
+    tau = r.uniform(-1.0, 1.0, (n, n_qd))
+    return dict(model=model, q=_f32(q), qd=_f32(qd), tau=_f32(tau), params=dict(friction=0.7, keep_all_points=False), mode=2)
