@@ -156,11 +156,17 @@ int tds_b200_step_host(tds_b200_sim* sim, int mode, int use_pd, const double* q,
  * those with distance < 0: resolve_collision, mb_constraint_solver.hpp:169-180), computed on the device from the
  * contact distances of that step: count[e] and (link_a, link_b) of the k-th kept point, -9 beyond count.
  *   device: contact_dist [n_points][ns] (output of tds_b200_step_device), count [ns], links [2 * n_points][ns]
- *   host:   uses the distances of the last tds_b200_step_host(..., contact_dist != NULL); count [n], links [n][n_points][2] */
+ *   host:   uses the distances of the last tds_b200_step_host(..., contact_dist != NULL); count [n], links [n][n_points][2]
+ * Worlds of several multibodies (TDSM_H_NBODIES > 1, include/tds_b200_model.h): the multibodies of the model are bodies
+ * 1, 2, ... of the world (the plane, if any, is body 0), link indices are those inside their multibody, and the candidates
+ * BETWEEN multibodies (sphere-sphere, capsule-sphere; one list of World::mb_contacts_ per pair a < b, src/world.hpp:212-281)
+ * follow the plane candidates; contact_dist carries their distances in the same order (+inf: the contact function emitted no
+ * point).  tds_b200_contact_list_candidates_host: cand [n][n_points] = index into the candidate list of the k-th kept point. */
 int tds_b200_contact_pairs(const tds_b200_sim* sim, int* tuples, int cap);
 int tds_b200_model_contact_pairs(const double* model, int n_model, int* tuples, int cap);   /* host-only, from a flat model */
 int tds_b200_contact_list_device(tds_b200_sim* sim, const float* contact_dist, int* count, int* links, void* stream);
 int tds_b200_contact_list_host(tds_b200_sim* sim, int* count, int* links);
+int tds_b200_contact_list_candidates_host(tds_b200_sim* sim, int* count, int* cand);
 
 int tds_b200_env_set_state_host(tds_b200_sim* sim, const double* q, const double* qd);
 int tds_b200_env_get_state_host(tds_b200_sim* sim, double* q, double* qd);

@@ -25,6 +25,7 @@ static thread_local EmuDim emu_threadIdx, emu_blockIdx, emu_blockDim, emu_gridDi
 #define gridDim emu_gridDim
 #define __any_sync(mask, pred) ((pred) ? 1 : 0)
 #define __reduce_max_sync(mask, v) (v)
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 #define __syncwarp() ((void)0)
 #define clock64() (0LL)
 #undef __shared__
@@ -95,7 +96,7 @@ int tdsemu_stepw(const double* model, int n_model, const double* params, const d
   const int ns = (n + 31) & ~31, n_q = D->n_q, n_qd = D->n_qd;
   const int n_tau = n_qd - (D->floating ? 6 : 0), n_in = use_pd ? E.n_act : n_tau;
   std::vector<float> sq((size_t)(n_q > 0 ? n_q : 1) * ns), sqd((size_t)(n_qd > 0 ? n_qd : 1) * ns), st((size_t)(n_in > 0 ? n_in : 1) * ns, 0.f);
-  std::vector<float> oq(sq.size()), oqd(sqd.size()), oqdd(sqd.size()), ocd((size_t)(D->max_contacts > 0 ? D->max_contacts : 1) * ns);
+  std::vector<float> oq(sq.size()), oqd(sqd.size()), oqdd(sqd.size()), ocd((size_t)(D->max_contacts + D->n_pair_points + 1) * ns);
   for (int e = 0; e < n; ++e) {
     for (int k = 0; k < n_q; ++k) sq[(size_t)k * ns + e] = (float)q[(size_t)e * n_q + k];
     for (int k = 0; k < n_qd; ++k) sqd[(size_t)k * ns + e] = (float)qd[(size_t)e * n_qd + k];
@@ -121,10 +122,10 @@ int tdsemu_stepw(const double* model, int n_model, const double* params, const d
     if (q_out) for (int k = 0; k < n_q; ++k) q_out[(size_t)e * n_q + k] = oq[(size_t)k * ns + e];
     if (qd_out) for (int k = 0; k < n_qd; ++k) qd_out[(size_t)e * n_qd + k] = oqd[(size_t)k * ns + e];
     if (qdd_out) for (int k = 0; k < n_qd; ++k) qdd_out[(size_t)e * n_qd + k] = oqdd[(size_t)k * ns + e];
-    if (contact_dist) for (int k = 0; k < D->max_contacts; ++k) contact_dist[(size_t)e * D->max_contacts + k] = ocd[(size_t)k * ns + e];
+    if (contact_dist) for (int k = 0; k < D->max_contacts + D->n_pair_points; ++k) contact_dist[(size_t)e * (D->max_contacts + D->n_pair_points) + k] = ocd[(size_t)k * ns + e];
     if (ad) for (int k = 0; k < rows * cols; ++k) jac[(size_t)e * rows * cols + k] = jbuf[(size_t)k * ns + e];
   }
-  const int npts = D->max_contacts;
+  const int npts = D->max_contacts + D->n_pair_points;   // plane candidates, then the candidates between multibodies
   delete D;
   return ad ? rows * 1000 + cols : npts;
 }

@@ -57,9 +57,8 @@ def step(model, mode, q, qd, tau=None, precision=1, use_pd=False, env=None, jaco
     rows = n_qd if mode == 0 else n_q + n_qd
     cols = n_q + n_qd + ((int(e[0]) + 3) if use_pd else n_tau)
     jac = np.zeros((n, rows, cols)) if jacobian else None
-    cd = np.zeros((n, 64))
     # contact_dist is written [n][n_points]: size it after the call from the return value
-    cdbuf = np.zeros(n * 64)
+    cdbuf = np.zeros(n * 128)
     rc = lib().tdsemu_stepw(_dp(m), m.size, _dp(params), _dp(e), precision, mode, int(use_pd), n, _dp(q), _dp(qd), _dp(t),
                             _dp(out["q"]), _dp(out["qd"]), _dp(out["qdd"]), _dp(cdbuf), _dp(jac))
     if rc < 0:

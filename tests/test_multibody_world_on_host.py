@@ -112,3 +112,64 @@ def test_merge_models_refuses_what_the_reference_world_cannot_mean():
     two_roots = merge_models([a, a])   # a world is not a multibody: it cannot be merged again as one
     with pytest.raises(ValueError):
         merge_models([two_roots, a])
+
+
+def _reference_lists(g):
+    """(body_a, link_a, body_b, link_b) per contact of the reference's step, from the list index: World::mb_contacts_ holds one list
+    per pair of multibodies (i < j), the plane being multibody 0 (src/world.hpp:212-281)."""
+    k = int(g["model"][12])
+    pairs = [(i, j) for i in range(k + 1) for j in range(i + 1, k + 1)]
+    out = []
+    for e in range(g["q_in"].shape[0]):
+        rows = g["contact_idx"][e, :g["n_contacts"][e]]
+        out.append(np.array([[pairs[l][0], a, pairs[l][1], b] for l, a, b in rows], dtype=np.int32).reshape(-1, 4))
+    return out
+
+
+@pytest.mark.parametrize("kind", wl.MULTIBODY_WORLDS)
+def test_multibody_candidate_lists_and_distances_match_the_reference(kind):
+    """Contact-pair index lists (north_star: bit-exact): the static candidate list of the C-ABI (host-only call) equals what the
+    reference's World::mb_contacts_ holds after a step - multibody and link indices, list after list - and the distances the
+    kernel reports per candidate are the reference's contact distances."""
+    import ctypes
+    from tds_b200 import _lib
+    g = np.load(os.path.join(GOLDEN, "mb_" + kind + ".npz"))
+    m = np.ascontiguousarray(g["model"])
+    L = _lib.lib()
+    t = np.zeros((128, 4), dtype=np.int32)
+    k = L.tds_b200_model_contact_pairs(m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), m.size, ctypes.c_void_p(t.ctypes.data), 128)
+    assert k > 0
+    ref_lists = _reference_lists(g)
+    for e, r in enumerate(ref_lists):
+        assert np.array_equal(t[:k], r), e    # every candidate emits a point in these fixtures (no coincident centres)
+    out = emu.step(g["model"], 2, g["q_in"], g["qd_in"], g["tau"], precision=1, **params_from_golden(g))
+    assert out["contact_dist"].shape == (g["q_in"].shape[0], k)
+    ref_d = np.array([g["contact_data"][e, :k, 9] for e in range(g["q_in"].shape[0])])
+    assert np.max(np.abs(out["contact_dist"] - ref_d)) < 2e-6
+
+
+def test_world_of_urdf_multibodies_vs_live_reference():
+    """Two URDF multibodies (tests/golden/urdf/free_*.urdf) through the model compiler, merged into one world: the compiled models
+    equal the reference loader's, and the step of the merged world equals the reference World holding the same multibodies."""
+    from oracle import ref
+    from tds_b200.model import compile_urdf
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    here = os.path.join(GOLDEN, "urdf")
+    plane = os.path.join(here, "plane.urdf")
+    models = []
+    for name in ("free_capsule", "free_sphere"):
+        m = compile_urdf(os.path.join(here, name + ".urdf"), plane, False)
+        assert np.array_equal(m, ref.RefSim.from_urdf(os.path.join(here, name + ".urdf"), plane, False).export_model())
+        models.append(m)
+    world = merge_models(models)
+    w = wl.multibody_world("capsule_sphere", 32, seed=31)    # same shapes of state: two free bodies of 6 coordinates
+    rw = ref.RefWorld(world)
+    rw.set_params(**w["params"])
+    out = emu.step(world, 2, w["q"], w["qd"], w["tau"], precision=1, **w["params"])
+    hit = 0
+    for i in range(32):
+        r = rw.step(2, w["q"][i], w["qd"][i], w["tau"][i])
+        assert rel_err(out["q"][i], r["q"]) <= TOL and rel_err(out["qd"][i], r["qd"]) <= TOL
+        hit += int(np.any((r["contact_idx"][:, 0] == 2) & (r["contact_data"][:, 9] < 0)))
+    assert hit >= 8   # contacts between the two multibodies do occur

@@ -858,3 +858,105 @@ def test_spherical_joints_stiffness_damping_and_jacobian(golden_dir):
 def test_golden_vectors_spherical_joints(name, precision, golden_dir):
     """pendulum5spherical.urdf (five spherical joints) and humanoid_xyz_spherical.urdf on the plane, from the reference."""
     _check_golden_vectors(name, precision, golden_dir)
+
+
+# ---- worlds of several multibodies (SURVEY 8f.3) ---------------------------------------------------------------------------------
+# Added after the round's GPU budget was spent: verified through the host-compiled kernel source
+# (tests/test_multibody_world_on_host.py) against the same goldens and the live reference.
+@pytest.mark.parametrize("kind", wl.MULTIBODY_WORLDS)
+@pytest.mark.parametrize("precision", [tds_b200.PREC_MIXED, tds_b200.PREC_F64])
+def test_multibody_world_golden_vectors(kind, precision, golden_dir):
+    """Contacts between the multibodies of one world (src/world.hpp:206-282: sphere-sphere, capsule-sphere and the dispatcher's
+    swapped call), one LCP per list of World::mb_contacts_ solved in sequence after the plane contacts (:351-355): full step and
+    World::step alone against the reference, candidate distances, and the contact-pair index lists bit for bit."""
+    g = np.load(os.path.join(golden_dir, "mb_" + kind + ".npz"))
+    n = g["q_in"].shape[0]
+    sim = tds_b200.BatchSim(g["model"], n, precision=precision, **params_from_golden(g))
+    tol = TOL if precision == tds_b200.PREC_F64 else 3e-5
+    out = sim.step_host(2, g["q_in"], g["qd_in"], g["tau"], want_contacts=True)
+    assert "tds_stepw_kernel" in sim.kernel_name()
+    assert rel_err(out["q"], g["q_out"]) <= tol and rel_err(out["qd"], g["qd_out"]) <= tol
+    # candidate list = what World::mb_contacts_ holds after the step: multibody and link indices, list after list
+    k_bodies = int(g["model"][12])
+    lists = [(i, j) for i in range(k_bodies + 1) for j in range(i + 1, k_bodies + 1)]
+    pairs = sim.contact_pairs()
+    for e in range(n):
+        rows = g["contact_idx"][e, :g["n_contacts"][e]]
+        want = np.array([[lists[l][0], a, lists[l][1], b] for l, a, b in rows], dtype=np.int32).reshape(-1, 4)
+        assert np.array_equal(pairs, want)
+    k = pairs.shape[0]
+    ref_d = g["contact_data"][:, :k, 9]
+    assert out["contact_dist"].shape == ref_d.shape and np.max(np.abs(out["contact_dist"] - ref_d)) < 2e-6
+    # the list the constraint solver keeps (distance < 0), as candidate indices and as (link_a, link_b)
+    keep = ref_d < 0
+    assert np.array_equal(out["contact_count"], keep.sum(axis=1).astype(np.int32))
+    for e in range(n):
+        idx = np.nonzero(keep[e])[0]
+        assert np.array_equal(out["contact_candidates"][e, :idx.size], idx) and np.all(out["contact_candidates"][e, idx.size:] == -9)
+        assert np.array_equal(out["contact_links"][e, :idx.size], pairs[idx][:, [1, 3]])
+    world = sim.step_host(tds_b200.MODE_WORLD, g["q_in"], g["qd_in"])
+    assert rel_err(world["qd"], g["qd_world_step"]) <= tol
+
+
+def test_multibody_world_solver_parameters_and_jacobian_vs_live_reference():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref did not travel")
+    n = 32
+    w = wl.multibody_world("three_bodies", n, seed=2024)
+    params = dict(w["params"]); params.update(pgs_iterations=4, restitution=0.3, erp=0.1, cfm=1e-4, keep_all_points=True)
+    rw = ref.RefWorld(w["model"])
+    rw.set_params(**params)
+    sim = tds_b200.BatchSim(w["model"], n, precision=tds_b200.PREC_F64, **params)
+    out = sim.step_host(2, w["q"], w["qd"], w["tau"])
+    for i in range(n):
+        r = rw.step(2, w["q"][i], w["qd"][i], w["tau"][i])
+        assert rel_err(out["q"][i], r["q"]) <= TOL and rel_err(out["qd"][i], r["qd"]) <= TOL
+    w = wl.multibody_world("capsule_sphere", 6, seed=77)
+    rw = ref.RefWorld(w["model"])
+    rw.set_params(**w["params"])
+    sim = tds_b200.BatchSim(w["model"], 6, precision=tds_b200.PREC_F64, **w["params"])
+    J = sim.step_jacobian_host(2, w["q"], w["qd"], w["tau"])
+    ok = []
+    for e in range(6):
+        f = lambda x: (lambda r: np.concatenate([r["q"], r["qd"]]))(rw.step(2, x[:12], x[12:24], x[24:]))
+        Jr = _central_differences(f, np.concatenate([w["q"][e], w["qd"][e], w["tau"][e]]))
+        ok.append(np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-4)
+    assert np.mean(ok) >= 0.8
+
+
+def test_pytinydiffsim_world_of_two_multibodies():
+    """pytinydiffsim surface with two URDF multibodies in one TinyWorld: forward_dynamics -> integrate_euler_qdd on each,
+    world.step once (contacts with the plane AND between the multibodies, on the merged model), integrate_euler on each -
+    against a reference World holding the same multibodies."""
+    import pytinydiffsim as pd
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref did not travel")
+    here = os.path.join(os.path.dirname(__file__), "golden", "urdf")
+    world = pd.TinyWorld()
+    world.friction = 0.7
+    parser, conv = pd.TinyUrdfParser(), pd.UrdfToMultiBody2()
+    plane_mb, cap, sph = pd.TinyMultiBody(False), pd.TinyMultiBody(False), pd.TinyMultiBody(False)
+    assert conv.convert2(parser.load_urdf(os.path.join(here, "plane.urdf")), world, plane_mb)
+    assert conv.convert2(parser.load_urdf(os.path.join(here, "free_capsule.urdf")), world, cap)
+    assert conv.convert2(parser.load_urdf(os.path.join(here, "free_sphere.urdf")), world, sph)
+    from tds_b200.model import merge_models
+    rw = ref.RefWorld(merge_models([cap._model, sph._model]))
+    rw.set_params(friction=0.7)
+    w = wl.multibody_world("capsule_sphere", 24, seed=31)
+    hit = 0
+    for i in range(24):
+        cap.set_q(w["q"][i, :6]); cap.qd[:] = w["qd"][i, :6]; cap.tau[:] = w["tau"][i, :6]
+        sph.set_q(w["q"][i, 6:]); sph.qd[:] = w["qd"][i, 6:]; sph.tau[:] = w["tau"][i, 6:]
+        for mb in (cap, sph):
+            pd.forward_dynamics(mb, world.gravity)
+            mb.clear_forces()
+            pd.integrate_euler_qdd(mb, 1e-3)
+        world.step(1e-3)
+        for mb in (cap, sph):
+            pd.integrate_euler(mb, 1e-3)
+        r = rw.step(2, w["q"][i], w["qd"][i], w["tau"][i])
+        assert rel_err(np.concatenate([cap.q, sph.q]), r["q"]) <= TOL and rel_err(np.concatenate([cap.qd, sph.qd]), r["qd"]) <= TOL
+        hit += int(np.any((r["contact_idx"][:, 0] == 2) & (r["contact_data"][:, 9] < 0)))
+    assert hit >= 6

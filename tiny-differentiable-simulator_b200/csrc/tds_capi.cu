@@ -34,10 +34,39 @@ extern "C" int tds_launch_stepw(const DevModel* M, const SimParams* P, const Env
                                 int warps_per_block, cudaStream_t stream);
 
 // candidate contact points of a model, reference enumeration order: (link_a, link_b) per point
+// (plane candidates first, then - worlds of several multibodies - the candidates between multibodies, list after list)
 struct ContactCandTable {
   int n_points;
-  signed char link_a[TDS_MAX_POINTS], link_b[TDS_MAX_POINTS];
+  signed char link_a[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS], link_b[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS];   // link index inside its multibody
+  signed char body_a[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS], body_b[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS];   // multibody of the world (0 = the plane)
 };
+
+// Candidate points of a model in the reference's enumeration order (World::compute_contacts_multi_body_internal,
+// src/world.hpp:212-281).  The plane is multibody 0 of the world, created first (body A of its contacts, base link -1); the
+// multibodies of the model follow as 1, 2, ...; link indices are the reference's: inside their multibody.
+static ContactCandTable make_cand_table(const DevModel& D) {
+  ContactCandTable T;
+  memset(&T, 0, sizeof(T));
+  int first[TDS_MAX_LINKS + 1];   // first link of every multibody
+  for (int i = 0, b = -1; i < D.n_links; ++i) if (D.body_of[i] != b) { b = D.body_of[i]; first[b] = i; }
+  auto local = [&](int link) { return link < 0 ? -1 : link - first[D.body_of[link]]; };
+  int c = 0;
+  if (D.has_plane)
+    for (int g = 0; g < D.n_geoms; ++g) {
+      const int pts = D.g_type[g] == TDSG_SPHERE ? 1 : (D.g_type[g] == TDSG_CAPSULE ? 2 : (D.g_type[g] == TDSG_BOX ? 8 : 0));
+      for (int j = 0; j < pts; ++j, ++c) {
+        T.body_a[c] = 0; T.link_a[c] = -1;
+        T.body_b[c] = (signed char)(1 + (D.g_link[g] < 0 ? 0 : D.body_of[D.g_link[g]])); T.link_b[c] = (signed char)local(D.g_link[g]);
+      }
+    }
+  for (int p = 0; p < D.n_pair_points; ++p, ++c) {
+    const int la = D.g_link[D.pp_ga[p]], lb = D.g_link[D.pp_gb[p]];
+    T.body_a[c] = (signed char)(1 + D.body_of[la]); T.link_a[c] = (signed char)local(la);
+    T.body_b[c] = (signed char)(1 + D.body_of[lb]); T.link_b[c] = (signed char)local(lb);
+  }
+  T.n_points = c;
+  return T;
+}
 
 namespace {
 
@@ -233,20 +262,27 @@ __global__ void rollout_accum_kernel(const float* __restrict__ reward, const flo
 // what varies per environment is which of them the constraint solver keeps: all with keep_all_points_, else those with
 // distance < 0 (MultiBodyConstraintSolver::resolve_collision, src/mb_constraint_solver.hpp:169-180).
 // links: [2 * n_points][ns] = (link_a, link_b) of the k-th kept point (MultiBodyContactPoint::link_a/b, :29-40), -9 beyond count.
+// cand (optional): [n_points][ns] index of the k-th kept point in the candidate list (tds_b200_contact_pairs), -9 beyond count.
+// A distance of +inf marks a candidate between multibodies whose contact function emitted nothing (contact_point.hpp:80).
 __global__ void contact_list_kernel(const float* __restrict__ dist, ContactCandTable T, int keep_all, int* __restrict__ count,
-                                    int* __restrict__ links, int n, int ns) {
+                                    int* __restrict__ links, int* __restrict__ cand, int n, int ns) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   int k = 0;
   for (int c = 0; c < T.n_points; ++c) {
-    if (keep_all || dist[(size_t)c * ns + e] < 0.f) {
+    const float d = dist[(size_t)c * ns + e];
+    if (d < 3.0e38f && (keep_all || d < 0.f)) {
       links[(size_t)(2 * k) * ns + e] = T.link_a[c];
       links[(size_t)(2 * k + 1) * ns + e] = T.link_b[c];
+      if (cand) cand[(size_t)k * ns + e] = c;
       ++k;
     }
   }
   count[e] = k;
-  for (; k < T.n_points; ++k) { links[(size_t)(2 * k) * ns + e] = -9; links[(size_t)(2 * k + 1) * ns + e] = -9; }
+  for (; k < T.n_points; ++k) {
+    links[(size_t)(2 * k) * ns + e] = -9; links[(size_t)(2 * k + 1) * ns + e] = -9;
+    if (cand) cand[(size_t)k * ns + e] = -9;
+  }
 }
 // integrate_euler (src/dynamics/integrator.hpp:10-133) and integrate_euler_qdd (:141-195) as stand-alone stages of the
 // fine-grained pytinydiffsim surface (forward_dynamics -> integrate_euler_qdd -> World::step -> integrate_euler): the fused
@@ -361,7 +397,7 @@ struct tds_b200_sim {
                                             // instance, else to the strict F64 (rebuild_team)
   int n_tau = 0, n_points = 0;
   ContactCandTable cand;              // static candidate table (reference enumeration order)
-  int *c_count = nullptr, *c_links = nullptr;   // device: per-environment contact list of the last tds_b200_contact_list_* call
+  int *c_count = nullptr, *c_links = nullptr, *c_cand = nullptr;   // device: per-environment contact list of the last tds_b200_contact_list_* call
   // resident state + staging
   float *q = nullptr, *qd = nullptr, *act = nullptr, *qdd = nullptr, *reward = nullptr, *done = nullptr;
   float *cdist = nullptr, *link_xf = nullptr;
@@ -528,16 +564,8 @@ tds_b200_sim* tds_b200_create(const double* model, int n_model, int n_envs, int 
     s->kernel_req = strcmp(kv, "world") == 0 ? 1 : (strcmp(kv, "team") == 0 ? 2 : (strcmp(kv, "role") == 0 ? 3 : 4));
   s->kernel = s->kernel_req;
   s->n_tau = base.n_qd - (base.floating ? 6 : 0);
-  s->n_points = base.max_contacts;
-  memset(&s->cand, 0, sizeof(s->cand));
-  if (base.has_plane) {   // plane (body A, base link -1) x every geom of the robot (body B), geoms grouped by link, base first
-    int c = 0;
-    for (int g = 0; g < base.n_geoms; ++g) {
-      const int pts = base.g_type[g] == TDSG_SPHERE ? 1 : (base.g_type[g] == TDSG_CAPSULE ? 2 : (base.g_type[g] == TDSG_BOX ? 8 : 0));
-      for (int j = 0; j < pts; ++j) { s->cand.link_a[c] = -1; s->cand.link_b[c] = (signed char)base.g_link[g]; ++c; }
-    }
-    s->cand.n_points = c;
-  }
+  s->n_points = base.max_contacts + base.n_pair_points;
+  s->cand = make_cand_table(base);
   // visuals for the v1 output packing
   memset(&s->vis, 0, sizeof(s->vis));
   {
@@ -580,7 +608,7 @@ void tds_b200_destroy(tds_b200_sim* s) {
   drop_host_graph(s);
   cudaFree(s->rq); cudaFree(s->rqd); cudaFree(s->zero_act); cudaFree(s->pol_act); cudaFree(s->sticky); cudaFree(s->r_total);
   cudaFree(s->pol_params); cudaFree(s->act_qidx); cudaFree(s->r_steps);
-  cudaFree(s->c_count); cudaFree(s->c_links); cudaFree(s->jac_scratch); cudaFree(s->jac_dev);
+  cudaFree(s->c_count); cudaFree(s->c_links); cudaFree(s->c_cand); cudaFree(s->jac_scratch); cudaFree(s->jac_dev);
   cudaFree(s->cdist); cudaFree(s->link_xf); cudaFree(s->scratch); cudaFree(s->stage_dev); cudaFree(s->phase_clk); cudaFree(s->team_dev);
   if (s->stage_host) cudaFreeHost(s->stage_host);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -881,38 +909,36 @@ int tds_b200_integrate_euler_qdd_device(tds_b200_sim* s, float* qd, const float*
   return 0;
 }
 
+static int write_tuples(const ContactCandTable& T, int* tuples, int cap) {
+  for (int c = 0; c < T.n_points && c < cap && tuples; ++c) {
+    tuples[4 * c + 0] = T.body_a[c]; tuples[4 * c + 1] = T.link_a[c];
+    tuples[4 * c + 2] = T.body_b[c]; tuples[4 * c + 3] = T.link_b[c];
+  }
+  return T.n_points;
+}
+
 // Host-only variant (no GPU needed): the candidate list of a flat model.
 int tds_b200_model_contact_pairs(const double* model, int n_model, int* tuples, int cap) {
   if (!model) { set_err("null model"); return -1; }
   DevModel* D = new DevModel;
   const int rc = tds_build_dev_model(model, n_model, D);
-  int c = 0;
-  if (rc == 0 && D->has_plane) {
-    for (int g = 0; g < D->n_geoms; ++g) {
-      const int pts = D->g_type[g] == TDSG_SPHERE ? 1 : (D->g_type[g] == TDSG_CAPSULE ? 2 : (D->g_type[g] == TDSG_BOX ? 8 : 0));
-      for (int j = 0; j < pts; ++j, ++c)
-        if (tuples && c < cap) { tuples[4 * c] = 0; tuples[4 * c + 1] = -1; tuples[4 * c + 2] = 1; tuples[4 * c + 3] = D->g_link[g]; }
-    }
-  }
+  ContactCandTable T;
+  if (rc == 0) T = make_cand_table(*D);
   delete D;
   if (rc) { set_err(std::string("unsupported model: ") + tds_model_error(rc)); return rc; }
-  return c;
+  return write_tuples(T, tuples, cap);
 }
 
 int tds_b200_contact_pairs(const tds_b200_sim* s, int* tuples, int cap) {
   if (!s) return -1;
-  for (int c = 0; c < s->cand.n_points && c < cap && tuples; ++c) {
-    tuples[4 * c + 0] = 0; tuples[4 * c + 1] = s->cand.link_a[c];     // body A = the plane (created first), its base link
-    tuples[4 * c + 2] = 1; tuples[4 * c + 3] = s->cand.link_b[c];     // body B = the robot
-  }
-  return s->cand.n_points;
+  return write_tuples(s->cand, tuples, cap);
 }
 
 int tds_b200_contact_list_device(tds_b200_sim* s, const float* contact_dist, int* count, int* links, void* stream) {
   if (!s || !contact_dist || !count || !links) return -1;
   if (s->cand.n_points == 0) return 0;
   const int T = 128, B = (s->n + T - 1) / T;
-  contact_list_kernel<<<B, T, 0, (cudaStream_t)stream>>>(contact_dist, s->cand, s->P.keep_all_points, count, links, s->n, s->ns);
+  contact_list_kernel<<<B, T, 0, (cudaStream_t)stream>>>(contact_dist, s->cand, s->P.keep_all_points, count, links, nullptr, s->n, s->ns);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -935,6 +961,28 @@ int tds_b200_contact_list_host(tds_b200_sim* s, int* count, int* links) {
   if (links)
     for (int e = 0; e < n; ++e)
       for (int k = 0; k < 2 * np; ++k) links[(size_t)e * 2 * np + k] = tmp[(size_t)k * ns + e];
+  return 0;
+}
+
+int tds_b200_contact_list_candidates_host(tds_b200_sim* s, int* count, int* cand) {
+  if (!s || !count || !cand) return -1;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int n = s->n, ns = s->ns, np = s->cand.n_points;
+  if (np == 0) { for (int e = 0; e < n; ++e) count[e] = 0; return 0; }
+  if (!s->c_count) {
+    CUDA_TRY(cudaMalloc((void**)&s->c_count, sizeof(int) * ns));
+    CUDA_TRY(cudaMalloc((void**)&s->c_links, sizeof(int) * (size_t)ns * 2 * np));
+  }
+  if (!s->c_cand) CUDA_TRY(cudaMalloc((void**)&s->c_cand, sizeof(int) * (size_t)ns * np));
+  const int T = 128, B = (n + T - 1) / T;
+  contact_list_kernel<<<B, T, 0, s->stream>>>(s->cdist, s->cand, s->P.keep_all_points, s->c_count, s->c_links, s->c_cand, n, ns);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> tmp((size_t)ns * np);
+  CUDA_TRY(cudaMemcpyAsync(count, s->c_count, sizeof(int) * n, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(tmp.data(), s->c_cand, sizeof(int) * tmp.size(), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  for (int e = 0; e < n; ++e)
+    for (int k = 0; k < np; ++k) cand[(size_t)e * np + k] = tmp[(size_t)k * ns + e];
   return 0;
 }
 

@@ -317,6 +317,8 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
         const V3<RC> diff = swapped ? cb - ca : ca - cb;       // poseA.position - poseB.position of the call
         const RC len = sqrt_t(dot(diff, diff));
         const RC dist = len - (r1 + r2);
+        // candidate distances behind the plane candidates; +inf: the contact function emitted no point (centres closer than CONTACT_EPSILON)
+        if (io.contact_dist && live) io.contact_dist[(size_t)(pt_index + pt) * ns + e] = len > RC(1e-5) ? (float)val_of(dist) : __int_as_float(0x7f800000);
         if (len > RC(1e-5) && dist < RC(0)) {                  // CONTACT_EPSILON; resolve_collision keeps distance < 0 (the others are zero rows)
           const V3<RC> nrm = diff * (RC(1) / len);
           const V3<RC> p1 = (swapped ? cb : ca) - nrm * r1;    // point_a_world of the call

@@ -19,10 +19,8 @@ import numpy as np
 
 from . import _lib
 from .envs import VectorizedLaikagoEnv, VectorizedLaikagoEnvOutput, VectorizedAntEnv  # noqa: F401
-from .model import compile_urdf, fixture_path, load_model
-from .sim import BatchSim, MODE_FD, MODE_NOCONTACT, MODE_FULL
-
-MODE_WORLD = 3
+from .model import compile_urdf, fixture_path, load_model, merge_models
+from .sim import BatchSim, MODE_FD, MODE_NOCONTACT, MODE_FULL, MODE_WORLD
 
 
 class TinyUrdfStructures:
@@ -48,8 +46,26 @@ class TinyWorld:
         self._bodies = []
 
     def step(self, dt):
-        """World::step (src/world.hpp:302-363): contact detection + constraint solve of every multibody against the plane."""
-        for mb in self._bodies:
+        """World::step (src/world.hpp:302-363): contact detection + constraint solve.  One multibody: against the plane.  Several
+        fixed-base multibodies (one root link each): ONE simulator over the merged model (tds_b200.model.merge_models), so that
+        the contacts between multibodies (sphere-sphere, capsule-sphere, :206-282) are found and solved list after list like the
+        reference does.  A world mixing in floating-base multibodies steps each against the plane only."""
+        bodies = self._bodies
+        if len(bodies) > 1 and all(not b._floating and b._single_root() for b in bodies):
+            key = tuple(id(b) for b in bodies)
+            if getattr(self, "_merged_key", None) != key:
+                self._merged = BatchSim(merge_models([b._model for b in bodies]), 1, precision=1)
+                self._merged_key = key
+            sim = self._merged
+            sim.set_params(dt, self.gravity, self.friction, self.restitution, self.erp, self.cfm, self.pgs_iterations, self.keep_all_points)
+            q = np.concatenate([b.q for b in bodies]); qd = np.concatenate([b.qd for b in bodies])
+            out = sim.step_host(MODE_WORLD, q[None], qd[None], None)["qd"][0]
+            o = 0
+            for b in bodies:
+                b.qd = out[o:o + b.qd.size].copy()
+                o += b.qd.size
+            return
+        for mb in bodies:
             mb._world_step(self, dt)
 
 
@@ -62,6 +78,12 @@ class TinyMultiBody:
 
     def is_floating(self):
         return self._floating
+
+    def _single_root(self):
+        m = self._model
+        n_links = int(m[1])
+        parents = m[16 + 13:16 + 13 + n_links * 34:34]
+        return int(np.sum(parents < 0)) == 1
 
     @property
     def num_dofs(self):
@@ -118,6 +140,7 @@ class UrdfToMultiBody2:
             return True
         model = compile_urdf(urdf_structures.source, world._plane, mb.is_floating())
         mb._world = world
+        mb._model = model
         mb._bind(BatchSim(model, 1, precision=1))    # strict fp64 arithmetic: a single body is not a throughput case
         world._bodies.append(mb)
         return True

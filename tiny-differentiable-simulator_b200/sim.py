@@ -13,6 +13,7 @@ from . import _lib
 from .model import model_dims
 
 MODE_FD, MODE_NOCONTACT, MODE_FULL = 0, 1, 2
+MODE_WORLD = 3   # World::step(dt) alone (src/world.hpp:293-363): contacts + constraint solve on (q, qd) -> qd; world-frame kernel
 PREC_MIXED, PREC_F64, PREC_F32, PREC_AUTO = 0, 1, 2, -1
 
 
@@ -138,6 +139,11 @@ class BatchSim:
                                                            ctypes.c_void_p(links.ctypes.data)), "contact_list_host")
             out["contact_count"] = cnt
             out["contact_links"] = links[:, :self.n_contact_points]
+            # ... and which candidates (rows of contact_pairs()) they are: needed to tell the multibodies of a world apart
+            cand = np.full((n, max(self.n_contact_points, 1)), -9, dtype=np.int32)
+            self._check(self._L.tds_b200_contact_list_candidates_host(self._h, ctypes.c_void_p(cnt.ctypes.data),
+                                                                      ctypes.c_void_p(cand.ctypes.data)), "contact_list_candidates_host")
+            out["contact_candidates"] = cand[:, :self.n_contact_points]
         return out
 
     def step_jacobian_host(self, mode, q, qd, tau_or_action=None, use_pd=False):
