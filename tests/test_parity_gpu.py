@@ -960,3 +960,34 @@ def test_pytinydiffsim_world_of_two_multibodies():
         assert rel_err(np.concatenate([cap.q, sph.q]), r["q"]) <= TOL and rel_err(np.concatenate([cap.qd, sph.qd]), r["qd"]) <= TOL
         hit += int(np.any((r["contact_idx"][:, 0] == 2) & (r["contact_data"][:, 9] < 0)))
     assert hit >= 6
+
+
+def test_vectorized_env_auto_reset_settles_and_sticky_done():
+    """VectorizedEnvironment::step (ars_vectorized_environment.h:252-284): with auto_reset_when_done a finished environment is
+    reset (noisy pose, zero velocity, 10 settle steps) and observes the settled state; without it, it keeps stepping but reports
+    reward 0 and stays done."""
+    n = 8
+    env = tds_b200.VectorizedLaikagoEnv(n, auto_reset_when_done=True)
+    env.reset()
+    q, qd = env.sim.env_get_state()
+    q[:3, 3:6] = [1.2, 0.0, 0.0]                       # three robots rolled over: done on the next step
+    env.sim.env_set_state(q, qd)
+    out = env.step(np.zeros((n, 12)))
+    assert np.array_equal(out.dones > 0, np.arange(n) < 3)
+    pose = tds_b200.envs.laikago_reset_pose()
+    o = out.obs[:3]
+    assert np.all(np.abs(o[:, 3:6]) < 0.05) and np.all(np.abs(o[:, 6:18] - pose[6:18]) < 0.2) and np.all(np.abs(o[:, 2] - pose[2]) < 0.1)
+    q2, _ = env.sim.env_get_state()
+    assert np.allclose(q2[:3, 2:], o[:, 2:18], atol=1e-6)             # the observation IS the settled state
+    env = tds_b200.VectorizedLaikagoEnv(n, auto_reset_when_done=False)
+    env.reset()
+    q, qd = env.sim.env_get_state()
+    q[:3, 3:6] = [1.2, 0.0, 0.0]
+    env.sim.env_set_state(q, qd)
+    first = env.step(np.zeros((n, 12)))
+    q, qd = env.sim.env_get_state()
+    q[:3, 3:6] = 0.0                                   # upright again: the done flag must stay
+    env.sim.env_set_state(q, qd)
+    second = env.step(np.zeros((n, 12)))
+    assert np.array_equal(first.dones > 0, np.arange(n) < 3) and np.array_equal(second.dones > 0, np.arange(n) < 3)
+    assert np.all(second.rewards[:3] == 0) and np.all(second.rewards[3:] != 0)

@@ -55,6 +55,7 @@ class VectorizedLaikagoEnv:
         self._obs = np.zeros((num_envs, self.obs_dim()), dtype=np.float32)
         self._rew = np.zeros(num_envs, dtype=np.float32)
         self._done = np.zeros(num_envs, dtype=np.float32)
+        self._was_done = np.zeros(num_envs, dtype=bool)
 
     def action_dim(self):
         return 12
@@ -81,6 +82,7 @@ class VectorizedLaikagoEnv:
         q, qd = self._initial_state(self.num_envs)
         self.sim.env_set_state(q, qd)
         self._settle()
+        self._was_done = np.zeros(self.num_envs, dtype=bool)
         return self._obs.copy()
 
     def rollouts(self, policies, rollout_length, shift=0.0, noise=None):
@@ -97,14 +99,27 @@ class VectorizedLaikagoEnv:
         self.sim.env_step_host(a, self._obs, self._rew, self._done)
         obs = self._obs.copy()
         rewards, dones = self._rew.copy(), self._done.copy()
-        if self.auto_reset and dones.any():  # ars_vectorized_environment.h:262-283
+        if self.auto_reset and dones.any():
+            # ars_vectorized_environment.h:261-272: contact_sim.reset() of the finished environments = reset pose + joint noise,
+            # zero velocities, then 10 settle steps (laikago_environment2.h:63-116); the observation is the settled state.
+            # tds_b200_env_reset_device does exactly that under a mask, the others are left untouched.
+            import torch
             idx = np.nonzero(dones)[0]
+            dev = f"cuda:{self.sim.device}"
+            noise = np.zeros((self.action_dim(), self.sim.n_stride), dtype=np.float32)
+            noise[:, idx] = (0.05 * (self.rng.random((idx.size, self.action_dim())) - 0.5) * 2.0).T
+            mask = torch.from_numpy(np.ascontiguousarray(dones, dtype=np.float32)).to(dev)
+            noise_t = torch.from_numpy(noise).to(dev)
+            torch.cuda.synchronize(dev)     # produced on torch's stream, consumed on the simulator's own
+            self.sim.env_reset_device(mask=mask, noise=noise_t, settle_steps=10)
             q, qd = self.sim.env_get_state()
-            q0, qd0 = self._initial_state(idx.size)
-            q[idx], qd[idx] = q0, qd0
-            self.sim.env_set_state(q, qd)
-            obs[idx, :self.sim.n_q] = q0
-            obs[idx, self.sim.n_q:] = qd0
+            obs[idx, :self.sim.n_q] = q[idx]
+            obs[idx, self.sim.n_q:] = qd[idx]
+        elif not self.auto_reset:
+            # :252-277: an environment that was already done keeps stepping but reports reward 0 and stays done
+            rewards[self._was_done] = 0.0
+            dones[self._was_done] = 1.0
+            self._was_done = dones > 0
         obs[:, 0] = 0.0  # ars_vectorized_environment.h:285-287
         obs[:, 1] = 0.0
         return VectorizedLaikagoEnvOutput(obs, rewards, dones)
@@ -145,6 +160,7 @@ class VectorizedAntEnv(VectorizedLaikagoEnv):
         self._obs = np.zeros((num_envs, self.obs_dim()), dtype=np.float32)
         self._rew = np.zeros(num_envs, dtype=np.float32)
         self._done = np.zeros(num_envs, dtype=np.float32)
+        self._was_done = np.zeros(num_envs, dtype=bool)
 
     def action_dim(self):
         return 8
