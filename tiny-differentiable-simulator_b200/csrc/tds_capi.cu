@@ -18,6 +18,7 @@
 extern "C" int tds_launch_stept(const TeamModel* TM, const TeamLink* tl_dev, const DevModel* M, const SimParams* P,
                                 const EnvParams* E, const StepIO* io, int mode, int use_pd, int precision,
                                 char* gscratch, int use_smem, cudaStream_t stream);
+extern "C" unsigned long long tds_stepr_table_owner(int dev);
 extern "C" int tds_launch_stepr(const TeamModel* TM, const TeamLink* tl_host, unsigned long long token, const DevModel* M,
                                 const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
                                 int precision, char* gscratch, int use_smem, cudaStream_t stream);
@@ -1280,6 +1281,9 @@ int tds_b200_env_step_host(tds_b200_sim* s, const float* actions, float* obs, fl
   }
   const void* key[4] = {actions, obs, rewards, dones};
   const bool same = s->g_key[0] == key[0] && s->g_key[1] == key[1] && s->g_key[2] == key[2] && s->g_key[3] == key[3];
+  // the role-warp kernel reads its link table from ONE constant symbol per device: if another simulator took the symbol over
+  // since the capture, the captured launch would run on that simulator's table - drop the graph, the eager path re-uploads
+  if (s->g_exec && s->kernel == 3 && tds_stepr_table_owner(s->device) != s->table_token) drop_host_graph(s);
   if (same && s->g_exec) {
     CUDA_TRY(cudaGraphLaunch(s->g_exec, sm));
   } else if (same && s->g_seen >= 2 && !s->phase_clk && is_pinned(actions) && is_pinned(obs) && is_pinned(rewards) && is_pinned(dones)) {

@@ -880,6 +880,11 @@ tds_stepr_kernel(const __grid_constant__ TeamModel TM,
 // may still be reading the symbol).  Not allowed while the stream is being captured into a CUDA graph.
 static unsigned long long g_table_token[64] = {0};
 
+// Owner of the table resident on a device (0: none yet).  A CUDA graph that holds a launch of this kernel replays WITHOUT
+// passing through tds_launch_stepr: whoever replays one must check that its simulator still owns the table (the library's
+// own graph of tds_b200_env_step_host does, tds_capi.cu; user captures of tds_b200_env_step_device: see INTEGRATION.md).
+extern "C" unsigned long long tds_stepr_table_owner(int dev) { return (dev >= 0 && dev < 64) ? g_table_token[dev] : 0ull; }
+
 extern "C" int tds_launch_stepr(const TeamModel* TM, const TeamLink* tl_host, unsigned long long token, const DevModel* M,
                                 const SimParams* P, const EnvParams* E, const StepIO* io, int mode, int use_pd,
                                 int precision, char* gscratch, int use_smem, cudaStream_t stream) {
