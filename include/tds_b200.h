@@ -267,6 +267,28 @@ bool b200_laikago_jacobian_send_local(int num_total_threads, const double* input
 bool b200_laikago_jacobian_send_global(const double* input);
 void b200_laikago_jacobian(int num_total_threads, int num_blocks, int num_threads_per_block, double* output);
 
+/* ---- the RigidBody path of World::step (src/world.hpp:293-363, src/rigid_body.hpp, src/rb_constraint_solver.hpp) ----------
+ * A world of up to 16 rigid bodies with ONE collision shape each (sphere, plane, capsule, box), a batch of such worlds per
+ * simulator, one GPU lane per world: apply_gravity / apply_force_impulse / clear_forces, contacts of every pair through the
+ * reference's dispatcher (sphere-sphere, plane-sphere / capsule / box, capsule-sphere, and the swapped calls), the
+ * sequential-impulse solver (num_solver_iterations sweeps over the contact list), integrate.
+ *   desc   [n_bodies][6]  = mass (0: static), shape (TDSG_*, tds_b200_model.h), p0..p3: sphere radius | capsule radius, length |
+ *                           box extents | plane normal [3], constant
+ *   state  per body 13 doubles: position [3], orientation xyzw [4], linear velocity [3], angular velocity [3]
+ *          device layout [13 * n_bodies][n_stride] fp64 (n_stride = n_worlds rounded up to 32), host layout [n_worlds][n_bodies][13]
+ *   force  RigidBody::apply_central_force before the FIRST step ([3 * n_bodies][n_stride] / [n_worlds][n_bodies][3]) or NULL
+ * Defaults are the reference's (dt 1/60 is ours): gravity (0, 0, -9.81), friction 0.5, restitution 0, erp 0.1, 1 solver iteration.
+ * tds_b200_rigid_jacobian_host: d state_out / d (state | force) [n_worlds][13 n_bodies][16 n_bodies] by forward-mode dual numbers
+ * (python/examples/billiard_optimization.py differentiates exactly this path). */
+typedef struct tds_b200_rigid tds_b200_rigid;
+tds_b200_rigid* tds_b200_rigid_create(const double* desc, int n_bodies, int n_worlds, int device);
+void tds_b200_rigid_destroy(tds_b200_rigid* h);
+int tds_b200_rigid_set_params(tds_b200_rigid* h, double dt, const double* gravity, double friction, double restitution, double erp,
+                              int num_solver_iterations);
+int tds_b200_rigid_step_device(tds_b200_rigid* h, const double* state_in, double* state_out, const double* force, int steps, void* stream);
+int tds_b200_rigid_step_host(tds_b200_rigid* h, const double* state, const double* force, int steps, double* state_out);
+int tds_b200_rigid_jacobian_host(tds_b200_rigid* h, const double* state, const double* force, int steps, double* state_out, double* jac);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,8 +20,9 @@ $CXX $FLAGS $INC -c "$HERE/ref/ref_core.cpp" -o "$OUT/ref_core.o" &
 $CXX $FLAGS $INC -c "$HERE/ref/ref_laikago.cpp" -o "$OUT/ref_laikago.o" &
 $CXX $FLAGS $INC -c "$HERE/ref/ref_ant.cpp" -o "$OUT/ref_ant.o" &
 $CXX $FLAGS $INC -c "$HERE/ref/ref_world.cpp" -o "$OUT/ref_world.o" &
+$CXX $FLAGS $INC -c "$HERE/ref/ref_rigid.cpp" -o "$OUT/ref_rigid.o" &
 $CXX $FLAGS -I"$REF/third_party/tinyxml2/include" -c "$REF/third_party/tinyxml2/tinyxml2.cpp" -o "$OUT/tinyxml2.o" &
 wait
-$CXX -shared -fopenmp -o "$OUT/libtds_ref.so" "$OUT/ref_core.o" "$OUT/ref_laikago.o" "$OUT/ref_ant.o" "$OUT/ref_world.o" "$OUT/tinyxml2.o"
+$CXX -shared -fopenmp -o "$OUT/libtds_ref.so" "$OUT/ref_core.o" "$OUT/ref_laikago.o" "$OUT/ref_ant.o" "$OUT/ref_world.o" "$OUT/ref_rigid.o" "$OUT/tinyxml2.o"
 rm -f "$OUT"/*.o
 echo "built $OUT/libtds_ref.so"

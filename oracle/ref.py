@@ -74,6 +74,12 @@ def lib():
             L.tdsrefw_set_params.argtypes = [vp, ctypes.c_double, dp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_double]
             L.tdsrefw_step.argtypes = [vp, ctypes.c_int, dp, dp, dp, dp, dp, ip, ip, dp, ctypes.c_int]
+        if hasattr(L, "tdsrefr_create"):
+            L.tdsrefr_create.restype = vp
+            L.tdsrefr_create.argtypes = [dp, ctypes.c_int]
+            L.tdsrefr_destroy.argtypes = [vp]
+            L.tdsrefr_set_params.argtypes = [vp, ctypes.c_double, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+            L.tdsrefr_step.argtypes = [vp, dp, dp, ctypes.c_int, dp, ip]
         L.tdsref_laikago_create.restype = vp
         L.tdsref_laikago_create.argtypes = [ctypes.c_int]
         L.tdsref_laikago_destroy.argtypes = [vp]
@@ -244,6 +250,41 @@ class RefWorld:
             self._L.tdsrefw_step(self._h, mode, _dp(q), _dp(qd), _dp(t), _dp(qo), _dp(qdo), ctypes.byref(nc), _ip(idx), _dp(dat), contact_cap)
         n = min(nc.value, contact_cap)
         return dict(q=qo, qd=qdo, n_contacts=nc.value, contact_idx=idx[:n].copy(), contact_data=dat[:n].copy())
+
+
+class RefRigidWorld:
+    """A reference World of RigidBodys (oracle/ref/ref_rigid.cpp).  desc [n_bodies][6]: mass, shape, p0..p3."""
+
+    def __init__(self, desc):
+        d = np.ascontiguousarray(desc, dtype=np.float64)
+        self.n_bodies = d.shape[0]
+        self._L = lib()
+        self._h = self._L.tdsrefr_create(_dp(d), self.n_bodies)
+        if not self._h:
+            raise RuntimeError("tdsrefr_create failed")
+
+    def close(self):
+        if self._h:
+            self._L.tdsrefr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, dt=1.0 / 60.0, gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0, erp=0.1, num_solver_iterations=1):
+        g = np.asarray(gravity, dtype=np.float64)
+        self._L.tdsrefr_set_params(self._h, dt, _dp(g), friction, restitution, erp, num_solver_iterations)
+
+    def step(self, state, force=None, steps=1):
+        s = np.ascontiguousarray(state, dtype=np.float64)
+        f = None if force is None else np.ascontiguousarray(force, dtype=np.float64)
+        out = np.zeros_like(s)
+        nc = ctypes.c_int(0)
+        self._L.tdsrefr_step(self._h, _dp(s), _dp(f), steps, _dp(out), ctypes.byref(nc))
+        return out, nc.value
 
 
 class LaikagoRef:

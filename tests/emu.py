@@ -140,3 +140,41 @@ def step_spec(name, mode, q, qd, tau=None, precision=0, var=0, use_pd=False, env
 def link_xf_of(out, n, n_links):
     """[n][n_links][12] world transforms (R row-major 9, p 3) from step_spec(var=0)."""
     return out["_xf_flat"][:n * n_links * 12].reshape(n, n_links, 12)
+
+
+# ---- the rigid-body world kernel (csrc/tds_rigid.cu) ---------------------------------------------------------------------------------
+SO_R = os.path.join(HERE, "cpp", "_rigid_host.so")
+SRC_R = os.path.join(HERE, "cpp", "rigid_host.cpp")
+_lib_r = None
+
+
+def lib_rigid():
+    global _lib_r
+    if _lib_r is None:
+        deps = [SRC_R] + [os.path.join(CSRC, f) for f in ("tds_rigid.cu", "tds_math.cuh", "tds_dual.cuh")]
+        if not (os.path.exists(SO_R) and all(os.path.getmtime(d) <= os.path.getmtime(SO_R) for d in deps)):
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-w", "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                                   "-I/usr/local/cuda/include", SRC_R, "-o", SO_R + ".tmp"])
+            os.replace(SO_R + ".tmp", SO_R)
+        L = ctypes.CDLL(SO_R)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.tdsemu_rigid.restype = ctypes.c_int
+        L.tdsemu_rigid.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, dp, dp, ctypes.c_int, dp, dp]
+        _lib_r = L
+    return _lib_r
+
+
+def rigid_step(desc, state, force=None, steps=1, jacobian=False, dt=1.0 / 60.0, gravity=(0.0, 0.0, -9.81), friction=0.5, restitution=0.0,
+               erp=0.1, num_solver_iterations=1):
+    """`steps` World::step calls of every world of state [n][n_bodies][13] through the host-compiled rigid-body kernel."""
+    d = np.ascontiguousarray(desc, dtype=np.float64)
+    s = np.ascontiguousarray(state, dtype=np.float64)
+    n, nb = s.shape[0], d.shape[0]
+    f = None if force is None else np.ascontiguousarray(force, dtype=np.float64)
+    params = np.array([dt, *gravity, friction, restitution, erp, num_solver_iterations], dtype=np.float64)
+    out = np.zeros_like(s)
+    jac = np.zeros((n, 13 * nb, 16 * nb)) if jacobian else None
+    rc = lib_rigid().tdsemu_rigid(_dp(d), nb, _dp(params), n, _dp(s), _dp(f), steps, _dp(out), _dp(jac))
+    if rc:
+        raise RuntimeError(f"tdsemu_rigid rc={rc}")
+    return (out, jac) if jacobian else out

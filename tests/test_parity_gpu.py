@@ -991,3 +991,59 @@ def test_vectorized_env_auto_reset_settles_and_sticky_done():
     second = env.step(np.zeros((n, 12)))
     assert np.array_equal(first.dones > 0, np.arange(n) < 3) and np.array_equal(second.dones > 0, np.arange(n) < 3)
     assert np.all(second.rewards[:3] == 0) and np.all(second.rewards[3:] != 0)
+
+
+# ---- the RigidBody path of World::step -----------------------------------------------------------------------------
+# Added after the round's GPU budget was spent: verified through the host-compiled kernel source (tests/test_rigid_world_on_host.py).
+@pytest.mark.parametrize("kind", wl.RIGID_WORLDS)
+def test_rigid_world_golden_vectors(kind, golden_dir):
+    """csrc/tds_rigid.cu through the C-ABI (tds_b200_rigid_step_host) against the reference's World::step on rigid bodies: 1 and 5
+    steps with an external force before the first; fp64 on both sides."""
+    g = np.load(os.path.join(golden_dir, "rigid_" + kind + ".npz"))
+    params = params_from_golden(g)
+    params["num_solver_iterations"] = int(params["num_solver_iterations"])
+    world = tds_b200.RigidWorld(g["bodies"], g["state"].shape[0], **params)
+    assert np.max(np.abs(world.step(g["state"], g["force"], 1) - g["state_1"])) <= 1e-11
+    assert np.max(np.abs(world.step(g["state"], g["force"], 5) - g["state_5"])) <= 1e-11
+    # device arrays, in place, ragged batch (the last warp is partly empty)
+    import torch
+    n = 40
+    w2 = tds_b200.RigidWorld(g["bodies"], n, **params)
+    nb = w2.n_bodies
+    st = torch.zeros((13 * nb, w2.n_stride), dtype=torch.float64, device="cuda")
+    st[:, :n] = torch.tensor(g["state"][:n].reshape(n, 13 * nb).T)
+    fo = torch.zeros((3 * nb, w2.n_stride), dtype=torch.float64, device="cuda")
+    fo[:, :n] = torch.tensor(g["force"][:n].reshape(n, 3 * nb).T)
+    torch.cuda.synchronize()
+    w2.step_device(st, st, fo, steps=1)
+    w2.step_device(st, st, None, steps=4)
+    torch.cuda.synchronize()
+    assert np.max(np.abs(st[:, :n].cpu().numpy().T.reshape(n, nb, 13) - g["state_5"][:n])) <= 1e-11
+
+
+def test_rigid_world_jacobian_and_pytinydiffsim_names():
+    from oracle import ref
+    import pytinydiffsim as pd
+    w = wl.rigid_world("billiard", 4, seed=5)
+    world = tds_b200.RigidWorld(w["bodies"], 4, **w["params"])
+    out, J = world.step_jacobian(w["state"], w["force"], steps=3)
+    assert J.shape == (4, 91, 112) and np.max(np.abs(out - world.step(w["state"], w["force"], 3))) <= 1e-12
+    if ref.available():
+        rw = ref.RefRigidWorld(w["bodies"])
+        rw.set_params(**w["params"])
+        ok = []
+        for e in range(4):
+            f = lambda x: rw.step(x[:91].reshape(7, 13), x[91:].reshape(7, 3), 3)[0].ravel()
+            Jr = _central_differences(f, np.concatenate([w["state"][e].ravel(), w["force"][e].ravel()]))
+            ok.append(np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-5)
+        assert np.mean(ok) >= 0.75
+    # the reference's Python names (python/pytinydiffsim.inl:336-385): one world of three balls, the billiard loop as one call
+    tw = pd.TinyWorld()
+    tw.gravity = (0.0, 0.0, 0.0)
+    tw.num_solver_iterations = 50
+    balls = [pd.TinyRigidBody(1.0, pd.TinySphere(0.5)) for _ in range(3)]
+    for b, x in zip(balls, (0.0, 0.9, 3.0)):
+        b.world_pose.position = [x, 0.0, 0.0]
+    balls[0].apply_central_force([60.0, 0.0, 0.0])
+    pd.rigid_world_step(tw, balls, 1.0 / 60.0, steps=2)
+    assert balls[1].linear_velocity[0] > 0.1 and abs(balls[2].linear_velocity[0]) < 1e-12   # the first pushes the second, the third is out of reach

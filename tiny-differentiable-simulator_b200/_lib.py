@@ -96,6 +96,18 @@ def lib():
     L.tds_b200_contact_list_device.argtypes = [vp, fp, vp, vp, vp]
     L.tds_b200_contact_list_host.restype = ci
     L.tds_b200_contact_list_host.argtypes = [vp, vp, vp]
+    L.tds_b200_rigid_create.restype = vp
+    L.tds_b200_rigid_create.argtypes = [vp, ci, ci, ci]
+    L.tds_b200_rigid_destroy.restype = None
+    L.tds_b200_rigid_destroy.argtypes = [vp]
+    L.tds_b200_rigid_set_params.restype = ci
+    L.tds_b200_rigid_set_params.argtypes = [vp, ctypes.c_double, vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci]
+    L.tds_b200_rigid_step_device.restype = ci
+    L.tds_b200_rigid_step_device.argtypes = [vp, vp, vp, vp, ci, vp]
+    L.tds_b200_rigid_step_host.restype = ci
+    L.tds_b200_rigid_step_host.argtypes = [vp, vp, vp, ci, vp]
+    L.tds_b200_rigid_jacobian_host.restype = ci
+    L.tds_b200_rigid_jacobian_host.argtypes = [vp, vp, vp, ci, vp, vp]
     L.tds_b200_contact_list_candidates_host.restype = ci
     L.tds_b200_contact_list_candidates_host.argtypes = [vp, vp, vp]
     L.tds_b200_env_set_state_host.restype = ci
@@ -136,6 +148,7 @@ DECLARED_SYMBOLS = [
     "b200_laikago_jacobian", "b200_laikago_jacobian_meta", "b200_laikago_jacobian_allocate", "b200_laikago_jacobian_deallocate",
     "b200_laikago_jacobian_send_local", "b200_laikago_jacobian_send_global",
     "tds_b200_jacobian_dims", "tds_b200_step_jacobian_device", "tds_b200_step_jacobian_host", "tds_b200_integrate_euler_device", "tds_b200_integrate_euler_qdd_device", "tds_b200_contact_pairs", "tds_b200_model_contact_pairs", "tds_b200_contact_list_device", "tds_b200_contact_list_host", "tds_b200_contact_list_candidates_host",
+    "tds_b200_rigid_create", "tds_b200_rigid_destroy", "tds_b200_rigid_set_params", "tds_b200_rigid_step_device", "tds_b200_rigid_step_host", "tds_b200_rigid_jacobian_host",
     "tds_b200_step_device", "tds_b200_step_host", "tds_b200_env_set_state_host",
     "tds_b200_env_get_state_host", "tds_b200_env_step_host", "tds_b200_env_step_device",
     "tds_b200_stream", "tds_b200_env_q", "tds_b200_env_qd", "cuda_model_laikago_forward_zero",

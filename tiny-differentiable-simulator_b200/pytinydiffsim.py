@@ -18,6 +18,7 @@ every compute call raises.
 import numpy as np
 
 from . import _lib
+from . import rigid as _rigid
 from .envs import VectorizedLaikagoEnv, VectorizedLaikagoEnvOutput, VectorizedAntEnv  # noqa: F401
 from .model import compile_urdf, fixture_path, load_model, merge_models
 from .sim import BatchSim, MODE_FD, MODE_NOCONTACT, MODE_FULL, MODE_WORLD
@@ -156,6 +157,80 @@ def integrate_euler(mb, dt):
 
 def integrate_euler_qdd(mb, dt):
     mb._integrate(dt, False)
+
+
+# ---- rigid bodies (python/pytinydiffsim.inl:336-385, 448-455; examples/billiard_optimization.py) --------------------------------
+class TinySphere:
+    def __init__(self, radius):
+        self._record = lambda mass: _rigid.sphere(mass, float(radius))
+        self._radius = float(radius)
+
+    def get_radius(self):
+        return self._radius
+
+
+class TinyCapsule:
+    def __init__(self, radius, length):
+        self._record = lambda mass: _rigid.capsule(mass, float(radius), float(length))
+        self._radius, self._length = float(radius), float(length)
+
+    def get_radius(self):
+        return self._radius
+
+    def get_length(self):
+        return self._length
+
+
+class TinyPlane:
+    def __init__(self):
+        self._record = lambda mass: _rigid.plane()
+
+    def get_normal(self):
+        return (0.0, 0.0, 1.0)
+
+    def get_constant(self):
+        return 0.0
+
+
+class TinyPose:
+    def __init__(self, position=(0.0, 0.0, 0.0), orientation=(0.0, 0.0, 0.0, 1.0)):
+        self.position, self.orientation = list(position), list(orientation)     # orientation: quaternion x, y, z, w
+
+
+class TinyRigidBody:
+    """RigidBody (src/rigid_body.hpp): state holder on the host; the arithmetic runs on the GPU in rigid_world_step."""
+
+    def __init__(self, mass, geometry):
+        self.mass, self.collision_geometry = float(mass), geometry
+        self.world_pose = TinyPose()
+        self.linear_velocity, self.angular_velocity = [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+        self.total_force = [0.0, 0.0, 0.0]
+
+    def apply_central_force(self, force):
+        self.total_force = [a + float(b) for a, b in zip(self.total_force, force)]
+
+    def clear_forces(self):
+        self.total_force = [0.0, 0.0, 0.0]
+
+
+def rigid_world_step(world, bodies, dt, steps=1):
+    """The stepping loop of python/examples/billiard_optimization.py:118-131 (= World::step on rigid bodies, src/world.hpp:293-363)
+    as ONE call: apply_gravity / apply_force_impulse / clear_forces, compute_contacts_rigid_body, num_solver_iterations sweeps of
+    resolve_collision over the contacts, integrate - `steps` times, on the GPU (csrc/tds_rigid.cu).  Updates the bodies in place."""
+    key = tuple(id(b) for b in bodies)
+    if getattr(world, "_rigid_key", None) != key:
+        world._rigid = _rigid.RigidWorld([b.collision_geometry._record(b.mass) for b in bodies], 1)
+        world._rigid_key = key
+    world._rigid.set_params(dt=dt, gravity=tuple(world.gravity), friction=world.friction, restitution=world.restitution,
+                            num_solver_iterations=world.num_solver_iterations)
+    state = np.array([[list(b.world_pose.position) + list(b.world_pose.orientation) + list(b.linear_velocity) + list(b.angular_velocity)
+                       for b in bodies]], dtype=np.float64)
+    force = np.array([[b.total_force for b in bodies]], dtype=np.float64)
+    out = world._rigid.step(state, force, steps)[0]
+    for b, s in zip(bodies, out):
+        b.world_pose.position, b.world_pose.orientation = list(s[0:3]), list(s[3:7])
+        b.linear_velocity, b.angular_velocity = list(s[7:10]), list(s[10:13])
+        b.clear_forces()
 
 
 class CartpoleEnvOutput:

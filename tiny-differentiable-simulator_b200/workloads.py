@@ -253,3 +253,42 @@ def multibody_world(kind, n, seed=SEED):
             off += 1
     tau = r.uniform(-1.0, 1.0, (n, n_qd))
     return dict(model=model, q=_f32(q), qd=_f32(qd), tau=_f32(tau), params=dict(friction=0.7, keep_all_points=False), mode=2)
+
+
+# ---- worlds of rigid bodies (the RigidBody path of World::step) -------------------------------------------------------------------
+RIGID_WORLDS = ("billiard", "stack", "swapped")
+
+
+def rigid_world(kind, n, seed=SEED):
+    """bodies (tds_b200.rigid records), states [n][n_bodies][13], forces [n][n_bodies][3] and World parameters of the test worlds.
+    billiard: the seven balls of python/examples/billiard_optimization.py (no gravity, 50 solver iterations); stack: plane, two
+    spheres, a capsule and a box under gravity; swapped: bodies listed so that the dispatcher's swapped calls are taken, tilted
+    plane with a non-zero constant."""
+    from . import rigid as rg
+    r = np.random.default_rng(seed)
+    if kind == "billiard":
+        bodies = [rg.sphere(1.0, 0.5)] * 7
+        params = dict(gravity=(0.0, 0.0, 0.0), num_solver_iterations=50)
+    elif kind == "stack":
+        bodies = [rg.plane(), rg.sphere(1.0, 0.3), rg.sphere(2.0, 0.2), rg.capsule(1.5, 0.15, 0.6), rg.box(2.0, (0.4, 0.3, 0.2))]
+        params = dict(num_solver_iterations=50, friction=0.6)
+    elif kind == "swapped":
+        bodies = [rg.sphere(1.0, 0.3), rg.capsule(1.5, 0.15, 0.6), rg.plane((0.1, 0.0, 1.0), 0.05), rg.box(2.0, (0.4, 0.3, 0.2))]
+        params = dict(num_solver_iterations=10, restitution=0.3, erp=0.2)
+    else:
+        raise ValueError(kind)
+    desc = np.asarray(bodies, dtype=np.float64)
+    nb = desc.shape[0]
+    s = np.zeros((n, nb, 13))
+    s[:, :, 0:2] = r.uniform(-0.6, 0.6, (n, nb, 2)) * (2.5 if kind == "billiard" else 1.0)
+    s[:, :, 2] = 0.0 if kind == "billiard" else r.uniform(0.05, 0.5, (n, nb))
+    q = r.normal(size=(n, nb, 4))
+    s[:, :, 3:7] = q / np.linalg.norm(q, axis=2, keepdims=True)
+    s[:, :, 7:10] = r.uniform(-1, 1, (n, nb, 3))
+    s[:, :, 10:13] = r.uniform(-1, 1, (n, nb, 3))
+    for b in range(nb):
+        if desc[b, 1] == rg.PLANE:
+            s[:, b, :] = 0.0
+            s[:, b, 6] = 1.0
+    f = r.uniform(-50, 50, (n, nb, 3))
+    return dict(bodies=desc, state=s, force=f, params=params)
