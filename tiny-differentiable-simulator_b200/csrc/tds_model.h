@@ -160,8 +160,9 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
       D->g_radius[g] = r;
       if (D->has_plane) D->world_only = 1;
     }
-    // the contact stage implements plane x {sphere, capsule, box}; a mesh against the ground plane would be silently
-    // contact-free here while the reference collides it: refuse the model
+    // the contact stage implements plane x {sphere, capsule, box}.  The reference has no mesh COLLISION shapes at all
+    // (TINY_MESH_TYPE is "only for visual shapes", src/geometry.hpp:34; its URDF loader drops them, urdf_to_multi_body.hpp:234-277,
+    // and so does ours): a flat model carrying one is malformed rather than something to simulate - refuse it
     if (D->has_plane && D->g_type[g] != TDSG_SPHERE && D->g_type[g] != TDSG_CAPSULE && D->g_type[g] != TDSG_BOX) return -6;
   }
   if (D->has_plane && n_points > TDS_MAX_POINTS) return -2;
