@@ -1047,3 +1047,26 @@ def test_rigid_world_jacobian_and_pytinydiffsim_names():
     balls[0].apply_central_force([60.0, 0.0, 0.0])
     pd.rigid_world_step(tw, balls, 1.0 / 60.0, steps=2)
     assert balls[1].linear_velocity[0] > 0.1 and abs(balls[2].linear_velocity[0]) < 1e-12   # the first pushes the second, the third is out of reach
+
+
+@pytest.mark.parametrize("name,cls,n_rec", [("laikago", "VectorizedLaikagoEnv", 17), ("ant", "VectorizedAntEnv", 9)])
+def test_vectorized_env_visual_world_transforms(name, cls, n_rec, golden_dir):
+    """pytinydiffsim.Vectorized*Env.step(...).visual_world_transforms: the rows of the reference's env output
+    (q | qd | per-visual pos3 + quat4 | up.z, locomotion_contact_simulation.h:273-303) from the same step."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n = g["q_in"].shape[0]
+    env = getattr(tds_b200, cls)(n, auto_reset_when_done=False, with_visual_transforms=True)
+    env.sim.env_set_state(g["q_in"], g["qd_in"])
+    out = env.step(g["action"])
+    ref = g["env_output_templated"]
+    nq = g["q_in"].shape[1] * 2
+    vw = out.visual_world_transforms
+    assert vw.shape == ref.shape and vw.dtype == np.float32
+    assert rel_err(vw[:, 2:nq].astype(np.float64), ref[:, 2:nq]) <= TOL
+    assert np.max(np.abs(vw[:, nq:nq + n_rec * 7] - ref[:, nq:nq + n_rec * 7])) < 5e-6
+    assert np.array_equal(vw[:, nq + n_rec * 7], ref[:, nq + n_rec * 7].astype(np.float32))
+    assert np.array_equal(out.dones, g["env_done"].astype(np.float32))
+    plain = getattr(tds_b200, cls)(n, auto_reset_when_done=False)
+    plain.sim.env_set_state(g["q_in"], g["qd_in"])
+    o2 = plain.step(g["action"])
+    assert o2.visual_world_transforms is None and np.array_equal(o2.obs, out.obs) and np.array_equal(o2.rewards, out.rewards)

@@ -47,9 +47,13 @@ class VectorizedLaikagoEnvOutput:
 
 
 class VectorizedLaikagoEnv:
-    def __init__(self, num_envs, auto_reset_when_done=True, device=0, seed=12345, model=None):
+    def __init__(self, num_envs, auto_reset_when_done=True, device=0, seed=12345, model=None, with_visual_transforms=False):
+        """with_visual_transforms: also return the reference's `visual_world_transforms` rows from step() (off by default: the
+        plain step moves 200 B per environment over PCIe, the rows 1.6 KB)."""
         self.num_envs = num_envs
         self.auto_reset = auto_reset_when_done
+        self.with_visual_transforms = bool(with_visual_transforms)
+        self._output_dim = 411     # cuda_model_laikago_forward_zero_meta().output_dim
         self.sim = laikago_sim(num_envs, device=device, model=model)
         self.rng = np.random.default_rng(seed)
         self._obs = np.zeros((num_envs, self.obs_dim()), dtype=np.float32)
@@ -93,10 +97,47 @@ class VectorizedLaikagoEnv:
             noise = 0.05 * (self.rng.random((self.num_envs, self.action_dim())) - 0.5) * 2.0
         return self.sim.env_rollout_host(policies, rollout_length, shift=shift, noise=noise)
 
+    def output_dim(self):
+        """LocomotionContactSimulation::output_dim(): q | qd | one (pos3, quat4) record per link x visual slot | up.z
+        (locomotion_contact_simulation.h:75-77; 411 for Laikago, 155 for Ant - only the first n_visuals records are written)."""
+        return self._output_dim
+
+    def _step_with_visuals(self, a):
+        """The step through tds_b200_env_step_visual_device: same physics, plus the per-visual world transforms of the step
+        (locomotion_contact_simulation.h:281-299) - returned as the reference's `visual_world_transforms` rows
+        q | qd | n_visuals x (pos3, quat xyzw) | up.z (= 1: fixed-base emulation, :131) | unwritten tail (zeros)."""
+        import torch
+        sim, n = self.sim, self.num_envs
+        nv = sim.num_visuals()
+        if not hasattr(self, "_vis"):
+            dev = f"cuda:{sim.device}"
+            self._vis = dict(act=sim.alloc(self.action_dim()), rew=sim.alloc(1), done=sim.alloc(1),
+                             pos=torch.zeros((n * nv, 4), device=dev), quat=torch.zeros((n * nv, 4), device=dev))
+        v = self._vis
+        v["act"][:, :n] = torch.from_numpy(np.ascontiguousarray(a.T)).to(v["act"].device)
+        torch.cuda.synchronize(v["act"].device)
+        sim.env_step_visual_device(v["act"], v["pos"], v["quat"], reward=v["rew"], done=v["done"])
+        torch.cuda.synchronize(v["act"].device)
+        q, qd = sim.env_get_state()
+        self._obs[:, :sim.n_q], self._obs[:, sim.n_q:] = q, qd
+        self._rew[:] = v["rew"][0, :n].cpu().numpy()
+        self._done[:] = v["done"][0, :n].cpu().numpy()
+        out = np.zeros((n, self._output_dim), dtype=np.float32)
+        nq = sim.n_q + sim.n_qd
+        out[:, :nq] = self._obs
+        rec = np.concatenate([v["pos"].cpu().numpy().reshape(n, nv, 4)[:, :, :3], v["quat"].cpu().numpy().reshape(n, nv, 4)], axis=2)
+        out[:, nq:nq + nv * 7] = rec.reshape(n, nv * 7)
+        out[:, nq + nv * 7] = 1.0
+        return out
+
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float32)
         assert a.shape == (self.num_envs, self.action_dim())
-        self.sim.env_step_host(a, self._obs, self._rew, self._done)
+        visuals = None
+        if self.with_visual_transforms:
+            visuals = self._step_with_visuals(a)
+        else:
+            self.sim.env_step_host(a, self._obs, self._rew, self._done)
         obs = self._obs.copy()
         rewards, dones = self._rew.copy(), self._done.copy()
         if self.auto_reset and dones.any():
@@ -122,7 +163,7 @@ class VectorizedLaikagoEnv:
             self._was_done = dones > 0
         obs[:, 0] = 0.0  # ars_vectorized_environment.h:285-287
         obs[:, 1] = 0.0
-        return VectorizedLaikagoEnvOutput(obs, rewards, dones)
+        return VectorizedLaikagoEnvOutput(obs, rewards, dones, visuals)
 
 
 ANT_INITIAL_POSES = np.array([0.0, -0.5] * 4)        # ant_environment2.h:43-54
@@ -152,9 +193,11 @@ class VectorizedAntEnv(VectorizedLaikagoEnv):
     """pytinydiffsim.VectorizedAntEnv (python/pytinydiffsim_includes.h:58-141): same vectorized environment template
     as the Laikago one, over AntContactSimulation2 (8 actions, 28 observations)."""
 
-    def __init__(self, num_envs, auto_reset_when_done=True, device=0, seed=12345, model=None):
+    def __init__(self, num_envs, auto_reset_when_done=True, device=0, seed=12345, model=None, with_visual_transforms=False):
         self.num_envs = num_envs
         self.auto_reset = auto_reset_when_done
+        self.with_visual_transforms = bool(with_visual_transforms)
+        self._output_dim = 155     # cuda_model_ant_forward_zero_meta().output_dim
         self.sim = ant_sim(num_envs, device=device, model=model)
         self.rng = np.random.default_rng(seed)
         self._obs = np.zeros((num_envs, self.obs_dim()), dtype=np.float32)
