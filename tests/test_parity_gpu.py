@@ -1069,4 +1069,6 @@ def test_vectorized_env_visual_world_transforms(name, cls, n_rec, golden_dir):
     plain = getattr(tds_b200, cls)(n, auto_reset_when_done=False)
     plain.sim.env_set_state(g["q_in"], g["qd_in"])
     o2 = plain.step(g["action"])
-    assert o2.visual_world_transforms is None and np.array_equal(o2.obs, out.obs) and np.array_equal(o2.rewards, out.rewards)
+    # (another instance of the kernel serves the plain step: equal to fp32 round-off, not bit for bit)
+    assert o2.visual_world_transforms is None and rel_err(o2.obs.astype(np.float64), out.obs.astype(np.float64)) <= 1e-5
+    assert np.max(np.abs(o2.rewards - out.rewards)) <= 1e-4 * max(1.0, np.max(np.abs(out.rewards)))
