@@ -173,3 +173,51 @@ def test_world_of_urdf_multibodies_vs_live_reference():
         assert rel_err(out["q"][i], r["q"]) <= TOL and rel_err(out["qd"][i], r["qd"]) <= TOL
         hit += int(np.any((r["contact_idx"][:, 0] == 2) & (r["contact_data"][:, 9] < 0)))
     assert hit >= 8   # contacts between the two multibodies do occur
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_worlds_of_multibodies_vs_live_reference(seed):
+    """Differential fuzzing of the contact stage between multibodies: two to four random free bodies (1-3 spheres / capsules each at
+    random offsets, some on xyz + spherical joints, some with an extra revolute arm), random solver parameters."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(4400 + seed)
+    spherical = bool(seed % 2)
+    bodies, dofs = [], []
+    for b in range(int(rng.integers(2, 5))):
+        geoms = []
+        for _ in range(int(rng.integers(1, 4))):
+            off = tuple(rng.uniform(-0.25, 0.25, 3))
+            if rng.random() < 0.5:
+                geoms.append(("sphere", float(rng.uniform(0.1, 0.3)), off))
+            else:
+                geoms.append(("capsule", float(rng.uniform(0.08, 0.15)), float(rng.uniform(0.2, 0.6)), off, wl._rot_y(float(rng.uniform(-1.5, 1.5)))))
+        arm = (0.4, 0.3, 0.1) if (not spherical and rng.random() < 0.4) else None
+        m = float(rng.uniform(0.5, 3.0))
+        bodies.append(wl.free_body_model(m, tuple(rng.uniform(0.02, 0.1, 3)), geoms, arm=arm, spherical=spherical))
+        dofs.append((int(bodies[-1][3]), int(bodies[-1][4])))
+    world = merge_models(bodies)
+    n, nq, nqd = 12, int(world[3]), int(world[4])
+    q, qd, tau = np.zeros((n, nq)), rng.uniform(-1, 1, (n, nqd)), rng.uniform(-1, 1, (n, nqd))
+    centre = rng.uniform(-0.3, 0.3, (n, 2))
+    o = 0
+    for bq, _ in dofs:
+        q[:, o:o + 2] = centre + rng.uniform(-0.25, 0.25, (n, 2)); q[:, o + 2] = rng.uniform(0.1, 0.5, n)
+        if spherical:
+            v = rng.normal(size=(n, 4)); q[:, o + 3:o + 7] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        else:
+            q[:, o + 3:o + bq] = rng.uniform(-1, 1, (n, bq - 3))
+        o += bq
+    q, qd, tau = wl._f32(q), wl._f32(qd), wl._f32(tau)
+    params = dict(friction=float(rng.uniform(0.2, 1.0)), restitution=float(rng.uniform(0, 0.5)), pgs_iterations=int(rng.integers(1, 5)),
+                  keep_all_points=bool(seed % 3 == 0))
+    rw = ref.RefWorld(world)
+    rw.set_params(**params)
+    out = emu.step(world, 2, q, qd, tau, precision=1, **params)
+    pair_hits = 0
+    for i in range(n):
+        r = rw.step(2, q[i], qd[i], tau[i], contact_cap=128)
+        assert rel_err(out["q"][i], r["q"]) <= TOL and rel_err(out["qd"][i], r["qd"]) <= TOL
+        pair_hits += int(np.any((r["contact_idx"][:, 0] >= len(bodies)) & (r["contact_data"][:, 9] < 0)))
+    assert pair_hits >= 1   # contacts between multibodies do occur in the sample
