@@ -185,3 +185,47 @@ def test_random_models_through_the_kernel_source_vs_live_reference(seed, tmp_pat
                 assert rel_err(out["qdd"][i], r["qdd"]) <= TOL
             else:
                 assert rel_err(out["q"][i], r["q"]) <= TOL and rel_err(out["qd"][i], r["qd"]) <= TOL
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dual_number_jacobian_on_random_models_vs_reference(seed, tmp_path):
+    """The differentiable instance on random trees (spherical joints, oblique axes, floating bases: derivatives with respect to the
+    raw quaternion components, as the reference's own differentiation would see them) against central differences of the
+    reference: forward dynamics and the contact-free step (smooth maps: every environment must agree)."""
+    from oracle import ref
+    from tds_b200.model import compile_urdf
+    from test_model_compiler import _random_urdf
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7000 + seed)
+    text = _random_urdf(rng, int(rng.integers(2, 7)), massless_links=False, boxes=False)
+    if seed % 2 == 0:
+        text = text.replace('type="continuous"', 'type="spherical"', 1)
+    path = tmp_path / "rnd.urdf"
+    path.write_text(text)
+    floating = bool(seed % 2) and "spherical" not in text
+    model = compile_urdf(str(path), None, floating)
+    rs = ref.RefSim.from_model(model)
+    rs.set_params()
+    n, nq, nqd, nt = 2, rs.n_q, rs.n_qd, rs.n_tau
+    if nqd == 0:
+        pytest.skip("a tree of fixed joints")
+    q, qd, tau = rng.uniform(-0.8, 0.8, (n, nq)), rng.uniform(-1, 1, (n, nqd)), rng.uniform(-2, 2, (n, max(nt, 1)))[:, :nt]
+    for l in model[16 + 13:16 + 13 + int(model[1]) * 34].reshape(-1, 34):
+        if int(l[1]) == 8:
+            k = int(l[2]); v = rng.normal(size=(n, 4)); q[:, k:k + 4] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    if floating:
+        v = rng.normal(size=(n, 4)); q[:, :4] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    q, qd, tau = (a.astype(np.float32).astype(np.float64) for a in (q, qd, tau))
+    for mode in (0, 1):
+        J = emu.step(model, mode, q, qd, tau if nt else None, jacobian=True)["jac"]
+        for e in range(n):
+            def f(x):
+                r = rs.step(mode, x[:nq], x[nq:nq + nqd], x[nq + nqd:] if nt else None)
+                return r["qdd"] if mode == 0 else np.concatenate([r["q"], r["qd"]])
+            x0 = np.concatenate([q[e], qd[e], tau[e]])
+            Jr = np.zeros((f(x0).size, x0.size))
+            for j in range(x0.size):
+                xp, xm = x0.copy(), x0.copy(); xp[j] += 1e-6; xm[j] -= 1e-6
+                Jr[:, j] = (f(xp) - f(xm)) / 2e-6
+            assert np.max(np.abs(J[e] - Jr) / np.maximum(1.0, np.abs(Jr))) <= 1e-6
