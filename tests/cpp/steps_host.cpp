@@ -54,17 +54,30 @@ alignas(16) char* g_smem = nullptr;
 #define __launch_bounds__(...)
 #define smem_raw emu_smem_raw
 
+#ifdef TDSEMU_SPEC_TEST   // -I<dir with spec_test.h>: a model compiled by csrc/gen_spec.cpp for this build (random robots of the tests)
+#include "spec_test.h"
+#endif
 #include "../../tiny-differentiable-simulator_b200/csrc/tds_steps.cu"
+#ifdef TDSEMU_SPEC_TEST
+TDS_SPEC_TABLES(SpecTest, test)
+typedef SpecTest SpecB;   // spec index 1
+#else
+typedef SpecAnt SpecB;
+#endif
 
-namespace tdss { alignas(16) char emu_smem_raw[256 * 1024]; }   // the tile's shared memory (block-scope extern in the kernel)
+namespace tdss { alignas(16) char emu_smem_raw[1024 * 1024]; }   // the tile's shared memory (block-scope extern in the kernel)
 
 namespace {
 int g_whole_tile = 0;
 // whole_tile 1: a tile = one CTA of 128 host threads, all alive at once - exact (the host-layout instance stages the tile's actions /
 // observations cooperatively; __syncthreads_or is tile-wide) but slow on the host.  0: one lane at a time, its four role threads only
 // (the lanes of the device-layout instances never talk to each other, only the roles do; the tile-wide OR is covered by force_or).
+int g_rc = 0;
 template <class SP, typename RA, typename RC, typename RS, int VAR>
 void run(const SimParams& P, const EnvParams& E, const StepIO& io, int mode, int use_pd) {
+  // (instances whose tile exceeds the 227 KB a CTA can have on the device are never selected by the library - see
+  // tdsemu_steps_tile_bytes - but their arithmetic can still be checked here: the host "shared memory" is 1 MB)
+  if ((size_t)tdss::Lay<SP, RA, RC, RS>::TOTAL * 32 * 4 > sizeof(tdss::emu_smem_raw)) { g_rc = -2; return; }
   const int tiles = (io.n + 31) / 32;
   for (int t = 0; t < tiles; ++t)
     for (int lane0 = 0; lane0 < (g_whole_tile ? 1 : 32); ++lane0) {
@@ -97,6 +110,7 @@ int tdsemu_steps(int spec, const double* params, const double* env, int precisio
                  const double* q, const double* qd, const double* tau, double* q_out, double* qd_out, double* qdd_out,
                  double* reward, double* done, double* contact_dist, double* link_xf, double* obs_aos, double* obs_tail) {
   emu::g_force_or = flags & 1;
+  g_rc = 0;
   g_whole_tile = (flags >> 1) & 1;
   if (var == 2 && !g_whole_tile) return -1;
   SimParams P;
@@ -107,17 +121,17 @@ int tdsemu_steps(int spec, const double* params, const double* env, int precisio
   P.pgs_iterations = (int)params[8]; P.keep_all_points = (int)params[9];
   EnvParams E;
   memset(&E, 0, sizeof(E));
-  const int n_q = spec == 0 ? SpecLaikago::N_Q : SpecAnt::N_Q, n_qd = spec == 0 ? SpecLaikago::N_QD : SpecAnt::N_QD;
-  const int n_act_model = spec == 0 ? SpecLaikago::N_ACT : SpecAnt::N_ACT;
-  const int n_cand = spec == 0 ? SpecLaikago::N_CAND : SpecAnt::N_CAND, n_links = spec == 0 ? SpecLaikago::N_LINKS : SpecAnt::N_LINKS;
+  const int n_q = spec == 0 ? SpecLaikago::N_Q : SpecB::N_Q, n_qd = spec == 0 ? SpecLaikago::N_QD : SpecB::N_QD;
+  const int n_act_model = spec == 0 ? SpecLaikago::N_ACT : SpecB::N_ACT;
+  const int n_cand = spec == 0 ? SpecLaikago::N_CAND : SpecB::N_CAND, n_links = spec == 0 ? SpecLaikago::N_LINKS : SpecB::N_LINKS;
   if (env) {
     E.n_act = (int)env[0]; E.start_link = (int)env[1];
     E.kp = (float)env[2]; E.kd = (float)env[3]; E.max_force = (float)env[4]; E.action_limit = (float)env[5];
     E.reward_kind = (int)env[6]; E.auto_reset = (int)env[7];
-    for (int k = 0; k < E.n_act; ++k) { E.initial_poses[k] = (float)env[8 + k]; E.act_link[k] = spec == 0 ? SpecLaikago::ACT_LINK[k] : SpecAnt::ACT_LINK[k]; }
+    for (int k = 0; k < E.n_act; ++k) { E.initial_poses[k] = (float)env[8 + k]; E.act_link[k] = spec == 0 ? SpecLaikago::ACT_LINK[k] : SpecB::ACT_LINK[k]; }
     for (int k = 0; k < n_q; ++k) E.reset_q[k] = (float)env[8 + E.n_act + k];
   }
-  const int floating = spec == 0 ? SpecLaikago::FLOATING : SpecAnt::FLOATING;
+  const int floating = spec == 0 ? SpecLaikago::FLOATING : SpecB::FLOATING;
   const int ns = (n + 31) & ~31, n_in = use_pd ? n_act_model : n_qd - (floating ? 6 : 0), n_obs = n_q + n_qd;
   std::vector<float> sq((size_t)n_q * ns), sqd((size_t)n_qd * ns), st((size_t)n_in * ns, 0.f), oq(sq.size()), oqd(sqd.size()), oqdd(sqd.size()), orew(ns), odone(ns);
   std::vector<float> ocd((size_t)n_cand * ns), oxf((size_t)n_links * 12 * ns), aos((size_t)n_in * ns, 0.f), oobs((size_t)n_obs * ns), otail(2 * (size_t)ns);
@@ -134,11 +148,15 @@ int tdsemu_steps(int spec, const double* params, const double* env, int precisio
   if (var == 0) { io.contact_dist = contact_dist ? ocd.data() : nullptr; io.link_xf = link_xf ? oxf.data() : nullptr; }
   if (var == 2) { io.act_aos = aos.data(); io.obs_aos = oobs.data(); io.obs_tail = otail.data(); }
   io.n = n; io.n_stride = ns;
+#ifdef TDSEMU_SPEC_TEST   // (only the general instance, to keep the build of a test-time model short)
+#define TDSEMU_LEAN(SP, A, C, S) else g_rc = -3;
+#else
+#define TDSEMU_LEAN(SP, A, C, S) else if (var == 1) run<SP, A, C, S, 1>(P, E, io, mode, use_pd); else run<SP, A, C, S, 2>(P, E, io, mode, use_pd);
+#endif
 #define RUN3(SP, A, C, S)                                                                         \
   do {                                                                                            \
     if (var == 0) run<SP, A, C, S, 0>(P, E, io, mode, use_pd);                                    \
-    else if (var == 1) run<SP, A, C, S, 1>(P, E, io, mode, use_pd);                               \
-    else run<SP, A, C, S, 2>(P, E, io, mode, use_pd);                                             \
+    TDSEMU_LEAN(SP, A, C, S)                                                                      \
   } while (0)
 #define RUN(SP)                                                                                   \
   do {                                                                                            \
@@ -146,7 +164,7 @@ int tdsemu_steps(int spec, const double* params, const double* env, int precisio
     else if (precision == 1) RUN3(SP, double, double, double);                                    \
     else RUN3(SP, float, float, float);                                                           \
   } while (0)
-  if (spec == 0) RUN(SpecLaikago); else RUN(SpecAnt);
+  if (spec == 0) RUN(SpecLaikago); else RUN(SpecB);
 #undef RUN
 #undef RUN3
   for (int e = 0; e < n; ++e) {
@@ -160,6 +178,12 @@ int tdsemu_steps(int spec, const double* params, const double* env, int precisio
     if (obs_aos && var == 2) for (int k = 0; k < n_obs; ++k) obs_aos[(size_t)e * n_obs + k] = oobs[(size_t)e * n_obs + k];
     if (obs_tail && var == 2) { obs_tail[e] = otail[e]; obs_tail[n + e] = otail[n + e]; }
   }
-  return n_cand;
+  return g_rc ? g_rc : n_cand;
+}
+// bytes of shared memory one tile of the instance needs (the library selects the kernel only if this fits the device's opt-in limit)
+long tdsemu_steps_tile_bytes(int spec, int precision) {
+#define TB(SP) (precision == 0 ? (long)tdss::Lay<SP, float, double, float>::TOTAL : precision == 1 ? (long)tdss::Lay<SP, double, double, double>::TOTAL : (long)tdss::Lay<SP, float, float, float>::TOTAL) * 32 * 4
+  return spec == 0 ? TB(SpecLaikago) : TB(SpecB);
+#undef TB
 }
 }  // extern "C"

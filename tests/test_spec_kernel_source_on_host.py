@@ -189,3 +189,106 @@ def test_auto_reset_inside_the_kernel():
     assert d[:3].all() and not d.all()
     assert np.allclose(out["q"][d], reset_q.astype(np.float32)) and np.all(out["qd"][d] == 0)
     assert np.array_equal(out["q"][~d], keep["q"][~d]) and np.array_equal(out["qd"][~d], keep["qd"][~d])
+
+
+def _random_quadruped_urdf(rng, leg_len, trunk_geom):
+    """A random robot of the class the specialised kernel serves: xyz + xyz-rotation root chain (the reference's fixed-base
+    emulation of a free trunk), four legs of `leg_len` revolute links each - the same joint kinds / shapes at the same depth in every
+    leg (one structural class), every length, axis offset, mass, inertia and shape size drawn per leg - and optionally fixed toes."""
+    v3 = lambda lo, hi: " ".join("%.6g" % x for x in rng.uniform(lo, hi, 3))
+    inert = lambda m, I: f'<mass value="{m:.6g}"/><inertia ixx="{I[0]:.6g}" iyy="{I[1]:.6g}" izz="{I[2]:.6g}" ixy="0" ixz="0" iyz="0"/>'
+    parts = ['<?xml version="1.0"?>', '<robot name="q">', '<link name="world"/>']
+    prev = "world"
+    for k, (ax, ty) in enumerate([("1 0 0", "prismatic"), ("0 1 0", "prismatic"), ("0 0 1", "prismatic"), ("1 0 0", "continuous"),
+                                  ("0 1 0", "continuous"), ("0 0 1", "continuous")]):
+        last = k == 5
+        name = "body" if last else f"c{k}"
+        col = (f'<collision><origin xyz="0 0 0"/><geometry><sphere radius="{rng.uniform(0.1, 0.2):.4g}"/></geometry></collision>'
+               if (last and trunk_geom) else "")
+        body = inert(rng.uniform(2, 8), rng.uniform(0.02, 0.3, 3)) if last else inert(0.0, np.zeros(3))
+        parts.append(f'<link name="{name}"><inertial><origin xyz="0 0 0"/>{body}</inertial>{col}</link>')
+        parts.append(f'<joint name="j{k}" type="{ty}"><parent link="{prev}"/><child link="{name}"/><origin xyz="0 0 0"/><axis xyz="{ax}"/></joint>')
+        prev = name
+    axes = [rng.choice(["1 0 0", "0 1 0", "0 0 1", "0 -1 0", "0.6 0 0.8"]) for _ in range(leg_len)]
+    toe_fixed = rng.random() < 0.7
+    geom_kind = [int(rng.integers(0, 3)) for _ in range(leg_len)]   # per depth: none / sphere / capsule
+    for leg in range(4):
+        par = "body"
+        for d in range(leg_len):
+            name = f"l{leg}_{d}"
+            col = ""
+            if geom_kind[d] == 1:
+                col = f'<collision><origin xyz="{v3(-0.05, 0.05)}"/><geometry><sphere radius="{rng.uniform(0.03, 0.08):.4g}"/></geometry></collision>'
+            if geom_kind[d] == 2:
+                col = (f'<collision><origin xyz="{v3(-0.05, 0.05)}" rpy="{v3(-1, 1)}"/><geometry><capsule radius="{rng.uniform(0.03, 0.06):.4g}" '
+                       f'length="{rng.uniform(0.1, 0.3):.4g}"/></geometry></collision>')
+            parts.append(f'<link name="{name}"><inertial><origin xyz="{v3(-0.05, 0.05)}" rpy="{v3(-0.5, 0.5)}"/>'
+                         f'{inert(rng.uniform(0.2, 1.5), rng.uniform(1e-3, 0.05, 3))}</inertial>{col}</link>')
+            parts.append(f'<joint name="j{leg}_{d}" type="continuous"><parent link="{par}"/><child link="{name}"/>'
+                         f'<origin xyz="{v3(-0.3, 0.3)}" rpy="{v3(-0.5, 0.5)}"/><axis xyz="{axes[d]}"/></joint>')
+            par = name
+        if toe_fixed:
+            parts.append(f'<link name="toe{leg}"><inertial><origin xyz="0 0 0"/>{inert(0.0, np.zeros(3))}</inertial><collision><origin xyz="0 0 0"/>'
+                         f'<geometry><sphere radius="{rng.uniform(0.02, 0.05):.4g}"/></geometry></collision></link>')
+            parts.append(f'<joint name="jt{leg}" type="fixed"><parent link="{par}"/><child link="toe{leg}"/><origin xyz="{v3(-0.1, 0.1)}"/></joint>')
+    parts.append("</robot>")
+    return "\n".join(parts)
+
+
+@pytest.mark.parametrize("seed", [2, 3])
+def test_model_compiler_and_specialised_kernel_on_random_robots(seed, tmp_path):
+    """Not only Laikago and Ant: a random quadruped goes through our URDF compiler, the ahead-of-time model compiler of the
+    specialised kernel (csrc/gen_spec.cpp -> constexpr tables) and the kernel source itself (host build with that model), and must
+    step like the reference built from the same flat model - forward dynamics, contact-free step and full step with dozens of
+    penetrating points, 1 and 2 Gauss-Seidel sweeps.  fp64 arithmetic meets the 1e-5 bar with three orders of margin; the mixed
+    arithmetic is reported against a looser bound (its error is model- and state-dependent: violent random states here)."""
+    import ctypes
+    import subprocess
+    from oracle import ref
+    from tds_b200.model import compile_urdf
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(seed)
+    leg_len = int(rng.integers(2, 4))
+    (tmp_path / "q.urdf").write_text(_random_quadruped_urdf(rng, leg_len, bool(seed % 2)))
+    model = compile_urdf(str(tmp_path / "q.urdf"), os.path.join(GOLDEN, "urdf", "plane.urdf"), False)
+    with open(tmp_path / "model.inc", "w") as f:
+        vals = [repr(float(v)) for v in model]
+        f.write("// flat model\n" + "".join(", ".join(vals[i:i + 6]) + ",\n" for i in range(0, len(vals), 6)))
+    inc = ["-I" + emu.CSRC, "-I" + os.path.join(emu.ROOT, "include")]
+    subprocess.check_call(["g++", "-std=c++17", "-O1"] + inc + [os.path.join(emu.CSRC, "gen_spec.cpp"), "-o", str(tmp_path / "gen_spec")])
+    subprocess.check_call([str(tmp_path / "gen_spec"), "SpecTest", str(tmp_path / "model.inc"), str(4 * leg_len), "6", str(tmp_path / "spec_test.h")])
+    so = str(tmp_path / "_steps_test.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-DTDSEMU_SPEC_TEST", "-I" + str(tmp_path)] + inc +
+                          ["-I/usr/local/cuda/include", emu.SRC_S, "-o", so])
+    L = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.tdsemu_steps.restype = ctypes.c_int
+    L.tdsemu_steps.argtypes = [ctypes.c_int, dp, dp] + [ctypes.c_int] * 6 + [dp] * 12
+    L.tdsemu_steps_tile_bytes.restype = ctypes.c_long
+    assert 0 < L.tdsemu_steps_tile_bytes(1, 0) <= 227 * 1024        # the mixed instance of this robot fits a CTA's shared memory
+    rs = ref.RefSim.from_model(model)
+    params = dict(dt=1e-3, friction=0.9, keep_all_points=bool(seed % 3 == 0), pgs_iterations=1 + seed % 2)
+    rs.set_params(**params)
+    n, nq = 24, rs.n_q
+    q = np.zeros((n, nq))
+    q[:, 0:2], q[:, 2], q[:, 3:6], q[:, 6:] = rng.uniform(-0.3, 0.3, (n, 2)), rng.uniform(0.05, 0.6, n), rng.uniform(-0.6, 0.6, (n, 3)), rng.uniform(-1, 1, (n, nq - 6))
+    qd, tau = rng.uniform(-1, 1, (n, nq)), rng.uniform(-3, 3, (n, nq))
+    q, qd, tau = (a.astype(np.float32).astype(np.float64) for a in (q, qd, tau))
+    pv = np.array([params["dt"], 0.0, 0.0, -9.81, params["friction"], 0.0, 0.2, 1e-5, params["pgs_iterations"], int(params["keep_all_points"])])
+    penetrating = 0
+    for precision, tol in ((1, TOL), (0, 1e-4)):
+        for mode in (0, 1, 2):
+            oq, oqd, oqdd = np.zeros((n, nq)), np.zeros((n, nq)), np.zeros((n, nq))
+            rc = L.tdsemu_steps(1, emu._dp(pv), None, precision, 0, mode, 0, 0, n, emu._dp(q), emu._dp(qd), emu._dp(tau), emu._dp(oq), emu._dp(oqd),
+                                emu._dp(oqdd), None, None, None, None, None, None)
+            assert rc >= 0
+            for i in range(n):
+                r = rs.step(mode, q[i], qd[i], tau[i])
+                if mode == 0:
+                    assert rel_err(oqdd[i], r["qdd"]) <= tol
+                else:
+                    assert rel_err(oq[i], r["q"]) <= tol and rel_err(oqd[i], r["qd"]) <= tol
+                if mode == 2 and precision == 1:
+                    penetrating += int(np.sum(r["contact_data"][:, 9] < 0))
+    assert penetrating >= 20
