@@ -1,13 +1,13 @@
 """"additionally report agreement vs the fp32 oracle build".  The reference compiled in place on
 TinyAlgebra<float, FloatUtils> (oracle/_ref, prec=32) against its own fp64 build, next to the kernel sources (host-compiled,
 tests/cpp) in their mixed arithmetic - same golden inputs, one step.  CPU only.
-    python scripts/fp32_reference_report.py > profiles/r02_fp32_reference_agreement.txt"""
+    python tests/reports/fp32_reference_report.py > profiles/r02_fp32_reference_agreement.txt"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import emu  # noqa: E402

@@ -1,12 +1,12 @@
 """Evidence for profiles/: errors of the kernel SOURCES executed on the CPU (tests/cpp/*_host.cpp) against the reference's golden
 vectors - the specialised step kernel, the generic world-frame kernel (incl. worlds of several multibodies) and the rigid-body
-world kernel.  No GPU involved; says so in its header.    python scripts/host_kernel_report.py > profiles/r02_host_compiled_kernels.txt"""
+world kernel.  No GPU involved; says so in its header.    python tests/reports/host_kernel_report.py > profiles/r02_host_compiled_kernels.txt"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import emu  # noqa: E402
