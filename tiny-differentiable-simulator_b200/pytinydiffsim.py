@@ -41,7 +41,7 @@ class TinyWorld:
         self.gravity = (0.0, 0.0, -9.81)
         self.friction = 0.5               # World::default_friction, src/world.hpp:68
         self.restitution = 0.0
-        self.num_solver_iterations = 50
+        self.num_solver_iterations = 1    # World::num_solver_iterations, src/world.hpp:65 (sweeps of the rigid-body solver; the multibody LCP does not use it)
         self.pgs_iterations, self.erp, self.cfm, self.keep_all_points = 1, 0.2, 1e-5, False   # mb_constraint_solver.hpp:59-70
         self._plane = None                # URDF of the static plane body (created first, like the locomotion envs do)
         self._bodies = []
