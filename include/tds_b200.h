@@ -164,6 +164,10 @@ int tds_b200_step_host(tds_b200_sim* sim, int mode, int use_pd, const double* q,
  * point).  tds_b200_contact_list_candidates_host: cand [n][n_points] = index into the candidate list of the k-th kept point. */
 int tds_b200_contact_pairs(const tds_b200_sim* sim, int* tuples, int cap);
 int tds_b200_model_contact_pairs(const double* model, int n_model, int* tuples, int cap);   /* host-only, from a flat model */
+/* (mb_a, link_a, geom_a, mb_b, link_b, geom_b) per candidate = the loop indices of world.hpp:212-240 at which the point is emitted
+ * (geom: index in collision_geometries(link)); 6 ints per candidate, same order as tds_b200_contact_pairs */
+int tds_b200_contact_tuples(const tds_b200_sim* sim, int* tuples, int cap);
+int tds_b200_model_contact_tuples(const double* model, int n_model, int* tuples, int cap);   /* host-only */
 int tds_b200_contact_list_device(tds_b200_sim* sim, const float* contact_dist, int* count, int* links, void* stream);
 int tds_b200_contact_list_host(tds_b200_sim* sim, int* count, int* links);
 int tds_b200_contact_list_candidates_host(tds_b200_sim* sim, int* count, int* cand);

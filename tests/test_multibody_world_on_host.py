@@ -221,3 +221,57 @@ def test_random_worlds_of_multibodies_vs_live_reference(seed):
         assert rel_err(out["q"][i], r["q"]) <= TOL and rel_err(out["qd"][i], r["qd"]) <= TOL
         pair_hits += int(np.any((r["contact_idx"][:, 0] >= len(bodies)) & (r["contact_data"][:, 9] < 0)))
     assert pair_hits >= 1   # contacts between multibodies do occur in the sample
+
+
+def _enumerate_like_the_reference(model):
+    """Independent restatement of the loops of World::compute_contacts_multi_body_internal (src/world.hpp:212-281) with the plane as
+    multibody 0 and the dispatcher's point counts: (mb_a, link_a, geom_a, mb_b, link_b, geom_b) per emitted point."""
+    m = np.asarray(model)
+    n_links, n_geoms, has_plane, k = int(m[1]), int(m[5]), int(m[7]), max(int(m[12]), 1)
+    L = m[16 + 13:16 + 13 + n_links * 34].reshape(n_links, 34)
+    G = m[16 + 13 + n_links * 34:16 + 13 + n_links * 34 + n_geoms * 18].reshape(n_geoms, 18)
+    body_of, first = [], {}
+    for i in range(n_links):
+        b = (len(first) if int(L[i, 0]) < 0 else body_of[int(L[i, 0])]) if k > 1 else 0
+        first.setdefault(b, i)
+        body_of.append(b)
+    bodies = []      # per multibody: list of (local link, [(geom index in link, type)])
+    for b in range(k):
+        links = [(-1, [(gi, int(g[1])) for gi, g in enumerate(G[G[:, 0] < 0])] if (b == 0 and k == 1) else [])]
+        for i in range(n_links):
+            if body_of[i] == b:
+                gs = G[G[:, 0] == i]
+                links.append((i - first[b], [(gi, int(g[1])) for gi, g in enumerate(gs)]))
+        bodies.append(links)
+    world = ([[(-1, [(0, 1)])]] if has_plane else []) + bodies     # the plane: one PLANE geom on its base
+    off = 0 if has_plane else 1
+    pts = {(1, 0): 1, (1, 2): 2, (1, 4): 8, (0, 0): 1, (2, 0): 2}   # [type a][type b] -> points (contact_point.hpp:468-473)
+    out = []
+    for i in range(len(world)):
+        for j in range(i + 1, len(world)):
+            for la, ga in world[i]:
+                for gia, ta in ga:
+                    for lb, gb in world[j]:
+                        for gib, tb in gb:
+                            n = pts.get((ta, tb), pts.get((tb, ta), 0))
+                            out += [[i + off, la, gia, j + off, lb, gib]] * n
+    return np.array(out, dtype=np.int32).reshape(-1, 6)
+
+
+@pytest.mark.parametrize("name", ["sphere2", "laikago", "humanoid", "ant", "box", "cartpole_plane", "humanoid_spherical"] + ["mb_" + k for k in wl.MULTIBODY_WORLDS])
+def test_contact_tuples_with_geometry_indices(name):
+    """(mb_a, link_a, geom_a, mb_b, link_b, geom_b) per candidate through the C-ABI (host-only call) against an independent
+    enumeration of the reference's loops; the first, second, fourth and fifth columns are also what the goldens pin."""
+    import ctypes
+    from tds_b200 import _lib
+    from tds_b200.model import fixture_path, load_model
+    model = np.load(os.path.join(GOLDEN, name + ".npz"))["model"] if name.startswith("mb_") else load_model(fixture_path(name))
+    m = np.ascontiguousarray(model, dtype=np.float64)
+    L = _lib.lib()
+    t6 = np.zeros((128, 6), dtype=np.int32)
+    k = L.tds_b200_model_contact_tuples(ctypes.c_void_p(m.ctypes.data), m.size, ctypes.c_void_p(t6.ctypes.data), 128)
+    want = _enumerate_like_the_reference(m)
+    assert k == want.shape[0] and k > 0 and np.array_equal(t6[:k], want)
+    t4 = np.zeros((128, 4), dtype=np.int32)
+    assert L.tds_b200_model_contact_pairs(m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), m.size, ctypes.c_void_p(t4.ctypes.data), 128) == k
+    assert np.array_equal(t4[:k], t6[:k][:, [0, 1, 3, 4]])

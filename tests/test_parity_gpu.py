@@ -885,6 +885,7 @@ def test_multibody_world_golden_vectors(kind, precision, golden_dir):
         want = np.array([[lists[l][0], a, lists[l][1], b] for l, a, b in rows], dtype=np.int32).reshape(-1, 4)
         assert np.array_equal(pairs, want)
     k = pairs.shape[0]
+    assert np.array_equal(sim.contact_tuples()[:, [0, 1, 3, 4]], pairs)   # (the six-index form adds the geom index inside each link)
     ref_d = g["contact_data"][:, :k, 9]
     assert out["contact_dist"].shape == ref_d.shape and np.max(np.abs(out["contact_dist"] - ref_d)) < 2e-6
     # the list the constraint solver keeps (distance < 0), as candidate indices and as (link_a, link_b)

@@ -40,6 +40,7 @@ struct ContactCandTable {
   int n_points;
   signed char link_a[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS], link_b[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS];   // link index inside its multibody
   signed char body_a[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS], body_b[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS];   // multibody of the world (0 = the plane)
+  signed char geom_a[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS], geom_b[TDS_MAX_POINTS + TDS_MAX_PAIR_POINTS];   // index in collision_geometries(link)
 };
 
 // Candidate points of a model in the reference's enumeration order (World::compute_contacts_multi_body_internal,
@@ -51,12 +52,13 @@ static ContactCandTable make_cand_table(const DevModel& D) {
   int first[TDS_MAX_LINKS + 1];   // first link of every multibody
   for (int i = 0, b = -1; i < D.n_links; ++i) if (D.body_of[i] != b) { b = D.body_of[i]; first[b] = i; }
   auto local = [&](int link) { return link < 0 ? -1 : link - first[D.body_of[link]]; };
+  auto geom_in_link = [&](int g) { return g - D.geom_begin[D.g_link[g] + 1]; };   // iii / jjj of the reference's loops
   int c = 0;
   if (D.has_plane)
     for (int g = 0; g < D.n_geoms; ++g) {
       const int pts = D.g_type[g] == TDSG_SPHERE ? 1 : (D.g_type[g] == TDSG_CAPSULE ? 2 : (D.g_type[g] == TDSG_BOX ? 8 : 0));
       for (int j = 0; j < pts; ++j, ++c) {
-        T.body_a[c] = 0; T.link_a[c] = -1;
+        T.body_a[c] = 0; T.link_a[c] = -1; T.geom_a[c] = 0; T.geom_b[c] = (signed char)geom_in_link(g);
         T.body_b[c] = (signed char)(1 + (D.g_link[g] < 0 ? 0 : D.body_of[D.g_link[g]])); T.link_b[c] = (signed char)local(D.g_link[g]);
       }
     }
@@ -64,6 +66,7 @@ static ContactCandTable make_cand_table(const DevModel& D) {
     const int la = D.g_link[D.pp_ga[p]], lb = D.g_link[D.pp_gb[p]];
     T.body_a[c] = (signed char)(1 + D.body_of[la]); T.link_a[c] = (signed char)local(la);
     T.body_b[c] = (signed char)(1 + D.body_of[lb]); T.link_b[c] = (signed char)local(lb);
+    T.geom_a[c] = (signed char)geom_in_link(D.pp_ga[p]); T.geom_b[c] = (signed char)geom_in_link(D.pp_gb[p]);
   }
   T.n_points = c;
   return T;
@@ -916,6 +919,32 @@ static int write_tuples(const ContactCandTable& T, int* tuples, int cap) {
     tuples[4 * c + 2] = T.body_b[c]; tuples[4 * c + 3] = T.link_b[c];
   }
   return T.n_points;
+}
+
+static int write_tuples6(const ContactCandTable& T, int* tuples, int cap) {
+  for (int c = 0; c < T.n_points && c < cap && tuples; ++c) {
+    tuples[6 * c + 0] = T.body_a[c]; tuples[6 * c + 1] = T.link_a[c]; tuples[6 * c + 2] = T.geom_a[c];
+    tuples[6 * c + 3] = T.body_b[c]; tuples[6 * c + 4] = T.link_b[c]; tuples[6 * c + 5] = T.geom_b[c];
+  }
+  return T.n_points;
+}
+
+// (mb_a, link_a, geom_a, mb_b, link_b, geom_b) per candidate: the loop indices i, ii, iii, j, jj, jjj of
+// World::compute_contacts_multi_body_internal (src/world.hpp:212-240) at which the point is emitted.
+int tds_b200_model_contact_tuples(const double* model, int n_model, int* tuples, int cap) {
+  if (!model) { set_err("null model"); return -1; }
+  DevModel* D = new DevModel;
+  const int rc = tds_build_dev_model(model, n_model, D);
+  ContactCandTable T;
+  if (rc == 0) T = make_cand_table(*D);
+  delete D;
+  if (rc) { set_err(std::string("unsupported model: ") + tds_model_error(rc)); return rc; }
+  return write_tuples6(T, tuples, cap);
+}
+
+int tds_b200_contact_tuples(const tds_b200_sim* s, int* tuples, int cap) {
+  if (!s) return -1;
+  return write_tuples6(s->cand, tuples, cap);
 }
 
 // Host-only variant (no GPU needed): the candidate list of a flat model.

@@ -188,6 +188,13 @@ class BatchSim:
         k = self._L.tds_b200_contact_pairs(self._h, ctypes.c_void_p(t.ctypes.data), t.shape[0])
         return t[:k]
 
+    def contact_tuples(self):
+        """(mb_a, link_a, geom_a, mb_b, link_b, geom_b) of every candidate contact point (geom: index among the link's collision
+        shapes): the loop indices of World::compute_contacts_multi_body_internal at which the point is emitted."""
+        t = np.zeros((max(self.n_contact_points, 1), 6), dtype=np.int32)
+        k = self._L.tds_b200_contact_tuples(self._h, ctypes.c_void_p(t.ctypes.data), t.shape[0])
+        return t[:k]
+
     # ---- resident environment state ----
     def env_set_state(self, q, qd):
         q = np.ascontiguousarray(q, dtype=np.float64)
