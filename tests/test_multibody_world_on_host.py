@@ -275,3 +275,29 @@ def test_contact_tuples_with_geometry_indices(name):
     t4 = np.zeros((128, 4), dtype=np.int32)
     assert L.tds_b200_model_contact_pairs(m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), m.size, ctypes.c_void_p(t4.ctypes.data), 128) == k
     assert np.array_equal(t4[:k], t6[:k][:, [0, 1, 3, 4]])
+
+
+def test_rollout_of_a_world_of_multibodies_tracks_the_reference():
+    """80 chained steps of two free bodies on xyz + spherical joints (no Euler-angle singularity to run into: with the x-y-z revolute
+    emulation a body tumbling through pitch = 90 degrees makes the reference's own mass matrix singular and its velocities explode -
+    which the kernel reproduces digit for digit, but is no test), falling onto the plane and onto each other; state carried in fp32
+    between steps as on the device: per-step error against the reference stepping from the kernel's own previous state."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    n, steps = 6, 80
+    w = wl.multibody_world("spherical_pair", n, seed=12)
+    params = dict(w["params"], dt=2e-3)
+    rw = ref.RefWorld(w["model"])
+    rw.set_params(**params)
+    q, qd = w["q"], 0.2 * w["qd"]
+    worst, pair_steps = 0.0, 0
+    for s in range(steps):
+        q32, qd32 = wl._f32(q), wl._f32(qd)
+        out = emu.step(w["model"], 2, q32, qd32, None, precision=1, **params)
+        for i in range(n):
+            r = rw.step(2, q32[i], qd32[i], None, contact_cap=128)
+            worst = max(worst, rel_err(out["q"][i], r["q"]), rel_err(out["qd"][i], r["qd"]))
+            pair_steps += int(np.any((r["contact_idx"][:, 0] >= 2) & (r["contact_data"][:, 9] < 0)))
+        q, qd = out["q"], out["qd"]
+    assert worst <= TOL and np.all(np.isfinite(q)) and np.max(np.abs(qd)) < 100.0 and pair_steps >= 20
