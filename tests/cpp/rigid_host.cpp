@@ -28,7 +28,7 @@ extern "C" {
 int tdsemu_rigid(const double* desc, int nb, const double* params, int n, const double* state, const double* force, int steps,
                  double* state_out, double* jac) {
   RigidWorld W;
-  if (tds_rigid_world_from_desc(desc, nb, &W)) return -1;
+  { const int rcw = tds_rigid_world_from_desc(desc, nb, &W); if (rcw) return rcw; }   // as tds_b200_rigid_create refuses
   W.dt = params[0]; for (int k = 0; k < 3; ++k) W.gravity[k] = params[1 + k];
   W.friction = params[4]; W.restitution = params[5]; W.erp = params[6]; W.num_solver_iterations = (int)params[7];
   const int ns = (n + 31) & ~31, rows = 13 * nb, cols = 16 * nb;

@@ -30,7 +30,7 @@ struct RigidWorld {                       // constant for all worlds of a batch 
 };
 
 // desc [n_bodies][6] = mass, shape (TDSG_*), p0..p3 -> RigidWorld (host).  The plane normal is normalised like Plane's constructor
-// does (src/geometry.hpp:163-168).  Returns 0, or -1 on an unknown shape.
+// does (src/geometry.hpp:163-168).  Returns 0, -1 on an unknown shape, -2 when the contact list could overflow.
 static inline int tds_rigid_world_from_desc(const double* desc, int n_bodies, RigidWorld* W) {
   memset(W, 0, sizeof(*W));
   W->n_bodies = n_bodies;
@@ -45,6 +45,16 @@ static inline int tds_rigid_world_from_desc(const double* desc, int n_bodies, Ri
       for (int k = 0; k < 3; ++k) W->p[i][k] = d[2 + k] / l;
     }
   }
+  // worst case of the contact list (every pair at the point count of its contact function): the kernel's list is fixed-size
+  int worst = 0;
+  for (int i = 0; i < n_bodies; ++i)
+    for (int j = i + 1; j < n_bodies; ++j) {
+      auto pts = [](int a, int b) { return (a == TDSG_SPHERE && b == TDSG_SPHERE) ? 1 : (a == TDSG_PLANE && b == TDSG_SPHERE) ? 1 : (a == TDSG_PLANE && b == TDSG_CAPSULE) ? 2
+                                    : (a == TDSG_PLANE && b == TDSG_BOX) ? 8 : (a == TDSG_CAPSULE && b == TDSG_SPHERE) ? 2 : 0; };
+      const int t = W->type[i], u = W->type[j];
+      worst += pts(t, u) ? pts(t, u) : pts(u, t);
+    }
+  if (worst > TDS_RIGID_MAX_CONTACTS) return -2;
   // World defaults (world.hpp:65-72), RigidBodyConstraintSolver::erp_ (rb_constraint_solver.hpp:45)
   W->dt = 1.0 / 60.0; W->gravity[2] = -9.81; W->friction = 0.5; W->restitution = 0.0; W->erp = 0.1; W->num_solver_iterations = 1;
   return 0;
@@ -242,22 +252,13 @@ extern "C" {
 // desc: [n_bodies][6] = mass, shape (TDSG_*), p0, p1, p2, p3 (see RigidWorld::p).  NULL on a refused description / no GPU.
 tds_b200_rigid* tds_b200_rigid_create(const double* desc, int n_bodies, int n_worlds, int device) {
   if (!desc || n_bodies < 1 || n_bodies > TDS_RIGID_MAX_BODIES || n_worlds < 1) { tds_b200_set_error("rigid world: 1..16 bodies, >= 1 world"); return nullptr; }
-  // worst case of the contact list: every pair at its largest point count
-  int worst = 0;
-  for (int i = 0; i < n_bodies; ++i) {
-    const int t = (int)desc[i * 6 + 1];
-    if (t != TDSG_SPHERE && t != TDSG_PLANE && t != TDSG_CAPSULE && t != TDSG_BOX) { tds_b200_set_error("rigid world: shapes are sphere, plane, capsule, box"); return nullptr; }
-    for (int j = i + 1; j < n_bodies; ++j) {
-      const int u = (int)desc[j * 6 + 1];
-      auto pts = [](int a, int b) { return (a == TDSG_SPHERE && b == TDSG_SPHERE) ? 1 : (a == TDSG_PLANE && b == TDSG_SPHERE) ? 1 : (a == TDSG_PLANE && b == TDSG_CAPSULE) ? 2
-                                    : (a == TDSG_PLANE && b == TDSG_BOX) ? 8 : (a == TDSG_CAPSULE && b == TDSG_SPHERE) ? 2 : 0; };
-      worst += pts(t, u) ? pts(t, u) : pts(u, t);
-    }
-  }
-  if (worst > TDS_RIGID_MAX_CONTACTS) { tds_b200_set_error("rigid world: more than 48 candidate contact points"); return nullptr; }
+  RigidWorld W0;
+  const int rcw = tds_rigid_world_from_desc(desc, n_bodies, &W0);
+  if (rcw == -1) { tds_b200_set_error("rigid world: shapes are sphere, plane, capsule, box"); return nullptr; }
+  if (rcw == -2) { tds_b200_set_error("rigid world: more than 48 candidate contact points"); return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { tds_b200_set_error("cudaSetDevice failed"); return nullptr; }
   tds_b200_rigid* h = new tds_b200_rigid;
-  tds_rigid_world_from_desc(desc, n_bodies, &h->W);
+  h->W = W0;
   h->n = n_worlds; h->ns = (n_worlds + 31) & ~31; h->device = device;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void**)&h->state, sizeof(double) * 13 * n_bodies * h->ns) != cudaSuccess ||
