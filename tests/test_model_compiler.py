@@ -133,7 +133,7 @@ def test_committed_spec_headers_are_what_gen_spec_emits(name, inc, n_act, tmp_pa
     assert open(out).read() == open(committed).read()
 
 
-def _random_urdf(rng, n_links, massless_links=True, boxes=True):
+def _random_urdf(rng, n_links, massless_links=True, boxes=True, extras=False):
     """A random tree of links: every joint type the step supports, unit / negative / oblique axes, joint and inertial
     origins with rotations, sphere / capsule / box collision shapes with their own origins, link visuals."""
     def v3(lo, hi):
@@ -151,6 +151,9 @@ def _random_urdf(rng, n_links, massless_links=True, boxes=True):
             geo = (f'<sphere radius="{rng.uniform(0.02, 0.2):.6g}"/>' if kind == 0 else
                    f'<capsule radius="{rng.uniform(0.02, 0.1):.6g}" length="{rng.uniform(0.1, 0.6):.6g}"/>' if kind == 1 else
                    f'<box size="{v3(0.05, 0.4)}"/>')
+            if extras and rng.random() < 0.3:    # shapes the reference's loader drops (urdf_to_multi_body.hpp:234-277)
+                geo = ('<mesh filename="part.obj" scale="1 1 1"/>' if rng.random() < 0.5 else
+                       f'<cylinder radius="{rng.uniform(0.02, 0.1):.6g}" length="{rng.uniform(0.1, 0.6):.6g}"/>')
             s.append(f'<collision><origin xyz="{v3(-0.3, 0.3)}" rpy="{v3(-1.5, 1.5)}"/><geometry>{geo}</geometry></collision>')
         if rng.random() < 0.6:
             s.append(f'<visual><origin xyz="{v3(-0.1, 0.1)}" rpy="{v3(-1, 1)}"/><geometry><sphere radius="0.1"/></geometry></visual>')
@@ -162,6 +165,8 @@ def _random_urdf(rng, n_links, massless_links=True, boxes=True):
     for i in order:
         parent = int(rng.integers(0, i))
         jt = ["revolute", "continuous", "prismatic", "fixed"][rng.integers(0, 4)]
+        if extras and rng.random() < 0.2:
+            jt = "spherical"
         ax = axes[rng.integers(0, len(axes))]
         axis = f'<axis xyz="{ax}"/>' if (ax is not None and jt != "fixed") else ""
         lim = '<limit lower="-1" upper="1" effort="10" velocity="10"/>' if jt in ("revolute", "prismatic") else ""
@@ -187,5 +192,23 @@ def test_random_urdfs_match_reference_loader(seed, tmp_path):
     plane = os.path.join(REFERENCE_ROOT, "data", "plane_implicit.urdf") if seed % 3 else None
     theirs = ref.RefSim.from_urdf(str(path), plane, floating).export_model()
     mine = compile_urdf(str(path), plane, floating)
+    assert mine.shape == theirs.shape, text
+    assert np.abs(mine - theirs).max() < 1e-14, text
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_urdfs_with_spherical_joints_and_dropped_shapes_match_reference_loader(seed, tmp_path):
+    """As above with spherical joints (4 coordinates / 3 velocities in the index bookkeeping) and the collision shapes the
+    reference's loader silently drops (mesh, cylinder); own plane URDF, so the test needs oracle/_ref only."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(2500 + seed)
+    text = _random_urdf(rng, int(rng.integers(2, 12)), extras=True)
+    path = tmp_path / "rnd.urdf"
+    path.write_text(text)
+    plane = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "urdf", "plane.urdf") if seed % 3 else None
+    theirs = ref.RefSim.from_urdf(str(path), plane, False).export_model()
+    mine = compile_urdf(str(path), plane, False)
     assert mine.shape == theirs.shape, text
     assert np.abs(mine - theirs).max() < 1e-14, text
