@@ -853,7 +853,7 @@ def test_vectorized_env_auto_reset_settles_and_sticky_done():
     env.sim.env_set_state(q, qd)
     second = env.step(np.zeros((n, 12)))
     assert np.array_equal(first.dones > 0, np.arange(n) < 3) and np.array_equal(second.dones > 0, np.arange(n) < 3)
-    assert np.all(second.rewards[:3] == 0) and np.all(second.rewards[3:] != 0)
+    assert np.all(second.rewards[:3] == 0) and np.array_equal(second.rewards[3:] != 0, first.rewards[3:] != 0)
 
 
 @pytest.mark.parametrize("name,cls,n_rec", [("laikago", "VectorizedLaikagoEnv", 17), ("ant", "VectorizedAntEnv", 9)])
