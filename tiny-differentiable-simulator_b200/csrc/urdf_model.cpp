@@ -8,7 +8,8 @@
 // including its quirks (SURVEY.md section 8 "parity traps" 11): only ixx/iyy/izz are read, the inertial
 // rpy rotates both the inertia and the com by R^T, axes equal to exactly +1 become *_X/Y/Z joints,
 // a missing <axis> defaults to (0,0,1), joint damping/stiffness are not transferred, mesh / cylinder
-// collision shapes are dropped, the plane constant is 0.
+// collision shapes are dropped, the plane constant is 0.  Deviation: a <plane> collision shape on a link of the robot itself is
+// dropped here while the reference keeps it (it could only meet the shapes of another multibody).
 // Own minimal XML reader (no third-party parser): elements, attributes, comments, declarations.
 #include <math.h>
 #include <stdio.h>
