@@ -96,6 +96,12 @@ struct RefSim {
           case TINY_BOX_TYPE:
             geom = world.create_box(Vector3(Scalar(gg[TDSM_G_P]), Scalar(gg[TDSM_G_P + 1]), Scalar(gg[TDSM_G_P + 2])));
             break;
+          case TINY_PLANE_TYPE: {   // a plane shape on a link (urdf_to_multi_body.hpp:264-270)
+            Plane<A>* pl = world.create_plane();
+            pl->set_normal(Vector3(Scalar(gg[TDSM_G_P]), Scalar(gg[TDSM_G_P + 1]), Scalar(gg[TDSM_G_P + 2])));
+            geom = pl;
+            break;
+          }
           default: continue;
         }
         geoms.push_back(geom);
@@ -154,6 +160,11 @@ struct RefSim {
           case TINY_BOX_TYPE: {
             auto e = ((const Box<A>*)gs[g])->get_extents();
             rec[TDSM_G_P] = (double)e[0]; rec[TDSM_G_P + 1] = (double)e[1]; rec[TDSM_G_P + 2] = (double)e[2];
+            break;
+          }
+          case TINY_PLANE_TYPE: {
+            auto nn = ((const Plane<A>*)gs[g])->get_normal();
+            rec[TDSM_G_P] = (double)nn[0]; rec[TDSM_G_P + 1] = (double)nn[1]; rec[TDSM_G_P + 2] = (double)nn[2];
             break;
           }
           default: break;

@@ -86,6 +86,12 @@ struct RefWorld {
           case TINY_SPHERE_TYPE: geom = world.create_sphere(gg[TDSM_G_P]); break;
           case TINY_CAPSULE_TYPE: geom = world.create_capsule(gg[TDSM_G_P], gg[TDSM_G_P + 1]); break;
           case TINY_BOX_TYPE: geom = world.create_box(Vector3(gg[TDSM_G_P], gg[TDSM_G_P + 1], gg[TDSM_G_P + 2])); break;
+          case TINY_PLANE_TYPE: {
+            Plane<A>* pl = world.create_plane();
+            pl->set_normal(Vector3(gg[TDSM_G_P], gg[TDSM_G_P + 1], gg[TDSM_G_P + 2]));
+            geom = pl;
+            break;
+          }
           default: continue;
         }
         link.collision_geometries.push_back(geom);

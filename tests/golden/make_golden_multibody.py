@@ -1,7 +1,7 @@
 """Golden fixtures for worlds of several multibodies (contacts between multibodies, src/world.hpp:206-282; one LCP per list of
 World::mb_contacts_, :351-355) from the UNMODIFIED reference compiled in place (oracle/_ref/libtds_ref.so, oracle/ref/ref_world.cpp).
 
-    python tests/golden/make_golden_multibody.py
+    python tests/golden/make_golden_multibody.py [world ...]
 
 Writes tests/golden/mb_<world>.npz: the merged flat model (tds_b200.workloads.multibody_world_model), seeded inputs and the
 reference's (fp64) outputs of one full step and of World::step alone, with the contact lists of the step.
@@ -22,7 +22,7 @@ CAP = 32
 
 
 def main():
-    for kind in wl.MULTIBODY_WORLDS:
+    for kind in (sys.argv[1:] or wl.MULTIBODY_WORLDS):      # optionally only the named worlds
         w = wl.multibody_world(kind, N)
         rw = ref.RefWorld(w["model"])
         rw.set_params(**w["params"])

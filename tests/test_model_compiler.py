@@ -151,7 +151,9 @@ def _random_urdf(rng, n_links, massless_links=True, boxes=True, extras=False):
             geo = (f'<sphere radius="{rng.uniform(0.02, 0.2):.6g}"/>' if kind == 0 else
                    f'<capsule radius="{rng.uniform(0.02, 0.1):.6g}" length="{rng.uniform(0.1, 0.6):.6g}"/>' if kind == 1 else
                    f'<box size="{v3(0.05, 0.4)}"/>')
-            if extras and rng.random() < 0.3:    # shapes the reference's loader drops (urdf_to_multi_body.hpp:234-277)
+            if extras and rng.random() < 0.15:   # a plane shape on a link: kept, with its normal normalised (geometry.hpp:183)
+                geo = f'<plane normal="{v3(-1, 1)}"/>'
+            elif extras and rng.random() < 0.3:  # shapes the reference's loader drops (urdf_to_multi_body.hpp:234-277)
                 geo = ('<mesh filename="part.obj" scale="1 1 1"/>' if rng.random() < 0.5 else
                        f'<cylinder radius="{rng.uniform(0.02, 0.1):.6g}" length="{rng.uniform(0.1, 0.6):.6g}"/>')
             s.append(f'<collision><origin xyz="{v3(-0.3, 0.3)}" rpy="{v3(-1.5, 1.5)}"/><geometry>{geo}</geometry></collision>')

@@ -163,7 +163,10 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
     // the contact stage implements plane x {sphere, capsule, box}.  The reference has no mesh COLLISION shapes at all
     // (TINY_MESH_TYPE is "only for visual shapes", src/geometry.hpp:34; its URDF loader drops them, urdf_to_multi_body.hpp:234-277,
     // and so does ours): a flat model carrying one is malformed rather than something to simulate - refuse it
-    if (D->has_plane && D->g_type[g] != TDSG_SPHERE && D->g_type[g] != TDSG_CAPSULE && D->g_type[g] != TDSG_BOX) return -6;
+    // (a PLANE shape on a link of the robot is legal: it has no contact function against the ground plane, only against the
+    // spheres / capsules / boxes of ANOTHER multibody; its unit normal travels in g_half)
+    if (D->g_type[g] == TDSG_PLANE) { for (int k = 0; k < 3; ++k) D->g_half[g][k] = gg[TDSM_G_P + k]; }
+    else if (D->has_plane && D->g_type[g] != TDSG_SPHERE && D->g_type[g] != TDSG_CAPSULE && D->g_type[g] != TDSG_BOX) return -6;
   }
   if (D->has_plane && n_points > TDS_MAX_POINTS) return -2;
   D->max_contacts = D->has_plane ? n_points : 0;
@@ -203,10 +206,17 @@ TDS_HOST_INLINE int tds_build_dev_model(const double* m, int n_doubles, DevModel
               const int ta = D->g_type[ga], tb = D->g_type[gb];
               // CollisionDispatcher, src/contact_point.hpp:468-501: sphere x sphere, capsule x sphere, and sphere x capsule through
               // the swapped call; every other pair of shapes has no contact function
-              int kinds[2], nk = 0;
+              int kinds[8], nk = 0;
               if (ta == TDSG_SPHERE && tb == TDSG_SPHERE) { kinds[0] = 0; nk = 1; }
               else if (ta == TDSG_CAPSULE && tb == TDSG_SPHERE) { kinds[0] = 1; kinds[1] = -1; nk = 2; }
               else if (ta == TDSG_SPHERE && tb == TDSG_CAPSULE) { kinds[0] = 2; kinds[1] = -2; nk = 2; }
+              // a PLANE shape on a link (contact_plane_sphere / _capsule / _box, contact_point.hpp:97-198; the pose of the plane's
+              // link is not used): 100 + point on the other shape; 200 + point when the plane is on b (the dispatcher's swapped call)
+              else if (ta == TDSG_PLANE || tb == TDSG_PLANE) {
+                const int other = ta == TDSG_PLANE ? tb : ta, base = ta == TDSG_PLANE ? 100 : 200;
+                const int n_o = other == TDSG_SPHERE ? 1 : (other == TDSG_CAPSULE ? 2 : (other == TDSG_BOX ? 8 : 0));
+                for (int k = 0; k < n_o; ++k) kinds[nk++] = base + k;
+              }
               for (int k = 0; k < nk; ++k) {
                 if (np >= TDS_MAX_PAIR_POINTS) return -2;
                 D->pp_ga[np] = ga; D->pp_gb[np] = gb; D->pp_kind[np] = kinds[k]; ++np;
@@ -299,7 +309,7 @@ TDS_HOST_INLINE void tds_build_layout_w(DevModel* D, int size_ra, int size_rc, i
   w = even(w);
   D->x_con = w; w += D->max_contacts * 5 * rc;
   w = even(w);
-  D->x_gw = w; w += D->n_gw * 6 * rc;                       // world centre (+ capsule half axis) of the geoms of the pair stage
+  D->x_gw = w; w += D->n_gw * 12 * rc;                      // world centre + capsule half axis / the three box half axes, for the pair stage
   D->x_pcon = w; w += D->n_pair_points * 9 * rc;            // pair contacts: point on a [3], normal on b [3], distance, link a, link b
   w = even(w);
   D->x_M = w; w += (D->nb * (D->nb + 1) / 2) * 9 * rs;

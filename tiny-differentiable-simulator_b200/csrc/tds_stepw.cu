@@ -158,9 +158,15 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       const V3<RC> c = pr + mul(R, v3<RC>(RC(M.g_t[g][0]), RC(M.g_t[g][1]), RC(M.g_t[g][2])));
       const RC rad = RC(M.g_radius[g]);
       if (M.g_wslot[g] >= 0) {         // kept for the contacts between multibodies (after this pass)
-        RC* pw = A.ptr<RC>(M.x_gw + M.g_wslot[g] * 6 * RCW);
+        RC* pw = A.ptr<RC>(M.x_gw + M.g_wslot[g] * 12 * RCW);
         st3<RC>(pw, ST, c);
         if (ty == TDSG_CAPSULE) st3<RC>(pw + 3 * ST, ST, mul(R, v3<RC>(RC(M.g_half[g][0]), RC(M.g_half[g][1]), RC(M.g_half[g][2]))));
+        if (ty == TDSG_BOX) {
+          const double* b = M.g_box[g];
+          st3<RC>(pw + 3 * ST, ST, mul(R, v3<RC>(RC(b[0]), RC(b[1]), RC(b[2]))));
+          st3<RC>(pw + 6 * ST, ST, mul(R, v3<RC>(RC(b[3]), RC(b[4]), RC(b[5]))));
+          st3<RC>(pw + 9 * ST, ST, mul(R, v3<RC>(RC(b[6]), RC(b[7]), RC(b[8]))));
+        }
       }
       if (ty == TDSG_SPHERE) emit_point(li, c, rad);
       else if (ty == TDSG_CAPSULE) {   // contact_plane_capsule, contact_point.hpp:128-161: end spheres at +L/2, then -L/2
@@ -307,8 +313,40 @@ tds_stepw_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Sim
       int cnt = 0;
       for (int pt = M.pg_begin[g]; pt < M.pg_begin[g + 1]; ++pt) {
         const int ga = M.pp_ga[pt], gb = M.pp_gb[pt], kind = M.pp_kind[pt];
-        const RC* wa = A.ptr<RC>(M.x_gw + M.g_wslot[ga] * 6 * RCW);
-        const RC* wb = A.ptr<RC>(M.x_gw + M.g_wslot[gb] * 6 * RCW);
+        const RC* wa = A.ptr<RC>(M.x_gw + M.g_wslot[ga] * 12 * RCW);
+        const RC* wb = A.ptr<RC>(M.x_gw + M.g_wslot[gb] * 12 * RCW);
+        if (kind >= 100) {
+          // a PLANE shape on a link x point k of the other multibody's sphere / capsule / box: contact_plane_sphere
+          // (contact_point.hpp:97-124) on the sphere, the capsule's end spheres (+L/2, -L/2) or the box's corner spheres (x outermost);
+          // plane constant 0, world-frame normal as given - the pose of the plane's link is not used; a point is always emitted
+          const bool swapped = kind >= 200;                      // the plane is on b: points exchanged, normal negated (:478-492)
+          const int gp = swapped ? gb : ga, go = swapped ? ga : gb, k = kind - (swapped ? 200 : 100);
+          const RC* wo = swapped ? wa : wb;
+          const V3<RC> pnrm = v3<RC>(RC(M.g_half[gp][0]), RC(M.g_half[gp][1]), RC(M.g_half[gp][2]));
+          V3<RC> c = ld3<RC>(wo, ST);
+          const int to = M.g_type[go];
+          if (to == TDSG_CAPSULE) c = k == 0 ? c + ld3<RC>(wo + 3 * ST, ST) : c - ld3<RC>(wo + 3 * ST, ST);
+          else if (to == TDSG_BOX) {
+            const V3<RC> ex = ld3<RC>(wo + 3 * ST, ST), ey = ld3<RC>(wo + 6 * ST, ST), ez = ld3<RC>(wo + 9 * ST, ST);
+            c = (k & 4) ? c - ex : c + ex;
+            c = (k & 2) ? c - ey : c + ey;
+            c = (k & 1) ? c - ez : c + ez;
+          }
+          const RC rad = RC(M.g_radius[go]);
+          const RC t = dot(c + O, pnrm);                         // -(dot(position, -normal) + constant), constant = 0
+          const RC dist = t - rad;
+          if (io.contact_dist && live) io.contact_dist[(size_t)(pt_index + pt) * ns + e] = (float)val_of(dist);
+          if (dist < RC(0)) {
+            RC* pr = A.ptr<RC>(M.x_pcon + n_pair_active * 9 * RCW);
+            if (!swapped) { st3<RC>(pr, ST, c - pnrm * t); st3<RC>(pr + 3 * ST, ST, v3<RC>(-pnrm.x, -pnrm.y, -pnrm.z)); }   // point on the plane, normal on b = -n
+            else { st3<RC>(pr, ST, c - pnrm * rad); st3<RC>(pr + 3 * ST, ST, pnrm); }                                        // point on the sphere, normal = +n
+            pr[6 * ST] = dist;
+            pr[7 * ST] = RC(M.g_link[ga]);
+            pr[8 * ST] = RC(M.g_link[gb]);
+            ++n_pair_active; ++cnt;
+          }
+          continue;
+        }
         V3<RC> ca = ld3<RC>(wa, ST), cb = ld3<RC>(wb, ST);
         if (kind == 1) ca = ca + ld3<RC>(wa + 3 * ST, ST); else if (kind == -1) ca = ca - ld3<RC>(wa + 3 * ST, ST);
         if (kind == 2) cb = cb + ld3<RC>(wb + 3 * ST, ST); else if (kind == -2) cb = cb - ld3<RC>(wb + 3 * ST, ST);

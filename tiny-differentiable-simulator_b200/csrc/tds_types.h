@@ -59,7 +59,7 @@ struct DevModel {
   int g_link[TDS_MAX_GEOMS];
   int g_type[TDS_MAX_GEOMS];
   double g_t[TDS_MAX_GEOMS][3];     // local translation
-  double g_half[TDS_MAX_GEOMS][3];  // capsule: local half-axis R_local * (0,0,L/2)
+  double g_half[TDS_MAX_GEOMS][3];  // capsule: local half-axis R_local * (0,0,L/2); plane shape on a link: its unit normal
   double g_radius[TDS_MAX_GEOMS];
   double g_box[TDS_MAX_GEOMS][9];   // box: the three local half-axes R_local * diag(extent / 2 - r), columns x | y | z
   int n_sph;                        // spherical joints; S columns of the s-th one at x_S3 + s * 18 RC words
@@ -76,10 +76,11 @@ struct DevModel {
   int pg_begin[TDS_MAX_PAIR_GROUPS + 1]; // candidate points of group g: [pg_begin[g], pg_begin[g + 1]), groups in (a, b) lexicographic order
   int pp_ga[TDS_MAX_PAIR_POINTS];        // geom on the lower-indexed multibody (body A of the contact)
   int pp_gb[TDS_MAX_PAIR_POINTS];        // geom on the other one (body B)
-  int pp_kind[TDS_MAX_PAIR_POINTS];      // 0 sphere-sphere; +-1 capsule A (end +-L/2) x sphere B; +-2 sphere A x capsule B (dispatcher swap)
+  int pp_kind[TDS_MAX_PAIR_POINTS];      // 0 sphere-sphere; +-1 capsule A (end +-L/2) x sphere B; +-2 sphere A x capsule B (dispatcher swap);
+                                         // 100 + k: plane shape on A x point k of B's sphere / capsule / box; 200 + k: the plane on B (swap)
   int g_wslot[TDS_MAX_GEOMS];            // slot of the geom's world centre (+ capsule half axis) kept for the pair stage, -1: none
   int n_gw, max_pair_rows;               // slots; largest group (rows of the pair LCP)
-  int x_gw, x_pcon;                      // arena: [n_gw][6] RC, [n_pair_points][9] RC
+  int x_gw, x_pcon;                      // arena: [n_gw][12] RC, [n_pair_points][9] RC
   // static ground plane (multibody 0)
   double plane_n[3];
   double plane_c;

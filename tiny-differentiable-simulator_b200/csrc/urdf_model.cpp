@@ -8,8 +8,8 @@
 // including its quirks (SURVEY.md section 8 "parity traps" 11): only ixx/iyy/izz are read, the inertial
 // rpy rotates both the inertia and the com by R^T, axes equal to exactly +1 become *_X/Y/Z joints,
 // a missing <axis> defaults to (0,0,1), joint damping/stiffness are not transferred, mesh / cylinder
-// collision shapes are dropped, the plane constant is 0.  Deviation: a <plane> collision shape on a link of the robot itself is
-// dropped here while the reference keeps it (it could only meet the shapes of another multibody).
+// collision shapes are dropped, the plane constant is 0; a <plane> collision shape on a link of the robot itself is kept like any
+// other shape (record: P = unit normal) - it can only meet the shapes of another multibody.
 // Own minimal XML reader (no third-party parser): elements, attributes, comments, declarations.
 #include <math.h>
 #include <stdio.h>
@@ -365,11 +365,15 @@ extern "C" int tds_b200_urdf_to_model(const char* urdf, const char* plane_urdf, 
   std::vector<double> geoms, vis;
   auto add_shapes = [&](int link_index, const ULink& l) {
     for (auto& sh : l.collisions) {  // convert_collisions, urdf_to_multi_body.hpp:222-277
-      if (sh.type != TDSG_SPHERE && sh.type != TDSG_BOX && sh.type != TDSG_CAPSULE) continue;
+      if (sh.type != TDSG_SPHERE && sh.type != TDSG_BOX && sh.type != TDSG_CAPSULE && sh.type != TDSG_PLANE) continue;
       double rec[TDSM_GEOM] = {0};
       rec[TDSM_G_LINK] = link_index;
       rec[TDSM_G_TYPE] = sh.type;
       memcpy(rec + TDSM_G_P, sh.p, sizeof sh.p);
+      if (sh.type == TDSG_PLANE) {   // a plane shape on a link of the robot: Plane::set_normal normalises (geometry.hpp:183)
+        const double len = sqrt(sh.p[0] * sh.p[0] + sh.p[1] * sh.p[1] + sh.p[2] * sh.p[2]);
+        for (int k = 0; k < 3; ++k) rec[TDSM_G_P + k] = sh.p[k] * (1.0 / len);
+      }
       rpy_matrix(sh.rpy.v, rec + TDSM_G_R);
       memcpy(rec + TDSM_G_T, sh.xyz.v, sizeof sh.xyz.v);
       geoms.insert(geoms.end(), rec, rec + TDSM_GEOM);

@@ -180,6 +180,11 @@ def free_body_model(mass, inertia_diag, geoms, plane=True, arm=None, spherical=F
         r[0] = body
         if g[0] == "sphere":
             r[1], r[2], r[5:14], r[14:17] = 0, g[1], eye, g[2]
+        elif g[0] == "box":          # ("box", extents (x, y, z), offset[, R])
+            r[1], r[2:5], r[14:17] = 4, g[1], g[2]
+            r[5:14] = np.asarray(g[3], dtype=np.float64).ravel() if len(g) > 3 else eye
+        elif g[0] == "plane":        # ("plane", unit normal): a plane shape on the body link (the reference ignores the link's pose for it)
+            r[1], r[2:5], r[5:14] = 1, g[1], eye
         else:
             r[1], r[2], r[3], r[14:17] = 2, g[1], g[2], g[3]
             r[5:14] = np.asarray(g[4], dtype=np.float64).ravel() if len(g) > 4 else eye
@@ -203,7 +208,7 @@ def _rot_y(a):
     return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
 
 
-MULTIBODY_WORLDS = ("spheres2", "capsule_sphere", "sphere_capsule", "three_bodies", "spherical_pair")
+MULTIBODY_WORLDS = ("spheres2", "capsule_sphere", "sphere_capsule", "three_bodies", "spherical_pair", "racket", "racket_last")
 
 
 def multibody_world_model(kind):
@@ -224,6 +229,13 @@ def multibody_world_model(kind):
         a = free_body_model(1.0, (0.04, 0.05, 0.06), [("sphere", 0.3, (0.05, 0, 0))], spherical=True)
         b = free_body_model(2.0, (0.05, 0.05, 0.01), [("capsule", 0.15, 0.6, (0, 0, 0), _rot_y(0.2))], spherical=True)
         return merge_models([a, b])
+    if kind in ("racket", "racket_last"):
+        # a <plane> collision shape on a link of a multibody (the reference's data has one: franka_panda/panda_racket.urdf) against
+        # a ball, a capsule and a box of other multibodies; "racket_last": the plane's multibody comes last (dispatcher's swapped call)
+        racket = free_body_model(1.2, (0.05, 0.04, 0.03), [("plane", (0.0, 0.0, 1.0)), ("sphere", 0.1, (0.2, 0, 0))])
+        ball = sph(0.2, 0.4)
+        boxy = free_body_model(1.5, (0.05, 0.06, 0.07), [("box", (0.4, 0.3, 0.2), (0.02, 0, 0))])
+        return merge_models([racket, ball, cap(), boxy] if kind == "racket" else [ball, cap(), boxy, racket])
     raise ValueError(kind)
 
 
